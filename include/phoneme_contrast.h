@@ -1,0 +1,224 @@
+/*
+ * phoneme_contrast.h -- C ABI of libpc_b200.so, the B200 (sm_100a) implementation of the
+ * phoneme_contrast data-parallel training hot path.
+ *
+ * The reference (brant01/phoneme_contrast) is pure Python: it has no FFI. Its "plugin API" for this
+ * path is four Python seams; each group of entry points below states which
+ * reference interface it sits behind (paths relative to the reference repo). The Python host side
+ * (phoneme_contrast_b200/) mirrors those interfaces and calls these symbols through ctypes with raw
+ * device pointers -- no torch types cross this boundary. INTEGRATION.md shows the binding stubs.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are dense fp32; activations are NHWC ([B,H,W,C]); conv weights cross the ABI in the
+ *     reference's OIHW layout and are re-packed on the device by pc_pack_conv_weight;
+ *   - labels are int64 (torch.long), as trainer.py:189,197 produces them;
+ *   - every launcher is asynchronous on `stream` (the caller's current CUDA stream), allocates
+ *     nothing, and returns 0 on success or a negative PcStatus; pc_last_error() gives the text.
+ *     No exception crosses the ABI; the Python shim turns PC_EINVAL into the ValueError the reference
+ *     raises at the same place (losses.py:44-45, features.py:168, registry.py:18,27).
+ */
+#ifndef PHONEME_CONTRAST_H_
+#define PHONEME_CONTRAST_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* pc_stream_t;
+
+typedef enum PcStatus {
+  PC_OK = 0,
+  PC_EINVAL = -1,      /* bad shape / argument (maps to ValueError)            */
+  PC_EUNSUPPORTED = -2, /* configuration outside what the kernels cover         */
+  PC_ECUDA = -3        /* CUDA launch / runtime error (maps to RuntimeError)    */
+} PcStatus;
+
+const char* pc_last_error(void);
+int pc_abi_version(void);
+/* Number of kernels this library has launched since load (bench.py "gpu_launches"). */
+unsigned long long pc_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1. MFCC / log-mel front end + view augmentation
+ *    replaces: MFCCExtractor.forward            src/datasets/features.py:61-103
+ *              MelSpectrogramExtractor.forward  src/datasets/features.py:134-153
+ *              (torchaudio MFCC: _transforms.py:701-718, functional.py:123-144,390-405)
+ *              TimeMask/FrequencyMask/GaussianNoise/Compose  src/datasets/transforms.py:38-97,139-144
+ *              waveform gain                    src/datasets/dataset.py:165-167
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PcViewDesc {   /* one per output view; built on the host with the reference's RNG calls */
+  float gain;                 /* waveform gain (1.0 = none)                      dataset.py:165-167   */
+  int32_t t0, t1;             /* time-mask columns [t0,t1) zero-filled (0,0 = none)  transforms.py:45 */
+  int32_t f0, f1;             /* freq-mask rows    [f0,f1)                           transforms.py:69 */
+  float noise_level;          /* x + N(0,1)*level after the masks (0 = none)         transforms.py:93-96 */
+  uint32_t noise_seed;        /* Philox key when no explicit noise tensor is passed                   */
+  int32_t clip;               /* source clip index in `wave`                                          */
+} PcViewDesc;
+
+typedef struct PcMfccConsts { /* device pointers, built once by the host (features.py:25-59)          */
+  const float* window;        /* [n_fft]  periodic Hann                                               */
+  const int32_t* fb_start;    /* [n_mels] first non-zero FFT bin of each mel filter                   */
+  const int32_t* fb_len;      /* [n_mels] number of non-zero bins (<= PC_FB_MAXW)                      */
+  const float* fb_w;          /* [n_mels][PC_FB_MAXW] filter weights                                   */
+  const float* dct;           /* [n_mels][n_mfcc] DCT-II ortho (unused for log-mel)                    */
+  const float* tw;            /* twiddles: cos/sin tables, see mfcc.cu                                 */
+  int32_t n_fft, hop, n_mels, n_mfcc;
+} PcMfccConsts;
+#define PC_FB_MAXW 32
+
+enum { PC_FE_MFCC = 0, PC_FE_LOGMEL = 1 };
+enum { PC_CLAMP_PER_CLIP = 0, PC_CLAMP_NONE = 1, PC_CLAMP_GIVEN = 2 };
+
+/* wave [n_clips, S] (row stride `wave_ld` floats) -> out [n_views, n_out, T] with T = 1 + S/hop and
+ * n_out = n_mfcc (MFCC) or n_mels (log-mel). views == NULL means one un-augmented view per clip.
+ * noise (optional) [n_views, n_out*T]: explicit N(0,1) draws (parity with the torch CPU generator);
+ * otherwise Philox noise is generated on the device. clamp_mode PER_CLIP is the dataset's semantics
+ * (one clip per call, dataset.py:90); GIVEN takes the floor reference from clamp_ref[0] (device),
+ * which reproduces a batched MFCCExtractor call whose amax spans the batch (functional.py:396-399);
+ * clip_max_out (optional) [n_views] receives each view's max dB. */
+int pc_frontend_fwd(const float* wave, int n_clips, int S, int wave_ld, const PcMfccConsts* consts_host,
+                    const PcViewDesc* views, int n_views, const float* noise, int kind, int clamp_mode,
+                    float top_db, const float* clamp_ref, float* clip_max_out, float* out, pc_stream_t stream);
+/* max over n floats -> out[0] (used for the whole-call clamp). */
+int pc_reduce_max(const float* x, int n, float* out, pc_stream_t stream);
+/* Apply masks + noise to existing features x [n_views, F, T] (BaseTransform.__call__ on a tensor,
+ * transforms.py:12-22): out may alias x. */
+int pc_augment_apply(const float* x, const PcViewDesc* views, int n_views, int F, int T, const float* noise,
+                     float* out, pc_stream_t stream);
+/* 5-tap regression deltas along T (features.py:82-95; torchaudio compute_deltas), rows = n*F. */
+int pc_compute_deltas(const float* x, int rows, int T, float* out, pc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2. Supervised contrastive loss
+ *    replaces: SupervisedContrastiveLoss.forward + autograd backward  src/training/losses.py:26-86
+ * ---------------------------------------------------------------------------------------------- */
+/* Row block [row0,row0+nrows) of the N x N problem. F [N,D]; labels [N] (or NULL with mask [N,N] float,
+ * losses.py:27,52). stats [nrows,4] = (row max m, den incl. 1e-6, n_pos, sum_pos(z-m)); row_loss [nrows]
+ * = -(T/T_base) * mean_log_prob_pos (losses.py:76-79). The N x N logits never reach HBM. */
+int pc_supcon_fwd(const float* F, const int64_t* labels, const float* mask, int N, int D, int row0, int nrows,
+                  float temperature, float base_temperature, float* stats, float* row_loss, pc_stream_t stream);
+/* loss[0] = scale * sum(row_loss[0..n)) in a fixed order (scale = 1/N for 'mean', losses.py:81-84). */
+int pc_sum_scaled(const float* x, int n, float scale, float* out, pc_stream_t stream);
+/* dF[row0..row0+nrows) given the stats of ALL N rows (stats_all [N,4]); coef = (T/T_base)*grad_out/N
+ * for 'mean'. grad_scale (optional, device scalar) multiplies coef (upstream gradient). */
+int pc_supcon_bwd(const float* F, const int64_t* labels, const float* mask, int N, int D, int row0, int nrows,
+                  float temperature, float coef, const float* grad_scale, const float* stats_all, float* dF,
+                  pc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 3. CNN building blocks (PhonemeNet / PhonemeNetDeep forward + backward)
+ *    replaces: nn.Conv2d / BatchNorm2d / ReLU / MaxPool2d / Dropout2d / SpatialAttention /
+ *              AdaptiveAvgPool2d / Linear / BatchNorm1d / F.normalize as composed in
+ *              src/models/phoneme_cnn.py:33-77,98-126 (PhonemeNet), :129-143, :146-184, :209-272,274-304
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct PcConvGeom {
+  int32_t B, H, W, Cin;       /* input  [B,H,W,Cin]   */
+  int32_t Ho, Wo, Cout;       /* output [B,Ho,Wo,Cout] */
+  int32_t R, S, stride, pad;
+} PcConvGeom;
+
+/* Per-channel input transform applied while a conv reads its input, so that the activation
+ * a = drop * relu(scale*y + shift) of the previous BatchNorm never has to be materialised:
+ * scale/shift [C] (NULL = identity), relu flag, drop [B,C] multipliers (NULL = none). */
+typedef struct PcInXform {
+  const float* scale;
+  const float* shift;
+  const float* drop;
+  int32_t relu;
+} PcInXform;
+
+/* OIHW fp32 -> fwd layout Wf [(r,s,c)][o] and dgrad layout Wd [(r,s,o)][c] (either may be NULL). */
+int pc_pack_conv_weight(const float* w_oihw, int O, int I, int R, int S, float* wf, float* wd, pc_stream_t stream);
+
+/* y = conv(xform(x)) + bias; if stats != NULL accumulates per-channel sum / sum of squares of y into
+ * stats [2][Cout] (fp64) for the following train-mode BatchNorm. Cin == 1 uses a direct kernel;
+ * otherwise Cin % 16 == 0 and the implicit-GEMM kernel runs (prec: PC_PREC_*). */
+enum { PC_PREC_FP32 = 0, PC_PREC_TF32X3 = 1, PC_PREC_BF16 = 2 };
+int pc_conv_fwd(const float* x, const float* wf, const float* bias, const PcConvGeom* g, const PcInXform* xf,
+                float* y, double* stats, int prec, pc_stream_t stream);
+/* dx (+)= conv_transpose(dy, w): accumulate != 0 adds into dx. */
+int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom* g, float* dx, int accumulate, int prec,
+                  pc_stream_t stream);
+/* dw (OIHW) and db from x (through xform) and dy. workspace >= pc_conv_wgrad_workspace(g) bytes. */
+size_t pc_conv_wgrad_workspace(const PcConvGeom* g);
+int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw,
+                  float* db, void* workspace, size_t workspace_bytes, int prec, pc_stream_t stream);
+
+/* BatchNorm statistics -> per-channel coefficients.
+ * training: mean/var from stats (count = elements per channel), running stats updated with `momentum`
+ * (unbiased variance) exactly like nn.BatchNorm2d; eval: coefficients from the running stats.
+ * Outputs: scale = gamma*invstd, shift = beta - mean*scale, mean, invstd (all [C]). */
+int pc_bn_finalize(const double* stats, int C, double count, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum, float eps,
+                   int training, float* scale, float* shift, float* mean, float* invstd, pc_stream_t stream);
+
+/* Fused BatchNorm-apply + ReLU (+ max-pool) (+ Dropout2d multiplier) producing a materialised activation.
+ * pool: 0 none, 2 = MaxPool2d(2,2) (phoneme_cnn.py:42,52), 3 = MaxPool2d(3,2,1) (:215; writes argmax u8). */
+int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const float* scale, const float* shift,
+                  const float* drop, int pool, float* out, uint8_t* argmax, pc_stream_t stream);
+/* Backward of the above w.r.t. y: two passes. pass 1 accumulates sums[0][C] = sum dz, sums[1][C] = sum dz*xhat (fp64);
+ * pass 2 writes dy = scale*(dz - sum_dz/M - xhat*sum_dzxhat/M) and dgamma/dbeta. dout is the gradient w.r.t. `out`. */
+int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
+                         const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
+                         const uint8_t* argmax, double* sums, pc_stream_t stream);
+int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
+                        const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
+                        const uint8_t* argmax, const double* sums, float* dy, float* dgamma, float* dbeta,
+                        pc_stream_t stream);
+
+/* Residual tail: out = relu(bn2(y2) + (sc_scale ? bn_s(ysc) : ysc))   (phoneme_cnn.py:177-182). */
+int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const float* shift2, const float* ysc,
+                       const float* sc_scale, const float* sc_shift, int64_t n_pix, int C, float* out,
+                       pc_stream_t stream);
+/* g = dout * (out > 0); pass 1: sums2[2][C] over (g, y2) and sums_s[2][C] over (g, ysc) (sums_s NULL for identity);
+ * pass 2: dy2, dysc (or, identity shortcut, dsc (+)= g into dx_identity), dgamma/dbeta for both norms. */
+int pc_bn_add_relu_bwd_reduce(const float* dout, const float* out, const float* y2, const float* mean2,
+                              const float* invstd2, const float* ysc, const float* mean_s, const float* invstd_s,
+                              int64_t n_pix, int C, double* sums2, double* sums_s, pc_stream_t stream);
+int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, const float* y2, const float* scale2,
+                             const float* mean2, const float* invstd2, const double* sums2, const float* ysc,
+                             const float* sc_scale, const float* mean_s, const float* invstd_s, const double* sums_s,
+                             int64_t n_pix, int C, float* dy2, float* dysc_or_dx, float* dgamma2, float* dbeta2,
+                             float* dgamma_s, float* dbeta_s, pc_stream_t stream);
+
+/* SpatialAttention + AdaptiveAvgPool2d(1): pooled[b,c] = mean_p a[b,p,c] * sigmoid(w.a[b,p,:] + b0)
+ * (phoneme_cnn.py:134-143,117-118). w == NULL: plain mean (use_attention False). gate [B,HW] saved for backward. */
+int pc_attn_pool_fwd(const float* a, int B, int HW, int C, const float* w, const float* b0, float* gate,
+                     float* pooled, pc_stream_t stream);
+int pc_attn_pool_bwd(const float* a, const float* gate, const float* dpooled, int B, int HW, int C, const float* w,
+                     float* da, float* dw, float* db0, pc_stream_t stream);
+
+/* Projection head: z = x W^T + b (Linear, [N,K] weight) ; zn = BatchNorm1d(z) ; e = zn / max(||zn||, 1e-12)
+ * (phoneme_cnn.py:75-77,121-124). ws: >= pc_head_workspace(B,K,N) bytes, kept until the backward. */
+size_t pc_head_workspace(int B, int K, int N);
+int pc_head_fwd(const float* x, int B, int K, int N, const float* W, const float* bias, const float* gamma,
+                const float* beta, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                float momentum, float eps, int training, float* emb, void* ws, pc_stream_t stream);
+int pc_head_bwd(const float* demb, const float* x, int B, int K, int N, const float* W, const float* gamma,
+                const float* beta, int training, void* ws, float* dx, float* dW, float* dbias, float* dgamma,
+                float* dbeta, pc_stream_t stream);
+
+/* Dropout2d multipliers drop[B,C] in {0, 1/(1-p)} from Philox(seed, offset) (phoneme_cnn.py:43,53,62,176). */
+int pc_dropout2d_mask(float* drop, int B, int C, float p, uint64_t seed, uint64_t offset, pc_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 4. Optimiser step on flat buffers
+ *    replaces: clip_grad_norm_ (src/training/trainer.py:147-150) + torch.optim.Adam.step
+ *              (scripts/train.py:129-133; L2 weight decay, betas .9/.999, eps 1e-8)
+ * ---------------------------------------------------------------------------------------------- */
+/* norm_sq[0] += sum g^2 (fp64; caller zeroes it). */
+int pc_grad_sumsq(const float* g, int64_t n, double* norm_sq, pc_stream_t stream);
+/* In-place Adam on n elements. grad is first multiplied by grad_prescale (e.g. 1/world_size) and by the
+ * clip coefficient min(1, max_norm/(sqrt(norm_sq*prescale^2)+1e-6)) when max_norm > 0. `step` is 1-based. */
+int pc_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, float max_norm, const double* norm_sq, float grad_prescale,
+                 int64_t step, pc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHONEME_CONTRAST_H_ */

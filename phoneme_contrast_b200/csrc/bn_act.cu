@@ -1,0 +1,558 @@
+// BatchNorm coefficient finalisation and the fused BatchNorm-apply / ReLU / max-pool / Dropout2d /
+// residual-add elementwise passes, forward and backward. All tensors NHWC fp32; these kernels are
+// HBM-bound: float4 channel vectors, grid-stride over pixels, per-channel reductions accumulated in
+// registers -> shared memory -> one fp64 atomic per channel per CTA.
+//
+// Reference modules: nn.BatchNorm2d / ReLU / MaxPool2d / Dropout2d as composed in
+// src/models/phoneme_cnn.py:36-63 (PhonemeNet blocks), :211-216 (init_conv), :173-184 (ResidualBlock).
+#include "common.cuh"
+
+namespace pc {
+
+// ------------------------------------------------------------------------------------------------ finalize
+__global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
+                                   int64_t* __restrict__ nbt, float momentum, float eps, int training,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
+                                   float* __restrict__ invstd_o) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && training && nbt != nullptr) nbt[0] += 1;
+  if (c >= C) return;
+  float mean, invstd;
+  if (training) {
+    const double mu = stats[c] / count;
+    double var = stats[C + c] / count - mu * mu;
+    var = var < 0.0 ? 0.0 : var;
+    mean = (float)mu;
+    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean != nullptr) {
+      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+      rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
+      rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
+    }
+  } else {
+    mean = rmean[c];
+    invstd = 1.0f / sqrtf(rvar[c] + eps);
+  }
+  const float g = gamma != nullptr ? gamma[c] : 1.f, b = beta != nullptr ? beta[c] : 0.f;
+  const float s = g * invstd;
+  scale[c] = s;
+  shift[c] = b - mean * s;
+  if (mean_o != nullptr) mean_o[c] = mean;
+  if (invstd_o != nullptr) invstd_o[c] = invstd;
+}
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 bn_relu4(float4 y, float4 s, float4 t) {
+  return make_float4(fmaxf(fmaf(y.x, s.x, t.x), 0.f), fmaxf(fmaf(y.y, s.y, t.y), 0.f), fmaxf(fmaf(y.z, s.z, t.z), 0.f),
+                     fmaxf(fmaf(y.w, s.w, t.w), 0.f));
+}
+#define PC_F4_ARR(v) {(v).x, (v).y, (v).z, (v).w}
+
+// ------------------------------------------------------------------------------------------------ forward
+template <int POOL>
+__global__ void __launch_bounds__(256)
+bn_act_fwd_kernel(const float* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const float* __restrict__ drop, float* __restrict__ out,
+                  uint8_t* __restrict__ argmax) {
+  const int C4 = C >> 2;
+  const long long total = (long long)B * Ho * Wo * C4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % C4);
+    long long p = idx / C4;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    const int c = c4 * 4;
+    const float4 s = ld4(scale + c), t = ld4(shift + c);
+    float4 r;
+    if (POOL == 0) {
+      r = bn_relu4(ld4(y + (((size_t)b * H + ho) * W + wo) * C + c), s, t);
+    } else if (POOL == 2) {
+      r = make_float4(0.f, 0.f, 0.f, 0.f);  // relu output >= 0
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 2; ++kw) {
+          const float4 a = bn_relu4(ld4(y + (((size_t)b * H + 2 * ho + kh) * W + 2 * wo + kw) * C + c), s, t);
+          r.x = fmaxf(r.x, a.x); r.y = fmaxf(r.y, a.y); r.z = fmaxf(r.z, a.z); r.w = fmaxf(r.w, a.w);
+        }
+    } else {  // MaxPool2d(3, 2, 1): padding acts as -inf; first maximum in scan order wins (strict >)
+      float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      int arg[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h = 2 * ho - 1 + kh;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int w = 2 * wo - 1 + kw;
+          if (w < 0 || w >= W) continue;
+          const float4 a4 = bn_relu4(ld4(y + (((size_t)b * H + h) * W + w) * C + c), s, t);
+          const float a[4] = PC_F4_ARR(a4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (a[q] > best[q]) { best[q] = a[q]; arg[q] = kh * 3 + kw; }
+        }
+      }
+      r = make_float4(best[0], best[1], best[2], best[3]);
+      if (argmax != nullptr) {
+        uchar4 am = make_uchar4((unsigned char)arg[0], (unsigned char)arg[1], (unsigned char)arg[2], (unsigned char)arg[3]);
+        *reinterpret_cast<uchar4*>(argmax + (((size_t)b * Ho + ho) * Wo + wo) * C + c) = am;
+      }
+    }
+    if (drop != nullptr) {
+      const float4 d = ld4(drop + (size_t)b * C + c);
+      r.x *= d.x; r.y *= d.y; r.z *= d.z; r.w *= d.w;
+    }
+    st4(out + (((size_t)b * Ho + ho) * Wo + wo) * C + c, r);
+  }
+}
+
+// dz (gradient w.r.t. the BatchNorm output) of input pixel (b,h,w), channels c..c+3, and xhat.
+template <int POOL>
+__device__ __forceinline__ void bn_act_dz(const float* __restrict__ dout, const float* __restrict__ y, int b, int h, int w,
+                                          int c, int H, int W, int C, int Ho, int Wo, float4 s, float4 t,
+                                          const float* __restrict__ drop, const uint8_t* __restrict__ argmax,
+                                          float dz[4], float4& yv) {
+  yv = ld4(y + (((size_t)b * H + h) * W + w) * C + c);
+  const float4 a4 = bn_relu4(yv, s, t);
+  const float a[4] = PC_F4_ARR(a4);
+  float g[4] = {0.f, 0.f, 0.f, 0.f};
+  if (POOL == 0) {
+    const float4 d4 = ld4(dout + (((size_t)b * H + h) * W + w) * C + c);
+    g[0] = d4.x; g[1] = d4.y; g[2] = d4.z; g[3] = d4.w;
+  } else if (POOL == 2) {
+    const int ho = h >> 1, wo = w >> 1;
+    if (ho < Ho && wo < Wo) {
+      // recompute the window; the first maximum in scan order receives the gradient
+      float best[4] = {-1.f, -1.f, -1.f, -1.f};
+      int arg[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int kh = 0; kh < 2; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 2; ++kw) {
+          const float4 o4 = bn_relu4(ld4(y + (((size_t)b * H + 2 * ho + kh) * W + 2 * wo + kw) * C + c), s, t);
+          const float o[4] = PC_F4_ARR(o4);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (o[q] > best[q]) { best[q] = o[q]; arg[q] = kh * 2 + kw; }
+        }
+      const int me = (h & 1) * 2 + (w & 1);
+      const float4 d4 = ld4(dout + (((size_t)b * Ho + ho) * Wo + wo) * C + c);
+      const float d[4] = PC_F4_ARR(d4);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g[q] = (arg[q] == me) ? d[q] : 0.f;
+    }
+  } else {
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int hn = h + 1 - kh;
+      if (hn < 0 || (hn & 1)) continue;
+      const int ho = hn >> 1;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int wn = w + 1 - kw;
+        if (wn < 0 || (wn & 1)) continue;
+        const int wo = wn >> 1;
+        if (wo >= Wo) continue;
+        const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * C + c;
+        const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + o);
+        const float4 d4 = ld4(dout + o);
+        const int me = kh * 3 + kw;
+        if (am.x == me) g[0] += d4.x;
+        if (am.y == me) g[1] += d4.y;
+        if (am.z == me) g[2] += d4.z;
+        if (am.w == me) g[3] += d4.w;
+      }
+    }
+  }
+  float dr[4] = {1.f, 1.f, 1.f, 1.f};
+  if (drop != nullptr) {
+    const float4 d = ld4(drop + (size_t)b * C + c);
+    dr[0] = d.x; dr[1] = d.y; dr[2] = d.z; dr[3] = d.w;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dz[q] = (a[q] > 0.f) ? g[q] * dr[q] : 0.f;
+}
+
+// Block-level per-channel reduction of NV values per thread (thread owns channels c4*4..+3), then fp64 atomics.
+template <int NV>
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][4], int C4, double* const* dst, int C, float* sh) {
+  // sh: [256][4] floats
+  const int tid = threadIdx.x;
+  const int c4 = tid % C4;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sh[tid * 4 + q] = acc[v][q];
+    __syncthreads();
+    if (tid < C4) {
+      double s[4] = {0.0, 0.0, 0.0, 0.0};
+      for (int t = tid; t < (int)blockDim.x; t += C4)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s[q] += (double)sh[t * 4 + q];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) atomicAdd(dst[v] + c4 * 4 + q, s[q]);
+    }
+  }
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ y, int B, int H, int W, int C, int Ho,
+                         int Wo, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ drop,
+                         const uint8_t* __restrict__ argmax, double* __restrict__ sums) {
+  __shared__ float sh[256 * 4];
+  const int C4 = C >> 2;
+  const int c4 = threadIdx.x % C4, c = c4 * 4;
+  const int ppb = blockDim.x / C4;  // pixels per block iteration
+  const float4 s = ld4(scale + c), t = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  const long long npix = (long long)B * H * W;
+  for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < npix; p += (long long)gridDim.x * ppb) {
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const int b = (int)(p / ((long long)W * H));
+    float dz[4];
+    float4 yv;
+    bn_act_dz<POOL>(dout, y, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
+    acc[0][0] += dz[0]; acc[0][1] += dz[1]; acc[0][2] += dz[2]; acc[0][3] += dz[3];
+    acc[1][0] += dz[0] * (yv.x - mu.x) * is.x;
+    acc[1][1] += dz[1] * (yv.y - mu.y) * is.y;
+    acc[1][2] += dz[2] * (yv.z - mu.z) * is.z;
+    acc[1][3] += dz[3] * (yv.w - mu.w) * is.w;
+  }
+  double* dst[2] = {sums, sums + C};
+  block_channel_reduce<2>(acc, C4, dst, C, sh);
+}
+
+template <int POOL>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y, int B, int H, int W, int C, int Ho,
+                        int Wo, const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ drop,
+                        const uint8_t* __restrict__ argmax, const double* __restrict__ sums, float* __restrict__ dy,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int C4 = C >> 2;
+  const int c4 = threadIdx.x % C4, c = c4 * 4;
+  const int ppb = blockDim.x / C4;
+  const long long npix = (long long)B * H * W;
+  const float invM = 1.0f / (float)npix;
+  const float4 s = ld4(scale + c), t = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
+  float sdz[4], sdzx[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    sdz[q] = (float)sums[c + q];
+    sdzx[q] = (float)sums[C + c + q];
+  }
+  if (blockIdx.x == 0 && threadIdx.x < C4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (dgamma != nullptr) dgamma[c + q] = sdzx[q];
+      if (dbeta != nullptr) dbeta[c + q] = sdz[q];
+    }
+  }
+  const float sv[4] = PC_F4_ARR(s), muv[4] = PC_F4_ARR(mu), isv[4] = PC_F4_ARR(is);
+  for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < npix; p += (long long)gridDim.x * ppb) {
+    const int w = (int)(p % W);
+    const int h = (int)((p / W) % H);
+    const int b = (int)(p / ((long long)W * H));
+    float dz[4];
+    float4 yv;
+    bn_act_dz<POOL>(dout, y, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
+    const float yy[4] = PC_F4_ARR(yv);
+    float r[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float xhat = (yy[q] - muv[q]) * isv[q];
+      r[q] = sv[q] * (dz[q] - sdz[q] * invM - xhat * sdzx[q] * invM);
+    }
+    st4(dy + (size_t)p * C + c, make_float4(r[0], r[1], r[2], r[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ residual tail
+__global__ void __launch_bounds__(256)
+bn_add_relu_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ scale2, const float* __restrict__ shift2,
+                       const float* __restrict__ ysc, const float* __restrict__ sc_scale, const float* __restrict__ sc_shift,
+                       long long n_pix, int C, float* __restrict__ out) {
+  const int C4 = C >> 2;
+  const long long total = n_pix * C4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C4) * 4;
+    const size_t o = (size_t)(idx / C4) * C + c;
+    const float4 a = ld4(y2 + o), s = ld4(scale2 + c), t = ld4(shift2 + c);
+    float4 r = ld4(ysc + o);
+    if (sc_scale != nullptr) {
+      const float4 ss = ld4(sc_scale + c), ts = ld4(sc_shift + c);
+      r = make_float4(fmaf(r.x, ss.x, ts.x), fmaf(r.y, ss.y, ts.y), fmaf(r.z, ss.z, ts.z), fmaf(r.w, ss.w, ts.w));
+    }
+    r.x = fmaxf(fmaf(a.x, s.x, t.x) + r.x, 0.f);
+    r.y = fmaxf(fmaf(a.y, s.y, t.y) + r.y, 0.f);
+    r.z = fmaxf(fmaf(a.z, s.z, t.z) + r.z, 0.f);
+    r.w = fmaxf(fmaf(a.w, s.w, t.w) + r.w, 0.f);
+    st4(out + o, r);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y2,
+                              const float* __restrict__ mean2, const float* __restrict__ invstd2,
+                              const float* __restrict__ ysc, const float* __restrict__ mean_s,
+                              const float* __restrict__ invstd_s, long long n_pix, int C, double* __restrict__ sums2,
+                              double* __restrict__ sums_s) {
+  __shared__ float sh[256 * 4];
+  const int C4 = C >> 2;
+  const int c4 = threadIdx.x % C4, c = c4 * 4;
+  const int ppb = blockDim.x / C4;
+  const float4 mu2 = ld4(mean2 + c), is2 = ld4(invstd2 + c);
+  const bool proj = sums_s != nullptr;
+  float4 mus = make_float4(0.f, 0.f, 0.f, 0.f), iss = mus;
+  if (proj) { mus = ld4(mean_s + c); iss = ld4(invstd_s + c); }
+  float acc[3][4] = {};
+  for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < n_pix; p += (long long)gridDim.x * ppb) {
+    const size_t o = (size_t)p * C + c;
+    const float4 d = ld4(dout + o), ov = ld4(out + o), yv = ld4(y2 + o);
+    const float g[4] = {ov.x > 0.f ? d.x : 0.f, ov.y > 0.f ? d.y : 0.f, ov.z > 0.f ? d.z : 0.f, ov.w > 0.f ? d.w : 0.f};
+    acc[0][0] += g[0]; acc[0][1] += g[1]; acc[0][2] += g[2]; acc[0][3] += g[3];
+    acc[1][0] += g[0] * (yv.x - mu2.x) * is2.x;
+    acc[1][1] += g[1] * (yv.y - mu2.y) * is2.y;
+    acc[1][2] += g[2] * (yv.z - mu2.z) * is2.z;
+    acc[1][3] += g[3] * (yv.w - mu2.w) * is2.w;
+    if (proj) {
+      const float4 sv = ld4(ysc + o);
+      acc[2][0] += g[0] * (sv.x - mus.x) * iss.x;
+      acc[2][1] += g[1] * (sv.y - mus.y) * iss.y;
+      acc[2][2] += g[2] * (sv.z - mus.z) * iss.z;
+      acc[2][3] += g[3] * (sv.w - mus.w) * iss.w;
+    }
+  }
+  // sums2 = [sum g, sum g*xhat2]; sums_s = [sum g, sum g*xhat_s]
+  if (proj) {
+    double* dst[3] = {sums2, sums2 + C, sums_s + C};
+    block_channel_reduce<3>(acc, C4, dst, C, sh);
+  } else {
+    float acc2[2][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { acc2[0][q] = acc[0][q]; acc2[1][q] = acc[1][q]; }
+    double* dst[2] = {sums2, sums2 + C};
+    block_channel_reduce<2>(acc2, C4, dst, C, sh);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y2,
+                             const float* __restrict__ scale2, const float* __restrict__ mean2,
+                             const float* __restrict__ invstd2, const double* __restrict__ sums2,
+                             const float* __restrict__ ysc, const float* __restrict__ sc_scale,
+                             const float* __restrict__ mean_s, const float* __restrict__ invstd_s,
+                             const double* __restrict__ sums_s, long long n_pix, int C, float* __restrict__ dy2,
+                             float* __restrict__ dysc, float* __restrict__ dgamma2, float* __restrict__ dbeta2,
+                             float* __restrict__ dgamma_s, float* __restrict__ dbeta_s) {
+  const int C4 = C >> 2;
+  const int c4 = threadIdx.x % C4, c = c4 * 4;
+  const int ppb = blockDim.x / C4;
+  const float invM = 1.0f / (float)n_pix;
+  const bool proj = sc_scale != nullptr;
+  const float4 s2 = ld4(scale2 + c), mu2 = ld4(mean2 + c), is2 = ld4(invstd2 + c);
+  float4 ss = make_float4(1.f, 1.f, 1.f, 1.f), mus = make_float4(0.f, 0.f, 0.f, 0.f), iss = mus;
+  if (proj) { ss = ld4(sc_scale + c); mus = ld4(mean_s + c); iss = ld4(invstd_s + c); }
+  float sg[4], sgx2[4], sgxs[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    sg[q] = (float)sums2[c + q];
+    sgx2[q] = (float)sums2[C + c + q];
+    sgxs[q] = proj ? (float)sums_s[C + c + q] : 0.f;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < C4) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (dgamma2 != nullptr) dgamma2[c + q] = sgx2[q];
+      if (dbeta2 != nullptr) dbeta2[c + q] = sg[q];
+      if (proj && dgamma_s != nullptr) dgamma_s[c + q] = sgxs[q];
+      if (proj && dbeta_s != nullptr) dbeta_s[c + q] = sg[q];
+    }
+  }
+  const float s2v[4] = PC_F4_ARR(s2), mu2v[4] = PC_F4_ARR(mu2), is2v[4] = PC_F4_ARR(is2);
+  const float ssv[4] = PC_F4_ARR(ss), musv[4] = PC_F4_ARR(mus), issv[4] = PC_F4_ARR(iss);
+  for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < n_pix; p += (long long)gridDim.x * ppb) {
+    const size_t o = (size_t)p * C + c;
+    const float4 d = ld4(dout + o), ov = ld4(out + o), yv = ld4(y2 + o);
+    const float g[4] = {ov.x > 0.f ? d.x : 0.f, ov.y > 0.f ? d.y : 0.f, ov.z > 0.f ? d.z : 0.f, ov.w > 0.f ? d.w : 0.f};
+    const float yy[4] = PC_F4_ARR(yv);
+    float r2[4], rs[4];
+    float scv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (proj) {
+      const float4 sv = ld4(ysc + o);
+      scv[0] = sv.x; scv[1] = sv.y; scv[2] = sv.z; scv[3] = sv.w;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x2 = (yy[q] - mu2v[q]) * is2v[q];
+      r2[q] = s2v[q] * (g[q] - sg[q] * invM - x2 * sgx2[q] * invM);
+      if (proj) {
+        const float xs = (scv[q] - musv[q]) * issv[q];
+        rs[q] = ssv[q] * (g[q] - sg[q] * invM - xs * sgxs[q] * invM);
+      } else {
+        rs[q] = g[q];
+      }
+    }
+    st4(dy2 + o, make_float4(r2[0], r2[1], r2[2], r2[3]));
+    st4(dysc + o, make_float4(rs[0], rs[1], rs[2], rs[3]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dropout mask
+__global__ void dropout2d_mask_kernel(float* __restrict__ drop, int n, float p, float keep_scale, uint64_t seed, uint64_t offset) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i * 4 >= n) return;
+  const uint64_t ctr = offset + (uint64_t)i;
+  const uint4 r = Philox::round10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x44524f50u, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const uint32_t rv[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (i * 4 + q < n) drop[i * 4 + q] = (Philox::u01(rv[q]) >= p) ? keep_scale : 0.f;
+}
+
+static inline int ew_grid(long long work_items, int per_block) {
+  long long g = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)kNumSMs * 16;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+static inline void pool_out_dims(int H, int W, int pool, int* Ho, int* Wo) {
+  if (pool == 0) { *Ho = H; *Wo = W; }
+  else if (pool == 2) { *Ho = H / 2; *Wo = W / 2; }
+  else { *Ho = (H + 2 - 3) / 2 + 1; *Wo = (W + 2 - 3) / 2 + 1; }
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+extern "C" int pc_bn_finalize(const double* stats, int C, double count, const float* gamma, const float* beta,
+                              float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
+                              float eps, int training, float* scale, float* shift, float* mean, float* invstd,
+                              pc_stream_t stream) {
+  PC_REQUIRE(C > 0 && scale && shift, PC_EINVAL, "pc_bn_finalize: bad arguments");
+  PC_REQUIRE(training ? (stats != nullptr && count >= 1.0) : (running_mean && running_var), PC_EINVAL,
+             "pc_bn_finalize: missing statistics");
+  // nn.BatchNorm raises for a single value per channel in training mode (tests/test_models.py:52,97-103 avoid it)
+  PC_REQUIRE(!training || count > 1.0, PC_EINVAL, "Expected more than 1 value per channel when training");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(stats, C, count, gamma, beta, running_mean, running_var,
+                                                            num_batches_tracked, momentum, eps, training, scale, shift,
+                                                            mean, invstd);
+  PC_LAUNCH_CHECK("bn_finalize_kernel");
+  return PC_OK;
+}
+
+#define PC_CHECK_C4(fn, C) \
+  PC_REQUIRE((C) > 0 && (C) % 4 == 0 && (C) <= 1024 && 256 % ((C) / 4) == 0, PC_EUNSUPPORTED, fn ": channels=%d must be 4*2^k <= 1024", (C))
+
+extern "C" int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const float* scale, const float* shift,
+                             const float* drop, int pool, float* out, uint8_t* argmax, pc_stream_t stream) {
+  PC_REQUIRE(y && scale && shift && out && B > 0 && H > 0 && W > 0, PC_EINVAL, "pc_bn_act_fwd: bad arguments");
+  PC_CHECK_C4("pc_bn_act_fwd", C);
+  PC_REQUIRE(pool == 0 || pool == 2 || pool == 3, PC_EINVAL, "pc_bn_act_fwd: pool must be 0, 2 or 3");
+  int Ho, Wo;
+  pool_out_dims(H, W, pool, &Ho, &Wo);
+  PC_REQUIRE(Ho > 0 && Wo > 0, PC_EINVAL, "pc_bn_act_fwd: input %dx%d too small for pooling", H, W);
+  const long long total = (long long)B * Ho * Wo * (C / 4);
+  const int grid = ew_grid(total, 256);
+  if (pool == 0) bn_act_fwd_kernel<0><<<grid, 256, 0, stream>>>(y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
+  else if (pool == 2) bn_act_fwd_kernel<2><<<grid, 256, 0, stream>>>(y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
+  else bn_act_fwd_kernel<3><<<grid, 256, 0, stream>>>(y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
+  PC_LAUNCH_CHECK("bn_act_fwd_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
+                                    const float* shift, const float* mean, const float* invstd, const float* drop,
+                                    int pool, const uint8_t* argmax, double* sums, pc_stream_t stream) {
+  PC_REQUIRE(dout && y && scale && shift && mean && invstd && sums, PC_EINVAL, "pc_bn_act_bwd_reduce: null pointer");
+  PC_CHECK_C4("pc_bn_act_bwd_reduce", C);
+  PC_REQUIRE(pool == 0 || pool == 2 || (pool == 3 && argmax), PC_EINVAL, "pc_bn_act_bwd_reduce: bad pool / argmax");
+  int Ho, Wo;
+  pool_out_dims(H, W, pool, &Ho, &Wo);
+  const long long items = (long long)B * H * W * (C / 4);
+  const int grid = ew_grid(items, 256 * 4);
+  if (pool == 0) bn_act_bwd_reduce_kernel<0><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
+  else if (pool == 2) bn_act_bwd_reduce_kernel<2><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
+  else bn_act_bwd_reduce_kernel<3><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
+  PC_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
+                                   const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
+                                   const uint8_t* argmax, const double* sums, float* dy, float* dgamma, float* dbeta,
+                                   pc_stream_t stream) {
+  PC_REQUIRE(dout && y && scale && shift && mean && invstd && sums && dy, PC_EINVAL, "pc_bn_act_bwd_apply: null pointer");
+  PC_CHECK_C4("pc_bn_act_bwd_apply", C);
+  PC_REQUIRE(pool == 0 || pool == 2 || (pool == 3 && argmax), PC_EINVAL, "pc_bn_act_bwd_apply: bad pool / argmax");
+  int Ho, Wo;
+  pool_out_dims(H, W, pool, &Ho, &Wo);
+  const long long items = (long long)B * H * W * (C / 4);
+  const int grid = ew_grid(items, 256 * 2);
+  if (pool == 0) bn_act_bwd_apply_kernel<0><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta);
+  else if (pool == 2) bn_act_bwd_apply_kernel<2><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta);
+  else bn_act_bwd_apply_kernel<3><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta);
+  PC_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const float* shift2, const float* ysc,
+                                  const float* sc_scale, const float* sc_shift, int64_t n_pix, int C, float* out,
+                                  pc_stream_t stream) {
+  PC_REQUIRE(y2 && scale2 && shift2 && ysc && out && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_fwd: bad arguments");
+  PC_REQUIRE((sc_scale == nullptr) == (sc_shift == nullptr), PC_EINVAL, "pc_bn_add_relu_fwd: shortcut scale/shift mismatch");
+  PC_CHECK_C4("pc_bn_add_relu_fwd", C);
+  bn_add_relu_fwd_kernel<<<ew_grid(n_pix * (C / 4), 256), 256, 0, stream>>>(y2, scale2, shift2, ysc, sc_scale, sc_shift, n_pix, C, out);
+  PC_LAUNCH_CHECK("bn_add_relu_fwd_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_bn_add_relu_bwd_reduce(const float* dout, const float* out, const float* y2, const float* mean2,
+                                         const float* invstd2, const float* ysc, const float* mean_s,
+                                         const float* invstd_s, int64_t n_pix, int C, double* sums2, double* sums_s,
+                                         pc_stream_t stream) {
+  PC_REQUIRE(dout && out && y2 && mean2 && invstd2 && sums2 && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_bwd_reduce: bad arguments");
+  PC_REQUIRE(sums_s == nullptr || (ysc && mean_s && invstd_s), PC_EINVAL, "pc_bn_add_relu_bwd_reduce: shortcut pointers");
+  PC_CHECK_C4("pc_bn_add_relu_bwd_reduce", C);
+  bn_add_relu_bwd_reduce_kernel<<<ew_grid(n_pix * (C / 4), 256 * 4), 256, 0, stream>>>(dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s);
+  PC_LAUNCH_CHECK("bn_add_relu_bwd_reduce_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, const float* y2, const float* scale2,
+                                        const float* mean2, const float* invstd2, const double* sums2, const float* ysc,
+                                        const float* sc_scale, const float* mean_s, const float* invstd_s,
+                                        const double* sums_s, int64_t n_pix, int C, float* dy2, float* dysc_or_dx,
+                                        float* dgamma2, float* dbeta2, float* dgamma_s, float* dbeta_s, pc_stream_t stream) {
+  PC_REQUIRE(dout && out && y2 && scale2 && mean2 && invstd2 && sums2 && dy2 && dysc_or_dx && n_pix > 0, PC_EINVAL,
+             "pc_bn_add_relu_bwd_apply: bad arguments");
+  PC_REQUIRE(sc_scale == nullptr || (ysc && mean_s && invstd_s && sums_s), PC_EINVAL, "pc_bn_add_relu_bwd_apply: shortcut pointers");
+  PC_CHECK_C4("pc_bn_add_relu_bwd_apply", C);
+  bn_add_relu_bwd_apply_kernel<<<ew_grid(n_pix * (C / 4), 256 * 2), 256, 0, stream>>>(
+      dout, out, y2, scale2, mean2, invstd2, sums2, ysc, sc_scale, mean_s, invstd_s, sums_s, n_pix, C, dy2, dysc_or_dx,
+      dgamma2, dbeta2, dgamma_s, dbeta_s);
+  PC_LAUNCH_CHECK("bn_add_relu_bwd_apply_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_dropout2d_mask(float* drop, int B, int C, float p, uint64_t seed, uint64_t offset, pc_stream_t stream) {
+  PC_REQUIRE(drop && B > 0 && C > 0 && p >= 0.f && p < 1.f, PC_EINVAL, "pc_dropout2d_mask: bad arguments (p=%f)", p);
+  const int n = B * C;
+  dropout2d_mask_kernel<<<ceil_div(ceil_div(n, 4), 128), 128, 0, stream>>>(drop, n, p, 1.0f / (1.0f - p), seed, offset);
+  PC_LAUNCH_CHECK("dropout2d_mask_kernel");
+  return PC_OK;
+}

@@ -1,0 +1,86 @@
+// Shared helpers for libpc_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/phoneme_contrast.h"
+
+namespace pc {
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define PC_REQUIRE(cond, status, ...)        \
+  do {                                       \
+    if (!(cond)) {                           \
+      pc::set_error(__VA_ARGS__);            \
+      return (status);                       \
+    }                                        \
+  } while (0)
+
+// Call right after a kernel launch.
+#define PC_LAUNCH_CHECK(name)                                                   \
+  do {                                                                          \
+    pc::count_launch();                                                         \
+    cudaError_t e__ = cudaGetLastError();                                       \
+    if (e__ != cudaSuccess) {                                                   \
+      pc::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+      return PC_ECUDA;                                                          \
+    }                                                                           \
+  } while (0)
+
+#define PC_CUDA(call)                                                           \
+  do {                                                                          \
+    cudaError_t e__ = (call);                                                   \
+    if (e__ != cudaSuccess) {                                                   \
+      pc::set_error("%s: %s", #call, cudaGetErrorString(e__));                  \
+      return PC_ECUDA;                                                          \
+    }                                                                           \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200
+
+__host__ __device__ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Philox4x32-10 (counter-based RNG; Salmon et al. 2011), used for device noise and dropout masks.
+struct Philox {
+  __device__ static inline uint4 round10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+      const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+      ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+      key.x += 0x9E3779B9u;
+      key.y += 0xBB67AE85u;
+    }
+    return ctr;
+  }
+  __device__ static inline float u01(uint32_t x) { return ((x >> 8) + 0.5f) * (1.0f / 16777216.0f); }
+  // two N(0,1) from two uniforms (Box-Muller)
+  __device__ static inline float2 normal2(uint32_t a, uint32_t b) {
+    const float u1 = u01(a), u2 = u01(b);
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincosf(6.283185307179586f * u2, &s, &c);
+    return make_float2(r * c, r * s);
+  }
+};
+
+}  // namespace pc

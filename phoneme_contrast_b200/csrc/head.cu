@@ -1,0 +1,312 @@
+// Network head: SpatialAttention gate + global average pool, then Linear + BatchNorm1d + L2 normalise,
+// forward and backward. Reference: src/models/phoneme_cnn.py:129-143 (SpatialAttention), :117-124 / :295-302
+// (pool, projection, F.normalize). Tensors are tiny here ([B,HW,C] with HW*C <= 32 K floats per sample,
+// [B,128] embeddings); the kernels are latency-bound, so they are kept few and simple.
+#include "common.cuh"
+
+namespace pc {
+
+// one CTA per sample
+__global__ void __launch_bounds__(256)
+attn_pool_fwd_kernel(const float* __restrict__ a, int HW, int C, const float* __restrict__ w, const float* __restrict__ b0,
+                     float* __restrict__ gate, float* __restrict__ pooled) {
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* ab = a + (size_t)b * HW * C;
+  float* gb = gate + (size_t)b * HW;
+  if (w != nullptr) {
+    const float bias = b0 != nullptr ? b0[0] : 0.f;
+    for (int p = warp; p < HW; p += 8) {
+      float s = 0.f;
+      for (int c = lane; c < C; c += 32) s = fmaf(ab[(size_t)p * C + c], w[c], s);
+      s = warp_sum(s);
+      if (lane == 0) gb[p] = 1.0f / (1.0f + expf(-(s + bias)));
+    }
+  } else {
+    for (int p = tid; p < HW; p += 256) gb[p] = 1.0f;
+  }
+  __syncthreads();
+  const float inv = 1.0f / (float)HW;
+  for (int c = tid; c < C; c += 256) {
+    float s = 0.f;
+    for (int p = 0; p < HW; ++p) s = fmaf(ab[(size_t)p * C + c], gb[p], s);
+    pooled[(size_t)b * C + c] = s * inv;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+attn_pool_bwd_kernel(const float* __restrict__ a, const float* __restrict__ gate, const float* __restrict__ dpooled, int HW,
+                     int C, const float* __restrict__ w, float* __restrict__ da, float* __restrict__ dw,
+                     float* __restrict__ db0) {
+  extern __shared__ float du[];   // [HW]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* ab = a + (size_t)b * HW * C;
+  const float* gb = gate + (size_t)b * HW;
+  const float* gp = dpooled + (size_t)b * C;
+  float* dab = da + (size_t)b * HW * C;
+  const float inv = 1.0f / (float)HW;
+  if (w != nullptr) {
+    float dbacc = 0.f;
+    for (int p = warp; p < HW; p += 8) {
+      float t = 0.f;
+      for (int c = lane; c < C; c += 32) t = fmaf(ab[(size_t)p * C + c], gp[c], t);
+      t = warp_sum(t) * inv;
+      const float s = gb[p];
+      const float d = s * (1.0f - s) * t;
+      if (lane == 0) { du[p] = d; dbacc += d; }
+    }
+    __shared__ float dbs[8];
+    if (lane == 0) dbs[warp] = dbacc;
+    __syncthreads();
+    if (tid == 0 && db0 != nullptr) {
+      float s = 0.f;
+      for (int k = 0; k < 8; ++k) s += dbs[k];
+      atomicAdd(db0, s);
+    }
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += 256) {
+    const float g = gp[c] * inv;
+    if (w != nullptr) {
+      const float wc = w[c];
+      float dwacc = 0.f;
+      for (int p = 0; p < HW; ++p) {
+        const float av = ab[(size_t)p * C + c];
+        dab[(size_t)p * C + c] = fmaf(g, gb[p], du[p] * wc);
+        dwacc = fmaf(du[p], av, dwacc);
+      }
+      atomicAdd(dw + c, dwacc);
+    } else {
+      for (int p = 0; p < HW; ++p) dab[(size_t)p * C + c] = g;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ projection head
+// ws layout (floats): z [B*N] | mean [N] | invstd [N] | scratch [B*N]
+__global__ void head_linear_kernel(const float* __restrict__ x, int B, int K, int N, const float* __restrict__ W,
+                                   const float* __restrict__ bias, float* __restrict__ z) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * N) return;
+  const int n = idx % N, b = idx / N;
+  const float* xr = x + (size_t)b * K;
+  const float* wr = W + (size_t)n * K;
+  float s = 0.f;
+  for (int k = 0; k < K; ++k) s = fmaf(xr[k], wr[k], s);
+  z[idx] = s + (bias != nullptr ? bias[n] : 0.f);
+}
+
+// one CTA (128 threads) per feature n: batch statistics (two-pass) + running-stat update
+__global__ void __launch_bounds__(128)
+head_bn_stats_kernel(const float* __restrict__ z, int B, int N, float* __restrict__ rmean, float* __restrict__ rvar,
+                     int64_t* __restrict__ nbt, float momentum, float eps, int training, float* __restrict__ mean_o,
+                     float* __restrict__ invstd_o) {
+  __shared__ double sh[4];
+  __shared__ double mu_s;
+  const int n = blockIdx.x, tid = threadIdx.x;
+  if (!training) {
+    if (tid == 0) { mean_o[n] = rmean[n]; invstd_o[n] = 1.0f / sqrtf(rvar[n] + eps); }
+    return;
+  }
+  double s = 0.0;
+  for (int b = tid; b < B; b += 128) s += (double)z[(size_t)b * N + n];
+  s = warp_sum(s);
+  if ((tid & 31) == 0) sh[tid >> 5] = s;
+  __syncthreads();
+  if (tid == 0) mu_s = (sh[0] + sh[1] + sh[2] + sh[3]) / (double)B;
+  __syncthreads();
+  const double mu = mu_s;
+  double q = 0.0;
+  for (int b = tid; b < B; b += 128) { const double d = (double)z[(size_t)b * N + n] - mu; q += d * d; }
+  q = warp_sum(q);
+  __syncthreads();
+  if ((tid & 31) == 0) sh[tid >> 5] = q;
+  __syncthreads();
+  if (tid == 0) {
+    const double var = (sh[0] + sh[1] + sh[2] + sh[3]) / (double)B;
+    mean_o[n] = (float)mu;
+    invstd_o[n] = (float)(1.0 / sqrt(var + (double)eps));
+    if (rmean != nullptr) {
+      const double unbiased = B > 1 ? var * (double)B / (double)(B - 1) : var;
+      rmean[n] = (1.f - momentum) * rmean[n] + momentum * (float)mu;
+      rvar[n] = (1.f - momentum) * rvar[n] + momentum * (float)unbiased;
+    }
+    if (n == 0 && nbt != nullptr) nbt[0] += 1;
+  }
+}
+
+// warp per row: zn = (z-mu)*invstd*gamma+beta ; e = zn / max(||zn||, 1e-12)
+__global__ void __launch_bounds__(256)
+head_normalize_kernel(const float* __restrict__ z, int B, int N, const float* __restrict__ mean, const float* __restrict__ invstd,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ emb) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float ss = 0.f;
+  for (int n = lane; n < N; n += 32) {
+    const float v = fmaf((z[(size_t)row * N + n] - mean[n]) * invstd[n], gamma[n], beta[n]);
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int n = lane; n < N; n += 32) {
+    const float v = fmaf((z[(size_t)row * N + n] - mean[n]) * invstd[n], gamma[n], beta[n]);
+    emb[(size_t)row * N + n] = v * inv;
+  }
+}
+
+// warp per row: dzn = (demb - e (e.demb)) / ||zn||   -> scratch
+__global__ void __launch_bounds__(256)
+head_normalize_bwd_kernel(const float* __restrict__ demb, const float* __restrict__ z, int B, int N, const float* __restrict__ mean,
+                          const float* __restrict__ invstd, const float* __restrict__ gamma, const float* __restrict__ beta,
+                          float* __restrict__ dzn) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= B) return;
+  float ss = 0.f, dot = 0.f;
+  for (int n = lane; n < N; n += 32) {
+    const float v = fmaf((z[(size_t)row * N + n] - mean[n]) * invstd[n], gamma[n], beta[n]);
+    ss = fmaf(v, v, ss);
+    dot = fmaf(v, demb[(size_t)row * N + n], dot);
+  }
+  ss = warp_sum(ss);
+  dot = warp_sum(dot);
+  const float nrm = sqrtf(ss);
+  const bool clamped = nrm < 1e-12f;           // F.normalize: x / clamp_min(norm, eps) -> constant denominator
+  const float inv = 1.0f / fmaxf(nrm, 1e-12f);
+  for (int n = lane; n < N; n += 32) {
+    const float v = fmaf((z[(size_t)row * N + n] - mean[n]) * invstd[n], gamma[n], beta[n]);
+    const float g = demb[(size_t)row * N + n];
+    dzn[(size_t)row * N + n] = clamped ? g * inv : (g - v * inv * (dot * inv)) * inv;
+  }
+}
+
+// one CTA per feature: BatchNorm1d backward in place on dzn -> dz
+__global__ void __launch_bounds__(128)
+head_bn_bwd_kernel(float* __restrict__ dzn, const float* __restrict__ z, int B, int N, const float* __restrict__ mean,
+                   const float* __restrict__ invstd, const float* __restrict__ gamma, int training, float* __restrict__ dgamma,
+                   float* __restrict__ dbeta, float* __restrict__ dbias) {
+  __shared__ double sh[2][4];
+  __shared__ float bc[2];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const float mu = mean[n], is = invstd[n], g = gamma[n];
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = tid; b < B; b += 128) {
+    const float d = dzn[(size_t)b * N + n];
+    s1 += (double)d;
+    s2 += (double)d * (double)((z[(size_t)b * N + n] - mu) * is);
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((tid & 31) == 0) { sh[0][tid >> 5] = s1; sh[1][tid >> 5] = s2; }
+  __syncthreads();
+  if (tid == 0) {
+    const double a = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3], c = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3];
+    bc[0] = (float)a; bc[1] = (float)c;
+    if (dbeta != nullptr) dbeta[n] = (float)a;
+    if (dgamma != nullptr) dgamma[n] = (float)c;
+  }
+  __syncthreads();
+  const float sdz = bc[0], sdzx = bc[1], invB = 1.0f / (float)B;
+  double sb = 0.0;
+  for (int b = tid; b < B; b += 128) {
+    const float d = dzn[(size_t)b * N + n];
+    float r;
+    if (training) {
+      const float xhat = (z[(size_t)b * N + n] - mu) * is;
+      r = g * is * (d - sdz * invB - xhat * sdzx * invB);
+    } else {
+      r = g * is * d;
+    }
+    dzn[(size_t)b * N + n] = r;
+    sb += (double)r;
+  }
+  sb = warp_sum(sb);
+  __syncthreads();
+  if ((tid & 31) == 0) sh[0][tid >> 5] = sb;
+  __syncthreads();
+  if (tid == 0 && dbias != nullptr) dbias[n] = (float)(sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]);
+}
+
+// dW[n,k] = sum_b dz[b,n] x[b,k]
+__global__ void head_dw_kernel(const float* __restrict__ dz, const float* __restrict__ x, int B, int K, int N, float* __restrict__ dW) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * K) return;
+  const int k = idx % K, n = idx / K;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s = fmaf(dz[(size_t)b * N + n], x[(size_t)b * K + k], s);
+  dW[idx] = s;
+}
+// dx[b,k] = sum_n dz[b,n] W[n,k]
+__global__ void head_dx_kernel(const float* __restrict__ dz, const float* __restrict__ W, int B, int K, int N, float* __restrict__ dx) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * K) return;
+  const int k = idx % K, b = idx / K;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s = fmaf(dz[(size_t)b * N + n], W[(size_t)n * K + k], s);
+  dx[idx] = s;
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+extern "C" int pc_attn_pool_fwd(const float* a, int B, int HW, int C, const float* w, const float* b0, float* gate,
+                                float* pooled, pc_stream_t stream) {
+  PC_REQUIRE(a && gate && pooled && B > 0 && HW > 0 && C > 0, PC_EINVAL, "pc_attn_pool_fwd: bad arguments");
+  attn_pool_fwd_kernel<<<B, 256, 0, stream>>>(a, HW, C, w, b0, gate, pooled);
+  PC_LAUNCH_CHECK("attn_pool_fwd_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_attn_pool_bwd(const float* a, const float* gate, const float* dpooled, int B, int HW, int C, const float* w,
+                                float* da, float* dw, float* db0, pc_stream_t stream) {
+  PC_REQUIRE(a && gate && dpooled && da && B > 0 && HW > 0 && C > 0, PC_EINVAL, "pc_attn_pool_bwd: bad arguments");
+  PC_REQUIRE(w == nullptr || (dw != nullptr && db0 != nullptr), PC_EINVAL, "pc_attn_pool_bwd: dw/db0 required with attention");
+  PC_REQUIRE(HW <= 10240, PC_EUNSUPPORTED, "pc_attn_pool_bwd: HW=%d too large", HW);
+  if (w != nullptr) {
+    PC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C, stream));
+    PC_CUDA(cudaMemsetAsync(db0, 0, sizeof(float), stream));
+  }
+  attn_pool_bwd_kernel<<<B, 256, sizeof(float) * HW, stream>>>(a, gate, dpooled, HW, C, w, da, dw, db0);
+  PC_LAUNCH_CHECK("attn_pool_bwd_kernel");
+  return PC_OK;
+}
+
+extern "C" size_t pc_head_workspace(int B, int K, int N) {
+  (void)K;
+  return sizeof(float) * ((size_t)2 * B * N + 2 * (size_t)N);
+}
+
+extern "C" int pc_head_fwd(const float* x, int B, int K, int N, const float* W, const float* bias, const float* gamma,
+                           const float* beta, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                           float momentum, float eps, int training, float* emb, void* ws, pc_stream_t stream) {
+  PC_REQUIRE(x && W && gamma && beta && emb && ws && B > 0 && K > 0 && N > 0, PC_EINVAL, "pc_head_fwd: bad arguments");
+  PC_REQUIRE(!training || B > 1, PC_EINVAL, "Expected more than 1 value per channel when training");
+  PC_REQUIRE(training || (running_mean && running_var), PC_EINVAL, "pc_head_fwd: eval mode needs running statistics");
+  float* z = static_cast<float*>(ws);
+  float* mean = z + (size_t)B * N;
+  float* invstd = mean + N;
+  head_linear_kernel<<<ceil_div((long long)B * N, 128), 128, 0, stream>>>(x, B, K, N, W, bias, z);
+  PC_LAUNCH_CHECK("head_linear_kernel");
+  head_bn_stats_kernel<<<N, 128, 0, stream>>>(z, B, N, running_mean, running_var, num_batches_tracked, momentum, eps, training, mean, invstd);
+  PC_LAUNCH_CHECK("head_bn_stats_kernel");
+  head_normalize_kernel<<<ceil_div(B, 8), 256, 0, stream>>>(z, B, N, mean, invstd, gamma, beta, emb);
+  PC_LAUNCH_CHECK("head_normalize_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_head_bwd(const float* demb, const float* x, int B, int K, int N, const float* W, const float* gamma,
+                           const float* beta, int training, void* ws, float* dx, float* dW, float* dbias, float* dgamma,
+                           float* dbeta, pc_stream_t stream) {
+  PC_REQUIRE(demb && x && W && gamma && beta && ws && dx && dW && B > 0 && K > 0 && N > 0, PC_EINVAL, "pc_head_bwd: bad arguments");
+  float* z = static_cast<float*>(ws);
+  float* mean = z + (size_t)B * N;
+  float* invstd = mean + N;
+  float* dz = invstd + N;
+  head_normalize_bwd_kernel<<<ceil_div(B, 8), 256, 0, stream>>>(demb, z, B, N, mean, invstd, gamma, beta, dz);
+  PC_LAUNCH_CHECK("head_normalize_bwd_kernel");
+  head_bn_bwd_kernel<<<N, 128, 0, stream>>>(dz, z, B, N, mean, invstd, gamma, training, dgamma, dbeta, dbias);
+  PC_LAUNCH_CHECK("head_bn_bwd_kernel");
+  head_dw_kernel<<<ceil_div((long long)N * K, 128), 128, 0, stream>>>(dz, x, B, K, N, dW);
+  PC_LAUNCH_CHECK("head_dw_kernel");
+  head_dx_kernel<<<ceil_div((long long)B * K, 128), 128, 0, stream>>>(dz, W, B, K, N, dx);
+  PC_LAUNCH_CHECK("head_dx_kernel");
+  return PC_OK;
+}

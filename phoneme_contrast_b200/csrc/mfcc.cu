@@ -1,0 +1,402 @@
+// MFCC / log-mel front end with the view augmentations fused into the epilogue.
+//
+// One CTA per clip: frames are loaded (coalesced, reflect-padded, Hann-windowed), transformed with an
+// in-shared-memory mixed-radix real FFT (400 real points = one 200-point complex FFT, 200 = 8 x 5 x 5,
+// + split post-processing), reduced through the sparse (banded) mel filterbank, and kept as a
+// log-mel tile [n_mels][T] in shared memory. Each view of the clip (gain, time/freq mask, noise --
+// src/datasets/dataset.py:79-98) is then a cheap epilogue over that tile: gain is a dB offset, the
+// top_db clamp needs the clip-wide maximum (hence the resident tile), the DCT-II is a small
+// shared-memory contraction, masks / noise are applied as the result is stored. The spectrogram is
+// computed ONCE per clip no matter how many views are emitted.
+//
+// Reference arithmetic (torchaudio 2.x, see oracle/mfcc_oracle.py for the line-by-line restatement):
+//   stft(center, reflect, periodic Hann 400, hop 160) -> |.|^2 -> fb[201,80] -> 10 log10(max(.,1e-10))
+//   -> max(., amax - 80) -> dct[80,40]           (functional.py:123-144, 390-405; _transforms.py:701-718)
+#include "common.cuh"
+
+namespace pc {
+
+constexpr int FE_NFFT = 400, FE_NC = 200, FE_FC = 16;   // complex points, frames per chunk
+constexpr int FE_ZLD = FE_NC + 1;                       // float2 row stride (odd -> fewer bank conflicts)
+constexpr int FE_PLD = 204;
+constexpr int FE_THREADS = 256;
+constexpr float FE_LOG_FLOOR = 1e-37f;
+
+struct FeParams {
+  const float* wave; int n_clips, S, wave_ld;
+  const float* window; const int* fb_start; const int* fb_len; const float* fb_w; const float* dct; const float* tw;
+  int hop, n_mels, n_mfcc, T, TLD, Lsz;
+  const PcViewDesc* views; int n_views, views_per_clip;
+  const float* noise; int kind, clamp_mode; float top_db; const float* clamp_ref; float* clip_max_out; float* out;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+__device__ __forceinline__ void dft4(const float2 y[4], float2 Y[4]) {
+  const float2 c0 = cadd(y[0], y[2]), c1 = csub(y[0], y[2]), c2 = cadd(y[1], y[3]), c3 = cmul_mi(csub(y[1], y[3]));
+  Y[0] = cadd(c0, c2); Y[1] = cadd(c1, c3); Y[2] = csub(c0, c2); Y[3] = csub(c1, c3);
+}
+__device__ __forceinline__ void dft8(float2 x[8]) {
+  const float r = 0.70710678118654752f;
+  float2 a[4], b[4], E[4], O[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { a[j] = cadd(x[j], x[j + 4]); b[j] = csub(x[j], x[j + 4]); }
+  b[1] = make_float2(r * (b[1].x + b[1].y), r * (b[1].y - b[1].x));       // * (1 - i)/sqrt2
+  b[2] = cmul_mi(b[2]);                                                   // * (-i)
+  b[3] = make_float2(r * (b[3].y - b[3].x), r * (-b[3].x - b[3].y));      // * (-1 - i)/sqrt2
+  dft4(a, E);
+  dft4(b, O);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { x[2 * q] = E[q]; x[2 * q + 1] = O[q]; }
+}
+__device__ __forceinline__ void dft5(float2 x[5]) {
+  const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f, s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;
+  const float2 t1 = cadd(x[1], x[4]), t2 = cadd(x[2], x[3]), t3 = csub(x[1], x[4]), t4 = csub(x[2], x[3]);
+  const float2 m1 = make_float2(x[0].x + c1 * t1.x + c2 * t2.x, x[0].y + c1 * t1.y + c2 * t2.y);
+  const float2 m2 = make_float2(x[0].x + c2 * t1.x + c1 * t2.x, x[0].y + c2 * t1.y + c1 * t2.y);
+  const float2 n1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+  const float2 n2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+  x[0] = make_float2(x[0].x + t1.x + t2.x, x[0].y + t1.y + t2.y);
+  // m - i n = (m.x + n.y, m.y - n.x) ; m + i n = (m.x - n.y, m.y + n.x)
+  x[1] = make_float2(m1.x + n1.y, m1.y - n1.x);
+  x[4] = make_float2(m1.x - n1.y, m1.y + n1.x);
+  x[2] = make_float2(m2.x + n2.y, m2.y - n2.x);
+  x[3] = make_float2(m2.x - n2.y, m2.y + n2.x);
+}
+
+// position of natural-order bin k (0..199) after the in-place 8 x 5 x 5 passes
+__device__ __forceinline__ int fft_pos(int k) {
+  const int k1 = k & 7, k2 = k >> 3;
+  const int d = k2 / 5, c = k2 - 5 * d;
+  return 25 * k1 + 5 * c + d;
+}
+
+__global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  // layout: Z [FC][ZLD] float2 | P [FC][PLD] | L [n_mels][TLD] | win [400] | W200 [200] float2 | W400 [201] float2 | dct [n_mels*n_mfcc]
+  float2* Z = reinterpret_cast<float2*>(smem_raw);
+  float* P = reinterpret_cast<float*>(Z + FE_FC * FE_ZLD);
+  float* L = P + FE_FC * FE_PLD;
+  float* win = L + p.Lsz;   // Lsz = n_mels*TLD rounded up to 4 floats (keeps float2/float4 tables aligned)
+  float2* W200 = reinterpret_cast<float2*>(win + FE_NFFT);
+  float2* W400 = W200 + 200;
+  float* dcts = reinterpret_cast<float*>(W400 + 202);
+  __shared__ float red[FE_THREADS / 32];
+  __shared__ float lmax_s;
+
+  const int tid = threadIdx.x;
+  const int V = p.views_per_clip;
+  const int view0 = blockIdx.x * V;
+  const int clip = p.views != nullptr ? p.views[view0].clip : blockIdx.x;
+  const float* x = p.wave + (size_t)clip * p.wave_ld;
+  const int S = p.S, T = p.T;
+
+  for (int i = tid; i < FE_NFFT; i += FE_THREADS) win[i] = p.window[i];
+  for (int i = tid; i < 200; i += FE_THREADS) W200[i] = make_float2(p.tw[2 * i], p.tw[2 * i + 1]);
+  for (int i = tid; i < 201; i += FE_THREADS) W400[i] = make_float2(p.tw[400 + 2 * i], p.tw[400 + 2 * i + 1]);
+  if (p.kind == PC_FE_MFCC)
+    for (int i = tid; i < p.n_mels * p.n_mfcc; i += FE_THREADS) dcts[i] = p.dct[i];
+  __syncthreads();
+
+  for (int f0 = 0; f0 < T; f0 += FE_FC) {
+    const int nf = min(FE_FC, T - f0);
+    // ---- P1: load, reflect-pad, window, pack even/odd samples into complex points
+    for (int i = tid; i < nf * FE_NC; i += FE_THREADS) {
+      const int fl = i / FE_NC, n = i - fl * FE_NC;
+      const int base = (f0 + fl) * p.hop - FE_NFFT / 2 + 2 * n;
+      int i0 = base, i1 = base + 1;
+      i0 = i0 < 0 ? -i0 : (i0 >= S ? 2 * (S - 1) - i0 : i0);
+      i1 = i1 < 0 ? -i1 : (i1 >= S ? 2 * (S - 1) - i1 : i1);
+      Z[fl * FE_ZLD + n] = make_float2(x[i0] * win[2 * n], x[i1] * win[2 * n + 1]);
+    }
+    __syncthreads();
+    // ---- A: 25 radix-8 butterflies per frame over stride-25 points, twiddle W200^(n2*k1)
+    for (int i = tid; i < nf * 25; i += FE_THREADS) {
+      const int fl = i / 25, n2 = i - fl * 25;
+      float2* z = Z + fl * FE_ZLD;
+      float2 v[8];
+#pragma unroll
+      for (int n1 = 0; n1 < 8; ++n1) v[n1] = z[25 * n1 + n2];
+      dft8(v);
+#pragma unroll
+      for (int k1 = 0; k1 < 8; ++k1) z[25 * k1 + n2] = k1 == 0 ? v[0] : cmul(v[k1], W200[n2 * k1]);
+    }
+    __syncthreads();
+    // ---- B1: radix-5 over a (stride 5), twiddle W25^(b*c) = W200^(8*b*c)
+    for (int i = tid; i < nf * 40; i += FE_THREADS) {
+      const int fl = i / 40, r = i - fl * 40;
+      const int k1 = r / 5, b = r - k1 * 5;
+      float2* z = Z + fl * FE_ZLD + 25 * k1 + b;
+      float2 v[5];
+#pragma unroll
+      for (int a = 0; a < 5; ++a) v[a] = z[5 * a];
+      dft5(v);
+#pragma unroll
+      for (int c = 0; c < 5; ++c) z[5 * c] = (c == 0 || b == 0) ? v[c] : cmul(v[c], W200[8 * b * c]);
+    }
+    __syncthreads();
+    // ---- B2: radix-5 over b (stride 1); output bin k = k1 + 8*(c + 5*d) stays at position 25*k1 + 5*c + d
+    for (int i = tid; i < nf * 40; i += FE_THREADS) {
+      const int fl = i / 40, r = i - fl * 40;
+      float2* z = Z + fl * FE_ZLD + 5 * r;   // r = 5*k1 + c
+      float2 v[5];
+#pragma unroll
+      for (int b = 0; b < 5; ++b) v[b] = z[b];
+      dft5(v);
+#pragma unroll
+      for (int d = 0; d < 5; ++d) z[d] = v[d];
+    }
+    __syncthreads();
+    // ---- post: real-FFT split, power spectrum bins k and 200-k together
+    for (int i = tid; i < nf * 101; i += FE_THREADS) {
+      const int fl = i / 101, k = i - fl * 101;
+      const float2* z = Z + fl * FE_ZLD;
+      const float2 zk = z[fft_pos(k % 200)];
+      const float2 zn = z[fft_pos((200 - k) % 200)];
+      // Xe = (zk + conj(zn))/2 ; Xo = -i (zk - conj(zn))/2 ; X[k] = Xe + W400^k Xo ; X[200-k] = conj(Xe - W400^k Xo)
+      const float2 xe = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
+      const float2 dd = make_float2(0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y));
+      const float2 xo = cmul_mi(dd);
+      const float2 wx = cmul(W400[k], xo);
+      const float2 a = cadd(xe, wx), b = csub(xe, wx);
+      P[fl * FE_PLD + k] = a.x * a.x + a.y * a.y;
+      P[fl * FE_PLD + 200 - k] = b.x * b.x + b.y * b.y;
+    }
+    __syncthreads();
+    // ---- mel: banded filterbank, stored as 10 log10(mel)
+    for (int i = tid; i < nf * p.n_mels; i += FE_THREADS) {
+      const int m = i / nf, fl = i - m * nf;   // fl fastest -> conflict-free L writes
+      const int s = p.fb_start[m], len = p.fb_len[m];
+      const float* wq = p.fb_w + m * PC_FB_MAXW;
+      float acc = 0.f;
+      for (int q = 0; q < len; ++q) acc = fmaf(P[fl * FE_PLD + s + q], __ldg(wq + q), acc);
+      L[m * p.TLD + f0 + fl] = 10.0f * log10f(fmaxf(acc, FE_LOG_FLOOR));
+    }
+    __syncthreads();
+  }
+
+  // ---- clip-wide maximum of the log-mel tile
+  float lm = -INFINITY;
+  for (int i = tid; i < p.n_mels * T; i += FE_THREADS) {
+    const int m = i / T, t = i - m * T;
+    lm = fmaxf(lm, L[m * p.TLD + t]);
+  }
+  lm = warp_max(lm);
+  if ((tid & 31) == 0) red[tid >> 5] = lm;
+  __syncthreads();
+  if (tid == 0) {
+    float v = red[0];
+    for (int w = 1; w < FE_THREADS / 32; ++w) v = fmaxf(v, red[w]);
+    lmax_s = v;
+  }
+  __syncthreads();
+  const float lmax = lmax_s;
+  const float amin_db = -100.0f;   // 10 log10(1e-10)
+
+  const int n_out = p.kind == PC_FE_MFCC ? p.n_mfcc : p.n_mels;
+  for (int v = 0; v < V; ++v) {
+    const int view = view0 + v;
+    if (view >= p.n_views) break;
+    PcViewDesc d;
+    if (p.views != nullptr) d = p.views[view];
+    else { d.gain = 1.f; d.t0 = d.t1 = d.f0 = d.f1 = 0; d.noise_level = 0.f; d.noise_seed = 0u; d.clip = clip; }
+    // gain g scales power by g^2: +20 log10|g| dB (dataset.py:165-167 multiplies the waveform)
+    const float G = d.gain == 1.0f ? 0.f : 20.0f * log10f(fabsf(d.gain));
+    const float vmax = fmaxf(lmax + G, amin_db);
+    float floor_db = -INFINITY;
+    if (p.clamp_mode == PC_CLAMP_PER_CLIP) floor_db = vmax - p.top_db;
+    else if (p.clamp_mode == PC_CLAMP_GIVEN) floor_db = p.clamp_ref[0] - p.top_db;
+    if (tid == 0 && p.clip_max_out != nullptr) p.clip_max_out[view] = vmax;
+    const float lo = fmaxf(amin_db, floor_db);
+    float* o = p.out + (size_t)view * n_out * T;
+    const float* nz = p.noise != nullptr ? p.noise + (size_t)view * n_out * T : nullptr;
+
+    if (p.kind == PC_FE_MFCC) {
+      const int n_cg = (p.n_mfcc + 7) >> 3;
+      for (int i = tid; i < n_cg * T; i += FE_THREADS) {
+        const int cg = i / T, t = i - cg * T;
+        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        const int c0 = cg * 8;
+        if (c0 + 8 <= p.n_mfcc && (p.n_mfcc & 3) == 0) {
+          for (int m = 0; m < p.n_mels; ++m) {
+            const float val = fmaxf(L[m * p.TLD + t] + G, lo);
+            const float4 d0 = *reinterpret_cast<const float4*>(dcts + m * p.n_mfcc + c0);
+            const float4 d1 = *reinterpret_cast<const float4*>(dcts + m * p.n_mfcc + c0 + 4);
+            acc[0] = fmaf(val, d0.x, acc[0]); acc[1] = fmaf(val, d0.y, acc[1]); acc[2] = fmaf(val, d0.z, acc[2]); acc[3] = fmaf(val, d0.w, acc[3]);
+            acc[4] = fmaf(val, d1.x, acc[4]); acc[5] = fmaf(val, d1.y, acc[5]); acc[6] = fmaf(val, d1.z, acc[6]); acc[7] = fmaf(val, d1.w, acc[7]);
+          }
+        } else {
+          for (int m = 0; m < p.n_mels; ++m) {
+            const float val = fmaxf(L[m * p.TLD + t] + G, lo);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (c0 + q < p.n_mfcc) acc[q] = fmaf(val, dcts[m * p.n_mfcc + c0 + q], acc[q]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = c0 + q;
+          if (c >= p.n_mfcc) break;
+          float r = acc[q];
+          if ((t >= d.t0 && t < d.t1) || (c >= d.f0 && c < d.f1)) r = 0.f;
+          if (d.noise_level != 0.f) {
+            float nv;
+            if (nz != nullptr) nv = nz[c * T + t];
+            else {
+              const uint4 rr = Philox::round10(make_uint4((uint32_t)(c * T + t), (uint32_t)view, 0x4e4f4953u, 0u), make_uint2(d.noise_seed, 0x70635f66u));
+              nv = Philox::normal2(rr.x, rr.y).x;
+            }
+            r = fmaf(nv, d.noise_level, r);
+          }
+          o[c * T + t] = r;
+        }
+      }
+    } else {
+      for (int i = tid; i < p.n_mels * T; i += FE_THREADS) {
+        const int m = i / T, t = i - m * T;
+        float r = fmaxf(L[m * p.TLD + t] + G, lo);
+        if ((t >= d.t0 && t < d.t1) || (m >= d.f0 && m < d.f1)) r = 0.f;
+        if (d.noise_level != 0.f) {
+          float nv;
+          if (nz != nullptr) nv = nz[i];
+          else {
+            const uint4 rr = Philox::round10(make_uint4((uint32_t)i, (uint32_t)view, 0x4e4f4953u, 0u), make_uint2(d.noise_seed, 0x70635f66u));
+            nv = Philox::normal2(rr.x, rr.y).x;
+          }
+          r = fmaf(nv, d.noise_level, r);
+        }
+        o[i] = r;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) reduce_max_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  __shared__ float red[8];
+  float v = -INFINITY;
+  for (int i = threadIdx.x; i < n; i += 256) v = fmaxf(v, x[i]);
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) v = fmaxf(v, red[w]);
+    out[0] = fmaxf(v, red[0]);
+  }
+}
+
+__global__ void augment_apply_kernel(const float* __restrict__ x, const PcViewDesc* __restrict__ views, int n_views, int F, int T,
+                                     const float* __restrict__ noise, float* __restrict__ out) {
+  const long long total = (long long)n_views * F * T;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % T);
+    const int f = (int)((idx / T) % F);
+    const int v = (int)(idx / ((long long)T * F));
+    const PcViewDesc d = views[v];
+    float r = x[idx];
+    if ((t >= d.t0 && t < d.t1) || (f >= d.f0 && f < d.f1)) r = 0.f;
+    if (d.noise_level != 0.f) {
+      float nv;
+      if (noise != nullptr) nv = noise[idx];
+      else {
+        const uint4 rr = Philox::round10(make_uint4((uint32_t)(f * T + t), (uint32_t)v, 0x4e4f4953u, 0u), make_uint2(d.noise_seed, 0x70635f66u));
+        nv = Philox::normal2(rr.x, rr.y).x;
+      }
+      r = fmaf(nv, d.noise_level, r);
+    }
+    out[idx] = r;
+  }
+}
+
+// torchaudio compute_deltas, win_length 5, replicate padding: d_t = sum_{k=-2..2} k x_{t+k} / 10
+__global__ void compute_deltas_kernel(const float* __restrict__ x, int rows, int T, float* __restrict__ out) {
+  const long long total = (long long)rows * T;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(idx % T);
+    const float* r = x + (idx - t);
+    float s = 0.f;
+#pragma unroll
+    for (int k = -2; k <= 2; ++k) {
+      int tt = t + k;
+      tt = tt < 0 ? 0 : (tt >= T ? T - 1 : tt);
+      s = fmaf((float)k, r[tt], s);
+    }
+    out[idx] = s / 10.0f;
+  }
+}
+
+}  // namespace pc
+
+using namespace pc;
+
+extern "C" int pc_frontend_fwd(const float* wave, int n_clips, int S, int wave_ld, const PcMfccConsts* c, const PcViewDesc* views,
+                               int n_views, const float* noise, int kind, int clamp_mode, float top_db, const float* clamp_ref,
+                               float* clip_max_out, float* out, pc_stream_t stream) {
+  PC_REQUIRE(wave && c && out && n_clips > 0 && S > 0 && wave_ld >= S, PC_EINVAL, "pc_frontend_fwd: bad arguments");
+  PC_REQUIRE(c->n_fft == FE_NFFT, PC_EUNSUPPORTED, "pc_frontend_fwd: n_fft=%d not built (the in-smem FFT is specialised for 400)", c->n_fft);
+  PC_REQUIRE(c->hop > 0 && c->n_mels > 0 && c->n_mels <= 128, PC_EUNSUPPORTED, "pc_frontend_fwd: hop=%d n_mels=%d unsupported", c->hop, c->n_mels);
+  PC_REQUIRE(kind == PC_FE_MFCC || kind == PC_FE_LOGMEL, PC_EINVAL, "pc_frontend_fwd: bad kind");
+  PC_REQUIRE(kind != PC_FE_MFCC || (c->n_mfcc > 0 && c->n_mfcc <= c->n_mels && c->dct), PC_EINVAL,
+             "Cannot select more MFCC coefficients than # mel bins");
+  PC_REQUIRE(S > FE_NFFT / 2, PC_EINVAL, "pc_frontend_fwd: reflect padding needs more than %d samples (got %d)", FE_NFFT / 2, S);
+  PC_REQUIRE(clamp_mode != PC_CLAMP_GIVEN || clamp_ref, PC_EINVAL, "pc_frontend_fwd: clamp_ref required");
+  PC_REQUIRE(c->window && c->fb_start && c->fb_len && c->fb_w && c->tw, PC_EINVAL, "pc_frontend_fwd: null constants");
+  int V = 1, n_ctas = n_clips;
+  if (views != nullptr) {
+    PC_REQUIRE(n_views > 0 && n_views % n_clips == 0, PC_EINVAL, "pc_frontend_fwd: n_views must be a multiple of n_clips (views grouped by clip)");
+    V = n_views / n_clips;
+  } else {
+    n_views = n_clips;
+  }
+  FeParams p;
+  p.wave = wave; p.n_clips = n_clips; p.S = S; p.wave_ld = wave_ld;
+  p.window = c->window; p.fb_start = c->fb_start; p.fb_len = c->fb_len; p.fb_w = c->fb_w; p.dct = c->dct; p.tw = c->tw;
+  p.hop = c->hop; p.n_mels = c->n_mels; p.n_mfcc = kind == PC_FE_MFCC ? c->n_mfcc : 0;
+  p.T = 1 + S / c->hop;
+  p.TLD = p.T | 1;
+  p.Lsz = (p.n_mels * p.TLD + 3) & ~3;
+  p.views = views; p.n_views = n_views; p.views_per_clip = V;
+  p.noise = noise; p.kind = kind; p.clamp_mode = clamp_mode; p.top_db = top_db; p.clamp_ref = clamp_ref;
+  p.clip_max_out = clip_max_out; p.out = out;
+  size_t smem = sizeof(float2) * FE_FC * FE_ZLD + sizeof(float) * (FE_FC * FE_PLD + (size_t)p.Lsz + FE_NFFT) +
+                sizeof(float2) * (200 + 202) + sizeof(float) * ((size_t)p.n_mels * p.n_mfcc + 4);
+  PC_REQUIRE(smem <= 227 * 1024, PC_EUNSUPPORTED, "pc_frontend_fwd: clip of %d samples (%d frames) needs %zu B shared memory (> 227 KB)", S, p.T, smem);
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    PC_CUDA(cudaFuncSetAttribute(frontend_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  frontend_kernel<<<n_ctas, FE_THREADS, smem, stream>>>(p);
+  PC_LAUNCH_CHECK("frontend_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_reduce_max(const float* x, int n, float* out, pc_stream_t stream) {
+  PC_REQUIRE(x && out && n > 0, PC_EINVAL, "pc_reduce_max: bad arguments");
+  reduce_max_kernel<<<1, 256, 0, stream>>>(x, n, out);
+  PC_LAUNCH_CHECK("reduce_max_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_augment_apply(const float* x, const PcViewDesc* views, int n_views, int F, int T, const float* noise, float* out,
+                                pc_stream_t stream) {
+  PC_REQUIRE(x && views && out && n_views > 0 && F > 0 && T > 0, PC_EINVAL, "pc_augment_apply: bad arguments");
+  const long long total = (long long)n_views * F * T;
+  int grid = ceil_div(total, 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  augment_apply_kernel<<<grid, 256, 0, stream>>>(x, views, n_views, F, T, noise, out);
+  PC_LAUNCH_CHECK("augment_apply_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_compute_deltas(const float* x, int rows, int T, float* out, pc_stream_t stream) {
+  PC_REQUIRE(x && out && rows > 0 && T > 0, PC_EINVAL, "pc_compute_deltas: bad arguments");
+  const long long total = (long long)rows * T;
+  int grid = ceil_div(total, 256);
+  if (grid > kNumSMs * 16) grid = kNumSMs * 16;
+  compute_deltas_kernel<<<grid, 256, 0, stream>>>(x, rows, T, out);
+  PC_LAUNCH_CHECK("compute_deltas_kernel");
+  return PC_OK;
+}

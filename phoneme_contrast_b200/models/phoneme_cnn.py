@@ -1,0 +1,397 @@
+"""PhonemeNet (cnn_small) and PhonemeNetDeep (cnn_deep): drop-ins for src/models/phoneme_cnn.py.
+
+Same registry names ("phoneme_cnn", "phoneme_cnn_deep"), same config keys and defaults, same module tree
+(hence identical state_dict keys -- SURVEY.md 8b -- so checkpoints interchange with the reference), same
+initialisation (phoneme_cnn.py:79-96, :258-272). The nn.Conv2d / nn.BatchNorm2d / nn.Linear children are
+parameter containers only: forward and backward of the WHOLE network run as one autograd node that
+sequences the sm_100a kernels of libpc_b200.so (NHWC activations, BatchNorm-apply/ReLU/Dropout folded into
+the next convolution's operand load, BatchNorm statistics accumulated in the convolution epilogue).
+There is no PyTorch/CPU fallback: a CPU input raises.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+from .. import ops
+from .base import BaseModel
+from .registry import model_registry
+
+_PREC = {"fp32": L.PREC_FP32, "tf32x3": L.PREC_TF32X3, "bf16": L.PREC_BF16}
+
+
+def _precision(config) -> int:
+    name = os.environ.get("PC_PRECISION") or config.get("precision", "fp32")
+    if name not in _PREC:
+        raise ValueError(f"precision must be one of {list(_PREC)}, got {name!r}")
+    return _PREC[name]
+
+
+def _init_weights(model: nn.Module) -> None:
+    """phoneme_cnn.py:79-96 / :258-272."""
+    for m in model.modules():
+        if isinstance(m, nn.Conv2d):
+            nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, (nn.BatchNorm2d, nn.BatchNorm1d)):
+            nn.init.constant_(m.weight, 1)
+            nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.Linear):
+            nn.init.normal_(m.weight, 0, 0.01)
+            nn.init.constant_(m.bias, 0)
+
+
+class SpatialAttention(nn.Module):
+    """1x1 conv C->1, sigmoid gate (phoneme_cnn.py:129-143); evaluated inside the fused attn_pool kernel."""
+
+    def __init__(self, in_channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, 1, kernel_size=1)
+
+
+class ResidualBlock(nn.Module):
+    """Parameter layout of phoneme_cnn.py:146-171."""
+
+    def __init__(self, in_channels: int, out_channels: int, stride: int = 1, dropout_rate: float = 0.1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_channels, out_channels, kernel_size=3, stride=stride, padding=1)
+        self.bn1 = nn.BatchNorm2d(out_channels)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1)
+        self.bn2 = nn.BatchNorm2d(out_channels)
+        self.dropout = nn.Dropout2d(dropout_rate)
+        self.shortcut = nn.Sequential()
+        if stride != 1 or in_channels != out_channels:
+            self.shortcut = nn.Sequential(nn.Conv2d(in_channels, out_channels, kernel_size=1, stride=stride),
+                                          nn.BatchNorm2d(out_channels))
+        self.stride = stride
+
+
+# =============================================================================================== engine
+class _Saved:
+    """Per-forward record kept for the backward pass."""
+
+
+class _StatSlots:
+    """One zeroed fp64 buffer holding the [2, C] sum / sum-of-squares accumulator of every BatchNorm layer."""
+
+    def __init__(self, channel_counts, device, enabled):
+        self.buf = torch.zeros(2 * sum(channel_counts), device=device, dtype=torch.float64) if enabled else None
+        self.off = 0
+
+    def take(self, c):
+        if self.buf is None:
+            return None
+        t = self.buf[self.off:self.off + 2 * c].view(2, c)
+        self.off += 2 * c
+        return t
+
+
+def _prep_input(x: torch.Tensor, in_channels: int) -> torch.Tensor:
+    if x.dim() != 4:
+        raise ValueError(f"expected input [batch, channels, freq, time], got shape {tuple(x.shape)}")
+    if not x.is_cuda:
+        raise RuntimeError("phoneme_contrast_b200 models run on CUDA only (no CPU fallback); move the input to the GPU")
+    if x.shape[1] != in_channels:
+        raise ValueError(f"expected {in_channels} input channel(s), got {x.shape[1]}")
+    if in_channels != 1:
+        raise NotImplementedError("the stem kernel covers in_channels == 1 (the reference's only configuration)")
+    return x.to(torch.float32).contiguous()   # [B,1,H,W] == NHWC [B,H,W,1]
+
+
+def _drop_masks(net, B, chans, training):
+    if not training or net.dropout_rate <= 0.0:
+        return [None] * len(chans)
+    if net._inject_drop is not None:
+        return list(net._inject_drop)
+    dev = next(net.parameters()).device
+    seed = torch.initial_seed() & 0xFFFFFFFFFFFF
+    net._drop_calls += 1
+    return [ops.dropout2d_mask(B, c, net.dropout_rate, seed, (net._drop_calls << 24) + (i << 20), dev) for i, c in enumerate(chans)]
+
+
+def _head(net, s, a, training):
+    att = net.attention.conv if net.use_attention else None
+    w_att = att.weight.view(-1) if att is not None else None
+    s.pooled, s.gate = ops.attn_pool_fwd(a, w_att, att.bias if att is not None else None)
+    emb, s.head_ws = ops.head_fwd(s.pooled, net.projection[0], net.projection[1], training)
+    return emb
+
+
+def _head_bwd(net, s, demb, grads, training):
+    lin, bn = net.projection[0], net.projection[1]
+    dpooled, *_ = ops.head_bwd(demb, s.pooled, lin.weight, bn.weight, bn.bias, training, s.head_ws, dW=grads[lin.weight],
+                               dbias=grads[lin.bias], dgamma=grads[bn.weight], dbeta=grads[bn.bias])
+    if net.use_attention:
+        att = net.attention.conv
+        da, _, _ = ops.attn_pool_bwd(s.a_last, s.gate, dpooled, att.weight.view(-1), dw=grads[att.weight].view(-1),
+                                     db0=grads[att.bias])
+    else:
+        da, _, _ = ops.attn_pool_bwd(s.a_last, s.gate, dpooled, None)
+    return da
+
+
+def _small_forward(net, x, training):
+    s = _Saved()
+    prec = net._prec
+    B, _, H, W = x.shape
+    s.x = x
+    blocks = net.conv_blocks
+    chans = [blocks[b][0].out_channels for b in range(3)]
+    s.drop = _drop_masks(net, B, chans, training)
+    slots = _StatSlots([c for c in chans for _ in range(2)], x.device, training)
+    s.layers = []
+    cur, cin, h, w = x, 1, H, W
+    for b in range(3):
+        convA, bnA, convB, bnB = blocks[b][0], blocks[b][1], blocks[b][3], blocks[b][4]
+        co = chans[b]
+        gA = ops.conv_geom(B, h, w, cin, co, 3, 1, 1)
+        if cin == 1:
+            wfA, wdA = convA.weight, None          # stem kernel reads OIHW directly; no dgrad into the input
+        else:
+            wfA, wdA = ops.pack_conv_weight(convA.weight)
+        stA = slots.take(co)
+        yA = ops.conv_fwd(cur, wfA, convA.bias, gA, None, stA, prec)
+        coA = ops.bn_finalize(stA, B * gA.Ho * gA.Wo, bnA, training)
+        gB = ops.conv_geom(B, h, w, co, co, 3, 1, 1)
+        wfB, wdB = ops.pack_conv_weight(convB.weight)
+        stB = slots.take(co)
+        yB = ops.conv_fwd(yA, wfB, convB.bias, gB, dict(scale=coA.scale, shift=coA.shift, relu=True), stB, prec)
+        coB = ops.bn_finalize(stB, B * h * w, bnB, training)
+        pool = 2 if b < 2 else 0
+        out, _ = ops.bn_act_fwd(yB, coB, pool, s.drop[b])
+        s.layers.append(dict(xin=cur, gA=gA, gB=gB, yA=yA, yB=yB, coA=coA, coB=coB, wdA=wdA, wdB=wdB, pool=pool))
+        cur, cin = out, co
+        h, w = ops.pool_dims(h, w, pool)
+    s.a_last = cur
+    emb = _head(net, s, cur, training)
+    return emb, s
+
+
+def _small_backward(net, s, demb, grads, training=True):
+    prec = net._prec
+    blocks = net.conv_blocks
+    dout = _head_bwd(net, s, demb, grads, training)
+    for b in (2, 1, 0):
+        convA, bnA, convB, bnB = blocks[b][0], blocks[b][1], blocks[b][3], blocks[b][4]
+        ly = s.layers[b]
+        dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias])
+        xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
+        ops.conv_wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], grads[convB.bias], prec)
+        dA = ops.conv_dgrad(dyB, ly["wdB"], ly["gB"], prec=prec)
+        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias])
+        ops.conv_wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], grads[convA.bias], prec)
+        if b > 0:
+            dout = ops.conv_dgrad(dyA, ly["wdA"], ly["gA"], prec=prec)
+
+
+def _deep_forward(net, x, training):
+    s = _Saved()
+    prec = net._prec
+    B, _, H, W = x.shape
+    s.x = x
+    hd = net.hidden_dims
+    conv0, bn0 = net.init_conv[0], net.init_conv[1]
+    s.drop = _drop_masks(net, B, list(hd), training)
+    slots = _StatSlots([hd[0]] + [c for c in hd for _ in range(3)], x.device, training)
+    st = slots.take
+
+    g0 = ops.conv_geom(B, H, W, 1, hd[0], 7, 1, 3)
+    st0 = st(hd[0])
+    y0 = ops.conv_fwd(x, conv0.weight, conv0.bias, g0, None, st0, prec)
+    co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
+    p0, argmax0 = ops.bn_act_fwd(y0, co0, 3, None)
+    s.stem = dict(g=g0, y=y0, co=co0, argmax=argmax0)
+    s.blocks = []
+    cur, cin = p0, hd[0]
+    h, w = p0.shape[1], p0.shape[2]
+    for i, blk in enumerate(net.conv_blocks):
+        co = hd[i]
+        stride = blk.stride
+        g1 = ops.conv_geom(B, h, w, cin, co, 3, stride, 1)
+        wf1, wd1 = ops.pack_conv_weight(blk.conv1.weight)
+        st1 = st(co)
+        y1 = ops.conv_fwd(cur, wf1, blk.conv1.bias, g1, None, st1, prec)
+        c1 = ops.bn_finalize(st1, B * g1.Ho * g1.Wo, blk.bn1, training)
+        g2 = ops.conv_geom(B, g1.Ho, g1.Wo, co, co, 3, 1, 1)
+        wf2, wd2 = ops.pack_conv_weight(blk.conv2.weight)
+        st2 = st(co)
+        y2 = ops.conv_fwd(y1, wf2, blk.conv2.bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True, drop=s.drop[i]), st2, prec)
+        c2 = ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk.bn2, training)
+        rec = dict(xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, wd1=wd1, wd2=wd2, proj=len(blk.shortcut) > 0)
+        if rec["proj"]:
+            convs, bns = blk.shortcut[0], blk.shortcut[1]
+            gs = ops.conv_geom(B, h, w, cin, co, 1, stride, 0)
+            wfs, wds = ops.pack_conv_weight(convs.weight)
+            sts = st(co)
+            ys = ops.conv_fwd(cur, wfs, convs.bias, gs, None, sts, prec)
+            cs = ops.bn_finalize(sts, B * gs.Ho * gs.Wo, bns, training)
+            out = ops.bn_add_relu_fwd(y2, c2, ys, cs)
+            rec.update(gs=gs, ys=ys, cs=cs, wds=wds)
+        else:
+            out = ops.bn_add_relu_fwd(y2, c2, cur, None)
+        rec["out"] = out
+        s.blocks.append(rec)
+        cur, cin, h, w = out, co, g1.Ho, g1.Wo
+    s.a_last = cur
+    emb = _head(net, s, cur, training)
+    return emb, s
+
+
+def _deep_backward(net, s, demb, grads, training=True):
+    prec = net._prec
+    dout = _head_bwd(net, s, demb, grads, training)
+    for i in reversed(range(len(s.blocks))):
+        blk = net.conv_blocks[i]
+        r = s.blocks[i]
+        g2 = (grads[blk.bn2.weight], grads[blk.bn2.bias])
+        if r["proj"]:
+            convs, bns = blk.shortcut[0], blk.shortcut[1]
+            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], r["ys"], r["cs"], g2,
+                                                  (grads[bns.weight], grads[bns.bias]))
+        else:
+            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None)
+        xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
+        ops.conv_wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec)
+        dA1 = ops.conv_dgrad(dy2, r["wd2"], r["g2"], prec=prec)
+        dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias])
+        ops.conv_wgrad(r["xin"], dy1, r["g1"], None, grads[blk.conv1.weight], grads[blk.conv1.bias], prec)
+        if r["proj"]:
+            ops.conv_wgrad(r["xin"], dysc, r["gs"], None, grads[convs.weight], grads[convs.bias], prec)
+            dxin = ops.conv_dgrad(dysc, r["wds"], r["gs"], prec=prec)
+        else:
+            dxin = dysc                                        # identity shortcut: d(out)/d(xin) passes g through
+        ops.conv_dgrad(dy1, r["wd1"], r["g1"], out=dxin, accumulate=True, prec=prec)
+        dout = dxin
+    conv0, bn0 = net.init_conv[0], net.init_conv[1]
+    st = s.stem
+    dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias])
+    ops.conv_wgrad(s.x, dy0, st["g"], None, grads[conv0.weight], grads[conv0.bias], prec)
+
+
+class _NetFunction(torch.autograd.Function):
+    """One autograd node for the whole network: forward saves the per-layer record, backward fills ONE flat
+    gradient buffer and hands out views of it (so the optimiser / the DP all-reduce can work on one bucket)."""
+
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        emb, saved = net._engine_forward(x, True)
+        ctx.net = net
+        ctx.saved = saved
+        return emb
+
+    @staticmethod
+    def backward(ctx, demb):
+        net, saved = ctx.net, ctx.saved
+        params = net._param_list
+        flat = torch.empty(net._n_param_elems, device=demb.device, dtype=torch.float32)
+        views, grads, off = [], {}, 0
+        for p in params:
+            v = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+            views.append(v)
+            grads[p] = v
+        net._engine_backward(saved, demb.contiguous().to(torch.float32), grads)
+        ctx.saved = None
+        del grads, flat
+        return (None, None, *views)
+
+
+class _FusedNet(BaseModel):
+    _inject_drop = None
+    _drop_calls = 0
+
+    def _finish_init(self):
+        _init_weights(self)
+        self._prec = _precision(self.config)
+
+    @property
+    def _param_list(self):
+        return list(self.parameters())
+
+    @property
+    def _n_param_elems(self):
+        return sum(p.numel() for p in self.parameters())
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        x = _prep_input(x, self.in_channels)
+        params = self._param_list
+        if self.training and x.shape[0] * 1 < 2:
+            raise ValueError("Expected more than 1 value per channel when training")   # nn.BatchNorm1d raises the same
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _NetFunction.apply(self, x, *params)
+        with torch.no_grad():
+            emb, _ = self._engine_forward(x, self.training)
+        return emb
+
+
+@model_registry.register("phoneme_cnn")
+class PhonemeNet(_FusedNet):
+    """CNN for phoneme representation learning with attention (config keys of phoneme_cnn.py:18-21)."""
+
+    def __init__(self, config: dict):
+        super().__init__(config)
+        self.in_channels = config.get("in_channels", 1)
+        self.embedding_dim = config.get("embedding_dim", 128)
+        self.use_attention = config.get("use_attention", True)
+        self.dropout_rate = config.get("dropout_rate", 0.1)
+        chans = [(self.in_channels, 32), (32, 64), (64, 128)]
+        blocks = []
+        for i, (ci, co) in enumerate(chans):
+            layers = [nn.Conv2d(ci, co, kernel_size=3, padding=1), nn.BatchNorm2d(co), nn.ReLU(inplace=True),
+                      nn.Conv2d(co, co, kernel_size=3, padding=1), nn.BatchNorm2d(co), nn.ReLU(inplace=True)]
+            if i < 2:
+                layers.append(nn.MaxPool2d(2, 2))
+            layers.append(nn.Dropout2d(self.dropout_rate))
+            blocks.append(nn.Sequential(*layers))
+        self.conv_blocks = nn.ModuleList(blocks)
+        if self.use_attention:
+            self.attention = SpatialAttention(128)
+        self.global_pool = nn.AdaptiveAvgPool2d(1)
+        self.projection = nn.Sequential(nn.Linear(128, self.embedding_dim), nn.BatchNorm1d(self.embedding_dim))
+        self._finish_init()
+
+    def _engine_forward(self, x, training):
+        return _small_forward(self, x, training)
+
+    def _engine_backward(self, saved, demb, grads):
+        return _small_backward(self, saved, demb, grads)
+
+
+@model_registry.register("phoneme_cnn_deep")
+class PhonemeNetDeep(_FusedNet):
+    """Deep residual CNN (config keys of phoneme_cnn.py:195-200)."""
+
+    def __init__(self, config: dict):
+        super().__init__(config)
+        self.in_channels = config.get("in_channels", 1)
+        self.embedding_dim = config.get("embedding_dim", 128)
+        self.use_attention = config.get("use_attention", True)
+        self.dropout_rate = config.get("dropout_rate", 0.2)
+        self.hidden_dims = list(config.get("hidden_dims", [64, 128, 256, 512]))
+        self.use_residual = config.get("use_residual", True)
+        if not self.use_residual:
+            raise NotImplementedError("use_residual=False is not covered by the fused engine (never run by the reference's configs)")
+        hd = self.hidden_dims
+        self.init_conv = nn.Sequential(nn.Conv2d(self.in_channels, hd[0], kernel_size=7, stride=1, padding=3),
+                                       nn.BatchNorm2d(hd[0]), nn.ReLU(inplace=True),
+                                       nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
+        layers, cin = [], hd[0]
+        for i, co in enumerate(hd):
+            layers.append(ResidualBlock(cin, co, 1 if i == 0 else 2, self.dropout_rate))
+            cin = co
+        self.conv_blocks = nn.Sequential(*layers)
+        if self.use_attention:
+            self.attention = SpatialAttention(hd[-1])
+        self.global_pool = nn.AdaptiveAvgPool2d(1)
+        self.projection = nn.Sequential(nn.Linear(hd[-1], self.embedding_dim), nn.BatchNorm1d(self.embedding_dim))
+        self._finish_init()
+
+    def _engine_forward(self, x, training):
+        return _deep_forward(self, x, training)
+
+    def _engine_backward(self, saved, demb, grads):
+        return _deep_backward(self, saved, demb, grads)

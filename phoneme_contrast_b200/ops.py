@@ -1,0 +1,237 @@
+"""Tensor-level wrappers over the C ABI (one Python function per entry point of include/phoneme_contrast.h).
+
+torch is used here only for device memory (torch.empty) and the current stream; every computation is a
+kernel of libpc_b200.so. Activations are NHWC fp32.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import PcConvGeom, PcInXform, call, ptr, stream
+
+F32 = torch.float32
+
+
+def conv_geom(B, H, W, Cin, Cout, k, stride, pad) -> PcConvGeom:
+    Ho = (H + 2 * pad - k) // stride + 1
+    Wo = (W + 2 * pad - k) // stride + 1
+    return PcConvGeom(B, H, W, Cin, Ho, Wo, Cout, k, k, stride, pad)
+
+
+def _xf(scale=None, shift=None, drop=None, relu=False):
+    if scale is None and drop is None and not relu:
+        return None
+    return PcInXform(ptr(scale), ptr(shift), ptr(drop), 1 if relu else 0)
+
+
+def pack_conv_weight(w: torch.Tensor, want_fwd=True, want_dgrad=True):
+    O, I, R, S = w.shape
+    wf = torch.empty(R * S * I, O, device=w.device, dtype=F32) if want_fwd else None
+    wd = torch.empty(R * S * O, I, device=w.device, dtype=F32) if want_dgrad else None
+    call("pc_pack_conv_weight", ptr(w), O, I, R, S, ptr(wf), ptr(wd), stream())
+    return wf, wd
+
+
+def conv_fwd(x, w, bias, g: PcConvGeom, xform=None, stats=None, prec=L.PREC_FP32):
+    """x NHWC [B,H,W,Cin]; w = packed Wf (Cin>1) or the raw OIHW weight (Cin==1 stem)."""
+    y = torch.empty(g.B, g.Ho, g.Wo, g.Cout, device=x.device, dtype=F32)
+    xf = _xf(**xform) if xform else None
+    call("pc_conv_fwd", ptr(x), ptr(w), ptr(bias), C.byref(g), C.byref(xf) if xf is not None else None, ptr(y),
+         ptr(stats, torch.float64), prec, stream())
+    return y
+
+
+def conv_dgrad(dy, wd, g: PcConvGeom, out=None, accumulate=False, prec=L.PREC_FP32):
+    if out is None:
+        out = torch.empty(g.B, g.H, g.W, g.Cin, device=dy.device, dtype=F32)
+    call("pc_conv_dgrad", ptr(dy), ptr(wd), C.byref(g), ptr(out), 1 if accumulate else 0, prec, stream())
+    return out
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream-capture state); contents are dead after each call."""
+    key = (device, torch.cuda.is_current_stream_capturing())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
+        _ws_cache[key] = buf
+    return buf
+
+
+def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_FP32):
+    if dw is None:
+        dw = torch.empty(g.Cout, g.Cin, g.R, g.S, device=x.device, dtype=F32)
+    if db is None:
+        db = torch.empty(g.Cout, device=x.device, dtype=F32)
+    nbytes = int(L.lib().pc_conv_wgrad_workspace(C.byref(g)))
+    ws = _workspace(nbytes, x.device)
+    xf = _xf(**xform) if xform else None
+    call("pc_conv_wgrad", ptr(x), ptr(dy), C.byref(g), C.byref(xf) if xf is not None else None, ptr(dw), ptr(db),
+         ptr(ws, torch.uint8), ws.numel(), prec, stream())
+    return dw, db
+
+
+class BnCoeffs:
+    """scale/shift/mean/invstd of one BatchNorm for the current batch (or from running stats in eval)."""
+    __slots__ = ("scale", "shift", "mean", "invstd", "C")
+
+    def __init__(self, C_, device):
+        buf = torch.empty(4, C_, device=device, dtype=F32)
+        self.scale, self.shift, self.mean, self.invstd = buf[0], buf[1], buf[2], buf[3]
+        self.C = C_
+
+
+def bn_finalize(stats, count, bn: torch.nn.modules.batchnorm._BatchNorm, training: bool) -> BnCoeffs:
+    C_ = bn.num_features
+    co = BnCoeffs(C_, bn.weight.device)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    call("pc_bn_finalize", ptr(stats, torch.float64), C_, float(count), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+         ptr(bn.running_var), ptr(bn.num_batches_tracked, torch.int64), momentum, bn.eps, 1 if training else 0,
+         ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd), stream())
+    return co
+
+
+def pool_dims(H, W, pool):
+    if pool == 0:
+        return H, W
+    if pool == 2:
+        return H // 2, W // 2
+    return (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+
+
+def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None):
+    B, H, W, C_ = y.shape
+    Ho, Wo = pool_dims(H, W, pool)
+    out = torch.empty(B, Ho, Wo, C_, device=y.device, dtype=F32)
+    argmax = torch.empty(B, Ho, Wo, C_, device=y.device, dtype=torch.uint8) if pool == 3 else None
+    call("pc_bn_act_fwd", ptr(y), B, H, W, C_, ptr(co.scale), ptr(co.shift), ptr(drop), pool, ptr(out),
+         ptr(argmax, torch.uint8), stream())
+    return out, argmax
+
+
+def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None):
+    """Gradient w.r.t. the pre-BatchNorm tensor y of out = drop * pool(relu(bn(y))) (train-mode statistics)."""
+    B, H, W, C_ = y.shape
+    sums = torch.zeros(2, C_, device=y.device, dtype=torch.float64)
+    args = (ptr(dout), ptr(y), B, H, W, C_, ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd), ptr(drop), pool,
+            ptr(argmax, torch.uint8))
+    call("pc_bn_act_bwd_reduce", *args, ptr(sums, torch.float64), stream())
+    dy = torch.empty_like(y)
+    if dgamma is None:
+        dgamma = torch.empty(C_, device=y.device, dtype=F32)
+    if dbeta is None:
+        dbeta = torch.empty(C_, device=y.device, dtype=F32)
+    call("pc_bn_act_bwd_apply", *args, ptr(sums, torch.float64), ptr(dy), ptr(dgamma), ptr(dbeta), stream())
+    return dy, dgamma, dbeta
+
+
+def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None):
+    C_ = y2.shape[-1]
+    n_pix = y2.numel() // C_
+    out = torch.empty_like(y2)
+    call("pc_bn_add_relu_fwd", ptr(y2), ptr(co2.scale), ptr(co2.shift), ptr(ysc), ptr(co_s.scale) if co_s else None,
+         ptr(co_s.shift) if co_s else None, n_pix, C_, ptr(out), stream())
+    return out
+
+
+def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, grads2=None, grads_s=None):
+    """Returns dy2, d(shortcut branch input: dysc for a projection shortcut, dx for identity), (dgamma2, dbeta2), (dgamma_s, dbeta_s)."""
+    C_ = y2.shape[-1]
+    n_pix = y2.numel() // C_
+    dev = y2.device
+    sums2 = torch.zeros(2, C_, device=dev, dtype=torch.float64)
+    sums_s = torch.zeros(2, C_, device=dev, dtype=torch.float64) if co_s else None
+    call("pc_bn_add_relu_bwd_reduce", ptr(dout), ptr(out), ptr(y2), ptr(co2.mean), ptr(co2.invstd), ptr(ysc) if co_s else None,
+         ptr(co_s.mean) if co_s else None, ptr(co_s.invstd) if co_s else None, n_pix, C_, ptr(sums2, torch.float64),
+         ptr(sums_s, torch.float64), stream())
+    dy2 = torch.empty_like(y2)
+    dsc = torch.empty_like(y2)
+    g2 = grads2 or (torch.empty(C_, device=dev, dtype=F32), torch.empty(C_, device=dev, dtype=F32))
+    gs = grads_s or ((torch.empty(C_, device=dev, dtype=F32), torch.empty(C_, device=dev, dtype=F32)) if co_s else (None, None))
+    call("pc_bn_add_relu_bwd_apply", ptr(dout), ptr(out), ptr(y2), ptr(co2.scale), ptr(co2.mean), ptr(co2.invstd),
+         ptr(sums2, torch.float64), ptr(ysc) if co_s else None, ptr(co_s.scale) if co_s else None,
+         ptr(co_s.mean) if co_s else None, ptr(co_s.invstd) if co_s else None, ptr(sums_s, torch.float64), n_pix, C_,
+         ptr(dy2), ptr(dsc), ptr(g2[0]), ptr(g2[1]), ptr(gs[0]), ptr(gs[1]), stream())
+    return dy2, dsc, g2, gs
+
+
+def attn_pool_fwd(a, w=None, b0=None):
+    B, H, W, C_ = a.shape
+    gate = torch.empty(B, H * W, device=a.device, dtype=F32)
+    pooled = torch.empty(B, C_, device=a.device, dtype=F32)
+    call("pc_attn_pool_fwd", ptr(a), B, H * W, C_, ptr(w), ptr(b0), ptr(gate), ptr(pooled), stream())
+    return pooled, gate
+
+
+def attn_pool_bwd(a, gate, dpooled, w=None, dw=None, db0=None):
+    B, H, W, C_ = a.shape
+    da = torch.empty_like(a)
+    if w is not None:
+        dw = torch.empty(C_, device=a.device, dtype=F32) if dw is None else dw
+        db0 = torch.empty(1, device=a.device, dtype=F32) if db0 is None else db0
+    call("pc_attn_pool_bwd", ptr(a), ptr(gate), ptr(dpooled), B, H * W, C_, ptr(w), ptr(da), ptr(dw), ptr(db0), stream())
+    return da, dw, db0
+
+
+def head_fwd(x, lin: torch.nn.Linear, bn: torch.nn.BatchNorm1d, training: bool):
+    B, K = x.shape
+    N = lin.out_features
+    nbytes = int(L.lib().pc_head_workspace(B, K, N))
+    ws = torch.empty(nbytes // 4, device=x.device, dtype=F32)
+    emb = torch.empty(B, N, device=x.device, dtype=F32)
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    call("pc_head_fwd", ptr(x), B, K, N, ptr(lin.weight), ptr(lin.bias), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
+         ptr(bn.running_var), ptr(bn.num_batches_tracked, torch.int64), momentum, bn.eps, 1 if training else 0, ptr(emb),
+         ptr(ws), stream())
+    return emb, ws
+
+
+def head_bwd(demb, x, lin_w, bn_w, bn_b, training, ws, dW=None, dbias=None, dgamma=None, dbeta=None):
+    B, K = x.shape
+    N = lin_w.shape[0]
+    dev = x.device
+    dx = torch.empty(B, K, device=dev, dtype=F32)
+    dW = torch.empty(N, K, device=dev, dtype=F32) if dW is None else dW
+    dbias = torch.empty(N, device=dev, dtype=F32) if dbias is None else dbias
+    dgamma = torch.empty(N, device=dev, dtype=F32) if dgamma is None else dgamma
+    dbeta = torch.empty(N, device=dev, dtype=F32) if dbeta is None else dbeta
+    call("pc_head_bwd", ptr(demb), ptr(x), B, K, N, ptr(lin_w), ptr(bn_w), ptr(bn_b), 1 if training else 0, ptr(ws), ptr(dx),
+         ptr(dW), ptr(dbias), ptr(dgamma), ptr(dbeta), stream())
+    return dx, dW, dbias, dgamma, dbeta
+
+
+def dropout2d_mask(B, C_, p, seed, offset, device):
+    m = torch.empty(B, C_, device=device, dtype=F32)
+    call("pc_dropout2d_mask", ptr(m), B, C_, float(p), int(seed), int(offset), stream())
+    return m
+
+
+def supcon_fwd(feats, labels, mask, temperature, base_temperature, row0=0, nrows=None):
+    N, D = feats.shape
+    nrows = N - row0 if nrows is None else nrows
+    stats = torch.empty(nrows, 4, device=feats.device, dtype=F32)
+    row_loss = torch.empty(nrows, device=feats.device, dtype=F32)
+    call("pc_supcon_fwd", ptr(feats), ptr(labels, torch.int64), ptr(mask), N, D, row0, nrows, float(temperature),
+         float(base_temperature), ptr(stats), ptr(row_loss), stream())
+    return stats, row_loss
+
+
+def sum_scaled(x, scale):
+    out = torch.empty((), device=x.device, dtype=F32)
+    call("pc_sum_scaled", ptr(x), x.numel(), float(scale), ptr(out), stream())
+    return out
+
+
+def supcon_bwd(feats, labels, mask, temperature, coef, grad_scale, stats_all, row0=0, nrows=None):
+    N, D = feats.shape
+    nrows = N - row0 if nrows is None else nrows
+    dF = torch.empty(nrows, D, device=feats.device, dtype=F32)
+    call("pc_supcon_bwd", ptr(feats), ptr(labels, torch.int64), ptr(mask), N, D, row0, nrows, float(temperature), float(coef),
+         ptr(grad_scale), ptr(stats_all), ptr(dF), stream())
+    return dF

@@ -1,0 +1,5 @@
+from .losses import NTXentLoss, SupervisedContrastiveLoss, get_loss_fn
+from .optim import FusedClipAdam
+from .trainer import ContrastiveTrainer
+
+__all__ = ["NTXentLoss", "SupervisedContrastiveLoss", "get_loss_fn", "FusedClipAdam", "ContrastiveTrainer"]

@@ -1,0 +1,234 @@
+"""Drop-in for src/training/trainer.py: ContrastiveTrainer with the reference's constructor, train(),
+load_checkpoint(), checkpoint format (trainer.py:231-245) and metrics.json, driving the fused sm_100a path.
+
+What changed inside the hot loop (reference trainer.py:126-164), not in the interface:
+  * model / loss / optimiser steps are the fused kernels (no per-op ATen launches);
+  * with a FusedClipAdam optimiser, clip_grad_norm_ + Adam.step collapse into two launches;
+  * the loss is accumulated on the device and read back once per epoch instead of two .item() syncs per step
+    (trainer.py:155,160) -- set config["sync_loss_every_step"]=True to get the reference's per-step postfix;
+  * optional data parallelism (phoneme_contrast_b200.parallel): embeddings/labels all_gather for global
+    negatives, one flat-bucket gradient all-reduce.
+"""
+from __future__ import annotations
+
+import json
+import logging
+from collections import defaultdict
+from pathlib import Path
+from typing import Any, Dict, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.optim import Optimizer
+from torch.utils.data import DataLoader
+
+from .optim import FusedClipAdam
+
+try:  # progress bars are cosmetic
+    from tqdm import tqdm
+except Exception:  # pragma: no cover
+    def tqdm(it, **kw):
+        return it
+
+
+class ContrastiveTrainer:
+    """Trainer for contrastive learning (constructor of reference trainer.py:22-67)."""
+
+    def __init__(self, model: nn.Module, train_loader: DataLoader, val_loader: Optional[DataLoader], loss_fn: nn.Module,
+                 optimizer: Optimizer, scheduler, device: torch.device, config: Dict[str, Any], output_dir: Path,
+                 logger: logging.Logger, parallel=None):
+        self.model = model
+        self.train_loader = train_loader
+        self.val_loader = val_loader
+        self.loss_fn = loss_fn
+        self.optimizer = optimizer
+        self.scheduler = scheduler
+        self.device = torch.device(device)
+        self.config = config
+        self.output_dir = Path(output_dir)
+        self.logger = logger
+        self.parallel = parallel          # phoneme_contrast_b200.parallel.DataParallelContext or None
+        if self.device.type != "cuda":
+            raise RuntimeError("phoneme_contrast_b200 trains on CUDA only (no CPU fallback); got device=%s" % device)
+        self.checkpoint_dir = self.output_dir / "checkpoints"
+        self.checkpoint_dir.mkdir(parents=True, exist_ok=True)
+        self.current_epoch = 0
+        self.global_step = 0
+        self.best_val_loss = float("inf")
+        self.metrics_history = defaultdict(list)
+
+    # ------------------------------------------------------------------------------------------- loop
+    def train(self, num_epochs: int) -> None:
+        self.logger.info(f"Starting training for {num_epochs} epochs")
+        self.logger.info(f"Training samples: {len(self.train_loader.dataset)}")
+        if self.val_loader:
+            self.logger.info(f"Validation samples: {len(self.val_loader.dataset)}")
+        for epoch in range(num_epochs):
+            self.current_epoch = epoch
+            train_metrics = self._train_epoch()
+            val_metrics = {}
+            if self.val_loader and (epoch + 1) % self.config.get("eval_every", 1) == 0:
+                val_metrics = self._validate()
+            if self.val_loader and (epoch + 1) % self.config.get("eval_classifier_every", 5) == 0:
+                val_metrics.update(self._evaluate_classifier(epoch + 1))
+            if self.scheduler:
+                self.scheduler.step()
+            self._log_metrics(train_metrics, val_metrics)
+            if (epoch + 1) % self.config.get("save_every", 10) == 0:
+                self._save_checkpoint("periodic")
+            best_key = self.config.get("best_metric", "loss")
+            metric_for_best = val_metrics.get(best_key, float("inf"))
+            if best_key == "loss":
+                is_best = metric_for_best < self.best_val_loss
+            else:  # accuracy metrics: the reference compares with '>' against the same attribute (trainer.py:111-114)
+                is_best = metric_for_best > self.best_val_loss
+            if is_best:
+                self.best_val_loss = metric_for_best
+                self._save_checkpoint("best")
+                self.logger.info(f"New best model! {best_key}: {metric_for_best:.4f}")
+        self._save_checkpoint("final")
+        self._save_metrics()
+
+    def train_step(self, views: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """One optimisation step on device-resident inputs; returns the (device) loss. This is the unit bench.py times."""
+        embeddings = self._forward_pass(views)
+        if self.parallel is not None:
+            loss = self.parallel.loss(self.loss_fn, embeddings, labels)
+        else:
+            loss = self.loss_fn(embeddings, labels)
+        self.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        clip = self.config.get("gradient_clip_val")
+        if isinstance(self.optimizer, FusedClipAdam):
+            flat = self.optimizer.flat_grad()
+            if self.parallel is not None:
+                self.parallel.all_reduce_gradients(flat)          # sum; 1/R folded into grad_prescale
+            self.optimizer.step(max_grad_norm=clip or 0.0, flat_grad=flat)
+        else:
+            if self.parallel is not None:
+                self.parallel.all_reduce_parameters(self.model)
+            if clip:
+                torch.nn.utils.clip_grad_norm_(self.model.parameters(), clip)
+            self.optimizer.step()
+        return loss.detach()
+
+    def _train_epoch(self) -> Dict[str, float]:
+        self.model.train()
+        total = torch.zeros((), device=self.device, dtype=torch.float32)
+        num_batches = 0
+        sync_each = bool(self.config.get("sync_loss_every_step", False))
+        pbar = tqdm(self.train_loader, desc=f"Epoch {self.current_epoch + 1}", disable=not self.config.get("progress", True))
+        for batch in pbar:
+            views, labels = self._prepare_batch(batch)
+            loss = self.train_step(views, labels)
+            total += loss
+            num_batches += 1
+            self.global_step += 1
+            if sync_each and hasattr(pbar, "set_postfix"):
+                pbar.set_postfix({"loss": loss.item()})
+        mean_loss = float(total.item()) / max(num_batches, 1)     # the epoch's only host sync
+        return {"loss": mean_loss, "lr": self.optimizer.param_groups[0]["lr"]}
+
+    def _validate(self) -> Dict[str, float]:
+        self.model.eval()
+        total = torch.zeros((), device=self.device, dtype=torch.float32)
+        num_batches = 0
+        with torch.no_grad():
+            for batch in tqdm(self.val_loader, desc="Validation", disable=not self.config.get("progress", True)):
+                views, labels = self._prepare_batch(batch)
+                embeddings = self._forward_pass(views)
+                total += self.loss_fn(embeddings, labels)
+                num_batches += 1
+        return {"loss": float(total.item()) / max(num_batches, 1)}
+
+    def _prepare_batch(self, batch: Dict) -> Tuple[torch.Tensor, torch.Tensor]:
+        """trainer.py:186-199: H2D, [B,V,C,H,W] -> [B*V,C,H,W], labels repeat_interleave(V)."""
+        views = batch["views"].to(self.device, non_blocking=True)
+        labels = batch["label"].to(self.device, non_blocking=True)
+        if views.dim() == 5:
+            b, v = views.shape[:2]
+            views = views.reshape(b * v, *views.shape[2:])
+            labels = labels.repeat_interleave(v)
+        return views, labels
+
+    def _forward_pass(self, views: torch.Tensor) -> torch.Tensor:
+        return self.model(views)
+
+    # ------------------------------------------------------------------------------------------- bookkeeping
+    def _log_metrics(self, train_metrics: Dict, val_metrics: Dict) -> None:
+        for k, v in train_metrics.items():
+            self.metrics_history[f"train_{k}"].append(v)
+        for k, v in val_metrics.items():
+            self.metrics_history[f"val_{k}"].append(v)
+        msg = f"Epoch {self.current_epoch + 1} | Train Loss: {train_metrics['loss']:.4f}"
+        if "loss" in val_metrics:
+            msg += f" | Val Loss: {val_metrics['loss']:.4f}"
+        if "linear_accuracy" in val_metrics:
+            msg += f" | Linear Acc: {val_metrics['linear_accuracy']:.3f}"
+        if "rf_accuracy" in val_metrics:
+            msg += f" | RF Acc: {val_metrics['rf_accuracy']:.3f}"
+        msg += f" | LR: {train_metrics['lr']:.6f}"
+        self.logger.info(msg)
+
+    def _save_checkpoint(self, tag: str) -> None:
+        if self.parallel is not None and self.parallel.rank != 0:
+            return
+        checkpoint = {
+            "epoch": self.current_epoch,
+            "global_step": self.global_step,
+            "model_state_dict": self.model.state_dict(),
+            "optimizer_state_dict": self.optimizer.state_dict(),
+            "scheduler_state_dict": self.scheduler.state_dict() if self.scheduler else None,
+            "best_val_loss": self.best_val_loss,
+            "config": self.config,
+        }
+        path = self.checkpoint_dir / f"checkpoint_{tag}.pt"
+        torch.save(checkpoint, path)
+        self.logger.info(f"Saved checkpoint: {path}")
+
+    def _save_metrics(self) -> None:
+        if self.parallel is not None and self.parallel.rank != 0:
+            return
+        with open(self.output_dir / "metrics.json", "w") as f:
+            json.dump(self.metrics_history, f, indent=2)
+
+    def load_checkpoint(self, path: Path) -> None:
+        checkpoint = torch.load(path, map_location=self.device, weights_only=False)
+        self.model.load_state_dict(checkpoint["model_state_dict"])
+        self.optimizer.load_state_dict(checkpoint["optimizer_state_dict"])
+        if self.scheduler and checkpoint["scheduler_state_dict"]:
+            self.scheduler.load_state_dict(checkpoint["scheduler_state_dict"])
+        self.current_epoch = checkpoint["epoch"]
+        self.global_step = checkpoint["global_step"]
+        self.best_val_loss = checkpoint["best_val_loss"]
+        self.logger.info(f"Loaded checkpoint from epoch {self.current_epoch}")
+
+    def _evaluate_classifier(self, epoch: int) -> Dict[str, float]:
+        """Linear / random-forest 5-fold probes on the embeddings (trainer.py:272-323). Host-side sklearn, as in
+        the reference: evaluation only, off the hot path; only the embedding extraction runs on the GPU."""
+        from sklearn.ensemble import RandomForestClassifier
+        from sklearn.linear_model import LogisticRegression
+        from sklearn.model_selection import cross_val_score
+
+        self.model.eval()
+        embs, labs = [], []
+        with torch.no_grad():
+            for batch in self.val_loader:
+                views, y = self._prepare_batch(batch)
+                embs.append(self.model(views).cpu())
+                labs.extend(y.cpu().tolist())
+            for batch in self.train_loader:
+                views, y = self._prepare_batch(batch)
+                embs.append(self.model(views).cpu())
+                labs.extend(y.cpu().tolist())
+        x = torch.cat(embs, dim=0).numpy()
+        y = np.array(labs)
+        results = {}
+        for key, clf in (("linear_accuracy", LogisticRegression(max_iter=1000, random_state=42)),
+                         ("rf_accuracy", RandomForestClassifier(n_estimators=100, random_state=42))):
+            try:
+                results[key] = cross_val_score(clf, x, y, cv=5).mean()
+            except (ValueError, RuntimeError) as e:
+                self.logger.warning(f"{key} probe failed: {e}")
+        return results

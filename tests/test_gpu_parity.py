@@ -1,0 +1,467 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu). Every check goes through the public Python mirrors of the
+reference interface, which call libpc_b200.so through the C ABI, and compares against the CPU oracle and/or the
+golden vectors produced by the real reference. Tolerances are the north_star's: MFCC 1e-4 relative, embeddings and
+loss 1e-4 relative in fp32, masks/indices bit-exact; gradient tolerance stated at GRAD_RTOL below."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import augment_oracle, mfcc_oracle, nets_oracle, optim_oracle, supcon_oracle
+from tests.golden.synth import synth_waves
+from tests.helpers import analytically_zero_grad, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+# max |g - g_ref| <= GRAD_RTOL * max|g_ref| per parameter tensor (fp32 path); analytically-zero gradients use an absolute floor.
+GRAD_RTOL = 2e-3
+DEV = "cuda"
+
+
+def cu(a, dtype=torch.float32):
+    return torch.as_tensor(np.asarray(a)).to(device=DEV, dtype=dtype)
+
+
+# ============================================================================================= SupCon
+def _supcon(f, y, mask=None, **kw):
+    from phoneme_contrast_b200.training import SupervisedContrastiveLoss
+    ft = cu(f).requires_grad_(True)
+    loss = SupervisedContrastiveLoss(**kw)(ft, None if y is None else cu(y, torch.int64), None if mask is None else cu(mask))
+    loss.backward()
+    return float(loss), ft.grad.cpu().numpy()
+
+
+def test_supcon_kats(golden):
+    f8 = np.tile(np.eye(4, dtype=np.float32), (2, 1))
+    y8 = np.array([0, 0, 1, 1, 2, 2, 3, 3])
+    for T, want in ((0.5, 18.53170204), (0.15, 14.30201626), (0.07, 14.28571987)):
+        loss, _ = _supcon(f8, y8, temperature=T)
+        assert abs(loss - want) <= 1e-4 * want
+
+
+@pytest.mark.parametrize("tag", ["n64_d128", "n37_d64", "n256_d128", "n130_d128_singletons", "n96_d256"])
+def test_supcon_vs_reference_golden(golden, tag):
+    g = golden.supcon
+    loss, grad = _supcon(g[f"{tag}_f"], g[f"{tag}_y"], temperature=0.15)
+    ref = float(g[f"{tag}_loss"])
+    assert abs(loss - ref) <= 1e-4 * max(abs(ref), 1e-3)
+    gref = g[f"{tag}_grad"]
+    assert np.abs(grad - gref).max() <= 1e-4 * max(np.abs(gref).max(), 1e-6) + 1e-8
+
+
+def test_supcon_unnorm_sum_mask(golden):
+    g = golden.supcon
+    loss, grad = _supcon(g["unnorm_f"], g["unnorm_y"], temperature=0.3, base_temperature=0.2, reduction="sum")
+    assert abs(loss - float(g["unnorm_loss"])) <= 1e-4 * abs(float(g["unnorm_loss"]))
+    assert rel_l2(grad, g["unnorm_grad"]) < 1e-4
+    loss, grad = _supcon(g["mask_f"], None, mask=g["mask_m"], temperature=0.15)
+    assert abs(loss - float(g["mask_loss"])) <= 1e-4 * abs(float(g["mask_loss"]))
+    assert rel_l2(grad, g["mask_grad"]) < 1e-4
+
+
+def test_supcon_errors_and_properties():
+    from phoneme_contrast_b200.training import SupervisedContrastiveLoss
+    with pytest.raises(ValueError):       # reference tests/test_losses.py:77-84
+        SupervisedContrastiveLoss()(torch.randn(1, 128, device=DEV), torch.tensor([0], device=DEV))
+    f = torch.nn.functional.normalize(torch.randn(8, 128, device=DEV), dim=1)
+    y = torch.tensor([0, 0, 1, 1, 2, 2, 3, 3], device=DEV)
+    lo = SupervisedContrastiveLoss(temperature=0.5)(f, y)
+    assert lo.dim() == 0 and lo.item() > 0
+    assert SupervisedContrastiveLoss(temperature=0.1)(f, y) != SupervisedContrastiveLoss(temperature=1.0)(f, y)
+
+
+@pytest.mark.parametrize("n,d", [(1000, 128), (8192, 128)])
+def test_supcon_large_vs_oracle(n, d):
+    rs = np.random.RandomState(0)
+    f = rs.standard_normal((n, d)).astype(np.float32)
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    y = rs.randint(0, 38, n)
+    loss, grad = _supcon(f, y, temperature=0.15)
+    if n <= 1000:
+        assert abs(loss - supcon_oracle.loss(f, y, temperature=0.15)) <= 1e-4 * loss
+        gref = supcon_oracle.grad(f, y, temperature=0.15)
+        assert np.abs(grad - gref).max() <= 1e-4 * np.abs(gref).max()
+    else:
+        # full BASELINE size (config 4): oracle on a row block + size-independent properties
+        rows = slice(4096, 4096 + 64)
+        st = supcon_oracle.row_stats(f, y, temperature=0.15, rows=rows)
+        from phoneme_contrast_b200 import ops
+        stats, row_loss = ops.supcon_fwd(cu(f), cu(y, torch.int64), None, 0.15, 0.07)
+        s = stats.cpu().numpy()[rows]
+        np.testing.assert_allclose(s[:, 0], st["m"], rtol=1e-5)
+        np.testing.assert_allclose(s[:, 1], st["den"], rtol=1e-4)
+        assert np.array_equal(s[:, 2], st["npos"])                       # positive counts: bit-exact (integer label equality)
+        gref = supcon_oracle.grad(f, y, temperature=0.15, rows=rows)
+        assert np.abs(grad[rows] - gref).max() <= 1e-4 * np.abs(gref).max()
+        # invariance: permuting the batch permutes the gradient and keeps the loss
+        perm = rs.permutation(n)
+        loss_p, grad_p = _supcon(f[perm], y[perm], temperature=0.15)
+        assert abs(loss_p - loss) <= 1e-5 * loss
+        assert np.abs(grad_p - grad[perm]).max() <= 1e-5 * np.abs(grad).max() + 1e-9
+
+
+def test_supcon_row_blocks_equal_full():
+    """The row-sharded entry points (data-parallel path) reproduce the single-call result."""
+    from phoneme_contrast_b200 import ops
+    rs = np.random.RandomState(3)
+    n, d = 300, 128
+    f = cu(rs.standard_normal((n, d)).astype(np.float32))
+    f = torch.nn.functional.normalize(f, dim=1).contiguous()
+    y = cu(rs.randint(0, 10, n), torch.int64)
+    st_full, rl_full = ops.supcon_fwd(f, y, None, 0.15, 0.07)
+    parts = [ops.supcon_fwd(f, y, None, 0.15, 0.07, r0, nr) for r0, nr in ((0, 100), (100, 77), (177, 123))]
+    assert torch.equal(torch.cat([p[0] for p in parts]), st_full)
+    assert torch.equal(torch.cat([p[1] for p in parts]), rl_full)
+    coef = (0.15 / 0.07) / n
+    g_full = ops.supcon_bwd(f, y, None, 0.15, coef, None, st_full)
+    g_parts = torch.cat([ops.supcon_bwd(f, y, None, 0.15, coef, None, st_full, r0, nr) for r0, nr in ((0, 100), (100, 77), (177, 123))])
+    assert torch.equal(g_parts, g_full)
+
+
+# ============================================================================================= front end
+@pytest.mark.parametrize("tag,s", [("s16000", 16000), ("s4000", 4000), ("s1234", 1234)])
+def test_mfcc_vs_reference_golden(golden, tag, s):
+    from phoneme_contrast_b200.datasets import MFCCExtractor
+    g = golden.mfcc
+    w = cu(synth_waves(4, s, seed=int(g[f"{tag}_seed"])))
+    ext = MFCCExtractor()
+    per_clip = torch.cat([ext(w[i:i + 1]) for i in range(4)], 0).cpu().numpy()       # dataset-style, one clip per call
+    batched_clip = ext(w, clamp_scope="clip").cpu().numpy()
+    batched_call = ext(w).cpu().numpy()                                              # == MFCCExtractor(batch)
+    ref_pc, ref_b = g[f"{tag}_per_clip"], g[f"{tag}_batched"]
+    assert per_clip.shape == ref_pc.shape
+    assert np.array_equal(per_clip, batched_clip)
+    assert rel_l2(per_clip, ref_pc) < 1e-4
+    assert rel_l2(batched_call, ref_b) < 1e-4
+    assert np.abs(per_clip - ref_pc).max() < 1e-4 * np.abs(ref_pc).max() * 5
+    # fp64 oracle agrees as well
+    assert rel_l2(per_clip, mfcc_oracle.mfcc(w.cpu().numpy(), clamp_scope="clip")) < 1e-4
+
+
+def test_mfcc_input_ranks_delta_mel_gain(golden):
+    from phoneme_contrast_b200.datasets import MFCCExtractor, MelSpectrogramExtractor
+    g = golden.mfcc
+    w = synth_waves(2, 4000, seed=int(g["delta_in_seed"]))
+    ext = MFCCExtractor()
+    a = ext(cu(w[0]))                     # [S]
+    b = ext(cu(w[0:1]))                   # [1,S]
+    c = ext(cu(w[0:1])[:, None, :])       # [1,1,S]
+    assert a.shape == (1, 1, 40, 26) and torch.equal(a, b) and torch.equal(a, c)
+    dd = MFCCExtractor(add_delta=True, add_delta_delta=True)(cu(w[0:1])).cpu().numpy()
+    assert dd.shape == (1, 1, 120, 26) and rel_l2(dd, g["delta_dd"]) < 1e-4
+    mel = MelSpectrogramExtractor()(cu(w)).cpu().numpy()
+    assert rel_l2(mel, g["mel_s4000"]) < 1e-4
+    gain = np.float32(float(g["gain_value"]))
+    assert rel_l2(ext(cu(w[1:2] * gain)).cpu().numpy(), g["gain_per_clip"]) < 1e-4
+
+
+AUG_CFG = {"time_mask": {"enabled": True, "max_width": 30, "prob": 0.5},
+           "freq_mask": {"enabled": True, "max_width": 10, "prob": 0.5},
+           "noise": {"enabled": True, "min_snr": 0.001, "max_snr": 0.005, "prob": 0.3}}
+
+
+def test_transforms_vs_reference_golden(golden):
+    """Masks bit-exact; with noise_source='torch_cpu' the noise values equal the reference's CPU draws too."""
+    from phoneme_contrast_b200.datasets import build_augmentation_pipeline
+    g = golden.augment
+    x = cu(g["x"])
+    pipe = build_augmentation_pipeline(AUG_CFG, noise_source="torch_cpu")
+    k = 0
+    for idx in range(8):
+        for v in range(2):
+            out = pipe(x, seed=idx * 20000 + v).cpu().numpy()[0, 0]
+            ref = g["outs"][k]
+            k += 1
+            assert np.array_equal(out == 0.0, ref == 0.0)                 # mask cells bit-exact
+            np.testing.assert_allclose(out, ref, rtol=0, atol=1e-6)
+
+
+def test_transform_contracts():
+    """reference tests/test_transforms.py:22-84."""
+    from phoneme_contrast_b200.datasets import Compose, FrequencyMask, GaussianNoise, TimeMask
+    x = torch.randn(1, 1, 40, 100, device=DEV)
+    o = TimeMask(max_width=10, prob=1.0)(x, seed=42)
+    assert o.shape == x.shape and (o == 0).any()
+    o = FrequencyMask(max_width=5, prob=1.0)(x, seed=42)
+    assert o.shape == x.shape and (o == 0).any()
+    tr = GaussianNoise(min_snr=0.01, max_snr=0.02, prob=1.0)
+    o1, o2 = tr(x, seed=42), tr(x, seed=42)
+    assert not torch.allclose(o1, x) and torch.equal(o1, o2)
+    assert torch.equal(TimeMask(prob=0.0)(x, seed=42), x)
+    oc = Compose([TimeMask(prob=1.0), GaussianNoise(prob=1.0)])(x, seed=42)
+    assert oc.shape == x.shape and not torch.allclose(oc, x)
+    # device noise is N(0, level^2)
+    big = torch.zeros(1, 1, 40, 1000, device=DEV)
+    nz = GaussianNoise(min_snr=0.01, max_snr=0.01, prob=1.0)(big, seed=7)
+    assert abs(float(nz.std()) - 0.01) < 5e-4 and abs(float(nz.mean())) < 2e-4
+
+
+def test_fused_views_equal_dataset_loop(golden):
+    """forward_views (one launch: MFCC + gain + masks + noise for both views) == the reference's per-item loop
+    dataset.py:79-98 restated with the oracle; masks bit-exact, values within the MFCC tolerance."""
+    from phoneme_contrast_b200.datasets import MFCCExtractor, build_augmentation_pipeline, build_view_descriptors, pack_view_descs
+    n, s, V = 6, 16000, 2
+    w = synth_waves(n, s, seed=5)
+    pipe = build_augmentation_pipeline(AUG_CFG, noise_source="torch_cpu")
+    idx = [3, 10, 11, 40, 41, 77]
+    recs, noise = build_view_descriptors(idx, V, 40, 101, pipe, want_noise=True)
+    out = MFCCExtractor().forward_views(cu(w), pack_view_descs(recs, DEV), n * V, cu(noise.numpy())).cpu().numpy()
+    assert out.shape == (n * V, 1, 40, 101)
+    k = 0
+    for ci, i in enumerate(idx):
+        for v in range(V):
+            d = augment_oracle.view_descriptor(i, v, 40, 101, noise_shape=(1, 1, 40, 101))
+            feats = mfcc_oracle.mfcc(w[ci:ci + 1] * np.float32(d["gain"]), clamp_scope="clip")[0, 0]
+            ref = augment_oracle.apply_view(feats, d)
+            got = out[k, 0]
+            k += 1
+            if not d["noise"][0]:
+                assert np.array_equal(got == 0.0, ref == 0.0)
+            assert np.abs(got - ref).max() < 1e-4 * np.abs(feats).max() * 5, (i, v)
+
+
+# ============================================================================================= networks
+def _run_net(arch, cfg, sd, x, y, training=True):
+    from phoneme_contrast_b200.models import model_registry
+    from phoneme_contrast_b200.training import get_loss_fn
+    m = model_registry.create(arch, dict(cfg)).to(DEV)
+    m.load_state_dict({k: v.clone() for k, v in sd.items()})
+    m.train(training)
+    xt = cu(x)
+    if not training:
+        with torch.no_grad():
+            return m, m(xt).cpu().numpy(), None, None
+    emb = m(xt)
+    loss = get_loss_fn("supervised_contrastive", temperature=0.15)(emb, cu(y, torch.int64))
+    loss.backward()
+    grads = {n: p.grad.detach().cpu().numpy() for n, p in m.named_parameters()}
+    return m, emb.detach().cpu().numpy(), float(loss), grads
+
+
+def _oracle_net(arch, cfg, sd, x, y):
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+    live = {k: v.clone() for k, v in sd.items()}
+    live.update(params)
+    emb = nets_oracle.forward(arch, live, torch.from_numpy(x), training=True, use_attention=cfg.get("use_attention", True))
+    loss = supcon_oracle.loss_torch_cpu(emb, torch.from_numpy(y), temperature=0.15)
+    loss.backward()
+    return emb.detach().numpy(), float(loss.detach()), {k: p.grad.numpy() for k, p in params.items()}, live
+
+
+def _check_grads(grads, ref):
+    for name, gr in ref.items():
+        got = grads[name]
+        if analytically_zero_grad(name):
+            assert np.abs(got).max() < 2e-4, name
+            continue
+        scale = max(np.abs(gr).max(), 1e-7)
+        assert np.abs(got - gr).max() <= GRAD_RTOL * scale, (name, np.abs(got - gr).max() / scale)
+
+
+NET_CASES = [
+    ("small", "phoneme_cnn", {"embedding_dim": 128, "use_attention": True, "dropout_rate": 0.0}),
+    ("small_noattn_e64", "phoneme_cnn", {"embedding_dim": 64, "use_attention": False, "dropout_rate": 0.0}),
+    ("deep_mini", "phoneme_cnn_deep", {"embedding_dim": 128, "use_attention": True, "dropout_rate": 0.0, "hidden_dims": [16, 32, 64, 128]}),
+    ("deep_mini_odd", "phoneme_cnn_deep", {"embedding_dim": 32, "use_attention": True, "dropout_rate": 0.0, "hidden_dims": [16, 16, 32, 32]}),
+]
+
+
+@pytest.mark.parametrize("tag,arch,cfg", NET_CASES)
+def test_nets_vs_reference_golden(golden, tag, arch, cfg):
+    g = golden.nets
+    sd = nets_oracle.synthetic_state_dict(arch, cfg, seed=21)
+    x, y = g[f"{tag}_x"], g[f"{tag}_y"]
+    m, emb, loss, grads = _run_net(arch, cfg, sd, x, y)
+    ref = g[f"{tag}_emb_train"]
+    assert np.abs(emb - ref).max() <= 1e-4 * np.abs(ref).max(), np.abs(emb - ref).max()
+    assert abs(loss - float(g[f"{tag}_loss"])) <= 1e-4 * abs(float(g[f"{tag}_loss"]))
+    np.testing.assert_allclose(np.linalg.norm(emb, axis=1), 1.0, atol=1e-6)
+    for name in g[f"{tag}_param_names"]:
+        name = str(name)
+        if analytically_zero_grad(name):
+            continue
+        want = float(g[f"{tag}_gnorm_{name}"])
+        assert abs(np.linalg.norm(grads[name].astype(np.float64)) - want) <= GRAD_RTOL * want, name
+        key = f"{tag}_grad_{name}"
+        if key in g.files:
+            assert np.abs(grads[name] - g[key]).max() <= GRAD_RTOL * max(np.abs(g[key]).max(), 1e-7), name
+    sd_after = m.state_dict()
+    for k in g.files:
+        if k.startswith(f"{tag}_after_"):
+            np.testing.assert_allclose(sd_after[k[len(tag) + 7:]].cpu().numpy(), g[k], rtol=1e-5, atol=1e-6, err_msg=k)
+    assert int(sd_after["projection.1.num_batches_tracked"]) == 1
+    _, emb_eval, _, _ = _run_net(arch, cfg, sd, x, y, training=False)
+    assert np.abs(emb_eval - g[f"{tag}_emb_eval"]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("arch,B,shape", [("phoneme_cnn", 16, (40, 101)), ("phoneme_cnn_deep", 8, (40, 101)),
+                                          ("phoneme_cnn", 4, (40, 100)), ("phoneme_cnn_deep", 4, (40, 200))])
+def test_full_size_nets_vs_oracle(arch, B, shape):
+    """Full-width networks (the BASELINE architectures) against the oracle on seeded inputs, dropout off."""
+    cfg = {"dropout_rate": 0.0}
+    sd = nets_oracle.synthetic_state_dict(arch, cfg, seed=3)
+    rs = np.random.RandomState(8)
+    x = rs.standard_normal((B, 1) + shape).astype(np.float32)
+    y = (np.arange(B) // 2).astype(np.int64)
+    _, emb, loss, grads = _run_net(arch, cfg, sd, x, y)
+    emb_ref, loss_ref, grads_ref, _ = _oracle_net(arch, cfg, sd, x, y)
+    assert np.abs(emb - emb_ref).max() <= 1e-4 * np.abs(emb_ref).max()
+    assert abs(loss - loss_ref) <= 1e-4 * abs(loss_ref)
+    _check_grads(grads, grads_ref)
+
+
+def test_dropout_masks_injected_match_oracle():
+    """Dropout2d parity with explicit per-(sample,channel) multipliers on both sides (torch's CPU
+    bernoulli stream cannot be reproduced on the device, so masks are injected)."""
+    from phoneme_contrast_b200.models import model_registry
+    from phoneme_contrast_b200.training import get_loss_fn
+    for arch, chans in (("phoneme_cnn", [32, 64, 128]), ("phoneme_cnn_deep", [64, 128, 256, 512])):
+        cfg = {"dropout_rate": 0.25}
+        sd = nets_oracle.synthetic_state_dict(arch, cfg, seed=4)
+        rs = np.random.RandomState(9)
+        B = 6
+        x = rs.standard_normal((B, 1, 40, 64)).astype(np.float32)
+        y = (np.arange(B) // 2).astype(np.int64)
+        masks = [((rs.uniform(size=(B, c)) >= 0.25) / 0.75).astype(np.float32) for c in chans]
+        m = model_registry.create(arch, cfg).to(DEV)
+        m.load_state_dict(sd)
+        m._inject_drop = [cu(k) for k in masks]
+        m.train()
+        emb = m(cu(x))
+        loss = get_loss_fn("supervised_contrastive", temperature=0.15)(emb, cu(y, torch.int64))
+        loss.backward()
+        params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+        live = {k: v.clone() for k, v in sd.items()}
+        live.update(params)
+        emb_ref = nets_oracle.forward(arch, live, torch.from_numpy(x), training=True, drop=[torch.from_numpy(k) for k in masks])
+        loss_ref = supcon_oracle.loss_torch_cpu(emb_ref, torch.from_numpy(y), temperature=0.15)
+        loss_ref.backward()
+        assert np.abs(emb.detach().cpu().numpy() - emb_ref.detach().numpy()).max() <= 1e-4
+        _check_grads({n: p.grad.cpu().numpy() for n, p in m.named_parameters()}, {k: p.grad.numpy() for k, p in params.items()})
+
+
+def test_dropout_device_masks_statistics():
+    from phoneme_contrast_b200 import ops
+    m = ops.dropout2d_mask(512, 512, 0.2, 1234, 0, DEV)
+    vals = torch.unique(m).cpu().numpy()
+    np.testing.assert_allclose(vals, [0.0, 1.25], rtol=1e-6)
+    assert abs(float((m == 0).float().mean()) - 0.2) < 0.01
+    assert not torch.equal(m, ops.dropout2d_mask(512, 512, 0.2, 1234, 1 << 24, DEV))
+
+
+def test_model_contracts():
+    """reference tests/test_models.py:50-116: shapes, unit norms, embedding dims, train-mode batches, B=1 behaviour."""
+    from phoneme_contrast_b200.models import model_registry
+    m = model_registry.create("phoneme_cnn", {"in_channels": 1, "embedding_dim": 128, "use_attention": True, "dropout_rate": 0.1}).to(DEV)
+    m.eval()
+    for b in (1, 4, 16):
+        with torch.no_grad():
+            o = m(torch.randn(b, 1, 40, 100, device=DEV))
+        assert o.shape == (b, 128)
+        assert torch.allclose(o.norm(p=2, dim=1), torch.ones(b, device=DEV), atol=1e-6)
+    for e in (64, 128, 256):
+        mm = model_registry.create("phoneme_cnn", {"embedding_dim": e}).to(DEV).eval()
+        assert mm(torch.randn(4, 1, 40, 100, device=DEV)).shape == (4, e)
+    m.train()
+    for b in (2, 4, 16):
+        assert m(torch.randn(b, 1, 40, 100, device=DEV)).shape == (b, 128)
+    with pytest.raises(ValueError):
+        m(torch.randn(1, 1, 40, 100, device=DEV))
+    d = model_registry.create("phoneme_cnn_deep", {}).to(DEV).eval()   # scripts/test_cnn_deep.py: B=4, 40x200
+    with torch.no_grad():
+        o = d(torch.randn(4, 1, 40, 200, device=DEV))
+    assert o.shape == (4, 128) and torch.allclose(o.norm(dim=1), torch.ones(4, device=DEV), atol=1e-6)
+
+
+# ============================================================================================= optimiser + trainer
+def test_fused_clip_adam_vs_torch_golden(golden):
+    from phoneme_contrast_b200.training import FusedClipAdam
+    g = golden.optim
+    n = int(g["n"])
+    params = [torch.nn.Parameter(cu(g[f"p0_{i}"])) for i in range(n)]
+    opt = FusedClipAdam(params, lr=3e-4, weight_decay=1e-4)
+    for step in range(3):
+        for i, p in enumerate(params):
+            p.grad = cu(g[f"g{step}_{i}"])
+        opt.step(max_grad_norm=1.0)
+        assert abs(float(opt.total_grad_norm()) - float(g[f"norm{step}"])) <= 1e-5 * float(g[f"norm{step}"])
+        for i, p in enumerate(params):
+            np.testing.assert_allclose(p.detach().cpu().numpy(), g[f"p{step + 1}_{i}"], rtol=0, atol=3e-7)
+    sd = opt.state_dict()
+    assert set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"} and float(sd["state"][0]["step"]) == 3.0
+
+
+def test_training_step_matches_oracle_three_steps():
+    """fwd + loss + bwd + clip + Adam for 3 steps, cnn_small at the reference recipe's shape (64 views, 8x4x2)."""
+    from phoneme_contrast_b200.models import model_registry
+    from phoneme_contrast_b200.training import FusedClipAdam, get_loss_fn
+    arch, cfg = "phoneme_cnn", {"dropout_rate": 0.0}
+    sd = nets_oracle.synthetic_state_dict(arch, cfg, seed=12)
+    rs = np.random.RandomState(13)
+    B = 64
+    y = np.repeat(np.arange(B // 2) // 4, 2).astype(np.int64)
+    m = model_registry.create(arch, cfg).to(DEV)
+    m.load_state_dict(sd)
+    m.train()
+    opt = FusedClipAdam(m.parameters(), lr=3e-4, weight_decay=1e-4)
+    loss_fn = get_loss_fn("supervised_contrastive", temperature=0.15)
+    names = [n for n, _ in m.named_parameters()]
+    live = {k: v.clone() for k, v in sd.items()}
+    plist = [live[n].clone() for n in names]
+    mom = [np.zeros(p.shape, np.float32) for p in plist]
+    var = [np.zeros(p.shape, np.float32) for p in plist]
+    for step in range(3):
+        x = rs.standard_normal((B, 1, 40, 101)).astype(np.float32)
+        emb = m(cu(x))
+        loss = loss_fn(emb, cu(y, torch.int64))
+        opt.zero_grad()
+        loss.backward()
+        opt.step(max_grad_norm=1.0)
+        for n_, p in zip(names, plist):
+            live[n_] = p.clone().requires_grad_(True)
+        emb_ref = nets_oracle.forward(arch, live, torch.from_numpy(x), training=True)
+        loss_ref = supcon_oracle.loss_torch_cpu(emb_ref, torch.from_numpy(y), temperature=0.15)
+        loss_ref.backward()
+        assert abs(float(loss) - float(loss_ref.detach())) <= 2e-4 * abs(float(loss_ref.detach())), step
+        grads = [live[n_].grad.numpy() for n_ in names]
+        pn = [p.detach().numpy().copy() for p in plist]
+        optim_oracle.adam_step(pn, grads, mom, var, step + 1, lr=3e-4, weight_decay=1e-4, max_norm=1.0)
+        plist = [torch.from_numpy(p) for p in pn]
+        for n_, p in zip(names, plist):
+            live[n_] = p
+    for n_, p, ref in zip(names, m.parameters(), plist):
+        # after 3 Adam steps each weight moved by <= 3*lr; agreement to a small fraction of that
+        assert np.abs(p.detach().cpu().numpy() - ref.numpy()).max() <= 3e-5, n_
+
+
+def test_trainer_one_epoch(tmp_path):
+    """reference tests/test_trainer.py: SimpleDataset, PhonemeNet(emb 64, no attention), SupCon(T=.5), Adam, 1 epoch."""
+    import logging
+
+    from torch.utils.data import DataLoader
+
+    from phoneme_contrast_b200.models import model_registry
+    from phoneme_contrast_b200.training import ContrastiveTrainer, FusedClipAdam, SupervisedContrastiveLoss
+
+    class SimpleDataset:
+        def __len__(self):
+            return 100
+
+        def __getitem__(self, idx):
+            g = torch.Generator().manual_seed(idx)
+            return {"views": torch.randn(2, 1, 40, 50, generator=g), "label": idx % 10, "index": idx}
+
+    for fused in (False, True):
+        model = model_registry.create("phoneme_cnn", {"embedding_dim": 64, "use_attention": False}).to(DEV)
+        opt = FusedClipAdam(model.parameters(), lr=1e-3) if fused else torch.optim.Adam(model.parameters(), lr=1e-3)
+        tr = ContrastiveTrainer(model=model, train_loader=DataLoader(SimpleDataset(), batch_size=16, shuffle=True),
+                                val_loader=DataLoader(SimpleDataset(), batch_size=16, shuffle=False),
+                                loss_fn=SupervisedContrastiveLoss(temperature=0.5), optimizer=opt, scheduler=None,
+                                device=torch.device(DEV), config={"eval_every": 1, "save_every": 2, "gradient_clip_val": 1.0, "progress": False},
+                                output_dir=tmp_path / f"run{int(fused)}", logger=logging.getLogger("t"))
+        assert tr.current_epoch == 0 and tr.global_step == 0 and tr.checkpoint_dir.exists()
+        tr.train(num_epochs=1)
+        assert len(tr.metrics_history["train_loss"]) == 1 and "val_loss" in tr.metrics_history
+        assert np.isfinite(tr.metrics_history["train_loss"][0]) and tr.global_step == 7
+        ck = torch.load(tr.checkpoint_dir / "checkpoint_final.pt", weights_only=False)
+        assert set(ck) == {"epoch", "global_step", "model_state_dict", "optimizer_state_dict", "scheduler_state_dict", "best_val_loss", "config"}
+        tr.load_checkpoint(tr.checkpoint_dir / "checkpoint_final.pt")
