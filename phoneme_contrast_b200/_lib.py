@@ -114,8 +114,41 @@ def check(rc: int) -> None:
     raise RuntimeError(msg)
 
 
+# Optional per-entry-point device timing (bench.py's live roofline measurement): CUDA events recorded on the
+# launching stream around every C-ABI call while a profile is open.
+_prof = None
+
+
+def profile_begin() -> None:
+    global _prof
+    _prof = {"events": {}, "work": {}}
+
+
+def profile_end() -> dict:
+    """-> {entry point: {"ms": total device ms, "calls": n, "work": accumulated algorithmic work}}."""
+    global _prof
+    p, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, evs in p["events"].items():
+        out[name] = {"ms": sum(a.elapsed_time(b) for a, b in evs), "calls": len(evs), "work": p["work"].get(name, 0.0)}
+    return out
+
+
+def note_work(name: str, amount: float) -> None:
+    if _prof is not None:
+        _prof["work"][name] = _prof["work"].get(name, 0.0) + amount
+
+
 def call(name: str, *args):
+    if _prof is None:
+        check(getattr(lib(), name)(*args))
+        return
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     check(getattr(lib(), name)(*args))
+    e1.record()
+    _prof["events"].setdefault(name, []).append((e0, e1))
 
 
 def stream() -> C.c_void_p:

@@ -39,6 +39,7 @@ def conv_fwd(x, w, bias, g: PcConvGeom, xform=None, stats=None, prec=L.PREC_FP32
     """x NHWC [B,H,W,Cin]; w = packed Wf (Cin>1) or the raw OIHW weight (Cin==1 stem)."""
     y = torch.empty(g.B, g.Ho, g.Wo, g.Cout, device=x.device, dtype=F32)
     xf = _xf(**xform) if xform else None
+    L.note_work("pc_conv_fwd", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
     call("pc_conv_fwd", ptr(x), ptr(w), ptr(bias), C.byref(g), C.byref(xf) if xf is not None else None, ptr(y),
          ptr(stats, torch.float64), prec, stream())
     return y
@@ -47,6 +48,7 @@ def conv_fwd(x, w, bias, g: PcConvGeom, xform=None, stats=None, prec=L.PREC_FP32
 def conv_dgrad(dy, wd, g: PcConvGeom, out=None, accumulate=False, prec=L.PREC_FP32):
     if out is None:
         out = torch.empty(g.B, g.H, g.W, g.Cin, device=dy.device, dtype=F32)
+    L.note_work("pc_conv_dgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
     call("pc_conv_dgrad", ptr(dy), ptr(wd), C.byref(g), ptr(out), 1 if accumulate else 0, prec, stream())
     return out
 
@@ -72,6 +74,7 @@ def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_F
     nbytes = int(L.lib().pc_conv_wgrad_workspace(C.byref(g)))
     ws = _workspace(nbytes, x.device)
     xf = _xf(**xform) if xform else None
+    L.note_work("pc_conv_wgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
     call("pc_conv_wgrad", ptr(x), ptr(dy), C.byref(g), C.byref(xf) if xf is not None else None, ptr(dw), ptr(db),
          ptr(ws, torch.uint8), ws.numel(), prec, stream())
     return dw, db
