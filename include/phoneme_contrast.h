@@ -134,10 +134,26 @@ typedef struct PcInXform {
 /* OIHW fp32 -> fwd layout Wf [(r,s,c)][o] and dgrad layout Wd [(r,s,o)][c] (either may be NULL). */
 int pc_pack_conv_weight(const float* w_oihw, int O, int I, int R, int S, float* wf, float* wd, pc_stream_t stream);
 
-/* y = conv(xform(x)) + bias; if stats != NULL accumulates per-channel sum / sum of squares of y into
- * stats [2][Cout] (fp64) for the following train-mode BatchNorm. Cin == 1 uses a direct kernel;
- * otherwise Cin % 16 == 0 and the implicit-GEMM kernel runs (prec: PC_PREC_*). */
+/* Precision of the implicit-GEMM convolutions:
+ *   PC_PREC_FP32   exact-fp32 SIMT kernels (operands packed by pc_pack_conv_weight);
+ *   PC_PREC_TF32X3 tcgen05 tensor cores, fp32 operands split hi+lo, 3 kind::tf32 MMAs per k-step (fp32-level accuracy);
+ *   PC_PREC_BF16   tcgen05 tensor cores, operands rounded to bf16 (1e-2 tolerance mode).
+ * For the two tensor-core modes the weight operand is the pre-swizzled tile image written by
+ * pc_pack_conv_weight_tc, and a layer is eligible when pc_conv_tc_supported() != 0 (gathered channels a multiple of
+ * 32 / 64); ineligible layers must be run with PC_PREC_FP32. */
 enum { PC_PREC_FP32 = 0, PC_PREC_TF32X3 = 1, PC_PREC_BF16 = 2 };
+int pc_conv_tc_supported(const PcConvGeom* g, int dgrad, int prec);
+size_t pc_conv_tc_packed_bytes(int O, int I, int R, int S, int dgrad, int prec);
+int pc_pack_conv_weight_tc(const float* w_oihw, int O, int I, int R, int S, int dgrad, int prec, void* out, pc_stream_t stream);
+/* C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) through the same tcgen05 tile engine (unit check of the tensor-core path;
+ * also usable as a stand-alone fp32-accurate GEMM). ws >= pc_tc_gemm_workspace(N, K, prec) bytes. */
+size_t pc_tc_gemm_workspace(int N, int K, int prec);
+int pc_tc_gemm(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int prec, void* ws,
+               size_t ws_bytes, pc_stream_t stream);
+
+/* y = conv(xform(x)) + bias; if stats != NULL accumulates per-channel sum / sum of squares of y into
+ * stats [2][Cout] (fp64) for the following train-mode BatchNorm. Cin == 1 uses a direct kernel (wf = the OIHW
+ * weight itself); otherwise Cin % 16 == 0 and the implicit-GEMM kernel of the requested precision runs. */
 int pc_conv_fwd(const float* x, const float* wf, const float* bias, const PcConvGeom* g, const PcInXform* xf,
                 float* y, double* stats, int prec, pc_stream_t stream);
 /* dx (+)= conv_transpose(dy, w): accumulate != 0 adds into dx. */

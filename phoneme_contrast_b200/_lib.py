@@ -54,6 +54,11 @@ SIGNATURES = {
     "pc_sum_scaled": (i32, [vp, i32, f32, vp, vp]),
     "pc_supcon_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, vp]),
     "pc_pack_conv_weight": (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),
+    "pc_conv_tc_supported": (i32, [C.POINTER(PcConvGeom), i32, i32]),
+    "pc_conv_tc_packed_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
+    "pc_pack_conv_weight_tc": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "pc_tc_gemm_workspace": (sz, [i32, i32, i32]),
+    "pc_tc_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]),
     "pc_conv_fwd": (i32, [vp, vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, i32, vp]),
     "pc_conv_dgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, i32, i32, vp]),
     "pc_conv_wgrad_workspace": (sz, [C.POINTER(PcConvGeom)]),

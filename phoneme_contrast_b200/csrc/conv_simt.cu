@@ -543,8 +543,10 @@ extern "C" int pc_pack_conv_weight(const float* w_oihw, int O, int I, int R, int
 }
 
 // tensor-core path (conv_tc.cu); returns PC_EUNSUPPORTED when the shape is not covered.
-extern "C" int pc_conv_fwd_tc(const float* x, const float* wf, const float* bias, const PcConvGeom* g, const PcInXform* xf,
+extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias, const PcConvGeom* g, const PcInXform* xf,
                               float* y, double* stats, int prec, pc_stream_t stream);
+extern "C" int pc_conv_dgrad_tc(const float* dy, const void* wp, const PcConvGeom* g, float* dx, int accumulate, int prec,
+                                pc_stream_t stream);
 
 extern "C" int pc_conv_fwd(const float* x, const float* wf, const float* bias, const PcConvGeom* g, const PcInXform* xf,
                            float* y, double* stats, int prec, pc_stream_t stream) {
@@ -568,8 +570,10 @@ extern "C" int pc_conv_fwd(const float* x, const float* wf, const float* bias, c
   }
   PC_REQUIRE(g->Cin % CG_BK == 0 && g->Cout % 4 == 0, PC_EUNSUPPORTED, "pc_conv_fwd: Cin=%d must be a multiple of 16 and Cout=%d of 4", g->Cin, g->Cout);
   if (prec != PC_PREC_FP32) {
+    // tensor-core path: `wf` is the buffer produced by pc_pack_conv_weight_tc for this precision
     rc = pc_conv_fwd_tc(x, wf, bias, g, xf, y, stats, prec, stream);
-    if (rc != PC_EUNSUPPORTED) return rc;
+    PC_REQUIRE(rc != PC_EUNSUPPORTED, PC_EUNSUPPORTED, "pc_conv_fwd: shape not covered by the tensor-core path (check pc_conv_tc_supported)");
+    return rc;
   }
   const long long M = (long long)g->B * g->Ho * g->Wo;
   const XformDev d = to_dev(xf);
@@ -593,7 +597,11 @@ extern "C" int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom*
   if (rc != PC_OK) return rc;
   PC_REQUIRE(dy && wd && dx, PC_EINVAL, "pc_conv_dgrad: null pointer");
   PC_REQUIRE(g->Cout % CG_BK == 0 && g->Cin % 4 == 0, PC_EUNSUPPORTED, "pc_conv_dgrad: Cout=%d must be a multiple of 16 and Cin=%d of 4", g->Cout, g->Cin);
-  (void)prec;
+  if (prec != PC_PREC_FP32) {
+    rc = pc_conv_dgrad_tc(dy, wd, g, dx, accumulate, prec, stream);
+    PC_REQUIRE(rc != PC_EUNSUPPORTED, PC_EUNSUPPORTED, "pc_conv_dgrad: shape not covered by the tensor-core path (check pc_conv_tc_supported)");
+    return rc;
+  }
   const long long M = (long long)g->B * g->H * g->W;
   const XformDev d{nullptr, nullptr, nullptr, 0};
   if (g->Cin <= 32) {

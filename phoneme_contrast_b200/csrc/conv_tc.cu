@@ -1,8 +1,538 @@
-// tcgen05 tensor-core implicit-GEMM convolution (sm_100a). Placeholder dispatcher until the kernel lands:
-// reports PC_EUNSUPPORTED so pc_conv_fwd falls through to the exact-fp32 SIMT kernel.
+// tcgen05 tensor-core implicit-GEMM convolution for sm_100a (forward and data-gradient), plus the plain
+// C = A * B^T GEMM built from the same tile engine (used by tests as a unit check of the tensor-core path).
+//
+//   D[128 x BN] (fp32, TMEM)  +=  A[128 x K] * B[BN x K]^T        K = taps x channels, walked in 128-byte k-chunks
+//
+// Warp roles (192 threads, one CTA per 128-row M tile x BN-column N tile):
+//   warps 0-3  producers, then epilogue. The A operand is an im2col GATHER with the previous layer's
+//              BatchNorm-apply + ReLU + Dropout2d folded in, so it cannot come from TMA: 8 lanes fetch one
+//              pixel's 128 contiguous bytes (coalesced), transform, convert, and store them into the
+//              SWIZZLE_128B K-major tile the UMMA descriptor expects; fence.proxy.async; mbarrier arrive.
+//   warp 4     allocates TMEM, then one lane issues tcgen05.mma (D in TMEM) and tcgen05.commit per stage.
+//   warp 5     one lane streams the pre-swizzled weight tiles with 1-D bulk async copies (cp.async.bulk, TMA
+//              engine) that complete on the same "full" mbarrier as the producers' arrivals.
+//   epilogue   tcgen05.ld (32 lanes x 32 columns per instruction) -> + bias -> BatchNorm sum / sum-of-squares via a
+//              31-shuffle warp reduce-scatter -> NHWC fp32 store.
+//
+// Precision modes (include/phoneme_contrast.h PC_PREC_*):
+//   TF32X3  fp32 operands split as x = hi + lo (hi = top 19 bits, lo = x - hi exactly); three kind::tf32 MMAs
+//           per k-step (lo*hi, hi*lo, hi*hi) accumulate ~fp32-accurate products in the fp32 TMEM accumulator.
+//           This is the mode that keeps the 1e-4 parity bar ("fp32 parity on tensor cores").
+//   BF16    operands rounded to bf16, one kind::f16 MMA per k-step (the 1e-2 tolerance mode).
 #include "common.cuh"
+#include "tc_common.cuh"
 
-extern "C" int pc_conv_fwd_tc(const float*, const float*, const float*, const PcConvGeom*, const PcInXform*, float*, double*, int,
-                              pc_stream_t) {
-  return PC_EUNSUPPORTED;
+namespace pc {
+namespace tcconv {
+
+using namespace pc::tc;
+
+constexpr int BM = 128;
+constexpr int NPROD = 128;
+constexpr int THREADS = 192;
+constexpr int MAX_STAGES = 6;
+constexpr uint32_t SMEM_BUDGET = 200 * 1024;
+
+struct XformDev {
+  const float* scale;
+  const float* shift;
+  const float* drop;
+  int relu;
+};
+
+struct Params {
+  const float* A;
+  const unsigned char* Bp;
+  const float* bias;
+  float* C;
+  double* stats;
+  XformDev xf;
+  PcConvGeom g;
+  int mode;          // 0 conv fwd gather, 1 conv dgrad gather, 2 plain row-major A [M][lda]
+  long long M;
+  int Nn, Npad, Ca, n_kc, lda, accumulate, stages;
+};
+
+template <int PREC> struct Prec;
+// NACC: TMEM accumulators per tile. The tensor core adds into its fp32 accumulator with truncation, so a long
+// dependent chain of accumulations picks up a bias of ~2^-24 per step. TF32X3 therefore spreads the hi*hi terms
+// round-robin over 3 accumulators and keeps the two small correction terms in a 4th; the epilogue adds the four
+// partial sums in registers with round-to-nearest (measured: ~10x lower error than a single accumulator).
+template <> struct Prec<PC_PREC_TF32X3> { static constexpr int BKC = 32, PARTS = 2, NACC = 4; };
+template <> struct Prec<PC_PREC_BF16> { static constexpr int BKC = 64, PARTS = 1, NACC = 1; };
+
+template <int BN, int PREC>
+__host__ __device__ constexpr uint32_t stage_bytes() { return (uint32_t)Prec<PREC>::PARTS * (BM * 128 + BN * 128); }
+
+// v[32] per lane (lane = row) -> returns sum over the 32 lanes of column `lane`
+__device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <int BN, int PREC>
+__global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
+  using P = Prec<PREC>;
+  constexpr int BKC = P::BKC, PARTS = P::PARTS, NACC = P::NACC;
+  constexpr uint32_t A_PART = BM * 128, B_PART = BN * 128;
+  constexpr uint32_t STAGE = stage_bytes<BN, PREC>();
+
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // SWIZZLE_128B tiles need a 1024-byte aligned base: align by hand (the launch reserves 1 KB of slack)
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int S = p.stages;
+  unsigned char* tiles = smem;                                                    // [S][A parts | B parts]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * STAGE);        // [S]
+  uint64_t* empty = full + MAX_STAGES;                                            // [S]
+  uint64_t* acc_full = empty + MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);                        // [BN]
+  float* s_sum = s_bias + BN;                                                     // [BN]
+  float* s_sq = s_sum + BN;                                                       // [BN]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const long long m0 = (long long)blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+
+  if (tid < BN) {
+    const int n = n0 + tid;
+    s_bias[tid] = (p.bias != nullptr && n < p.Nn) ? p.bias[n] : 0.f;
+    s_sum[tid] = 0.f;
+    s_sq[tid] = 0.f;
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(&full[s], NPROD + 1);
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(acc_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, NACC * BN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ============================================================ producers
+    const int j = tid & 7;          // 16-byte chunk of the 128-byte k-chunk row
+    const int rg = tid >> 3;        // rows rg + 16*i
+    // per-row decode (8 rows per thread)
+    int rb[8], rh[8], rw[8];
+    const PcConvGeom g = p.g;
+    const int Hr = p.mode == 0 ? g.Ho : g.H, Wr = p.mode == 0 ? g.Wo : g.W;
+    const int Ha = p.mode == 0 ? g.H : g.Ho, Wa = p.mode == 0 ? g.W : g.Wo;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long m = m0 + rg + 16 * i;
+      if (m < p.M) {
+        if (p.mode == 2) {
+          rb[i] = 0; rh[i] = 0; rw[i] = 0;
+        } else {
+          rw[i] = (int)(m % Wr);
+          rh[i] = (int)((m / Wr) % Hr);
+          rb[i] = (int)(m / ((long long)Wr * Hr));
+        }
+      } else {
+        rb[i] = -1; rh[i] = 0; rw[i] = 0;
+      }
+    }
+    const int cpt = p.Ca / BKC;     // k-chunks per tap
+    constexpr int EPC = (PREC == PC_PREC_BF16) ? 8 : 4;   // source elements per 16-byte destination chunk
+    for (int kc = 0; kc < p.n_kc; ++kc) {
+      const int s = kc % S;
+      const uint32_t ph = (uint32_t)(kc / S) & 1u;
+      mbar_wait(&empty[s], ph ^ 1u);
+      const int tap = kc / cpt;
+      const int c0 = (kc - tap * cpt) * BKC + j * EPC;      // first channel of my chunk
+      const int tr = tap / g.S, ts = tap - tr * g.S;
+      float sc[EPC], sh[EPC];
+      const bool has_aff = (p.mode == 0 && p.xf.scale != nullptr);
+      if (has_aff) {
+#pragma unroll
+        for (int q = 0; q < EPC; q += 4) {
+          const float4 a = *reinterpret_cast<const float4*>(p.xf.scale + c0 + q);
+          const float4 b = *reinterpret_cast<const float4*>(p.xf.shift + c0 + q);
+          sc[q] = a.x; sc[q + 1] = a.y; sc[q + 2] = a.z; sc[q + 3] = a.w;
+          sh[q] = b.x; sh[q + 1] = b.y; sh[q + 2] = b.z; sh[q + 3] = b.w;
+        }
+      }
+      unsigned char* a_hi = tiles + (size_t)s * STAGE;
+      unsigned char* a_lo = a_hi + A_PART;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = rg + 16 * i;
+        float v[EPC];
+#pragma unroll
+        for (int q = 0; q < EPC; ++q) v[q] = 0.f;
+        bool ok = rb[i] >= 0;
+        const float* src = nullptr;
+        if (p.mode == 2) {
+          if (ok) src = p.A + (size_t)(m0 + r) * p.lda + c0;
+        } else {
+          int ha, wa;
+          if (p.mode == 0) {
+            ha = rh[i] * g.stride - g.pad + tr;
+            wa = rw[i] * g.stride - g.pad + ts;
+          } else {
+            const int hn = rh[i] + g.pad - tr, wn = rw[i] + g.pad - ts;
+            ok = ok && hn >= 0 && wn >= 0 && (hn % g.stride == 0) && (wn % g.stride == 0);
+            ha = hn / g.stride;
+            wa = wn / g.stride;
+          }
+          ok = ok && ha >= 0 && ha < Ha && wa >= 0 && wa < Wa;
+          if (ok) src = p.A + (((size_t)rb[i] * Ha + ha) * Wa + wa) * p.Ca + c0;
+        }
+        if (ok) {
+#pragma unroll
+          for (int q = 0; q < EPC; q += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(src + q);
+            v[q] = t.x; v[q + 1] = t.y; v[q + 2] = t.z; v[q + 3] = t.w;
+          }
+          if (has_aff) {
+#pragma unroll
+            for (int q = 0; q < EPC; ++q) v[q] = fmaf(v[q], sc[q], sh[q]);
+          }
+          if (p.mode == 0 && p.xf.relu) {
+#pragma unroll
+            for (int q = 0; q < EPC; ++q) v[q] = fmaxf(v[q], 0.f);
+          }
+          if (p.mode == 0 && p.xf.drop != nullptr) {
+#pragma unroll
+            for (int q = 0; q < EPC; q += 4) {
+              const float4 d = *reinterpret_cast<const float4*>(p.xf.drop + (size_t)rb[i] * p.Ca + c0 + q);
+              v[q] *= d.x; v[q + 1] *= d.y; v[q + 2] *= d.z; v[q + 3] *= d.w;
+            }
+          }
+        }
+        const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)j);
+        if (PREC == PC_PREC_TF32X3) {
+          float h[4], l[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
+          *reinterpret_cast<float4*>(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+          uint4 w;
+          w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
+          w.z = pack_bf16(v[4 % EPC], v[5 % EPC]); w.w = pack_bf16(v[6 % EPC], v[7 % EPC]);
+          *reinterpret_cast<uint4*>(a_hi + off) = w;
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+
+    // ============================================================ epilogue (thread = tile row = TMEM lane)
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int r = tid;
+    const long long m = m0 + r;
+    const bool valid = m < p.M;
+    float* dst_row = p.C + (size_t)(valid ? m : 0) * p.Nn + n0;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      float v[32];
+      {
+        uint32_t raw[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        tmem_ld_32x32(taddr, raw);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(raw[q]);
+        if (NACC == 4) {
+          float u[32];
+          tmem_ld_32x32(taddr + BN, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(raw[q]);
+          tmem_ld_32x32(taddr + 2 * BN, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) u[q] = __uint_as_float(raw[q]);
+          tmem_ld_32x32(taddr + 3 * BN, raw);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] += u[q] + __uint_as_float(raw[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] = valid ? v[q] + s_bias[c0 + q] : 0.f;
+      if (valid) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4) {
+          if (n0 + c0 + q < p.Nn) {
+            float4 o = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            float* d = dst_row + c0 + q;
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(d);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            *reinterpret_cast<float4*>(d) = o;
+          }
+        }
+      }
+      if (p.stats != nullptr) {
+        float sq[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) sq[q] = v[q] * v[q];
+        const float cs = warp_reduce_scatter32(v, lane);
+        const float cq = warp_reduce_scatter32(sq, lane);
+        atomicAdd(&s_sum[c0 + lane], cs);
+        atomicAdd(&s_sq[c0 + lane], cq);
+      }
+    }
+    if (p.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps only
+      if (tid < BN) {
+        const int n = n0 + tid;
+        if (n < p.Nn) {
+          atomicAdd(p.stats + n, (double)s_sum[tid]);
+          atomicAdd(p.stats + p.Nn + n, (double)s_sq[tid]);
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ============================================================ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(PREC == PC_PREC_BF16 ? 1u : 2u, BM, BN);
+      for (int kc = 0; kc < p.n_kc; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (uint32_t)(kc / S) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t base = smem_u32(tiles + (size_t)s * STAGE);
+        const uint64_t a_hi = smem_desc_sw128(base);
+        const uint64_t a_lo = smem_desc_sw128(base + A_PART);
+        const uint64_t b_hi = smem_desc_sw128(base + PARTS * A_PART);
+        const uint64_t b_lo = smem_desc_sw128(base + PARTS * A_PART + B_PART);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * 2);       // 32 bytes per k-step, in 16-byte units
+          const int ks = kc * 4 + kk;                    // global k-step
+          if (PREC == PC_PREC_TF32X3) {
+            const uint32_t d_main = tmem_base + (uint32_t)((ks % 3) * BN);
+            const uint32_t d_corr = tmem_base + (uint32_t)(3 * BN);
+            mma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, ks == 0 ? 0u : 1u);
+            mma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+            mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ks < 3 ? 0u : 1u);
+          } else {
+            mma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, ks == 0 ? 0u : 1u);
+          }
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(acc_full);
+    }
+    __syncwarp();
+  } else {
+    // ============================================================ weight loader
+    if (lane == 0) {
+      const size_t kc_stride = (size_t)PARTS * p.Npad * 128;
+      for (int kc = 0; kc < p.n_kc; ++kc) {
+        const int s = kc % S;
+        const uint32_t ph = (uint32_t)(kc / S) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        unsigned char* b_dst = tiles + (size_t)s * STAGE + PARTS * A_PART;
+        const unsigned char* src = p.Bp + (size_t)kc * kc_stride + (size_t)n0 * 128;
+        mbar_arrive_expect_tx(&full[s], PARTS * B_PART);
+#pragma unroll
+        for (int part = 0; part < PARTS; ++part)
+          bulk_g2s(b_dst + part * B_PART, src + (size_t)part * p.Npad * 128, B_PART, &full[s]);
+      }
+    }
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 4) tmem_dealloc(tmem_base, NACC * BN);
+}
+
+// ------------------------------------------------------------------------------------------------ weight / B packing
+// out layout: [n_kc][PARTS][Npad rows][128 bytes, 16-byte chunk index XOR (row & 7)]
+// src_mode 0: conv fwd   B[n = o][k = (r,s,c)] = w[o][c][r][s]      (Ca = I)
+// src_mode 1: conv dgrad B[n = c][k = (r,s,o)] = w[o][c][r][s]      (Ca = O)
+// src_mode 2: plain      B[n][k] = src[n * ld + k]                  (taps = 1, Ca = K)
+template <int PREC>
+__global__ void pack_b_kernel(const float* __restrict__ src, int O, int I, int R, int S, int src_mode, int ld, int Nn, int Npad,
+                              int Ca, unsigned char* __restrict__ out) {
+  using P = Prec<PREC>;
+  constexpr int BKC = P::BKC, PARTS = P::PARTS;
+  constexpr int EPC = (PREC == PC_PREC_BF16) ? 8 : 4;
+  const int taps = src_mode == 2 ? 1 : R * S;
+  const int cpt = Ca / BKC;
+  const long long total = (long long)taps * cpt * Npad * 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx & 7);
+    const int n = (int)((idx >> 3) % Npad);
+    const int kc = (int)((idx >> 3) / Npad);
+    const int tap = kc / cpt, c0 = (kc % cpt) * BKC + j * EPC;
+    float v[EPC];
+#pragma unroll
+    for (int q = 0; q < EPC; ++q) {
+      float x = 0.f;
+      if (n < Nn) {
+        const int c = c0 + q;
+        if (src_mode == 0) x = src[(((size_t)n * I + c) * R + tap / S) * S + tap % S];
+        else if (src_mode == 1) x = src[(((size_t)c * I + n) * R + tap / S) * S + tap % S];
+        else x = src[(size_t)n * ld + c];
+      }
+      v[q] = x;
+    }
+    unsigned char* base = out + ((size_t)kc * PARTS * Npad + n) * 128 + (size_t)((j ^ (n & 7)) << 4);
+    if (PREC == PC_PREC_TF32X3) {
+      float h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
+      *reinterpret_cast<float4*>(base) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(base + (size_t)Npad * 128) = make_float4(l[0], l[1], l[2], l[3]);
+    } else {
+      uint4 w;
+      w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
+      w.z = pack_bf16(v[4 % EPC], v[5 % EPC]); w.w = pack_bf16(v[6 % EPC], v[7 % EPC]);
+      *reinterpret_cast<uint4*>(base) = w;
+    }
+  }
+}
+
+static inline int pick_bn(int Nn) { return Nn <= 32 ? 32 : (Nn <= 64 ? 64 : 128); }
+static inline int npad_of(int Nn) { const int bn = pick_bn(Nn); return ceil_div(Nn, bn) * bn; }
+static inline int bkc_of(int prec) { return prec == PC_PREC_BF16 ? 64 : 32; }
+static inline int parts_of(int prec) { return prec == PC_PREC_BF16 ? 1 : 2; }
+
+template <int BN, int PREC>
+static int launch(const Params& p0, pc_stream_t stream) {
+  Params p = p0;
+  const uint32_t st = stage_bytes<BN, PREC>();
+  int stages = (int)(SMEM_BUDGET / st);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  if (stages > p.n_kc) stages = p.n_kc < 2 ? 2 : p.n_kc;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + sizeof(float) * 3 * BN + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    PC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  dim3 grid(ceil_div(p.M, BM), p.Npad / BN);
+  igemm_tc_kernel<BN, PREC><<<grid, THREADS, smem, stream>>>(p);
+  PC_LAUNCH_CHECK("igemm_tc_kernel");
+  return PC_OK;
+}
+
+static int dispatch(const Params& p, int prec, pc_stream_t stream) {
+  const int bn = pick_bn(p.Nn);
+  if (prec == PC_PREC_TF32X3) {
+    if (bn == 32) return launch<32, PC_PREC_TF32X3>(p, stream);
+    if (bn == 64) return launch<64, PC_PREC_TF32X3>(p, stream);
+    return launch<128, PC_PREC_TF32X3>(p, stream);
+  }
+  if (bn == 32) return launch<32, PC_PREC_BF16>(p, stream);
+  if (bn == 64) return launch<64, PC_PREC_BF16>(p, stream);
+  return launch<128, PC_PREC_BF16>(p, stream);
+}
+
+}  // namespace tcconv
+}  // namespace pc
+
+using namespace pc;
+using namespace pc::tcconv;
+
+extern "C" int pc_conv_tc_supported(const PcConvGeom* g, int dgrad, int prec) {
+  if (g == nullptr || (prec != PC_PREC_TF32X3 && prec != PC_PREC_BF16)) return 0;
+  const int ca = dgrad ? g->Cout : g->Cin, nn = dgrad ? g->Cin : g->Cout;
+  return (ca % bkc_of(prec) == 0 && nn % 4 == 0 && nn >= 16) ? 1 : 0;
+}
+
+extern "C" size_t pc_conv_tc_packed_bytes(int O, int I, int R, int S, int dgrad, int prec) {
+  const int ca = dgrad ? O : I, nn = dgrad ? I : O;
+  return (size_t)R * S * (ca / bkc_of(prec)) * parts_of(prec) * npad_of(nn) * 128;
+}
+
+extern "C" int pc_pack_conv_weight_tc(const float* w_oihw, int O, int I, int R, int S, int dgrad, int prec, void* out,
+                                      pc_stream_t stream) {
+  PC_REQUIRE(w_oihw && out && O > 0 && I > 0 && R > 0 && S > 0, PC_EINVAL, "pc_pack_conv_weight_tc: bad arguments");
+  PC_REQUIRE(prec == PC_PREC_TF32X3 || prec == PC_PREC_BF16, PC_EINVAL, "pc_pack_conv_weight_tc: precision must be TF32X3 or BF16");
+  const int ca = dgrad ? O : I, nn = dgrad ? I : O;
+  PC_REQUIRE(ca % bkc_of(prec) == 0, PC_EUNSUPPORTED, "pc_pack_conv_weight_tc: %d channels not a multiple of %d", ca, bkc_of(prec));
+  const int npad = npad_of(nn);
+  const long long total = (long long)R * S * (ca / bkc_of(prec)) * npad * 8;
+  int grid = ceil_div(total, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (prec == PC_PREC_TF32X3)
+    pack_b_kernel<PC_PREC_TF32X3><<<grid, 256, 0, stream>>>(w_oihw, O, I, R, S, dgrad ? 1 : 0, 0, nn, npad, ca, (unsigned char*)out);
+  else
+    pack_b_kernel<PC_PREC_BF16><<<grid, 256, 0, stream>>>(w_oihw, O, I, R, S, dgrad ? 1 : 0, 0, nn, npad, ca, (unsigned char*)out);
+  PC_LAUNCH_CHECK("pack_b_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias, const PcConvGeom* g, const PcInXform* xf, float* y,
+                              double* stats, int prec, pc_stream_t stream) {
+  if (!pc_conv_tc_supported(g, 0, prec)) return PC_EUNSUPPORTED;
+  Params p{};
+  p.A = x; p.Bp = (const unsigned char*)wp; p.bias = bias; p.C = y; p.stats = stats;
+  if (xf != nullptr) { p.xf.scale = xf->scale; p.xf.shift = xf->shift; p.xf.drop = xf->drop; p.xf.relu = xf->relu; }
+  p.g = *g; p.mode = 0;
+  p.M = (long long)g->B * g->Ho * g->Wo;
+  p.Nn = g->Cout; p.Npad = npad_of(g->Cout); p.Ca = g->Cin;
+  p.n_kc = g->R * g->S * (g->Cin / bkc_of(prec));
+  p.accumulate = 0;
+  return dispatch(p, prec, stream);
+}
+
+extern "C" int pc_conv_dgrad_tc(const float* dy, const void* wp, const PcConvGeom* g, float* dx, int accumulate, int prec,
+                                pc_stream_t stream) {
+  if (!pc_conv_tc_supported(g, 1, prec)) return PC_EUNSUPPORTED;
+  Params p{};
+  p.A = dy; p.Bp = (const unsigned char*)wp; p.C = dx;
+  p.g = *g; p.mode = 1;
+  p.M = (long long)g->B * g->H * g->W;
+  p.Nn = g->Cin; p.Npad = npad_of(g->Cin); p.Ca = g->Cout;
+  p.n_kc = g->R * g->S * (g->Cout / bkc_of(prec));
+  p.accumulate = accumulate;
+  return dispatch(p, prec, stream);
+}
+
+// C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) on the tensor cores; ws >= pc_tc_gemm_workspace(N, K, prec) bytes.
+extern "C" size_t pc_tc_gemm_workspace(int N, int K, int prec) {
+  return (size_t)(K / bkc_of(prec)) * parts_of(prec) * npad_of(N) * 128;
+}
+
+extern "C" int pc_tc_gemm(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int prec, void* ws,
+                          size_t ws_bytes, pc_stream_t stream) {
+  PC_REQUIRE(A && B && C && ws && M > 0 && N > 0 && K > 0, PC_EINVAL, "pc_tc_gemm: bad arguments");
+  PC_REQUIRE(prec == PC_PREC_TF32X3 || prec == PC_PREC_BF16, PC_EINVAL, "pc_tc_gemm: precision must be TF32X3 or BF16");
+  PC_REQUIRE(K % bkc_of(prec) == 0 && N % 4 == 0 && N >= 16, PC_EUNSUPPORTED, "pc_tc_gemm: K=%d must be a multiple of %d, N=%d of 4", K,
+             bkc_of(prec), N);
+  PC_REQUIRE(ws_bytes >= pc_tc_gemm_workspace(N, K, prec), PC_EINVAL, "pc_tc_gemm: workspace too small");
+  const int npad = npad_of(N);
+  const long long total = (long long)(K / bkc_of(prec)) * npad * 8;
+  int grid = ceil_div(total, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  if (prec == PC_PREC_TF32X3)
+    pack_b_kernel<PC_PREC_TF32X3><<<grid, 256, 0, stream>>>(B, 0, 0, 1, 1, 2, K, N, npad, K, (unsigned char*)ws);
+  else
+    pack_b_kernel<PC_PREC_BF16><<<grid, 256, 0, stream>>>(B, 0, 0, 1, 1, 2, K, N, npad, K, (unsigned char*)ws);
+  PC_LAUNCH_CHECK("pack_b_kernel");
+  Params p{};
+  p.A = A; p.Bp = (const unsigned char*)ws; p.bias = bias; p.C = C;
+  p.mode = 2; p.M = M; p.Nn = N; p.Npad = npad; p.Ca = K; p.n_kc = K / bkc_of(prec); p.lda = K;
+  p.g.S = 1; p.g.R = 1; p.g.stride = 1;
+  return dispatch(p, prec, stream);
 }

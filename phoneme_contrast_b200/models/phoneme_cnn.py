@@ -150,20 +150,22 @@ def _small_forward(net, x, training):
         co = chans[b]
         gA = ops.conv_geom(B, h, w, cin, co, 3, 1, 1)
         if cin == 1:
-            wfA, wdA = convA.weight, None          # stem kernel reads OIHW directly; no dgrad into the input
+            cwA = None                             # stem kernel reads OIHW directly; no dgrad into the input
+            wfA, precA = convA.weight, L.PREC_FP32
         else:
-            wfA, wdA = ops.pack_conv_weight(convA.weight)
+            cwA = ops.ConvWeights(convA.weight, gA, prec)
+            wfA, precA = cwA.wf, cwA.prec_f
         stA = slots.take(co)
-        yA = ops.conv_fwd(cur, wfA, convA.bias, gA, None, stA, prec)
+        yA = ops.conv_fwd(cur, wfA, convA.bias, gA, None, stA, precA)
         coA = ops.bn_finalize(stA, B * gA.Ho * gA.Wo, bnA, training)
         gB = ops.conv_geom(B, h, w, co, co, 3, 1, 1)
-        wfB, wdB = ops.pack_conv_weight(convB.weight)
+        cwB = ops.ConvWeights(convB.weight, gB, prec)
         stB = slots.take(co)
-        yB = ops.conv_fwd(yA, wfB, convB.bias, gB, dict(scale=coA.scale, shift=coA.shift, relu=True), stB, prec)
+        yB = ops.conv_fwd(yA, cwB.wf, convB.bias, gB, dict(scale=coA.scale, shift=coA.shift, relu=True), stB, cwB.prec_f)
         coB = ops.bn_finalize(stB, B * h * w, bnB, training)
         pool = 2 if b < 2 else 0
         out, _ = ops.bn_act_fwd(yB, coB, pool, s.drop[b])
-        s.layers.append(dict(xin=cur, gA=gA, gB=gB, yA=yA, yB=yB, coA=coA, coB=coB, wdA=wdA, wdB=wdB, pool=pool))
+        s.layers.append(dict(xin=cur, gA=gA, gB=gB, yA=yA, yB=yB, coA=coA, coB=coB, cwA=cwA, cwB=cwB, pool=pool))
         cur, cin = out, co
         h, w = ops.pool_dims(h, w, pool)
     s.a_last = cur
@@ -181,11 +183,11 @@ def _small_backward(net, s, demb, grads, training=True):
         dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias])
         xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
         ops.conv_wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], grads[convB.bias], prec)
-        dA = ops.conv_dgrad(dyB, ly["wdB"], ly["gB"], prec=prec)
+        dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d)
         dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias])
         ops.conv_wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], grads[convA.bias], prec)
         if b > 0:
-            dout = ops.conv_dgrad(dyA, ly["wdA"], ly["gA"], prec=prec)
+            dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d)
 
 
 def _deep_forward(net, x, training):
@@ -212,25 +214,25 @@ def _deep_forward(net, x, training):
         co = hd[i]
         stride = blk.stride
         g1 = ops.conv_geom(B, h, w, cin, co, 3, stride, 1)
-        wf1, wd1 = ops.pack_conv_weight(blk.conv1.weight)
+        cw1 = ops.ConvWeights(blk.conv1.weight, g1, prec)
         st1 = st(co)
-        y1 = ops.conv_fwd(cur, wf1, blk.conv1.bias, g1, None, st1, prec)
+        y1 = ops.conv_fwd(cur, cw1.wf, blk.conv1.bias, g1, None, st1, cw1.prec_f)
         c1 = ops.bn_finalize(st1, B * g1.Ho * g1.Wo, blk.bn1, training)
         g2 = ops.conv_geom(B, g1.Ho, g1.Wo, co, co, 3, 1, 1)
-        wf2, wd2 = ops.pack_conv_weight(blk.conv2.weight)
+        cw2 = ops.ConvWeights(blk.conv2.weight, g2, prec)
         st2 = st(co)
-        y2 = ops.conv_fwd(y1, wf2, blk.conv2.bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True, drop=s.drop[i]), st2, prec)
+        y2 = ops.conv_fwd(y1, cw2.wf, blk.conv2.bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True, drop=s.drop[i]), st2, cw2.prec_f)
         c2 = ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk.bn2, training)
-        rec = dict(xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, wd1=wd1, wd2=wd2, proj=len(blk.shortcut) > 0)
+        rec = dict(xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, cw1=cw1, cw2=cw2, proj=len(blk.shortcut) > 0)
         if rec["proj"]:
             convs, bns = blk.shortcut[0], blk.shortcut[1]
             gs = ops.conv_geom(B, h, w, cin, co, 1, stride, 0)
-            wfs, wds = ops.pack_conv_weight(convs.weight)
+            cws = ops.ConvWeights(convs.weight, gs, prec)
             sts = st(co)
-            ys = ops.conv_fwd(cur, wfs, convs.bias, gs, None, sts, prec)
+            ys = ops.conv_fwd(cur, cws.wf, convs.bias, gs, None, sts, cws.prec_f)
             cs = ops.bn_finalize(sts, B * gs.Ho * gs.Wo, bns, training)
             out = ops.bn_add_relu_fwd(y2, c2, ys, cs)
-            rec.update(gs=gs, ys=ys, cs=cs, wds=wds)
+            rec.update(gs=gs, ys=ys, cs=cs, cws=cws)
         else:
             out = ops.bn_add_relu_fwd(y2, c2, cur, None)
         rec["out"] = out
@@ -256,15 +258,15 @@ def _deep_backward(net, s, demb, grads, training=True):
             dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None)
         xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
         ops.conv_wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec)
-        dA1 = ops.conv_dgrad(dy2, r["wd2"], r["g2"], prec=prec)
+        dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d)
         dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias])
         ops.conv_wgrad(r["xin"], dy1, r["g1"], None, grads[blk.conv1.weight], grads[blk.conv1.bias], prec)
         if r["proj"]:
             ops.conv_wgrad(r["xin"], dysc, r["gs"], None, grads[convs.weight], grads[convs.bias], prec)
-            dxin = ops.conv_dgrad(dysc, r["wds"], r["gs"], prec=prec)
+            dxin = ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], prec=r["cws"].prec_d)
         else:
             dxin = dysc                                        # identity shortcut: d(out)/d(xin) passes g through
-        ops.conv_dgrad(dy1, r["wd1"], r["g1"], out=dxin, accumulate=True, prec=prec)
+        ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d)
         dout = dxin
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
     st = s.stem
@@ -296,8 +298,17 @@ class _NetFunction(torch.autograd.Function):
             grads[p] = v
         net._engine_backward(saved, demb.contiguous().to(torch.float32), grads)
         ctx.saved = None
-        del grads, flat
-        return (None, None, *views)
+        # Hand the bucket to the parameters. Where .grad is empty (the usual case after zero_grad(set_to_none=True))
+        # the view is installed directly, so every .grad aliases ONE flat buffer in parameter order and the fused
+        # optimiser / the DP all-reduce need no gather; otherwise autograd accumulates the returned view as usual.
+        out = []
+        for p, v in zip(params, views):
+            if p.grad is None and p.requires_grad:
+                p.grad = v
+                out.append(None)
+            else:
+                out.append(v if p.requires_grad else None)
+        return (None, None, *out)
 
 
 class _FusedNet(BaseModel):

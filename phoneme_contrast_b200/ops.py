@@ -35,12 +35,56 @@ def pack_conv_weight(w: torch.Tensor, want_fwd=True, want_dgrad=True):
     return wf, wd
 
 
+def tc_supported(g: PcConvGeom, dgrad: bool, prec: int) -> bool:
+    return prec != L.PREC_FP32 and bool(L.lib().pc_conv_tc_supported(C.byref(g), 1 if dgrad else 0, prec))
+
+
+def pack_conv_weight_tc(w: torch.Tensor, dgrad: bool, prec: int) -> torch.Tensor:
+    """Pre-swizzled tensor-core weight tiles (pc_pack_conv_weight_tc) for the forward (dgrad=False) or data-gradient GEMM."""
+    O, I, R, S = w.shape
+    nbytes = int(L.lib().pc_conv_tc_packed_bytes(O, I, R, S, 1 if dgrad else 0, prec))
+    out = torch.empty(nbytes, device=w.device, dtype=torch.uint8)
+    call("pc_pack_conv_weight_tc", ptr(w), O, I, R, S, 1 if dgrad else 0, prec, ptr(out, torch.uint8), stream())
+    return out
+
+
+class ConvWeights:
+    """Per-step packed forms of one conv weight: forward operand, data-gradient operand, and the precision each runs in
+    (tensor cores when the layer is eligible, exact-fp32 SIMT otherwise)."""
+    __slots__ = ("wf", "wd", "prec_f", "prec_d")
+
+    def __init__(self, w: torch.Tensor, g: PcConvGeom, prec: int, need_dgrad: bool = True):
+        self.prec_f = prec if tc_supported(g, False, prec) else L.PREC_FP32
+        self.prec_d = prec if tc_supported(g, True, prec) else L.PREC_FP32
+        self.wf = self.wd = None
+        need_simt_f = self.prec_f == L.PREC_FP32
+        need_simt_d = need_dgrad and self.prec_d == L.PREC_FP32
+        if need_simt_f or need_simt_d:
+            wf, wd = pack_conv_weight(w, need_simt_f, need_simt_d)
+            self.wf, self.wd = wf, wd
+        if not need_simt_f:
+            self.wf = pack_conv_weight_tc(w, False, self.prec_f)
+        if need_dgrad and not need_simt_d:
+            self.wd = pack_conv_weight_tc(w, True, self.prec_d)
+
+
+def tc_gemm(a: torch.Tensor, b: torch.Tensor, bias=None, prec=L.PREC_TF32X3) -> torch.Tensor:
+    """C = A @ B^T (+ bias) through the tcgen05 tile engine."""
+    M, K = a.shape
+    N = b.shape[0]
+    nbytes = int(L.lib().pc_tc_gemm_workspace(N, K, prec))
+    ws = torch.empty(nbytes, device=a.device, dtype=torch.uint8)
+    c = torch.empty(M, N, device=a.device, dtype=F32)
+    call("pc_tc_gemm", ptr(a), ptr(b), ptr(bias), ptr(c), M, N, K, prec, ptr(ws, torch.uint8), nbytes, stream())
+    return c
+
+
 def conv_fwd(x, w, bias, g: PcConvGeom, xform=None, stats=None, prec=L.PREC_FP32):
     """x NHWC [B,H,W,Cin]; w = packed Wf (Cin>1) or the raw OIHW weight (Cin==1 stem)."""
     y = torch.empty(g.B, g.Ho, g.Wo, g.Cout, device=x.device, dtype=F32)
     xf = _xf(**xform) if xform else None
     L.note_work("pc_conv_fwd", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
-    call("pc_conv_fwd", ptr(x), ptr(w), ptr(bias), C.byref(g), C.byref(xf) if xf is not None else None, ptr(y),
+    call("pc_conv_fwd", ptr(x), ptr(w, None), ptr(bias), C.byref(g), C.byref(xf) if xf is not None else None, ptr(y),
          ptr(stats, torch.float64), prec, stream())
     return y
 
@@ -49,7 +93,7 @@ def conv_dgrad(dy, wd, g: PcConvGeom, out=None, accumulate=False, prec=L.PREC_FP
     if out is None:
         out = torch.empty(g.B, g.H, g.W, g.Cin, device=dy.device, dtype=F32)
     L.note_work("pc_conv_dgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
-    call("pc_conv_dgrad", ptr(dy), ptr(wd), C.byref(g), ptr(out), 1 if accumulate else 0, prec, stream())
+    call("pc_conv_dgrad", ptr(dy), ptr(wd, None), C.byref(g), ptr(out), 1 if accumulate else 0, prec, stream())
     return out
 
 
