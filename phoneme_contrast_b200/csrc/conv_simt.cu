@@ -493,6 +493,12 @@ conv_stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy
   }
 }
 
+void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream) {
+  const long long total = (long long)(R * S * Cin + 1) * Cout;
+  conv_wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(partial, n_splits, R, S, Cin, Cout, dw, db);
+  count_launch();
+}
+
 static inline XformDev to_dev(const PcInXform* xf) {
   XformDev d{nullptr, nullptr, nullptr, 0};
   if (xf != nullptr) { d.scale = xf->scale; d.shift = xf->shift; d.drop = xf->drop; d.relu = xf->relu; }
@@ -618,8 +624,24 @@ extern "C" int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom*
   return PC_OK;
 }
 
+extern "C" int pc_conv_wgrad_tc_supported(const PcConvGeom* g);
+extern "C" size_t pc_conv_wgrad_tc_workspace(const PcConvGeom* g);
+extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw, float* db,
+                                void* workspace, size_t workspace_bytes, pc_stream_t stream);
+
+static size_t wgrad_workspace_simt(const PcConvGeom* g);
+
 extern "C" size_t pc_conv_wgrad_workspace(const PcConvGeom* g) {
   if (g == nullptr) return 0;
+  size_t a = wgrad_workspace_simt(g);
+  if (g->Cin != 1 && pc_conv_wgrad_tc_supported(g)) {
+    const size_t b = pc_conv_wgrad_tc_workspace(g);
+    if (b > a) a = b;
+  }
+  return a;
+}
+
+static size_t wgrad_workspace_simt(const PcConvGeom* g) {
   if (g->Cin == 1) return (size_t)stem_wgrad_ctas(g) * (size_t)(g->R * g->S + 1) * g->Cout * sizeof(float);
   int rps;
   const int splits = wgrad_splits(g, &rps);
@@ -633,7 +655,9 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
   PC_REQUIRE(x && dy && dw_oihw && workspace, PC_EINVAL, "pc_conv_wgrad: null pointer");
   PC_REQUIRE(workspace_bytes >= pc_conv_wgrad_workspace(g), PC_EINVAL, "pc_conv_wgrad: workspace too small (%zu < %zu)", workspace_bytes,
              pc_conv_wgrad_workspace(g));
-  (void)prec;
+  // tensor-core path (TF32x3) for eligible layers whenever a tensor-core precision is requested
+  if (prec != PC_PREC_FP32 && g->Cin != 1 && pc_conv_wgrad_tc_supported(g))
+    return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, stream);
   float* partial = static_cast<float*>(workspace);
   int n_partials;
   if (g->Cin == 1) {

@@ -3,13 +3,13 @@
 //
 //   D[128 x BN] (fp32, TMEM)  +=  A[128 x K] * B[BN x K]^T        K = taps x channels, walked in 128-byte k-chunks
 //
-// Warp roles (192 threads, one CTA per 128-row M tile x BN-column N tile):
-//   warps 0-3  producers, then epilogue. The A operand is an im2col GATHER with the previous layer's
+// Warp roles (14 warps, one CTA per 128-row M tile x BN-column N tile):
+//   warps 0-11 three producer groups of 4 warps (group g fills k-chunks g, g+3, ...), then all join the epilogue. The A operand is an im2col GATHER with the previous layer's
 //              BatchNorm-apply + ReLU + Dropout2d folded in, so it cannot come from TMA: 8 lanes fetch one
 //              pixel's 128 contiguous bytes (coalesced), transform, convert, and store them into the
 //              SWIZZLE_128B K-major tile the UMMA descriptor expects; fence.proxy.async; mbarrier arrive.
-//   warp 4     allocates TMEM, then one lane issues tcgen05.mma (D in TMEM) and tcgen05.commit per stage.
-//   warp 5     one lane streams the pre-swizzled weight tiles with 1-D bulk async copies (cp.async.bulk, TMA
+//   warp 12    allocates TMEM, then one lane issues tcgen05.mma (D in TMEM) and tcgen05.commit per stage.
+//   warp 13    one lane streams the pre-swizzled weight tiles with 1-D bulk async copies (cp.async.bulk, TMA
 //              engine) that complete on the same "full" mbarrier as the producers' arrivals.
 //   epilogue   tcgen05.ld (32 lanes x 32 columns per instruction) -> + bias -> BatchNorm sum / sum-of-squares via a
 //              31-shuffle warp reduce-scatter -> NHWC fp32 store.
@@ -28,8 +28,11 @@ namespace tcconv {
 using namespace pc::tc;
 
 constexpr int BM = 128;
-constexpr int NPROD = 128;
-constexpr int THREADS = 192;
+constexpr int NPROD = 128;            // threads that fill one stage (one producer group)
+constexpr int NGROUPS = 3;            // producer groups; group g owns k-chunks g, g+NGROUPS, ... so that the global-load
+                                      // latency of several stages is in flight at once (one group alone is latency-bound)
+constexpr int PROD_WARPS = 4 * NGROUPS;
+constexpr int THREADS = 32 * (PROD_WARPS + 2);
 constexpr int MAX_STAGES = 6;
 constexpr uint32_t SMEM_BUDGET = 200 * 1024;
 
@@ -51,7 +54,13 @@ struct Params {
   int mode;          // 0 conv fwd gather, 1 conv dgrad gather, 2 plain row-major A [M][lda]
   long long M;
   int Nn, Npad, Ca, n_kc, lda, accumulate, stages;
+  long long* dbg;    // optional [gridDim.x*gridDim.y][16] clock64 stamps (diagnostics, see pc_tc_set_debug)
 };
+
+#define PC_STAMP(slot)                                                                                 \
+  do {                                                                                                 \
+    if (p.dbg != nullptr) p.dbg[((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 16 + (slot)] = clock64(); \
+  } while (0)
 
 template <int PREC> struct Prec;
 // NACC: TMEM accumulators per tile. The tensor core adds into its fp32 accumulator with truncation, so a long
@@ -98,8 +107,11 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);                        // [BN]
   float* s_sum = s_bias + BN;                                                     // [BN]
   float* s_sq = s_sum + BN;                                                       // [BN]
+  int* s_off0 = reinterpret_cast<int*>(s_sq + BN);                                // [BM] per-row window-origin offset
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_off0 + BM);                    // [BM] per-row valid-tap bitmask
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) PC_STAMP(0);
   const long long m0 = (long long)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
 
@@ -109,7 +121,57 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
     s_sum[tid] = 0.f;
     s_sq[tid] = 0.f;
   }
-  if (warp == 4) {
+  // ---- row_info: one thread per tile row computes the element offset of the row's window origin in the gathered
+  // tensor and the bitmask of taps that fall inside it; per k-chunk a row then costs one bit test and one add.
+  //   fwd   : pixel (b,ho,wo) reads x[b, ho*stride - pad + r, wo*stride - pad + s, :]          -> off0 + (r*Wa + s)*Ca
+  //   dgrad : pixel (b,h,w) reads dy[b, (h+pad-r)/stride, (w+pad-s)/stride, :] when divisible  -> off0 - ((r/stride)*Wa + s/stride)*Ca
+  //           (for a valid tap (h+pad-r)/stride == floor((h+pad)/stride) - floor(r/stride))
+  if (tid < BM) {
+    const PcConvGeom g = p.g;
+    const int Hr = p.mode == 0 ? g.Ho : g.H, Wr = p.mode == 0 ? g.Wo : g.W;
+    const int Ha = p.mode == 0 ? g.H : g.Ho, Wa = p.mode == 0 ? g.W : g.Wo;
+    const int st = g.stride;
+    const int m = (int)m0 + tid;
+    int off = 0;
+    uint32_t mask = 0u;
+    if (m < (int)p.M) {
+      if (p.mode == 2) {
+        off = m * p.lda;
+        mask = 1u;
+      } else {
+        const int wq = m % Wr, t = m / Wr;
+        const int hq = t % Hr, bq = t / Hr;
+        int hb, wb;
+        if (p.mode == 0) {
+          hb = hq * st - g.pad;
+          wb = wq * st - g.pad;
+          uint32_t wmask = 0u;
+          for (int ts = 0; ts < g.S; ++ts)
+            if ((unsigned)(wb + ts) < (unsigned)Wa) wmask |= 1u << ts;
+          for (int tr = 0; tr < g.R; ++tr)
+            if ((unsigned)(hb + tr) < (unsigned)Ha) mask |= wmask << (tr * g.S);
+        } else {
+          const int hp = hq + g.pad, wp = wq + g.pad;
+          hb = hp / st;
+          wb = wp / st;
+          const int hpar = hp - hb * st, wpar = wp - wb * st;
+          uint32_t wmask = 0u;
+          for (int ts = 0; ts < g.S; ++ts) {
+            const int q = ts / st;
+            if (ts - q * st == wpar && (unsigned)(wb - q) < (unsigned)Wa) wmask |= 1u << ts;
+          }
+          for (int tr = 0; tr < g.R; ++tr) {
+            const int q = tr / st;
+            if (tr - q * st == hpar && (unsigned)(hb - q) < (unsigned)Ha) mask |= wmask << (tr * g.S);
+          }
+        }
+        off = ((bq * Ha + hb) * Wa + wb) * p.Ca;
+      }
+    }
+    s_off0[tid] = off;
+    s_mask[tid] = mask;
+  }
+  if (warp == PROD_WARPS) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(&full[s], NPROD + 1);
@@ -125,42 +187,54 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) PC_STAMP(1);
 
-  if (warp < 4) {
+  if (warp < PROD_WARPS) {
     // ============================================================ producers
-    const int j = tid & 7;          // 16-byte chunk of the 128-byte k-chunk row
-    const int rg = tid >> 3;        // rows rg + 16*i
-    // per-row decode (8 rows per thread)
-    int rb[8], rh[8], rw[8];
+    const int group = warp >> 2;            // producer group
+    const int gt = tid & (NPROD - 1);       // thread index inside the group
+    const int j = gt & 7;           // 16-byte chunk of the 128-byte k-chunk row
+    const int rg = gt >> 3;         // rows rg + 16*i
+    // per-row window-origin offsets and valid-tap masks were computed once per CTA (see row_info above)
     const PcConvGeom g = p.g;
-    const int Hr = p.mode == 0 ? g.Ho : g.H, Wr = p.mode == 0 ? g.Wo : g.W;
     const int Ha = p.mode == 0 ? g.H : g.Ho, Wa = p.mode == 0 ? g.W : g.Wo;
+    int off0[8];
+    uint32_t tapmask[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const long long m = m0 + rg + 16 * i;
-      if (m < p.M) {
-        if (p.mode == 2) {
-          rb[i] = 0; rh[i] = 0; rw[i] = 0;
-        } else {
-          rw[i] = (int)(m % Wr);
-          rh[i] = (int)((m / Wr) % Hr);
-          rb[i] = (int)(m / ((long long)Wr * Hr));
-        }
-      } else {
-        rb[i] = -1; rh[i] = 0; rw[i] = 0;
-      }
+      off0[i] = s_off0[rg + 16 * i];
+      tapmask[i] = s_mask[rg + 16 * i];
     }
     const int cpt = p.Ca / BKC;     // k-chunks per tap
     constexpr int EPC = (PREC == PC_PREC_BF16) ? 8 : 4;   // source elements per 16-byte destination chunk
-    for (int kc = 0; kc < p.n_kc; ++kc) {
+    const bool has_aff = (p.mode == 0 && p.xf.scale != nullptr);
+    const bool has_relu = (p.mode == 0 && p.xf.relu);
+    const bool has_drop = (p.mode == 0 && p.xf.drop != nullptr);
+    const uint32_t soff0 = sw128_offset((uint32_t)rg, (uint32_t)j);     // rows rg + 16*i share (row & 7): + 2048*i
+    if (tid == 0) PC_STAMP(2);
+    for (int kc = group; kc < p.n_kc; kc += NGROUPS) {
       const int s = kc % S;
       const uint32_t ph = (uint32_t)(kc / S) & 1u;
-      mbar_wait(&empty[s], ph ^ 1u);
       const int tap = kc / cpt;
       const int c0 = (kc - tap * cpt) * BKC + j * EPC;      // first channel of my chunk
-      const int tr = tap / g.S, ts = tap - tr * g.S;
+      int tap_off;
+      if (p.mode == 0) { const int tr = tap / g.S; tap_off = (tr * Wa + (tap - tr * g.S)) * p.Ca; }
+      else if (p.mode == 1) { const int tr = tap / g.S; tap_off = -((tr / g.stride) * Wa + (tap - tr * g.S) / g.stride) * p.Ca; }
+      else tap_off = 0;
+      const float* src_base = p.A + tap_off + c0;
+      // issue this chunk's global loads before waiting for the smem slot
+      float v[8][EPC];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const bool ok = (tapmask[i] >> tap) & 1u;
+#pragma unroll
+        for (int q = 0; q < EPC; q += 4) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) t = *reinterpret_cast<const float4*>(src_base + off0[i] + q);
+          v[i][q] = t.x; v[i][q + 1] = t.y; v[i][q + 2] = t.z; v[i][q + 3] = t.w;
+        }
+      }
       float sc[EPC], sh[EPC];
-      const bool has_aff = (p.mode == 0 && p.xf.scale != nullptr);
       if (has_aff) {
 #pragma unroll
         for (int q = 0; q < EPC; q += 4) {
@@ -170,85 +244,65 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
           sh[q] = b.x; sh[q + 1] = b.y; sh[q + 2] = b.z; sh[q + 3] = b.w;
         }
       }
-      unsigned char* a_hi = tiles + (size_t)s * STAGE;
+      mbar_wait(&empty[s], ph ^ 1u);
+      unsigned char* a_hi = tiles + (size_t)s * STAGE + soff0;
       unsigned char* a_lo = a_hi + A_PART;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int r = rg + 16 * i;
-        float v[EPC];
-#pragma unroll
-        for (int q = 0; q < EPC; ++q) v[q] = 0.f;
-        bool ok = rb[i] >= 0;
-        const float* src = nullptr;
-        if (p.mode == 2) {
-          if (ok) src = p.A + (size_t)(m0 + r) * p.lda + c0;
-        } else {
-          int ha, wa;
-          if (p.mode == 0) {
-            ha = rh[i] * g.stride - g.pad + tr;
-            wa = rw[i] * g.stride - g.pad + ts;
-          } else {
-            const int hn = rh[i] + g.pad - tr, wn = rw[i] + g.pad - ts;
-            ok = ok && hn >= 0 && wn >= 0 && (hn % g.stride == 0) && (wn % g.stride == 0);
-            ha = hn / g.stride;
-            wa = wn / g.stride;
-          }
-          ok = ok && ha >= 0 && ha < Ha && wa >= 0 && wa < Wa;
-          if (ok) src = p.A + (((size_t)rb[i] * Ha + ha) * Wa + wa) * p.Ca + c0;
-        }
+        const bool ok = (tapmask[i] >> tap) & 1u;
         if (ok) {
-#pragma unroll
-          for (int q = 0; q < EPC; q += 4) {
-            const float4 t = *reinterpret_cast<const float4*>(src + q);
-            v[q] = t.x; v[q + 1] = t.y; v[q + 2] = t.z; v[q + 3] = t.w;
-          }
           if (has_aff) {
 #pragma unroll
-            for (int q = 0; q < EPC; ++q) v[q] = fmaf(v[q], sc[q], sh[q]);
+            for (int q = 0; q < EPC; ++q) v[i][q] = fmaf(v[i][q], sc[q], sh[q]);
           }
-          if (p.mode == 0 && p.xf.relu) {
+          if (has_relu) {
 #pragma unroll
-            for (int q = 0; q < EPC; ++q) v[q] = fmaxf(v[q], 0.f);
+            for (int q = 0; q < EPC; ++q) v[i][q] = fmaxf(v[i][q], 0.f);
           }
-          if (p.mode == 0 && p.xf.drop != nullptr) {
+          if (has_drop) {
+            const int b = (off0[i] + tap_off) / (Ha * Wa * p.Ca);   // sample index of the (valid, in-image) source pixel
 #pragma unroll
             for (int q = 0; q < EPC; q += 4) {
-              const float4 d = *reinterpret_cast<const float4*>(p.xf.drop + (size_t)rb[i] * p.Ca + c0 + q);
-              v[q] *= d.x; v[q + 1] *= d.y; v[q + 2] *= d.z; v[q + 3] *= d.w;
+              const float4 d = *reinterpret_cast<const float4*>(p.xf.drop + (size_t)b * p.Ca + c0 + q);
+              v[i][q] *= d.x; v[i][q + 1] *= d.y; v[i][q + 2] *= d.z; v[i][q + 3] *= d.w;
             }
           }
         }
-        const uint32_t off = sw128_offset((uint32_t)r, (uint32_t)j);
         if (PREC == PC_PREC_TF32X3) {
           float h[4], l[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
-          *reinterpret_cast<float4*>(a_hi + off) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(a_lo + off) = make_float4(l[0], l[1], l[2], l[3]);
+          for (int q = 0; q < 4; ++q) split_tf32(v[i][q], h[q], l[q]);
+          *reinterpret_cast<float4*>(a_hi + 2048 * i) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>(a_lo + 2048 * i) = make_float4(l[0], l[1], l[2], l[3]);
         } else {
           uint4 w;
-          w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
-          w.z = pack_bf16(v[4 % EPC], v[5 % EPC]); w.w = pack_bf16(v[6 % EPC], v[7 % EPC]);
-          *reinterpret_cast<uint4*>(a_hi + off) = w;
+          w.x = pack_bf16(v[i][0], v[i][1]); w.y = pack_bf16(v[i][2], v[i][3]);
+          w.z = pack_bf16(v[i][4 % EPC], v[i][5 % EPC]); w.w = pack_bf16(v[i][6 % EPC], v[i][7 % EPC]);
+          *reinterpret_cast<uint4*>(a_hi + 2048 * i) = w;
         }
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
+      if (tid == 0 && kc == 0) PC_STAMP(3);
+      if (tid == 0 && kc == 3) PC_STAMP(4);
     }
+    if (tid == 0) PC_STAMP(5);
 
-    // ============================================================ epilogue (thread = tile row = TMEM lane)
+    // ============================================================ epilogue
+    // warp w reads TMEM lanes 32*(w%4).. (its hardware lane quarter) = tile rows, and the 32-column chunks w/4, w/4+NGROUPS, ..
     mbar_wait(acc_full, 0);
     tc_fence_after();
-    const int r = tid;
+    if (tid == 0) PC_STAMP(6);
+    const int r = (warp & 3) * 32 + lane;
     const long long m = m0 + r;
     const bool valid = m < p.M;
     float* dst_row = p.C + (size_t)(valid ? m : 0) * p.Nn + n0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
+    for (int c0 = 32 * group; c0 < BN; c0 += 32 * NGROUPS) {
       float v[32];
       {
         uint32_t raw[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
         tmem_ld_32x32(taddr, raw);
         tmem_ld_wait();
 #pragma unroll
@@ -296,7 +350,7 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
       }
     }
     if (p.stats != nullptr) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");     // the four epilogue warps only
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * PROD_WARPS) : "memory");     // producer/epilogue warps only
       if (tid < BN) {
         const int n = n0 + tid;
         if (n < p.Nn) {
@@ -305,7 +359,7 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == PROD_WARPS) {
     // ============================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = instr_desc(PREC == PC_PREC_BF16 ? 1u : 2u, BM, BN);
@@ -314,6 +368,9 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
         const uint32_t ph = (uint32_t)(kc / S) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
+        if (kc == 0) PC_STAMP(8);
+        if (kc == 1) PC_STAMP(9);
+        if (kc == 4) PC_STAMP(10);
         const uint32_t base = smem_u32(tiles + (size_t)s * STAGE);
         const uint64_t a_hi = smem_desc_sw128(base);
         const uint64_t a_lo = smem_desc_sw128(base + A_PART);
@@ -336,6 +393,7 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
         mma_commit(&empty[s]);
       }
       mma_commit(acc_full);
+      PC_STAMP(11);
     }
     __syncwarp();
   } else {
@@ -357,10 +415,12 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
     __syncwarp();
   }
 
+  if (tid == 0) PC_STAMP(7);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 4) tmem_dealloc(tmem_base, NACC * BN);
+  if (warp == PROD_WARPS) tmem_dealloc(tmem_base, NACC * BN);
+  if (tid == 0) PC_STAMP(12);
 }
 
 // ------------------------------------------------------------------------------------------------ weight / B packing
@@ -423,7 +483,7 @@ static int launch(const Params& p0, pc_stream_t stream) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.n_kc) stages = p.n_kc < 2 ? 2 : p.n_kc;
   p.stages = stages;
-  const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + sizeof(float) * 3 * BN + 1024;
+  const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + sizeof(float) * 3 * BN + sizeof(int) * 2 * BM + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     PC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -435,7 +495,11 @@ static int launch(const Params& p0, pc_stream_t stream) {
   return PC_OK;
 }
 
-static int dispatch(const Params& p, int prec, pc_stream_t stream) {
+static long long* g_dbg = nullptr;
+
+static int dispatch(const Params& p_in, int prec, pc_stream_t stream) {
+  Params p = p_in;
+  p.dbg = g_dbg;
   const int bn = pick_bn(p.Nn);
   if (prec == PC_PREC_TF32X3) {
     if (bn == 32) return launch<32, PC_PREC_TF32X3>(p, stream);
@@ -452,6 +516,9 @@ static int dispatch(const Params& p, int prec, pc_stream_t stream) {
 
 using namespace pc;
 using namespace pc::tcconv;
+
+// Diagnostics: when set, every tensor-core tile writes 16 clock64() stamps (see PC_STAMP) to buf[tile][16].
+extern "C" void pc_tc_set_debug(long long* buf) { pc::tcconv::g_dbg = buf; }
 
 extern "C" int pc_conv_tc_supported(const PcConvGeom* g, int dgrad, int prec) {
   if (g == nullptr || (prec != PC_PREC_TF32X3 && prec != PC_PREC_BF16)) return 0;

@@ -1,0 +1,370 @@
+// tcgen05 tensor-core weight gradient (TF32x3):
+//
+//   dW[(tap,c)][n] = sum over output pixels m of  xform(x)[pix(m,tap)][c] * dy[m][n]
+//
+// GEMM view: D[128 (tap,c) rows x BN out-channels] += A'[128 x 8 pixels] * B'[BN x 8 pixels]^T per k-step, where the
+// REDUCTION dimension is the pixel index. In NHWC both operands have the pixel index as their slow dimension and the
+// channel index contiguous, i.e. they are "MN-major" in UMMA terms. MN-major tf32 operands have exactly one legal
+// shared-memory layout, SWIZZLE_128B_BASE32B: atoms of 4 pixel rows x 128 B (32 channels) whose 32-byte chunks are
+// XOR-ed with the row index. Tiles are stored as [channel group of 32][pixel group of 4][4 rows][128 B] and described
+// with LBO = 4096 B (next channel group), SBO = 512 B (next pixel group), a_major = b_major = MN.
+// A 128-row M tile is a run of 128 consecutive (tap, channel) indices, so for Cin = 64 it covers two taps and the
+// producers gather two different input pixels per output pixel.
+//
+// grid = (ceil(K/128), ceil(Cout/BN), splits over pixels); each CTA writes its partial tile to
+// partial[split][K+1][Cout] and conv_wgrad_reduce_kernel (conv_simt.cu) sums the splits in a fixed order into OIHW.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pc {
+namespace tcwg {
+
+using namespace pc::tc;
+
+constexpr int NPROD = 128, NGROUPS = 3, PROD_WARPS = 4 * NGROUPS, THREADS = 32 * (PROD_WARPS + 1);
+constexpr int PIX = 32;                 // pixels per stage (4 k-steps of 8)
+constexpr int MAX_STAGES = 6;
+constexpr uint32_t SMEM_BUDGET = 200 * 1024;
+constexpr int NACC = 4;
+
+struct XformDev {
+  const float* scale;
+  const float* shift;
+  const float* drop;
+  int relu;
+};
+
+struct Params {
+  const float* x;
+  const float* dy;
+  float* partial;
+  XformDev xf;
+  PcConvGeom g;
+  int K, M, rows_per_split, stages;
+};
+
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr_bytes >> 4) & 0x3FFF);
+  d |= (uint64_t)(4096 >> 4) << 16;      // LBO: next 32-channel group
+  d |= (uint64_t)(512 >> 4) << 32;       // SBO: next 4-pixel group (one swizzle atom = 4 pixel rows x 128 B)
+  d |= (uint64_t)1 << 46;                // version
+  d |= (uint64_t)1 << 61;                // SWIZZLE_128B_BASE32B: the only layout for MN-major tf32 operands
+  return d;
+}
+
+template <int BN>
+__host__ __device__ constexpr uint32_t stage_bytes() { return 2u * (4u * 4096u + (BN / 32) * 4096u); }
+
+template <int BN>
+__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Params p) {
+  constexpr uint32_t A_PART = 4 * 4096, B_PART = (BN / 32) * 4096;
+  constexpr uint32_t STAGE = stage_bytes<BN>();
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int S = p.stages;
+  unsigned char* tiles = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)S * STAGE);
+  uint64_t* empty = full + MAX_STAGES;
+  uint64_t* acc_full = empty + MAX_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const PcConvGeom g = p.g;
+  const int kt = blockIdx.x, n0 = blockIdx.y * BN, split = blockIdx.z;
+  const int m_begin = split * p.rows_per_split;
+  const int m_end = min(p.M, m_begin + p.rows_per_split);
+  const int n_stages = (m_end - m_begin + PIX - 1) / PIX;
+
+  if (warp == PROD_WARPS) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) {
+        mbar_init(&full[s], NPROD);
+        mbar_init(&empty[s], 1);
+      }
+      mbar_init(acc_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, NACC * BN);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < PROD_WARPS) {
+    const int group = warp >> 2;
+    const int gt = tid & (NPROD - 1);
+    const int j = gt & 7, pr = gt >> 3;       // 16-byte chunk, pixel row pr (+16)
+    // the four 32-channel groups of this M tile: (tap, first channel)
+    int q_tr[4], q_ts[4], q_c0[4];
+    bool q_ok[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int kidx0 = 128 * kt + 32 * q;
+      q_ok[q] = kidx0 < p.K;
+      const int tap = q_ok[q] ? kidx0 / g.Cin : 0;
+      q_c0[q] = (q_ok[q] ? kidx0 - tap * g.Cin : 0) + 4 * j;
+      q_tr[q] = tap / g.S;
+      q_ts[q] = tap - q_tr[q] * g.S;
+    }
+    const bool has_aff = p.xf.scale != nullptr, has_relu = p.xf.relu != 0, has_drop = p.xf.drop != nullptr;
+    float4 q_sc[4], q_sh[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      q_sc[q] = make_float4(1.f, 1.f, 1.f, 1.f);
+      q_sh[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_aff && q_ok[q]) {
+        q_sc[q] = *reinterpret_cast<const float4*>(p.xf.scale + q_c0[q]);
+        q_sh[q] = *reinterpret_cast<const float4*>(p.xf.shift + q_c0[q]);
+      }
+    }
+    for (int st = group; st < n_stages; st += NGROUPS) {
+      const int s = st % S;
+      const uint32_t ph = (uint32_t)(st / S) & 1u;
+      float4 av[2][4], bv[2][BN / 32];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int pl = pr + 16 * h;
+        const int m = m_begin + st * PIX + pl;
+        const bool mv = m < m_end;
+        int b = 0, ho = 0, wo = 0;
+        if (mv) {
+          wo = m % g.Wo;
+          const int t = m / g.Wo;
+          ho = t % g.Ho;
+          b = t / g.Ho;
+        }
+#pragma unroll
+        for (int q = 0; q < BN / 32; ++q) {
+          const int n = n0 + 32 * q + 4 * j;
+          bv[h][q] = (mv && n < g.Cout) ? *reinterpret_cast<const float4*>(p.dy + (size_t)m * g.Cout + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int hi = ho * g.stride - g.pad + q_tr[q], wi = wo * g.stride - g.pad + q_ts[q];
+          const bool ok = mv && q_ok[q] && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ok) {
+            v = *reinterpret_cast<const float4*>(p.x + (((size_t)b * g.H + hi) * g.W + wi) * g.Cin + q_c0[q]);
+            if (has_aff) v = make_float4(fmaf(v.x, q_sc[q].x, q_sh[q].x), fmaf(v.y, q_sc[q].y, q_sh[q].y), fmaf(v.z, q_sc[q].z, q_sh[q].z), fmaf(v.w, q_sc[q].w, q_sh[q].w));
+            if (has_relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+            if (has_drop) {
+              const float4 d = *reinterpret_cast<const float4*>(p.xf.drop + (size_t)b * g.Cin + q_c0[q]);
+              v = make_float4(v.x * d.x, v.y * d.y, v.z * d.z, v.w * d.w);
+            }
+          }
+          av[h][q] = v;
+        }
+      }
+      mbar_wait(&empty[s], ph ^ 1u);
+      unsigned char* a_hi = tiles + (size_t)s * STAGE;
+      unsigned char* a_lo = a_hi + A_PART;
+      unsigned char* b_hi = a_hi + 2 * A_PART;
+      unsigned char* b_lo = b_hi + B_PART;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int pl = pr + 16 * h;
+        // atom = 4 pixel rows x 128 B; 32-byte chunk index XOR (row & 3)  (Swizzle<2,5,2> on the byte address)
+        const uint32_t off = (uint32_t)((pl >> 2) * 512 + (pl & 3) * 128 + ((((j >> 1) ^ (pl & 3)) << 5) | ((j & 1) << 4)));
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float hh[4], ll[4];
+          split_tf32(av[h][q].x, hh[0], ll[0]); split_tf32(av[h][q].y, hh[1], ll[1]);
+          split_tf32(av[h][q].z, hh[2], ll[2]); split_tf32(av[h][q].w, hh[3], ll[3]);
+          *reinterpret_cast<float4*>(a_hi + q * 4096 + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<float4*>(a_lo + q * 4096 + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < BN / 32; ++q) {
+          float hh[4], ll[4];
+          split_tf32(bv[h][q].x, hh[0], ll[0]); split_tf32(bv[h][q].y, hh[1], ll[1]);
+          split_tf32(bv[h][q].z, hh[2], ll[2]); split_tf32(bv[h][q].w, hh[3], ll[3]);
+          *reinterpret_cast<float4*>(b_hi + q * 4096 + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<float4*>(b_lo + q * 4096 + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+        }
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+
+    // ---- epilogue: TMEM lane = (tap,c) row of the tile; 32-column chunks spread over the producer groups
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    const int row = (warp & 3) * 32 + lane;
+    const int kidx = 128 * kt + row;
+    float* dst = p.partial + ((size_t)split * (p.K + 1) + (kidx < p.K ? kidx : 0)) * g.Cout + n0;
+#pragma unroll 1
+    for (int c0 = 32 * group; c0 < BN; c0 += 32 * NGROUPS) {
+      float v[32];
+      uint32_t raw[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
+      tmem_ld_32x32(taddr, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(raw[q]);
+      tmem_ld_32x32(taddr + BN, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(raw[q]);
+      float u[32];
+      tmem_ld_32x32(taddr + 2 * BN, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) u[q] = __uint_as_float(raw[q]);
+      tmem_ld_32x32(taddr + 3 * BN, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] += u[q] + __uint_as_float(raw[q]);
+      if (kidx < p.K) {
+#pragma unroll
+        for (int q = 0; q < 32; q += 4)
+          if (n0 + c0 + q < g.Cout) *reinterpret_cast<float4*>(dst + c0 + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+      }
+    }
+  } else {
+    // ---- MMA issuer
+    if (lane == 0) {
+      // kind::tf32, D fp32, A and B MN-major (bits 15, 16), N = BN, M = 128
+      const uint32_t idesc = instr_desc(2u, 128, BN) | (1u << 15) | (1u << 16);
+      if (n_stages == 0) {
+        // nothing to reduce in this split (cannot happen with the host's split choice, kept for safety)
+      }
+      for (int st = 0; st < n_stages; ++st) {
+        const int s = st % S;
+        const uint32_t ph = (uint32_t)(st / S) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t base = smem_u32(tiles + (size_t)s * STAGE);
+        const uint64_t a_hi = smem_desc_mn_sw128(base), a_lo = smem_desc_mn_sw128(base + A_PART);
+        const uint64_t b_hi = smem_desc_mn_sw128(base + 2 * A_PART), b_lo = smem_desc_mn_sw128(base + 2 * A_PART + B_PART);
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * (1024 >> 4));   // next 8-pixel group
+          const int ks = st * 4 + kk;
+          const uint32_t d_main = tmem_base + (uint32_t)((ks % 3) * BN);
+          const uint32_t d_corr = tmem_base + (uint32_t)(3 * BN);
+          mma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, ks == 0 ? 0u : 1u);
+          mma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
+          mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ks < 3 ? 0u : 1u);
+        }
+        mma_commit(&empty[s]);
+      }
+      mma_commit(acc_full);
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == PROD_WARPS) tmem_dealloc(tmem_base, NACC * BN);
+}
+
+// bias gradient: db[n] = sum_m dy[m][n] -> written into partial[0][K][n]; other splits' bias rows are zeroed
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, int M, int C, float* __restrict__ out) {
+  __shared__ float sh[256 * 4];
+  const int C4 = C >> 2, c4 = threadIdx.x % C4, ppb = 256 / C4;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int m = blockIdx.x * ppb + threadIdx.x / C4; m < M; m += gridDim.x * ppb) {
+    const float4 v = *reinterpret_cast<const float4*>(dy + (size_t)m * C + c4 * 4);
+    acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) sh[threadIdx.x * 4 + q] = acc[q];
+  __syncthreads();
+  if (threadIdx.x < C4) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int t = threadIdx.x; t < 256; t += C4)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s[q] += sh[t * 4 + q];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) out[(size_t)blockIdx.x * C + c4 * 4 + q] = s[q];
+  }
+}
+
+static inline int pick_bn(int n) { return n <= 64 ? 64 : 128; }
+
+static int plan(const PcConvGeom* g, int* splits, int* rps) {
+  const int K = g->R * g->S * g->Cin;
+  const long long M = (long long)g->B * g->Ho * g->Wo;
+  const int bn = pick_bn(g->Cout);
+  const int tiles = ceil_div(K, 128) * ceil_div(g->Cout, bn);
+  int sp = ceil_div(2LL * kNumSMs, tiles);
+  const int max_sp = (int)(M / (PIX * 8) > 0 ? M / (PIX * 8) : 1);
+  if (sp > max_sp) sp = max_sp;
+  if (sp < 1) sp = 1;
+  int r = ceil_div(M, sp);
+  r = ceil_div(r, PIX) * PIX;
+  sp = ceil_div(M, r);
+  *splits = sp;
+  *rps = r;
+  return bn;
+}
+
+}  // namespace tcwg
+}  // namespace pc
+
+using namespace pc;
+using namespace pc::tcwg;
+
+namespace pc { void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream); }
+
+extern "C" int pc_conv_wgrad_tc_supported(const PcConvGeom* g) {
+  if (g == nullptr) return 0;
+  const bool cout_pow2 = g->Cout >= 32 && g->Cout <= 1024 && (g->Cout & (g->Cout - 1)) == 0;
+  const long long M = (long long)g->B * g->Ho * g->Wo;
+  const int cmax = g->Cout > g->Cin ? g->Cout : g->Cin;
+  return (g->Cin % 32 == 0 && cout_pow2 && g->R * g->S <= 32 && M * cmax < (1LL << 31)) ? 1 : 0;
+}
+
+extern "C" size_t pc_conv_wgrad_tc_workspace(const PcConvGeom* g) {
+  if (g == nullptr) return 0;
+  int sp, rps;
+  plan(g, &sp, &rps);
+  const size_t part = (size_t)sp * (size_t)(g->R * g->S * g->Cin + 1) * g->Cout * sizeof(float);
+  const size_t cs = (size_t)kNumSMs * 2 * g->Cout * sizeof(float);
+  return part + cs;
+}
+
+extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw, float* db,
+                                void* workspace, size_t workspace_bytes, pc_stream_t stream) {
+  PC_REQUIRE(x && dy && g && dw_oihw && workspace, PC_EINVAL, "pc_conv_wgrad_tc: null pointer");
+  PC_REQUIRE(pc_conv_wgrad_tc_supported(g), PC_EUNSUPPORTED, "pc_conv_wgrad_tc: shape not covered (Cin %% 32, Cout %% 4)");
+  PC_REQUIRE(workspace_bytes >= pc_conv_wgrad_tc_workspace(g), PC_EINVAL, "pc_conv_wgrad_tc: workspace too small");
+  int sp, rps;
+  const int bn = plan(g, &sp, &rps);
+  Params p{};
+  p.x = x; p.dy = dy; p.partial = static_cast<float*>(workspace);
+  if (xf != nullptr) { p.xf.scale = xf->scale; p.xf.shift = xf->shift; p.xf.drop = xf->drop; p.xf.relu = xf->relu; }
+  p.g = *g;
+  p.K = g->R * g->S * g->Cin;
+  p.M = g->B * g->Ho * g->Wo;
+  p.rows_per_split = rps;
+  const uint32_t st = bn == 64 ? stage_bytes<64>() : stage_bytes<128>();
+  int stages = (int)(SMEM_BUDGET / st);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + 1024;
+  dim3 grid(ceil_div(p.K, 128), ceil_div(g->Cout, bn), sp);
+  if (bn == 64) {
+    static size_t conf = 0;
+    if (smem > conf) { PC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; }
+    wgrad_tc_kernel<64><<<grid, THREADS, smem, stream>>>(p);
+  } else {
+    static size_t conf = 0;
+    if (smem > conf) { PC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; }
+    wgrad_tc_kernel<128><<<grid, THREADS, smem, stream>>>(p);
+  }
+  PC_LAUNCH_CHECK("wgrad_tc_kernel");
+  // bias gradient: per-CTA column sums of dy -> bias rows of the partial buffer (one row per colsum CTA, appended after the
+  // split partials), then the common reduce
+  float* cs = p.partial + (size_t)sp * (size_t)(p.K + 1) * g->Cout;
+  const int cs_ctas = kNumSMs * 2;
+  colsum_kernel<<<cs_ctas, 256, 0, stream>>>(dy, p.M, g->Cout, cs);
+  PC_LAUNCH_CHECK("colsum_kernel");
+  launch_wgrad_reduce(p.partial, sp, g->R, g->S, g->Cin, g->Cout, dw_oihw, nullptr, stream);
+  launch_wgrad_reduce(cs, cs_ctas, 0, 0, 0, g->Cout, nullptr, db, stream);
+  PC_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
+  return PC_OK;
+}

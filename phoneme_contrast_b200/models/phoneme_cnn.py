@@ -24,7 +24,9 @@ _PREC = {"fp32": L.PREC_FP32, "tf32x3": L.PREC_TF32X3, "bf16": L.PREC_BF16}
 
 
 def _precision(config) -> int:
-    name = os.environ.get("PC_PRECISION") or config.get("precision", "fp32")
+    # default: tf32x3 -- tcgen05 tensor cores with fp32-level accuracy (3-term TF32 split) for every eligible layer,
+    # exact-fp32 SIMT kernels elsewhere. "fp32" forces the SIMT kernels everywhere; "bf16" is the 1e-2 opt-in mode.
+    name = os.environ.get("PC_PRECISION") or config.get("precision", "tf32x3")
     if name not in _PREC:
         raise ValueError(f"precision must be one of {list(_PREC)}, got {name!r}")
     return _PREC[name]

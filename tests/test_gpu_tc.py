@@ -78,6 +78,29 @@ def test_tc_conv_fwd_dgrad(prec, case):
         assert float((dx2.double() - 2 * dref).abs().max() / dref.abs().max()) < 2 * TOL[prec]
 
 
+@pytest.mark.parametrize("case", CONV_CASES + [(16, 40, 101, 32, 32, 3, 1, 1), (9, 20, 51, 64, 64, 3, 1, 1)])
+def test_tc_conv_wgrad(case):
+    """Weight / bias gradient on the tensor cores (MN-major TF32x3 tiles, pixel-split partials) vs torch fp64."""
+    from phoneme_contrast_b200 import ops
+    B, H, W, Cin, Cout, k, stride, pad = case
+    g = ops.conv_geom(B, H, W, Cin, Cout, k, stride, pad)
+    gen = torch.Generator(device=DEV).manual_seed(Cin * 3 + Cout + k)
+    x = torch.randn(B, H, W, Cin, device=DEV, generator=gen)
+    dy = torch.randn(B, g.Ho, g.Wo, Cout, device=DEV, generator=gen)
+    scale = 1.0 + 0.1 * torch.randn(Cin, device=DEV, generator=gen)
+    shift = 0.1 * torch.randn(Cin, device=DEV, generator=gen)
+    drop = ((torch.rand(B, Cin, device=DEV, generator=gen) > 0.2).float() / 0.8).contiguous()
+    xf = dict(scale=scale, shift=shift, relu=True, drop=drop)
+    dw, db = ops.conv_wgrad(x, dy, g, xf, prec=1)
+    a = (torch.relu(x.double() * scale.double() + shift.double()) * drop.double()[:, None, None, :]).permute(0, 3, 1, 2)
+    wr = torch.zeros(Cout, Cin, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    br = torch.zeros(Cout, device=DEV, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(a, wr, br, stride=stride, padding=pad).backward(dy.permute(0, 3, 1, 2).double())
+    err = float((dw.double() - wr.grad).abs().max() / wr.grad.abs().max())
+    assert err < TOL[1], ("dw", err)
+    assert float((db.double() - br.grad).abs().max() / br.grad.abs().max()) < 1e-5
+
+
 @pytest.mark.parametrize("arch,B", [("phoneme_cnn", 16), ("phoneme_cnn_deep", 8)])
 def test_nets_tf32x3_match_oracle(arch, B, monkeypatch):
     """Whole networks with the tensor-core convolutions in TF32x3 mode keep the fp32 parity bar (1e-4)."""
