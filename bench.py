@@ -125,30 +125,37 @@ def max_over_ranks(ms, parallel, device):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arms
-def bench_train(workload, steps, warmup, parallel, device, want_profile=True):
+def bench_train(workload, steps, warmup, parallel, device, want_profile=True, use_graph=True):
     from phoneme_contrast_b200 import _lib
     cfg = WORKLOADS[workload]
     arch, views = cfg["arch"], cfg["views"]
     rank = 0 if parallel is None else parallel.rank
     world = 1 if parallel is None else parallel.world_size
     tr = build_trainer(arch, device, parallel)
+    tr.config["cuda_graph"] = bool(use_graph)
     xs_h, y_h = train_inputs(views, 1000 + rank, device)
     xs = [x.to(device) for x in xs_h]
     y = y_h.to(device)
 
     for i in range(warmup):
-        tr.train_step(xs[i % len(xs)], y)
+        tr.step(xs[i % len(xs)], y)
     barrier(parallel)
     sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
-        loss = tr.train_step(xs[i % len(xs)], y)
+        loss = tr.step(xs[i % len(xs)], y)
     e1.record()
     barrier(parallel)
     ms = max_over_ranks(e0.elapsed_time(e1), parallel, device)
     launches = _lib.launch_count() - l0
+    if use_graph and tr._graphed is not None:
+        # replays do not pass through the launch counter: count the kernels of one eagerly executed step instead
+        c0 = _lib.launch_count()
+        tr.train_step(xs[0], y)
+        torch.cuda.synchronize()
+        launches = (_lib.launch_count() - c0) * steps
     clocks = sampler.stop() if sampler else None
     assert torch.isfinite(loss).item(), "training diverged"
 
@@ -156,24 +163,28 @@ def bench_train(workload, steps, warmup, parallel, device, want_profile=True):
     xs_p = [x.pin_memory() for x in xs_h]
     y_p = y_h.pin_memory()
     for i in range(2):
-        tr.train_step(xs_p[i % len(xs_p)].to(device, non_blocking=True), y_p.to(device, non_blocking=True)).item()
+        tr.step(xs_p[i % len(xs_p)].to(device, non_blocking=True), y_p.to(device, non_blocking=True)).item()
     barrier(parallel)
     t0 = time.perf_counter()
     for i in range(steps):
-        float(tr.train_step(xs_p[i % len(xs_p)].to(device, non_blocking=True), y_p.to(device, non_blocking=True)).item())
+        float(tr.step(xs_p[i % len(xs_p)].to(device, non_blocking=True), y_p.to(device, non_blocking=True)).item())
     barrier(parallel)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, parallel, device)
 
     prof = None
-    if want_profile and rank == 0:
-        _lib.profile_begin()
-        for i in range(min(steps, 5)):
+    if want_profile:
+        # every rank runs the profiled steps (they contain collectives); only rank 0 records events
+        n_prof = min(steps, 5)
+        if rank == 0:
+            _lib.profile_begin()
+        for i in range(n_prof):
             tr.train_step(xs[i % len(xs)], y)
-        prof = _lib.profile_end()
-        for v in prof.values():
-            v["ms"] /= min(steps, 5)
-            v["calls"] /= min(steps, 5)
-            v["work"] /= min(steps, 5)
+        if rank == 0:
+            prof = _lib.profile_end()
+            for v in prof.values():
+                v["ms"] /= n_prof
+                v["calls"] /= n_prof
+                v["work"] /= n_prof
     barrier(parallel)
     return dict(arch=arch, views=views, ms_per_step=ms / steps, value=views * world * steps / (ms * 1e-3),
                 e2e_value=views * world * steps / (e2e_ms * 1e-3), launches=launches / steps, clocks=clocks, prof=prof,
@@ -350,6 +361,7 @@ def main():
     ap.add_argument("--workload", default="train_cnn_deep", choices=list(WORKLOADS))
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-graph", action="store_true", help="eager launches instead of whole-step CUDA-graph replay")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -377,7 +389,7 @@ def main():
                 "gpu_launches": r["launches"] * args.steps, "config": {"workload": wl["desc"], "l2": "4.19 GB in / 2.1 GB out per step, far larger than the 126 MB L2"}}
         clocks = None
     else:
-        r = bench_train(args.workload, args.steps, args.warmup, parallel, device)
+        r = bench_train(args.workload, args.steps, args.warmup, parallel, device, use_graph=not args.no_graph)
         roof = roofline_from_profile(r["prof"], pk, pk_kind)
         line = {"metric": "supcon_train_samples_per_sec", "value": r["value"], "unit": "samples/s", "ms_per_step": r["ms_per_step"], "dtype": "f32",
                 "roofline": roof,
@@ -385,7 +397,8 @@ def main():
                 "gpu_launches": int(round(r["launches"] * args.steps)),
                 "config": {"workload": wl["desc"], "views_per_gpu": r["views"], "global_views": r["views"] * world,
                            "parallelism": f"dp{world}: all_gather(embeddings, labels, row stats) + flat-bucket gradient all-reduce; per-rank BatchNorm statistics",
-                           "precision": "fp32 accumulate, fp32 operands (exact-fp32 SIMT convolution path)",
+                           "precision": "fp32 storage and accumulate; convolutions on tcgen05 tensor cores in TF32x3 (3-term split, fp32-level accuracy), exact-fp32 SIMT for the Cin=1 stem",
+                           "launch": "eager" if args.no_graph else "whole step captured in one CUDA graph (inputs copied into static buffers each step)",
                            "l2": "no explicit flush: each step streams ~2 GB of activations (>> 126 MB L2); inputs rotate over 4 device buffers",
                            "step_tflops": FLOP_PER_SAMPLE[r["arch"]] * r["views"] / (r["ms_per_step"] * 1e-3) / 1e12,
                            "final_loss": r["loss"]}}
@@ -409,7 +422,7 @@ def main():
                                                        "roofline": {"bound": "hbm", "kernel": "frontend_kernel", "achieved": f["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": f["gbs"] / pk["hbm_gbs"]},
                                                        "e2e": {"value": f["e2e_value"], "unit": "clips/s", "sample": f["e2e_sample"]}}
             other = "train_cnn_small" if args.workload != "train_cnn_small" else "train_cnn_deep"
-            o = bench_train(other, args.steps, args.warmup, None, device, want_profile=False)
+            o = bench_train(other, args.steps, args.warmup, None, device, want_profile=False, use_graph=not args.no_graph)
             also[f"supcon_train_samples_per_sec[{other}]"] = {"value": o["value"], "unit": "samples/s", "ms_per_step": o["ms_per_step"], "e2e": o["e2e_value"],
                                                               "workload": WORKLOADS[other]["desc"]}
         except Exception as e:  # secondary numbers must never sink the primary line

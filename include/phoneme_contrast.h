@@ -218,8 +218,10 @@ int pc_head_bwd(const float* demb, const float* x, int B, int K, int N, const fl
                 const float* beta, int training, void* ws, float* dx, float* dW, float* dbias, float* dgamma,
                 float* dbeta, pc_stream_t stream);
 
-/* Dropout2d multipliers drop[B,C] in {0, 1/(1-p)} from Philox(seed, offset) (phoneme_cnn.py:43,53,62,176). */
-int pc_dropout2d_mask(float* drop, int B, int C, float p, uint64_t seed, uint64_t offset, pc_stream_t stream);
+/* Dropout2d multipliers drop[B,C] in {0, 1/(1-p)} from Philox(seed, offset) (phoneme_cnn.py:43,53,62,176).
+ * step_dev (optional, device int64): its value << 24 is added to offset, so a CUDA-graph replay draws fresh masks. */
+int pc_dropout2d_mask(float* drop, int B, int C, float p, uint64_t seed, uint64_t offset, const int64_t* step_dev,
+                      pc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 4. Optimiser step on flat buffers
@@ -233,6 +235,14 @@ int pc_grad_sumsq(const float* g, int64_t n, double* norm_sq, pc_stream_t stream
 int pc_clip_adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                  float eps, float weight_decay, float max_norm, const double* norm_sq, float grad_prescale,
                  int64_t step, pc_stream_t stream);
+
+/* Graph-capturable form: learning rate and 1-based step count are read from device memory (lr_dev[0], step_dev[0]),
+ * so the launch can be captured once in a CUDA graph and replayed while the host updates those scalars. */
+int pc_clip_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, const float* lr_dev, float beta1, float beta2,
+                     float eps, float weight_decay, float max_norm, const double* norm_sq, float grad_prescale,
+                     const int64_t* step_dev, pc_stream_t stream);
+/* counter[0] += inc on the stream (device-side step counters for captured steps). */
+int pc_counter_add(int64_t* counter, int64_t inc, pc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -75,7 +75,9 @@ SIGNATURES = {
     "pc_head_workspace": (sz, [i32, i32, i32]),
     "pc_head_fwd": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp]),
     "pc_head_bwd": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
-    "pc_dropout2d_mask": (i32, [vp, i32, i32, f32, u64, u64, vp]),
+    "pc_dropout2d_mask": (i32, [vp, i32, i32, f32, u64, u64, vp, vp]),
+    "pc_clip_adam_dev": (i32, [vp, vp, vp, vp, i64, vp, f32, f32, f32, f32, f32, vp, f32, vp, vp]),
+    "pc_counter_add": (i32, [vp, i64, vp]),
     "pc_grad_sumsq": (i32, [vp, i64, vp, vp]),
     "pc_clip_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, f32, i64, vp]),
 }

@@ -409,9 +409,11 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ dropout mask
-__global__ void dropout2d_mask_kernel(float* __restrict__ drop, int n, float p, float keep_scale, uint64_t seed, uint64_t offset) {
+__global__ void dropout2d_mask_kernel(float* __restrict__ drop, int n, float p, float keep_scale, uint64_t seed, uint64_t offset,
+                                      const long long* __restrict__ step_dev) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i * 4 >= n) return;
+  if (step_dev != nullptr) offset += (uint64_t)step_dev[0] << 24;      // graph-capturable: the call counter lives on the device
   const uint64_t ctr = offset + (uint64_t)i;
   const uint4 r = Philox::round10(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x44524f50u, 0u),
                                   make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -549,10 +551,12 @@ extern "C" int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, con
   return PC_OK;
 }
 
-extern "C" int pc_dropout2d_mask(float* drop, int B, int C, float p, uint64_t seed, uint64_t offset, pc_stream_t stream) {
+extern "C" int pc_dropout2d_mask(float* drop, int B, int C, float p, uint64_t seed, uint64_t offset, const int64_t* step_dev,
+                                 pc_stream_t stream) {
   PC_REQUIRE(drop && B > 0 && C > 0 && p >= 0.f && p < 1.f, PC_EINVAL, "pc_dropout2d_mask: bad arguments (p=%f)", p);
   const int n = B * C;
-  dropout2d_mask_kernel<<<ceil_div(ceil_div(n, 4), 128), 128, 0, stream>>>(drop, n, p, 1.0f / (1.0f - p), seed, offset);
+  dropout2d_mask_kernel<<<ceil_div(ceil_div(n, 4), 128), 128, 0, stream>>>(drop, n, p, 1.0f / (1.0f - p), seed, offset,
+                                                                            reinterpret_cast<const long long*>(step_dev));
   PC_LAUNCH_CHECK("dropout2d_mask_kernel");
   return PC_OK;
 }

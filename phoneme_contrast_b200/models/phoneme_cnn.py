@@ -111,8 +111,11 @@ def _drop_masks(net, B, chans, training):
         return list(net._inject_drop)
     dev = next(net.parameters()).device
     seed = torch.initial_seed() & 0xFFFFFFFFFFFF
-    net._drop_calls += 1
-    return [ops.dropout2d_mask(B, c, net.dropout_rate, seed, (net._drop_calls << 24) + (i << 20), dev) for i, c in enumerate(chans)]
+    # the forward-call counter lives on the device so that a captured (CUDA-graph) step draws fresh masks on every replay
+    if net._drop_step is None or net._drop_step.device != dev:
+        net._drop_step = torch.zeros(1, device=dev, dtype=torch.int64)
+    ops.counter_add(net._drop_step, 1)
+    return [ops.dropout2d_mask(B, c, net.dropout_rate, seed, i << 20, dev, net._drop_step) for i, c in enumerate(chans)]
 
 
 def _head(net, s, a, training):
@@ -315,7 +318,7 @@ class _NetFunction(torch.autograd.Function):
 
 class _FusedNet(BaseModel):
     _inject_drop = None
-    _drop_calls = 0
+    _drop_step = None
 
     def _finish_init(self):
         _init_weights(self)

@@ -54,8 +54,11 @@ class ConvWeights:
     __slots__ = ("wf", "wd", "prec_f", "prec_d")
 
     def __init__(self, w: torch.Tensor, g: PcConvGeom, prec: int, need_dgrad: bool = True):
-        self.prec_f = prec if tc_supported(g, False, prec) else L.PREC_FP32
-        self.prec_d = prec if tc_supported(g, True, prec) else L.PREC_FP32
+        import os
+        skip = os.environ.get("PC_TC_SKIP", "")
+        tag = f"{g.Cin}-{g.Cout}-{g.R}-{g.stride}"
+        self.prec_f = prec if (tc_supported(g, False, prec) and os.environ.get("PC_TC_FWD", "1") == "1" and tag not in skip.split(",")) else L.PREC_FP32
+        self.prec_d = prec if (tc_supported(g, True, prec) and os.environ.get("PC_TC_DGRAD", "1") == "1") else L.PREC_FP32
         self.wf = self.wd = None
         need_simt_f = self.prec_f == L.PREC_FP32
         need_simt_d = need_dgrad and self.prec_d == L.PREC_FP32
@@ -117,6 +120,9 @@ def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_F
         db = torch.empty(g.Cout, device=x.device, dtype=F32)
     nbytes = int(L.lib().pc_conv_wgrad_workspace(C.byref(g)))
     ws = _workspace(nbytes, x.device)
+    import os
+    if os.environ.get("PC_TC_WGRAD", "1") != "1":
+        prec = L.PREC_FP32
     xf = _xf(**xform) if xform else None
     L.note_work("pc_conv_wgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
     call("pc_conv_wgrad", ptr(x), ptr(dy), C.byref(g), C.byref(xf) if xf is not None else None, ptr(dw), ptr(db),
@@ -253,10 +259,14 @@ def head_bwd(demb, x, lin_w, bn_w, bn_b, training, ws, dW=None, dbias=None, dgam
     return dx, dW, dbias, dgamma, dbeta
 
 
-def dropout2d_mask(B, C_, p, seed, offset, device):
+def dropout2d_mask(B, C_, p, seed, offset, device, step_dev=None):
     m = torch.empty(B, C_, device=device, dtype=F32)
-    call("pc_dropout2d_mask", ptr(m), B, C_, float(p), int(seed), int(offset), stream())
+    call("pc_dropout2d_mask", ptr(m), B, C_, float(p), int(seed), int(offset), ptr(step_dev, torch.int64), stream())
     return m
+
+
+def counter_add(counter: torch.Tensor, inc: int = 1):
+    call("pc_counter_add", ptr(counter, torch.int64), int(inc), stream())
 
 
 def supcon_fwd(feats, labels, mask, temperature, base_temperature, row0=0, nrows=None):

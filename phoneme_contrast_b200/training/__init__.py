@@ -1,5 +1,6 @@
 from .losses import NTXentLoss, SupervisedContrastiveLoss, get_loss_fn
+from .graph import GraphedTrainStep
 from .optim import FusedClipAdam
 from .trainer import ContrastiveTrainer
 
-__all__ = ["NTXentLoss", "SupervisedContrastiveLoss", "get_loss_fn", "FusedClipAdam", "ContrastiveTrainer"]
+__all__ = ["NTXentLoss", "SupervisedContrastiveLoss", "get_loss_fn", "FusedClipAdam", "GraphedTrainStep", "ContrastiveTrainer"]

@@ -40,6 +40,11 @@ class FusedClipAdam(torch.optim.Optimizer):
         self.flat_v = torch.zeros(n, device=dev, dtype=torch.float32)
         self._norm_sq = torch.zeros(1, device=dev, dtype=torch.float64)
         self._step = 0
+        # device-resident copies of the step count and learning rate: the update kernel reads them from memory, so a
+        # step captured in a CUDA graph stays correct across replays (the host refreshes lr_dev when the scheduler moves it)
+        self._step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        self._lr_dev = torch.full((1,), float(lr), device=dev, dtype=torch.float32)
+        self._lr_host = float(lr)
         off = 0
         with torch.no_grad():
             for p, k in zip(ps, self._sizes):
@@ -82,16 +87,34 @@ class FusedClipAdam(torch.optim.Optimizer):
         clip = float(clip) if clip else 0.0
         self._step += 1
         n = self.flat_p.numel()
+        capturing = torch.cuda.is_current_stream_capturing()
+        if not capturing:
+            self.sync_lr()
+        call("pc_counter_add", ptr(self._step_dev, torch.int64), 1, stream())
         if clip > 0.0:
             self._norm_sq.zero_()
             call("pc_grad_sumsq", ptr(g), n, ptr(self._norm_sq, torch.float64), stream())
         b1, b2 = grp["betas"]
-        call("pc_clip_adam", ptr(self.flat_p), ptr(g), ptr(self.flat_m), ptr(self.flat_v), n, float(grp["lr"]), float(b1),
+        call("pc_clip_adam_dev", ptr(self.flat_p), ptr(g), ptr(self.flat_m), ptr(self.flat_v), n, ptr(self._lr_dev), float(b1),
              float(b2), float(grp["eps"]), float(grp["weight_decay"]), clip, ptr(self._norm_sq, torch.float64),
-             float(self.grad_prescale), self._step, stream())
+             float(self.grad_prescale), ptr(self._step_dev, torch.int64), stream())
+        return loss
+
+    def sync_lr(self) -> None:
+        """Push param_groups[0]['lr'] to the device scalar the kernel reads (no-op when unchanged)."""
+        lr = float(self.param_groups[0]["lr"])
+        if lr != self._lr_host:
+            self._lr_dev.fill_(lr)
+            self._lr_host = lr
+
+    def note_replayed_steps(self, n: int = 1) -> None:
+        """Host-side bookkeeping after CUDA-graph replays (the device counter advanced inside the graph)."""
+        self._step += n
+
+    def state_dict(self):
         for p in self._params:
             self.state[p]["step"] = torch.tensor(float(self._step))
-        return loss
+        return super().state_dict()
 
     def total_grad_norm(self) -> torch.Tensor:
         """L2 norm of the (pre-clip, pre-scaled) gradient seen by the last step (device scalar)."""
@@ -112,3 +135,6 @@ class FusedClipAdam(torch.optim.Optimizer):
             self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
             self._step = int(float(st["step"]))
             self.state[p]["step"] = torch.tensor(float(self._step))
+        self._step_dev.fill_(self._step)
+        self._lr_host = None
+        self.sync_lr()

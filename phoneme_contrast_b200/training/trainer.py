@@ -57,6 +57,7 @@ class ContrastiveTrainer:
         self.global_step = 0
         self.best_val_loss = float("inf")
         self.metrics_history = defaultdict(list)
+        self._graphed = None            # GraphedTrainStep, built lazily when config["cuda_graph"] is set
 
     # ------------------------------------------------------------------------------------------- loop
     def train(self, num_epochs: int) -> None:
@@ -90,6 +91,18 @@ class ContrastiveTrainer:
         self._save_checkpoint("final")
         self._save_metrics()
 
+    def step(self, views: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        """train_step, replayed from a captured CUDA graph when config["cuda_graph"] is set and the batch shape is static
+        (ContrastiveBatchSampler batches are); falls back to the eager path for odd-shaped batches."""
+        if not self.config.get("cuda_graph") or not isinstance(self.optimizer, FusedClipAdam):
+            return self.train_step(views, labels)
+        if self._graphed is None:
+            from .graph import GraphedTrainStep
+            self._graphed = GraphedTrainStep(self, views, labels)
+        if self._graphed.matches(views, labels):
+            return self._graphed(views, labels)
+        return self.train_step(views, labels)
+
     def train_step(self, views: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """One optimisation step on device-resident inputs; returns the (device) loss. This is the unit bench.py times."""
         embeddings = self._forward_pass(views)
@@ -121,7 +134,7 @@ class ContrastiveTrainer:
         pbar = tqdm(self.train_loader, desc=f"Epoch {self.current_epoch + 1}", disable=not self.config.get("progress", True))
         for batch in pbar:
             views, labels = self._prepare_batch(batch)
-            loss = self.train_step(views, labels)
+            loss = self.step(views, labels)
             total += loss
             num_batches += 1
             self.global_step += 1

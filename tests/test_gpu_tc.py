@@ -78,7 +78,8 @@ def test_tc_conv_fwd_dgrad(prec, case):
         assert float((dx2.double() - 2 * dref).abs().max() / dref.abs().max()) < 2 * TOL[prec]
 
 
-@pytest.mark.parametrize("case", CONV_CASES + [(16, 40, 101, 32, 32, 3, 1, 1), (9, 20, 51, 64, 64, 3, 1, 1)])
+@pytest.mark.parametrize("case", CONV_CASES + [(16, 40, 101, 32, 32, 3, 1, 1), (9, 20, 51, 64, 64, 3, 1, 1), (4, 10, 50, 128, 128, 3, 1, 1),
+                                               (4, 20, 100, 64, 64, 3, 1, 1), (4, 5, 25, 256, 256, 3, 1, 1), (4, 20, 100, 64, 128, 3, 2, 1)])
 def test_tc_conv_wgrad(case):
     """Weight / bias gradient on the tensor cores (MN-major TF32x3 tiles, pixel-split partials) vs torch fp64."""
     from phoneme_contrast_b200 import ops
