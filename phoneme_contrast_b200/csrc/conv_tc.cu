@@ -109,6 +109,9 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
   float* s_sq = s_sum + BN;                                                       // [BN]
   int* s_off0 = reinterpret_cast<int*>(s_sq + BN);                                // [BM] per-row window-origin offset
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_off0 + BM);                    // [BM] per-row valid-tap bitmask
+  int* s_pix = reinterpret_cast<int*>(s_mask + BM);                               // [BM] output row (pixel) index, -1 = none
+  int* s_nact = s_pix + BM;                                                       // [1] number of active k-chunks
+  unsigned short* s_kc = reinterpret_cast<unsigned short*>(s_nact + 1);           // [n_kc] active k-chunk indices
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) PC_STAMP(0);
@@ -132,15 +135,38 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
     const int Ha = p.mode == 0 ? g.H : g.Ho, Wa = p.mode == 0 ? g.W : g.Wo;
     const int st = g.stride;
     const int m = (int)m0 + tid;
-    int off = 0;
+    int off = 0, pix = -1;
     uint32_t mask = 0u;
     if (m < (int)p.M) {
       if (p.mode == 2) {
         off = m * p.lda;
         mask = 1u;
+        pix = m;
       } else {
-        const int wq = m % Wr, t = m / Wr;
-        const int hq = t % Hr, bq = t / Hr;
+        int wq, hq, bq;
+        if (p.mode == 1 && st == 2) {
+          // stride-2 data gradient: enumerate input pixels parity-class-major ((h&1, w&1) = (0,0),(0,1),(1,0),(1,1)) so that the
+          // rows of a tile share their valid taps (a pixel of one class receives from only 1, 2, 2 or 4 of the 9 taps) and the
+          // k-chunks of taps nobody in the tile needs are skipped altogether.
+          int loc = m, c = 0, nh = 0, nw = 0;
+          for (; c < 4; ++c) {
+            nh = (Hr - (c >> 1) + 1) >> 1;
+            nw = (Wr - (c & 1) + 1) >> 1;
+            const int cnt = g.B * nh * nw;
+            if (loc < cnt) break;
+            loc -= cnt;
+          }
+          const int w2 = loc % nw, t = loc / nw;
+          wq = 2 * w2 + (c & 1);
+          hq = 2 * (t % nh) + (c >> 1);
+          bq = t / nh;
+        } else {
+          wq = m % Wr;
+          const int t = m / Wr;
+          hq = t % Hr;
+          bq = t / Hr;
+        }
+        pix = (bq * Hr + hq) * Wr + wq;
         int hb, wb;
         if (p.mode == 0) {
           hb = hq * st - g.pad;
@@ -168,8 +194,24 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
         off = ((bq * Ha + hb) * Wa + wb) * p.Ca;
       }
     }
+    s_pix[tid] = pix;
     s_off0[tid] = off;
     s_mask[tid] = mask;
+    asm volatile("bar.sync 2, 128;" ::: "memory");
+    if (warp == 0) {
+      uint32_t tm = s_mask[lane] | s_mask[lane + 32] | s_mask[lane + 64] | s_mask[lane + 96];
+      tm = __reduce_or_sync(0xffffffffu, tm);                      // taps that at least one row of this tile needs
+      const int cpt_ = p.Ca / BKC;
+      int n_act = 0;
+      for (int base = 0; base < p.n_kc; base += 32) {
+        const int kc = base + lane;
+        const bool act = kc < p.n_kc && ((tm >> (kc / cpt_)) & 1u);
+        const uint32_t bal = __ballot_sync(0xffffffffu, act);
+        if (act) s_kc[n_act + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)kc;
+        n_act += __popc(bal);
+      }
+      if (lane == 0) s_nact[0] = n_act;
+    }
   }
   if (warp == PROD_WARPS) {
     if (lane == 0) {
@@ -212,9 +254,11 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
     const bool has_drop = (p.mode == 0 && p.xf.drop != nullptr);
     const uint32_t soff0 = sw128_offset((uint32_t)rg, (uint32_t)j);     // rows rg + 16*i share (row & 7): + 2048*i
     if (tid == 0) PC_STAMP(2);
-    for (int kc = group; kc < p.n_kc; kc += NGROUPS) {
-      const int s = kc % S;
-      const uint32_t ph = (uint32_t)(kc / S) & 1u;
+    const int n_act = s_nact[0];
+    for (int it = group; it < n_act; it += NGROUPS) {
+      const int kc = s_kc[it];
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
       const int tap = kc / cpt;
       const int c0 = (kc - tap * cpt) * BKC + j * EPC;      // first channel of my chunk
       int tap_off;
@@ -283,8 +327,8 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
-      if (tid == 0 && kc == 0) PC_STAMP(3);
-      if (tid == 0 && kc == 3) PC_STAMP(4);
+      if (tid == 0 && it == 0) PC_STAMP(3);
+      if (tid == 0 && it == 3) PC_STAMP(4);
     }
     if (tid == 0) PC_STAMP(5);
 
@@ -294,13 +338,16 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
     tc_fence_after();
     if (tid == 0) PC_STAMP(6);
     const int r = (warp & 3) * 32 + lane;
-    const long long m = m0 + r;
-    const bool valid = m < p.M;
-    float* dst_row = p.C + (size_t)(valid ? m : 0) * p.Nn + n0;
+    const int pix = s_pix[r];
+    const bool valid = pix >= 0;
+    float* dst_row = p.C + (size_t)(valid ? pix : 0) * p.Nn + n0;
 #pragma unroll 1
     for (int c0 = 32 * group; c0 < BN; c0 += 32 * NGROUPS) {
       float v[32];
-      {
+      if (n_act == 0) {                      // no tap reaches this tile (e.g. odd pixels of a 1x1 stride-2 conv): zeros
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] = 0.f;
+      } else {
         uint32_t raw[32];
         const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c0;
         tmem_ld_32x32(taddr, raw);
@@ -363,14 +410,15 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
     // ============================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = instr_desc(PREC == PC_PREC_BF16 ? 1u : 2u, BM, BN);
-      for (int kc = 0; kc < p.n_kc; ++kc) {
-        const int s = kc % S;
-        const uint32_t ph = (uint32_t)(kc / S) & 1u;
+      const int n_act = s_nact[0];
+      for (int it = 0; it < n_act; ++it) {
+        const int s = it % S;
+        const uint32_t ph = (uint32_t)(it / S) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (kc == 0) PC_STAMP(8);
-        if (kc == 1) PC_STAMP(9);
-        if (kc == 4) PC_STAMP(10);
+        if (it == 0) PC_STAMP(8);
+        if (it == 1) PC_STAMP(9);
+        if (it == 4) PC_STAMP(10);
         const uint32_t base = smem_u32(tiles + (size_t)s * STAGE);
         const uint64_t a_hi = smem_desc_sw128(base);
         const uint64_t a_lo = smem_desc_sw128(base + A_PART);
@@ -379,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t adv = (uint64_t)(kk * 2);       // 32 bytes per k-step, in 16-byte units
-          const int ks = kc * 4 + kk;                    // global k-step
+          const int ks = it * 4 + kk;                    // global k-step
           if (PREC == PC_PREC_TF32X3) {
             const uint32_t d_main = tmem_base + (uint32_t)((ks % 3) * BN);
             const uint32_t d_corr = tmem_base + (uint32_t)(3 * BN);
@@ -400,9 +448,11 @@ __global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
     // ============================================================ weight loader
     if (lane == 0) {
       const size_t kc_stride = (size_t)PARTS * p.Npad * 128;
-      for (int kc = 0; kc < p.n_kc; ++kc) {
-        const int s = kc % S;
-        const uint32_t ph = (uint32_t)(kc / S) & 1u;
+      const int n_act = s_nact[0];
+      for (int it = 0; it < n_act; ++it) {
+        const int kc = s_kc[it];
+        const int s = it % S;
+        const uint32_t ph = (uint32_t)(it / S) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         unsigned char* b_dst = tiles + (size_t)s * STAGE + PARTS * A_PART;
         const unsigned char* src = p.Bp + (size_t)kc * kc_stride + (size_t)n0 * 128;
@@ -483,7 +533,7 @@ static int launch(const Params& p0, pc_stream_t stream) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.n_kc) stages = p.n_kc < 2 ? 2 : p.n_kc;
   p.stages = stages;
-  const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + sizeof(float) * 3 * BN + sizeof(int) * 2 * BM + 1024;
+  const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + sizeof(float) * 3 * BN + sizeof(int) * (3 * BM + 1) + sizeof(unsigned short) * (size_t)(p.n_kc + 2) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     PC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
