@@ -31,6 +31,7 @@ WORKLOADS = {
     "train_cnn_deep": dict(arch="phoneme_cnn_deep", views=256, desc="cnn_deep PhonemeNetDeep (64->512 ch residual) + SupCon T=0.15, 256 views/GPU, 40x101 MFCC (BASELINE configs[2])"),
     "train_cnn_small": dict(arch="phoneme_cnn", views=64, desc="cnn_small PhonemeNet + SupCon T=0.15, emb 128, 64 views (8x4x2), 40x101 MFCC (BASELINE configs[0] on GPU)"),
     "frontend": dict(clips=65536, desc="MFCC front end + 2-view augmentation, 65 536 synthetic 1 s 16 kHz clips (BASELINE configs[1])"),
+    "supcon_8192": dict(n=8192, d=128, desc="SupCon loss alone, forward+backward, 8192 views x 128-d, 38 classes, rows sharded over the ranks with embedding/label/row-stat all_gather (BASELINE configs[3])"),
 }
 FLOP_PER_SAMPLE = {"phoneme_cnn": 3 * 298.07e6, "phoneme_cnn_deep": 3 * 568.59e6}   # fwd MAC*2, x3 for training
 
@@ -191,6 +192,55 @@ def bench_train(workload, steps, warmup, parallel, device, want_profile=True, us
                 h2d=views * 4040 * 4 + views * 8, d2h=4, loss=float(loss))
 
 
+def bench_supcon(steps, warmup, parallel, device, n=8192, d=128):
+    """fwd+bwd of the loss on N = 8192 global views; rank r owns rows [r*n/R, (r+1)*n/R). value = global views/s."""
+    from phoneme_contrast_b200 import _lib
+    from phoneme_contrast_b200.training import get_loss_fn
+    rank = 0 if parallel is None else parallel.rank
+    world = 1 if parallel is None else parallel.world_size
+    g = torch.Generator().manual_seed(0)
+    F_all = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1)
+    y_all = torch.randint(0, 38, (n,), generator=g)
+    nl = n // world
+    f = F_all[rank * nl:(rank + 1) * nl].to(device).requires_grad_(True)
+    y = y_all[rank * nl:(rank + 1) * nl].to(device)
+    loss_fn = get_loss_fn("supervised_contrastive", temperature=T_SUPCON)
+
+    def step():
+        f.grad = None
+        loss = parallel.loss(loss_fn, f, y) if parallel is not None else loss_fn(f, y)
+        loss.backward()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    barrier(parallel)
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    barrier(parallel)
+    ms = max_over_ranks(e0.elapsed_time(e1), parallel, device) / steps
+    launches = (_lib.launch_count() - l0) / steps
+    # e2e: embeddings start in pinned host memory, gradient rows are read back
+    f_h = F_all[rank * nl:(rank + 1) * nl].clone().pin_memory()
+    g_h = torch.empty(nl, d).pin_memory()
+    barrier(parallel)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        f.data.copy_(f_h, non_blocking=True)
+        step()
+        g_h.copy_(f.grad, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier(parallel)
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, parallel, device) / steps
+    flops = 8.0 * n * n * d / world          # 2N^2D forward + 2N^2D recompute + 4N^2D backward products, per rank 1/R
+    return dict(ms_per_step=ms, value=n / (ms * 1e-3), e2e_value=n / (e2e_ms * 1e-3), launches=launches, tflops=flops / (ms * 1e-3) / 1e12,
+                loss=float(loss), h2d=nl * d * 4, d2h=nl * d * 4)
+
+
 def roofline_from_profile(prof, pk, pk_kind):
     """Dominant C-ABI entry point by device time; convolution entry points carry algorithmic FLOPs (2*M*N*K per launch set)."""
     if not prof:
@@ -332,7 +382,19 @@ def run_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    if args.workload == "frontend":
+    if args.workload == "supcon_8192":
+        from oracle import supcon_oracle
+        torch.set_num_threads(os.cpu_count())
+        g = torch.Generator().manual_seed(0)
+        fc = torch.nn.functional.normalize(torch.randn(8192, 128, generator=g), dim=1).requires_grad_(True)
+        yc = torch.randint(0, 38, (8192,), generator=g)
+        supcon_oracle.loss_torch_cpu(fc, yc, temperature=T_SUPCON).backward()
+        t0 = time.perf_counter()
+        fc.grad = None
+        supcon_oracle.loss_torch_cpu(fc, yc, temperature=T_SUPCON).backward()
+        value, unit, metric, threads = 8192 / (time.perf_counter() - t0), "views/s", "supcon_fwd_bwd_views_per_sec", os.cpu_count()
+        sample = "1 timed fwd+bwd of the same 8192 x 128 problem after 1 warm-up"
+    elif args.workload == "frontend":
         per_clip, batched, threads = cpu_frontend(1024)
         value, unit = max(per_clip, batched), "clips/s"
         sample = "1024 clips: one clip per call (dataset.py:90 behaviour, %d thread(s)) %.0f clips/s; one batched call (all %d threads) %.0f clips/s; value = the better" % (threads, per_clip, os.cpu_count(), batched)
@@ -344,7 +406,7 @@ def run_reference(args):
         unit, metric = "samples/s", "supcon_train_samples_per_sec"
         sample = f"{steps} timed step(s) of the same {wl['views']}-view step after {min(args.warmup, 1)} warm-up"
     line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": (wl.get("views", 1) / value * 1e3) if args.workload != "frontend" else None, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": (wl.get("views", wl.get("n", 1)) / value * 1e3) if args.workload != "frontend" else None, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
             "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -380,7 +442,17 @@ def main():
     pk, pk_kind = peaks()
     wl = WORKLOADS[args.workload]
 
-    if args.workload == "frontend":
+    if args.workload == "supcon_8192":
+        r = bench_supcon(args.steps, args.warmup, parallel, device)
+        line = {"metric": "supcon_fwd_bwd_views_per_sec", "value": r["value"], "unit": "views/s", "ms_per_step": r["ms_per_step"], "dtype": "f32",
+                "roofline": {"bound": "tensor", "kernel": "supcon_bwd_kernel", "achieved": r["tflops"], "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+                             "unit": "TFLOP/s", "frac": r["tflops"] / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "traffic": None,
+                             "note": "per-rank algorithmic FLOPs 8*N^2*D/R (forward, backward recompute, two backward products) / step time; fp32 SIMT kernel"},
+                "e2e": {"value": r["e2e_value"], "unit": "views/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+                "gpu_launches": int(round(r["launches"] * args.steps)),
+                "config": {"workload": wl["desc"], "final_loss": r["loss"], "l2": "F is 4 MB (L2-resident by design: every rank re-reads all N rows); no flush"}}
+        clocks = None
+    elif args.workload == "frontend":
         r = bench_frontend(args.steps, args.warmup, device)
         line = {"metric": "mfcc_frontend_clips_per_sec", "value": r["value"], "unit": "clips/s", "ms_per_step": r["ms_per_step"], "dtype": "f32",
                 "roofline": {"bound": "hbm", "kernel": "frontend_kernel", "achieved": r["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -429,7 +501,20 @@ def main():
             also["error"] = repr(e)
         line["also"] = also
 
-    if world == 1 and not args.no_cpu:
+    if world == 1 and not args.no_cpu and args.workload == "supcon_8192":
+        from oracle import supcon_oracle
+        torch.set_num_threads(os.cpu_count())
+        g = torch.Generator().manual_seed(0)
+        fc = torch.nn.functional.normalize(torch.randn(8192, 128, generator=g), dim=1).requires_grad_(True)
+        yc = torch.randint(0, 38, (8192,), generator=g)
+        supcon_oracle.loss_torch_cpu(fc, yc, temperature=T_SUPCON).backward()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            fc.grad = None
+            supcon_oracle.loss_torch_cpu(fc, yc, temperature=T_SUPCON).backward()
+        dt = (time.perf_counter() - t0) / 2
+        line["cpu_baseline"] = {"value": 8192 / dt, "unit": "views/s", "cores": os.cpu_count(), "kind": "port", "sample": "2 timed fwd+bwd of the same 8192 x 128 problem (torch CPU, reference op sequence)"}
+    elif world == 1 and not args.no_cpu:
         if args.workload == "frontend":
             per_clip, batched, threads = cpu_frontend(1024)
             line["cpu_baseline"] = {"value": max(per_clip, batched), "unit": "clips/s", "cores": os.cpu_count() if batched >= per_clip else threads, "kind": "port",

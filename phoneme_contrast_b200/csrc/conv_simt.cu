@@ -333,22 +333,50 @@ conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, PcC
   }
 }
 
-// partial [splits][K+1][Cout] -> dw OIHW + db, fixed summation order
-__global__ void conv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int R, int S, int Cin, int Cout,
-                                         float* __restrict__ dw, float* __restrict__ db) {
+// partial [splits][K+1][Cout] -> dw OIHW + db, fixed summation order. Block = 32 float4 columns x 8 split lanes: lane y sums
+// splits y, y+8, ... (independent 16-byte loads in flight), then the 8 partial sums are combined in a fixed order through
+// shared memory, so the result does not depend on scheduling.
+__global__ void __launch_bounds__(256)
+conv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int R, int S, int Cin, int Cout,
+                         float* __restrict__ dw, float* __restrict__ db) {
+  __shared__ double sh[8][32][4];
   const int K = R * S * Cin;
-  const long long total = (long long)(K + 1) * Cout;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int sp = 0; sp < n_splits; ++sp) s += (double)partial[(size_t)sp * total + idx];
+  const long long total = (long long)(K + 1) * Cout;      // floats per split; Cout % 4 == 0
+  const long long total4 = total >> 2;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long i4 = (long long)blockIdx.x * 32 + tx;
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  if (i4 < total4) {
+    const float4* src = reinterpret_cast<const float4*>(partial) + i4;
+    for (int sp = ty; sp < n_splits; sp += 8) {
+      const float4 a = src[(size_t)sp * total4];
+      s0 += (double)a.x; s1 += (double)a.y; s2 += (double)a.z; s3 += (double)a.w;
+    }
+  }
+  sh[ty][tx][0] = s0; sh[ty][tx][1] = s1; sh[ty][tx][2] = s2; sh[ty][tx][3] = s3;
+  __syncthreads();
+  if (ty == 0 && i4 < total4) {
+    double sv[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      double t = sh[0][tx][q];
+#pragma unroll
+      for (int y = 1; y < 8; ++y) t += sh[y][tx][q];
+      sv[q] = t;
+    }
+    const long long idx = i4 << 2;
     const int n = (int)(idx % Cout);
     const int k = (int)(idx / Cout);
     if (k == K) {
-      if (db != nullptr) db[n] = (float)s;
-    } else {
+      if (db != nullptr) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) db[n + q] = (float)sv[q];
+      }
+    } else if (dw != nullptr) {
       const int c = k % Cin, tap = k / Cin;
       const int r = tap / S, ss = tap % S;
-      dw[(((size_t)n * Cin + c) * R + r) * S + ss] = (float)s;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dw[(((size_t)(n + q) * Cin + c) * R + r) * S + ss] = (float)sv[q];
     }
   }
 }
@@ -375,41 +403,55 @@ conv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w_oi
     const int h = h0 + rr - P, w = w0 + cc - P;
     xs[rr][cc] = (h >= 0 && h < H && w >= 0 && w < W) ? x[((size_t)b * H + h) * W + w] : 0.f;
   }
+  // weights: coalesced global -> shared, then each lane picks up its channels' taps (row stride KS*KS is odd: conflict-free)
+  __shared__ float ws[COUT * KS * KS];
+  for (int i = threadIdx.x; i < COUT * KS * KS; i += 256) ws[i] = w_oihw[i];
+  __syncthreads();
   float wr[CPL][KS * KS], bv[CPL];
 #pragma unroll
   for (int q = 0; q < CPL; ++q) {
     const int n = lane + 32 * q;
     bv[q] = (bias != nullptr && n < COUT) ? bias[n] : 0.f;
 #pragma unroll
-    for (int t = 0; t < KS * KS; ++t) wr[q][t] = n < COUT ? w_oihw[(size_t)n * KS * KS + t] : 0.f;
+    for (int t = 0; t < KS * KS; ++t) wr[q][t] = n < COUT ? ws[n * KS * KS + t] : 0.f;
   }
-  __syncthreads();
   float ssum[CPL], ssq[CPL];
 #pragma unroll
   for (int q = 0; q < CPL; ++q) { ssum[q] = 0.f; ssq[q] = 0.f; }
-  // warp `warp` handles output row h0 + warp, all TW columns
+  // warp `warp` handles output row h0 + warp; 4 adjacent pixels per iteration share one (KS+3)-wide window row held in
+  // registers, so each shared-memory (broadcast) load feeds up to 4*CPL FMAs instead of CPL
   const int h = h0 + warp;
   if (h < H) {
-    for (int cw = 0; cw < TW; ++cw) {
-      const int w = w0 + cw;
-      if (w >= W) break;
-      float acc[CPL];
+    for (int cw = 0; cw < TW && w0 + cw < W; cw += 4) {
+      float acc[4][CPL];
 #pragma unroll
-      for (int q = 0; q < CPL; ++q) acc[q] = bv[q];
+      for (int px = 0; px < 4; ++px)
 #pragma unroll
-      for (int r = 0; r < KS; ++r)
+        for (int q = 0; q < CPL; ++q) acc[px][q] = bv[q];
 #pragma unroll
-        for (int s = 0; s < KS; ++s) {
-          const float xv = xs[warp + r][cw + s];
+      for (int r = 0; r < KS; ++r) {
+        float xw[KS + 3];
 #pragma unroll
-          for (int q = 0; q < CPL; ++q) acc[q] = fmaf(xv, wr[q][r * KS + s], acc[q]);
+        for (int t = 0; t < KS + 3; ++t) xw[t] = xs[warp + r][cw + t];
+#pragma unroll
+        for (int s = 0; s < KS; ++s)
+#pragma unroll
+          for (int px = 0; px < 4; ++px)
+#pragma unroll
+            for (int q = 0; q < CPL; ++q) acc[px][q] = fmaf(xw[px + s], wr[q][r * KS + s], acc[px][q]);
+      }
+#pragma unroll
+      for (int px = 0; px < 4; ++px) {
+        const int w = w0 + cw + px;
+        if (w < W) {
+          float* dst = y + (((size_t)b * H + h) * W + w) * COUT;
+#pragma unroll
+          for (int q = 0; q < CPL; ++q) {
+            if (lane + 32 * q < COUT) dst[lane + 32 * q] = acc[px][q];
+            ssum[q] += acc[px][q];
+            ssq[q] = fmaf(acc[px][q], acc[px][q], ssq[q]);
+          }
         }
-      float* dst = y + (((size_t)b * H + h) * W + w) * COUT;
-#pragma unroll
-      for (int q = 0; q < CPL; ++q) {
-        if (lane + 32 * q < COUT) dst[lane + 32 * q] = acc[q];
-        ssum[q] += acc[q];
-        ssq[q] = fmaf(acc[q], acc[q], ssq[q]);
       }
     }
   }
@@ -458,21 +500,39 @@ conv_stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy
     __syncthreads();
     const int h = h0 + warp;
     if (h < H) {
-      for (int cw = 0; cw < TW; ++cw) {
-        const int w = w0 + cw;
-        if (w >= W) break;
-        const float* src = dy + (((size_t)b * H + h) * W + w) * COUT;
-        float d[CPL];
+      // dy for the next 4 pixels is fetched while the current 4 are being accumulated (the loop is otherwise exposed to
+      // the full global-load latency once per iteration: only 8 warps are resident)
+      auto load_d = [&](int cw, float (&d)[4][CPL]) {
 #pragma unroll
-        for (int q = 0; q < CPL; ++q) { d[q] = (lane + 32 * q < COUT) ? src[lane + 32 * q] : 0.f; acc[q][T] += d[q]; }
+        for (int px = 0; px < 4; ++px) {
+          const int w = w0 + cw + px;
+          const bool ok = cw < TW && w < W;
+          const float* src = dy + (((size_t)b * H + h) * W + (ok ? w : 0)) * COUT;
 #pragma unroll
-        for (int r = 0; r < KS; ++r)
+          for (int q = 0; q < CPL; ++q) d[px][q] = (ok && lane + 32 * q < COUT) ? src[lane + 32 * q] : 0.f;
+        }
+      };
+      float dn[4][CPL];
+      load_d(0, dn);
+      for (int cw = 0; cw < TW && w0 + cw < W; cw += 4) {
+        float d[4][CPL];
 #pragma unroll
-          for (int s = 0; s < KS; ++s) {
-            const float xv = xs[warp + r][cw + s];
+        for (int px = 0; px < 4; ++px)
 #pragma unroll
-            for (int q = 0; q < CPL; ++q) acc[q][r * KS + s] = fmaf(xv, d[q], acc[q][r * KS + s]);
-          }
+          for (int q = 0; q < CPL; ++q) { d[px][q] = dn[px][q]; acc[q][T] += d[px][q]; }
+        load_d(cw + 4, dn);
+#pragma unroll
+        for (int r = 0; r < KS; ++r) {
+          float xw[KS + 3];
+#pragma unroll
+          for (int t = 0; t < KS + 3; ++t) xw[t] = xs[warp + r][cw + t];
+#pragma unroll
+          for (int s = 0; s < KS; ++s)
+#pragma unroll
+            for (int px = 0; px < 4; ++px)
+#pragma unroll
+              for (int q = 0; q < CPL; ++q) acc[q][r * KS + s] = fmaf(xw[px + s], d[px][q], acc[q][r * KS + s]);
+        }
       }
     }
   }
@@ -494,8 +554,8 @@ conv_stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy
 }
 
 void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream) {
-  const long long total = (long long)(R * S * Cin + 1) * Cout;
-  conv_wgrad_reduce_kernel<<<ceil_div(total, 256), 256, 0, stream>>>(partial, n_splits, R, S, Cin, Cout, dw, db);
+  const long long total4 = ((long long)(R * S * Cin + 1) * Cout) >> 2;
+  conv_wgrad_reduce_kernel<<<ceil_div(total4, 32), 256, 0, stream>>>(partial, n_splits, R, S, Cin, Cout, dw, db);
   count_launch();
 }
 
@@ -681,8 +741,8 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
     PC_LAUNCH_CHECK("conv_wgrad_kernel");
     n_partials = splits;
   }
-  const long long total = (long long)(g->R * g->S * g->Cin + 1) * g->Cout;
-  int grid = ceil_div(total, 256);
+  const long long total4 = ((long long)(g->R * g->S * g->Cin + 1) * g->Cout) >> 2;
+  int grid = ceil_div(total4, 32);
   conv_wgrad_reduce_kernel<<<grid, 256, 0, stream>>>(partial, n_partials, g->R, g->S, g->Cin, g->Cout, dw_oihw, db);
   PC_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
   return PC_OK;

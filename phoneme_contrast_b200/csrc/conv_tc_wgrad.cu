@@ -290,7 +290,9 @@ static int plan(const PcConvGeom* g, int* splits, int* rps) {
   const long long M = (long long)g->B * g->Ho * g->Wo;
   const int bn = pick_bn(g->Cout);
   const int tiles = ceil_div(K, 128) * ceil_div(g->Cout, bn);
-  int sp = ceil_div(2LL * kNumSMs, tiles);
+  // fill (at most) two full waves of the 148 SMs: one CTA per SM is resident, so tiles*splits just above a multiple of
+  // 148 would cost a whole extra wave
+  int sp = (2 * kNumSMs) / tiles;
   const int max_sp = (int)(M / (PIX * 8) > 0 ? M / (PIX * 8) : 1);
   if (sp > max_sp) sp = max_sp;
   if (sp < 1) sp = 1;
