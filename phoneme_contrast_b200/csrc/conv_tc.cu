@@ -29,10 +29,11 @@ using namespace pc::tc;
 
 constexpr int BM = 128;
 constexpr int NPROD = 128;            // threads that fill one stage (one producer group)
-constexpr int NGROUPS = 3;            // producer groups; group g owns k-chunks g, g+NGROUPS, ... so that the global-load
-                                      // latency of several stages is in flight at once (one group alone is latency-bound)
-constexpr int PROD_WARPS = 4 * NGROUPS;
-constexpr int THREADS = 32 * (PROD_WARPS + 2);
+// Producer groups: group g owns k-chunks g, g+NGROUPS, ... so that the global-load latency of several stages is in flight
+// at once (one group alone is latency-bound). Two shapes are built:
+//   NGROUPS = 3, one CTA per SM  (BN = 128: the 4 x 128 TMEM accumulator columns fill the SM's tensor memory)
+//   NGROUPS = 2, two CTAs per SM (BN <= 64: 256 TMEM columns and ~100 KB smem each) -- while one CTA is in its prologue,
+//   MMA drain or epilogue (~38 % of a K = 576 tile), the other's main loop keeps the shared-memory pipes busy.
 constexpr int MAX_STAGES = 6;
 constexpr uint32_t SMEM_BUDGET = 200 * 1024;
 
@@ -88,8 +89,9 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
   return v[0];
 }
 
-template <int BN, int PREC>
-__global__ void __launch_bounds__(THREADS, 1) igemm_tc_kernel(const Params p) {
+template <int BN, int PREC, int NGROUPS, int MINB>
+__global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(const Params p) {
+  constexpr int PROD_WARPS = 4 * NGROUPS;
   using P = Prec<PREC>;
   constexpr int BKC = P::BKC, PARTS = P::PARTS, NACC = P::NACC;
   constexpr uint32_t A_PART = BM * 128, B_PART = BN * 128;
@@ -528,19 +530,23 @@ static inline int parts_of(int prec) { return prec == PC_PREC_BF16 ? 1 : 2; }
 template <int BN, int PREC>
 static int launch(const Params& p0, pc_stream_t stream) {
   Params p = p0;
+  constexpr bool kTwoPerSm = (BN <= 64) && (Prec<PREC>::NACC * BN <= 256);
+  constexpr int NG = kTwoPerSm ? 2 : 3;
+  constexpr int MINB = kTwoPerSm ? 2 : 1;
+  constexpr int THREADS = 32 * (4 * NG + 2);
   const uint32_t st = stage_bytes<BN, PREC>();
-  int stages = (int)(SMEM_BUDGET / st);
+  int stages = (int)((kTwoPerSm ? 100u * 1024u : SMEM_BUDGET) / st);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.n_kc) stages = p.n_kc < 2 ? 2 : p.n_kc;
   p.stages = stages;
   const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + sizeof(float) * 3 * BN + sizeof(int) * (3 * BM + 1) + sizeof(unsigned short) * (size_t)(p.n_kc + 2) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
-    PC_CUDA(cudaFuncSetAttribute(igemm_tc_kernel<BN, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute((igemm_tc_kernel<BN, PREC, NG, MINB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   dim3 grid(ceil_div(p.M, BM), p.Npad / BN);
-  igemm_tc_kernel<BN, PREC><<<grid, THREADS, smem, stream>>>(p);
+  igemm_tc_kernel<BN, PREC, NG, MINB><<<grid, THREADS, smem, stream>>>(p);
   PC_LAUNCH_CHECK("igemm_tc_kernel");
   return PC_OK;
 }

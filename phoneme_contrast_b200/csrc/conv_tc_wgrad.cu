@@ -21,7 +21,8 @@ namespace tcwg {
 
 using namespace pc::tc;
 
-constexpr int NPROD = 128, NGROUPS = 3, PROD_WARPS = 4 * NGROUPS, THREADS = 32 * (PROD_WARPS + 1);
+constexpr int NPROD = 128;             // threads per producer group; NGROUPS groups: 3 with one CTA per SM (BN = 128),
+                                       // 2 with two co-resident CTAs per SM (BN = 64), as in conv_tc.cu
 constexpr int PIX = 32;                 // pixels per stage (4 k-steps of 8)
 constexpr int MAX_STAGES = 6;
 constexpr uint32_t SMEM_BUDGET = 200 * 1024;
@@ -56,8 +57,9 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr_bytes)
 template <int BN>
 __host__ __device__ constexpr uint32_t stage_bytes() { return 2u * (4u * 4096u + (BN / 32) * 4096u); }
 
-template <int BN>
-__global__ void __launch_bounds__(THREADS, 1) wgrad_tc_kernel(const Params p) {
+template <int BN, int NGROUPS, int MINB>
+__global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(const Params p) {
+  constexpr int PROD_WARPS = 4 * NGROUPS;
   constexpr uint32_t A_PART = 4 * 4096, B_PART = (BN / 32) * 4096;
   constexpr uint32_t STAGE = stage_bytes<BN>();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -351,12 +353,14 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
   dim3 grid(ceil_div(p.K, 128), ceil_div(g->Cout, bn), sp);
   if (bn == 64) {
     static size_t conf = 0;
-    if (smem > conf) { PC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; }
-    wgrad_tc_kernel<64><<<grid, THREADS, smem, stream>>>(p);
+    // (two co-resident CTAs per SM were tried here as in conv_tc.cu: the register cap made the two-operand gather spill and
+    //  the kernel got slower, so the weight gradient keeps one CTA per SM)
+    if (smem > conf) { PC_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<64, 3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; }
+    wgrad_tc_kernel<64, 3, 1><<<grid, 32 * 13, smem, stream>>>(p);
   } else {
     static size_t conf = 0;
-    if (smem > conf) { PC_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; }
-    wgrad_tc_kernel<128><<<grid, THREADS, smem, stream>>>(p);
+    if (smem > conf) { PC_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<128, 3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; }
+    wgrad_tc_kernel<128, 3, 1><<<grid, 32 * 13, smem, stream>>>(p);
   }
   PC_LAUNCH_CHECK("wgrad_tc_kernel");
   // bias gradient: per-CTA column sums of dy -> bias rows of the partial buffer (one row per colsum CTA, appended after the
