@@ -67,6 +67,7 @@ typedef struct PcMfccConsts { /* device pointers, built once by the host (featur
   const float* dct;           /* [n_mels][n_mfcc] DCT-II ortho (unused for log-mel)                    */
   const float* tw;            /* twiddles: cos/sin tables, see mfcc.cu                                 */
   int32_t n_fft, hop, n_mels, n_mfcc;
+  int32_t fb_wmax;            /* max over filters of fb_len (0 = unknown: assume PC_FB_MAXW)                  */
 } PcMfccConsts;
 #define PC_FB_MAXW 32
 

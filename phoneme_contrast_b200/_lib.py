@@ -30,7 +30,7 @@ class PcViewDesc(C.Structure):
 
 class PcMfccConsts(C.Structure):
     _fields_ = [("window", vp), ("fb_start", vp), ("fb_len", vp), ("fb_w", vp), ("dct", vp), ("tw", vp),
-                ("n_fft", C.c_int32), ("hop", C.c_int32), ("n_mels", C.c_int32), ("n_mfcc", C.c_int32)]
+                ("n_fft", C.c_int32), ("hop", C.c_int32), ("n_mels", C.c_int32), ("n_mfcc", C.c_int32), ("fb_wmax", C.c_int32)]
 
 
 class PcConvGeom(C.Structure):

@@ -25,10 +25,19 @@ constexpr float FE_LOG_FLOOR = 1e-37f;
 struct FeParams {
   const float* wave; int n_clips, S, wave_ld;
   const float* window; const int* fb_start; const int* fb_len; const float* fb_w; const float* dct; const float* tw;
-  int hop, n_mels, n_mfcc, T, TLD, Lsz;
+  int hop, n_mels, n_mfcc, T, TLD, Lsz, dct_sz, xs_len, fb_ld, dct_alias;
   const PcViewDesc* views; int n_views, views_per_clip;
   const float* noise; int kind, clamp_mode; float top_db; const float* clamp_ref; float* clip_max_out; float* out;
+  long long* dbg;   // optional [grid][8] per-phase cycle totals (diagnostics: pc_fe_set_debug)
 };
+#define FE_T(slot)                                              \
+  do {                                                          \
+    if (p.dbg != nullptr && tid == 0) {                         \
+      const long long now = clock64();                          \
+      p.dbg[(size_t)blockIdx.x * 8 + (slot)] += now - t_last;   \
+      t_last = now;                                             \
+    }                                                           \
+  } while (0)
 
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
@@ -83,11 +92,17 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
   float* win = L + p.Lsz;   // Lsz = n_mels*TLD rounded up to 4 floats (keeps float2/float4 tables aligned)
   float2* W200 = reinterpret_cast<float2*>(win + FE_NFFT);
   float2* W400 = W200 + 200;
-  float* dcts = reinterpret_cast<float*>(W400 + 202);
+  // the DCT matrix is only needed after the last frame chunk: when it fits it aliases the FFT work buffers (Z, P), which
+  // keeps the CTA at ~104 KB so that two CTAs stay resident per SM
+  float* dcts = p.dct_alias ? reinterpret_cast<float*>(Z) : reinterpret_cast<float*>(W400 + 202);
+  float* xs = reinterpret_cast<float*>(W400 + 202) + (p.dct_alias ? 0 : p.dct_sz);   // 2 x [(FC-1)*hop + n_fft] samples of the current / next frame chunk (reflect-padded)
+  float* fbw = xs + 2 * p.xs_len;                                  // [n_mels][fb_ld] filter weights
+  int* fbs = reinterpret_cast<int*>(fbw + p.n_mels * p.fb_ld);     // [n_mels] first bin, [n_mels] length
   __shared__ float red[FE_THREADS / 32];
   __shared__ float lmax_s;
 
   const int tid = threadIdx.x;
+  long long t_last = clock64();
   const int V = p.views_per_clip;
   const int view0 = blockIdx.x * V;
   const int clip = p.views != nullptr ? p.views[view0].clip : blockIdx.x;
@@ -97,22 +112,62 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
   for (int i = tid; i < FE_NFFT; i += FE_THREADS) win[i] = p.window[i];
   for (int i = tid; i < 200; i += FE_THREADS) W200[i] = make_float2(p.tw[2 * i], p.tw[2 * i + 1]);
   for (int i = tid; i < 201; i += FE_THREADS) W400[i] = make_float2(p.tw[400 + 2 * i], p.tw[400 + 2 * i + 1]);
-  if (p.kind == PC_FE_MFCC)
+  if (p.kind == PC_FE_MFCC && !p.dct_alias)
     for (int i = tid; i < p.n_mels * p.n_mfcc; i += FE_THREADS) dcts[i] = p.dct[i];
+  for (int i = tid; i < p.n_mels * p.fb_ld; i += FE_THREADS) {
+    const int m = i / p.fb_ld, q = i - m * p.fb_ld;
+    fbw[i] = p.fb_w[m * PC_FB_MAXW + q];
+  }
+  for (int i = tid; i < p.n_mels; i += FE_THREADS) { fbs[i] = p.fb_start[i]; fbs[p.n_mels + i] = p.fb_len[i]; }
   __syncthreads();
+
+  // Stage the sample span of the frame chunk starting at frame f into dst: 16-byte cp.async for interior vectors (no
+  // register staging, completion tracked per commit group), plain loads with reflect padding at the clip edges.
+  const bool vec_ok = ((p.hop & 3) == 0) && ((p.wave_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  auto stage_chunk = [&](int f, float* dst) {
+    const int nfc = min(FE_FC, T - f);
+    const int base = f * p.hop - FE_NFFT / 2;
+    const int nv = ((nfc - 1) * p.hop + FE_NFFT + 3) >> 2;
+    for (int v = tid; v < nv; v += FE_THREADS) {
+      const int i = base + 4 * v;
+      if (vec_ok && i >= 0 && i + 3 < S) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst + 4 * v)), "l"(x + i) : "memory");
+      } else {
+        float t[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          int ii = i + e;
+          ii = ii < 0 ? -ii : (ii >= S ? 2 * (S - 1) - ii : ii);
+          ii = ii < 0 ? 0 : (ii >= S ? S - 1 : ii);      // only reachable in the unused tail of the last vector
+          t[e] = x[ii];
+        }
+        *reinterpret_cast<float4*>(dst + 4 * v) = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+  };
+  stage_chunk(0, xs);
+  asm volatile("cp.async.commit_group;" ::: "memory");
 
   for (int f0 = 0; f0 < T; f0 += FE_FC) {
     const int nf = min(FE_FC, T - f0);
-    // ---- P1: load, reflect-pad, window, pack even/odd samples into complex points
+    // ---- P0: the chunk's sample span was staged into xs[buf] by the previous iteration's prefetch (cp.async, overlapped
+    // with that chunk's FFT); stage the NEXT chunk now, then wait for the current one.
+    const int buf = (f0 / FE_FC) & 1;
+    if (f0 + FE_FC < T) stage_chunk(f0 + FE_FC, xs + (buf ^ 1) * p.xs_len);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const float* xc = xs + buf * p.xs_len;
+    // ---- P1: window, pack even/odd samples into complex points
+#pragma unroll 4
     for (int i = tid; i < nf * FE_NC; i += FE_THREADS) {
       const int fl = i / FE_NC, n = i - fl * FE_NC;
-      const int base = (f0 + fl) * p.hop - FE_NFFT / 2 + 2 * n;
-      int i0 = base, i1 = base + 1;
-      i0 = i0 < 0 ? -i0 : (i0 >= S ? 2 * (S - 1) - i0 : i0);
-      i1 = i1 < 0 ? -i1 : (i1 >= S ? 2 * (S - 1) - i1 : i1);
-      Z[fl * FE_ZLD + n] = make_float2(x[i0] * win[2 * n], x[i1] * win[2 * n + 1]);
+      const float* sp = xc + fl * p.hop + 2 * n;                 // (hop may be odd: no vector access here)
+      const float2 wv = *reinterpret_cast<const float2*>(win + 2 * n);
+      Z[fl * FE_ZLD + n] = make_float2(sp[0] * wv.x, sp[1] * wv.y);
     }
     __syncthreads();
+    FE_T(0);
     // ---- A: 25 radix-8 butterflies per frame over stride-25 points, twiddle W200^(n2*k1)
     for (int i = tid; i < nf * 25; i += FE_THREADS) {
       const int fl = i / 25, n2 = i - fl * 25;
@@ -125,7 +180,9 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
       for (int k1 = 0; k1 < 8; ++k1) z[25 * k1 + n2] = k1 == 0 ? v[0] : cmul(v[k1], W200[n2 * k1]);
     }
     __syncthreads();
+    FE_T(1);
     // ---- B1: radix-5 over a (stride 5), twiddle W25^(b*c) = W200^(8*b*c)
+#pragma unroll 2
     for (int i = tid; i < nf * 40; i += FE_THREADS) {
       const int fl = i / 40, r = i - fl * 40;
       const int k1 = r / 5, b = r - k1 * 5;
@@ -139,6 +196,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
     }
     __syncthreads();
     // ---- B2: radix-5 over b (stride 1); output bin k = k1 + 8*(c + 5*d) stays at position 25*k1 + 5*c + d
+#pragma unroll 2
     for (int i = tid; i < nf * 40; i += FE_THREADS) {
       const int fl = i / 40, r = i - fl * 40;
       float2* z = Z + fl * FE_ZLD + 5 * r;   // r = 5*k1 + c
@@ -150,7 +208,9 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
       for (int d = 0; d < 5; ++d) z[d] = v[d];
     }
     __syncthreads();
+    FE_T(2);
     // ---- post: real-FFT split, power spectrum bins k and 200-k together
+#pragma unroll 2
     for (int i = tid; i < nf * 101; i += FE_THREADS) {
       const int fl = i / 101, k = i - fl * 101;
       const float2* z = Z + fl * FE_ZLD;
@@ -166,19 +226,26 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
       P[fl * FE_PLD + 200 - k] = b.x * b.x + b.y * b.y;
     }
     __syncthreads();
+    FE_T(3);
     // ---- mel: banded filterbank, stored as 10 log10(mel)
+#pragma unroll 2
     for (int i = tid; i < nf * p.n_mels; i += FE_THREADS) {
       const int m = i / nf, fl = i - m * nf;   // fl fastest -> conflict-free L writes
-      const int s = p.fb_start[m], len = p.fb_len[m];
-      const float* wq = p.fb_w + m * PC_FB_MAXW;
+      const int s = fbs[m], len = fbs[p.n_mels + m];
+      const float* wq = fbw + m * p.fb_ld;
+      const float* pq = P + fl * FE_PLD + s;
       float acc = 0.f;
-      for (int q = 0; q < len; ++q) acc = fmaf(P[fl * FE_PLD + s + q], __ldg(wq + q), acc);
-      L[m * p.TLD + f0 + fl] = 10.0f * log10f(fmaxf(acc, FE_LOG_FLOOR));
+#pragma unroll 4
+      for (int q = 0; q < len; ++q) acc = fmaf(pq[q], wq[q], acc);
+      L[m * p.TLD + f0 + fl] = 3.0102999566398120f * __log2f(fmaxf(acc, FE_LOG_FLOOR));   // 10 log10(x) = 10 log10(2) log2(x)
     }
     __syncthreads();
+    FE_T(4);
   }
 
-  // ---- clip-wide maximum of the log-mel tile
+  if (p.kind == PC_FE_MFCC && p.dct_alias)      // FFT buffers are free now (the frame loop ended with a barrier)
+    for (int i = tid; i < p.n_mels * p.n_mfcc; i += FE_THREADS) dcts[i] = p.dct[i];
+  // ---- clip-wide maximum of the log-mel tile (the barriers below also publish the DCT matrix)
   float lm = -INFINITY;
   for (int i = tid; i < p.n_mels * T; i += FE_THREADS) {
     const int m = i / T, t = i - m * T;
@@ -196,6 +263,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
   const float lmax = lmax_s;
   const float amin_db = -100.0f;   // 10 log10(1e-10)
 
+  FE_T(5);
   const int n_out = p.kind == PC_FE_MFCC ? p.n_mfcc : p.n_mels;
   for (int v = 0; v < V; ++v) {
     const int view = view0 + v;
@@ -221,6 +289,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
         float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         const int c0 = cg * 8;
         if (c0 + 8 <= p.n_mfcc && (p.n_mfcc & 3) == 0) {
+#pragma unroll 4
           for (int m = 0; m < p.n_mels; ++m) {
             const float val = fmaxf(L[m * p.TLD + t] + G, lo);
             const float4 d0 = *reinterpret_cast<const float4*>(dcts + m * p.n_mfcc + c0);
@@ -272,6 +341,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
       }
     }
   }
+  FE_T(6);
 }
 
 __global__ void __launch_bounds__(256) reduce_max_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
@@ -327,9 +397,13 @@ __global__ void compute_deltas_kernel(const float* __restrict__ x, int rows, int
   }
 }
 
+static long long* g_fe_dbg = nullptr;
 }  // namespace pc
 
 using namespace pc;
+
+// Diagnostics: per-CTA cycle totals of the front-end phases (load, radix-8, radix-5 x2 [slots 1,2 = B1, B2+post...], mel, max, epilogue).
+extern "C" void pc_fe_set_debug(long long* buf) { pc::g_fe_dbg = buf; }
 
 extern "C" int pc_frontend_fwd(const float* wave, int n_clips, int S, int wave_ld, const PcMfccConsts* c, const PcViewDesc* views,
                                int n_views, const float* noise, int kind, int clamp_mode, float top_db, const float* clamp_ref,
@@ -357,11 +431,16 @@ extern "C" int pc_frontend_fwd(const float* wave, int n_clips, int S, int wave_l
   p.T = 1 + S / c->hop;
   p.TLD = p.T | 1;
   p.Lsz = (p.n_mels * p.TLD + 3) & ~3;
+  p.dct_sz = (p.n_mels * p.n_mfcc + 3) & ~3;
+  p.xs_len = ((FE_FC - 1) * c->hop + FE_NFFT + 7) & ~3;
+  p.fb_ld = c->fb_wmax > 0 ? ((c->fb_wmax + 3) & ~3) : PC_FB_MAXW;
+  p.dct_alias = (sizeof(float) * (size_t)p.dct_sz <= sizeof(float2) * FE_FC * FE_ZLD + sizeof(float) * FE_FC * FE_PLD) ? 1 : 0;
   p.views = views; p.n_views = n_views; p.views_per_clip = V;
   p.noise = noise; p.kind = kind; p.clamp_mode = clamp_mode; p.top_db = top_db; p.clamp_ref = clamp_ref;
   p.clip_max_out = clip_max_out; p.out = out;
+  p.dbg = g_fe_dbg;
   size_t smem = sizeof(float2) * FE_FC * FE_ZLD + sizeof(float) * (FE_FC * FE_PLD + (size_t)p.Lsz + FE_NFFT) +
-                sizeof(float2) * (200 + 202) + sizeof(float) * ((size_t)p.n_mels * p.n_mfcc + 4);
+                sizeof(float2) * (200 + 202) + sizeof(float) * ((p.dct_alias ? 0 : (size_t)p.dct_sz) + 2 * (size_t)p.xs_len + (size_t)p.n_mels * p.fb_ld + 2 * (size_t)p.n_mels + 4);
   PC_REQUIRE(smem <= 227 * 1024, PC_EUNSUPPORTED, "pc_frontend_fwd: clip of %d samples (%d frames) needs %zu B shared memory (> 227 KB)", S, p.T, smem);
   static size_t smem_set = 0;
   if (smem > smem_set) {

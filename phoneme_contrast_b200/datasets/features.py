@@ -92,7 +92,7 @@ class _FrontEndConsts:
             keep = [t.to(device) if t is not None else None for t in (self.window, self.start, self.length, self.w, self.dct, self.tw)]
             st = PcMfccConsts(ptr(keep[0]), ptr(keep[1], torch.int32), ptr(keep[2], torch.int32), ptr(keep[3]),
                               ptr(keep[4]) if keep[4] is not None else None, ptr(keep[5]), self.n_fft, self.hop, self.n_mels,
-                              self.n_mfcc or 0)
+                              self.n_mfcc or 0, int(self.length.max()))
             self._dev[key] = (st, keep)
         return self._dev[key]
 
