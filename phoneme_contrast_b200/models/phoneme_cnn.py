@@ -118,6 +118,35 @@ def _drop_masks(net, B, chans, training):
     return [ops.dropout2d_mask(B, c, net.dropout_rate, seed, i << 20, dev, net._drop_step) for i, c in enumerate(chans)]
 
 
+class _WgradLane:
+    """Weight gradients run on a second CUDA stream: wgrad(l) needs only dy_l, while the main stream continues with
+    dgrad(l) and the BatchNorm backward of layer l-1, so the two chains overlap (they also fill each other's wave tails:
+    most tensor-core kernels here occupy one CTA per SM). The lane joins the main stream before the backward returns;
+    inside a CUDA-graph capture this becomes a fork/join in the graph."""
+
+    def __init__(self, net, keep):
+        self.enabled = os.environ.get("PC_WGRAD_STREAM", "1") == "1"
+        self.keep = keep            # tensors that must outlive the side-stream kernels
+        if self.enabled:
+            if getattr(net, "_side_stream", None) is None:
+                net._side_stream = torch.cuda.Stream()
+            self.side = net._side_stream
+            self.main = torch.cuda.current_stream()
+
+    def __call__(self, x, dy, g, xform, dw, db, prec):
+        if not self.enabled:
+            ops.conv_wgrad(x, dy, g, xform, dw, db, prec)
+            return
+        self.keep.extend((x, dy))
+        self.side.wait_stream(self.main)
+        with torch.cuda.stream(self.side):
+            ops.conv_wgrad(x, dy, g, xform, dw, db, prec)
+
+    def join(self):
+        if self.enabled:
+            self.main.wait_stream(self.side)
+
+
 def _head(net, s, a, training):
     att = net.attention.conv if net.use_attention else None
     w_att = att.weight.view(-1) if att is not None else None
@@ -181,18 +210,21 @@ def _small_forward(net, x, training):
 def _small_backward(net, s, demb, grads, training=True):
     prec = net._prec
     blocks = net.conv_blocks
+    keep = []
+    wgrad = _WgradLane(net, keep)
     dout = _head_bwd(net, s, demb, grads, training)
     for b in (2, 1, 0):
         convA, bnA, convB, bnB = blocks[b][0], blocks[b][1], blocks[b][3], blocks[b][4]
         ly = s.layers[b]
         dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias])
         xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
-        ops.conv_wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], grads[convB.bias], prec)
+        wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], grads[convB.bias], prec)
         dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d)
         dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias])
-        ops.conv_wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], grads[convA.bias], prec)
+        wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], grads[convA.bias], prec)
         if b > 0:
             dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d)
+    wgrad.join()
 
 
 def _deep_forward(net, x, training):
@@ -250,6 +282,8 @@ def _deep_forward(net, x, training):
 
 def _deep_backward(net, s, demb, grads, training=True):
     prec = net._prec
+    keep = []
+    wgrad = _WgradLane(net, keep)
     dout = _head_bwd(net, s, demb, grads, training)
     for i in reversed(range(len(s.blocks))):
         blk = net.conv_blocks[i]
@@ -262,12 +296,12 @@ def _deep_backward(net, s, demb, grads, training=True):
         else:
             dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None)
         xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
-        ops.conv_wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec)
+        wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec)
         dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d)
         dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias])
-        ops.conv_wgrad(r["xin"], dy1, r["g1"], None, grads[blk.conv1.weight], grads[blk.conv1.bias], prec)
+        wgrad(r["xin"], dy1, r["g1"], None, grads[blk.conv1.weight], grads[blk.conv1.bias], prec)
         if r["proj"]:
-            ops.conv_wgrad(r["xin"], dysc, r["gs"], None, grads[convs.weight], grads[convs.bias], prec)
+            wgrad(r["xin"], dysc, r["gs"], None, grads[convs.weight], grads[convs.bias], prec)
             dxin = ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], prec=r["cws"].prec_d)
         else:
             dxin = dysc                                        # identity shortcut: d(out)/d(xin) passes g through
@@ -276,7 +310,8 @@ def _deep_backward(net, s, demb, grads, training=True):
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
     st = s.stem
     dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias])
-    ops.conv_wgrad(s.x, dy0, st["g"], None, grads[conv0.weight], grads[conv0.bias], prec)
+    wgrad(s.x, dy0, st["g"], None, grads[conv0.weight], grads[conv0.bias], prec)
+    wgrad.join()
 
 
 class _NetFunction(torch.autograd.Function):
