@@ -214,11 +214,11 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict
   const int ppb = blockDim.x / C4;  // pixels per block iteration
   const float4 s = ld4(scale + c), t = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  const long long npix = (long long)B * H * W;
-  for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < npix; p += (long long)gridDim.x * ppb) {
-    const int w = (int)(p % W);
-    const int h = (int)((p / W) % H);
-    const int b = (int)(p / ((long long)W * H));
+  const int npix = B * H * W;      // < 2^31 (checked by the launcher)
+#pragma unroll 2
+  for (int p = blockIdx.x * ppb + threadIdx.x / C4; p < npix; p += gridDim.x * ppb) {
+    const int w = p % W, t2 = p / W;
+    const int h = t2 % H, b = t2 / H;
     float dz[4];
     float4 yv;
     bn_act_dz<POOL>(dout, y, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
@@ -242,7 +242,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
   const int C4 = C >> 2;
   const int c4 = threadIdx.x % C4, c = c4 * 4;
   const int ppb = blockDim.x / C4;
-  const long long npix = (long long)B * H * W;
+  const int npix = B * H * W;
   const float invM = 1.0f / (float)npix;
   const float4 s = ld4(scale + c), t = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
   float sdz[4], sdzx[4];
@@ -259,10 +259,10 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
     }
   }
   const float sv[4] = PC_F4_ARR(s), muv[4] = PC_F4_ARR(mu), isv[4] = PC_F4_ARR(is);
-  for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < npix; p += (long long)gridDim.x * ppb) {
-    const int w = (int)(p % W);
-    const int h = (int)((p / W) % H);
-    const int b = (int)(p / ((long long)W * H));
+#pragma unroll 2
+  for (int p = blockIdx.x * ppb + threadIdx.x / C4; p < npix; p += gridDim.x * ppb) {
+    const int w = p % W, t2 = p / W;
+    const int h = t2 % H, b = t2 / H;
     float dz[4];
     float4 yv;
     bn_act_dz<POOL>(dout, y, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
@@ -316,6 +316,7 @@ bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __res
   float4 mus = make_float4(0.f, 0.f, 0.f, 0.f), iss = mus;
   if (proj) { mus = ld4(mean_s + c); iss = ld4(invstd_s + c); }
   float acc[3][4] = {};
+#pragma unroll 2
   for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < n_pix; p += (long long)gridDim.x * ppb) {
     const size_t o = (size_t)p * C + c;
     const float4 d = ld4(dout + o), ov = ld4(out + o), yv = ld4(y2 + o);
@@ -423,6 +424,16 @@ __global__ void dropout2d_mask_kernel(float* __restrict__ drop, int n, float p, 
     if (i * 4 + q < n) drop[i * 4 + q] = (Philox::u01(rv[q]) >= p) ? keep_scale : 0.f;
 }
 
+// reduction passes end with one fp64 atomic per channel per block onto the SAME few addresses (they serialise in L2), so
+// they run on at most 4 blocks per SM
+static inline int reduce_grid(long long work_items, int per_block) {
+  long long g = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)kNumSMs * 4;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
 static inline int ew_grid(long long work_items, int per_block) {
   long long g = (work_items + per_block - 1) / per_block;
   const long long cap = (long long)kNumSMs * 16;
@@ -486,7 +497,8 @@ extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, in
   int Ho, Wo;
   pool_out_dims(H, W, pool, &Ho, &Wo);
   const long long items = (long long)B * H * W * (C / 4);
-  const int grid = ew_grid(items, 256 * 4);
+  PC_REQUIRE((long long)B * H * W < (1LL << 31), PC_EUNSUPPORTED, "pc_bn_act_bwd_reduce: too many pixels");
+  const int grid = reduce_grid(items, 256 * 4);
   if (pool == 0) bn_act_bwd_reduce_kernel<0><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
   else if (pool == 2) bn_act_bwd_reduce_kernel<2><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
   else bn_act_bwd_reduce_kernel<3><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
@@ -530,7 +542,7 @@ extern "C" int pc_bn_add_relu_bwd_reduce(const float* dout, const float* out, co
   PC_REQUIRE(dout && out && y2 && mean2 && invstd2 && sums2 && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_bwd_reduce: bad arguments");
   PC_REQUIRE(sums_s == nullptr || (ysc && mean_s && invstd_s), PC_EINVAL, "pc_bn_add_relu_bwd_reduce: shortcut pointers");
   PC_CHECK_C4("pc_bn_add_relu_bwd_reduce", C);
-  bn_add_relu_bwd_reduce_kernel<<<ew_grid(n_pix * (C / 4), 256 * 4), 256, 0, stream>>>(dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s);
+  bn_add_relu_bwd_reduce_kernel<<<reduce_grid(n_pix * (C / 4), 256 * 4), 256, 0, stream>>>(dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s);
   PC_LAUNCH_CHECK("bn_add_relu_bwd_reduce_kernel");
   return PC_OK;
 }
