@@ -579,6 +579,10 @@ extern "C" void pc_tc_set_debug(long long* buf) { pc::tcconv::g_dbg = buf; }
 extern "C" int pc_conv_tc_supported(const PcConvGeom* g, int dgrad, int prec) {
   if (g == nullptr || (prec != PC_PREC_TF32X3 && prec != PC_PREC_BF16)) return 0;
   const int ca = dgrad ? g->Cout : g->Cin, nn = dgrad ? g->Cin : g->Cout;
+  // 32-bit element offsets inside the kernel: the gathered tensor and the output must have fewer than 2^31 elements;
+  // the tap bitmask holds at most 32 taps
+  const long long in_elems = (long long)g->B * g->H * g->W * g->Cin, out_elems = (long long)g->B * g->Ho * g->Wo * g->Cout;
+  if (in_elems >= (1LL << 31) || out_elems >= (1LL << 31) || g->R * g->S > 32) return 0;
   return (ca % bkc_of(prec) == 0 && nn % 4 == 0 && nn >= 16) ? 1 : 0;
 }
 
