@@ -36,6 +36,26 @@ WORKLOADS = {
 FLOP_PER_SAMPLE = {"phoneme_cnn": 3 * 298.07e6, "phoneme_cnn_deep": 3 * 568.59e6}   # fwd MAC*2, x3 for training
 
 
+# mean dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from profiles/r1_tc_conv_full.md
+TRAFFIC_NCU = {}
+try:
+    import re as _re
+    _txt = open(os.path.join(ROOT, "profiles", "r1_tc_conv_full.md")).read()
+    for _entry, _pat in (("pc_conv_fwd", "igemm_tc_kernel"), ("pc_conv_dgrad", "igemm_tc_kernel"), ("pc_conv_wgrad", "wgrad_tc_kernel")):
+        _vals = []
+        for _sec in _txt.split("## ")[1:]:
+            if _pat in _sec.splitlines()[0]:
+                _r = _re.search(r"dram__bytes_read.sum \| ([0-9.]+) \| (\w+)", _sec)
+                _w = _re.search(r"dram__bytes_write.sum \| ([0-9.]+) \| (\w+)", _sec)
+                if _r and _w:
+                    _u = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+                    _vals.append(float(_r.group(1)) * _u.get(_r.group(2), 1.0) + float(_w.group(1)) * _u.get(_w.group(2), 1.0))
+        if _vals:
+            TRAFFIC_NCU[_entry] = sum(_vals) / len(_vals)
+except Exception:
+    pass
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -51,7 +71,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -179,10 +199,12 @@ def bench_train(workload, steps, warmup, parallel, device, want_profile=True, us
     if want_profile:
         # every rank runs the profiled steps (they contain collectives); only rank 0 records events
         n_prof = min(steps, 5)
+        os.environ["PC_WGRAD_STREAM"] = "0"      # serialise the weight-gradient lane so per-entry-point durations do not overlap
         if rank == 0:
             _lib.profile_begin()
         for i in range(n_prof):
             tr.train_step(xs[i % len(xs)], y)
+        os.environ["PC_WGRAD_STREAM"] = "1"
         if rank == 0:
             prof = _lib.profile_end()
             for v in prof.values():
@@ -254,10 +276,14 @@ def roofline_from_profile(prof, pk, pk_kind):
     conv_ms = sum(v["ms"] for v in conv.values())
     conv_flop = sum(v["work"] for v in conv.values())
     top = prof[name]
+    kernel_of = {"pc_conv_fwd": "tcconv::igemm_tc_kernel<fwd> (entry pc_conv_fwd; includes the Cin=1 stem kernel)",
+                 "pc_conv_dgrad": "tcconv::igemm_tc_kernel<dgrad> (entry pc_conv_dgrad)",
+                 "pc_conv_wgrad": "tcwg::wgrad_tc_kernel (entry pc_conv_wgrad; includes the split reduce and the stem wgrad kernel)"}
     ach = (top["work"] / (top["ms"] * 1e-3)) / 1e12 if top["work"] else None
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
-    return {"bound": "tensor", "kernel": name, "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
-            "traffic": None, "peak_source": f"{pk_kind} cuBLAS bf16 sustained (MEASURED_PEAKS.json); kernel timed inside a long step",
+    return {"bound": "tensor", "kernel": kernel_of.get(name, name), "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
+            "traffic": TRAFFIC_NCU.get(name), "traffic_note": "mean dram read+write bytes per launch over the launches captured with ncu --set full (profiles/r1_tc_conv_full.md)",
+            "peak_source": f"{pk_kind} cuBLAS bf16 sustained (MEASURED_PEAKS.json); kernel timed inside a long step; the kernels run TF32x3 (3 tf32 MMAs per k-step at half the bf16 rate), i.e. their own ceiling is peak/6",
             "kernel_share_of_step": top["ms"] / total, "kernel_ms_per_step": top["ms"], "launches_per_step": top["calls"],
             "all_conv": {"ms_per_step": conv_ms, "tflops": conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
                          "share_of_step": conv_ms / total},
@@ -420,7 +446,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="train_cnn_deep", choices=list(WORKLOADS))

@@ -64,10 +64,10 @@ struct Params {
   } while (0)
 
 template <int PREC> struct Prec;
-// NACC: TMEM accumulators per tile. The tensor core adds into its fp32 accumulator with truncation, so a long
-// dependent chain of accumulations picks up a bias of ~2^-24 per step. TF32X3 therefore spreads the hi*hi terms
-// round-robin over 3 accumulators and keeps the two small correction terms in a 4th; the epilogue adds the four
-// partial sums in registers with round-to-nearest (measured: ~10x lower error than a single accumulator).
+// NACC: TMEM accumulators (of BN columns) per tile. The tensor core adds into its fp32 accumulator with truncation, so a
+// long dependent chain of accumulations picks up a bias of ~2^-24 per step. TF32X3 therefore keeps the small correction
+// terms apart from the hi*hi terms and alternates between two accumulator sets [main | corr] per k-step; the epilogue adds
+// the four partial sums in registers with round-to-nearest (measured: ~10x lower error than a single accumulator).
 template <> struct Prec<PC_PREC_TF32X3> { static constexpr int BKC = 32, PARTS = 2, NACC = 4; };
 template <> struct Prec<PC_PREC_BF16> { static constexpr int BKC = 64, PARTS = 1, NACC = 1; };
 
@@ -412,6 +412,7 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
     // ============================================================ MMA issuer
     if (lane == 0) {
       const uint32_t idesc = instr_desc(PREC == PC_PREC_BF16 ? 1u : 2u, BM, BN);
+      const uint32_t idesc2 = instr_desc(2u, BM, 2 * BN);
       const int n_act = s_nact[0];
       for (int it = 0; it < n_act; ++it) {
         const int s = it % S;
@@ -431,11 +432,12 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
           const uint64_t adv = (uint64_t)(kk * 2);       // 32 bytes per k-step, in 16-byte units
           const int ks = it * 4 + kk;                    // global k-step
           if (PREC == PC_PREC_TF32X3) {
-            const uint32_t d_main = tmem_base + (uint32_t)((ks % 3) * BN);
-            const uint32_t d_corr = tmem_base + (uint32_t)(3 * BN);
-            mma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, ks == 0 ? 0u : 1u);
-            mma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-            mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ks < 3 ? 0u : 1u);
+            // b_lo is stored right behind b_hi, so ONE MMA with N = 2*BN forms a_hi*b_hi (columns [0,BN): main) and
+            // a_hi*b_lo (columns [BN,2BN): correction) while reading a_hi from shared memory once; the second MMA adds
+            // a_lo*b_hi into the correction half. Two accumulator sets alternate per k-step (see NACC note above).
+            const uint32_t d_set = tmem_base + (uint32_t)((ks & 1) * 2 * BN);
+            mma_tf32(d_set, a_hi + adv, b_hi + adv, idesc2, ks < 2 ? 0u : 1u);
+            mma_tf32(d_set + BN, a_lo + adv, b_hi + adv, idesc, 1u);
           } else {
             mma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, ks == 0 ? 0u : 1u);
           }

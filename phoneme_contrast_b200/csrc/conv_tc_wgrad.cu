@@ -230,6 +230,7 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
     if (lane == 0) {
       // kind::tf32, D fp32, A and B MN-major (bits 15, 16), N = BN, M = 128
       const uint32_t idesc = instr_desc(2u, 128, BN) | (1u << 15) | (1u << 16);
+      const uint32_t idesc2 = instr_desc(2u, 128, 2 * BN) | (1u << 15) | (1u << 16);
       if (n_stages == 0) {
         // nothing to reduce in this split (cannot happen with the host's split choice, kept for safety)
       }
@@ -245,11 +246,11 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
         for (int kk = 0; kk < 4; ++kk) {
           const uint64_t adv = (uint64_t)(kk * (1024 >> 4));   // next 8-pixel group
           const int ks = st * 4 + kk;
-          const uint32_t d_main = tmem_base + (uint32_t)((ks % 3) * BN);
-          const uint32_t d_corr = tmem_base + (uint32_t)(3 * BN);
-          mma_tf32(d_corr, a_lo + adv, b_hi + adv, idesc, ks == 0 ? 0u : 1u);
-          mma_tf32(d_corr, a_hi + adv, b_lo + adv, idesc, 1u);
-          mma_tf32(d_main, a_hi + adv, b_hi + adv, idesc, ks < 3 ? 0u : 1u);
+          // one N = 2*BN MMA forms a_hi*[b_hi; b_lo] (main | correction), a second adds a_lo*b_hi to the correction half;
+          // two accumulator sets alternate per k-step (same scheme as conv_tc.cu)
+          const uint32_t d_set = tmem_base + (uint32_t)((ks & 1) * 2 * BN);
+          mma_tf32(d_set, a_hi + adv, b_hi + adv, idesc2, ks < 2 ? 0u : 1u);
+          mma_tf32(d_set + BN, a_lo + adv, b_hi + adv, idesc, 1u);
         }
         mma_commit(&empty[s]);
       }
