@@ -283,7 +283,7 @@ def roofline_from_profile(prof, pk, pk_kind):
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     return {"bound": "tensor", "kernel": kernel_of.get(name, name), "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
             "traffic": TRAFFIC_NCU.get(name), "traffic_note": "mean dram read+write bytes per launch over the launches captured with ncu --set full (profiles/r1_tc_conv_full.md)",
-            "peak_source": f"{pk_kind} cuBLAS bf16 sustained (MEASURED_PEAKS.json); kernel timed inside a long step; the kernels run TF32x3 (3 tf32 MMAs per k-step at half the bf16 rate), i.e. their own ceiling is peak/6",
+            "peak_source": f"{pk_kind} cuBLAS bf16 sustained (MEASURED_PEAKS.json); kernel timed inside a long step; achieved counts the convolution's algorithmic fp32 FLOPs once, while the kernels issue 3 fp16 tensor-core products per operand pair (FP16x2 split for fp32-level accuracy), i.e. their own ceiling is peak/3",
             "kernel_share_of_step": top["ms"] / total, "kernel_ms_per_step": top["ms"], "launches_per_step": top["calls"],
             "all_conv": {"ms_per_step": conv_ms, "tflops": conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
                          "share_of_step": conv_ms / total},
@@ -498,7 +498,7 @@ def main():
                 "gpu_launches": int(round(r["launches"] * args.steps)),
                 "config": {"workload": wl["desc"], "views_per_gpu": r["views"], "global_views": r["views"] * world,
                            "parallelism": f"dp{world}: all_gather(embeddings, labels, row stats) + flat-bucket gradient all-reduce; per-rank BatchNorm statistics",
-                           "precision": "fp32 storage and accumulate; convolutions on tcgen05 tensor cores in TF32x3 (3-term split, fp32-level accuracy), exact-fp32 SIMT for the Cin=1 stem",
+                           "precision": "fp32 storage and accumulate; convolutions on tcgen05 tensor cores with fp32 operands split into fp16 hi + lo (3 products per pair, ~22-bit operands: fp32-level accuracy, parity-tested at 1e-4), exact-fp32 SIMT for the Cin=1 stem",
                            "launch": "eager launches" if (args.no_graph or world > 1) else "whole step captured in one CUDA graph (inputs copied into static buffers each step)",
                            "l2": "no explicit flush: each step streams ~2 GB of activations (>> 126 MB L2); inputs rotate over 4 device buffers",
                            "step_tflops": FLOP_PER_SAMPLE[r["arch"]] * r["views"] / (r["ms_per_step"] * 1e-3) / 1e12,

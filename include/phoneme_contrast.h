@@ -138,11 +138,15 @@ int pc_pack_conv_weight(const float* w_oihw, int O, int I, int R, int S, float* 
 /* Precision of the implicit-GEMM convolutions:
  *   PC_PREC_FP32   exact-fp32 SIMT kernels (operands packed by pc_pack_conv_weight);
  *   PC_PREC_TF32X3 tcgen05 tensor cores, fp32 operands split hi+lo, 3 kind::tf32 MMAs per k-step (fp32-level accuracy);
+ *   PC_PREC_FP16X2 tcgen05 tensor cores, fp32 operands split x = hi + lo*2^-11 with hi, lo in fp16, 3 products per k-step at
+ *                  the kind::f16 rate (same ~22-bit operand precision as TF32X3). Gradient operands are pre-scaled by a
+ *                  power of two taken from the tensor's max magnitude (the `*_amax` arguments below) to fit fp16's range;
+ *                  forward activations must stay below 65504 in magnitude (they follow a BatchNorm);
  *   PC_PREC_BF16   tcgen05 tensor cores, operands rounded to bf16 (1e-2 tolerance mode).
  * For the two tensor-core modes the weight operand is the pre-swizzled tile image written by
  * pc_pack_conv_weight_tc, and a layer is eligible when pc_conv_tc_supported() != 0 (gathered channels a multiple of
  * 32 / 64); ineligible layers must be run with PC_PREC_FP32. */
-enum { PC_PREC_FP32 = 0, PC_PREC_TF32X3 = 1, PC_PREC_BF16 = 2 };
+enum { PC_PREC_FP32 = 0, PC_PREC_TF32X3 = 1, PC_PREC_BF16 = 2, PC_PREC_FP16X2 = 3 };
 int pc_conv_tc_supported(const PcConvGeom* g, int dgrad, int prec);
 size_t pc_conv_tc_packed_bytes(int O, int I, int R, int S, int dgrad, int prec);
 int pc_pack_conv_weight_tc(const float* w_oihw, int O, int I, int R, int S, int dgrad, int prec, void* out, pc_stream_t stream);
@@ -157,13 +161,14 @@ int pc_tc_gemm(const float* A, const float* B, const float* bias, float* C, int 
  * weight itself); otherwise Cin % 16 == 0 and the implicit-GEMM kernel of the requested precision runs. */
 int pc_conv_fwd(const float* x, const float* wf, const float* bias, const PcConvGeom* g, const PcInXform* xf,
                 float* y, double* stats, int prec, pc_stream_t stream);
-/* dx (+)= conv_transpose(dy, w): accumulate != 0 adds into dx. */
+/* dx (+)= conv_transpose(dy, w): accumulate != 0 adds into dx. dy_amax (may be NULL): device scalar holding max|dy|, written by
+ * the BatchNorm-backward apply calls below; PC_PREC_FP16X2 derives its power-of-two operand scale from it (NULL: scale 1). */
 int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom* g, float* dx, int accumulate, int prec,
-                  pc_stream_t stream);
+                  const float* dy_amax, pc_stream_t stream);
 /* dw (OIHW) and db from x (through xform) and dy. workspace >= pc_conv_wgrad_workspace(g) bytes. */
 size_t pc_conv_wgrad_workspace(const PcConvGeom* g);
 int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw,
-                  float* db, void* workspace, size_t workspace_bytes, int prec, pc_stream_t stream);
+                  float* db, void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream);
 
 /* BatchNorm statistics -> per-channel coefficients.
  * training: mean/var from stats (count = elements per channel), running stats updated with `momentum`
@@ -178,14 +183,15 @@ int pc_bn_finalize(const double* stats, int C, double count, const float* gamma,
 int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const float* scale, const float* shift,
                   const float* drop, int pool, float* out, uint8_t* argmax, pc_stream_t stream);
 /* Backward of the above w.r.t. y: two passes. pass 1 accumulates sums[0][C] = sum dz, sums[1][C] = sum dz*xhat (fp64);
- * pass 2 writes dy = scale*(dz - sum_dz/M - xhat*sum_dzxhat/M) and dgamma/dbeta. dout is the gradient w.r.t. `out`. */
+ * pass 2 writes dy = scale*(dz - sum_dz/M - xhat*sum_dzxhat/M) and dgamma/dbeta. dout is the gradient w.r.t. `out`.
+ * dy_amax (may be NULL): zero-initialised device scalar that receives max|dy| (atomic max). */
 int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
                          const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
                          const uint8_t* argmax, double* sums, pc_stream_t stream);
 int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
                         const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
                         const uint8_t* argmax, const double* sums, float* dy, float* dgamma, float* dbeta,
-                        pc_stream_t stream);
+                        float* dy_amax, pc_stream_t stream);
 
 /* Residual tail: out = relu(bn2(y2) + (sc_scale ? bn_s(ysc) : ysc))   (phoneme_cnn.py:177-182). */
 int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const float* shift2, const float* ysc,
@@ -200,7 +206,7 @@ int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, const float* y
                              const float* mean2, const float* invstd2, const double* sums2, const float* ysc,
                              const float* sc_scale, const float* mean_s, const float* invstd_s, const double* sums_s,
                              int64_t n_pix, int C, float* dy2, float* dysc_or_dx, float* dgamma2, float* dbeta2,
-                             float* dgamma_s, float* dbeta_s, pc_stream_t stream);
+                             float* dgamma_s, float* dbeta_s, float* dy2_amax, float* dysc_amax, pc_stream_t stream);
 
 /* SpatialAttention + AdaptiveAvgPool2d(1): pooled[b,c] = mean_p a[b,p,c] * sigmoid(w.a[b,p,:] + b0)
  * (phoneme_cnn.py:134-143,117-118). w == NULL: plain mean (use_attention False). gate [B,HW] saved for backward. */

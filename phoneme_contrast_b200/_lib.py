@@ -18,7 +18,7 @@ PC_OK, PC_EINVAL, PC_EUNSUPPORTED, PC_ECUDA = 0, -1, -2, -3
 PC_FB_MAXW = 32
 FE_MFCC, FE_LOGMEL = 0, 1
 CLAMP_PER_CLIP, CLAMP_NONE, CLAMP_GIVEN = 0, 1, 2
-PREC_FP32, PREC_TF32X3, PREC_BF16 = 0, 1, 2
+PREC_FP32, PREC_TF32X3, PREC_BF16, PREC_FP16X2 = 0, 1, 2, 3
 
 vp, i32, i64, f32, f64, u64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64, C.c_size_t
 
@@ -60,16 +60,16 @@ SIGNATURES = {
     "pc_tc_gemm_workspace": (sz, [i32, i32, i32]),
     "pc_tc_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]),
     "pc_conv_fwd": (i32, [vp, vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, i32, vp]),
-    "pc_conv_dgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, i32, i32, vp]),
+    "pc_conv_dgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, i32, i32, vp, vp]),
     "pc_conv_wgrad_workspace": (sz, [C.POINTER(PcConvGeom)]),
-    "pc_conv_wgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, vp, sz, i32, vp]),
+    "pc_conv_wgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, vp, sz, i32, vp, vp]),
     "pc_bn_finalize": (i32, [vp, i32, f64, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp]),
     "pc_bn_act_fwd": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     "pc_bn_act_bwd_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
-    "pc_bn_act_bwd_apply": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp]),
+    "pc_bn_act_bwd_apply": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
     "pc_bn_add_relu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp]),
     "pc_bn_add_relu_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),
-    "pc_bn_add_relu_bwd_apply": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "pc_bn_add_relu_bwd_apply": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pc_attn_pool_fwd": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "pc_attn_pool_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "pc_head_workspace": (sz, [i32, i32, i32]),

@@ -4,6 +4,7 @@
 
 #include <atomic>
 
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace pc {
@@ -17,6 +18,13 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PC_PDL");   // opt-in: measured slightly slower than plain launches inside the captured step
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 }  // namespace pc
 
 extern "C" const char* pc_last_error(void) { return pc::g_err; }

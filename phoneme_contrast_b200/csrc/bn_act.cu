@@ -15,6 +15,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, doub
                                    int64_t* __restrict__ nbt, float momentum, float eps, int training,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_o,
                                    float* __restrict__ invstd_o) {
+  pdl_trigger();
+  pdl_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && training && nbt != nullptr) nbt[0] += 1;
   if (c >= C) return;
@@ -51,12 +53,25 @@ __device__ __forceinline__ float4 bn_relu4(float4 y, float4 s, float4 t) {
 }
 #define PC_F4_ARR(v) {(v).x, (v).y, (v).z, (v).w}
 
+// max |x| of a freshly written gradient tensor, accumulated with an integer atomicMax on the float's bit pattern (valid for
+// non-negative floats). Consumed by the FP16X2 convolutions as their operand scale (include/phoneme_contrast.h).
+__device__ __forceinline__ void amax_commit(float* amax, float local_max) {
+  if (amax == nullptr) return;
+  local_max = warp_max(local_max);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(local_max));
+}
+__device__ __forceinline__ float absmax4(const float (&r)[4], float m) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(r[0]), fabsf(r[1]))), fmaxf(fabsf(r[2]), fabsf(r[3])));
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 template <int POOL>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ drop, float* __restrict__ out,
                   uint8_t* __restrict__ argmax) {
+  pdl_trigger();
+  pdl_wait();
   const int C4 = C >> 2;
   const long long total = (long long)B * Ho * Wo * C4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -208,6 +223,8 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict
                          int Wo, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ drop,
                          const uint8_t* __restrict__ argmax, double* __restrict__ sums) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[256 * 4];
   const int C4 = C >> 2;
   const int c4 = threadIdx.x % C4, c = c4 * 4;
@@ -238,7 +255,9 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
                         int Wo, const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ drop,
                         const uint8_t* __restrict__ argmax, const double* __restrict__ sums, float* __restrict__ dy,
-                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dy_amax) {
+  pdl_trigger();
+  pdl_wait();
   const int C4 = C >> 2;
   const int c4 = threadIdx.x % C4, c = c4 * 4;
   const int ppb = blockDim.x / C4;
@@ -259,6 +278,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
     }
   }
   const float sv[4] = PC_F4_ARR(s), muv[4] = PC_F4_ARR(mu), isv[4] = PC_F4_ARR(is);
+  float lmax = 0.f;
 #pragma unroll 2
   for (int p = blockIdx.x * ppb + threadIdx.x / C4; p < npix; p += gridDim.x * ppb) {
     const int w = p % W, t2 = p / W;
@@ -273,8 +293,10 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
       const float xhat = (yy[q] - muv[q]) * isv[q];
       r[q] = sv[q] * (dz[q] - sdz[q] * invM - xhat * sdzx[q] * invM);
     }
+    lmax = absmax4(r, lmax);
     st4(dy + (size_t)p * C + c, make_float4(r[0], r[1], r[2], r[3]));
   }
+  amax_commit(dy_amax, lmax);
 }
 
 // ------------------------------------------------------------------------------------------------ residual tail
@@ -282,6 +304,8 @@ __global__ void __launch_bounds__(256)
 bn_add_relu_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ scale2, const float* __restrict__ shift2,
                        const float* __restrict__ ysc, const float* __restrict__ sc_scale, const float* __restrict__ sc_shift,
                        long long n_pix, int C, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int C4 = C >> 2;
   const long long total = n_pix * C4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -307,6 +331,8 @@ bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __res
                               const float* __restrict__ ysc, const float* __restrict__ mean_s,
                               const float* __restrict__ invstd_s, long long n_pix, int C, double* __restrict__ sums2,
                               double* __restrict__ sums_s) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[256 * 4];
   const int C4 = C >> 2;
   const int c4 = threadIdx.x % C4, c = c4 * 4;
@@ -355,7 +381,10 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
                              const float* __restrict__ mean_s, const float* __restrict__ invstd_s,
                              const double* __restrict__ sums_s, long long n_pix, int C, float* __restrict__ dy2,
                              float* __restrict__ dysc, float* __restrict__ dgamma2, float* __restrict__ dbeta2,
-                             float* __restrict__ dgamma_s, float* __restrict__ dbeta_s) {
+                             float* __restrict__ dgamma_s, float* __restrict__ dbeta_s, float* __restrict__ dy2_amax,
+                             float* __restrict__ dysc_amax) {
+  pdl_trigger();
+  pdl_wait();
   const int C4 = C >> 2;
   const int c4 = threadIdx.x % C4, c = c4 * 4;
   const int ppb = blockDim.x / C4;
@@ -382,6 +411,7 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
   }
   const float s2v[4] = PC_F4_ARR(s2), mu2v[4] = PC_F4_ARR(mu2), is2v[4] = PC_F4_ARR(is2);
   const float ssv[4] = PC_F4_ARR(ss), musv[4] = PC_F4_ARR(mus), issv[4] = PC_F4_ARR(iss);
+  float lmax2 = 0.f, lmaxs = 0.f;
   for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < n_pix; p += (long long)gridDim.x * ppb) {
     const size_t o = (size_t)p * C + c;
     const float4 d = ld4(dout + o), ov = ld4(out + o), yv = ld4(y2 + o);
@@ -404,14 +434,20 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
         rs[q] = g[q];
       }
     }
+    lmax2 = absmax4(r2, lmax2);
+    lmaxs = absmax4(rs, lmaxs);
     st4(dy2 + o, make_float4(r2[0], r2[1], r2[2], r2[3]));
     st4(dysc + o, make_float4(rs[0], rs[1], rs[2], rs[3]));
   }
+  amax_commit(dy2_amax, lmax2);
+  amax_commit(dysc_amax, lmaxs);
 }
 
 // ------------------------------------------------------------------------------------------------ dropout mask
 __global__ void dropout2d_mask_kernel(float* __restrict__ drop, int n, float p, float keep_scale, uint64_t seed, uint64_t offset,
                                       const long long* __restrict__ step_dev) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i * 4 >= n) return;
   if (step_dev != nullptr) offset += (uint64_t)step_dev[0] << 24;      // graph-capturable: the call counter lives on the device
@@ -461,7 +497,7 @@ extern "C" int pc_bn_finalize(const double* stats, int C, double count, const fl
              "pc_bn_finalize: missing statistics");
   // nn.BatchNorm raises for a single value per channel in training mode (tests/test_models.py:52,97-103 avoid it)
   PC_REQUIRE(!training || count > 1.0, PC_EINVAL, "Expected more than 1 value per channel when training");
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(stats, C, count, gamma, beta, running_mean, running_var,
+  launch_pdl(bn_finalize_kernel, dim3(ceil_div(C, 128)), dim3(128), 0, stream, stats, C, count, gamma, beta, running_mean, running_var,
                                                             num_batches_tracked, momentum, eps, training, scale, shift,
                                                             mean, invstd);
   PC_LAUNCH_CHECK("bn_finalize_kernel");
@@ -481,9 +517,9 @@ extern "C" int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const f
   PC_REQUIRE(Ho > 0 && Wo > 0, PC_EINVAL, "pc_bn_act_fwd: input %dx%d too small for pooling", H, W);
   const long long total = (long long)B * Ho * Wo * (C / 4);
   const int grid = ew_grid(total, 256);
-  if (pool == 0) bn_act_fwd_kernel<0><<<grid, 256, 0, stream>>>(y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
-  else if (pool == 2) bn_act_fwd_kernel<2><<<grid, 256, 0, stream>>>(y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
-  else bn_act_fwd_kernel<3><<<grid, 256, 0, stream>>>(y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
+  if (pool == 0) launch_pdl((bn_act_fwd_kernel<0>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
+  else if (pool == 2) launch_pdl((bn_act_fwd_kernel<2>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
+  else launch_pdl((bn_act_fwd_kernel<3>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
   PC_LAUNCH_CHECK("bn_act_fwd_kernel");
   return PC_OK;
 }
@@ -499,9 +535,9 @@ extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, in
   const long long items = (long long)B * H * W * (C / 4);
   PC_REQUIRE((long long)B * H * W < (1LL << 31), PC_EUNSUPPORTED, "pc_bn_act_bwd_reduce: too many pixels");
   const int grid = reduce_grid(items, 256 * 4);
-  if (pool == 0) bn_act_bwd_reduce_kernel<0><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
-  else if (pool == 2) bn_act_bwd_reduce_kernel<2><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
-  else bn_act_bwd_reduce_kernel<3><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
+  if (pool == 0) launch_pdl((bn_act_bwd_reduce_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
+  else if (pool == 2) launch_pdl((bn_act_bwd_reduce_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
+  else launch_pdl((bn_act_bwd_reduce_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
   PC_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
   return PC_OK;
 }
@@ -509,7 +545,7 @@ extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, in
 extern "C" int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
                                    const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
                                    const uint8_t* argmax, const double* sums, float* dy, float* dgamma, float* dbeta,
-                                   pc_stream_t stream) {
+                                   float* dy_amax, pc_stream_t stream) {
   PC_REQUIRE(dout && y && scale && shift && mean && invstd && sums && dy, PC_EINVAL, "pc_bn_act_bwd_apply: null pointer");
   PC_CHECK_C4("pc_bn_act_bwd_apply", C);
   PC_REQUIRE(pool == 0 || pool == 2 || (pool == 3 && argmax), PC_EINVAL, "pc_bn_act_bwd_apply: bad pool / argmax");
@@ -517,9 +553,9 @@ extern "C" int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int
   pool_out_dims(H, W, pool, &Ho, &Wo);
   const long long items = (long long)B * H * W * (C / 4);
   const int grid = ew_grid(items, 256 * 2);
-  if (pool == 0) bn_act_bwd_apply_kernel<0><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta);
-  else if (pool == 2) bn_act_bwd_apply_kernel<2><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta);
-  else bn_act_bwd_apply_kernel<3><<<grid, 256, 0, stream>>>(dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta);
+  if (pool == 0) launch_pdl((bn_act_bwd_apply_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax);
+  else if (pool == 2) launch_pdl((bn_act_bwd_apply_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax);
+  else launch_pdl((bn_act_bwd_apply_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax);
   PC_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return PC_OK;
 }
@@ -530,7 +566,7 @@ extern "C" int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const fl
   PC_REQUIRE(y2 && scale2 && shift2 && ysc && out && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_fwd: bad arguments");
   PC_REQUIRE((sc_scale == nullptr) == (sc_shift == nullptr), PC_EINVAL, "pc_bn_add_relu_fwd: shortcut scale/shift mismatch");
   PC_CHECK_C4("pc_bn_add_relu_fwd", C);
-  bn_add_relu_fwd_kernel<<<ew_grid(n_pix * (C / 4), 256), 256, 0, stream>>>(y2, scale2, shift2, ysc, sc_scale, sc_shift, n_pix, C, out);
+  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid(n_pix * (C / 4), 256)), dim3(256), 0, stream, y2, scale2, shift2, ysc, sc_scale, sc_shift, n_pix, C, out);
   PC_LAUNCH_CHECK("bn_add_relu_fwd_kernel");
   return PC_OK;
 }
@@ -542,7 +578,7 @@ extern "C" int pc_bn_add_relu_bwd_reduce(const float* dout, const float* out, co
   PC_REQUIRE(dout && out && y2 && mean2 && invstd2 && sums2 && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_bwd_reduce: bad arguments");
   PC_REQUIRE(sums_s == nullptr || (ysc && mean_s && invstd_s), PC_EINVAL, "pc_bn_add_relu_bwd_reduce: shortcut pointers");
   PC_CHECK_C4("pc_bn_add_relu_bwd_reduce", C);
-  bn_add_relu_bwd_reduce_kernel<<<reduce_grid(n_pix * (C / 4), 256 * 4), 256, 0, stream>>>(dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s);
+  launch_pdl(bn_add_relu_bwd_reduce_kernel, dim3(reduce_grid(n_pix * (C / 4), 256 * 4)), dim3(256), 0, stream, dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s);
   PC_LAUNCH_CHECK("bn_add_relu_bwd_reduce_kernel");
   return PC_OK;
 }
@@ -551,14 +587,14 @@ extern "C" int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, con
                                         const float* mean2, const float* invstd2, const double* sums2, const float* ysc,
                                         const float* sc_scale, const float* mean_s, const float* invstd_s,
                                         const double* sums_s, int64_t n_pix, int C, float* dy2, float* dysc_or_dx,
-                                        float* dgamma2, float* dbeta2, float* dgamma_s, float* dbeta_s, pc_stream_t stream) {
+                                        float* dgamma2, float* dbeta2, float* dgamma_s, float* dbeta_s, float* dy2_amax,
+                                        float* dysc_amax, pc_stream_t stream) {
   PC_REQUIRE(dout && out && y2 && scale2 && mean2 && invstd2 && sums2 && dy2 && dysc_or_dx && n_pix > 0, PC_EINVAL,
              "pc_bn_add_relu_bwd_apply: bad arguments");
   PC_REQUIRE(sc_scale == nullptr || (ysc && mean_s && invstd_s && sums_s), PC_EINVAL, "pc_bn_add_relu_bwd_apply: shortcut pointers");
   PC_CHECK_C4("pc_bn_add_relu_bwd_apply", C);
-  bn_add_relu_bwd_apply_kernel<<<ew_grid(n_pix * (C / 4), 256 * 2), 256, 0, stream>>>(
-      dout, out, y2, scale2, mean2, invstd2, sums2, ysc, sc_scale, mean_s, invstd_s, sums_s, n_pix, C, dy2, dysc_or_dx,
-      dgamma2, dbeta2, dgamma_s, dbeta_s);
+  launch_pdl(bn_add_relu_bwd_apply_kernel, dim3(ew_grid(n_pix * (C / 4), 256 * 2)), dim3(256), 0, stream, dout, out, y2, scale2, mean2, invstd2, sums2, ysc, sc_scale, mean_s, invstd_s, sums_s, n_pix, C, dy2, dysc_or_dx,
+      dgamma2, dbeta2, dgamma_s, dbeta_s, dy2_amax, dysc_amax);
   PC_LAUNCH_CHECK("bn_add_relu_bwd_apply_kernel");
   return PC_OK;
 }
@@ -567,7 +603,7 @@ extern "C" int pc_dropout2d_mask(float* drop, int B, int C, float p, uint64_t se
                                  pc_stream_t stream) {
   PC_REQUIRE(drop && B > 0 && C > 0 && p >= 0.f && p < 1.f, PC_EINVAL, "pc_dropout2d_mask: bad arguments (p=%f)", p);
   const int n = B * C;
-  dropout2d_mask_kernel<<<ceil_div(ceil_div(n, 4), 128), 128, 0, stream>>>(drop, n, p, 1.0f / (1.0f - p), seed, offset,
+  launch_pdl(dropout2d_mask_kernel, dim3(ceil_div(ceil_div(n, 4), 128)), dim3(128), 0, stream, drop, n, p, 1.0f / (1.0f - p), seed, offset,
                                                                             reinterpret_cast<const long long*>(step_dev));
   PC_LAUNCH_CHECK("dropout2d_mask_kernel");
   return PC_OK;

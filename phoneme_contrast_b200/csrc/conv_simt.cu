@@ -339,6 +339,8 @@ conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, PcC
 __global__ void __launch_bounds__(256)
 conv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int R, int S, int Cin, int Cout,
                          float* __restrict__ dw, float* __restrict__ db) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ double sh[8][32][4];
   const int K = R * S * Cin;
   const long long total = (long long)(K + 1) * Cout;      // floats per split; Cout % 4 == 0
@@ -388,6 +390,8 @@ template <int KS, int COUT>   // kernel size, output channels (16 | 32 | 64); la
 __global__ void __launch_bounds__(256)
 conv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w_oihw, const float* __restrict__ bias, int B,
                      int H, int W, float* __restrict__ y, double* __restrict__ stats) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int P = KS / 2, CPL = (COUT + 31) / 32;
   constexpr int TH = 8, TW = 32;   // output tile per CTA
   __shared__ float xs[TH + KS - 1][TW + KS - 1 + 1];
@@ -475,6 +479,8 @@ template <int KS, int COUT>
 __global__ void __launch_bounds__(256)
 conv_stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, int B, int H, int W,
                        float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int P = KS / 2, CPL = (COUT + 31) / 32, T = KS * KS;
   constexpr int TH = 8, TW = 32;
   __shared__ float xs[TH + KS - 1][TW + KS - 1 + 1];
@@ -555,7 +561,7 @@ conv_stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy
 
 void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream) {
   const long long total4 = ((long long)(R * S * Cin + 1) * Cout) >> 2;
-  conv_wgrad_reduce_kernel<<<ceil_div(total4, 32), 256, 0, stream>>>(partial, n_splits, R, S, Cin, Cout, dw, db);
+  launch_pdl(conv_wgrad_reduce_kernel, dim3(ceil_div(total4, 32)), dim3(256), 0, stream, partial, n_splits, R, S, Cin, Cout, dw, db);
   count_launch();
 }
 
@@ -612,7 +618,7 @@ extern "C" int pc_pack_conv_weight(const float* w_oihw, int O, int I, int R, int
 extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias, const PcConvGeom* g, const PcInXform* xf,
                               float* y, double* stats, int prec, pc_stream_t stream);
 extern "C" int pc_conv_dgrad_tc(const float* dy, const void* wp, const PcConvGeom* g, float* dx, int accumulate, int prec,
-                                pc_stream_t stream);
+                                const float* dy_amax, pc_stream_t stream);
 
 extern "C" int pc_conv_fwd(const float* x, const float* wf, const float* bias, const PcConvGeom* g, const PcInXform* xf,
                            float* y, double* stats, int prec, pc_stream_t stream) {
@@ -624,12 +630,12 @@ extern "C" int pc_conv_fwd(const float* x, const float* wf, const float* bias, c
     PC_REQUIRE(g->stride == 1 && g->R == g->S && g->pad == g->R / 2, PC_EUNSUPPORTED, "pc_conv_fwd: stem conv must be stride 1, 'same' padding");
     PC_REQUIRE(xf == nullptr || (xf->scale == nullptr && xf->drop == nullptr && !xf->relu), PC_EUNSUPPORTED, "pc_conv_fwd: stem conv takes no input transform");
     const int tiles = g->B * ceil_div(g->H, 8) * ceil_div(g->W, 32);
-    if (g->R == 3 && g->Cout == 16) conv_stem_fwd_kernel<3, 16><<<tiles, 256, 0, stream>>>(x, wf, bias, g->B, g->H, g->W, y, stats);
-    else if (g->R == 3 && g->Cout == 32) conv_stem_fwd_kernel<3, 32><<<tiles, 256, 0, stream>>>(x, wf, bias, g->B, g->H, g->W, y, stats);
-    else if (g->R == 3 && g->Cout == 64) conv_stem_fwd_kernel<3, 64><<<tiles, 256, 0, stream>>>(x, wf, bias, g->B, g->H, g->W, y, stats);
-    else if (g->R == 7 && g->Cout == 16) conv_stem_fwd_kernel<7, 16><<<tiles, 256, 0, stream>>>(x, wf, bias, g->B, g->H, g->W, y, stats);
-    else if (g->R == 7 && g->Cout == 32) conv_stem_fwd_kernel<7, 32><<<tiles, 256, 0, stream>>>(x, wf, bias, g->B, g->H, g->W, y, stats);
-    else if (g->R == 7 && g->Cout == 64) conv_stem_fwd_kernel<7, 64><<<tiles, 256, 0, stream>>>(x, wf, bias, g->B, g->H, g->W, y, stats);
+    if (g->R == 3 && g->Cout == 16) launch_pdl((conv_stem_fwd_kernel<3, 16>), dim3(tiles), dim3(256), 0, stream, x, wf, bias, g->B, g->H, g->W, y, stats);
+    else if (g->R == 3 && g->Cout == 32) launch_pdl((conv_stem_fwd_kernel<3, 32>), dim3(tiles), dim3(256), 0, stream, x, wf, bias, g->B, g->H, g->W, y, stats);
+    else if (g->R == 3 && g->Cout == 64) launch_pdl((conv_stem_fwd_kernel<3, 64>), dim3(tiles), dim3(256), 0, stream, x, wf, bias, g->B, g->H, g->W, y, stats);
+    else if (g->R == 7 && g->Cout == 16) launch_pdl((conv_stem_fwd_kernel<7, 16>), dim3(tiles), dim3(256), 0, stream, x, wf, bias, g->B, g->H, g->W, y, stats);
+    else if (g->R == 7 && g->Cout == 32) launch_pdl((conv_stem_fwd_kernel<7, 32>), dim3(tiles), dim3(256), 0, stream, x, wf, bias, g->B, g->H, g->W, y, stats);
+    else if (g->R == 7 && g->Cout == 64) launch_pdl((conv_stem_fwd_kernel<7, 64>), dim3(tiles), dim3(256), 0, stream, x, wf, bias, g->B, g->H, g->W, y, stats);
     else PC_REQUIRE(false, PC_EUNSUPPORTED, "pc_conv_fwd: stem conv k=%d Cout=%d not built (3|7 x 16|32|64)", g->R, g->Cout);
     PC_LAUNCH_CHECK("conv_stem_fwd_kernel");
     return PC_OK;
@@ -658,13 +664,13 @@ extern "C" int pc_conv_fwd(const float* x, const float* wf, const float* bias, c
 }
 
 extern "C" int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom* g, float* dx, int accumulate, int prec,
-                             pc_stream_t stream) {
+                             const float* dy_amax, pc_stream_t stream) {
   int rc = check_geom("pc_conv_dgrad", g);
   if (rc != PC_OK) return rc;
   PC_REQUIRE(dy && wd && dx, PC_EINVAL, "pc_conv_dgrad: null pointer");
   PC_REQUIRE(g->Cout % CG_BK == 0 && g->Cin % 4 == 0, PC_EUNSUPPORTED, "pc_conv_dgrad: Cout=%d must be a multiple of 16 and Cin=%d of 4", g->Cout, g->Cin);
   if (prec != PC_PREC_FP32) {
-    rc = pc_conv_dgrad_tc(dy, wd, g, dx, accumulate, prec, stream);
+    rc = pc_conv_dgrad_tc(dy, wd, g, dx, accumulate, prec, dy_amax, stream);
     PC_REQUIRE(rc != PC_EUNSUPPORTED, PC_EUNSUPPORTED, "pc_conv_dgrad: shape not covered by the tensor-core path (check pc_conv_tc_supported)");
     return rc;
   }
@@ -687,7 +693,7 @@ extern "C" int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom*
 extern "C" int pc_conv_wgrad_tc_supported(const PcConvGeom* g);
 extern "C" size_t pc_conv_wgrad_tc_workspace(const PcConvGeom* g);
 extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw, float* db,
-                                void* workspace, size_t workspace_bytes, pc_stream_t stream);
+                                void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream);
 
 static size_t wgrad_workspace_simt(const PcConvGeom* g);
 
@@ -709,7 +715,7 @@ static size_t wgrad_workspace_simt(const PcConvGeom* g) {
 }
 
 extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw,
-                             float* db, void* workspace, size_t workspace_bytes, int prec, pc_stream_t stream) {
+                             float* db, void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream) {
   int rc = check_geom("pc_conv_wgrad", g);
   if (rc != PC_OK) return rc;
   PC_REQUIRE(x && dy && dw_oihw && workspace, PC_EINVAL, "pc_conv_wgrad: null pointer");
@@ -717,18 +723,18 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
              pc_conv_wgrad_workspace(g));
   // tensor-core path (TF32x3) for eligible layers whenever a tensor-core precision is requested
   if (prec != PC_PREC_FP32 && g->Cin != 1 && pc_conv_wgrad_tc_supported(g))
-    return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, stream);
+    return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, stream);
   float* partial = static_cast<float*>(workspace);
   int n_partials;
   if (g->Cin == 1) {
     PC_REQUIRE(g->stride == 1 && g->R == g->S && g->pad == g->R / 2, PC_EUNSUPPORTED, "pc_conv_wgrad: stem conv must be stride 1, 'same' padding");
     const int tiles = stem_wgrad_ctas(g);
-    if (g->R == 3 && g->Cout == 16) conv_stem_wgrad_kernel<3, 16><<<tiles, 256, 0, stream>>>(x, dy, g->B, g->H, g->W, partial);
-    else if (g->R == 3 && g->Cout == 32) conv_stem_wgrad_kernel<3, 32><<<tiles, 256, 0, stream>>>(x, dy, g->B, g->H, g->W, partial);
-    else if (g->R == 3 && g->Cout == 64) conv_stem_wgrad_kernel<3, 64><<<tiles, 256, 0, stream>>>(x, dy, g->B, g->H, g->W, partial);
-    else if (g->R == 7 && g->Cout == 16) conv_stem_wgrad_kernel<7, 16><<<tiles, 256, 0, stream>>>(x, dy, g->B, g->H, g->W, partial);
-    else if (g->R == 7 && g->Cout == 32) conv_stem_wgrad_kernel<7, 32><<<tiles, 256, 0, stream>>>(x, dy, g->B, g->H, g->W, partial);
-    else if (g->R == 7 && g->Cout == 64) conv_stem_wgrad_kernel<7, 64><<<tiles, 256, 0, stream>>>(x, dy, g->B, g->H, g->W, partial);
+    if (g->R == 3 && g->Cout == 16) launch_pdl((conv_stem_wgrad_kernel<3, 16>), dim3(tiles), dim3(256), 0, stream, x, dy, g->B, g->H, g->W, partial);
+    else if (g->R == 3 && g->Cout == 32) launch_pdl((conv_stem_wgrad_kernel<3, 32>), dim3(tiles), dim3(256), 0, stream, x, dy, g->B, g->H, g->W, partial);
+    else if (g->R == 3 && g->Cout == 64) launch_pdl((conv_stem_wgrad_kernel<3, 64>), dim3(tiles), dim3(256), 0, stream, x, dy, g->B, g->H, g->W, partial);
+    else if (g->R == 7 && g->Cout == 16) launch_pdl((conv_stem_wgrad_kernel<7, 16>), dim3(tiles), dim3(256), 0, stream, x, dy, g->B, g->H, g->W, partial);
+    else if (g->R == 7 && g->Cout == 32) launch_pdl((conv_stem_wgrad_kernel<7, 32>), dim3(tiles), dim3(256), 0, stream, x, dy, g->B, g->H, g->W, partial);
+    else if (g->R == 7 && g->Cout == 64) launch_pdl((conv_stem_wgrad_kernel<7, 64>), dim3(tiles), dim3(256), 0, stream, x, dy, g->B, g->H, g->W, partial);
     else PC_REQUIRE(false, PC_EUNSUPPORTED, "pc_conv_wgrad: stem conv k=%d Cout=%d not built (3|7 x 16|32|64)", g->R, g->Cout);
     PC_LAUNCH_CHECK("conv_stem_wgrad_kernel");
     n_partials = tiles;
@@ -743,7 +749,7 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
   }
   const long long total4 = ((long long)(g->R * g->S * g->Cin + 1) * g->Cout) >> 2;
   int grid = ceil_div(total4, 32);
-  conv_wgrad_reduce_kernel<<<grid, 256, 0, stream>>>(partial, n_partials, g->R, g->S, g->Cin, g->Cout, dw_oihw, db);
+  launch_pdl(conv_wgrad_reduce_kernel, dim3(grid), dim3(256), 0, stream, partial, n_partials, g->R, g->S, g->Cin, g->Cout, dw_oihw, db);
   PC_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
   return PC_OK;
 }

@@ -18,7 +18,15 @@
 //   TF32X3  fp32 operands split as x = hi + lo (hi = top 19 bits, lo = x - hi exactly); three kind::tf32 MMAs
 //           per k-step (lo*hi, hi*lo, hi*hi) accumulate ~fp32-accurate products in the fp32 TMEM accumulator.
 //           This is the mode that keeps the 1e-4 parity bar ("fp32 parity on tensor cores").
+//   FP16X2  fp32 operands split as x = hi + lo * 2^-11 with hi, lo in fp16 (tc_common.cuh: split_f16x2): the same three
+//           products and the same ~22-bit operand precision as TF32X3, but kind::f16 MMAs run at twice the tf32 rate
+//           and every operand byte in shared memory carries twice the K extent (64 channels per 128-byte row). fp16's
+//           narrow exponent is handled by a power-of-two operand scale derived from the tensor's max magnitude
+//           (`a_amax`, used for the gradient operand of dgrad) and undone in the epilogue.
 //   BF16    operands rounded to bf16, one kind::f16 MMA per k-step (the 1e-2 tolerance mode).
+#include <stdlib.h>
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -48,6 +56,7 @@ struct Params {
   const float* A;
   const unsigned char* Bp;
   const float* bias;
+  const float* a_amax;   // FP16X2: device scalar max|A| -> power-of-two operand scale (null: scale 1)
   float* C;
   double* stats;
   XformDev xf;
@@ -55,6 +64,7 @@ struct Params {
   int mode;          // 0 conv fwd gather, 1 conv dgrad gather, 2 plain row-major A [M][lda]
   long long M;
   int Nn, Npad, Ca, n_kc, lda, accumulate, stages;
+  int aff_floats;    // 2 * Ca when the gather applies a per-channel affine (kept in shared memory), else 0
   long long* dbg;    // optional [gridDim.x*gridDim.y][16] clock64 stamps (diagnostics, see pc_tc_set_debug)
 };
 
@@ -70,6 +80,7 @@ template <int PREC> struct Prec;
 // the four partial sums in registers with round-to-nearest (measured: ~10x lower error than a single accumulator).
 template <> struct Prec<PC_PREC_TF32X3> { static constexpr int BKC = 32, PARTS = 2, NACC = 4; };
 template <> struct Prec<PC_PREC_BF16> { static constexpr int BKC = 64, PARTS = 1, NACC = 1; };
+template <> struct Prec<PC_PREC_FP16X2> { static constexpr int BKC = 64, PARTS = 2, NACC = 4; };
 
 template <int BN, int PREC>
 __host__ __device__ constexpr uint32_t stage_bytes() { return (uint32_t)Prec<PREC>::PARTS * (BM * 128 + BN * 128); }
@@ -89,7 +100,7 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
   return v[0];
 }
 
-template <int BN, int PREC, int NGROUPS, int MINB>
+template <int BN, int PREC, int NGROUPS, int MINB, bool PIPE>
 __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(const Params p) {
   constexpr int PROD_WARPS = 4 * NGROUPS;
   using P = Prec<PREC>;
@@ -112,8 +123,10 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
   int* s_off0 = reinterpret_cast<int*>(s_sq + BN);                                // [BM] per-row window-origin offset
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(s_off0 + BM);                    // [BM] per-row valid-tap bitmask
   int* s_pix = reinterpret_cast<int*>(s_mask + BM);                               // [BM] output row (pixel) index, -1 = none
-  int* s_nact = s_pix + BM;                                                       // [1] number of active k-chunks
-  unsigned short* s_kc = reinterpret_cast<unsigned short*>(s_nact + 1);           // [n_kc] active k-chunk indices
+  int* s_smp = s_pix + BM;                                                        // [BM] sample (batch) index of the row
+  int* s_nact = s_smp + BM;                                                       // [1] number of active k-chunks
+  float* s_aff = reinterpret_cast<float*>(s_nact + 4);                            // [2][Ca] fused BatchNorm scale | shift (aff_floats)
+  int4* s_kc = reinterpret_cast<int4*>(s_aff + p.aff_floats);                     // [n_kc] active k-chunks: {kc, tap, c_base, tap_off}
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) PC_STAMP(0);
@@ -122,7 +135,7 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
 
   if (tid < BN) {
     const int n = n0 + tid;
-    s_bias[tid] = (p.bias != nullptr && n < p.Nn) ? p.bias[n] : 0.f;
+    (void)n;
     s_sum[tid] = 0.f;
     s_sq[tid] = 0.f;
   }
@@ -197,6 +210,7 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
       }
     }
     s_pix[tid] = pix;
+    s_smp[tid] = pix >= 0 ? pix / (Hr * Wr) : 0;
     s_off0[tid] = off;
     s_mask[tid] = mask;
     asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -209,7 +223,15 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
         const int kc = base + lane;
         const bool act = kc < p.n_kc && ((tm >> (kc / cpt_)) & 1u);
         const uint32_t bal = __ballot_sync(0xffffffffu, act);
-        if (act) s_kc[n_act + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)kc;
+        if (act) {
+          // per-stage gather constants, computed once here instead of once per producer thread and stage
+          const int tap = kc / cpt_, tr = tap / p.g.S, ts = tap - tr * p.g.S;
+          const int Wa_ = p.mode == 0 ? p.g.W : p.g.Wo;
+          int tap_off = 0;
+          if (p.mode == 0) tap_off = (tr * Wa_ + ts) * p.Ca;
+          else if (p.mode == 1) tap_off = -((tr / p.g.stride) * Wa_ + ts / p.g.stride) * p.Ca;
+          s_kc[n_act + __popc(bal & ((1u << lane) - 1u))] = make_int4(kc, tap, (kc - tap * cpt_) * BKC, tap_off);
+        }
         n_act += __popc(bal);
       }
       if (lane == 0) s_nact[0] = n_act;
@@ -231,6 +253,19 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();   // TMEM is allocated: the next kernel on the stream may start its prologue behind us
+  pdl_wait();      // everything above used kernel parameters only; from here on we read the predecessor's output
+  if (tid < BN) {  // read by the epilogue warps after their "bar.sync 3" below
+    const int n = n0 + tid;
+    s_bias[tid] = (p.bias != nullptr && n < p.Nn) ? p.bias[n] : 0.f;
+  }
+  if (p.aff_floats != 0 && warp < PROD_WARPS) {
+    for (int c = tid; c < p.Ca; c += 32 * PROD_WARPS) {
+      s_aff[c] = p.xf.scale[c];
+      s_aff[p.Ca + c] = p.xf.shift[c];
+    }
+    asm volatile("bar.sync 4, %0;" ::"n"(32 * PROD_WARPS) : "memory");
+  }
   if (tid == 0) PC_STAMP(1);
 
   if (warp < PROD_WARPS) {
@@ -250,28 +285,34 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
       tapmask[i] = s_mask[rg + 16 * i];
     }
     const int cpt = p.Ca / BKC;     // k-chunks per tap
-    constexpr int EPC = (PREC == PC_PREC_BF16) ? 8 : 4;   // source elements per 16-byte destination chunk
+    constexpr int EPC = (PREC == PC_PREC_TF32X3) ? 4 : 8; // source elements per 16-byte destination chunk
+    const bool use_scale = (PREC == PC_PREC_FP16X2 && p.a_amax != nullptr);
+    const float a_scale = use_scale ? f16_operand_scale(p.a_amax[0]) : 1.f;
     const bool has_aff = (p.mode == 0 && p.xf.scale != nullptr);
     const bool has_relu = (p.mode == 0 && p.xf.relu);
     const bool has_drop = (p.mode == 0 && p.xf.drop != nullptr);
     const uint32_t soff0 = sw128_offset((uint32_t)rg, (uint32_t)j);     // rows rg + 16*i share (row & 7): + 2048*i
     if (tid == 0) PC_STAMP(2);
     const int n_act = s_nact[0];
-    for (int it = group; it < n_act; it += NGROUPS) {
-      const int kc = s_kc[it];
-      const int s = it % S;
-      const uint32_t ph = (uint32_t)(it / S) & 1u;
-      const int tap = kc / cpt;
-      const int c0 = (kc - tap * cpt) * BKC + j * EPC;      // first channel of my chunk
-      int tap_off;
-      if (p.mode == 0) { const int tr = tap / g.S; tap_off = (tr * Wa + (tap - tr * g.S)) * p.Ca; }
-      else if (p.mode == 1) { const int tr = tap / g.S; tap_off = -((tr / g.stride) * Wa + (tap - tr * g.S) / g.stride) * p.Ca; }
-      else tap_off = 0;
-      const float* src_base = p.A + tap_off + c0;
-      // issue this chunk's global loads before waiting for the smem slot
-      float v[8][EPC];
+    // Software pipeline inside a group: a thread's 8 rows are handled as two halves of 4. As soon as a half of stage `it` is
+    // converted and stored, the global loads of the same half for the group's NEXT stage (it + NGROUPS) are issued into the
+    // registers just freed, so the gather latency of the next stage overlaps the conversion of the other half, the wait for
+    // the smem slot and the MMA of this stage (otherwise load latency + conversion form one serial chain per group).
+    float v[8][EPC];
+    int tap = 0, c0 = 0, tap_off = 0;
+    const float* src_base = p.A;
+    auto setup = [&](int it_) {
+      const int4 st = s_kc[it_];
+      tap = st.y;
+      c0 = st.z + j * EPC;                        // first channel of my chunk
+      tap_off = st.w;
+      src_base = p.A + tap_off + c0;
+    };
+    auto load_half = [&](auto half) {
+      constexpr int H = decltype(half)::value;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int ii = 0; ii < 4; ++ii) {
+        const int i = 4 * H + ii;
         const bool ok = (tapmask[i] >> tap) & 1u;
 #pragma unroll
         for (int q = 0; q < EPC; q += 4) {
@@ -280,12 +321,29 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
           v[i][q] = t.x; v[i][q + 1] = t.y; v[i][q + 2] = t.z; v[i][q + 3] = t.w;
         }
       }
+    };
+    using Half0 = std::integral_constant<int, 0>;
+    using Half1 = std::integral_constant<int, 1>;
+    if (PIPE && group < n_act) {
+      setup(group);
+      load_half(Half0{});
+      load_half(Half1{});
+    }
+    for (int it = group; it < n_act; it += NGROUPS) {
+      const int s = it % S;
+      const uint32_t ph = (uint32_t)(it / S) & 1u;
+      if (!PIPE) {   // plain order: this stage's loads are issued here, ahead of the wait for the smem slot
+        setup(it);
+        load_half(Half0{});
+        load_half(Half1{});
+      }
+      const int cur_tap = tap, cur_c0 = c0;
       float sc[EPC], sh[EPC];
       if (has_aff) {
 #pragma unroll
         for (int q = 0; q < EPC; q += 4) {
-          const float4 a = *reinterpret_cast<const float4*>(p.xf.scale + c0 + q);
-          const float4 b = *reinterpret_cast<const float4*>(p.xf.shift + c0 + q);
+          const float4 a = *reinterpret_cast<const float4*>(s_aff + cur_c0 + q);
+          const float4 b = *reinterpret_cast<const float4*>(s_aff + p.Ca + cur_c0 + q);
           sc[q] = a.x; sc[q + 1] = a.y; sc[q + 2] = a.z; sc[q + 3] = a.w;
           sh[q] = b.x; sh[q + 1] = b.y; sh[q + 2] = b.z; sh[q + 3] = b.w;
         }
@@ -293,40 +351,64 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
       mbar_wait(&empty[s], ph ^ 1u);
       unsigned char* a_hi = tiles + (size_t)s * STAGE + soff0;
       unsigned char* a_lo = a_hi + A_PART;
+      auto convert_half = [&](auto half) {
+        constexpr int H = decltype(half)::value;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const bool ok = (tapmask[i] >> tap) & 1u;
-        if (ok) {
-          if (has_aff) {
+        for (int ii = 0; ii < 4; ++ii) {
+          const int i = 4 * H + ii;
+          const bool ok = (tapmask[i] >> cur_tap) & 1u;
+          if (ok) {
+            if (has_aff) {
 #pragma unroll
-            for (int q = 0; q < EPC; ++q) v[i][q] = fmaf(v[i][q], sc[q], sh[q]);
-          }
-          if (has_relu) {
+              for (int q = 0; q < EPC; ++q) v[i][q] = fmaf(v[i][q], sc[q], sh[q]);
+            }
+            if (has_relu) {
 #pragma unroll
-            for (int q = 0; q < EPC; ++q) v[i][q] = fmaxf(v[i][q], 0.f);
-          }
-          if (has_drop) {
-            const int b = (off0[i] + tap_off) / (Ha * Wa * p.Ca);   // sample index of the (valid, in-image) source pixel
+              for (int q = 0; q < EPC; ++q) v[i][q] = fmaxf(v[i][q], 0.f);
+            }
+            if (has_drop) {
+              const int b = s_smp[rg + 16 * i];                          // a valid tap reads the output pixel's own sample
 #pragma unroll
-            for (int q = 0; q < EPC; q += 4) {
-              const float4 d = *reinterpret_cast<const float4*>(p.xf.drop + (size_t)b * p.Ca + c0 + q);
-              v[i][q] *= d.x; v[i][q + 1] *= d.y; v[i][q + 2] *= d.z; v[i][q + 3] *= d.w;
+              for (int q = 0; q < EPC; q += 4) {
+                const float4 d = *reinterpret_cast<const float4*>(p.xf.drop + (size_t)b * p.Ca + cur_c0 + q);
+                v[i][q] *= d.x; v[i][q + 1] *= d.y; v[i][q + 2] *= d.z; v[i][q + 3] *= d.w;
+              }
             }
           }
-        }
-        if (PREC == PC_PREC_TF32X3) {
-          float h[4], l[4];
+          if (PREC == PC_PREC_TF32X3) {
+            float h[4], l[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) split_tf32(v[i][q], h[q], l[q]);
-          *reinterpret_cast<float4*>(a_hi + 2048 * i) = make_float4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<float4*>(a_lo + 2048 * i) = make_float4(l[0], l[1], l[2], l[3]);
-        } else {
-          uint4 w;
-          w.x = pack_bf16(v[i][0], v[i][1]); w.y = pack_bf16(v[i][2], v[i][3]);
-          w.z = pack_bf16(v[i][4 % EPC], v[i][5 % EPC]); w.w = pack_bf16(v[i][6 % EPC], v[i][7 % EPC]);
-          *reinterpret_cast<uint4*>(a_hi + 2048 * i) = w;
+            for (int q = 0; q < 4; ++q) split_tf32(v[i][q], h[q], l[q]);
+            *reinterpret_cast<float4*>(a_hi + 2048 * i) = make_float4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<float4*>(a_lo + 2048 * i) = make_float4(l[0], l[1], l[2], l[3]);
+          } else if (PREC == PC_PREC_FP16X2) {
+            uint4 h, l;
+            if (use_scale) {
+#pragma unroll
+              for (int q = 0; q < EPC; ++q) v[i][q] *= a_scale;
+            }
+            split_f16x2(v[i][0], v[i][1], h.x, l.x);
+            split_f16x2(v[i][2], v[i][3], h.y, l.y);
+            split_f16x2(v[i][4 % EPC], v[i][5 % EPC], h.z, l.z);
+            split_f16x2(v[i][6 % EPC], v[i][7 % EPC], h.w, l.w);
+            *reinterpret_cast<uint4*>(a_hi + 2048 * i) = h;
+            *reinterpret_cast<uint4*>(a_lo + 2048 * i) = l;
+          } else {
+            uint4 w;
+            w.x = pack_bf16(v[i][0], v[i][1]); w.y = pack_bf16(v[i][2], v[i][3]);
+            w.z = pack_bf16(v[i][4 % EPC], v[i][5 % EPC]); w.w = pack_bf16(v[i][6 % EPC], v[i][7 % EPC]);
+            *reinterpret_cast<uint4*>(a_hi + 2048 * i) = w;
+          }
         }
+      };
+      const bool more = PIPE && it + NGROUPS < n_act;
+      convert_half(Half0{});
+      if (more) {
+        setup(it + NGROUPS);
+        load_half(Half0{});
       }
+      convert_half(Half1{});
+      if (more) load_half(Half1{});
       fence_proxy_async();
       mbar_arrive(&full[s]);
       if (tid == 0 && it == 0) PC_STAMP(3);
@@ -336,9 +418,11 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
 
     // ============================================================ epilogue
     // warp w reads TMEM lanes 32*(w%4).. (its hardware lane quarter) = tile rows, and the 32-column chunks w/4, w/4+NGROUPS, ..
+    asm volatile("bar.sync 3, %0;" ::"n"(32 * PROD_WARPS) : "memory");     // s_bias visible to all epilogue warps
     mbar_wait(acc_full, 0);
     tc_fence_after();
     if (tid == 0) PC_STAMP(6);
+    const float out_scale = 1.f / a_scale;      // exact: a_scale is a power of two
     const int r = (warp & 3) * 32 + lane;
     const int pix = s_pix[r];
     const bool valid = pix >= 0;
@@ -357,19 +441,25 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
 #pragma unroll
         for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(raw[q]);
         if (NACC == 4) {
+          // accumulator sets [main0 | corr0 | main1 | corr1]: v = (main0 + main1) + corr_scale * (corr0 + corr1)
           float u[32];
-          tmem_ld_32x32(taddr + BN, raw);
+          tmem_ld_32x32(taddr + 2 * BN, raw);
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(raw[q]);
-          tmem_ld_32x32(taddr + 2 * BN, raw);
+          tmem_ld_32x32(taddr + BN, raw);
           tmem_ld_wait();
 #pragma unroll
           for (int q = 0; q < 32; ++q) u[q] = __uint_as_float(raw[q]);
           tmem_ld_32x32(taddr + 3 * BN, raw);
           tmem_ld_wait();
+          constexpr float corr_scale = (PREC == PC_PREC_FP16X2) ? kF16LoInv : 1.f;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] += u[q] + __uint_as_float(raw[q]);
+          for (int q = 0; q < 32; ++q) v[q] = fmaf(u[q] + __uint_as_float(raw[q]), corr_scale, v[q]);
+          if (PREC == PC_PREC_FP16X2 && p.a_amax != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] *= out_scale;
+          }
         }
       }
 #pragma unroll
@@ -411,8 +501,9 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
   } else if (warp == PROD_WARPS) {
     // ============================================================ MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = instr_desc(PREC == PC_PREC_BF16 ? 1u : 2u, BM, BN);
-      const uint32_t idesc2 = instr_desc(2u, BM, 2 * BN);
+      constexpr uint32_t FMT = PREC == PC_PREC_TF32X3 ? 2u : (PREC == PC_PREC_BF16 ? 1u : 0u);
+      const uint32_t idesc = instr_desc(FMT, BM, BN);
+      const uint32_t idesc2 = instr_desc(FMT, BM, 2 * BN);
       const int n_act = s_nact[0];
       for (int it = 0; it < n_act; ++it) {
         const int s = it % S;
@@ -438,6 +529,12 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
             const uint32_t d_set = tmem_base + (uint32_t)((ks & 1) * 2 * BN);
             mma_tf32(d_set, a_hi + adv, b_hi + adv, idesc2, ks < 2 ? 0u : 1u);
             mma_tf32(d_set + BN, a_lo + adv, b_hi + adv, idesc, 1u);
+          } else if (PREC == PC_PREC_FP16X2) {
+            // same scheme with kind::f16 (K = 16 per instruction, still 32 bytes per k-step); the correction half holds
+            // 2^11 x its value (split_f16x2) and is rescaled in the epilogue
+            const uint32_t d_set = tmem_base + (uint32_t)((ks & 1) * 2 * BN);
+            mma_bf16(d_set, a_hi + adv, b_hi + adv, idesc2, ks < 2 ? 0u : 1u);
+            mma_bf16(d_set + BN, a_lo + adv, b_hi + adv, idesc, 1u);
           } else {
             mma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, ks == 0 ? 0u : 1u);
           }
@@ -454,7 +551,7 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
       const size_t kc_stride = (size_t)PARTS * p.Npad * 128;
       const int n_act = s_nact[0];
       for (int it = 0; it < n_act; ++it) {
-        const int kc = s_kc[it];
+        const int kc = s_kc[it].x;
         const int s = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
@@ -485,9 +582,11 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
 template <int PREC>
 __global__ void pack_b_kernel(const float* __restrict__ src, int O, int I, int R, int S, int src_mode, int ld, int Nn, int Npad,
                               int Ca, unsigned char* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   using P = Prec<PREC>;
   constexpr int BKC = P::BKC, PARTS = P::PARTS;
-  constexpr int EPC = (PREC == PC_PREC_BF16) ? 8 : 4;
+  constexpr int EPC = (PREC == PC_PREC_TF32X3) ? 4 : 8;
   const int taps = src_mode == 2 ? 1 : R * S;
   const int cpt = Ca / BKC;
   const long long total = (long long)taps * cpt * Npad * 8;
@@ -515,6 +614,14 @@ __global__ void pack_b_kernel(const float* __restrict__ src, int O, int I, int R
       for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
       *reinterpret_cast<float4*>(base) = make_float4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<float4*>(base + (size_t)Npad * 128) = make_float4(l[0], l[1], l[2], l[3]);
+    } else if (PREC == PC_PREC_FP16X2) {
+      uint4 h, l;
+      split_f16x2(v[0], v[1], h.x, l.x);
+      split_f16x2(v[2], v[3], h.y, l.y);
+      split_f16x2(v[4 % EPC], v[5 % EPC], h.z, l.z);
+      split_f16x2(v[6 % EPC], v[7 % EPC], h.w, l.w);
+      *reinterpret_cast<uint4*>(base) = h;
+      *reinterpret_cast<uint4*>(base + (size_t)Npad * 128) = l;
     } else {
       uint4 w;
       w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
@@ -526,8 +633,21 @@ __global__ void pack_b_kernel(const float* __restrict__ src, int O, int I, int R
 
 static inline int pick_bn(int Nn) { return Nn <= 32 ? 32 : (Nn <= 64 ? 64 : 128); }
 static inline int npad_of(int Nn) { const int bn = pick_bn(Nn); return ceil_div(Nn, bn) * bn; }
-static inline int bkc_of(int prec) { return prec == PC_PREC_BF16 ? 64 : 32; }
+static inline int bkc_of(int prec) { return prec == PC_PREC_TF32X3 ? 32 : 64; }
 static inline int parts_of(int prec) { return prec == PC_PREC_BF16 ? 1 : 2; }
+static inline bool tc_prec(int prec) { return prec == PC_PREC_TF32X3 || prec == PC_PREC_BF16 || prec == PC_PREC_FP16X2; }
+
+template <int PREC>
+static void launch_pack(int grid, pc_stream_t stream, const float* src, int O, int I, int R, int S, int src_mode, int ld, int nn,
+                        int npad, int ca, void* out) {
+  launch_pdl((pack_b_kernel<PREC>), dim3(grid), dim3(256), 0, stream, src, O, I, R, S, src_mode, ld, nn, npad, ca, (unsigned char*)out);
+}
+static void launch_pack(int prec, int grid, pc_stream_t stream, const float* src, int O, int I, int R, int S, int src_mode, int ld,
+                        int nn, int npad, int ca, void* out) {
+  if (prec == PC_PREC_TF32X3) launch_pack<PC_PREC_TF32X3>(grid, stream, src, O, I, R, S, src_mode, ld, nn, npad, ca, out);
+  else if (prec == PC_PREC_FP16X2) launch_pack<PC_PREC_FP16X2>(grid, stream, src, O, I, R, S, src_mode, ld, nn, npad, ca, out);
+  else launch_pack<PC_PREC_BF16>(grid, stream, src, O, I, R, S, src_mode, ld, nn, npad, ca, out);
+}
 
 template <int BN, int PREC>
 static int launch(const Params& p0, pc_stream_t stream) {
@@ -541,14 +661,18 @@ static int launch(const Params& p0, pc_stream_t stream) {
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   if (stages > p.n_kc) stages = p.n_kc < 2 ? 2 : p.n_kc;
   p.stages = stages;
-  const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + sizeof(float) * 3 * BN + sizeof(int) * (3 * BM + 1) + sizeof(unsigned short) * (size_t)(p.n_kc + 2) + 1024;
+  p.aff_floats = (p.mode == 0 && p.xf.scale != nullptr) ? 2 * p.Ca : 0;
+  const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + sizeof(float) * 3 * BN + sizeof(int) * (4 * BM + 4) + sizeof(float) * (size_t)p.aff_floats + sizeof(int4) * (size_t)(p.n_kc + 1) + 1024;
   static size_t configured = 0;
   if (smem > configured) {
-    PC_CUDA(cudaFuncSetAttribute((igemm_tc_kernel<BN, PREC, NG, MINB>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute((igemm_tc_kernel<BN, PREC, NG, MINB, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PC_CUDA(cudaFuncSetAttribute((igemm_tc_kernel<BN, PREC, NG, MINB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   dim3 grid(ceil_div(p.M, BM), p.Npad / BN);
-  igemm_tc_kernel<BN, PREC, NG, MINB><<<grid, THREADS, smem, stream>>>(p);
+  static const bool pipe = [] { const char* e = getenv("PC_TC_PIPE"); return e && e[0] == '1'; }();
+  if (pipe) launch_pdl(igemm_tc_kernel<BN, PREC, NG, MINB, true>, dim3(grid), dim3(THREADS), smem, stream, p);
+  else launch_pdl(igemm_tc_kernel<BN, PREC, NG, MINB, false>, dim3(grid), dim3(THREADS), smem, stream, p);
   PC_LAUNCH_CHECK("igemm_tc_kernel");
   return PC_OK;
 }
@@ -563,6 +687,11 @@ static int dispatch(const Params& p_in, int prec, pc_stream_t stream) {
     if (bn == 32) return launch<32, PC_PREC_TF32X3>(p, stream);
     if (bn == 64) return launch<64, PC_PREC_TF32X3>(p, stream);
     return launch<128, PC_PREC_TF32X3>(p, stream);
+  }
+  if (prec == PC_PREC_FP16X2) {
+    if (bn == 32) return launch<32, PC_PREC_FP16X2>(p, stream);
+    if (bn == 64) return launch<64, PC_PREC_FP16X2>(p, stream);
+    return launch<128, PC_PREC_FP16X2>(p, stream);
   }
   if (bn == 32) return launch<32, PC_PREC_BF16>(p, stream);
   if (bn == 64) return launch<64, PC_PREC_BF16>(p, stream);
@@ -579,7 +708,7 @@ using namespace pc::tcconv;
 extern "C" void pc_tc_set_debug(long long* buf) { pc::tcconv::g_dbg = buf; }
 
 extern "C" int pc_conv_tc_supported(const PcConvGeom* g, int dgrad, int prec) {
-  if (g == nullptr || (prec != PC_PREC_TF32X3 && prec != PC_PREC_BF16)) return 0;
+  if (g == nullptr || !tc_prec(prec)) return 0;
   const int ca = dgrad ? g->Cout : g->Cin, nn = dgrad ? g->Cin : g->Cout;
   // 32-bit element offsets inside the kernel: the gathered tensor and the output must have fewer than 2^31 elements;
   // the tap bitmask holds at most 32 taps
@@ -596,17 +725,14 @@ extern "C" size_t pc_conv_tc_packed_bytes(int O, int I, int R, int S, int dgrad,
 extern "C" int pc_pack_conv_weight_tc(const float* w_oihw, int O, int I, int R, int S, int dgrad, int prec, void* out,
                                       pc_stream_t stream) {
   PC_REQUIRE(w_oihw && out && O > 0 && I > 0 && R > 0 && S > 0, PC_EINVAL, "pc_pack_conv_weight_tc: bad arguments");
-  PC_REQUIRE(prec == PC_PREC_TF32X3 || prec == PC_PREC_BF16, PC_EINVAL, "pc_pack_conv_weight_tc: precision must be TF32X3 or BF16");
+  PC_REQUIRE(tc_prec(prec), PC_EINVAL, "pc_pack_conv_weight_tc: precision must be TF32X3, FP16X2 or BF16");
   const int ca = dgrad ? O : I, nn = dgrad ? I : O;
   PC_REQUIRE(ca % bkc_of(prec) == 0, PC_EUNSUPPORTED, "pc_pack_conv_weight_tc: %d channels not a multiple of %d", ca, bkc_of(prec));
   const int npad = npad_of(nn);
   const long long total = (long long)R * S * (ca / bkc_of(prec)) * npad * 8;
   int grid = ceil_div(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  if (prec == PC_PREC_TF32X3)
-    pack_b_kernel<PC_PREC_TF32X3><<<grid, 256, 0, stream>>>(w_oihw, O, I, R, S, dgrad ? 1 : 0, 0, nn, npad, ca, (unsigned char*)out);
-  else
-    pack_b_kernel<PC_PREC_BF16><<<grid, 256, 0, stream>>>(w_oihw, O, I, R, S, dgrad ? 1 : 0, 0, nn, npad, ca, (unsigned char*)out);
+  launch_pack(prec, grid, stream, w_oihw, O, I, R, S, dgrad ? 1 : 0, 0, nn, npad, ca, out);
   PC_LAUNCH_CHECK("pack_b_kernel");
   return PC_OK;
 }
@@ -626,10 +752,10 @@ extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias,
 }
 
 extern "C" int pc_conv_dgrad_tc(const float* dy, const void* wp, const PcConvGeom* g, float* dx, int accumulate, int prec,
-                                pc_stream_t stream) {
+                                const float* dy_amax, pc_stream_t stream) {
   if (!pc_conv_tc_supported(g, 1, prec)) return PC_EUNSUPPORTED;
   Params p{};
-  p.A = dy; p.Bp = (const unsigned char*)wp; p.C = dx;
+  p.A = dy; p.Bp = (const unsigned char*)wp; p.C = dx; p.a_amax = dy_amax;
   p.g = *g; p.mode = 1;
   p.M = (long long)g->B * g->H * g->W;
   p.Nn = g->Cin; p.Npad = npad_of(g->Cin); p.Ca = g->Cout;
@@ -646,7 +772,7 @@ extern "C" size_t pc_tc_gemm_workspace(int N, int K, int prec) {
 extern "C" int pc_tc_gemm(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, int prec, void* ws,
                           size_t ws_bytes, pc_stream_t stream) {
   PC_REQUIRE(A && B && C && ws && M > 0 && N > 0 && K > 0, PC_EINVAL, "pc_tc_gemm: bad arguments");
-  PC_REQUIRE(prec == PC_PREC_TF32X3 || prec == PC_PREC_BF16, PC_EINVAL, "pc_tc_gemm: precision must be TF32X3 or BF16");
+  PC_REQUIRE(tc_prec(prec), PC_EINVAL, "pc_tc_gemm: precision must be TF32X3, FP16X2 or BF16");
   PC_REQUIRE(K % bkc_of(prec) == 0 && N % 4 == 0 && N >= 16, PC_EUNSUPPORTED, "pc_tc_gemm: K=%d must be a multiple of %d, N=%d of 4", K,
              bkc_of(prec), N);
   PC_REQUIRE(ws_bytes >= pc_tc_gemm_workspace(N, K, prec), PC_EINVAL, "pc_tc_gemm: workspace too small");
@@ -654,10 +780,7 @@ extern "C" int pc_tc_gemm(const float* A, const float* B, const float* bias, flo
   const long long total = (long long)(K / bkc_of(prec)) * npad * 8;
   int grid = ceil_div(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
-  if (prec == PC_PREC_TF32X3)
-    pack_b_kernel<PC_PREC_TF32X3><<<grid, 256, 0, stream>>>(B, 0, 0, 1, 1, 2, K, N, npad, K, (unsigned char*)ws);
-  else
-    pack_b_kernel<PC_PREC_BF16><<<grid, 256, 0, stream>>>(B, 0, 0, 1, 1, 2, K, N, npad, K, (unsigned char*)ws);
+  launch_pack(prec, grid, stream, B, 0, 0, 1, 1, 2, K, N, npad, K, ws);
   PC_LAUNCH_CHECK("pack_b_kernel");
   Params p{};
   p.A = A; p.Bp = (const unsigned char*)ws; p.bias = bias; p.C = C;

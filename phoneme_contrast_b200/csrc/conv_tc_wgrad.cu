@@ -11,6 +11,13 @@
 // A 128-row M tile is a run of 128 consecutive (tap, channel) indices, so for Cin = 64 it covers two taps and the
 // producers gather two different input pixels per output pixel.
 //
+// FP16X2 variant (F16 = true): operands split into fp16 hi / lo*2^11 (tc_common.cuh: split_f16x2), kind::f16 MMAs with
+// K = 16 pixels per instruction. 16-bit MN-major operands use the ordinary SWIZZLE_128B layout: atoms of 8 pixel rows x
+// 128 B (64 channels), 16-byte chunk index XOR (row & 7); tiles are [channel group of 64][32 pixels][128 B] with
+// LBO = 4096 B (next channel group) and SBO = 1024 B (next 8 pixels). A stage still holds 32 pixels (now 2 k-steps) in
+// half the bytes, dy is pre-scaled by a power of two from its max magnitude (dy_amax) and the scale is undone in the
+// epilogue.
+//
 // grid = (ceil(K/128), ceil(Cout/BN), splits over pixels); each CTA writes its partial tile to
 // partial[split][K+1][Cout] and conv_wgrad_reduce_kernel (conv_simt.cu) sums the splits in a fixed order into OIHW.
 #include "common.cuh"
@@ -42,6 +49,7 @@ struct Params {
   XformDev xf;
   PcConvGeom g;
   int K, M, rows_per_split, stages;
+  const float* dy_amax;   // FP16X2: device scalar max|dy| (null: scale 1)
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr_bytes) {
@@ -54,14 +62,29 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr_bytes)
   return d;
 }
 
-template <int BN>
-__host__ __device__ constexpr uint32_t stage_bytes() { return 2u * (4u * 4096u + (BN / 32) * 4096u); }
+// 16-bit MN-major operand, SWIZZLE_128B: 8-row x 128-byte atoms
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_h(uint32_t smem_addr_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr_bytes >> 4) & 0x3FFF);
+  d |= (uint64_t)(4096 >> 4) << 16;      // LBO: next 64-channel group
+  d |= (uint64_t)(1024 >> 4) << 32;      // SBO: next 8-pixel group
+  d |= (uint64_t)1 << 46;                // version
+  d |= (uint64_t)2 << 61;                // SWIZZLE_128B
+  return d;
+}
 
-template <int BN, int NGROUPS, int MINB>
+// channels per 128-byte row: 32 (tf32) or 64 (fp16); a 128-row M tile is 128 / CPG channel groups
+template <int BN, bool F16>
+__host__ __device__ constexpr uint32_t stage_bytes() { return 2u * ((F16 ? 2u : 4u) * 4096u + (BN / (F16 ? 64 : 32)) * 4096u); }
+
+template <int BN, int NGROUPS, int MINB, bool F16>
 __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(const Params p) {
   constexpr int PROD_WARPS = 4 * NGROUPS;
-  constexpr uint32_t A_PART = 4 * 4096, B_PART = (BN / 32) * 4096;
-  constexpr uint32_t STAGE = stage_bytes<BN>();
+  constexpr int CPG = F16 ? 64 : 32;          // channels per 128-byte row (one channel group)
+  constexpr int GA = 128 / CPG, GB = BN / CPG; // channel groups of the A' (M) and B' (N) tiles
+  constexpr int NV = F16 ? 2 : 1;             // float4 loads per thread, row and group (8 or 4 channels -> one 16-byte chunk)
+  constexpr uint32_t A_PART = GA * 4096, B_PART = GB * 4096;
+  constexpr uint32_t STAGE = stage_bytes<BN, F16>();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = p.stages;
@@ -94,38 +117,44 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_trigger();   // see common.cuh: only after the TMEM allocation
+  pdl_wait();      // nothing above touched global memory
 
   if (warp < PROD_WARPS) {
     const int group = warp >> 2;
     const int gt = tid & (NPROD - 1);
     const int j = gt & 7, pr = gt >> 3;       // 16-byte chunk, pixel row pr (+16)
-    // the four 32-channel groups of this M tile: (tap, first channel)
-    int q_tr[4], q_ts[4], q_c0[4];
-    bool q_ok[4];
+    // the channel groups of this M tile: (tap, first channel of my 16-byte chunk)
+    int q_tr[GA], q_ts[GA], q_c0[GA];
+    bool q_ok[GA];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int kidx0 = 128 * kt + 32 * q;
+    for (int q = 0; q < GA; ++q) {
+      const int kidx0 = 128 * kt + CPG * q;
       q_ok[q] = kidx0 < p.K;
       const int tap = q_ok[q] ? kidx0 / g.Cin : 0;
-      q_c0[q] = (q_ok[q] ? kidx0 - tap * g.Cin : 0) + 4 * j;
+      q_c0[q] = (q_ok[q] ? kidx0 - tap * g.Cin : 0) + 4 * NV * j;
       q_tr[q] = tap / g.S;
       q_ts[q] = tap - q_tr[q] * g.S;
     }
     const bool has_aff = p.xf.scale != nullptr, has_relu = p.xf.relu != 0, has_drop = p.xf.drop != nullptr;
-    float4 q_sc[4], q_sh[4];
+    float4 q_sc[GA][NV], q_sh[GA][NV];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      q_sc[q] = make_float4(1.f, 1.f, 1.f, 1.f);
-      q_sh[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has_aff && q_ok[q]) {
-        q_sc[q] = *reinterpret_cast<const float4*>(p.xf.scale + q_c0[q]);
-        q_sh[q] = *reinterpret_cast<const float4*>(p.xf.shift + q_c0[q]);
+    for (int q = 0; q < GA; ++q)
+#pragma unroll
+      for (int vv = 0; vv < NV; ++vv) {
+        q_sc[q][vv] = make_float4(1.f, 1.f, 1.f, 1.f);
+        q_sh[q][vv] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_aff && q_ok[q]) {
+          q_sc[q][vv] = *reinterpret_cast<const float4*>(p.xf.scale + q_c0[q] + 4 * vv);
+          q_sh[q][vv] = *reinterpret_cast<const float4*>(p.xf.shift + q_c0[q] + 4 * vv);
+        }
       }
-    }
+    const bool use_scale = F16 && p.dy_amax != nullptr;
+    const float b_scale = use_scale ? f16_operand_scale(p.dy_amax[0]) : 1.f;
     for (int st = group; st < n_stages; st += NGROUPS) {
       const int s = st % S;
       const uint32_t ph = (uint32_t)(st / S) & 1u;
-      float4 av[2][4], bv[2][BN / 32];
+      float4 av[2][GA][NV], bv[2][GB][NV];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int pl = pr + 16 * h;
@@ -139,25 +168,30 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
           b = t / g.Ho;
         }
 #pragma unroll
-        for (int q = 0; q < BN / 32; ++q) {
-          const int n = n0 + 32 * q + 4 * j;
-          bv[h][q] = (mv && n < g.Cout) ? *reinterpret_cast<const float4*>(p.dy + (size_t)m * g.Cout + n) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int q = 0; q < GB; ++q)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+          for (int vv = 0; vv < NV; ++vv) {
+            const int n = n0 + CPG * q + 4 * NV * j + 4 * vv;
+            bv[h][q][vv] = (mv && n < g.Cout) ? *reinterpret_cast<const float4*>(p.dy + (size_t)m * g.Cout + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+        for (int q = 0; q < GA; ++q) {
           const int hi = ho * g.stride - g.pad + q_tr[q], wi = wo * g.stride - g.pad + q_ts[q];
           const bool ok = mv && q_ok[q] && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok) {
-            v = *reinterpret_cast<const float4*>(p.x + (((size_t)b * g.H + hi) * g.W + wi) * g.Cin + q_c0[q]);
-            if (has_aff) v = make_float4(fmaf(v.x, q_sc[q].x, q_sh[q].x), fmaf(v.y, q_sc[q].y, q_sh[q].y), fmaf(v.z, q_sc[q].z, q_sh[q].z), fmaf(v.w, q_sc[q].w, q_sh[q].w));
-            if (has_relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
-            if (has_drop) {
-              const float4 d = *reinterpret_cast<const float4*>(p.xf.drop + (size_t)b * g.Cin + q_c0[q]);
-              v = make_float4(v.x * d.x, v.y * d.y, v.z * d.z, v.w * d.w);
+#pragma unroll
+          for (int vv = 0; vv < NV; ++vv) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok) {
+              v = *reinterpret_cast<const float4*>(p.x + (((size_t)b * g.H + hi) * g.W + wi) * g.Cin + q_c0[q] + 4 * vv);
+              if (has_aff) v = make_float4(fmaf(v.x, q_sc[q][vv].x, q_sh[q][vv].x), fmaf(v.y, q_sc[q][vv].y, q_sh[q][vv].y), fmaf(v.z, q_sc[q][vv].z, q_sh[q][vv].z), fmaf(v.w, q_sc[q][vv].w, q_sh[q][vv].w));
+              if (has_relu) v = make_float4(fmaxf(v.x, 0.f), fmaxf(v.y, 0.f), fmaxf(v.z, 0.f), fmaxf(v.w, 0.f));
+              if (has_drop) {
+                const float4 d = *reinterpret_cast<const float4*>(p.xf.drop + (size_t)b * g.Cin + q_c0[q] + 4 * vv);
+                v = make_float4(v.x * d.x, v.y * d.y, v.z * d.z, v.w * d.w);
+              }
             }
+            av[h][q][vv] = v;
           }
-          av[h][q] = v;
         }
       }
       mbar_wait(&empty[s], ph ^ 1u);
@@ -168,23 +202,49 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int pl = pr + 16 * h;
-        // atom = 4 pixel rows x 128 B; 32-byte chunk index XOR (row & 3)  (Swizzle<2,5,2> on the byte address)
-        const uint32_t off = (uint32_t)((pl >> 2) * 512 + (pl & 3) * 128 + ((((j >> 1) ^ (pl & 3)) << 5) | ((j & 1) << 4)));
+        if (F16) {
+          // atom = 8 pixel rows x 128 B; 16-byte chunk index XOR (row & 7)
+          const uint32_t off = (uint32_t)((pl >> 3) * 1024 + (pl & 7) * 128 + ((j ^ (pl & 7)) << 4));
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float hh[4], ll[4];
-          split_tf32(av[h][q].x, hh[0], ll[0]); split_tf32(av[h][q].y, hh[1], ll[1]);
-          split_tf32(av[h][q].z, hh[2], ll[2]); split_tf32(av[h][q].w, hh[3], ll[3]);
-          *reinterpret_cast<float4*>(a_hi + q * 4096 + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-          *reinterpret_cast<float4*>(a_lo + q * 4096 + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
-        }
+          for (int q = 0; q < GA; ++q) {
+            uint4 hh, ll;
+            split_f16x2(av[h][q][0].x, av[h][q][0].y, hh.x, ll.x); split_f16x2(av[h][q][0].z, av[h][q][0].w, hh.y, ll.y);
+            split_f16x2(av[h][q][NV - 1].x, av[h][q][NV - 1].y, hh.z, ll.z); split_f16x2(av[h][q][NV - 1].z, av[h][q][NV - 1].w, hh.w, ll.w);
+            *reinterpret_cast<uint4*>(a_hi + q * 4096 + off) = hh;
+            *reinterpret_cast<uint4*>(a_lo + q * 4096 + off) = ll;
+          }
 #pragma unroll
-        for (int q = 0; q < BN / 32; ++q) {
-          float hh[4], ll[4];
-          split_tf32(bv[h][q].x, hh[0], ll[0]); split_tf32(bv[h][q].y, hh[1], ll[1]);
-          split_tf32(bv[h][q].z, hh[2], ll[2]); split_tf32(bv[h][q].w, hh[3], ll[3]);
-          *reinterpret_cast<float4*>(b_hi + q * 4096 + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-          *reinterpret_cast<float4*>(b_lo + q * 4096 + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+          for (int q = 0; q < GB; ++q) {
+            float4 b0 = bv[h][q][0], b1 = bv[h][q][NV - 1];
+            if (use_scale) {
+              b0 = make_float4(b0.x * b_scale, b0.y * b_scale, b0.z * b_scale, b0.w * b_scale);
+              b1 = make_float4(b1.x * b_scale, b1.y * b_scale, b1.z * b_scale, b1.w * b_scale);
+            }
+            uint4 hh, ll;
+            split_f16x2(b0.x, b0.y, hh.x, ll.x); split_f16x2(b0.z, b0.w, hh.y, ll.y);
+            split_f16x2(b1.x, b1.y, hh.z, ll.z); split_f16x2(b1.z, b1.w, hh.w, ll.w);
+            *reinterpret_cast<uint4*>(b_hi + q * 4096 + off) = hh;
+            *reinterpret_cast<uint4*>(b_lo + q * 4096 + off) = ll;
+          }
+        } else {
+          // atom = 4 pixel rows x 128 B; 32-byte chunk index XOR (row & 3)  (Swizzle<2,5,2> on the byte address)
+          const uint32_t off = (uint32_t)((pl >> 2) * 512 + (pl & 3) * 128 + ((((j >> 1) ^ (pl & 3)) << 5) | ((j & 1) << 4)));
+#pragma unroll
+          for (int q = 0; q < GA; ++q) {
+            float hh[4], ll[4];
+            split_tf32(av[h][q][0].x, hh[0], ll[0]); split_tf32(av[h][q][0].y, hh[1], ll[1]);
+            split_tf32(av[h][q][0].z, hh[2], ll[2]); split_tf32(av[h][q][0].w, hh[3], ll[3]);
+            *reinterpret_cast<float4*>(a_hi + q * 4096 + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<float4*>(a_lo + q * 4096 + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+          }
+#pragma unroll
+          for (int q = 0; q < GB; ++q) {
+            float hh[4], ll[4];
+            split_tf32(bv[h][q][0].x, hh[0], ll[0]); split_tf32(bv[h][q][0].y, hh[1], ll[1]);
+            split_tf32(bv[h][q][0].z, hh[2], ll[2]); split_tf32(bv[h][q][0].w, hh[3], ll[3]);
+            *reinterpret_cast<float4*>(b_hi + q * 4096 + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<float4*>(b_lo + q * 4096 + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+          }
         }
       }
       fence_proxy_async();
@@ -206,19 +266,26 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(raw[q]);
-      tmem_ld_32x32(taddr + BN, raw);
+      // accumulator sets [main0 | corr0 | main1 | corr1]
+      tmem_ld_32x32(taddr + 2 * BN, raw);
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(raw[q]);
       float u[32];
-      tmem_ld_32x32(taddr + 2 * BN, raw);
+      tmem_ld_32x32(taddr + BN, raw);
       tmem_ld_wait();
 #pragma unroll
       for (int q = 0; q < 32; ++q) u[q] = __uint_as_float(raw[q]);
       tmem_ld_32x32(taddr + 3 * BN, raw);
       tmem_ld_wait();
+      constexpr float corr_scale = F16 ? kF16LoInv : 1.f;
 #pragma unroll
-      for (int q = 0; q < 32; ++q) v[q] += u[q] + __uint_as_float(raw[q]);
+      for (int q = 0; q < 32; ++q) v[q] = fmaf(u[q] + __uint_as_float(raw[q]), corr_scale, v[q]);
+      if (use_scale) {
+        const float inv = 1.f / b_scale;
+#pragma unroll
+        for (int q = 0; q < 32; ++q) v[q] *= inv;
+      }
       if (kidx < p.K) {
 #pragma unroll
         for (int q = 0; q < 32; q += 4)
@@ -229,28 +296,33 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
     // ---- MMA issuer
     if (lane == 0) {
       // kind::tf32, D fp32, A and B MN-major (bits 15, 16), N = BN, M = 128
-      const uint32_t idesc = instr_desc(2u, 128, BN) | (1u << 15) | (1u << 16);
-      const uint32_t idesc2 = instr_desc(2u, 128, 2 * BN) | (1u << 15) | (1u << 16);
-      if (n_stages == 0) {
-        // nothing to reduce in this split (cannot happen with the host's split choice, kept for safety)
-      }
+      constexpr uint32_t FMT = F16 ? 0u : 2u;
+      const uint32_t idesc = instr_desc(FMT, 128, BN) | (1u << 15) | (1u << 16);
+      const uint32_t idesc2 = instr_desc(FMT, 128, 2 * BN) | (1u << 15) | (1u << 16);
+      constexpr int KSTEPS = F16 ? 2 : 4;     // per 32-pixel stage: 16 (fp16) or 8 (tf32) pixels per MMA
       for (int st = 0; st < n_stages; ++st) {
         const int s = st % S;
         const uint32_t ph = (uint32_t)(st / S) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t base = smem_u32(tiles + (size_t)s * STAGE);
-        const uint64_t a_hi = smem_desc_mn_sw128(base), a_lo = smem_desc_mn_sw128(base + A_PART);
-        const uint64_t b_hi = smem_desc_mn_sw128(base + 2 * A_PART), b_lo = smem_desc_mn_sw128(base + 2 * A_PART + B_PART);
+        const uint64_t a_hi = F16 ? smem_desc_mn_sw128_h(base) : smem_desc_mn_sw128(base);
+        const uint64_t a_lo = F16 ? smem_desc_mn_sw128_h(base + A_PART) : smem_desc_mn_sw128(base + A_PART);
+        const uint64_t b_hi = F16 ? smem_desc_mn_sw128_h(base + 2 * A_PART) : smem_desc_mn_sw128(base + 2 * A_PART);
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          const uint64_t adv = (uint64_t)(kk * (1024 >> 4));   // next 8-pixel group
-          const int ks = st * 4 + kk;
+        for (int kk = 0; kk < KSTEPS; ++kk) {
+          const uint64_t adv = (uint64_t)(kk * ((F16 ? 2048 : 1024) >> 4));   // next pixel group of one MMA
+          const int ks = st * KSTEPS + kk;
           // one N = 2*BN MMA forms a_hi*[b_hi; b_lo] (main | correction), a second adds a_lo*b_hi to the correction half;
           // two accumulator sets alternate per k-step (same scheme as conv_tc.cu)
           const uint32_t d_set = tmem_base + (uint32_t)((ks & 1) * 2 * BN);
-          mma_tf32(d_set, a_hi + adv, b_hi + adv, idesc2, ks < 2 ? 0u : 1u);
-          mma_tf32(d_set + BN, a_lo + adv, b_hi + adv, idesc, 1u);
+          if (F16) {
+            mma_bf16(d_set, a_hi + adv, b_hi + adv, idesc2, ks < 2 ? 0u : 1u);
+            mma_bf16(d_set + BN, a_lo + adv, b_hi + adv, idesc, 1u);
+          } else {
+            mma_tf32(d_set, a_hi + adv, b_hi + adv, idesc2, ks < 2 ? 0u : 1u);
+            mma_tf32(d_set + BN, a_lo + adv, b_hi + adv, idesc, 1u);
+          }
         }
         mma_commit(&empty[s]);
       }
@@ -266,6 +338,8 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
 
 // bias gradient: db[n] = sum_m dy[m][n] -> written into partial[0][K][n]; other splits' bias rows are zeroed
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ dy, int M, int C, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float sh[256 * 4];
   const int C4 = C >> 2, c4 = threadIdx.x % C4, ppb = 256 / C4;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -333,7 +407,7 @@ extern "C" size_t pc_conv_wgrad_tc_workspace(const PcConvGeom* g) {
 }
 
 extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw, float* db,
-                                void* workspace, size_t workspace_bytes, pc_stream_t stream) {
+                                void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream) {
   PC_REQUIRE(x && dy && g && dw_oihw && workspace, PC_EINVAL, "pc_conv_wgrad_tc: null pointer");
   PC_REQUIRE(pc_conv_wgrad_tc_supported(g), PC_EUNSUPPORTED, "pc_conv_wgrad_tc: shape not covered (Cin %% 32, Cout %% 4)");
   PC_REQUIRE(workspace_bytes >= pc_conv_wgrad_tc_workspace(g), PC_EINVAL, "pc_conv_wgrad_tc: workspace too small");
@@ -346,29 +420,38 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
   p.K = g->R * g->S * g->Cin;
   p.M = g->B * g->Ho * g->Wo;
   p.rows_per_split = rps;
-  const uint32_t st = bn == 64 ? stage_bytes<64>() : stage_bytes<128>();
+  const bool f16 = prec == PC_PREC_FP16X2 && g->Cin % 64 == 0;   // 64-channel groups; otherwise the TF32x3 tiles
+  p.dy_amax = f16 ? dy_amax : nullptr;
+  const uint32_t st = bn == 64 ? (f16 ? stage_bytes<64, true>() : stage_bytes<64, false>())
+                               : (f16 ? stage_bytes<128, true>() : stage_bytes<128, false>());
   int stages = (int)(SMEM_BUDGET / st);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   p.stages = stages;
   const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + 1024;
   dim3 grid(ceil_div(p.K, 128), ceil_div(g->Cout, bn), sp);
+  // (two co-resident CTAs per SM were tried here as in conv_tc.cu: the register cap made the two-operand gather spill and
+  //  the kernel got slower, so the weight gradient keeps one CTA per SM)
+#define PC_WG_LAUNCH(BN_, F16_)                                                                                              \
+  do {                                                                                                                     \
+    static size_t conf = 0;                                                                                                \
+    if (smem > conf) {                                                                                                     \
+      PC_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<BN_, 3, 1, F16_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      conf = smem;                                                                                                         \
+    }                                                                                                                      \
+    launch_pdl(wgrad_tc_kernel<BN_, 3, 1, F16_>, grid, dim3(32 * 13), smem, stream, p);                                    \
+  } while (0)
   if (bn == 64) {
-    static size_t conf = 0;
-    // (two co-resident CTAs per SM were tried here as in conv_tc.cu: the register cap made the two-operand gather spill and
-    //  the kernel got slower, so the weight gradient keeps one CTA per SM)
-    if (smem > conf) { PC_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<64, 3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; }
-    wgrad_tc_kernel<64, 3, 1><<<grid, 32 * 13, smem, stream>>>(p);
+    if (f16) PC_WG_LAUNCH(64, true); else PC_WG_LAUNCH(64, false);
   } else {
-    static size_t conf = 0;
-    if (smem > conf) { PC_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<128, 3, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); conf = smem; }
-    wgrad_tc_kernel<128, 3, 1><<<grid, 32 * 13, smem, stream>>>(p);
+    if (f16) PC_WG_LAUNCH(128, true); else PC_WG_LAUNCH(128, false);
   }
+#undef PC_WG_LAUNCH
   PC_LAUNCH_CHECK("wgrad_tc_kernel");
   // bias gradient: per-CTA column sums of dy -> bias rows of the partial buffer (one row per colsum CTA, appended after the
   // split partials), then the common reduce
   float* cs = p.partial + (size_t)sp * (size_t)(p.K + 1) * g->Cout;
   const int cs_ctas = kNumSMs * 2;
-  colsum_kernel<<<cs_ctas, 256, 0, stream>>>(dy, p.M, g->Cout, cs);
+  launch_pdl(colsum_kernel, dim3(cs_ctas), dim3(256), 0, stream, dy, p.M, g->Cout, cs);
   PC_LAUNCH_CHECK("colsum_kernel");
   launch_wgrad_reduce(p.partial, sp, g->R, g->S, g->Cin, g->Cout, dw_oihw, nullptr, stream);
   launch_wgrad_reduce(cs, cs_ctas, 0, 0, 0, g->Cout, nullptr, db, stream);

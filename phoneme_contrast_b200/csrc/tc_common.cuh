@@ -3,6 +3,7 @@
 // Encodings follow the PTX ISA for sm_100a (cf. the descriptor bit-fields documented in CUTLASS's
 // cute/arch/mma_sm100_desc.hpp); everything here is inline PTX -- no CUTLASS code is compiled in.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -90,7 +91,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr_bytes) {
   return d;
 }
 // kind::f16 / kind::tf32 instruction descriptor: D = fp32, A/B K-major, dense.
-// fmt: 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
+// fmt: 0 = F16 (kind::f16), 1 = BF16 (kind::f16), 2 = TF32 (kind::tf32)
 __device__ __forceinline__ uint32_t instr_desc(uint32_t fmt, uint32_t M, uint32_t N) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
@@ -130,6 +131,29 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {   // a -> low 
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
   return r;
+}
+
+
+// FP16X2 split of a pair of fp32 values: x = hi + lo * 2^-11 with hi = fp16_rn(x) and lo = fp16_rn((x - hi) * 2^11).
+// The residual x - hi is exact in fp32 and at most 2^-12 |x|; scaling it by 2^11 keeps it in fp16's normal range whenever
+// hi is, so the pair carries ~22 significant bits (absolute error <= max(2^-23 |x|, 2^-36)) for |x| < 65504.
+// Packed as two halves per 32-bit word, first value in the low half.
+constexpr float kF16LoScale = 2048.f, kF16LoInv = 1.f / 2048.f;
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - f.x) * kF16LoScale, (b - f.y) * kF16LoScale);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// Power-of-two operand scale for a tensor whose largest magnitude is amax: amax * scale lies in [2^14, 2^15), i.e. inside
+// fp16's range with headroom, and elements down to amax * 2^-28 keep full precision. amax == 0 / non-finite -> 1.
+__device__ __forceinline__ float f16_operand_scale(float amax) {
+  const uint32_t e = (__float_as_uint(amax) >> 23) & 0xFFu;     // biased exponent, amax in [2^(e-127), 2^(e-126))
+  if (e == 0u || e == 0xFFu) return 1.f;
+  int se = 127 + 14 - ((int)e - 127);
+  se = se < 1 ? 1 : (se > 254 ? 254 : se);
+  return __uint_as_float((uint32_t)se << 23);
 }
 
 }  // namespace tc

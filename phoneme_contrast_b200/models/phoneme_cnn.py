@@ -20,13 +20,15 @@ from .. import ops
 from .base import BaseModel
 from .registry import model_registry
 
-_PREC = {"fp32": L.PREC_FP32, "tf32x3": L.PREC_TF32X3, "bf16": L.PREC_BF16}
+_PREC = {"fp32": L.PREC_FP32, "tf32x3": L.PREC_TF32X3, "bf16": L.PREC_BF16, "fp16x2": L.PREC_FP16X2}
 
 
 def _precision(config) -> int:
-    # default: tf32x3 -- tcgen05 tensor cores with fp32-level accuracy (3-term TF32 split) for every eligible layer,
-    # exact-fp32 SIMT kernels elsewhere. "fp32" forces the SIMT kernels everywhere; "bf16" is the 1e-2 opt-in mode.
-    name = os.environ.get("PC_PRECISION") or config.get("precision", "tf32x3")
+    # default: fp16x2 -- tcgen05 tensor cores with fp32-level accuracy (operands split into fp16 hi + lo, three products per
+    # pair at the kind::f16 rate) for every eligible layer (64-channel granularity; 32-channel layers fall back to the
+    # equivalent TF32x3 split), exact-fp32 SIMT kernels elsewhere. "tf32x3" selects the TF32 split everywhere (no fp16 range
+    # assumptions), "fp32" forces the SIMT kernels, "bf16" is the 1e-2 opt-in mode.
+    name = os.environ.get("PC_PRECISION") or config.get("precision", "fp16x2")
     if name not in _PREC:
         raise ValueError(f"precision must be one of {list(_PREC)}, got {name!r}")
     return _PREC[name]
@@ -118,6 +120,20 @@ def _drop_masks(net, B, chans, training):
     return [ops.dropout2d_mask(B, c, net.dropout_rate, seed, i << 20, dev, net._drop_step) for i, c in enumerate(chans)]
 
 
+class _AmaxSlots:
+    """One zeroed float per gradient tensor; the BatchNorm-backward apply kernels atomically max |dy| into a slot and the
+    convolutions that consume that dy read it back on the device (no host sync)."""
+
+    def __init__(self, device, n):
+        self.buf = torch.zeros(n, device=device, dtype=torch.float32)
+        self.k = 0
+
+    def take(self):
+        v = self.buf[self.k:self.k + 1]
+        self.k += 1
+        return v
+
+
 class _WgradLane:
     """Weight gradients run on a second CUDA stream: wgrad(l) needs only dy_l, while the main stream continues with
     dgrad(l) and the BatchNorm backward of layer l-1, so the two chains overlap (they also fill each other's wave tails:
@@ -133,14 +149,14 @@ class _WgradLane:
             self.side = net._side_stream
             self.main = torch.cuda.current_stream()
 
-    def __call__(self, x, dy, g, xform, dw, db, prec):
+    def __call__(self, x, dy, g, xform, dw, db, prec, amax=None):
         if not self.enabled:
-            ops.conv_wgrad(x, dy, g, xform, dw, db, prec)
+            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax)
             return
         self.keep.extend((x, dy))
         self.side.wait_stream(self.main)
         with torch.cuda.stream(self.side):
-            ops.conv_wgrad(x, dy, g, xform, dw, db, prec)
+            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax)
 
     def join(self):
         if self.enabled:
@@ -213,17 +229,19 @@ def _small_backward(net, s, demb, grads, training=True):
     keep = []
     wgrad = _WgradLane(net, keep)
     dout = _head_bwd(net, s, demb, grads, training)
+    amax = _AmaxSlots(demb.device, 6)   # max|dy| of every gradient tensor a convolution consumes (FP16X2 operand scale)
     for b in (2, 1, 0):
         convA, bnA, convB, bnB = blocks[b][0], blocks[b][1], blocks[b][3], blocks[b][4]
         ly = s.layers[b]
-        dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias])
+        mB, mA = amax.take(), amax.take()
+        dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias], mB)
         xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
-        wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], grads[convB.bias], prec)
-        dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d)
-        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias])
-        wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], grads[convA.bias], prec)
+        wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], grads[convB.bias], prec, mB)
+        dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d, dy_amax=mB)
+        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA)
+        wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], grads[convA.bias], prec, mA)
         if b > 0:
-            dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d)
+            dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d, dy_amax=mA)
     wgrad.join()
 
 
@@ -285,27 +303,29 @@ def _deep_backward(net, s, demb, grads, training=True):
     keep = []
     wgrad = _WgradLane(net, keep)
     dout = _head_bwd(net, s, demb, grads, training)
+    amax = _AmaxSlots(demb.device, 3 * len(s.blocks))   # max|dy| per gradient tensor a convolution consumes (FP16X2 scale)
     for i in reversed(range(len(s.blocks))):
         blk = net.conv_blocks[i]
         r = s.blocks[i]
         g2 = (grads[blk.bn2.weight], grads[blk.bn2.bias])
+        m2, m1, ms = amax.take(), amax.take(), amax.take()
         if r["proj"]:
             convs, bns = blk.shortcut[0], blk.shortcut[1]
             dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], r["ys"], r["cs"], g2,
-                                                  (grads[bns.weight], grads[bns.bias]))
+                                                  (grads[bns.weight], grads[bns.bias]), m2, ms)
         else:
-            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None)
+            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None)
         xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
-        wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec)
-        dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d)
-        dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias])
-        wgrad(r["xin"], dy1, r["g1"], None, grads[blk.conv1.weight], grads[blk.conv1.bias], prec)
+        wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2)
+        dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2)
+        dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1)
+        wgrad(r["xin"], dy1, r["g1"], None, grads[blk.conv1.weight], grads[blk.conv1.bias], prec, m1)
         if r["proj"]:
-            wgrad(r["xin"], dysc, r["gs"], None, grads[convs.weight], grads[convs.bias], prec)
-            dxin = ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], prec=r["cws"].prec_d)
+            wgrad(r["xin"], dysc, r["gs"], None, grads[convs.weight], grads[convs.bias], prec, ms)
+            dxin = ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], prec=r["cws"].prec_d, dy_amax=ms)
         else:
             dxin = dysc                                        # identity shortcut: d(out)/d(xin) passes g through
-        ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d)
+        ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d, dy_amax=m1)
         dout = dxin
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
     st = s.stem

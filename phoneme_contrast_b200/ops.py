@@ -57,8 +57,14 @@ class ConvWeights:
         import os
         skip = os.environ.get("PC_TC_SKIP", "")
         tag = f"{g.Cin}-{g.Cout}-{g.R}-{g.stride}"
-        self.prec_f = prec if (tc_supported(g, False, prec) and os.environ.get("PC_TC_FWD", "1") == "1" and tag not in skip.split(",")) else L.PREC_FP32
-        self.prec_d = prec if (tc_supported(g, True, prec) and os.environ.get("PC_TC_DGRAD", "1") == "1") else L.PREC_FP32
+        def pick(dgrad):
+            # FP16X2 needs 64-channel k-chunks; a layer with only 32-channel granularity runs the TF32x3 engine instead
+            for cand in ((prec, L.PREC_TF32X3) if prec == L.PREC_FP16X2 else (prec,)):
+                if tc_supported(g, dgrad, cand):
+                    return cand
+            return L.PREC_FP32
+        self.prec_f = pick(False) if (os.environ.get("PC_TC_FWD", "1") == "1" and tag not in skip.split(",")) else L.PREC_FP32
+        self.prec_d = pick(True) if os.environ.get("PC_TC_DGRAD", "1") == "1" else L.PREC_FP32
         self.wf = self.wd = None
         need_simt_f = self.prec_f == L.PREC_FP32
         need_simt_d = need_dgrad and self.prec_d == L.PREC_FP32
@@ -92,11 +98,12 @@ def conv_fwd(x, w, bias, g: PcConvGeom, xform=None, stats=None, prec=L.PREC_FP32
     return y
 
 
-def conv_dgrad(dy, wd, g: PcConvGeom, out=None, accumulate=False, prec=L.PREC_FP32):
+def conv_dgrad(dy, wd, g: PcConvGeom, out=None, accumulate=False, prec=L.PREC_FP32, dy_amax=None):
+    """dy_amax: 1-element device tensor holding max|dy| (FP16X2 operand scale; see include/phoneme_contrast.h)."""
     if out is None:
         out = torch.empty(g.B, g.H, g.W, g.Cin, device=dy.device, dtype=F32)
     L.note_work("pc_conv_dgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
-    call("pc_conv_dgrad", ptr(dy), ptr(wd, None), C.byref(g), ptr(out), 1 if accumulate else 0, prec, stream())
+    call("pc_conv_dgrad", ptr(dy), ptr(wd, None), C.byref(g), ptr(out), 1 if accumulate else 0, prec, ptr(dy_amax), stream())
     return out
 
 
@@ -113,7 +120,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return buf
 
 
-def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_FP32):
+def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_FP32, dy_amax=None):
     if dw is None:
         dw = torch.empty(g.Cout, g.Cin, g.R, g.S, device=x.device, dtype=F32)
     if db is None:
@@ -126,7 +133,7 @@ def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_F
     xf = _xf(**xform) if xform else None
     L.note_work("pc_conv_wgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
     call("pc_conv_wgrad", ptr(x), ptr(dy), C.byref(g), C.byref(xf) if xf is not None else None, ptr(dw), ptr(db),
-         ptr(ws, torch.uint8), ws.numel(), prec, stream())
+         ptr(ws, torch.uint8), ws.numel(), prec, ptr(dy_amax), stream())
     return dw, db
 
 
@@ -168,8 +175,9 @@ def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None):
     return out, argmax
 
 
-def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None):
-    """Gradient w.r.t. the pre-BatchNorm tensor y of out = drop * pool(relu(bn(y))) (train-mode statistics)."""
+def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None):
+    """Gradient w.r.t. the pre-BatchNorm tensor y of out = drop * pool(relu(bn(y))) (train-mode statistics).
+    amax: optional zero-initialised 1-element tensor that receives max|dy| (operand scale of the FP16X2 convolutions)."""
     B, H, W, C_ = y.shape
     sums = torch.zeros(2, C_, device=y.device, dtype=torch.float64)
     args = (ptr(dout), ptr(y), B, H, W, C_, ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd), ptr(drop), pool,
@@ -180,7 +188,7 @@ def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=Non
         dgamma = torch.empty(C_, device=y.device, dtype=F32)
     if dbeta is None:
         dbeta = torch.empty(C_, device=y.device, dtype=F32)
-    call("pc_bn_act_bwd_apply", *args, ptr(sums, torch.float64), ptr(dy), ptr(dgamma), ptr(dbeta), stream())
+    call("pc_bn_act_bwd_apply", *args, ptr(sums, torch.float64), ptr(dy), ptr(dgamma), ptr(dbeta), ptr(amax), stream())
     return dy, dgamma, dbeta
 
 
@@ -193,7 +201,8 @@ def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None):
     return out
 
 
-def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, grads2=None, grads_s=None):
+def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, grads2=None, grads_s=None, amax2=None,
+                    amax_s=None):
     """Returns dy2, d(shortcut branch input: dysc for a projection shortcut, dx for identity), (dgamma2, dbeta2), (dgamma_s, dbeta_s)."""
     C_ = y2.shape[-1]
     n_pix = y2.numel() // C_
@@ -210,7 +219,7 @@ def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, gr
     call("pc_bn_add_relu_bwd_apply", ptr(dout), ptr(out), ptr(y2), ptr(co2.scale), ptr(co2.mean), ptr(co2.invstd),
          ptr(sums2, torch.float64), ptr(ysc) if co_s else None, ptr(co_s.scale) if co_s else None,
          ptr(co_s.mean) if co_s else None, ptr(co_s.invstd) if co_s else None, ptr(sums_s, torch.float64), n_pix, C_,
-         ptr(dy2), ptr(dsc), ptr(g2[0]), ptr(g2[1]), ptr(gs[0]), ptr(gs[1]), stream())
+         ptr(dy2), ptr(dsc), ptr(g2[0]), ptr(g2[1]), ptr(gs[0]), ptr(gs[1]), ptr(amax2), ptr(amax_s), stream())
     return dy2, dsc, g2, gs
 
 

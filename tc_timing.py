@@ -29,6 +29,8 @@ def run(B,H,W,Cin,Cout,k,stride,pad,prec=1,xf=True):
     for i,n in enumerate(names): print(f"   {n:18s} median {med[i]:9.0f} cyc")
     span=(d[:,12].max()-d[:,0].min())
     print("   whole-kernel span cycles", span, " CTAs/SM waves ~", len(d)/148)
-run(256,20,51,64,64,3,1,1)
-run(256,10,26,128,128,3,1,1)
-run(256,3,7,512,512,3,1,1)
+for prec in (1,3):
+    print('=== prec',prec)
+    run(256,20,51,64,64,3,1,1,prec=prec)
+    run(256,5,13,256,256,3,1,1,prec=prec)
+    run(256,3,7,512,512,3,1,1,prec=prec)

@@ -8,10 +8,10 @@ import torch
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
-TOL = {1: 2e-5, 2: 1e-2}     # PC_PREC_TF32X3 (fp32-level), PC_PREC_BF16; relative to max |ref|
+TOL = {1: 2e-5, 2: 1e-2, 3: 2e-5}     # PC_PREC_TF32X3 (fp32-level), PC_PREC_BF16, PC_PREC_FP16X2 (fp32-level); relative to max |ref|
 
 
-@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("prec", [1, 2, 3])
 @pytest.mark.parametrize("M,N,K", [(128, 32, 64), (300, 64, 128), (1000, 128, 576), (4096, 256, 1152), (77, 16, 64), (260, 512, 256)])
 def test_tc_gemm(prec, M, N, K):
     from phoneme_contrast_b200 import ops
@@ -37,7 +37,7 @@ CONV_CASES = [
 ]
 
 
-@pytest.mark.parametrize("prec", [1, 2])
+@pytest.mark.parametrize("prec", [1, 2, 3])
 @pytest.mark.parametrize("case", CONV_CASES)
 def test_tc_conv_fwd_dgrad(prec, case):
     from phoneme_contrast_b200 import _lib as L
@@ -67,45 +67,51 @@ def test_tc_conv_fwd_dgrad(prec, case):
     np.testing.assert_allclose(stats[1].cpu().numpy(), (ref * ref).sum(dim=(0, 1, 2)).cpu().numpy(), rtol=5 * TOL[prec])
     # data gradient (+ accumulate)
     if cw.prec_d == prec:
-        dy = torch.randn(B, g.Ho, g.Wo, Cout, device=DEV, generator=gen)
-        dx = ops.conv_dgrad(dy, cw.wd, g, prec=cw.prec_d)
+        # FP16X2: gradients as small as real ones (1e-7) must survive fp16's range through the amax operand scale
+        dy = torch.randn(B, g.Ho, g.Wo, Cout, device=DEV, generator=gen) * (3e-7 if prec == 3 else 1.0)
+        amax = dy.abs().max().reshape(1) if prec == 3 else None
+        dx = ops.conv_dgrad(dy, cw.wd, g, prec=cw.prec_d, dy_amax=amax)
         xr = torch.zeros(B, Cin, H, W, device=DEV, dtype=torch.float64, requires_grad=True)
         torch.nn.functional.conv2d(xr, w.double(), None, stride=stride, padding=pad).backward(dy.permute(0, 3, 1, 2).double())
         dref = xr.grad.permute(0, 2, 3, 1)
         err = float((dx.double() - dref).abs().max() / dref.abs().max())
         assert err < TOL[prec], ("dgrad", err)
-        dx2 = ops.conv_dgrad(dy, cw.wd, g, out=dx.clone(), accumulate=True, prec=cw.prec_d)
+        dx2 = ops.conv_dgrad(dy, cw.wd, g, out=dx.clone(), accumulate=True, prec=cw.prec_d, dy_amax=amax)
         assert float((dx2.double() - 2 * dref).abs().max() / dref.abs().max()) < 2 * TOL[prec]
 
 
 @pytest.mark.parametrize("case", CONV_CASES + [(16, 40, 101, 32, 32, 3, 1, 1), (9, 20, 51, 64, 64, 3, 1, 1), (4, 10, 50, 128, 128, 3, 1, 1),
                                                (4, 20, 100, 64, 64, 3, 1, 1), (4, 5, 25, 256, 256, 3, 1, 1), (4, 20, 100, 64, 128, 3, 2, 1)])
-def test_tc_conv_wgrad(case):
-    """Weight / bias gradient on the tensor cores (MN-major TF32x3 tiles, pixel-split partials) vs torch fp64."""
+@pytest.mark.parametrize("prec", [1, 3])
+def test_tc_conv_wgrad(case, prec):
+    """Weight / bias gradient on the tensor cores (MN-major TF32x3 or FP16x2 tiles, pixel-split partials) vs torch fp64."""
     from phoneme_contrast_b200 import ops
     B, H, W, Cin, Cout, k, stride, pad = case
     g = ops.conv_geom(B, H, W, Cin, Cout, k, stride, pad)
     gen = torch.Generator(device=DEV).manual_seed(Cin * 3 + Cout + k)
     x = torch.randn(B, H, W, Cin, device=DEV, generator=gen)
-    dy = torch.randn(B, g.Ho, g.Wo, Cout, device=DEV, generator=gen)
+    # FP16X2: realistic tiny gradients; the amax operand scale must keep them inside fp16's range
+    dy = torch.randn(B, g.Ho, g.Wo, Cout, device=DEV, generator=gen) * (3e-7 if prec == 3 else 1.0)
+    amax = dy.abs().max().reshape(1) if prec == 3 else None
     scale = 1.0 + 0.1 * torch.randn(Cin, device=DEV, generator=gen)
     shift = 0.1 * torch.randn(Cin, device=DEV, generator=gen)
     drop = ((torch.rand(B, Cin, device=DEV, generator=gen) > 0.2).float() / 0.8).contiguous()
     xf = dict(scale=scale, shift=shift, relu=True, drop=drop)
-    dw, db = ops.conv_wgrad(x, dy, g, xf, prec=1)
+    dw, db = ops.conv_wgrad(x, dy, g, xf, prec=prec, dy_amax=amax)
     a = (torch.relu(x.double() * scale.double() + shift.double()) * drop.double()[:, None, None, :]).permute(0, 3, 1, 2)
     wr = torch.zeros(Cout, Cin, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
     br = torch.zeros(Cout, device=DEV, dtype=torch.float64, requires_grad=True)
     torch.nn.functional.conv2d(a, wr, br, stride=stride, padding=pad).backward(dy.permute(0, 3, 1, 2).double())
     err = float((dw.double() - wr.grad).abs().max() / wr.grad.abs().max())
-    assert err < TOL[1], ("dw", err)
+    assert err < TOL[prec], ("dw", err)
     assert float((db.double() - br.grad).abs().max() / br.grad.abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("precision", ["tf32x3", "fp16x2"])
 @pytest.mark.parametrize("arch,B", [("phoneme_cnn", 16), ("phoneme_cnn_deep", 8)])
-def test_nets_tf32x3_match_oracle(arch, B, monkeypatch):
-    """Whole networks with the tensor-core convolutions in TF32x3 mode keep the fp32 parity bar (1e-4)."""
-    monkeypatch.setenv("PC_PRECISION", "tf32x3")
+def test_nets_split_precision_match_oracle(arch, B, precision, monkeypatch):
+    """Whole networks with the tensor-core convolutions in a split-operand mode (TF32x3 / FP16x2) keep the fp32 parity bar (1e-4)."""
+    monkeypatch.setenv("PC_PRECISION", precision)
     from tests.test_gpu_parity import _check_grads, _oracle_net, _run_net
     from oracle import nets_oracle
     cfg = {"dropout_rate": 0.0}
