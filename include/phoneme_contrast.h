@@ -150,6 +150,17 @@ enum { PC_PREC_FP32 = 0, PC_PREC_TF32X3 = 1, PC_PREC_BF16 = 2, PC_PREC_FP16X2 = 
 int pc_conv_tc_supported(const PcConvGeom* g, int dgrad, int prec);
 size_t pc_conv_tc_packed_bytes(int O, int I, int R, int S, int dgrad, int prec);
 int pc_pack_conv_weight_tc(const float* w_oihw, int O, int I, int R, int S, int dgrad, int prec, void* out, pc_stream_t stream);
+/* All layers' weight operands in ONE launch (they are re-packed after every optimiser step). jobs: DEVICE array; each job is
+ * what one pc_pack_conv_weight_tc call would do; item_begin = running sum of pc_pack_conv_weight_tc_items() over the
+ * preceding jobs, total_items = the sum over all jobs. */
+typedef struct PcPackJob {
+  const float* w_oihw;
+  void* out;
+  int32_t O, I, R, S, dgrad, prec;
+  int64_t item_begin;
+} PcPackJob;
+int64_t pc_pack_conv_weight_tc_items(int O, int I, int R, int S, int dgrad, int prec);
+int pc_pack_conv_weights_tc_batch(const PcPackJob* jobs, int n_jobs, int64_t total_items, pc_stream_t stream);
 /* C[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) through the same tcgen05 tile engine (unit check of the tensor-core path;
  * also usable as a stand-alone fp32-accurate GEMM). ws >= pc_tc_gemm_workspace(N, K, prec) bytes. */
 size_t pc_tc_gemm_workspace(int N, int K, int prec);

@@ -41,6 +41,10 @@ class PcInXform(C.Structure):
     _fields_ = [("scale", vp), ("shift", vp), ("drop", vp), ("relu", C.c_int32)]
 
 
+class PcPackJob(C.Structure):
+    _fields_ = [("w_oihw", vp), ("out", vp)] + [(n, C.c_int32) for n in ("O", "I", "R", "S", "dgrad", "prec")] + [("item_begin", C.c_int64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/phoneme_contrast.h declares (tests check this)
 SIGNATURES = {
     "pc_last_error": (C.c_char_p, []),
@@ -57,6 +61,8 @@ SIGNATURES = {
     "pc_conv_tc_supported": (i32, [C.POINTER(PcConvGeom), i32, i32]),
     "pc_conv_tc_packed_bytes": (sz, [i32, i32, i32, i32, i32, i32]),
     "pc_pack_conv_weight_tc": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
+    "pc_pack_conv_weight_tc_items": (i64, [i32, i32, i32, i32, i32, i32]),
+    "pc_pack_conv_weights_tc_batch": (i32, [vp, i32, i64, vp]),
     "pc_tc_gemm_workspace": (sz, [i32, i32, i32]),
     "pc_tc_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]),
     "pc_conv_fwd": (i32, [vp, vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, i32, vp]),

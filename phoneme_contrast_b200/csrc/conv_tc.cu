@@ -580,54 +580,82 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
 // src_mode 1: conv dgrad B[n = c][k = (r,s,o)] = w[o][c][r][s]      (Ca = O)
 // src_mode 2: plain      B[n][k] = src[n * ld + k]                  (taps = 1, Ca = K)
 template <int PREC>
+__device__ __forceinline__ void pack_b_item(const float* __restrict__ src, int O, int I, int R, int S, int src_mode, int ld, int Nn,
+                                            int Npad, int Ca, unsigned char* __restrict__ out, long long idx) {
+  using P = Prec<PREC>;
+  constexpr int BKC = P::BKC, PARTS = P::PARTS;
+  constexpr int EPC = (PREC == PC_PREC_TF32X3) ? 4 : 8;
+  (void)O;
+  const int cpt = Ca / BKC;
+  const int j = (int)(idx & 7);
+  const int n = (int)((idx >> 3) % Npad);
+  const int kc = (int)((idx >> 3) / Npad);
+  const int tap = kc / cpt, c0 = (kc % cpt) * BKC + j * EPC;
+  float v[EPC];
+#pragma unroll
+  for (int q = 0; q < EPC; ++q) {
+    float x = 0.f;
+    if (n < Nn) {
+      const int c = c0 + q;
+      if (src_mode == 0) x = src[(((size_t)n * I + c) * R + tap / S) * S + tap % S];
+      else if (src_mode == 1) x = src[(((size_t)c * I + n) * R + tap / S) * S + tap % S];
+      else x = src[(size_t)n * ld + c];
+    }
+    v[q] = x;
+  }
+  unsigned char* base = out + ((size_t)kc * PARTS * Npad + n) * 128 + (size_t)((j ^ (n & 7)) << 4);
+  if (PREC == PC_PREC_TF32X3) {
+    float h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
+    *reinterpret_cast<float4*>(base) = make_float4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<float4*>(base + (size_t)Npad * 128) = make_float4(l[0], l[1], l[2], l[3]);
+  } else if (PREC == PC_PREC_FP16X2) {
+    uint4 h, l;
+    split_f16x2(v[0], v[1], h.x, l.x);
+    split_f16x2(v[2], v[3], h.y, l.y);
+    split_f16x2(v[4 % EPC], v[5 % EPC], h.z, l.z);
+    split_f16x2(v[6 % EPC], v[7 % EPC], h.w, l.w);
+    *reinterpret_cast<uint4*>(base) = h;
+    *reinterpret_cast<uint4*>(base + (size_t)Npad * 128) = l;
+  } else {
+    uint4 w;
+    w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
+    w.z = pack_bf16(v[4 % EPC], v[5 % EPC]); w.w = pack_bf16(v[6 % EPC], v[7 % EPC]);
+    *reinterpret_cast<uint4*>(base) = w;
+  }
+}
+
+template <int PREC>
 __global__ void pack_b_kernel(const float* __restrict__ src, int O, int I, int R, int S, int src_mode, int ld, int Nn, int Npad,
                               int Ca, unsigned char* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
-  using P = Prec<PREC>;
-  constexpr int BKC = P::BKC, PARTS = P::PARTS;
-  constexpr int EPC = (PREC == PC_PREC_TF32X3) ? 4 : 8;
   const int taps = src_mode == 2 ? 1 : R * S;
-  const int cpt = Ca / BKC;
-  const long long total = (long long)taps * cpt * Npad * 8;
+  const long long total = (long long)taps * (Ca / Prec<PREC>::BKC) * Npad * 8;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    pack_b_item<PREC>(src, O, I, R, S, src_mode, ld, Nn, Npad, Ca, out, idx);
+}
+
+// every layer's weight operand in one launch: job j owns items [item_begin_j, item_begin_{j+1})
+__global__ void __launch_bounds__(256) pack_b_batch_kernel(const PcPackJob* __restrict__ jobs, int n_jobs, long long total) {
+  pdl_trigger();
+  pdl_wait();
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(idx & 7);
-    const int n = (int)((idx >> 3) % Npad);
-    const int kc = (int)((idx >> 3) / Npad);
-    const int tap = kc / cpt, c0 = (kc % cpt) * BKC + j * EPC;
-    float v[EPC];
-#pragma unroll
-    for (int q = 0; q < EPC; ++q) {
-      float x = 0.f;
-      if (n < Nn) {
-        const int c = c0 + q;
-        if (src_mode == 0) x = src[(((size_t)n * I + c) * R + tap / S) * S + tap % S];
-        else if (src_mode == 1) x = src[(((size_t)c * I + n) * R + tap / S) * S + tap % S];
-        else x = src[(size_t)n * ld + c];
-      }
-      v[q] = x;
+    int lo = 0, hi = n_jobs - 1;               // last job whose item_begin <= idx
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].item_begin <= idx) lo = mid; else hi = mid - 1;
     }
-    unsigned char* base = out + ((size_t)kc * PARTS * Npad + n) * 128 + (size_t)((j ^ (n & 7)) << 4);
-    if (PREC == PC_PREC_TF32X3) {
-      float h[4], l[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) split_tf32(v[q], h[q], l[q]);
-      *reinterpret_cast<float4*>(base) = make_float4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<float4*>(base + (size_t)Npad * 128) = make_float4(l[0], l[1], l[2], l[3]);
-    } else if (PREC == PC_PREC_FP16X2) {
-      uint4 h, l;
-      split_f16x2(v[0], v[1], h.x, l.x);
-      split_f16x2(v[2], v[3], h.y, l.y);
-      split_f16x2(v[4 % EPC], v[5 % EPC], h.z, l.z);
-      split_f16x2(v[6 % EPC], v[7 % EPC], h.w, l.w);
-      *reinterpret_cast<uint4*>(base) = h;
-      *reinterpret_cast<uint4*>(base + (size_t)Npad * 128) = l;
-    } else {
-      uint4 w;
-      w.x = pack_bf16(v[0], v[1]); w.y = pack_bf16(v[2], v[3]);
-      w.z = pack_bf16(v[4 % EPC], v[5 % EPC]); w.w = pack_bf16(v[6 % EPC], v[7 % EPC]);
-      *reinterpret_cast<uint4*>(base) = w;
-    }
+    const PcPackJob jb = jobs[lo];
+    const int ca = jb.dgrad ? jb.O : jb.I, nn = jb.dgrad ? jb.I : jb.O;
+    const int bn = nn <= 32 ? 32 : (nn <= 64 ? 64 : 128);
+    const int npad = (nn + bn - 1) / bn * bn;
+    const long long li = idx - jb.item_begin;
+    unsigned char* out = static_cast<unsigned char*>(jb.out);
+    if (jb.prec == PC_PREC_TF32X3) pack_b_item<PC_PREC_TF32X3>(jb.w_oihw, jb.O, jb.I, jb.R, jb.S, jb.dgrad, 0, nn, npad, ca, out, li);
+    else if (jb.prec == PC_PREC_FP16X2) pack_b_item<PC_PREC_FP16X2>(jb.w_oihw, jb.O, jb.I, jb.R, jb.S, jb.dgrad, 0, nn, npad, ca, out, li);
+    else pack_b_item<PC_PREC_BF16>(jb.w_oihw, jb.O, jb.I, jb.R, jb.S, jb.dgrad, 0, nn, npad, ca, out, li);
   }
 }
 
@@ -734,6 +762,21 @@ extern "C" int pc_pack_conv_weight_tc(const float* w_oihw, int O, int I, int R, 
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   launch_pack(prec, grid, stream, w_oihw, O, I, R, S, dgrad ? 1 : 0, 0, nn, npad, ca, out);
   PC_LAUNCH_CHECK("pack_b_kernel");
+  return PC_OK;
+}
+
+extern "C" int64_t pc_pack_conv_weight_tc_items(int O, int I, int R, int S, int dgrad, int prec) {
+  if (!tc_prec(prec)) return 0;
+  const int ca = dgrad ? O : I, nn = dgrad ? I : O;
+  return (int64_t)R * S * (ca / bkc_of(prec)) * npad_of(nn) * 8;
+}
+
+extern "C" int pc_pack_conv_weights_tc_batch(const PcPackJob* jobs, int n_jobs, int64_t total_items, pc_stream_t stream) {
+  PC_REQUIRE(jobs && n_jobs > 0 && total_items > 0, PC_EINVAL, "pc_pack_conv_weights_tc_batch: bad arguments");
+  int grid = ceil_div(total_items, 256);
+  if (grid > kNumSMs * 8) grid = kNumSMs * 8;
+  launch_pdl(pack_b_batch_kernel, dim3(grid), dim3(256), 0, stream, jobs, n_jobs, (long long)total_items);
+  PC_LAUNCH_CHECK("pack_b_batch_kernel");
   return PC_OK;
 }
 

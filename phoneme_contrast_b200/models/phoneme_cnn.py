@@ -120,6 +120,16 @@ def _drop_masks(net, B, chans, training):
     return [ops.dropout2d_mask(B, c, net.dropout_rate, seed, i << 20, dev, net._drop_step) for i, c in enumerate(chans)]
 
 
+def _packer_begin(net, x, training):
+    """One batched launch refreshes every tensor-core weight operand of the net (ops.WeightPacker)."""
+    packer = getattr(net, "_packer", None)
+    if packer is None:
+        packer = net._packer = ops.WeightPacker()
+    packer.begin((tuple(x.shape), net._prec, bool(training), os.environ.get("PC_TC_FWD"), os.environ.get("PC_TC_DGRAD"),
+                  os.environ.get("PC_TC_SKIP")))
+    return packer
+
+
 class _AmaxSlots:
     """One zeroed float per gradient tensor; the BatchNorm-backward apply kernels atomically max |dy| into a slot and the
     convolutions that consume that dy read it back on the device (no host sync)."""
@@ -186,6 +196,7 @@ def _head_bwd(net, s, demb, grads, training):
 
 def _small_forward(net, x, training):
     s = _Saved()
+    packer = _packer_begin(net, x, training)
     prec = net._prec
     B, _, H, W = x.shape
     s.x = x
@@ -203,13 +214,13 @@ def _small_forward(net, x, training):
             cwA = None                             # stem kernel reads OIHW directly; no dgrad into the input
             wfA, precA = convA.weight, L.PREC_FP32
         else:
-            cwA = ops.ConvWeights(convA.weight, gA, prec)
+            cwA = ops.ConvWeights(convA.weight, gA, prec, packer=packer)
             wfA, precA = cwA.wf, cwA.prec_f
         stA = slots.take(co)
         yA = ops.conv_fwd(cur, wfA, convA.bias, gA, None, stA, precA)
         coA = ops.bn_finalize(stA, B * gA.Ho * gA.Wo, bnA, training)
         gB = ops.conv_geom(B, h, w, co, co, 3, 1, 1)
-        cwB = ops.ConvWeights(convB.weight, gB, prec)
+        cwB = ops.ConvWeights(convB.weight, gB, prec, packer=packer)
         stB = slots.take(co)
         yB = ops.conv_fwd(yA, cwB.wf, convB.bias, gB, dict(scale=coA.scale, shift=coA.shift, relu=True), stB, cwB.prec_f)
         coB = ops.bn_finalize(stB, B * h * w, bnB, training)
@@ -220,6 +231,7 @@ def _small_forward(net, x, training):
         h, w = ops.pool_dims(h, w, pool)
     s.a_last = cur
     emb = _head(net, s, cur, training)
+    packer.end()
     return emb, s
 
 
@@ -247,6 +259,7 @@ def _small_backward(net, s, demb, grads, training=True):
 
 def _deep_forward(net, x, training):
     s = _Saved()
+    packer = _packer_begin(net, x, training)
     prec = net._prec
     B, _, H, W = x.shape
     s.x = x
@@ -269,12 +282,12 @@ def _deep_forward(net, x, training):
         co = hd[i]
         stride = blk.stride
         g1 = ops.conv_geom(B, h, w, cin, co, 3, stride, 1)
-        cw1 = ops.ConvWeights(blk.conv1.weight, g1, prec)
+        cw1 = ops.ConvWeights(blk.conv1.weight, g1, prec, packer=packer)
         st1 = st(co)
         y1 = ops.conv_fwd(cur, cw1.wf, blk.conv1.bias, g1, None, st1, cw1.prec_f)
         c1 = ops.bn_finalize(st1, B * g1.Ho * g1.Wo, blk.bn1, training)
         g2 = ops.conv_geom(B, g1.Ho, g1.Wo, co, co, 3, 1, 1)
-        cw2 = ops.ConvWeights(blk.conv2.weight, g2, prec)
+        cw2 = ops.ConvWeights(blk.conv2.weight, g2, prec, packer=packer)
         st2 = st(co)
         y2 = ops.conv_fwd(y1, cw2.wf, blk.conv2.bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True, drop=s.drop[i]), st2, cw2.prec_f)
         c2 = ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk.bn2, training)
@@ -282,7 +295,7 @@ def _deep_forward(net, x, training):
         if rec["proj"]:
             convs, bns = blk.shortcut[0], blk.shortcut[1]
             gs = ops.conv_geom(B, h, w, cin, co, 1, stride, 0)
-            cws = ops.ConvWeights(convs.weight, gs, prec)
+            cws = ops.ConvWeights(convs.weight, gs, prec, packer=packer)
             sts = st(co)
             ys = ops.conv_fwd(cur, cws.wf, convs.bias, gs, None, sts, cws.prec_f)
             cs = ops.bn_finalize(sts, B * gs.Ho * gs.Wo, bns, training)
@@ -295,6 +308,7 @@ def _deep_forward(net, x, training):
         cur, cin, h, w = out, co, g1.Ho, g1.Wo
     s.a_last = cur
     emb = _head(net, s, cur, training)
+    packer.end()
     return emb, s
 
 

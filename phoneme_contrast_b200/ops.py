@@ -50,13 +50,18 @@ def pack_conv_weight_tc(w: torch.Tensor, dgrad: bool, prec: int) -> torch.Tensor
 
 class ConvWeights:
     """Per-step packed forms of one conv weight: forward operand, data-gradient operand, and the precision each runs in
-    (tensor cores when the layer is eligible, exact-fp32 SIMT otherwise)."""
+    (tensor cores when the layer is eligible, exact-fp32 SIMT otherwise). With a WeightPacker the tensor-core operands of
+    all layers are written by one batched launch at the start of the step instead of one launch per operand."""
     __slots__ = ("wf", "wd", "prec_f", "prec_d")
 
-    def __init__(self, w: torch.Tensor, g: PcConvGeom, prec: int, need_dgrad: bool = True):
+    def __init__(self, w: torch.Tensor, g: PcConvGeom, prec: int, need_dgrad: bool = True, packer=None):
         import os
+        if packer is not None and packer.replaying:
+            self.wf, self.wd, self.prec_f, self.prec_d = packer.next(w, need_dgrad)
+            return
         skip = os.environ.get("PC_TC_SKIP", "")
         tag = f"{g.Cin}-{g.Cout}-{g.R}-{g.stride}"
+
         def pick(dgrad):
             # FP16X2 needs 64-channel k-chunks; a layer with only 32-channel granularity runs the TF32x3 engine instead
             for cand in ((prec, L.PREC_TF32X3) if prec == L.PREC_FP16X2 else (prec,)):
@@ -75,6 +80,66 @@ class ConvWeights:
             self.wf = pack_conv_weight_tc(w, False, self.prec_f)
         if need_dgrad and not need_simt_d:
             self.wd = pack_conv_weight_tc(w, True, self.prec_d)
+        if packer is not None:
+            packer.record(w, need_dgrad, self, need_simt_f, need_simt_d)
+
+
+class WeightPacker:
+    """Batches the per-step weight re-packing of a network. The first forward with a given key records, layer by layer,
+    which operands are needed (and packs them one launch each, as without a packer); later forwards with the same key
+    issue ONE pc_pack_conv_weights_tc_batch launch that refreshes all recorded tensor-core operands in place and hand the
+    same buffers out in recording order. Exact-fp32 SIMT operands (ineligible layers) are still packed per layer."""
+
+    def __init__(self):
+        self.key = None
+        self.entries = []
+        self.table = None
+        self.replaying = False
+        self.cursor = 0
+
+    def begin(self, key):
+        ok = self.table is not None and key == self.key and all(e["w"].data_ptr() == e["ptr"] for e in self.entries)
+        self.cursor = 0
+        if ok:
+            self.replaying = True
+            if self.n_jobs:
+                call("pc_pack_conv_weights_tc_batch", self.table.data_ptr(), self.n_jobs, self.total, stream())
+        else:
+            self.replaying = False
+            self.key, self.entries, self.table = key, [], None
+
+    def record(self, w, need_dgrad, cw, simt_f, simt_d):
+        self.entries.append(dict(w=w, ptr=w.data_ptr(), need_dgrad=need_dgrad, wf=cw.wf, wd=cw.wd, prec_f=cw.prec_f, prec_d=cw.prec_d,
+                                 simt_f=simt_f, simt_d=simt_d))
+
+    def end(self):
+        if self.replaying:
+            return
+        jobs, total = [], 0
+        for e in self.entries:
+            O, I, R, S = e["w"].shape
+            for dgrad, buf, prec, simt in ((0, e["wf"], e["prec_f"], e["simt_f"]), (1, e["wd"], e["prec_d"], e["simt_d"])):
+                if buf is None or simt:
+                    continue
+                jobs.append(L.PcPackJob(e["ptr"], buf.data_ptr(), O, I, R, S, dgrad, prec, total))
+                total += int(L.lib().pc_pack_conv_weight_tc_items(O, I, R, S, dgrad, prec))
+        self.n_jobs, self.total = len(jobs), total
+        dev = self.entries[0]["w"].device if self.entries else "cpu"
+        raw = bytes(b"".join(bytes(j) for j in jobs)) or b"\0"
+        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+
+    def next(self, w, need_dgrad):
+        e = self.entries[self.cursor]
+        self.cursor += 1
+        if e["ptr"] != w.data_ptr() or e["need_dgrad"] != need_dgrad:
+            raise RuntimeError("WeightPacker: layer order changed since recording")
+        if e["simt_f"] or e["simt_d"]:
+            wf, wd = pack_conv_weight(w, e["simt_f"], e["simt_d"])
+            if e["simt_f"]:
+                e["wf"] = wf
+            if e["simt_d"]:
+                e["wd"] = wd
+        return e["wf"], e["wd"], e["prec_f"], e["prec_d"]
 
 
 def tc_gemm(a: torch.Tensor, b: torch.Tensor, bias=None, prec=L.PREC_TF32X3) -> torch.Tensor:
