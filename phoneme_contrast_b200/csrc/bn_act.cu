@@ -126,18 +126,18 @@ bn_act_fwd_kernel(const float* __restrict__ y, int B, int H, int W, int C, int H
   }
 }
 
-// dz (gradient w.r.t. the BatchNorm output) of input pixel (b,h,w), channels c..c+3, and xhat.
+// dz (gradient w.r.t. the BatchNorm output) of input pixel p = (b,h,w), channels c..c+3, and xhat.
 template <int POOL>
-__device__ __forceinline__ void bn_act_dz(const float* __restrict__ dout, const float* __restrict__ y, int b, int h, int w,
+__device__ __forceinline__ void bn_act_dz(const float* __restrict__ dout, const float* __restrict__ y, int p, int b, int h, int w,
                                           int c, int H, int W, int C, int Ho, int Wo, float4 s, float4 t,
                                           const float* __restrict__ drop, const uint8_t* __restrict__ argmax,
                                           float dz[4], float4& yv) {
-  yv = ld4(y + (((size_t)b * H + h) * W + w) * C + c);
+  yv = ld4(y + (size_t)p * C + c);
   const float4 a4 = bn_relu4(yv, s, t);
   const float a[4] = PC_F4_ARR(a4);
   float g[4] = {0.f, 0.f, 0.f, 0.f};
   if (POOL == 0) {
-    const float4 d4 = ld4(dout + (((size_t)b * H + h) * W + w) * C + c);
+    const float4 d4 = ld4(dout + (size_t)p * C + c);
     g[0] = d4.x; g[1] = d4.y; g[2] = d4.z; g[3] = d4.w;
   } else if (POOL == 2) {
     const int ho = h >> 1, wo = w >> 1;
@@ -162,22 +162,22 @@ __device__ __forceinline__ void bn_act_dz(const float* __restrict__ dout, const 
       for (int q = 0; q < 4; ++q) g[q] = (arg[q] == me) ? d[q] : 0.f;
     }
   } else {
+    // MaxPool2d(3, 2, 1): input row h belongs to window row ho with tap kh = h + 1 - 2*ho in {0,1,2}:
+    //   h even -> (ho = h/2, kh = 1);   h odd -> (ho = (h+1)/2, kh = 0) and (ho = (h-1)/2, kh = 2); same along w
+    const int ho0 = (h + 1) >> 1, nh = 1 + (h & 1), wo0 = (w + 1) >> 1, nw = 1 + (w & 1);
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int hn = h + 1 - kh;
-      if (hn < 0 || (hn & 1)) continue;
-      const int ho = hn >> 1;
-      if (ho >= Ho) continue;
+    for (int ih = 0; ih < 2; ++ih) {
+      const int ho = ho0 - ih;
+      if (ih >= nh || ho >= Ho) continue;
+      const int kh = h + 1 - 2 * ho;
 #pragma unroll
-      for (int kw = 0; kw < 3; ++kw) {
-        const int wn = w + 1 - kw;
-        if (wn < 0 || (wn & 1)) continue;
-        const int wo = wn >> 1;
-        if (wo >= Wo) continue;
+      for (int iw = 0; iw < 2; ++iw) {
+        const int wo = wo0 - iw;
+        if (iw >= nw || wo >= Wo) continue;
+        const int me = kh * 3 + (w + 1 - 2 * wo);
         const size_t o = (((size_t)b * Ho + ho) * Wo + wo) * C + c;
         const uchar4 am = *reinterpret_cast<const uchar4*>(argmax + o);
         const float4 d4 = ld4(dout + o);
-        const int me = kh * 3 + kw;
         if (am.x == me) g[0] += d4.x;
         if (am.y == me) g[1] += d4.y;
         if (am.z == me) g[2] += d4.z;
@@ -194,10 +194,30 @@ __device__ __forceinline__ void bn_act_dz(const float* __restrict__ dout, const 
   for (int q = 0; q < 4; ++q) dz[q] = (a[q] > 0.f) ? g[q] * dr[q] : 0.f;
 }
 
+// Visits the pixels of this block: f(p, b, h, w) with p the linear NHWC pixel index. Without pooling only p is needed (b
+// only for the per-sample dropout multiplier), so the loop is flat and division-free; with pooling a block walks whole
+// image rows, which keeps the (b, h) decomposition out of the inner loop.
+template <int POOL, typename F>
+__device__ __forceinline__ void for_each_pixel(int B, int H, int W, int C4, bool need_b, F&& f) {
+  const int ppb = blockDim.x / C4, lp = threadIdx.x / C4;
+  if (POOL == 0) {
+    const int npix = B * H * W, HW = H * W;      // < 2^31 (checked by the launcher)
+#pragma unroll 2
+    for (int p = blockIdx.x * ppb + lp; p < npix; p += gridDim.x * ppb) f(p, need_b ? p / HW : 0, 0, 0);
+  } else {
+    const int rows = B * H;
+    for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+      const int b = row / H, h = row - b * H;
+#pragma unroll 2
+      for (int w = lp; w < W; w += ppb) f(row * W + w, b, h, w);
+    }
+  }
+}
+
 // Block-level per-channel reduction of NV values per thread (thread owns channels c4*4..+3), then fp64 atomics.
 template <int NV>
-__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][4], int C4, double* const* dst, int C, float* sh) {
-  // sh: [256][4] floats
+__device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][4], int C4, int c4_off, double* const* dst, float* sh) {
+  // sh: [256][4] floats; C4 = channel quads handled by this block, starting at quad c4_off
   const int tid = threadIdx.x;
   const int c4 = tid % C4;
 #pragma unroll
@@ -212,7 +232,7 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][4], int C4
 #pragma unroll
         for (int q = 0; q < 4; ++q) s[q] += (double)sh[t * 4 + q];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) atomicAdd(dst[v] + c4 * 4 + q, s[q]);
+      for (int q = 0; q < 4; ++q) atomicAdd(dst[v] + (c4_off + c4) * 4 + q, s[q]);
     }
   }
 }
@@ -226,27 +246,23 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[256 * 4];
-  const int C4 = C >> 2;
-  const int c4 = threadIdx.x % C4, c = c4 * 4;
-  const int ppb = blockDim.x / C4;  // pixels per block iteration
+  // a block covers a tile of C4 channel quads (gridDim.y tiles) so that the closing fp64 atomics per block stay few
+  const int C4 = (C >> 2) / gridDim.y, c4_off = blockIdx.y * C4;
+  const int c4 = c4_off + threadIdx.x % C4, c = c4 * 4;
   const float4 s = ld4(scale + c), t = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  const int npix = B * H * W;      // < 2^31 (checked by the launcher)
-#pragma unroll 2
-  for (int p = blockIdx.x * ppb + threadIdx.x / C4; p < npix; p += gridDim.x * ppb) {
-    const int w = p % W, t2 = p / W;
-    const int h = t2 % H, b = t2 / H;
+  for_each_pixel<POOL>(B, H, W, C4, drop != nullptr, [&](int p, int b, int h, int w) {
     float dz[4];
     float4 yv;
-    bn_act_dz<POOL>(dout, y, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
+    bn_act_dz<POOL>(dout, y, p, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
     acc[0][0] += dz[0]; acc[0][1] += dz[1]; acc[0][2] += dz[2]; acc[0][3] += dz[3];
     acc[1][0] += dz[0] * (yv.x - mu.x) * is.x;
     acc[1][1] += dz[1] * (yv.y - mu.y) * is.y;
     acc[1][2] += dz[2] * (yv.z - mu.z) * is.z;
     acc[1][3] += dz[3] * (yv.w - mu.w) * is.w;
-  }
+  });
   double* dst[2] = {sums, sums + C};
-  block_channel_reduce<2>(acc, C4, dst, C, sh);
+  block_channel_reduce<2>(acc, C4, c4_off, dst, sh);
 }
 
 template <int POOL>
@@ -279,13 +295,10 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
   }
   const float sv[4] = PC_F4_ARR(s), muv[4] = PC_F4_ARR(mu), isv[4] = PC_F4_ARR(is);
   float lmax = 0.f;
-#pragma unroll 2
-  for (int p = blockIdx.x * ppb + threadIdx.x / C4; p < npix; p += gridDim.x * ppb) {
-    const int w = p % W, t2 = p / W;
-    const int h = t2 % H, b = t2 / H;
+  for_each_pixel<POOL>(B, H, W, C4, drop != nullptr, [&](int p, int b, int h, int w) {
     float dz[4];
     float4 yv;
-    bn_act_dz<POOL>(dout, y, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
+    bn_act_dz<POOL>(dout, y, p, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
     const float yy[4] = PC_F4_ARR(yv);
     float r[4];
 #pragma unroll
@@ -295,7 +308,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
     }
     lmax = absmax4(r, lmax);
     st4(dy + (size_t)p * C + c, make_float4(r[0], r[1], r[2], r[3]));
-  }
+  });
   amax_commit(dy_amax, lmax);
 }
 
@@ -334,8 +347,8 @@ bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __res
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[256 * 4];
-  const int C4 = C >> 2;
-  const int c4 = threadIdx.x % C4, c = c4 * 4;
+  const int C4 = (C >> 2) / gridDim.y, c4_off = blockIdx.y * C4;     // channel tile of this block (see bn_act_bwd_reduce_kernel)
+  const int c4 = c4_off + threadIdx.x % C4, c = c4 * 4;
   const int ppb = blockDim.x / C4;
   const float4 mu2 = ld4(mean2 + c), is2 = ld4(invstd2 + c);
   const bool proj = sums_s != nullptr;
@@ -363,13 +376,13 @@ bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __res
   // sums2 = [sum g, sum g*xhat2]; sums_s = [sum g, sum g*xhat_s]
   if (proj) {
     double* dst[3] = {sums2, sums2 + C, sums_s + C};
-    block_channel_reduce<3>(acc, C4, dst, C, sh);
+    block_channel_reduce<3>(acc, C4, c4_off, dst, sh);
   } else {
     float acc2[2][4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) { acc2[0][q] = acc[0][q]; acc2[1][q] = acc[1][q]; }
     double* dst[2] = {sums2, sums2 + C};
-    block_channel_reduce<2>(acc2, C4, dst, C, sh);
+    block_channel_reduce<2>(acc2, C4, c4_off, dst, sh);
   }
 }
 
@@ -469,6 +482,19 @@ static inline int reduce_grid(long long work_items, int per_block) {
   if (g < 1) g = 1;
   return (int)g;
 }
+// 2-D grid of a reduction pass: y = channel tiles of 64 channels (each block then ends with 64 atomics per sum instead of C),
+// x * y capped at 4 blocks per SM
+static inline dim3 reduce_grid2(long long n_pix, int C) {
+  const int c4 = C / 4;
+  const int tiles = (c4 % 16 == 0) ? c4 / 16 : 1;
+  const int c4t = c4 / tiles;
+  const int ppb = 256 / c4t;
+  long long gx = (n_pix + (long long)ppb * 4 - 1) / ((long long)ppb * 4);
+  const long long cap = (long long)kNumSMs * 4 / tiles;
+  if (gx > cap) gx = cap;
+  if (gx < 1) gx = 1;
+  return dim3((unsigned)gx, (unsigned)tiles);
+}
 
 static inline int ew_grid(long long work_items, int per_block) {
   long long g = (work_items + per_block - 1) / per_block;
@@ -534,7 +560,8 @@ extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, in
   pool_out_dims(H, W, pool, &Ho, &Wo);
   const long long items = (long long)B * H * W * (C / 4);
   PC_REQUIRE((long long)B * H * W < (1LL << 31), PC_EUNSUPPORTED, "pc_bn_act_bwd_reduce: too many pixels");
-  const int grid = reduce_grid(items, 256 * 4);
+  (void)items;
+  const dim3 grid = reduce_grid2((long long)B * H * W, C);
   if (pool == 0) launch_pdl((bn_act_bwd_reduce_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
   else if (pool == 2) launch_pdl((bn_act_bwd_reduce_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
   else launch_pdl((bn_act_bwd_reduce_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
@@ -578,7 +605,7 @@ extern "C" int pc_bn_add_relu_bwd_reduce(const float* dout, const float* out, co
   PC_REQUIRE(dout && out && y2 && mean2 && invstd2 && sums2 && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_bwd_reduce: bad arguments");
   PC_REQUIRE(sums_s == nullptr || (ysc && mean_s && invstd_s), PC_EINVAL, "pc_bn_add_relu_bwd_reduce: shortcut pointers");
   PC_CHECK_C4("pc_bn_add_relu_bwd_reduce", C);
-  launch_pdl(bn_add_relu_bwd_reduce_kernel, dim3(reduce_grid(n_pix * (C / 4), 256 * 4)), dim3(256), 0, stream, dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s);
+  launch_pdl(bn_add_relu_bwd_reduce_kernel, reduce_grid2(n_pix, C), dim3(256), 0, stream, dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s);
   PC_LAUNCH_CHECK("bn_add_relu_bwd_reduce_kernel");
   return PC_OK;
 }
