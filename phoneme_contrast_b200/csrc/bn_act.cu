@@ -197,18 +197,18 @@ __device__ __forceinline__ void bn_act_dz(const float* __restrict__ dout, const 
 // Visits the pixels of this block: f(p, b, h, w) with p the linear NHWC pixel index. Without pooling only p is needed (b
 // only for the per-sample dropout multiplier), so the loop is flat and division-free; with pooling a block walks whole
 // image rows, which keeps the (b, h) decomposition out of the inner loop.
-template <int POOL, typename F>
+template <int POOL, int UNROLL, typename F>
 __device__ __forceinline__ void for_each_pixel(int B, int H, int W, int C4, bool need_b, F&& f) {
   const int ppb = blockDim.x / C4, lp = threadIdx.x / C4;
   if (POOL == 0) {
     const int npix = B * H * W, HW = H * W;      // < 2^31 (checked by the launcher)
-#pragma unroll 2
+#pragma unroll UNROLL
     for (int p = blockIdx.x * ppb + lp; p < npix; p += gridDim.x * ppb) f(p, need_b ? p / HW : 0, 0, 0);
   } else {
     const int rows = B * H;
     for (int row = blockIdx.x; row < rows; row += gridDim.x) {
       const int b = row / H, h = row - b * H;
-#pragma unroll 2
+#pragma unroll UNROLL
       for (int w = lp; w < W; w += ppb) f(row * W + w, b, h, w);
     }
   }
@@ -238,7 +238,7 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][4], int C4
 }
 
 template <int POOL>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ y, int B, int H, int W, int C, int Ho,
                          int Wo, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ drop,
@@ -251,7 +251,7 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict
   const int c4 = c4_off + threadIdx.x % C4, c = c4 * 4;
   const float4 s = ld4(scale + c), t = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-  for_each_pixel<POOL>(B, H, W, C4, drop != nullptr, [&](int p, int b, int h, int w) {
+  for_each_pixel<POOL, 4>(B, H, W, C4, drop != nullptr, [&](int p, int b, int h, int w) {
     float dz[4];
     float4 yv;
     bn_act_dz<POOL>(dout, y, p, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
@@ -295,7 +295,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
   }
   const float sv[4] = PC_F4_ARR(s), muv[4] = PC_F4_ARR(mu), isv[4] = PC_F4_ARR(is);
   float lmax = 0.f;
-  for_each_pixel<POOL>(B, H, W, C4, drop != nullptr, [&](int p, int b, int h, int w) {
+  for_each_pixel<POOL, 2>(B, H, W, C4, drop != nullptr, [&](int p, int b, int h, int w) {
     float dz[4];
     float4 yv;
     bn_act_dz<POOL>(dout, y, p, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);

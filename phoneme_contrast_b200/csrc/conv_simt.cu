@@ -691,6 +691,7 @@ extern "C" int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom*
 }
 
 extern "C" int pc_conv_wgrad_tc_supported(const PcConvGeom* g);
+extern "C" int pc_conv_wgrad_tc_stem_supported(const PcConvGeom* g);
 extern "C" size_t pc_conv_wgrad_tc_workspace(const PcConvGeom* g);
 extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw, float* db,
                                 void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream);
@@ -700,7 +701,7 @@ static size_t wgrad_workspace_simt(const PcConvGeom* g);
 extern "C" size_t pc_conv_wgrad_workspace(const PcConvGeom* g) {
   if (g == nullptr) return 0;
   size_t a = wgrad_workspace_simt(g);
-  if (g->Cin != 1 && pc_conv_wgrad_tc_supported(g)) {
+  if ((g->Cin != 1 && pc_conv_wgrad_tc_supported(g)) || pc_conv_wgrad_tc_stem_supported(g)) {
     const size_t b = pc_conv_wgrad_tc_workspace(g);
     if (b > a) a = b;
   }
@@ -723,6 +724,8 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
              pc_conv_wgrad_workspace(g));
   // tensor-core path (TF32x3) for eligible layers whenever a tensor-core precision is requested
   if (prec != PC_PREC_FP32 && g->Cin != 1 && pc_conv_wgrad_tc_supported(g))
+    return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, stream);
+  if (prec == PC_PREC_FP16X2 && xf == nullptr && pc_conv_wgrad_tc_stem_supported(g))   // single-channel stem on the tensor cores
     return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, stream);
   float* partial = static_cast<float*>(workspace);
   int n_partials;

@@ -63,10 +63,10 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr_bytes)
 }
 
 // 16-bit MN-major operand, SWIZZLE_128B: 8-row x 128-byte atoms
-__device__ __forceinline__ uint64_t smem_desc_mn_sw128_h(uint32_t smem_addr_bytes) {
+__device__ __forceinline__ uint64_t smem_desc_mn_sw128_h(uint32_t smem_addr_bytes, uint32_t group_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr_bytes >> 4) & 0x3FFF);
-  d |= (uint64_t)(4096 >> 4) << 16;      // LBO: next 64-channel group
+  d |= (uint64_t)(group_bytes >> 4) << 16;   // LBO: next 64-channel group (pixels per stage x 128 B)
   d |= (uint64_t)(1024 >> 4) << 32;      // SBO: next 8-pixel group
   d |= (uint64_t)1 << 46;                // version
   d |= (uint64_t)2 << 61;                // SWIZZLE_128B
@@ -74,17 +74,27 @@ __device__ __forceinline__ uint64_t smem_desc_mn_sw128_h(uint32_t smem_addr_byte
 }
 
 // channels per 128-byte row: 32 (tf32) or 64 (fp16); a 128-row M tile is 128 / CPG channel groups
-template <int BN, bool F16>
-__host__ __device__ constexpr uint32_t stage_bytes() { return 2u * ((F16 ? 2u : 4u) * 4096u + (BN / (F16 ? 64 : 32)) * 4096u); }
+// STEM stages hold 64 pixels instead of 32: that kernel streams dy once from HBM with nothing else to do, so the bytes
+// each producer group has in flight set its speed
+template <int BN, bool F16, bool STEM = false>
+__host__ __device__ constexpr uint32_t stage_bytes() {
+  return 2u * ((F16 ? 2u : 4u) * (STEM ? 8192u : 4096u) + (BN / (F16 ? 64 : 32)) * (STEM ? 8192u : 4096u));
+}
 
-template <int BN, int NGROUPS, int MINB, bool F16>
+// STEM (with F16): single input channel. The M tile's first 64 rows are the R*S taps (zero padded), the second channel
+// group stays zero; thread (pixel row, j) gathers taps 8j..8j+7 of its pixel's window with scalar loads.
+template <int BN, int NGROUPS, int MINB, bool F16, bool STEM = false>
 __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(const Params p) {
+  static_assert(!STEM || F16, "the stem gather is built for the FP16X2 tiles only");
   constexpr int PROD_WARPS = 4 * NGROUPS;
   constexpr int CPG = F16 ? 64 : 32;          // channels per 128-byte row (one channel group)
   constexpr int GA = 128 / CPG, GB = BN / CPG; // channel groups of the A' (M) and B' (N) tiles
   constexpr int NV = F16 ? 2 : 1;             // float4 loads per thread, row and group (8 or 4 channels -> one 16-byte chunk)
-  constexpr uint32_t A_PART = GA * 4096, B_PART = GB * 4096;
-  constexpr uint32_t STAGE = stage_bytes<BN, F16>();
+  constexpr int PIXS = STEM ? 64 : PIX;       // pixels per stage
+  constexpr int HR = PIXS / 16;               // pixel rows per thread and stage (rows pr + 16*h)
+  constexpr uint32_t GRP = PIXS * 128;        // bytes of one channel group of a stage
+  constexpr uint32_t A_PART = GA * GRP, B_PART = GB * GRP;
+  constexpr uint32_t STAGE = stage_bytes<BN, F16, STEM>();
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int S = p.stages;
@@ -99,7 +109,7 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
   const int kt = blockIdx.x, n0 = blockIdx.y * BN, split = blockIdx.z;
   const int m_begin = split * p.rows_per_split;
   const int m_end = min(p.M, m_begin + p.rows_per_split);
-  const int n_stages = (m_end - m_begin + PIX - 1) / PIX;
+  const int n_stages = (m_end - m_begin + PIXS - 1) / PIXS;
 
   if (warp == PROD_WARPS) {
     if (lane == 0) {
@@ -151,14 +161,33 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
       }
     const bool use_scale = F16 && p.dy_amax != nullptr;
     const float b_scale = use_scale ? f16_operand_scale(p.dy_amax[0]) : 1.f;
+    int stem_dh[STEM ? 8 : 1], stem_dw[STEM ? 8 : 1];
+    float bsum[STEM ? 8 : 1] = {};     // STEM: bias gradient (column sums of dy) of my 8 channels, folded into this pass over dy
+    if (STEM) {
+      // rows 64..127 of the M tile (second channel group of a_hi / a_lo) are never written again: zero them once
+      constexpr int V = GRP / 16;     // uint4 per group
+      for (int i = tid; i < S * 2 * V; i += 32 * PROD_WARPS) {
+        const int sidx = i / (2 * V), rem = i - sidx * 2 * V;
+        unsigned char* part = tiles + (size_t)sidx * STAGE + (rem >= V ? A_PART : 0) + GRP;
+        *reinterpret_cast<uint4*>(part + (rem % V) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      fence_proxy_async();
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * PROD_WARPS) : "memory");
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int t = 8 * j + q, tr = t / g.S;
+        stem_dh[q] = t < p.K ? tr - g.pad : -100000;      // out-of-range sentinel -> bounds test fails
+        stem_dw[q] = t - tr * g.S - g.pad;
+      }
+    }
     for (int st = group; st < n_stages; st += NGROUPS) {
       const int s = st % S;
       const uint32_t ph = (uint32_t)(st / S) & 1u;
-      float4 av[2][GA][NV], bv[2][GB][NV];
+      float4 av[HR][STEM ? 1 : GA][NV], bv[HR][GB][NV];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < HR; ++h) {
         const int pl = pr + 16 * h;
-        const int m = m_begin + st * PIX + pl;
+        const int m = m_begin + st * PIXS + pl;
         const bool mv = m < m_end;
         int b = 0, ho = 0, wo = 0;
         if (mv) {
@@ -173,9 +202,24 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
           for (int vv = 0; vv < NV; ++vv) {
             const int n = n0 + CPG * q + 4 * NV * j + 4 * vv;
             bv[h][q][vv] = (mv && n < g.Cout) ? *reinterpret_cast<const float4*>(p.dy + (size_t)m * g.Cout + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (STEM) {
+              bsum[(4 * vv) % (STEM ? 8 : 1)] += bv[h][q][vv].x; bsum[(4 * vv + 1) % (STEM ? 8 : 1)] += bv[h][q][vv].y;
+              bsum[(4 * vv + 2) % (STEM ? 8 : 1)] += bv[h][q][vv].z; bsum[(4 * vv + 3) % (STEM ? 8 : 1)] += bv[h][q][vv].w;
+            }
           }
+        if (STEM) {
+          float tv[8];
 #pragma unroll
-        for (int q = 0; q < GA; ++q) {
+          for (int q = 0; q < 8; ++q) {
+            const int hi = ho + stem_dh[q], wi = wo + stem_dw[q];
+            const bool ok = mv && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+            tv[q] = ok ? p.x[((size_t)b * g.H + hi) * g.W + wi] : 0.f;
+          }
+          av[h][0][0] = make_float4(tv[0], tv[1], tv[2], tv[3]);
+          av[h][0][NV - 1] = make_float4(tv[4], tv[5], tv[6], tv[7]);
+        }
+#pragma unroll
+        for (int q = 0; q < (STEM ? 0 : GA); ++q) {
           const int hi = ho * g.stride - g.pad + q_tr[q], wi = wo * g.stride - g.pad + q_ts[q];
           const bool ok = mv && q_ok[q] && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
 #pragma unroll
@@ -200,18 +244,18 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
       unsigned char* b_hi = a_hi + 2 * A_PART;
       unsigned char* b_lo = b_hi + B_PART;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < HR; ++h) {
         const int pl = pr + 16 * h;
         if (F16) {
           // atom = 8 pixel rows x 128 B; 16-byte chunk index XOR (row & 7)
           const uint32_t off = (uint32_t)((pl >> 3) * 1024 + (pl & 7) * 128 + ((j ^ (pl & 7)) << 4));
 #pragma unroll
-          for (int q = 0; q < GA; ++q) {
+          for (int q = 0; q < (STEM ? 1 : GA); ++q) {
             uint4 hh, ll;
             split_f16x2(av[h][q][0].x, av[h][q][0].y, hh.x, ll.x); split_f16x2(av[h][q][0].z, av[h][q][0].w, hh.y, ll.y);
             split_f16x2(av[h][q][NV - 1].x, av[h][q][NV - 1].y, hh.z, ll.z); split_f16x2(av[h][q][NV - 1].z, av[h][q][NV - 1].w, hh.w, ll.w);
-            *reinterpret_cast<uint4*>(a_hi + q * 4096 + off) = hh;
-            *reinterpret_cast<uint4*>(a_lo + q * 4096 + off) = ll;
+            *reinterpret_cast<uint4*>(a_hi + q * GRP + off) = hh;
+            *reinterpret_cast<uint4*>(a_lo + q * GRP + off) = ll;
           }
 #pragma unroll
           for (int q = 0; q < GB; ++q) {
@@ -223,8 +267,8 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
             uint4 hh, ll;
             split_f16x2(b0.x, b0.y, hh.x, ll.x); split_f16x2(b0.z, b0.w, hh.y, ll.y);
             split_f16x2(b1.x, b1.y, hh.z, ll.z); split_f16x2(b1.z, b1.w, hh.w, ll.w);
-            *reinterpret_cast<uint4*>(b_hi + q * 4096 + off) = hh;
-            *reinterpret_cast<uint4*>(b_lo + q * 4096 + off) = ll;
+            *reinterpret_cast<uint4*>(b_hi + q * GRP + off) = hh;
+            *reinterpret_cast<uint4*>(b_lo + q * GRP + off) = ll;
           }
         } else {
           // atom = 4 pixel rows x 128 B; 32-byte chunk index XOR (row & 3)  (Swizzle<2,5,2> on the byte address)
@@ -234,16 +278,16 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
             float hh[4], ll[4];
             split_tf32(av[h][q][0].x, hh[0], ll[0]); split_tf32(av[h][q][0].y, hh[1], ll[1]);
             split_tf32(av[h][q][0].z, hh[2], ll[2]); split_tf32(av[h][q][0].w, hh[3], ll[3]);
-            *reinterpret_cast<float4*>(a_hi + q * 4096 + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<float4*>(a_lo + q * 4096 + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+            *reinterpret_cast<float4*>(a_hi + q * GRP + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<float4*>(a_lo + q * GRP + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
           }
 #pragma unroll
           for (int q = 0; q < GB; ++q) {
             float hh[4], ll[4];
             split_tf32(bv[h][q][0].x, hh[0], ll[0]); split_tf32(bv[h][q][0].y, hh[1], ll[1]);
             split_tf32(bv[h][q][0].z, hh[2], ll[2]); split_tf32(bv[h][q][0].w, hh[3], ll[3]);
-            *reinterpret_cast<float4*>(b_hi + q * 4096 + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<float4*>(b_lo + q * 4096 + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
+            *reinterpret_cast<float4*>(b_hi + q * GRP + off) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<float4*>(b_lo + q * GRP + off) = make_float4(ll[0], ll[1], ll[2], ll[3]);
           }
         }
       }
@@ -254,6 +298,17 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
     // ---- epilogue: TMEM lane = (tap,c) row of the tile; 32-column chunks spread over the producer groups
     mbar_wait(acc_full, 0);
     tc_fence_after();
+    if (STEM) {
+      // all MMAs have completed, so the stage buffers are free: sum the per-thread bias partials per channel there and
+      // write them as the bias row of this split's partial
+      float* s_b = reinterpret_cast<float*>(tiles);
+      if (tid < BN) s_b[tid] = 0.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * PROD_WARPS) : "memory");
+#pragma unroll
+      for (int e = 0; e < (STEM ? 8 : 1); ++e) atomicAdd(s_b + 8 * j + e, bsum[e]);
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * PROD_WARPS) : "memory");
+      if (tid < BN && n0 + tid < g.Cout) p.partial[((size_t)split * (p.K + 1) + p.K) * g.Cout + n0 + tid] = s_b[tid];
+    }
     const int row = (warp & 3) * 32 + lane;
     const int kidx = 128 * kt + row;
     float* dst = p.partial + ((size_t)split * (p.K + 1) + (kidx < p.K ? kidx : 0)) * g.Cout + n0;
@@ -299,16 +354,16 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
       constexpr uint32_t FMT = F16 ? 0u : 2u;
       const uint32_t idesc = instr_desc(FMT, 128, BN) | (1u << 15) | (1u << 16);
       const uint32_t idesc2 = instr_desc(FMT, 128, 2 * BN) | (1u << 15) | (1u << 16);
-      constexpr int KSTEPS = F16 ? 2 : 4;     // per 32-pixel stage: 16 (fp16) or 8 (tf32) pixels per MMA
+      constexpr int KSTEPS = F16 ? PIXS / 16 : 4;     // per stage: 16 (fp16) or 8 (tf32) pixels per MMA
       for (int st = 0; st < n_stages; ++st) {
         const int s = st % S;
         const uint32_t ph = (uint32_t)(st / S) & 1u;
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t base = smem_u32(tiles + (size_t)s * STAGE);
-        const uint64_t a_hi = F16 ? smem_desc_mn_sw128_h(base) : smem_desc_mn_sw128(base);
-        const uint64_t a_lo = F16 ? smem_desc_mn_sw128_h(base + A_PART) : smem_desc_mn_sw128(base + A_PART);
-        const uint64_t b_hi = F16 ? smem_desc_mn_sw128_h(base + 2 * A_PART) : smem_desc_mn_sw128(base + 2 * A_PART);
+        const uint64_t a_hi = F16 ? smem_desc_mn_sw128_h(base, GRP) : smem_desc_mn_sw128(base);
+        const uint64_t a_lo = F16 ? smem_desc_mn_sw128_h(base + A_PART, GRP) : smem_desc_mn_sw128(base + A_PART);
+        const uint64_t b_hi = F16 ? smem_desc_mn_sw128_h(base + 2 * A_PART, GRP) : smem_desc_mn_sw128(base + 2 * A_PART);
 #pragma unroll
         for (int kk = 0; kk < KSTEPS; ++kk) {
           const uint64_t adv = (uint64_t)(kk * ((F16 ? 2048 : 1024) >> 4));   // next pixel group of one MMA
@@ -373,8 +428,9 @@ static int plan(const PcConvGeom* g, int* splits, int* rps) {
   const int max_sp = (int)(M / (PIX * 8) > 0 ? M / (PIX * 8) : 1);
   if (sp > max_sp) sp = max_sp;
   if (sp < 1) sp = 1;
+  const int pixs = g->Cin == 1 ? 64 : PIX;
   int r = ceil_div(M, sp);
-  r = ceil_div(r, PIX) * PIX;
+  r = ceil_div(r, pixs) * pixs;
   sp = ceil_div(M, r);
   *splits = sp;
   *rps = r;
@@ -388,6 +444,14 @@ using namespace pc;
 using namespace pc::tcwg;
 
 namespace pc { void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream); }
+
+// single-channel stem on the FP16X2 tiles: taps as the (padded) M rows
+extern "C" int pc_conv_wgrad_tc_stem_supported(const PcConvGeom* g) {
+  if (g == nullptr || g->Cin != 1) return 0;
+  const long long M = (long long)g->B * g->Ho * g->Wo;
+  return (g->R == g->S && g->R * g->S <= 64 && g->stride == 1 && g->pad == g->R / 2 && (g->Cout == 32 || g->Cout == 64) &&
+          M * g->Cout < (1LL << 31)) ? 1 : 0;
+}
 
 extern "C" int pc_conv_wgrad_tc_supported(const PcConvGeom* g) {
   if (g == nullptr) return 0;
@@ -409,7 +473,9 @@ extern "C" size_t pc_conv_wgrad_tc_workspace(const PcConvGeom* g) {
 extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw, float* db,
                                 void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream) {
   PC_REQUIRE(x && dy && g && dw_oihw && workspace, PC_EINVAL, "pc_conv_wgrad_tc: null pointer");
-  PC_REQUIRE(pc_conv_wgrad_tc_supported(g), PC_EUNSUPPORTED, "pc_conv_wgrad_tc: shape not covered (Cin %% 32, Cout %% 4)");
+  const bool stem = g->Cin == 1;
+  PC_REQUIRE(stem ? (prec == PC_PREC_FP16X2 && pc_conv_wgrad_tc_stem_supported(g)) : pc_conv_wgrad_tc_supported(g), PC_EUNSUPPORTED,
+             "pc_conv_wgrad_tc: shape not covered (Cin %% 32, Cout %% 4; single-channel stem: FP16X2, k*k <= 64, Cout 32|64)");
   PC_REQUIRE(workspace_bytes >= pc_conv_wgrad_tc_workspace(g), PC_EINVAL, "pc_conv_wgrad_tc: workspace too small");
   int sp, rps;
   const int bn = plan(g, &sp, &rps);
@@ -420,9 +486,9 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
   p.K = g->R * g->S * g->Cin;
   p.M = g->B * g->Ho * g->Wo;
   p.rows_per_split = rps;
-  const bool f16 = prec == PC_PREC_FP16X2 && g->Cin % 64 == 0;   // 64-channel groups; otherwise the TF32x3 tiles
+  const bool f16 = prec == PC_PREC_FP16X2 && (g->Cin % 64 == 0 || stem);   // 64-channel groups; otherwise the TF32x3 tiles
   p.dy_amax = f16 ? dy_amax : nullptr;
-  const uint32_t st = bn == 64 ? (f16 ? stage_bytes<64, true>() : stage_bytes<64, false>())
+  const uint32_t st = stem ? stage_bytes<64, true, true>() : bn == 64 ? (f16 ? stage_bytes<64, true>() : stage_bytes<64, false>())
                                : (f16 ? stage_bytes<128, true>() : stage_bytes<128, false>());
   int stages = (int)(SMEM_BUDGET / st);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -440,7 +506,14 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
     }                                                                                                                      \
     launch_pdl(wgrad_tc_kernel<BN_, 3, 1, F16_>, grid, dim3(32 * 13), smem, stream, p);                                    \
   } while (0)
-  if (bn == 64) {
+  if (stem) {
+    static size_t conf = 0;
+    if (smem > conf) {
+      PC_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<64, 3, 1, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      conf = smem;
+    }
+    launch_pdl(wgrad_tc_kernel<64, 3, 1, true, true>, grid, dim3(32 * 13), smem, stream, p);
+  } else if (bn == 64) {
     if (f16) PC_WG_LAUNCH(64, true); else PC_WG_LAUNCH(64, false);
   } else {
     if (f16) PC_WG_LAUNCH(128, true); else PC_WG_LAUNCH(128, false);
@@ -449,6 +522,11 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
   PC_LAUNCH_CHECK("wgrad_tc_kernel");
   // bias gradient: per-CTA column sums of dy -> bias rows of the partial buffer (one row per colsum CTA, appended after the
   // split partials), then the common reduce
+  if (stem) {     // the stem kernel wrote its own bias rows
+    launch_wgrad_reduce(p.partial, sp, g->R, g->S, g->Cin, g->Cout, dw_oihw, db, stream);
+    PC_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
+    return PC_OK;
+  }
   float* cs = p.partial + (size_t)sp * (size_t)(p.K + 1) * g->Cout;
   const int cs_ctas = kNumSMs * 2;
   launch_pdl(colsum_kernel, dim3(cs_ctas), dim3(256), 0, stream, dy, p.M, g->Cout, cs);

@@ -107,6 +107,25 @@ def test_tc_conv_wgrad(case, prec):
     assert float((db.double() - br.grad).abs().max() / br.grad.abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize("B,H,W,Cout,k", [(3, 40, 101, 64, 7), (2, 17, 33, 32, 7), (2, 40, 50, 64, 3), (1, 9, 12, 64, 7)])
+def test_tc_stem_wgrad(B, H, W, Cout, k):
+    """Single-channel stem weight gradient on the tensor cores (taps as M rows, FP16X2) vs torch fp64."""
+    from phoneme_contrast_b200 import ops
+    g = ops.conv_geom(B, H, W, 1, Cout, k, 1, k // 2)
+    gen = torch.Generator(device=DEV).manual_seed(B * 13 + Cout + k)
+    x = torch.randn(B, H, W, 1, device=DEV, generator=gen) * 3.0
+    dy = torch.randn(B, H, W, Cout, device=DEV, generator=gen) * 2e-7
+    amax = dy.abs().max().reshape(1)
+    dw, db = ops.conv_wgrad(x, dy, g, None, prec=3, dy_amax=amax)
+    wr = torch.zeros(Cout, 1, k, k, device=DEV, dtype=torch.float64, requires_grad=True)
+    br = torch.zeros(Cout, device=DEV, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), wr, br, padding=k // 2).backward(dy.permute(0, 3, 1, 2).double())
+    assert float((dw.double() - wr.grad).abs().max() / wr.grad.abs().max()) < TOL[3]
+    assert float((db.double() - br.grad).abs().max() / br.grad.abs().max()) < 1e-5
+    dw0, _ = ops.conv_wgrad(x, dy, g, None, prec=0)       # exact-fp32 SIMT stem kernel
+    assert float((dw - dw0).abs().max() / dw0.abs().max()) < TOL[3]
+
+
 @pytest.mark.parametrize("precision", ["tf32x3", "fp16x2"])
 @pytest.mark.parametrize("arch,B", [("phoneme_cnn", 16), ("phoneme_cnn_deep", 8)])
 def test_nets_split_precision_match_oracle(arch, B, precision, monkeypatch):
