@@ -47,12 +47,11 @@ constexpr int kNumSMs = 148;  // B200
 // Contract for every kernel launched this way: NO global-memory access before pdl_wait(). pdl_trigger() lets the NEXT
 // kernel on the stream start being scheduled; kernels that allocate TMEM call it only after their allocation so that a
 // dependent CTA can never take TMEM columns ahead of a CTA it (transitively) waits for.
-// Opt-in with PC_PDL=1 (A/B switch). Measured on the cnn_deep step (CUDA graph, side-stream wgrad): 6.60 ms with PDL vs
-// 6.51 ms without - the early-resident CTAs take SM slots the overlapped weight-gradient lane would otherwise fill - so
-// the default is plain stream-ordered launches; griddepcontrol.* are no-ops then.
+// Used for eager launches; inside a stream capture plain launches measured faster (see pdl_enabled in abi.cu; PC_PDL=0/1
+// overrides). griddepcontrol.* are no-ops for a kernel launched without the attribute.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled();
+bool pdl_enabled(cudaStream_t stream);
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
@@ -65,7 +64,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_enabled(stream) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -2,6 +2,7 @@
 
   python profiles/summarize.py launches <launches.csv> <out.md> [title]
   python profiles/summarize.py full <prof.ncu-rep> <out.md> [title]
+  python profiles/summarize.py rawcsv <raw.csv> <out.md> [title]      (raw.csv = `ncu -i prof.ncu-rep --page raw --csv`, exported on the GPU box)
 """
 import collections
 import csv
@@ -41,12 +42,12 @@ def launches(path, out, title):
             f.write(f"| {100 * a[1] / tot:.2f}% | {a[1]:.1f} | {a[0]} | `{k[:120]}` |\n")
 
 
-def full(path, out, title):
-    txt = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def full(path, out, title, raw_csv=False):
+    txt = open(path).read() if raw_csv else subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(txt.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     with open(out, "w") as f:
-        f.write(f"# {title}\n\nSource: `ncu --set full --clock-control none --import-source on` ({path.split('/')[-1]}).\n\n")
+        f.write(f"# {title}\n\nSource: `ncu --set full --clock-control none` ({path.split('/')[-1]}).\n\n")
         for r in data:
             f.write(f"## `{r[hdr.index('Kernel Name')][:100]}`\n\n| metric | value | unit |\n|---|---:|---|\n")
             for m in FULL_METRICS:
@@ -61,4 +62,7 @@ def full(path, out, title):
 if __name__ == "__main__":
     kind, path, out = sys.argv[1:4]
     title = sys.argv[4] if len(sys.argv) > 4 else path
-    (launches if kind == "launches" else full)(path, out, title)
+    if kind == "launches":
+        launches(path, out, title)
+    else:
+        full(path, out, title, raw_csv=(kind == "rawcsv"))
