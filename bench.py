@@ -153,9 +153,9 @@ def bench_train(workload, steps, warmup, parallel, device, want_profile=True, us
     rank = 0 if parallel is None else parallel.rank
     world = 1 if parallel is None else parallel.world_size
     tr = build_trainer(arch, device, parallel)
-    # multi-rank steps run eagerly: capturing the NCCL collectives of the sharded loss in the step graph deadlocked under
-    # torchrun in round 1 (not yet root-caused), so the graph path is single-GPU only for now
-    use_graph = bool(use_graph) and parallel is None
+    # multi-rank steps replay four captured segments with the NCCL exchanges issued eagerly between them (training/graph.py:
+    # GraphedDPStep); capturing the collectives themselves in one whole-step graph deadlocked under torchrun
+    use_graph = bool(use_graph)
     tr.config["cuda_graph"] = use_graph
     xs_h, y_h = train_inputs(views, 1000 + rank, device)
     xs = [x.to(device) for x in xs_h]
@@ -499,7 +499,7 @@ def main():
                 "config": {"workload": wl["desc"], "views_per_gpu": r["views"], "global_views": r["views"] * world,
                            "parallelism": f"dp{world}: all_gather(embeddings, labels, row stats) + flat-bucket gradient all-reduce; per-rank BatchNorm statistics",
                            "precision": "fp32 storage and accumulate; convolutions on tcgen05 tensor cores with fp32 operands split into fp16 hi + lo (3 products per pair, ~22-bit operands: fp32-level accuracy, parity-tested at 1e-4), exact-fp32 SIMT for the Cin=1 stem",
-                           "launch": "eager launches" if (args.no_graph or world > 1) else "whole step captured in one CUDA graph (inputs copied into static buffers each step)",
+                           "launch": "eager launches" if args.no_graph else ("whole step captured in one CUDA graph (inputs copied into static buffers each step)" if world == 1 else "four captured graph segments per step with the 5 NCCL exchanges issued eagerly between them"),
                            "l2": "no explicit flush: each step streams ~2 GB of activations (>> 126 MB L2); inputs rotate over 4 device buffers",
                            "step_tflops": FLOP_PER_SAMPLE[r["arch"]] * r["views"] / (r["ms_per_step"] * 1e-3) / 1e12,
                            "final_loss": r["loss"]}}

@@ -83,16 +83,41 @@ attn_pool_bwd_kernel(const float* __restrict__ a, const float* __restrict__ gate
 
 // ------------------------------------------------------------------------------------------------ projection head
 // ws layout (floats): z [B*N] | mean [N] | invstd [N] | scratch [B*N]
-__global__ void head_linear_kernel(const float* __restrict__ x, int B, int K, int N, const float* __restrict__ W,
-                                   const float* __restrict__ bias, float* __restrict__ z) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= B * N) return;
-  const int n = idx % N, b = idx / N;
+// z[b][n] = x[b][:] . W[n][:] + bias[n]: one warp per (b, 4 consecutive n); lanes stride over K with float4 loads, so x and W
+// rows are read as full 512-byte lines and the x row is shared by the four outputs.
+__global__ void __launch_bounds__(256)
+head_linear_kernel(const float* __restrict__ x, int B, int K, int N, const float* __restrict__ W,
+                   const float* __restrict__ bias, float* __restrict__ z, int vec4) {
+  const int lane = threadIdx.x & 31;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int n4 = (N + 3) >> 2;
+  if (gw >= B * n4) return;
+  const int b = gw / n4, n0 = (gw - b * n4) * 4;
+  float s[4] = {0.f, 0.f, 0.f, 0.f};
   const float* xr = x + (size_t)b * K;
-  const float* wr = W + (size_t)n * K;
-  float s = 0.f;
-  for (int k = 0; k < K; ++k) s = fmaf(xr[k], wr[k], s);
-  z[idx] = s + (bias != nullptr ? bias[n] : 0.f);
+  if (vec4) {     // K % 4 == 0 and both base pointers 16-byte aligned (parameters may be views into a flat buffer)
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 xv = *reinterpret_cast<const float4*>(xr + k);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (n0 + q < N) {
+          const float4 wv = *reinterpret_cast<const float4*>(W + (size_t)(n0 + q) * K + k);
+          s[q] = fmaf(xv.x, wv.x, fmaf(xv.y, wv.y, fmaf(xv.z, wv.z, fmaf(xv.w, wv.w, s[q]))));
+        }
+      }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (n0 + q < N) s[q] = fmaf(xr[k], W[(size_t)(n0 + q) * K + k], s[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) s[q] = warp_sum(s[q]);
+  if (lane < 4 && n0 + lane < N) {
+    const float v = lane == 0 ? s[0] : (lane == 1 ? s[1] : (lane == 2 ? s[2] : s[3]));
+    z[(size_t)b * N + n0 + lane] = v + (bias != nullptr ? bias[n0 + lane] : 0.f);
+  }
 }
 
 // one CTA (128 threads) per feature n: batch statistics (two-pass) + running-stat update
@@ -225,13 +250,26 @@ head_bn_bwd_kernel(float* __restrict__ dzn, const float* __restrict__ z, int B, 
 }
 
 // dW[n,k] = sum_b dz[b,n] x[b,k]
-__global__ void head_dw_kernel(const float* __restrict__ dz, const float* __restrict__ x, int B, int K, int N, float* __restrict__ dW) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N * K) return;
-  const int k = idx % K, n = idx / K;
-  float s = 0.f;
-  for (int b = 0; b < B; ++b) s = fmaf(dz[(size_t)b * N + n], x[(size_t)b * K + k], s);
-  dW[idx] = s;
+// dW[n][k] = sum_b dz[b][n] x[b][k]: block = 128 consecutive k of one n x 4 batch quarters (fixed-order smem reduce: deterministic)
+__global__ void __launch_bounds__(512)
+head_dw_kernel(const float* __restrict__ dz, const float* __restrict__ x, int B, int K, int N, float* __restrict__ dW) {
+  __shared__ float part[4][128];
+  const int kx = threadIdx.x & 127, by = threadIdx.x >> 7;
+  const int kblocks = (K + 127) / 128;
+  const int n = blockIdx.x / kblocks, k = (blockIdx.x - n * kblocks) * 128 + kx;
+  const int bq = (B + 3) / 4, b0 = by * bq, b1 = min(B, b0 + bq);
+  float s0 = 0.f, s1 = 0.f;
+  if (k < K) {
+    int b = b0;
+    for (; b + 1 < b1; b += 2) {
+      s0 = fmaf(dz[(size_t)b * N + n], x[(size_t)b * K + k], s0);
+      s1 = fmaf(dz[(size_t)(b + 1) * N + n], x[(size_t)(b + 1) * K + k], s1);
+    }
+    if (b < b1) s0 = fmaf(dz[(size_t)b * N + n], x[(size_t)b * K + k], s0);
+  }
+  part[by][kx] = s0 + s1;
+  __syncthreads();
+  if (by == 0 && k < K) dW[(size_t)n * K + k] = (part[0][kx] + part[1][kx]) + (part[2][kx] + part[3][kx]);
 }
 // dx[b,k] = sum_n dz[b,n] W[n,k]
 __global__ void head_dx_kernel(const float* __restrict__ dz, const float* __restrict__ W, int B, int K, int N, float* __restrict__ dx) {
@@ -283,7 +321,8 @@ extern "C" int pc_head_fwd(const float* x, int B, int K, int N, const float* W, 
   float* z = static_cast<float*>(ws);
   float* mean = z + (size_t)B * N;
   float* invstd = mean + N;
-  head_linear_kernel<<<ceil_div((long long)B * N, 128), 128, 0, stream>>>(x, B, K, N, W, bias, z);
+  const int vec4 = ((K & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W)) & 15) == 0) ? 1 : 0;
+  head_linear_kernel<<<ceil_div((long long)B * ((N + 3) / 4), 8), 256, 0, stream>>>(x, B, K, N, W, bias, z, vec4);
   PC_LAUNCH_CHECK("head_linear_kernel");
   head_bn_stats_kernel<<<N, 128, 0, stream>>>(z, B, N, running_mean, running_var, num_batches_tracked, momentum, eps, training, mean, invstd);
   PC_LAUNCH_CHECK("head_bn_stats_kernel");
@@ -304,7 +343,7 @@ extern "C" int pc_head_bwd(const float* demb, const float* x, int B, int K, int 
   PC_LAUNCH_CHECK("head_normalize_bwd_kernel");
   head_bn_bwd_kernel<<<N, 128, 0, stream>>>(dz, z, B, N, mean, invstd, gamma, training, dgamma, dbeta, dbias);
   PC_LAUNCH_CHECK("head_bn_bwd_kernel");
-  head_dw_kernel<<<ceil_div((long long)N * K, 128), 128, 0, stream>>>(dz, x, B, K, N, dW);
+  head_dw_kernel<<<N * ceil_div(K, 128), 512, 0, stream>>>(dz, x, B, K, N, dW);
   PC_LAUNCH_CHECK("head_dw_kernel");
   head_dx_kernel<<<ceil_div((long long)B * K, 128), 128, 0, stream>>>(dz, W, B, K, N, dx);
   PC_LAUNCH_CHECK("head_dx_kernel");

@@ -94,11 +94,12 @@ class ContrastiveTrainer:
     def step(self, views: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         """train_step, replayed from a captured CUDA graph when config["cuda_graph"] is set and the batch shape is static
         (ContrastiveBatchSampler batches are); falls back to the eager path for odd-shaped batches."""
-        if not self.config.get("cuda_graph") or not isinstance(self.optimizer, FusedClipAdam) or self.parallel is not None:
-            return self.train_step(views, labels)      # (graph capture of the NCCL exchanges is not enabled yet)
+        if not self.config.get("cuda_graph") or not isinstance(self.optimizer, FusedClipAdam):
+            return self.train_step(views, labels)
         if self._graphed is None:
-            from .graph import GraphedTrainStep
-            self._graphed = GraphedTrainStep(self, views, labels)
+            from .graph import GraphedDPStep, GraphedTrainStep
+            # data parallel: four captured segments with the NCCL exchanges issued eagerly between them
+            self._graphed = (GraphedDPStep if self.parallel is not None else GraphedTrainStep)(self, views, labels)
         if self._graphed.matches(views, labels):
             return self._graphed(views, labels)
         return self.train_step(views, labels)

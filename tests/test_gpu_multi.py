@@ -58,6 +58,21 @@ def _worker(rank, world, port, out):
         res["step_loss"] = float(tr.train_step(x, yl))
         res["param_sum"] = float(opt.flat_p.double().sum())
         res["params"] = opt.flat_p.cpu()
+        # the same two steps through the graphed data-parallel step (four captured segments + eager NCCL) and eagerly:
+        # exact-fp32 kernels so both trajectories are deterministic
+        cfg32 = {"dropout_rate": 0.0, "precision": "fp32"}
+        finals = []
+        for graph in (False, True):
+            m2 = model_registry.create("phoneme_cnn", cfg32).to(dev)
+            m2.load_state_dict(nets_oracle.synthetic_state_dict("phoneme_cnn", cfg32, seed=2))
+            o2 = FusedClipAdam(m2.parameters(), lr=1e-3)
+            t2 = ContrastiveTrainer(m2, [], None, get_loss_fn("supervised_contrastive", temperature=0.15), o2, None, torch.device(dev),
+                                    {"gradient_clip_val": 1.0, "progress": False, "cuda_graph": graph}, tempfile.mkdtemp(),
+                                    logging.getLogger("t"), parallel=ctx)
+            m2.train()
+            losses = [float(t2.step(x, yl)), float(t2.step(x * 0.5, yl))]
+            finals.append((losses, o2.flat_p.cpu(), o2._step, int(o2._step_dev.item())))
+        res["graph_vs_eager"] = finals
         torch.save(res, os.path.join(out, f"r{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -84,3 +99,13 @@ def test_dp_two_gpus_match_single_process(tmp_path):
         assert np.abs(o["grad"].numpy() - want_grad[r * n:(r + 1) * n]).max() <= 1e-4 * np.abs(want_grad).max()
     assert outs[0]["step_loss"] == outs[1]["step_loss"]
     assert torch.equal(outs[0]["params"], outs[1]["params"])
+    # graphed data-parallel step == eager data-parallel step (same losses; parameters identical up to the order-dependent last
+    # bit of the fp64 BatchNorm statistics, cf. test_cuda_graph_step_matches_eager), on every rank, step counters advanced
+    for o in outs:
+        (l_e, p_e, s_e, d_e), (l_g, p_g, s_g, d_g) = o["graph_vs_eager"]
+        np.testing.assert_allclose(l_e, l_g, rtol=1e-5)
+        n_off = int(((p_e - p_g).abs() > 2e-5).sum())
+        assert n_off <= 3e-3 * p_e.numel(), (n_off, p_e.numel())
+        assert float((p_e - p_g).abs().max()) <= 2 * 1e-3 * 2
+        assert (s_e, d_e, s_g, d_g) == (2, 2, 2, 2)
+    assert torch.equal(outs[0]["graph_vs_eager"][1][1], outs[1]["graph_vs_eager"][1][1])
