@@ -110,6 +110,15 @@ int pc_supcon_bwd(const float* F, const int64_t* labels, const float* mask, int 
                   float temperature, float coef, const float* grad_scale, const float* stats_all, float* dF,
                   pc_stream_t stream);
 
+/* Tensor-core (tcgen05, FP16x2 operand split) forward of the label form: same outputs as pc_supcon_fwd. Eligible when
+ * pc_supcon_tc_supported() != 0 (N >= 128, D = 64 | 128, row0 % 8 == 0); workspace >= pc_supcon_tc_workspace(N, D, nrows)
+ * bytes, 128-byte aligned (packed fp16 hi/lo image of F + per-column-split partial row statistics). */
+int pc_supcon_tc_supported(int N, int D, int row0, int nrows);
+size_t pc_supcon_tc_workspace(int N, int D, int nrows);
+int pc_supcon_fwd_tc(const float* F, const int64_t* labels, int N, int D, int row0, int nrows, float temperature,
+                     float base_temperature, void* workspace, size_t workspace_bytes, float* stats, float* row_loss,
+                     pc_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3. CNN building blocks (PhonemeNet / PhonemeNetDeep forward + backward)
  *    replaces: nn.Conv2d / BatchNorm2d / ReLU / MaxPool2d / Dropout2d / SpatialAttention /

@@ -348,6 +348,16 @@ def supcon_fwd(feats, labels, mask, temperature, base_temperature, row0=0, nrows
     nrows = N - row0 if nrows is None else nrows
     stats = torch.empty(nrows, 4, device=feats.device, dtype=F32)
     row_loss = torch.empty(nrows, device=feats.device, dtype=F32)
+    import os
+    # large label-form problems: similarity tiles on the tensor cores (csrc/supcon_tc.cu); PC_SUPCON_TC=0 / 1 forces the choice
+    tc_env = os.environ.get("PC_SUPCON_TC")
+    if (mask is None and labels is not None and tc_env != "0" and (N >= 1024 or tc_env == "1")
+            and L.lib().pc_supcon_tc_supported(N, D, row0, nrows)):
+        nbytes = int(L.lib().pc_supcon_tc_workspace(N, D, nrows))
+        ws = _workspace(nbytes, feats.device)
+        call("pc_supcon_fwd_tc", ptr(feats), ptr(labels, torch.int64), N, D, row0, nrows, float(temperature), float(base_temperature),
+             ptr(ws, torch.uint8), ws.numel(), ptr(stats), ptr(row_loss), stream())
+        return stats, row_loss
     call("pc_supcon_fwd", ptr(feats), ptr(labels, torch.int64), ptr(mask), N, D, row0, nrows, float(temperature),
          float(base_temperature), ptr(stats), ptr(row_loss), stream())
     return stats, row_loss
