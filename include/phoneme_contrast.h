@@ -118,6 +118,12 @@ size_t pc_supcon_tc_workspace(int N, int D, int nrows);
 int pc_supcon_fwd_tc(const float* F, const int64_t* labels, int N, int D, int row0, int nrows, float temperature,
                      float base_temperature, void* workspace, size_t workspace_bytes, float* stats, float* row_loss,
                      pc_stream_t stream);
+/* Tensor-core backward of the label form: same dF as pc_supcon_bwd (S recomputed per tile in TMEM, W' = dL/dS turned into the
+ * fp16 hi/lo A operand of a second MMA that accumulates dF in TMEM; column splits reduced in a fixed order). */
+size_t pc_supcon_bwd_tc_workspace(int N, int D, int nrows);
+int pc_supcon_bwd_tc(const float* F, const int64_t* labels, int N, int D, int row0, int nrows, float temperature, float coef,
+                     const float* grad_scale, const float* stats_all, void* workspace, size_t workspace_bytes, float* dF,
+                     pc_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 3. CNN building blocks (PhonemeNet / PhonemeNetDeep forward + backward)

@@ -60,6 +60,8 @@ SIGNATURES = {
     "pc_supcon_tc_supported": (i32, [i32, i32, i32, i32]),
     "pc_supcon_tc_workspace": (sz, [i32, i32, i32]),
     "pc_supcon_fwd_tc": (i32, [vp, vp, i32, i32, i32, i32, f32, f32, vp, sz, vp, vp, vp]),
+    "pc_supcon_bwd_tc_workspace": (sz, [i32, i32, i32]),
+    "pc_supcon_bwd_tc": (i32, [vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, sz, vp, vp]),
     "pc_pack_conv_weight": (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),
     "pc_conv_tc_supported": (i32, [C.POINTER(PcConvGeom), i32, i32]),
     "pc_conv_tc_packed_bytes": (sz, [i32, i32, i32, i32, i32, i32]),

@@ -256,6 +256,286 @@ __global__ void __launch_bounds__(256) supcon_merge_kernel(const float* __restri
   row_loss[r] = -t_ratio * (spos - npos * logf(d)) / nn;
 }
 
+// ---------------------------------------------------------------------------------------------------------------- backward
+// dF_i = (c / T) * sum_{j != i} w'_ij F_j,   w'_ij = e_ij - [y_i == y_j] (1/n_i + 1/n_j),
+// e_ij = exp(z_ij - m_i) / den_i + exp(z_ij - m_j) / den_j          (same algebra as supcon_bwd_kernel in supcon.cu)
+//
+// Per column tile: MMA1 forms S = F_i F_j^T in TMEM columns [0,256); the epilogue warps turn it into W' (fp32), split it into
+// fp16 hi | lo and store it as the K-major A operand of MMA2; MMA2 accumulates dF[128 x D] += W'[128 x 64] F_j[64 x D] into
+// TMEM columns [256,512). The B operand of MMA2 is the SAME shared-memory tile MMA1 used: a [64 rows j][128 B = 64 d] block
+// with the 128-byte swizzle is a K-major operand when its rows are the N index (MMA1) and an MN-major operand when its rows
+// are the K index (MMA2), so F_j is fetched once. With LBO = 8 KB one N = 2D MMA walks [hi g0 | lo g0 | hi g1 | lo g1]
+// (g = 64-wide d group), i.e. main and correction columns interleave per group; the w_lo * b_hi term is one N = 64 MMA per group.
+struct BwdParams {
+  const unsigned char* Fp;
+  const long long* labels;
+  const float* stats_all;      // [N][4] (m, den, n_pos, s_pos) of ALL rows
+  const float* grad_scale;     // device scalar or null
+  float* partial;              // [splits][nrows][D]
+  int N, Npad, KC, D, row0, nrows, col_tiles, tiles_per_split;
+  float invT, coef;
+};
+
+__device__ __forceinline__ uint64_t smem_desc_mn_h(uint32_t smem_addr_bytes, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr_bytes >> 4) & 0x3FFF);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;     // next 64-wide d group
+  d |= (uint64_t)(1024 >> 4) << 32;          // next 8 rows (K direction)
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+constexpr int NSTB = 2;
+
+__global__ void __launch_bounds__(THREADS, 1) supcon_bwd_tc_kernel(const BwdParams p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int KC = p.KC;
+  const uint32_t A_BYTES = (uint32_t)KC * 2u * 16384u, B_STAGE = (uint32_t)KC * 2u * 8192u;
+  unsigned char* a_tile = smem;
+  unsigned char* b_ring = a_tile + A_BYTES;                         // [NSTB][KC][hi|lo][64 rows][128 B]
+  unsigned char* w_buf = b_ring + (size_t)NSTB * B_STAGE;           // [2][hi|lo][128 rows][128 B]
+  float4* cs_f = reinterpret_cast<float4*>(w_buf + 2 * 32768);      // [2][64] (m2_j, h_j/den_j, 1/n_j, -)
+  long long* cs_y = reinterpret_cast<long long*>(cs_f + 2 * BN);    // [2][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cs_y + 2 * BN);
+  uint64_t* a_full = bars;
+  uint64_t* b_full = bars + 1;            // [NSTB]
+  uint64_t* b_empty = b_full + NSTB;      // [NSTB]
+  uint64_t* s_full = b_empty + NSTB;      // [1]
+  uint64_t* s_empty = s_full + 1;         // [1]
+  uint64_t* w_full = s_empty + 1;         // [2]
+  uint64_t* w_empty = w_full + 2;         // [2]
+  uint64_t* d_full = w_empty + 2;         // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(d_full + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int i0 = p.row0 + blockIdx.x * BM;
+  const int t_begin = blockIdx.y * p.tiles_per_split;
+  const int n_tiles = min(p.col_tiles, t_begin + p.tiles_per_split) - t_begin;
+
+  if (warp == EPI_WARPS) {
+    if (lane == 0) {
+      mbar_init(a_full, 1);
+      for (int s = 0; s < NSTB; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+      mbar_init(s_full, 1);
+      mbar_init(s_empty, 32 * EPI_WARPS);
+      for (int b = 0; b < 2; ++b) { mbar_init(&w_full[b], 32 * EPI_WARPS); mbar_init(&w_empty[b], 1); }
+      mbar_init(d_full, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr float kLog2e = 1.4426950408889634f;
+
+  if (warp < EPI_WARPS) {
+    // ============================================================ S -> W' (thread = row, column half), then the dF read-out
+    const int r = (warp & 3) * 32 + lane, half = warp >> 2;
+    const int i = i0 + r;
+    float mi2 = 0.f, idi = 0.f, ini = 0.f;
+    long long yi = 0;
+    if (i < p.N) {
+      const float4 st = *reinterpret_cast<const float4*>(p.stats_all + (size_t)i * 4);
+      mi2 = st.x * kLog2e;
+      idi = (st.z != 0.f ? 1.f : 0.f) / st.y;
+      ini = st.z != 0.f ? 1.f / st.z : 0.f;
+      yi = p.labels[i];
+    }
+    const float c2 = p.invT * kLog2e;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int jt = (t_begin + t) * BN;
+      const int cb = t & 1;
+      if (tid < BN) {                       // column statistics of this tile -> shared memory
+        const int j = jt + tid;
+        float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+        long long y = 0;
+        if (j < p.N) {
+          const float4 st = *reinterpret_cast<const float4*>(p.stats_all + (size_t)j * 4);
+          c = make_float4(st.x * kLog2e, (st.z != 0.f ? 1.f : 0.f) / st.y, st.z != 0.f ? 1.f / st.z : 0.f, 0.f);
+          y = p.labels[j];
+        }
+        cs_f[cb * BN + tid] = c;
+        cs_y[cb * BN + tid] = y;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+      mbar_wait(s_full, (uint32_t)t & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(half * 32);
+      uint32_t raw[32];
+      float v[32], u[32];
+      tmem_ld_32x32(taddr, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] = __uint_as_float(raw[q]);
+      tmem_ld_32x32(taddr + 128, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] += __uint_as_float(raw[q]);
+      tmem_ld_32x32(taddr + 64, raw);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 32; ++q) u[q] = __uint_as_float(raw[q]);
+      tmem_ld_32x32(taddr + 192, raw);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_empty);                 // S may be overwritten by MMA1 of the next tile
+      const float4* cf = cs_f + cb * BN + half * 32;
+      const long long* cy = cs_y + cb * BN + half * 32;
+#pragma unroll
+      for (int q = 0; q < 32; ++q) {
+        const int j = jt + half * 32 + q;
+        const float z2 = fmaf(u[q] + __uint_as_float(raw[q]), kF16LoInv, v[q]) * c2;
+        const float4 c = cf[q];
+        float w = exp2f(z2 - mi2) * idi + exp2f(z2 - c.x) * c.y;
+        if (yi == cy[q]) w -= ini + c.z;
+        v[q] = (i < p.N && j < p.N && j != i) ? w : 0.f;
+      }
+      mbar_wait(&w_empty[cb], (((uint32_t)t >> 1) & 1u) ^ 1u);
+      unsigned char* w_hi = w_buf + (size_t)cb * 32768 + (size_t)r * 128;
+      unsigned char* w_lo = w_hi + 16384;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint4 h, l;
+        split_f16x2(v[8 * k + 0], v[8 * k + 1], h.x, l.x);
+        split_f16x2(v[8 * k + 2], v[8 * k + 3], h.y, l.y);
+        split_f16x2(v[8 * k + 4], v[8 * k + 5], h.z, l.z);
+        split_f16x2(v[8 * k + 6], v[8 * k + 7], h.w, l.w);
+        const uint32_t off = (uint32_t)(((half * 4 + k) ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(w_hi + off) = h;
+        *reinterpret_cast<uint4*>(w_lo + off) = l;
+      }
+      fence_proxy_async();
+      mbar_arrive(&w_full[cb]);
+    }
+    // ---- read-out: thread (row, half) owns d group `half` (64 columns) of its row
+    if (n_tiles > 0) {
+      mbar_wait(d_full, 0);
+      tc_fence_after();
+    }
+    const float scale = p.coef * (p.grad_scale != nullptr ? p.grad_scale[0] : 1.f) * p.invT;
+    const int lr = blockIdx.x * BM + r;
+    if (half < KC) {
+#pragma unroll 1
+      for (int cc = 0; cc < 2; ++cc) {
+        float v[32];
+        if (n_tiles > 0) {
+          uint32_t raw[32], rc[32];
+          const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(256 + half * 128 + cc * 32);
+          tmem_ld_32x32(taddr, raw);
+          tmem_ld_32x32(taddr + 64, rc);
+          tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = fmaf(__uint_as_float(rc[q]), kF16LoInv, __uint_as_float(raw[q])) * scale;
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = 0.f;
+        }
+        if (lr < p.nrows && i < p.N) {
+          float* dst = p.partial + ((size_t)blockIdx.y * p.nrows + lr) * p.D + half * 64 + cc * 32;
+#pragma unroll
+          for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+        }
+      }
+    }
+  } else if (warp == EPI_WARPS) {
+    // ============================================================ MMA issuer
+    if (lane == 0 && n_tiles > 0) {
+      const uint32_t idesc_s = instr_desc(0u, BM, BN), idesc_s2 = instr_desc(0u, BM, 2 * BN);
+      const uint32_t idesc_d2 = instr_desc(0u, BM, 2 * 64 * KC) | (1u << 16);     // B MN-major, N = 2D
+      const uint32_t idesc_d1 = instr_desc(0u, BM, 64) | (1u << 16);
+      const uint32_t a_base = smem_u32(a_tile);
+      auto mma1 = [&](int t) {
+        const uint32_t b_base = smem_u32(b_ring + (size_t)(t % NSTB) * B_STAGE);
+        for (int kc = 0; kc < KC; ++kc) {
+          const uint64_t a_hi = smem_desc_sw128(a_base + (uint32_t)(kc * 2) * 16384u);
+          const uint64_t a_lo = smem_desc_sw128(a_base + (uint32_t)(kc * 2 + 1) * 16384u);
+          const uint64_t b_hi = smem_desc_sw128(b_base + (uint32_t)(kc * 2) * 8192u);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t adv = (uint64_t)(kk * 2);
+            const int ks = kc * 4 + kk;
+            const uint32_t d_set = tmem_base + (uint32_t)((ks & 1) * 128);
+            mma_bf16(d_set, a_hi + adv, b_hi + adv, idesc_s2, ks < 2 ? 0u : 1u);
+            mma_bf16(d_set + 64, a_lo + adv, b_hi + adv, idesc_s, 1u);
+          }
+        }
+      };
+      mbar_wait(a_full, 0);
+      mbar_wait(&b_full[0], 0);
+      tc_fence_after();
+      mma1(0);
+      mma_commit(s_full);
+      for (int t = 0; t < n_tiles; ++t) {
+        if (t + 1 < n_tiles) {
+          mbar_wait(&b_full[(t + 1) % NSTB], (uint32_t)((t + 1) / NSTB) & 1u);
+          mbar_wait(s_empty, (uint32_t)t & 1u);
+          tc_fence_after();
+          mma1(t + 1);
+          mma_commit(s_full);
+        }
+        const int cb = t & 1;
+        mbar_wait(&w_full[cb], ((uint32_t)t >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t w_hi = smem_u32(w_buf + (size_t)cb * 32768), w_lo = w_hi + 16384u;
+        const uint32_t b_base = smem_u32(b_ring + (size_t)(t % NSTB) * B_STAGE);
+        const uint64_t wa_hi = smem_desc_sw128(w_hi), wa_lo = smem_desc_sw128(w_lo);
+        const uint64_t b_all = smem_desc_mn_h(b_base, 8192u);           // [hi g0 | lo g0 | hi g1 | lo g1]
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint64_t adv_a = (uint64_t)(kk * 2), adv_b = (uint64_t)(kk * (2048 >> 4));
+          const uint32_t acc = (t == 0 && kk == 0) ? 0u : 1u;
+          mma_bf16(tmem_base + 256, wa_hi + adv_a, b_all + adv_b, idesc_d2, acc);
+          for (int g = 0; g < KC; ++g) {
+            const uint64_t b_g = smem_desc_mn_h(b_base + (uint32_t)g * 16384u, 8192u);
+            mma_bf16(tmem_base + 256 + (uint32_t)(g * 128 + 64), wa_lo + adv_a, b_g + adv_b, idesc_d1, 1u);
+          }
+        }
+        mma_commit(&b_empty[t % NSTB]);
+        mma_commit(&w_empty[cb]);
+      }
+      mma_commit(d_full);
+    }
+    __syncwarp();
+  } else {
+    // ============================================================ bulk-copy loader
+    if (lane == 0 && n_tiles > 0) {
+      const size_t part_stride = (size_t)p.Npad * 128;
+      mbar_arrive_expect_tx(a_full, A_BYTES);
+      for (int q = 0; q < KC * 2; ++q) bulk_g2s(a_tile + (size_t)q * 16384, p.Fp + (size_t)q * part_stride + (size_t)i0 * 128, 16384, a_full);
+      for (int t = 0; t < n_tiles; ++t) {
+        const int s = t % NSTB;
+        mbar_wait(&b_empty[s], ((uint32_t)(t / NSTB) & 1u) ^ 1u);
+        unsigned char* dst = b_ring + (size_t)s * B_STAGE;
+        const size_t j0 = (size_t)(t_begin + t) * BN;
+        mbar_arrive_expect_tx(&b_full[s], B_STAGE);
+        for (int q = 0; q < KC * 2; ++q) bulk_g2s(dst + (size_t)q * 8192, p.Fp + (size_t)q * part_stride + j0 * 128, 8192, &b_full[s]);
+      }
+    }
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == EPI_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
+// dF[r][:] = sum over column splits, in split order (deterministic)
+__global__ void __launch_bounds__(256) supcon_dF_reduce_kernel(const float* __restrict__ partial, int splits, long long n4, float* __restrict__ dF) {
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n4; k += (long long)gridDim.x * blockDim.x) {
+    float4 a = reinterpret_cast<const float4*>(partial)[k];
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = reinterpret_cast<const float4*>(partial)[(size_t)s * n4 + k];
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    reinterpret_cast<float4*>(dF)[k] = a;
+  }
+}
+
 // one extra all-zero tile of rows: a 128-row A tile starting at any row0 + 128k <= N stays inside the image
 static inline int npad_of(int N) { return (ceil_div(N, 128) + 1) * 128; }
 static inline int splits_of(int N, int nrows) {
@@ -326,5 +606,60 @@ extern "C" int pc_supcon_fwd_tc(const float* F, const int64_t* labels, int N, in
   PC_LAUNCH_CHECK("supcon_fwd_tc_kernel");
   supcon_merge_kernel<<<ceil_div(nrows, 256), 256, 0, stream>>>(partial, sp, nrows, temperature / base_temperature, stats, row_loss);
   PC_LAUNCH_CHECK("supcon_merge_kernel");
+  return PC_OK;
+}
+
+extern "C" size_t pc_supcon_bwd_tc_workspace(int N, int D, int nrows) {
+  if (N <= 0 || D <= 0 || nrows <= 0) return 0;
+  const size_t packed = (size_t)(D / 64) * 2 * npad_of(N) * 128;
+  const size_t part = (size_t)splits_of(N, nrows) * nrows * D * sizeof(float);
+  return packed + part + 256;
+}
+
+extern "C" int pc_supcon_bwd_tc(const float* F, const int64_t* labels, int N, int D, int row0, int nrows, float temperature, float coef,
+                                const float* grad_scale, const float* stats_all, void* workspace, size_t workspace_bytes, float* dF,
+                                pc_stream_t stream) {
+  PC_REQUIRE(N > 1, PC_EINVAL, "Batch size must be greater than 1 for contrastive loss");
+  PC_REQUIRE(F && labels && stats_all && dF && workspace, PC_EINVAL, "pc_supcon_bwd_tc: null pointer");
+  PC_REQUIRE(pc_supcon_tc_supported(N, D, row0, nrows), PC_EUNSUPPORTED,
+             "pc_supcon_bwd_tc: needs N >= 128, D = 64 | 128, row0 %% 8 == 0 (got N=%d D=%d row0=%d nrows=%d)", N, D, row0, nrows);
+  PC_REQUIRE(workspace_bytes >= pc_supcon_bwd_tc_workspace(N, D, nrows), PC_EINVAL, "pc_supcon_bwd_tc: workspace too small");
+  PC_REQUIRE((reinterpret_cast<uintptr_t>(F) & 15) == 0 && (reinterpret_cast<uintptr_t>(workspace) & 127) == 0 &&
+                 (reinterpret_cast<uintptr_t>(stats_all) & 15) == 0 && (reinterpret_cast<uintptr_t>(dF) & 15) == 0,
+             PC_EINVAL, "pc_supcon_bwd_tc: F, stats_all, dF must be 16-byte and the workspace 128-byte aligned");
+  const int Npad = npad_of(N), KC = D / 64;
+  unsigned char* Fp = static_cast<unsigned char*>(workspace);
+  const size_t packed = (size_t)KC * 2 * Npad * 128;
+  float* partial = reinterpret_cast<float*>(Fp + ((packed + 255) & ~(size_t)255));
+  const long long chunks = (long long)Npad * (D / 8);
+  int pgrid = ceil_div(chunks, 256);
+  if (pgrid > kNumSMs * 8) pgrid = kNumSMs * 8;
+  pack_rows_kernel<<<pgrid, 256, 0, stream>>>(F, N, Npad, D, Fp);
+  PC_LAUNCH_CHECK("supcon pack_rows_kernel");
+
+  BwdParams p{};
+  p.Fp = Fp; p.labels = reinterpret_cast<const long long*>(labels); p.stats_all = stats_all; p.grad_scale = grad_scale;
+  p.partial = partial;
+  p.N = N; p.Npad = Npad; p.KC = KC; p.D = D; p.row0 = row0; p.nrows = nrows;
+  p.col_tiles = ceil_div(N, BN);
+  const int sp = splits_of(N, nrows);
+  p.tiles_per_split = ceil_div(p.col_tiles, sp);
+  p.invT = 1.0f / temperature;
+  p.coef = coef;
+  const size_t smem = (size_t)KC * 2 * 16384 + (size_t)NSTB * KC * 2 * 8192 + 2 * 32768 + 2 * BN * (sizeof(float4) + sizeof(long long)) +
+                      sizeof(uint64_t) * 16 + 16 + 1024;
+  static size_t conf = 0;
+  if (smem > conf) {
+    PC_CUDA(cudaFuncSetAttribute(supcon_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  dim3 grid(ceil_div(nrows, BM), sp);
+  supcon_bwd_tc_kernel<<<grid, THREADS, smem, stream>>>(p);
+  PC_LAUNCH_CHECK("supcon_bwd_tc_kernel");
+  const long long n4 = (long long)nrows * D / 4;
+  int rgrid = ceil_div(n4, 256);
+  if (rgrid > kNumSMs * 8) rgrid = kNumSMs * 8;
+  supcon_dF_reduce_kernel<<<rgrid, 256, 0, stream>>>(partial, sp, n4, dF);
+  PC_LAUNCH_CHECK("supcon_dF_reduce_kernel");
   return PC_OK;
 }

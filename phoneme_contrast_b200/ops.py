@@ -373,6 +373,15 @@ def supcon_bwd(feats, labels, mask, temperature, coef, grad_scale, stats_all, ro
     N, D = feats.shape
     nrows = N - row0 if nrows is None else nrows
     dF = torch.empty(nrows, D, device=feats.device, dtype=F32)
+    import os
+    tc_env = os.environ.get("PC_SUPCON_TC")
+    if (mask is None and labels is not None and tc_env != "0" and (N >= 1024 or tc_env == "1")
+            and L.lib().pc_supcon_tc_supported(N, D, row0, nrows)):
+        nbytes = int(L.lib().pc_supcon_bwd_tc_workspace(N, D, nrows))
+        ws = _workspace(nbytes, feats.device)
+        call("pc_supcon_bwd_tc", ptr(feats), ptr(labels, torch.int64), N, D, row0, nrows, float(temperature), float(coef),
+             ptr(grad_scale), ptr(stats_all), ptr(ws, torch.uint8), ws.numel(), ptr(dF), stream())
+        return dF
     call("pc_supcon_bwd", ptr(feats), ptr(labels, torch.int64), ptr(mask), N, D, row0, nrows, float(temperature), float(coef),
          ptr(grad_scale), ptr(stats_all), ptr(dF), stream())
     return dF

@@ -16,5 +16,7 @@ for N in (1024, 4096, 8192):
         print(f"supcon fwd N={N} rows={nrows}: SIMT {a:.0f} us  TC {b:.0f} us  ({2*nrows*N*128/b/1e6:.1f} TFLOP/s)")
         st,_=ops.supcon_fwd(F,y,None,0.15,0.07,0,nrows)
         coef=(0.15/0.07)/N
-        os.environ["PC_SUPCON_TC"]="0"; c=t(lambda: ops.supcon_bwd(F,y,None,0.15,coef,None,st if nrows==N else torch.cat([st, st.new_zeros(N-nrows,4)+1]),0,nrows))
-        print(f"   bwd SIMT {c:.0f} us")
+        sa = st if nrows==N else torch.cat([st, st.new_zeros(N-nrows,4)+1])
+        os.environ["PC_SUPCON_TC"]="0"; c=t(lambda: ops.supcon_bwd(F,y,None,0.15,coef,None,sa,0,nrows))
+        os.environ["PC_SUPCON_TC"]="1"; e=t(lambda: ops.supcon_bwd(F,y,None,0.15,coef,None,sa,0,nrows))
+        print(f"   bwd SIMT {c:.0f} us  TC {e:.0f} us  ({4*nrows*N*128/e/1e6:.1f} TFLOP/s)")

@@ -192,3 +192,34 @@ def test_supcon_tc_forward_matches_simt_and_oracle(n, d, row0, nrows, monkeypatc
     if row0 == 0 and nrows == n and n <= 2048:
         want = supcon_oracle.loss(f, y, temperature=0.15)
         assert abs(float(rl1.double().mean()) - want) <= 1e-5 * abs(want)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("n,d,row0,nrows", [(1024, 128, 0, 1024), (1100, 128, 0, 1100), (2000, 64, 0, 2000), (2048, 128, 512, 300),
+                                            (4096, 128, 1024, 1024), (130, 128, 8, 100)])
+def test_supcon_tc_backward_matches_simt_and_oracle(n, d, row0, nrows, monkeypatch):
+    """tcgen05 SupCon backward (S recomputed in TMEM, dL/dS as the fp16 hi/lo operand of a second MMA accumulating dF in TMEM)
+    vs the exact-fp32 SIMT kernel (1e-4 of max|dF|) and, for the small full problems, the numpy oracle."""
+    from oracle import supcon_oracle
+    from phoneme_contrast_b200 import _lib as L
+    from phoneme_contrast_b200 import ops
+    rs = np.random.RandomState(n + d + 1)
+    f = rs.standard_normal((n, d)).astype(np.float32)
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    y = rs.randint(0, 38, n)
+    ft, yt = torch.from_numpy(f).to(DEV), torch.from_numpy(y).to(DEV)
+    monkeypatch.setenv("PC_SUPCON_TC", "0")
+    stats_all, _ = ops.supcon_fwd(ft, yt, None, 0.15, 0.07)
+    coef = (0.15 / 0.07) / n
+    gs = torch.full((1,), 0.75, device=DEV)
+    g0 = ops.supcon_bwd(ft, yt, None, 0.15, coef, gs, stats_all, row0, nrows)
+    monkeypatch.setenv("PC_SUPCON_TC", "1")
+    before = L.lib().pc_launch_count()
+    g1 = ops.supcon_bwd(ft, yt, None, 0.15, coef, gs, stats_all, row0, nrows)
+    torch.cuda.synchronize()
+    assert L.lib().pc_launch_count() - before == 3          # pack + tensor-core kernel + split reduce
+    err = float((g1 - g0).abs().max() / g0.abs().max())
+    assert err <= 1e-4, err
+    if row0 == 0 and nrows == n and n <= 2048:
+        gref = 0.75 * supcon_oracle.grad(f, y, temperature=0.15)
+        assert np.abs(g1.cpu().numpy() - gref).max() <= 1e-4 * np.abs(gref).max()
