@@ -474,9 +474,9 @@ def main():
     if args.workload == "supcon_8192":
         r = bench_supcon(args.steps, args.warmup, parallel, device)
         line = {"metric": "supcon_fwd_bwd_views_per_sec", "value": r["value"], "unit": "views/s", "ms_per_step": r["ms_per_step"], "dtype": "f32",
-                "roofline": {"bound": "tensor", "kernel": "supcon_bwd_kernel", "achieved": r["tflops"], "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+                "roofline": {"bound": "tensor", "kernel": "sctc::supcon_bwd_tc_kernel (+ supcon_fwd_tc_kernel)", "achieved": r["tflops"], "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
                              "unit": "TFLOP/s", "frac": r["tflops"] / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "traffic": None,
-                             "note": "per-rank algorithmic FLOPs 8*N^2*D/R (forward, backward recompute, two backward products) / step time; fp32 SIMT kernel"},
+                             "note": "per-rank algorithmic FLOPs 8*N^2*D/R (forward S, backward S recompute, dF = W F counted twice as in SURVEY 8d's 6N^2D + recompute) / step time; tcgen05 kernels with the FP16x2 operand split (3 fp16 products per pair: own ceiling = peak/3)"},
                 "e2e": {"value": r["e2e_value"], "unit": "views/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
                 "gpu_launches": int(round(r["launches"] * args.steps)),
                 "config": {"workload": wl["desc"], "final_loss": r["loss"], "l2": "F is 4 MB (L2-resident by design: every rank re-reads all N rows); no flush"}}
