@@ -175,9 +175,10 @@ def conv_dgrad(dy, wd, g: PcConvGeom, out=None, accumulate=False, prec=L.PREC_FP
 _ws_cache: dict = {}
 
 
-def _workspace(nbytes: int, device) -> torch.Tensor:
-    """Grow-only scratch buffer per (device, stream-capture state); contents are dead after each call."""
-    key = (device, torch.cuda.is_current_stream_capturing())
+def _workspace(nbytes: int, device, tag: str = "conv") -> torch.Tensor:
+    """Grow-only scratch buffer per (device, stream-capture state, user); contents are dead after each call. Users that may
+    run on different streams (weight gradients on the side stream, the SupCon kernels on the main one) keep separate buffers."""
+    key = (device, torch.cuda.is_current_stream_capturing(), tag)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
@@ -349,12 +350,13 @@ def supcon_fwd(feats, labels, mask, temperature, base_temperature, row0=0, nrows
     stats = torch.empty(nrows, 4, device=feats.device, dtype=F32)
     row_loss = torch.empty(nrows, device=feats.device, dtype=F32)
     import os
-    # large label-form problems: similarity tiles on the tensor cores (csrc/supcon_tc.cu); PC_SUPCON_TC=0 / 1 forces the choice
+    # label-form problems from N = 256 up: similarity tiles on the tensor cores (csrc/supcon_tc.cu; at N = 256 it is 0.06 ms vs
+    # 0.12 ms fwd+bwd for the SIMT kernels); PC_SUPCON_TC=0 / 1 forces the choice
     tc_env = os.environ.get("PC_SUPCON_TC")
-    if (mask is None and labels is not None and tc_env != "0" and (N >= 1024 or tc_env == "1")
+    if (mask is None and labels is not None and tc_env != "0" and (N >= 256 or tc_env == "1")
             and L.lib().pc_supcon_tc_supported(N, D, row0, nrows)):
         nbytes = int(L.lib().pc_supcon_tc_workspace(N, D, nrows))
-        ws = _workspace(nbytes, feats.device)
+        ws = _workspace(nbytes, feats.device, "supcon")
         call("pc_supcon_fwd_tc", ptr(feats), ptr(labels, torch.int64), N, D, row0, nrows, float(temperature), float(base_temperature),
              ptr(ws, torch.uint8), ws.numel(), ptr(stats), ptr(row_loss), stream())
         return stats, row_loss
@@ -375,10 +377,10 @@ def supcon_bwd(feats, labels, mask, temperature, coef, grad_scale, stats_all, ro
     dF = torch.empty(nrows, D, device=feats.device, dtype=F32)
     import os
     tc_env = os.environ.get("PC_SUPCON_TC")
-    if (mask is None and labels is not None and tc_env != "0" and (N >= 1024 or tc_env == "1")
+    if (mask is None and labels is not None and tc_env != "0" and (N >= 256 or tc_env == "1")
             and L.lib().pc_supcon_tc_supported(N, D, row0, nrows)):
         nbytes = int(L.lib().pc_supcon_bwd_tc_workspace(N, D, nrows))
-        ws = _workspace(nbytes, feats.device)
+        ws = _workspace(nbytes, feats.device, "supcon")
         call("pc_supcon_bwd_tc", ptr(feats), ptr(labels, torch.int64), N, D, row0, nrows, float(temperature), float(coef),
              ptr(grad_scale), ptr(stats_all), ptr(ws, torch.uint8), ws.numel(), ptr(dF), stream())
         return dF

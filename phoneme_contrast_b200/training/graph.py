@@ -119,36 +119,40 @@ class GraphedDPStep:
         pool = torch.cuda.graph_pool_handle()
         self.g = [torch.cuda.CUDAGraph() for _ in range(4)]
         kw = dict(pool=pool, capture_error_mode="thread_local")
-        with torch.no_grad():
-            with torch.cuda.graph(self.g[0], **kw):
-                emb, saved = model._engine_forward(_prep_input(self.views, model.in_channels), True)
-                self.emb = emb.contiguous()
-            d = self.emb.shape[1]
-            self.F = torch.empty(N, d, device=dev, dtype=torch.float32)
-            self.stats_all = torch.empty(N, 4, device=dev, dtype=torch.float32)
-            with torch.cuda.graph(self.g[1], **kw):
-                stats, row_loss = backend.rows_forward(self.F, self.y, T, Tb, row0, n)
-                self.stats = stats.contiguous()
-                self.total.copy_(row_loss.sum(dtype=torch.float32).reshape(1) / N)
-            with torch.cuda.graph(self.g[2], **kw):
-                dF = backend.rows_backward(self.F, self.y, T, (T / Tb) / N, ones, self.stats_all, row0, n)
-                model._engine_backward(saved, dF.contiguous(), grads)
-            with torch.cuda.graph(self.g[3], **kw):
-                opt.step(max_grad_norm=clip, flat_grad=self.flat)
-            self._saved = saved
-            # the gradients stay visible the usual way: every .grad is a view of the static bucket
-            for p in params:
-                if p.requires_grad:
-                    p.grad = grads[p]
-            opt.flat_p.copy_(snap_opt[0]); opt.flat_m.copy_(snap_opt[1]); opt.flat_v.copy_(snap_opt[2])
-            opt._step_dev.copy_(snap_opt[3]); opt._step = snap_opt[4]
-            for b, sb in zip(model.buffers(), snap_buf):
-                b.copy_(sb)
-            if getattr(model, "_drop_step", None) is not None:
-                if snap_drop is not None:
-                    model._drop_step.copy_(snap_drop)
-                else:
-                    model._drop_step.zero_()
+        try:
+            with torch.no_grad():
+                with torch.cuda.graph(self.g[0], **kw):
+                    emb, saved = model._engine_forward(_prep_input(self.views, model.in_channels), True)
+                    self.emb = emb.contiguous()
+                d = self.emb.shape[1]
+                self.F = torch.empty(N, d, device=dev, dtype=torch.float32)
+                self.stats_all = torch.empty(N, 4, device=dev, dtype=torch.float32)
+                with torch.cuda.graph(self.g[1], **kw):
+                    stats, row_loss = backend.rows_forward(self.F, self.y, T, Tb, row0, n)
+                    self.stats = stats.contiguous()
+                    self.total.copy_(row_loss.sum(dtype=torch.float32).reshape(1) / N)
+                with torch.cuda.graph(self.g[2], **kw):
+                    dF = backend.rows_backward(self.F, self.y, T, (T / Tb) / N, ones, self.stats_all, row0, n)
+                    model._engine_backward(saved, dF.contiguous(), grads)
+                with torch.cuda.graph(self.g[3], **kw):
+                    opt.step(max_grad_norm=clip, flat_grad=self.flat)
+                self._saved = saved
+                # the gradients stay visible the usual way: every .grad is a view of the static bucket
+                for p in params:
+                    if p.requires_grad:
+                        p.grad = grads[p]
+        finally:
+            # warm-up steps and the host-side counters touched during capture must be invisible to the optimisation trajectory
+            with torch.no_grad():
+                opt.flat_p.copy_(snap_opt[0]); opt.flat_m.copy_(snap_opt[1]); opt.flat_v.copy_(snap_opt[2])
+                opt._step_dev.copy_(snap_opt[3]); opt._step = snap_opt[4]
+                for b, sb in zip(model.buffers(), snap_buf):
+                    b.copy_(sb)
+                if getattr(model, "_drop_step", None) is not None:
+                    if snap_drop is not None:
+                        model._drop_step.copy_(snap_drop)
+                    else:
+                        model._drop_step.zero_()
         self.shape = (tuple(views.shape), tuple(labels.shape))
 
     def matches(self, views: torch.Tensor, labels: torch.Tensor) -> bool:

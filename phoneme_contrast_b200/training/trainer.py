@@ -99,8 +99,12 @@ class ContrastiveTrainer:
         if self._graphed is None:
             from .graph import GraphedDPStep, GraphedTrainStep
             # data parallel: four captured segments with the NCCL exchanges issued eagerly between them
-            self._graphed = (GraphedDPStep if self.parallel is not None else GraphedTrainStep)(self, views, labels)
-        if self._graphed.matches(views, labels):
+            try:
+                self._graphed = (GraphedDPStep if self.parallel is not None else GraphedTrainStep)(self, views, labels)
+            except Exception as exc:      # capture is an optimisation: keep training eagerly (training state was restored)
+                self.logger.warning("CUDA-graph capture of the training step failed (%s); continuing with eager launches", exc)
+                self._graphed = False
+        if self._graphed and self._graphed.matches(views, labels):
             return self._graphed(views, labels)
         return self.train_step(views, labels)
 
