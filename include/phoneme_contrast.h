@@ -145,7 +145,15 @@ typedef struct PcInXform {
   const float* shift;
   const float* drop;
   int32_t relu;
+  int32_t presplit;   /* != 0: `x` is not fp32 but the fp16 hi | lo planes written by pc_bn_act_split (the transform is already
+                         applied; scale/shift/drop must be NULL, relu 0). PC_PREC_FP16X2 tensor-core paths only. */
 } PcInXform;
+
+/* a = drop * relu(scale*y + shift) written ONCE in the tensor-core operand form: planes[0][n_pix*C] = fp16 hi, planes[1] = fp16
+ * lo * 2^11 (see PC_PREC_FP16X2). A convolution that reads its input through `presplit` then only copies bytes instead of
+ * redoing this arithmetic for every tap and output-channel tile. hw = pixels per sample (row of `drop` = pixel / hw). */
+int pc_bn_act_split(const float* y, int64_t n_pix, int C, int hw, const float* scale, const float* shift, const float* drop,
+                    int relu, void* planes, pc_stream_t stream);
 
 /* OIHW fp32 -> fwd layout Wf [(r,s,c)][o] and dgrad layout Wd [(r,s,o)][c] (either may be NULL). */
 int pc_pack_conv_weight(const float* w_oihw, int O, int I, int R, int S, float* wf, float* wd, pc_stream_t stream);

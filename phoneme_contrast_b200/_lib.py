@@ -38,7 +38,7 @@ class PcConvGeom(C.Structure):
 
 
 class PcInXform(C.Structure):
-    _fields_ = [("scale", vp), ("shift", vp), ("drop", vp), ("relu", C.c_int32)]
+    _fields_ = [("scale", vp), ("shift", vp), ("drop", vp), ("relu", C.c_int32), ("presplit", C.c_int32)]
 
 
 class PcPackJob(C.Structure):
@@ -77,6 +77,7 @@ SIGNATURES = {
     "pc_bn_finalize": (i32, [vp, i32, f64, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp]),
     "pc_bn_act_fwd": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     "pc_bn_act_bwd_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
+    "pc_bn_act_split": (i32, [vp, i64, i32, i32, vp, vp, vp, i32, vp, vp]),
     "pc_bn_act_bwd_apply": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
     "pc_bn_add_relu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp]),
     "pc_bn_add_relu_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),

@@ -6,6 +6,7 @@
 // Reference modules: nn.BatchNorm2d / ReLU / MaxPool2d / Dropout2d as composed in
 // src/models/phoneme_cnn.py:36-63 (PhonemeNet blocks), :211-216 (init_conv), :173-184 (ResidualBlock).
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace pc {
 
@@ -456,6 +457,47 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
   amax_commit(dysc_amax, lmaxs);
 }
 
+// ------------------------------------------------------------------------------------------------ pre-split activation
+// a = drop * relu(scale*y + shift) -> fp16 hi plane | fp16 lo*2^11 plane (tensor-core operand form, see tc_common.cuh).
+// thread = 8 consecutive channels of one pixel: two float4 loads, two 16-byte stores.
+__global__ void __launch_bounds__(256)
+bn_act_split_kernel(const float* __restrict__ y, long long n_pix, int C, int hw, const float* __restrict__ scale,
+                    const float* __restrict__ shift, const float* __restrict__ drop, int relu, unsigned char* __restrict__ planes) {
+  pdl_trigger();
+  pdl_wait();
+  const int C8 = C >> 3;
+  const long long total = n_pix * C8;
+  const size_t plane_bytes = (size_t)n_pix * C * 2;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C8) * 8;
+    const long long pix = idx / C8;
+    const size_t o = (size_t)pix * C + c;
+    float4 a = ld4(y + o), b = ld4(y + o + 4);
+    if (scale != nullptr) {
+      const float4 s0 = ld4(scale + c), s1 = ld4(scale + c + 4), t0 = ld4(shift + c), t1 = ld4(shift + c + 4);
+      a = make_float4(fmaf(a.x, s0.x, t0.x), fmaf(a.y, s0.y, t0.y), fmaf(a.z, s0.z, t0.z), fmaf(a.w, s0.w, t0.w));
+      b = make_float4(fmaf(b.x, s1.x, t1.x), fmaf(b.y, s1.y, t1.y), fmaf(b.z, s1.z, t1.z), fmaf(b.w, s1.w, t1.w));
+    }
+    if (relu) {
+      a = make_float4(fmaxf(a.x, 0.f), fmaxf(a.y, 0.f), fmaxf(a.z, 0.f), fmaxf(a.w, 0.f));
+      b = make_float4(fmaxf(b.x, 0.f), fmaxf(b.y, 0.f), fmaxf(b.z, 0.f), fmaxf(b.w, 0.f));
+    }
+    if (drop != nullptr) {
+      const size_t od = (size_t)(pix / hw) * C + c;
+      const float4 d0 = ld4(drop + od), d1 = ld4(drop + od + 4);
+      a = make_float4(a.x * d0.x, a.y * d0.y, a.z * d0.z, a.w * d0.w);
+      b = make_float4(b.x * d1.x, b.y * d1.y, b.z * d1.z, b.w * d1.w);
+    }
+    uint4 h, l;
+    tc::split_f16x2(a.x, a.y, h.x, l.x);
+    tc::split_f16x2(a.z, a.w, h.y, l.y);
+    tc::split_f16x2(b.x, b.y, h.z, l.z);
+    tc::split_f16x2(b.z, b.w, h.w, l.w);
+    *reinterpret_cast<uint4*>(planes + o * 2) = h;
+    *reinterpret_cast<uint4*>(planes + plane_bytes + o * 2) = l;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ dropout mask
 __global__ void dropout2d_mask_kernel(float* __restrict__ drop, int n, float p, float keep_scale, uint64_t seed, uint64_t offset,
                                       const long long* __restrict__ step_dev) {
@@ -633,5 +675,18 @@ extern "C" int pc_dropout2d_mask(float* drop, int B, int C, float p, uint64_t se
   launch_pdl(dropout2d_mask_kernel, dim3(ceil_div(ceil_div(n, 4), 128)), dim3(128), 0, stream, drop, n, p, 1.0f / (1.0f - p), seed, offset,
                                                                             reinterpret_cast<const long long*>(step_dev));
   PC_LAUNCH_CHECK("dropout2d_mask_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_bn_act_split(const float* y, int64_t n_pix, int C, int hw, const float* scale, const float* shift, const float* drop,
+                               int relu, void* planes, pc_stream_t stream) {
+  PC_REQUIRE(y && planes && n_pix > 0 && hw > 0, PC_EINVAL, "pc_bn_act_split: bad arguments");
+  PC_REQUIRE(C > 0 && C % 8 == 0, PC_EUNSUPPORTED, "pc_bn_act_split: channels=%d must be a multiple of 8", C);
+  PC_REQUIRE((scale == nullptr) == (shift == nullptr), PC_EINVAL, "pc_bn_act_split: scale/shift mismatch");
+  PC_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0, PC_EINVAL,
+             "pc_bn_act_split: buffers must be 16-byte aligned");
+  launch_pdl(bn_act_split_kernel, dim3(ew_grid(n_pix * (C / 8), 256)), dim3(256), 0, stream, y, (long long)n_pix, C, hw, scale, shift, drop,
+             relu, static_cast<unsigned char*>(planes));
+  PC_LAUNCH_CHECK("bn_act_split_kernel");
   return PC_OK;
 }

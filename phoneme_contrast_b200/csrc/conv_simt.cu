@@ -647,6 +647,7 @@ extern "C" int pc_conv_fwd(const float* x, const float* wf, const float* bias, c
     PC_REQUIRE(rc != PC_EUNSUPPORTED, PC_EUNSUPPORTED, "pc_conv_fwd: shape not covered by the tensor-core path (check pc_conv_tc_supported)");
     return rc;
   }
+  PC_REQUIRE(xf == nullptr || !xf->presplit, PC_EUNSUPPORTED, "pc_conv_fwd: pre-split input planes need the FP16X2 tensor-core path");
   const long long M = (long long)g->B * g->Ho * g->Wo;
   const XformDev d = to_dev(xf);
   if (g->Cout <= 32) {
@@ -727,6 +728,7 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
     return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, stream);
   if (prec == PC_PREC_FP16X2 && xf == nullptr && pc_conv_wgrad_tc_stem_supported(g))   // single-channel stem on the tensor cores
     return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, stream);
+  PC_REQUIRE(xf == nullptr || !xf->presplit, PC_EUNSUPPORTED, "pc_conv_wgrad: pre-split input planes need the FP16X2 tensor-core path");
   float* partial = static_cast<float*>(workspace);
   int n_partials;
   if (g->Cin == 1) {

@@ -65,6 +65,8 @@ struct Params {
   long long M;
   int Nn, Npad, Ca, n_kc, lda, accumulate, stages;
   int aff_floats;    // 2 * Ca when the gather applies a per-channel affine (kept in shared memory), else 0
+  int presplit;      // A is a pair of fp16 planes (hi, lo) instead of fp32 (FP16X2, mode 0 only)
+  size_t plane_bytes;
   long long* dbg;    // optional [gridDim.x*gridDim.y][16] clock64 stamps (diagnostics, see pc_tc_set_debug)
 };
 
@@ -100,7 +102,10 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
   return v[0];
 }
 
-template <int BN, int PREC, int NGROUPS, int MINB, bool PIPE>
+// PRESPLIT: the gathered tensor is already stored as fp16 hi | lo planes (pc_bn_act_split): the producers only copy
+// 16-byte chunks into the swizzled tile (no BatchNorm / ReLU / dropout / split arithmetic, which the plain gather repeats
+// for every tap and every N tile that touches an input element).
+template <int BN, int PREC, int NGROUPS, int MINB, bool PRESPLIT>
 __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(const Params p) {
   constexpr int PROD_WARPS = 4 * NGROUPS;
   using P = Prec<PREC>;
@@ -294,10 +299,8 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
     const uint32_t soff0 = sw128_offset((uint32_t)rg, (uint32_t)j);     // rows rg + 16*i share (row & 7): + 2048*i
     if (tid == 0) PC_STAMP(2);
     const int n_act = s_nact[0];
-    // Software pipeline inside a group: a thread's 8 rows are handled as two halves of 4. As soon as a half of stage `it` is
-    // converted and stored, the global loads of the same half for the group's NEXT stage (it + NGROUPS) are issued into the
-    // registers just freed, so the gather latency of the next stage overlaps the conversion of the other half, the wait for
-    // the smem slot and the MMA of this stage (otherwise load latency + conversion form one serial chain per group).
+    // (A software pipeline inside a group -- prefetching the next stage's rows into registers freed by the conversion -- was
+    //  measured: no gain on the BN = 128 kernels and slower on the BN = 64 ones; the plain order below is kept.)
     float v[8][EPC];
     int tap = 0, c0 = 0, tap_off = 0;
     const float* src_base = p.A;
@@ -308,8 +311,25 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
       tap_off = st.w;
       src_base = p.A + tap_off + c0;
     };
+    const unsigned char* planes = reinterpret_cast<const unsigned char*>(p.A);     // PRESPLIT: hi plane, lo plane at + plane_bytes
     auto load_half = [&](auto half) {
       constexpr int H = decltype(half)::value;
+      if (PRESPLIT) {
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int i = 4 * H + ii;
+          const bool ok = (tapmask[i] >> tap) & 1u;
+          uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
+          if (ok) {
+            const size_t e = (size_t)(off0[i] + tap_off + c0) * 2;       // element index -> byte offset in an fp16 plane
+            h = *reinterpret_cast<const uint4*>(planes + e);
+            l = *reinterpret_cast<const uint4*>(planes + p.plane_bytes + e);
+          }
+          v[i][0] = __uint_as_float(h.x); v[i][1] = __uint_as_float(h.y); v[i][2] = __uint_as_float(h.z); v[i][3] = __uint_as_float(h.w);
+          v[i][4 % EPC] = __uint_as_float(l.x); v[i][5 % EPC] = __uint_as_float(l.y); v[i][6 % EPC] = __uint_as_float(l.z); v[i][7 % EPC] = __uint_as_float(l.w);
+        }
+        return;
+      }
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii) {
         const int i = 4 * H + ii;
@@ -324,19 +344,13 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
     };
     using Half0 = std::integral_constant<int, 0>;
     using Half1 = std::integral_constant<int, 1>;
-    if (PIPE && group < n_act) {
-      setup(group);
-      load_half(Half0{});
-      load_half(Half1{});
-    }
     for (int it = group; it < n_act; it += NGROUPS) {
       const int s = it % S;
       const uint32_t ph = (uint32_t)(it / S) & 1u;
-      if (!PIPE) {   // plain order: this stage's loads are issued here, ahead of the wait for the smem slot
-        setup(it);
-        load_half(Half0{});
-        load_half(Half1{});
-      }
+      // this stage's loads are issued here, ahead of the wait for the smem slot
+      setup(it);
+      load_half(Half0{});
+      load_half(Half1{});
       const int cur_tap = tap, cur_c0 = c0;
       float sc[EPC], sh[EPC];
       if (has_aff) {
@@ -356,6 +370,11 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
           const int i = 4 * H + ii;
+          if (PRESPLIT) {       // bits already in operand form: copy
+            *reinterpret_cast<uint4*>(a_hi + 2048 * i) = make_uint4(__float_as_uint(v[i][0]), __float_as_uint(v[i][1]), __float_as_uint(v[i][2]), __float_as_uint(v[i][3]));
+            *reinterpret_cast<uint4*>(a_lo + 2048 * i) = make_uint4(__float_as_uint(v[i][4 % EPC]), __float_as_uint(v[i][5 % EPC]), __float_as_uint(v[i][6 % EPC]), __float_as_uint(v[i][7 % EPC]));
+            continue;
+          }
           const bool ok = (tapmask[i] >> cur_tap) & 1u;
           if (ok) {
             if (has_aff) {
@@ -401,14 +420,8 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 2), MINB) igemm_tc_kernel(
           }
         }
       };
-      const bool more = PIPE && it + NGROUPS < n_act;
       convert_half(Half0{});
-      if (more) {
-        setup(it + NGROUPS);
-        load_half(Half0{});
-      }
       convert_half(Half1{});
-      if (more) load_half(Half1{});
       fence_proxy_async();
       mbar_arrive(&full[s]);
       if (tid == 0 && it == 0) PC_STAMP(3);
@@ -691,16 +704,26 @@ static int launch(const Params& p0, pc_stream_t stream) {
   p.stages = stages;
   p.aff_floats = (p.mode == 0 && p.xf.scale != nullptr) ? 2 * p.Ca : 0;
   const size_t smem = (size_t)stages * st + sizeof(uint64_t) * (2 * MAX_STAGES + 1) + 16 + sizeof(float) * 3 * BN + sizeof(int) * (4 * BM + 4) + sizeof(float) * (size_t)p.aff_floats + sizeof(int4) * (size_t)(p.n_kc + 1) + 1024;
+  dim3 grid(ceil_div(p.M, BM), p.Npad / BN);
+  if constexpr (PREC == PC_PREC_FP16X2) {
+    if (p.presplit) {
+      static size_t configured_ps = 0;
+      if (smem > configured_ps) {
+        PC_CUDA(cudaFuncSetAttribute((igemm_tc_kernel<BN, PREC, NG, MINB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_ps = smem;
+      }
+      launch_pdl(igemm_tc_kernel<BN, PREC, NG, MINB, true>, dim3(grid), dim3(THREADS), smem, stream, p);
+      PC_LAUNCH_CHECK("igemm_tc_kernel<presplit>");
+      return PC_OK;
+    }
+  }
+  PC_REQUIRE(!p.presplit, PC_EUNSUPPORTED, "pre-split fp16 input planes need the FP16X2 precision");
   static size_t configured = 0;
   if (smem > configured) {
     PC_CUDA(cudaFuncSetAttribute((igemm_tc_kernel<BN, PREC, NG, MINB, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PC_CUDA(cudaFuncSetAttribute((igemm_tc_kernel<BN, PREC, NG, MINB, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  dim3 grid(ceil_div(p.M, BM), p.Npad / BN);
-  static const bool pipe = [] { const char* e = getenv("PC_TC_PIPE"); return e && e[0] == '1'; }();
-  if (pipe) launch_pdl(igemm_tc_kernel<BN, PREC, NG, MINB, true>, dim3(grid), dim3(THREADS), smem, stream, p);
-  else launch_pdl(igemm_tc_kernel<BN, PREC, NG, MINB, false>, dim3(grid), dim3(THREADS), smem, stream, p);
+  launch_pdl(igemm_tc_kernel<BN, PREC, NG, MINB, false>, dim3(grid), dim3(THREADS), smem, stream, p);
   PC_LAUNCH_CHECK("igemm_tc_kernel");
   return PC_OK;
 }
@@ -786,6 +809,12 @@ extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias,
   Params p{};
   p.A = x; p.Bp = (const unsigned char*)wp; p.bias = bias; p.C = y; p.stats = stats;
   if (xf != nullptr) { p.xf.scale = xf->scale; p.xf.shift = xf->shift; p.xf.drop = xf->drop; p.xf.relu = xf->relu; }
+  if (xf != nullptr && xf->presplit) {
+    PC_REQUIRE(prec == PC_PREC_FP16X2 && !xf->scale && !xf->shift && !xf->drop && !xf->relu, PC_EINVAL,
+               "pc_conv_fwd: pre-split input planes take no further transform and need PC_PREC_FP16X2");
+    p.presplit = 1;
+    p.plane_bytes = (size_t)g->B * g->H * g->W * g->Cin * 2;
+  }
   p.g = *g; p.mode = 0;
   p.M = (long long)g->B * g->Ho * g->Wo;
   p.Nn = g->Cout; p.Npad = npad_of(g->Cout); p.Ca = g->Cin;

@@ -50,6 +50,7 @@ struct Params {
   PcConvGeom g;
   int K, M, rows_per_split, stages;
   const float* dy_amax;   // FP16X2: device scalar max|dy| (null: scale 1)
+  size_t plane_bytes;     // PRESPLIT: byte distance between the hi and lo planes of x
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr_bytes) {
@@ -83,9 +84,11 @@ __host__ __device__ constexpr uint32_t stage_bytes() {
 
 // STEM (with F16): single input channel. The M tile's first 64 rows are the R*S taps (zero padded), the second channel
 // group stays zero; thread (pixel row, j) gathers taps 8j..8j+7 of its pixel's window with scalar loads.
-template <int BN, int NGROUPS, int MINB, bool F16, bool STEM = false>
+// PRESPLIT (with F16): x is the pair of fp16 planes written by pc_bn_act_split; the A' gather copies 16-byte chunks.
+template <int BN, int NGROUPS, int MINB, bool F16, bool STEM = false, bool PRESPLIT = false>
 __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(const Params p) {
   static_assert(!STEM || F16, "the stem gather is built for the FP16X2 tiles only");
+  static_assert(!PRESPLIT || (F16 && !STEM), "pre-split planes feed the FP16X2 tiles only");
   constexpr int PROD_WARPS = 4 * NGROUPS;
   constexpr int CPG = F16 ? 64 : 32;          // channels per 128-byte row (one channel group)
   constexpr int GA = 128 / CPG, GB = BN / CPG; // channel groups of the A' (M) and B' (N) tiles
@@ -222,6 +225,17 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
         for (int q = 0; q < (STEM ? 0 : GA); ++q) {
           const int hi = ho * g.stride - g.pad + q_tr[q], wi = wo * g.stride - g.pad + q_ts[q];
           const bool ok = mv && q_ok[q] && (unsigned)hi < (unsigned)g.H && (unsigned)wi < (unsigned)g.W;
+          if (PRESPLIT) {       // hi bits -> av[..][0], lo bits -> av[..][NV-1]
+            uint4 hb = make_uint4(0u, 0u, 0u, 0u), lb = hb;
+            if (ok) {
+              const size_t e = ((((size_t)b * g.H + hi) * g.W + wi) * g.Cin + q_c0[q]) * 2;
+              hb = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.x) + e);
+              lb = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.x) + p.plane_bytes + e);
+            }
+            av[h][q][0] = make_float4(__uint_as_float(hb.x), __uint_as_float(hb.y), __uint_as_float(hb.z), __uint_as_float(hb.w));
+            av[h][q][NV - 1] = make_float4(__uint_as_float(lb.x), __uint_as_float(lb.y), __uint_as_float(lb.z), __uint_as_float(lb.w));
+            continue;
+          }
 #pragma unroll
           for (int vv = 0; vv < NV; ++vv) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -252,6 +266,13 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
 #pragma unroll
           for (int q = 0; q < (STEM ? 1 : GA); ++q) {
             uint4 hh, ll;
+            if (PRESPLIT) {
+              hh = make_uint4(__float_as_uint(av[h][q][0].x), __float_as_uint(av[h][q][0].y), __float_as_uint(av[h][q][0].z), __float_as_uint(av[h][q][0].w));
+              ll = make_uint4(__float_as_uint(av[h][q][NV - 1].x), __float_as_uint(av[h][q][NV - 1].y), __float_as_uint(av[h][q][NV - 1].z), __float_as_uint(av[h][q][NV - 1].w));
+              *reinterpret_cast<uint4*>(a_hi + q * GRP + off) = hh;
+              *reinterpret_cast<uint4*>(a_lo + q * GRP + off) = ll;
+              continue;
+            }
             split_f16x2(av[h][q][0].x, av[h][q][0].y, hh.x, ll.x); split_f16x2(av[h][q][0].z, av[h][q][0].w, hh.y, ll.y);
             split_f16x2(av[h][q][NV - 1].x, av[h][q][NV - 1].y, hh.z, ll.z); split_f16x2(av[h][q][NV - 1].z, av[h][q][NV - 1].w, hh.w, ll.w);
             *reinterpret_cast<uint4*>(a_hi + q * GRP + off) = hh;
@@ -482,6 +503,12 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
   Params p{};
   p.x = x; p.dy = dy; p.partial = static_cast<float*>(workspace);
   if (xf != nullptr) { p.xf.scale = xf->scale; p.xf.shift = xf->shift; p.xf.drop = xf->drop; p.xf.relu = xf->relu; }
+  const bool presplit = xf != nullptr && xf->presplit != 0;
+  if (presplit) {
+    PC_REQUIRE(prec == PC_PREC_FP16X2 && g->Cin % 64 == 0 && !xf->scale && !xf->shift && !xf->drop && !xf->relu, PC_EINVAL,
+               "pc_conv_wgrad: pre-split input planes take no further transform and need PC_PREC_FP16X2 with Cin %% 64 == 0");
+    p.plane_bytes = (size_t)g->B * g->H * g->W * g->Cin * 2;
+  }
   p.g = *g;
   p.K = g->R * g->S * g->Cin;
   p.M = g->B * g->Ho * g->Wo;
@@ -513,6 +540,18 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
       conf = smem;
     }
     launch_pdl(wgrad_tc_kernel<64, 3, 1, true, true>, grid, dim3(32 * 13), smem, stream, p);
+  } else if (presplit) {
+#define PC_WG_LAUNCH_PS(BN_)                                                                                                 \
+  do {                                                                                                                     \
+    static size_t conf = 0;                                                                                                \
+    if (smem > conf) {                                                                                                     \
+      PC_CUDA(cudaFuncSetAttribute((wgrad_tc_kernel<BN_, 3, 1, true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      conf = smem;                                                                                                         \
+    }                                                                                                                      \
+    launch_pdl(wgrad_tc_kernel<BN_, 3, 1, true, false, true>, grid, dim3(32 * 13), smem, stream, p);                       \
+  } while (0)
+    if (bn == 64) PC_WG_LAUNCH_PS(64); else PC_WG_LAUNCH_PS(128);
+#undef PC_WG_LAUNCH_PS
   } else if (bn == 64) {
     if (f16) PC_WG_LAUNCH(64, true); else PC_WG_LAUNCH(64, false);
   } else {

@@ -289,9 +289,17 @@ def _deep_forward(net, x, training):
         g2 = ops.conv_geom(B, g1.Ho, g1.Wo, co, co, 3, 1, 1)
         cw2 = ops.ConvWeights(blk.conv2.weight, g2, prec, packer=packer)
         st2 = st(co)
-        y2 = ops.conv_fwd(y1, cw2.wf, blk.conv2.bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True, drop=s.drop[i]), st2, cw2.prec_f)
+        # conv2 reads a1 = drop * relu(bn1(y1)). On the FP16X2 engine a1 is written once as fp16 hi | lo planes (one elementwise
+        # pass) and conv2's gather -- and later its weight gradient's -- only copies bytes, instead of redoing BatchNorm + ReLU +
+        # dropout + split for every tap and output-channel tile
+        a1 = None
+        if cw2.prec_f == L.PREC_FP16X2:
+            a1 = ops.bn_act_split(y1, c1.scale, c1.shift, s.drop[i], relu=True)
+            y2 = ops.conv_fwd(a1, cw2.wf, blk.conv2.bias, g2, dict(presplit=True), st2, cw2.prec_f)
+        else:
+            y2 = ops.conv_fwd(y1, cw2.wf, blk.conv2.bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True, drop=s.drop[i]), st2, cw2.prec_f)
         c2 = ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk.bn2, training)
-        rec = dict(xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, cw1=cw1, cw2=cw2, proj=len(blk.shortcut) > 0)
+        rec = dict(xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, cw1=cw1, cw2=cw2, proj=len(blk.shortcut) > 0, a1=a1)
         if rec["proj"]:
             convs, bns = blk.shortcut[0], blk.shortcut[1]
             gs = ops.conv_geom(B, h, w, cin, co, 1, stride, 0)
@@ -329,8 +337,11 @@ def _deep_backward(net, s, demb, grads, training=True):
                                                   (grads[bns.weight], grads[bns.bias]), m2, ms)
         else:
             dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None)
-        xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
-        wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2)
+        if r["a1"] is not None and prec == L.PREC_FP16X2:
+            wgrad(r["a1"], dy2, r["g2"], dict(presplit=True), grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2)
+        else:
+            xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
+            wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2)
         dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2)
         dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1)
         wgrad(r["xin"], dy1, r["g1"], None, grads[blk.conv1.weight], grads[blk.conv1.bias], prec, m1)

@@ -21,10 +21,20 @@ def conv_geom(B, H, W, Cin, Cout, k, stride, pad) -> PcConvGeom:
     return PcConvGeom(B, H, W, Cin, Ho, Wo, Cout, k, k, stride, pad)
 
 
-def _xf(scale=None, shift=None, drop=None, relu=False):
-    if scale is None and drop is None and not relu:
+def _xf(scale=None, shift=None, drop=None, relu=False, presplit=False):
+    if scale is None and drop is None and not relu and not presplit:
         return None
-    return PcInXform(ptr(scale), ptr(shift), ptr(drop), 1 if relu else 0)
+    return PcInXform(ptr(scale), ptr(shift), ptr(drop), 1 if relu else 0, 1 if presplit else 0)
+
+
+def bn_act_split(y, scale=None, shift=None, drop=None, relu=False):
+    """a = drop * relu(scale*y + shift) of an NHWC tensor, written once as fp16 hi | lo planes (uint8 view [2, numel*2]) for the
+    FP16X2 convolutions (`presplit=True` in their xform)."""
+    B, H, W, C_ = y.shape
+    planes = torch.empty(2, y.numel() * 2, device=y.device, dtype=torch.uint8)
+    call("pc_bn_act_split", ptr(y), B * H * W, C_, H * W, ptr(scale), ptr(shift), ptr(drop), 1 if relu else 0,
+         ptr(planes, torch.uint8), stream())
+    return planes
 
 
 def pack_conv_weight(w: torch.Tensor, want_fwd=True, want_dgrad=True):
@@ -158,7 +168,8 @@ def conv_fwd(x, w, bias, g: PcConvGeom, xform=None, stats=None, prec=L.PREC_FP32
     y = torch.empty(g.B, g.Ho, g.Wo, g.Cout, device=x.device, dtype=F32)
     xf = _xf(**xform) if xform else None
     L.note_work("pc_conv_fwd", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
-    call("pc_conv_fwd", ptr(x), ptr(w, None), ptr(bias), C.byref(g), C.byref(xf) if xf is not None else None, ptr(y),
+    call("pc_conv_fwd", ptr(x, None if (xform and xform.get("presplit")) else F32), ptr(w, None), ptr(bias), C.byref(g),
+         C.byref(xf) if xf is not None else None, ptr(y),
          ptr(stats, torch.float64), prec, stream())
     return y
 
@@ -198,7 +209,8 @@ def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_F
         prec = L.PREC_FP32
     xf = _xf(**xform) if xform else None
     L.note_work("pc_conv_wgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
-    call("pc_conv_wgrad", ptr(x), ptr(dy), C.byref(g), C.byref(xf) if xf is not None else None, ptr(dw), ptr(db),
+    call("pc_conv_wgrad", ptr(x, None if (xform and xform.get("presplit")) else F32), ptr(dy), C.byref(g),
+         C.byref(xf) if xf is not None else None, ptr(dw), ptr(db),
          ptr(ws, torch.uint8), ws.numel(), prec, ptr(dy_amax), stream())
     return dw, db
 

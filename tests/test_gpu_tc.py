@@ -223,3 +223,27 @@ def test_supcon_tc_backward_matches_simt_and_oracle(n, d, row0, nrows, monkeypat
     if row0 == 0 and nrows == n and n <= 2048:
         gref = 0.75 * supcon_oracle.grad(f, y, temperature=0.15)
         assert np.abs(g1.cpu().numpy() - gref).max() <= 1e-4 * np.abs(gref).max()
+
+
+@pytest.mark.parametrize("case", [(4, 20, 51, 64, 64, 3, 1, 1), (3, 20, 51, 64, 128, 3, 2, 1), (2, 10, 26, 128, 256, 3, 2, 1), (5, 3, 7, 512, 512, 3, 1, 1),
+                                  (3, 20, 51, 64, 128, 1, 2, 0)])
+def test_tc_conv_fwd_presplit_input(case):
+    """A convolution reading the activation as pre-split fp16 planes (pc_bn_act_split) gives bit-identical outputs to the one
+    that applies BatchNorm + ReLU + dropout + split inside its gather: the operand bytes are the same."""
+    from phoneme_contrast_b200 import ops
+    B, H, W, Cin, Cout, k, stride, pad = case
+    g = ops.conv_geom(B, H, W, Cin, Cout, k, stride, pad)
+    gen = torch.Generator(device=DEV).manual_seed(Cin + 2 * Cout + k)
+    x = torch.randn(B, H, W, Cin, device=DEV, generator=gen)
+    w = torch.randn(Cout, Cin, k, k, device=DEV, generator=gen) * (2.0 / (Cin * k * k)) ** 0.5
+    bias = torch.randn(Cout, device=DEV, generator=gen)
+    scale = 1.0 + 0.1 * torch.randn(Cin, device=DEV, generator=gen)
+    shift = 0.1 * torch.randn(Cin, device=DEV, generator=gen)
+    drop = ((torch.rand(B, Cin, device=DEV, generator=gen) > 0.2).float() / 0.8).contiguous()
+    cw = ops.ConvWeights(w, g, 3)
+    y0 = ops.conv_fwd(x, cw.wf, bias, g, dict(scale=scale, shift=shift, relu=True, drop=drop), None, cw.prec_f)
+    planes = ops.bn_act_split(x, scale, shift, drop, relu=True)
+    st = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    y1 = ops.conv_fwd(planes, cw.wf, bias, g, dict(presplit=True), st, cw.prec_f)
+    assert torch.equal(y0, y1)
+    np.testing.assert_allclose(st[0].cpu().numpy(), y0.double().sum(dim=(0, 1, 2)).cpu().numpy(), rtol=1e-6, atol=1e-4)
