@@ -215,7 +215,9 @@ int pc_bn_finalize(const double* stats, int C, double count, const float* gamma,
 /* Fused BatchNorm-apply + ReLU (+ max-pool) (+ Dropout2d multiplier) producing a materialised activation.
  * pool: 0 none, 2 = MaxPool2d(2,2) (phoneme_cnn.py:42,52), 3 = MaxPool2d(3,2,1) (:215; writes argmax u8). */
 int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const float* scale, const float* shift,
-                  const float* drop, int pool, float* out, uint8_t* argmax, pc_stream_t stream);
+                  const float* drop, int pool, float* out, uint8_t* argmax, void* planes, pc_stream_t stream);
+/* `planes` (may be NULL; here and in pc_bn_add_relu_fwd): additionally write `out` as fp16 hi | lo planes (the layout of
+ * pc_bn_act_split, numel(out) elements per plane) for a following convolution that reads its input with presplit != 0. */
 /* Backward of the above w.r.t. y: two passes. pass 1 accumulates sums[0][C] = sum dz, sums[1][C] = sum dz*xhat (fp64);
  * pass 2 writes dy = scale*(dz - sum_dz/M - xhat*sum_dzxhat/M) and dgamma/dbeta. dout is the gradient w.r.t. `out`.
  * dy_amax (may be NULL): zero-initialised device scalar that receives max|dy| (atomic max). */
@@ -230,7 +232,7 @@ int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, 
 /* Residual tail: out = relu(bn2(y2) + (sc_scale ? bn_s(ysc) : ysc))   (phoneme_cnn.py:177-182). */
 int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const float* shift2, const float* ysc,
                        const float* sc_scale, const float* sc_shift, int64_t n_pix, int C, float* out,
-                       pc_stream_t stream);
+                       void* planes, pc_stream_t stream);
 /* g = dout * (out > 0); pass 1: sums2[2][C] over (g, y2) and sums_s[2][C] over (g, ysc) (sums_s NULL for identity);
  * pass 2: dy2, dysc (or, identity shortcut, dsc (+)= g into dx_identity), dgamma/dbeta for both norms. */
 int pc_bn_add_relu_bwd_reduce(const float* dout, const float* out, const float* y2, const float* mean2,

@@ -65,12 +65,22 @@ __device__ __forceinline__ float absmax4(const float (&r)[4], float m) {
   return fmaxf(fmaxf(m, fmaxf(fabsf(r[0]), fabsf(r[1]))), fmaxf(fabsf(r[2]), fabsf(r[3])));
 }
 
+// optional second output of the forward kernels: the same 4 values in tensor-core operand form (fp16 hi | lo*2^11 planes of
+// `plane_elems` elements each, element index o), so that the next convolution's gather can copy bytes (see pc_bn_act_split)
+__device__ __forceinline__ void emit_planes4(unsigned char* __restrict__ planes, size_t plane_elems, size_t o, float4 r) {
+  uint2 h, l;
+  tc::split_f16x2(r.x, r.y, h.x, l.x);
+  tc::split_f16x2(r.z, r.w, h.y, l.y);
+  *reinterpret_cast<uint2*>(planes + o * 2) = h;
+  *reinterpret_cast<uint2*>(planes + (plane_elems + o) * 2) = l;
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 template <int POOL>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ drop, float* __restrict__ out,
-                  uint8_t* __restrict__ argmax) {
+                  uint8_t* __restrict__ argmax, unsigned char* __restrict__ planes) {
   pdl_trigger();
   pdl_wait();
   const int C4 = C >> 2;
@@ -123,7 +133,9 @@ bn_act_fwd_kernel(const float* __restrict__ y, int B, int H, int W, int C, int H
       const float4 d = ld4(drop + (size_t)b * C + c);
       r.x *= d.x; r.y *= d.y; r.z *= d.z; r.w *= d.w;
     }
-    st4(out + (((size_t)b * Ho + ho) * Wo + wo) * C + c, r);
+    const size_t oo = (((size_t)b * Ho + ho) * Wo + wo) * C + c;
+    st4(out + oo, r);
+    if (planes != nullptr) emit_planes4(planes, (size_t)B * Ho * Wo * C, oo, r);
   }
 }
 
@@ -317,7 +329,7 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
 __global__ void __launch_bounds__(256)
 bn_add_relu_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ scale2, const float* __restrict__ shift2,
                        const float* __restrict__ ysc, const float* __restrict__ sc_scale, const float* __restrict__ sc_shift,
-                       long long n_pix, int C, float* __restrict__ out) {
+                       long long n_pix, int C, float* __restrict__ out, unsigned char* __restrict__ planes) {
   pdl_trigger();
   pdl_wait();
   const int C4 = C >> 2;
@@ -336,6 +348,7 @@ bn_add_relu_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ s
     r.z = fmaxf(fmaf(a.z, s.z, t.z) + r.z, 0.f);
     r.w = fmaxf(fmaf(a.w, s.w, t.w) + r.w, 0.f);
     st4(out + o, r);
+    if (planes != nullptr) emit_planes4(planes, (size_t)n_pix * C, o, r);
   }
 }
 
@@ -576,7 +589,7 @@ extern "C" int pc_bn_finalize(const double* stats, int C, double count, const fl
   PC_REQUIRE((C) > 0 && (C) % 4 == 0 && (C) <= 1024 && 256 % ((C) / 4) == 0, PC_EUNSUPPORTED, fn ": channels=%d must be 4*2^k <= 1024", (C))
 
 extern "C" int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const float* scale, const float* shift,
-                             const float* drop, int pool, float* out, uint8_t* argmax, pc_stream_t stream) {
+                             const float* drop, int pool, float* out, uint8_t* argmax, void* planes, pc_stream_t stream) {
   PC_REQUIRE(y && scale && shift && out && B > 0 && H > 0 && W > 0, PC_EINVAL, "pc_bn_act_fwd: bad arguments");
   PC_CHECK_C4("pc_bn_act_fwd", C);
   PC_REQUIRE(pool == 0 || pool == 2 || pool == 3, PC_EINVAL, "pc_bn_act_fwd: pool must be 0, 2 or 3");
@@ -585,9 +598,9 @@ extern "C" int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const f
   PC_REQUIRE(Ho > 0 && Wo > 0, PC_EINVAL, "pc_bn_act_fwd: input %dx%d too small for pooling", H, W);
   const long long total = (long long)B * Ho * Wo * (C / 4);
   const int grid = ew_grid(total, 256);
-  if (pool == 0) launch_pdl((bn_act_fwd_kernel<0>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
-  else if (pool == 2) launch_pdl((bn_act_fwd_kernel<2>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
-  else launch_pdl((bn_act_fwd_kernel<3>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax);
+  if (pool == 0) launch_pdl((bn_act_fwd_kernel<0>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes));
+  else if (pool == 2) launch_pdl((bn_act_fwd_kernel<2>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes));
+  else launch_pdl((bn_act_fwd_kernel<3>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes));
   PC_LAUNCH_CHECK("bn_act_fwd_kernel");
   return PC_OK;
 }
@@ -631,11 +644,11 @@ extern "C" int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int
 
 extern "C" int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const float* shift2, const float* ysc,
                                   const float* sc_scale, const float* sc_shift, int64_t n_pix, int C, float* out,
-                                  pc_stream_t stream) {
+                                  void* planes, pc_stream_t stream) {
   PC_REQUIRE(y2 && scale2 && shift2 && ysc && out && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_fwd: bad arguments");
   PC_REQUIRE((sc_scale == nullptr) == (sc_shift == nullptr), PC_EINVAL, "pc_bn_add_relu_fwd: shortcut scale/shift mismatch");
   PC_CHECK_C4("pc_bn_add_relu_fwd", C);
-  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid(n_pix * (C / 4), 256)), dim3(256), 0, stream, y2, scale2, shift2, ysc, sc_scale, sc_shift, n_pix, C, out);
+  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid(n_pix * (C / 4), 256)), dim3(256), 0, stream, y2, scale2, shift2, ysc, sc_scale, sc_shift, n_pix, C, out, static_cast<unsigned char*>(planes));
   PC_LAUNCH_CHECK("bn_add_relu_fwd_kernel");
   return PC_OK;
 }

@@ -273,18 +273,26 @@ def _deep_forward(net, x, training):
     st0 = st(hd[0])
     y0 = ops.conv_fwd(x, conv0.weight, conv0.bias, g0, None, st0, prec)
     co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
-    p0, argmax0 = ops.bn_act_fwd(y0, co0, 3, None)
+    # On the FP16X2 engine every block input is also kept as fp16 hi | lo planes (written by the kernel that produces it), so
+    # that conv1 / the shortcut conv and their weight gradients gather bytes instead of splitting fp32 per tap
+    ps = prec == L.PREC_FP16X2 and all(c % 64 == 0 for c in hd)
+    if ps:
+        p0, argmax0, cur_ps = ops.bn_act_fwd(y0, co0, 3, None, want_planes=True)
+    else:
+        (p0, argmax0), cur_ps = ops.bn_act_fwd(y0, co0, 3, None), None
     s.stem = dict(g=g0, y=y0, co=co0, argmax=argmax0)
     s.blocks = []
     cur, cin = p0, hd[0]
     h, w = p0.shape[1], p0.shape[2]
+    xps = dict(presplit=True)
     for i, blk in enumerate(net.conv_blocks):
         co = hd[i]
         stride = blk.stride
         g1 = ops.conv_geom(B, h, w, cin, co, 3, stride, 1)
         cw1 = ops.ConvWeights(blk.conv1.weight, g1, prec, packer=packer)
         st1 = st(co)
-        y1 = ops.conv_fwd(cur, cw1.wf, blk.conv1.bias, g1, None, st1, cw1.prec_f)
+        in_ps = cur_ps if (cur_ps is not None and cw1.prec_f == L.PREC_FP16X2) else None
+        y1 = ops.conv_fwd(in_ps if in_ps is not None else cur, cw1.wf, blk.conv1.bias, g1, xps if in_ps is not None else None, st1, cw1.prec_f)
         c1 = ops.bn_finalize(st1, B * g1.Ho * g1.Wo, blk.bn1, training)
         g2 = ops.conv_geom(B, g1.Ho, g1.Wo, co, co, 3, 1, 1)
         cw2 = ops.ConvWeights(blk.conv2.weight, g2, prec, packer=packer)
@@ -299,18 +307,19 @@ def _deep_forward(net, x, training):
         else:
             y2 = ops.conv_fwd(y1, cw2.wf, blk.conv2.bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True, drop=s.drop[i]), st2, cw2.prec_f)
         c2 = ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk.bn2, training)
-        rec = dict(xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, cw1=cw1, cw2=cw2, proj=len(blk.shortcut) > 0, a1=a1)
+        rec = dict(xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, cw1=cw1, cw2=cw2, proj=len(blk.shortcut) > 0, a1=a1, xin_ps=in_ps)
         if rec["proj"]:
             convs, bns = blk.shortcut[0], blk.shortcut[1]
             gs = ops.conv_geom(B, h, w, cin, co, 1, stride, 0)
             cws = ops.ConvWeights(convs.weight, gs, prec, packer=packer)
             sts = st(co)
-            ys = ops.conv_fwd(cur, cws.wf, convs.bias, gs, None, sts, cws.prec_f)
+            sc_ps = in_ps if cws.prec_f == L.PREC_FP16X2 else None
+            ys = ops.conv_fwd(sc_ps if sc_ps is not None else cur, cws.wf, convs.bias, gs, xps if sc_ps is not None else None, sts, cws.prec_f)
             cs = ops.bn_finalize(sts, B * gs.Ho * gs.Wo, bns, training)
-            out = ops.bn_add_relu_fwd(y2, c2, ys, cs)
             rec.update(gs=gs, ys=ys, cs=cs, cws=cws)
-        else:
-            out = ops.bn_add_relu_fwd(y2, c2, cur, None)
+        last = i == len(net.conv_blocks) - 1          # the last block's output feeds the attention pool, not a convolution
+        res = ops.bn_add_relu_fwd(y2, c2, rec["ys"] if rec["proj"] else cur, rec["cs"] if rec["proj"] else None, want_planes=ps and not last)
+        out, cur_ps = res if (ps and not last) else (res, None)
         rec["out"] = out
         s.blocks.append(rec)
         cur, cin, h, w = out, co, g1.Ho, g1.Wo
@@ -344,9 +353,10 @@ def _deep_backward(net, s, demb, grads, training=True):
             wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2)
         dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2)
         dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1)
-        wgrad(r["xin"], dy1, r["g1"], None, grads[blk.conv1.weight], grads[blk.conv1.bias], prec, m1)
+        xin_w, xf_w = (r["xin_ps"], dict(presplit=True)) if r["xin_ps"] is not None else (r["xin"], None)
+        wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], grads[blk.conv1.bias], prec, m1)
         if r["proj"]:
-            wgrad(r["xin"], dysc, r["gs"], None, grads[convs.weight], grads[convs.bias], prec, ms)
+            wgrad(xin_w, dysc, r["gs"], xf_w, grads[convs.weight], grads[convs.bias], prec, ms)
             dxin = ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], prec=r["cws"].prec_d, dy_amax=ms)
         else:
             dxin = dysc                                        # identity shortcut: d(out)/d(xin) passes g through

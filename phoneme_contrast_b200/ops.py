@@ -243,14 +243,16 @@ def pool_dims(H, W, pool):
     return (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
 
 
-def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None):
+def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None, want_planes=False):
+    """want_planes: also return `out` as fp16 hi | lo planes (see bn_act_split) -> (out, argmax, planes)."""
     B, H, W, C_ = y.shape
     Ho, Wo = pool_dims(H, W, pool)
     out = torch.empty(B, Ho, Wo, C_, device=y.device, dtype=F32)
     argmax = torch.empty(B, Ho, Wo, C_, device=y.device, dtype=torch.uint8) if pool == 3 else None
+    planes = torch.empty(2, out.numel() * 2, device=y.device, dtype=torch.uint8) if want_planes else None
     call("pc_bn_act_fwd", ptr(y), B, H, W, C_, ptr(co.scale), ptr(co.shift), ptr(drop), pool, ptr(out),
-         ptr(argmax, torch.uint8), stream())
-    return out, argmax
+         ptr(argmax, torch.uint8), ptr(planes, torch.uint8), stream())
+    return (out, argmax, planes) if want_planes else (out, argmax)
 
 
 def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None):
@@ -270,13 +272,14 @@ def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=Non
     return dy, dgamma, dbeta
 
 
-def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None):
+def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, want_planes=False):
     C_ = y2.shape[-1]
     n_pix = y2.numel() // C_
     out = torch.empty_like(y2)
+    planes = torch.empty(2, out.numel() * 2, device=y2.device, dtype=torch.uint8) if want_planes else None
     call("pc_bn_add_relu_fwd", ptr(y2), ptr(co2.scale), ptr(co2.shift), ptr(ysc), ptr(co_s.scale) if co_s else None,
-         ptr(co_s.shift) if co_s else None, n_pix, C_, ptr(out), stream())
-    return out
+         ptr(co_s.shift) if co_s else None, n_pix, C_, ptr(out), ptr(planes, torch.uint8), stream())
+    return (out, planes) if want_planes else out
 
 
 def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, grads2=None, grads_s=None, amax2=None,
