@@ -198,11 +198,14 @@ int pc_conv_fwd(const float* x, const float* wf, const float* bias, const PcConv
 /* dx (+)= conv_transpose(dy, w): accumulate != 0 adds into dx. dy_amax (may be NULL): device scalar holding max|dy|, written by
  * the BatchNorm-backward apply calls below; PC_PREC_FP16X2 derives its power-of-two operand scale from it (NULL: scale 1). */
 int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom* g, float* dx, int accumulate, int prec,
-                  const float* dy_amax, pc_stream_t stream);
+                  const float* dy_amax, int dy_presplit, pc_stream_t stream);
+/* dy_presplit != 0 (here and in pc_conv_wgrad): `dy` points to the fp16 hi | lo planes written by pc_bn_*_bwd_apply (dy_planes),
+ * scaled by the power of two derived from *dy_amax; the gather copies bytes and the epilogue undoes the scale. */
 /* dw (OIHW) and db from x (through xform) and dy. workspace >= pc_conv_wgrad_workspace(g) bytes. */
 size_t pc_conv_wgrad_workspace(const PcConvGeom* g);
 int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw,
-                  float* db, void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream);
+                  float* db, void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, int dy_presplit,
+                  pc_stream_t stream);
 
 /* BatchNorm statistics -> per-channel coefficients.
  * training: mean/var from stats (count = elements per channel), running stats updated with `momentum`
@@ -223,11 +226,15 @@ int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const float* scale
  * dy_amax (may be NULL): zero-initialised device scalar that receives max|dy| (atomic max). */
 int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
                          const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
-                         const uint8_t* argmax, double* sums, pc_stream_t stream);
+                         const uint8_t* argmax, double* sums, float* maxes, pc_stream_t stream);
+/* maxes (may be NULL): zero-initialised float[2] receiving max|dz| and max|xhat| (atomic max); needed by dy_planes below. */
 int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
                         const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
                         const uint8_t* argmax, const double* sums, float* dy, float* dgamma, float* dbeta,
-                        float* dy_amax, pc_stream_t stream);
+                        float* dy_amax, const float* maxes, void* dy_planes, pc_stream_t stream);
+/* dy_planes (may be NULL): write dy (also) in tensor-core operand form -- fp16 hi | lo planes (pc_bn_act_split layout) of
+ * dy * 2^k, with 2^k derived from a bound of |dy| computed from `maxes` and `sums`; the bound is stored in dy_amax (which
+ * pc_conv_dgrad / pc_conv_wgrad with dy_presplit != 0 read to undo the scale). `dy` itself may then be NULL. */
 
 /* Residual tail: out = relu(bn2(y2) + (sc_scale ? bn_s(ysc) : ysc))   (phoneme_cnn.py:177-182). */
 int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const float* shift2, const float* ysc,
@@ -237,12 +244,14 @@ int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const float* shift2
  * pass 2: dy2, dysc (or, identity shortcut, dsc (+)= g into dx_identity), dgamma/dbeta for both norms. */
 int pc_bn_add_relu_bwd_reduce(const float* dout, const float* out, const float* y2, const float* mean2,
                               const float* invstd2, const float* ysc, const float* mean_s, const float* invstd_s,
-                              int64_t n_pix, int C, double* sums2, double* sums_s, pc_stream_t stream);
+                              int64_t n_pix, int C, double* sums2, double* sums_s, float* maxes, pc_stream_t stream);
 int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, const float* y2, const float* scale2,
                              const float* mean2, const float* invstd2, const double* sums2, const float* ysc,
                              const float* sc_scale, const float* mean_s, const float* invstd_s, const double* sums_s,
                              int64_t n_pix, int C, float* dy2, float* dysc_or_dx, float* dgamma2, float* dbeta2,
-                             float* dgamma_s, float* dbeta_s, float* dy2_amax, float* dysc_amax, pc_stream_t stream);
+                             float* dgamma_s, float* dbeta_s, float* dy2_amax, float* dysc_amax, const float* maxes,
+                             void* dy2_planes, void* dysc_planes, pc_stream_t stream);
+/* maxes: float[3] (max|g|, max|xhat2|, max|xhat_s|) from the reduce pass; *_planes as dy_planes of pc_bn_act_bwd_apply. */
 
 /* SpatialAttention + AdaptiveAvgPool2d(1): pooled[b,c] = mean_p a[b,p,c] * sigmoid(w.a[b,p,:] + b0)
  * (phoneme_cnn.py:134-143,117-118). w == NULL: plain mean (use_attention False). gate [B,HW] saved for backward. */

@@ -71,17 +71,17 @@ SIGNATURES = {
     "pc_tc_gemm_workspace": (sz, [i32, i32, i32]),
     "pc_tc_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]),
     "pc_conv_fwd": (i32, [vp, vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, i32, vp]),
-    "pc_conv_dgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, i32, i32, vp, vp]),
+    "pc_conv_dgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, i32, i32, vp, i32, vp]),
     "pc_conv_wgrad_workspace": (sz, [C.POINTER(PcConvGeom)]),
-    "pc_conv_wgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, vp, sz, i32, vp, vp]),
+    "pc_conv_wgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, vp, sz, i32, vp, i32, vp]),
     "pc_bn_finalize": (i32, [vp, i32, f64, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp, vp, vp]),
     "pc_bn_act_fwd": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp]),
-    "pc_bn_act_bwd_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
+    "pc_bn_act_bwd_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "pc_bn_act_split": (i32, [vp, i64, i32, i32, vp, vp, vp, i32, vp, vp]),
-    "pc_bn_act_bwd_apply": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "pc_bn_act_bwd_apply": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pc_bn_add_relu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),
-    "pc_bn_add_relu_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),
-    "pc_bn_add_relu_bwd_apply": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "pc_bn_add_relu_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp]),
+    "pc_bn_add_relu_bwd_apply": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pc_attn_pool_fwd": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "pc_attn_pool_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "pc_head_workspace": (sz, [i32, i32, i32]),

@@ -207,6 +207,27 @@ __device__ __forceinline__ void bn_act_dz(const float* __restrict__ dout, const 
   for (int q = 0; q < 4; ++q) dz[q] = (a[q] > 0.f) ? g[q] * dr[q] : 0.f;
 }
 
+// Block-wide maximum of a non-negative value, identical in every thread afterwards (order-independent, so every block of a
+// grid derives the same number from the same global data).
+__device__ __forceinline__ float block_max_all(float v, float* sh /*[9]*/) {
+  v = warp_max(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, sh[w]);
+    sh[8] = m;
+  }
+  __syncthreads();
+  return sh[8];
+}
+__device__ __forceinline__ void max_commit(float* slot, float local_max) {   // slot may be null
+  if (slot == nullptr) return;
+  local_max = warp_max(local_max);
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(local_max));
+}
+
 // Visits the pixels of this block: f(p, b, h, w) with p the linear NHWC pixel index. Without pooling only p is needed (b
 // only for the per-sample dropout multiplier), so the loop is flat and division-free; with pooling a block walks whole
 // image rows, which keeps the (b, h) decomposition out of the inner loop.
@@ -255,7 +276,7 @@ __global__ void __launch_bounds__(256, 4)
 bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ y, int B, int H, int W, int C, int Ho,
                          int Wo, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ drop,
-                         const uint8_t* __restrict__ argmax, double* __restrict__ sums) {
+                         const uint8_t* __restrict__ argmax, double* __restrict__ sums, float* __restrict__ maxes) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[256 * 4];
@@ -264,16 +285,24 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict
   const int c4 = c4_off + threadIdx.x % C4, c = c4 * 4;
   const float4 s = ld4(scale + c), t = ld4(shift + c), mu = ld4(mean + c), is = ld4(invstd + c);
   float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float gmax = 0.f, xmax = 0.f;     // max |dz| and max |xhat| (bound of |dy| for the pre-split gradient planes)
   for_each_pixel<POOL, 4>(B, H, W, C4, drop != nullptr, [&](int p, int b, int h, int w) {
     float dz[4];
     float4 yv;
     bn_act_dz<POOL>(dout, y, p, b, h, w, c, H, W, C, Ho, Wo, s, t, drop, argmax, dz, yv);
-    acc[0][0] += dz[0]; acc[0][1] += dz[1]; acc[0][2] += dz[2]; acc[0][3] += dz[3];
-    acc[1][0] += dz[0] * (yv.x - mu.x) * is.x;
-    acc[1][1] += dz[1] * (yv.y - mu.y) * is.y;
-    acc[1][2] += dz[2] * (yv.z - mu.z) * is.z;
-    acc[1][3] += dz[3] * (yv.w - mu.w) * is.w;
+    const float xh[4] = {(yv.x - mu.x) * is.x, (yv.y - mu.y) * is.y, (yv.z - mu.z) * is.z, (yv.w - mu.w) * is.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      acc[0][q] += dz[q];
+      acc[1][q] += dz[q] * xh[q];
+    }
+    gmax = absmax4(dz, gmax);
+    xmax = absmax4(xh, xmax);
   });
+  if (maxes != nullptr) {
+    max_commit(maxes, gmax);
+    max_commit(maxes + 1, xmax);
+  }
   double* dst[2] = {sums, sums + C};
   block_channel_reduce<2>(acc, C4, c4_off, dst, sh);
 }
@@ -284,9 +313,11 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
                         int Wo, const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ drop,
                         const uint8_t* __restrict__ argmax, const double* __restrict__ sums, float* __restrict__ dy,
-                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dy_amax) {
+                        float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dy_amax,
+                        const float* __restrict__ maxes, unsigned char* __restrict__ dy_planes) {
   pdl_trigger();
   pdl_wait();
+  __shared__ float sh_max[9];
   const int C4 = C >> 2;
   const int c4 = threadIdx.x % C4, c = c4 * 4;
   const int ppb = blockDim.x / C4;
@@ -307,6 +338,21 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
     }
   }
   const float sv[4] = PC_F4_ARR(s), muv[4] = PC_F4_ARR(mu), isv[4] = PC_F4_ARR(is);
+  // Pre-split output: dy is (also) written as fp16 hi | lo planes scaled by a power of two. The scale must be known before
+  // the first element is written, so it comes from a BOUND of |dy| built from the reduce pass (max |dz|, max |xhat|, the
+  // per-channel sums): |dy| <= |scale_c| (max|dz| + |sum dz_c| / M + max|xhat| |sum dz xhat_c| / M). Every block derives
+  // the same bound; block 0 publishes it in dy_amax, which the consuming convolutions use to undo the scale.
+  float pscale = 1.f;
+  if (dy_planes != nullptr) {
+    const float gmax = maxes[0], xmax = maxes[1];
+    float lb = 0.f;
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x)
+      lb = fmaxf(lb, fabsf(scale[cc]) * (gmax + fabsf((float)sums[cc]) * invM + xmax * fabsf((float)sums[C + cc]) * invM));
+    const float bound = block_max_all(lb, sh_max);
+    pscale = tc::f16_operand_scale(bound);
+    if (blockIdx.x == 0 && threadIdx.x == 0 && dy_amax != nullptr) dy_amax[0] = bound;
+  }
+  const size_t plane_elems = (size_t)npix * C;
   float lmax = 0.f;
   for_each_pixel<POOL, 2>(B, H, W, C4, drop != nullptr, [&](int p, int b, int h, int w) {
     float dz[4];
@@ -320,9 +366,11 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
       r[q] = sv[q] * (dz[q] - sdz[q] * invM - xhat * sdzx[q] * invM);
     }
     lmax = absmax4(r, lmax);
-    st4(dy + (size_t)p * C + c, make_float4(r[0], r[1], r[2], r[3]));
+    if (dy != nullptr) st4(dy + (size_t)p * C + c, make_float4(r[0], r[1], r[2], r[3]));
+    if (dy_planes != nullptr)
+      emit_planes4(dy_planes, plane_elems, (size_t)p * C + c, make_float4(r[0] * pscale, r[1] * pscale, r[2] * pscale, r[3] * pscale));
   });
-  amax_commit(dy_amax, lmax);
+  if (dy_planes == nullptr) amax_commit(dy_amax, lmax);
 }
 
 // ------------------------------------------------------------------------------------------------ residual tail
@@ -357,7 +405,7 @@ bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __res
                               const float* __restrict__ mean2, const float* __restrict__ invstd2,
                               const float* __restrict__ ysc, const float* __restrict__ mean_s,
                               const float* __restrict__ invstd_s, long long n_pix, int C, double* __restrict__ sums2,
-                              double* __restrict__ sums_s) {
+                              double* __restrict__ sums_s, float* __restrict__ maxes) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh[256 * 4];
@@ -369,23 +417,32 @@ bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __res
   float4 mus = make_float4(0.f, 0.f, 0.f, 0.f), iss = mus;
   if (proj) { mus = ld4(mean_s + c); iss = ld4(invstd_s + c); }
   float acc[3][4] = {};
+  float gmax = 0.f, x2max = 0.f, xsmax = 0.f;      // max |g|, |xhat2|, |xhat_s|: bound of |dy| for pre-split gradient planes
 #pragma unroll 2
   for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < n_pix; p += (long long)gridDim.x * ppb) {
     const size_t o = (size_t)p * C + c;
     const float4 d = ld4(dout + o), ov = ld4(out + o), yv = ld4(y2 + o);
     const float g[4] = {ov.x > 0.f ? d.x : 0.f, ov.y > 0.f ? d.y : 0.f, ov.z > 0.f ? d.z : 0.f, ov.w > 0.f ? d.w : 0.f};
-    acc[0][0] += g[0]; acc[0][1] += g[1]; acc[0][2] += g[2]; acc[0][3] += g[3];
-    acc[1][0] += g[0] * (yv.x - mu2.x) * is2.x;
-    acc[1][1] += g[1] * (yv.y - mu2.y) * is2.y;
-    acc[1][2] += g[2] * (yv.z - mu2.z) * is2.z;
-    acc[1][3] += g[3] * (yv.w - mu2.w) * is2.w;
+    const float x2[4] = {(yv.x - mu2.x) * is2.x, (yv.y - mu2.y) * is2.y, (yv.z - mu2.z) * is2.z, (yv.w - mu2.w) * is2.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      acc[0][q] += g[q];
+      acc[1][q] += g[q] * x2[q];
+    }
+    gmax = absmax4(g, gmax);
+    x2max = absmax4(x2, x2max);
     if (proj) {
       const float4 sv = ld4(ysc + o);
-      acc[2][0] += g[0] * (sv.x - mus.x) * iss.x;
-      acc[2][1] += g[1] * (sv.y - mus.y) * iss.y;
-      acc[2][2] += g[2] * (sv.z - mus.z) * iss.z;
-      acc[2][3] += g[3] * (sv.w - mus.w) * iss.w;
+      const float xs[4] = {(sv.x - mus.x) * iss.x, (sv.y - mus.y) * iss.y, (sv.z - mus.z) * iss.z, (sv.w - mus.w) * iss.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[2][q] += g[q] * xs[q];
+      xsmax = absmax4(xs, xsmax);
     }
+  }
+  if (maxes != nullptr) {
+    max_commit(maxes, gmax);
+    max_commit(maxes + 1, x2max);
+    max_commit(maxes + 2, xsmax);
   }
   // sums2 = [sum g, sum g*xhat2]; sums_s = [sum g, sum g*xhat_s]
   if (proj) {
@@ -409,9 +466,11 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
                              const double* __restrict__ sums_s, long long n_pix, int C, float* __restrict__ dy2,
                              float* __restrict__ dysc, float* __restrict__ dgamma2, float* __restrict__ dbeta2,
                              float* __restrict__ dgamma_s, float* __restrict__ dbeta_s, float* __restrict__ dy2_amax,
-                             float* __restrict__ dysc_amax) {
+                             float* __restrict__ dysc_amax, const float* __restrict__ maxes,
+                             unsigned char* __restrict__ dy2_planes, unsigned char* __restrict__ dysc_planes) {
   pdl_trigger();
   pdl_wait();
+  __shared__ float sh_max[9];
   const int C4 = C >> 2;
   const int c4 = threadIdx.x % C4, c = c4 * 4;
   const int ppb = blockDim.x / C4;
@@ -438,6 +497,26 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
   }
   const float s2v[4] = PC_F4_ARR(s2), mu2v[4] = PC_F4_ARR(mu2), is2v[4] = PC_F4_ARR(is2);
   const float ssv[4] = PC_F4_ARR(ss), musv[4] = PC_F4_ARR(mus), issv[4] = PC_F4_ARR(iss);
+  // pre-split outputs: same scheme as bn_act_bwd_apply_kernel (power-of-two scale from a bound of |dy|, published in *_amax)
+  float pscale2 = 1.f, pscales = 1.f;
+  if (dy2_planes != nullptr || dysc_planes != nullptr) {
+    const float gmax = maxes[0], x2max = maxes[1], xsmax = maxes[2];
+    float lb2 = 0.f, lbs = 0.f;
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+      const float sgc = fabsf((float)sums2[cc]) * invM;
+      lb2 = fmaxf(lb2, fabsf(scale2[cc]) * (gmax + sgc + x2max * fabsf((float)sums2[C + cc]) * invM));
+      if (proj) lbs = fmaxf(lbs, fabsf(sc_scale[cc]) * (gmax + sgc + xsmax * fabsf((float)sums_s[C + cc]) * invM));
+    }
+    const float b2 = block_max_all(lb2, sh_max);
+    const float bs = proj ? block_max_all(lbs, sh_max) : gmax;
+    pscale2 = tc::f16_operand_scale(b2);
+    pscales = tc::f16_operand_scale(bs);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      if (dy2_planes != nullptr && dy2_amax != nullptr) dy2_amax[0] = b2;
+      if (dysc_planes != nullptr && dysc_amax != nullptr) dysc_amax[0] = bs;
+    }
+  }
+  const size_t plane_elems = (size_t)n_pix * C;
   float lmax2 = 0.f, lmaxs = 0.f;
   for (long long p = (long long)blockIdx.x * ppb + threadIdx.x / C4; p < n_pix; p += (long long)gridDim.x * ppb) {
     const size_t o = (size_t)p * C + c;
@@ -463,11 +542,13 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
     }
     lmax2 = absmax4(r2, lmax2);
     lmaxs = absmax4(rs, lmaxs);
-    st4(dy2 + o, make_float4(r2[0], r2[1], r2[2], r2[3]));
-    st4(dysc + o, make_float4(rs[0], rs[1], rs[2], rs[3]));
+    if (dy2 != nullptr) st4(dy2 + o, make_float4(r2[0], r2[1], r2[2], r2[3]));
+    if (dysc != nullptr) st4(dysc + o, make_float4(rs[0], rs[1], rs[2], rs[3]));
+    if (dy2_planes != nullptr) emit_planes4(dy2_planes, plane_elems, o, make_float4(r2[0] * pscale2, r2[1] * pscale2, r2[2] * pscale2, r2[3] * pscale2));
+    if (dysc_planes != nullptr) emit_planes4(dysc_planes, plane_elems, o, make_float4(rs[0] * pscales, rs[1] * pscales, rs[2] * pscales, rs[3] * pscales));
   }
-  amax_commit(dy2_amax, lmax2);
-  amax_commit(dysc_amax, lmaxs);
+  if (dy2_planes == nullptr) amax_commit(dy2_amax, lmax2);
+  if (dysc_planes == nullptr) amax_commit(dysc_amax, lmaxs);
 }
 
 // ------------------------------------------------------------------------------------------------ pre-split activation
@@ -607,7 +688,7 @@ extern "C" int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const f
 
 extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
                                     const float* shift, const float* mean, const float* invstd, const float* drop,
-                                    int pool, const uint8_t* argmax, double* sums, pc_stream_t stream) {
+                                    int pool, const uint8_t* argmax, double* sums, float* maxes, pc_stream_t stream) {
   PC_REQUIRE(dout && y && scale && shift && mean && invstd && sums, PC_EINVAL, "pc_bn_act_bwd_reduce: null pointer");
   PC_CHECK_C4("pc_bn_act_bwd_reduce", C);
   PC_REQUIRE(pool == 0 || pool == 2 || (pool == 3 && argmax), PC_EINVAL, "pc_bn_act_bwd_reduce: bad pool / argmax");
@@ -617,9 +698,9 @@ extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, in
   PC_REQUIRE((long long)B * H * W < (1LL << 31), PC_EUNSUPPORTED, "pc_bn_act_bwd_reduce: too many pixels");
   (void)items;
   const dim3 grid = reduce_grid2((long long)B * H * W, C);
-  if (pool == 0) launch_pdl((bn_act_bwd_reduce_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
-  else if (pool == 2) launch_pdl((bn_act_bwd_reduce_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
-  else launch_pdl((bn_act_bwd_reduce_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums);
+  if (pool == 0) launch_pdl((bn_act_bwd_reduce_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes);
+  else if (pool == 2) launch_pdl((bn_act_bwd_reduce_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes);
+  else launch_pdl((bn_act_bwd_reduce_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes);
   PC_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
   return PC_OK;
 }
@@ -627,17 +708,19 @@ extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, in
 extern "C" int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
                                    const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
                                    const uint8_t* argmax, const double* sums, float* dy, float* dgamma, float* dbeta,
-                                   float* dy_amax, pc_stream_t stream) {
-  PC_REQUIRE(dout && y && scale && shift && mean && invstd && sums && dy, PC_EINVAL, "pc_bn_act_bwd_apply: null pointer");
+                                   float* dy_amax, const float* maxes, void* dy_planes, pc_stream_t stream) {
+  PC_REQUIRE(dout && y && scale && shift && mean && invstd && sums && (dy || dy_planes), PC_EINVAL, "pc_bn_act_bwd_apply: null pointer");
+  PC_REQUIRE(dy_planes == nullptr || (maxes != nullptr && dy_amax != nullptr), PC_EINVAL,
+             "pc_bn_act_bwd_apply: dy_planes needs the maxes of the reduce pass and a dy_amax slot");
   PC_CHECK_C4("pc_bn_act_bwd_apply", C);
   PC_REQUIRE(pool == 0 || pool == 2 || (pool == 3 && argmax), PC_EINVAL, "pc_bn_act_bwd_apply: bad pool / argmax");
   int Ho, Wo;
   pool_out_dims(H, W, pool, &Ho, &Wo);
   const long long items = (long long)B * H * W * (C / 4);
   const int grid = ew_grid(items, 256 * 2);
-  if (pool == 0) launch_pdl((bn_act_bwd_apply_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax);
-  else if (pool == 2) launch_pdl((bn_act_bwd_apply_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax);
-  else launch_pdl((bn_act_bwd_apply_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax);
+  if (pool == 0) launch_pdl((bn_act_bwd_apply_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes));
+  else if (pool == 2) launch_pdl((bn_act_bwd_apply_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes));
+  else launch_pdl((bn_act_bwd_apply_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes));
   PC_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return PC_OK;
 }
@@ -656,11 +739,11 @@ extern "C" int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const fl
 extern "C" int pc_bn_add_relu_bwd_reduce(const float* dout, const float* out, const float* y2, const float* mean2,
                                          const float* invstd2, const float* ysc, const float* mean_s,
                                          const float* invstd_s, int64_t n_pix, int C, double* sums2, double* sums_s,
-                                         pc_stream_t stream) {
+                                         float* maxes, pc_stream_t stream) {
   PC_REQUIRE(dout && out && y2 && mean2 && invstd2 && sums2 && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_bwd_reduce: bad arguments");
   PC_REQUIRE(sums_s == nullptr || (ysc && mean_s && invstd_s), PC_EINVAL, "pc_bn_add_relu_bwd_reduce: shortcut pointers");
   PC_CHECK_C4("pc_bn_add_relu_bwd_reduce", C);
-  launch_pdl(bn_add_relu_bwd_reduce_kernel, reduce_grid2(n_pix, C), dim3(256), 0, stream, dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s);
+  launch_pdl(bn_add_relu_bwd_reduce_kernel, reduce_grid2(n_pix, C), dim3(256), 0, stream, dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s, maxes);
   PC_LAUNCH_CHECK("bn_add_relu_bwd_reduce_kernel");
   return PC_OK;
 }
@@ -670,13 +753,17 @@ extern "C" int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, con
                                         const float* sc_scale, const float* mean_s, const float* invstd_s,
                                         const double* sums_s, int64_t n_pix, int C, float* dy2, float* dysc_or_dx,
                                         float* dgamma2, float* dbeta2, float* dgamma_s, float* dbeta_s, float* dy2_amax,
-                                        float* dysc_amax, pc_stream_t stream) {
-  PC_REQUIRE(dout && out && y2 && scale2 && mean2 && invstd2 && sums2 && dy2 && dysc_or_dx && n_pix > 0, PC_EINVAL,
-             "pc_bn_add_relu_bwd_apply: bad arguments");
+                                        float* dysc_amax, const float* maxes, void* dy2_planes, void* dysc_planes,
+                                        pc_stream_t stream) {
+  PC_REQUIRE(dout && out && y2 && scale2 && mean2 && invstd2 && sums2 && (dy2 || dy2_planes) && (dysc_or_dx || dysc_planes) && n_pix > 0,
+             PC_EINVAL, "pc_bn_add_relu_bwd_apply: bad arguments");
+  PC_REQUIRE((dy2_planes == nullptr || (maxes && dy2_amax)) && (dysc_planes == nullptr || (maxes && dysc_amax)), PC_EINVAL,
+             "pc_bn_add_relu_bwd_apply: *_planes need the maxes of the reduce pass and the matching *_amax slot");
   PC_REQUIRE(sc_scale == nullptr || (ysc && mean_s && invstd_s && sums_s), PC_EINVAL, "pc_bn_add_relu_bwd_apply: shortcut pointers");
   PC_CHECK_C4("pc_bn_add_relu_bwd_apply", C);
   launch_pdl(bn_add_relu_bwd_apply_kernel, dim3(ew_grid(n_pix * (C / 4), 256 * 2)), dim3(256), 0, stream, dout, out, y2, scale2, mean2, invstd2, sums2, ysc, sc_scale, mean_s, invstd_s, sums_s, n_pix, C, dy2, dysc_or_dx,
-      dgamma2, dbeta2, dgamma_s, dbeta_s, dy2_amax, dysc_amax);
+      dgamma2, dbeta2, dgamma_s, dbeta_s, dy2_amax, dysc_amax, maxes, static_cast<unsigned char*>(dy2_planes),
+      static_cast<unsigned char*>(dysc_planes));
   PC_LAUNCH_CHECK("bn_add_relu_bwd_apply_kernel");
   return PC_OK;
 }

@@ -618,7 +618,7 @@ extern "C" int pc_pack_conv_weight(const float* w_oihw, int O, int I, int R, int
 extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias, const PcConvGeom* g, const PcInXform* xf,
                               float* y, double* stats, int prec, pc_stream_t stream);
 extern "C" int pc_conv_dgrad_tc(const float* dy, const void* wp, const PcConvGeom* g, float* dx, int accumulate, int prec,
-                                const float* dy_amax, pc_stream_t stream);
+                                const float* dy_amax, int dy_presplit, pc_stream_t stream);
 
 extern "C" int pc_conv_fwd(const float* x, const float* wf, const float* bias, const PcConvGeom* g, const PcInXform* xf,
                            float* y, double* stats, int prec, pc_stream_t stream) {
@@ -665,16 +665,17 @@ extern "C" int pc_conv_fwd(const float* x, const float* wf, const float* bias, c
 }
 
 extern "C" int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom* g, float* dx, int accumulate, int prec,
-                             const float* dy_amax, pc_stream_t stream) {
+                             const float* dy_amax, int dy_presplit, pc_stream_t stream) {
   int rc = check_geom("pc_conv_dgrad", g);
   if (rc != PC_OK) return rc;
   PC_REQUIRE(dy && wd && dx, PC_EINVAL, "pc_conv_dgrad: null pointer");
   PC_REQUIRE(g->Cout % CG_BK == 0 && g->Cin % 4 == 0, PC_EUNSUPPORTED, "pc_conv_dgrad: Cout=%d must be a multiple of 16 and Cin=%d of 4", g->Cout, g->Cin);
   if (prec != PC_PREC_FP32) {
-    rc = pc_conv_dgrad_tc(dy, wd, g, dx, accumulate, prec, dy_amax, stream);
+    rc = pc_conv_dgrad_tc(dy, wd, g, dx, accumulate, prec, dy_amax, dy_presplit, stream);
     PC_REQUIRE(rc != PC_EUNSUPPORTED, PC_EUNSUPPORTED, "pc_conv_dgrad: shape not covered by the tensor-core path (check pc_conv_tc_supported)");
     return rc;
   }
+  PC_REQUIRE(!dy_presplit, PC_EUNSUPPORTED, "pc_conv_dgrad: pre-split dy needs the FP16X2 tensor-core path");
   const long long M = (long long)g->B * g->H * g->W;
   const XformDev d{nullptr, nullptr, nullptr, 0};
   if (g->Cin <= 32) {
@@ -695,7 +696,7 @@ extern "C" int pc_conv_wgrad_tc_supported(const PcConvGeom* g);
 extern "C" int pc_conv_wgrad_tc_stem_supported(const PcConvGeom* g);
 extern "C" size_t pc_conv_wgrad_tc_workspace(const PcConvGeom* g);
 extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw, float* db,
-                                void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream);
+                                void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, int dy_presplit, pc_stream_t stream);
 
 static size_t wgrad_workspace_simt(const PcConvGeom* g);
 
@@ -717,7 +718,8 @@ static size_t wgrad_workspace_simt(const PcConvGeom* g) {
 }
 
 extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw,
-                             float* db, void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream) {
+                             float* db, void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, int dy_presplit,
+                             pc_stream_t stream) {
   int rc = check_geom("pc_conv_wgrad", g);
   if (rc != PC_OK) return rc;
   PC_REQUIRE(x && dy && dw_oihw && workspace, PC_EINVAL, "pc_conv_wgrad: null pointer");
@@ -725,9 +727,10 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
              pc_conv_wgrad_workspace(g));
   // tensor-core path (TF32x3) for eligible layers whenever a tensor-core precision is requested
   if (prec != PC_PREC_FP32 && g->Cin != 1 && pc_conv_wgrad_tc_supported(g))
-    return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, stream);
+    return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, dy_presplit, stream);
   if (prec == PC_PREC_FP16X2 && xf == nullptr && pc_conv_wgrad_tc_stem_supported(g))   // single-channel stem on the tensor cores
-    return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, stream);
+    return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, 0, stream);
+  PC_REQUIRE(!dy_presplit, PC_EUNSUPPORTED, "pc_conv_wgrad: pre-split dy needs the FP16X2 tensor-core path");
   PC_REQUIRE(xf == nullptr || !xf->presplit, PC_EUNSUPPORTED, "pc_conv_wgrad: pre-split input planes need the FP16X2 tensor-core path");
   float* partial = static_cast<float*>(workspace);
   int n_partials;

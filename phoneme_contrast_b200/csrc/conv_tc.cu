@@ -824,10 +824,15 @@ extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias,
 }
 
 extern "C" int pc_conv_dgrad_tc(const float* dy, const void* wp, const PcConvGeom* g, float* dx, int accumulate, int prec,
-                                const float* dy_amax, pc_stream_t stream) {
+                                const float* dy_amax, int dy_presplit, pc_stream_t stream) {
   if (!pc_conv_tc_supported(g, 1, prec)) return PC_EUNSUPPORTED;
   Params p{};
   p.A = dy; p.Bp = (const unsigned char*)wp; p.C = dx; p.a_amax = dy_amax;
+  if (dy_presplit) {      // dy = fp16 hi | lo planes already scaled by f16_operand_scale(*dy_amax) (pc_bn_*_bwd_apply)
+    PC_REQUIRE(prec == PC_PREC_FP16X2 && dy_amax != nullptr, PC_EINVAL, "pc_conv_dgrad: pre-split dy needs PC_PREC_FP16X2 and dy_amax");
+    p.presplit = 1;
+    p.plane_bytes = (size_t)g->B * g->Ho * g->Wo * g->Cout * 2;
+  }
   p.g = *g; p.mode = 1;
   p.M = (long long)g->B * g->H * g->W;
   p.Nn = g->Cin; p.Npad = npad_of(g->Cin); p.Ca = g->Cout;

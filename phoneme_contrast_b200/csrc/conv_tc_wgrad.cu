@@ -51,6 +51,8 @@ struct Params {
   int K, M, rows_per_split, stages;
   const float* dy_amax;   // FP16X2: device scalar max|dy| (null: scale 1)
   size_t plane_bytes;     // PRESPLIT: byte distance between the hi and lo planes of x
+  int dy_presplit;        // dy is a pair of fp16 planes already scaled by f16_operand_scale(*dy_amax) (F16 only)
+  size_t dy_plane_bytes;
 };
 
 __device__ __forceinline__ uint64_t smem_desc_mn_sw128(uint32_t smem_addr_bytes) {
@@ -204,6 +206,15 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
 #pragma unroll
           for (int vv = 0; vv < NV; ++vv) {
             const int n = n0 + CPG * q + 4 * NV * j + 4 * vv;
+            if (F16 && p.dy_presplit) {      // vv = 0: hi bits, vv = 1: lo bits of the 8 channels n0 + CPG*q + 8*j ..
+              uint4 bits = make_uint4(0u, 0u, 0u, 0u);
+              const int n8 = n0 + CPG * q + 8 * j;
+              if (mv && n8 < g.Cout)
+                bits = *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(p.dy) + (vv ? p.dy_plane_bytes : 0) +
+                                                       ((size_t)m * g.Cout + n8) * 2);
+              bv[h][q][vv] = make_float4(__uint_as_float(bits.x), __uint_as_float(bits.y), __uint_as_float(bits.z), __uint_as_float(bits.w));
+              continue;
+            }
             bv[h][q][vv] = (mv && n < g.Cout) ? *reinterpret_cast<const float4*>(p.dy + (size_t)m * g.Cout + n) : make_float4(0.f, 0.f, 0.f, 0.f);
             if (STEM) {
               bsum[(4 * vv) % (STEM ? 8 : 1)] += bv[h][q][vv].x; bsum[(4 * vv + 1) % (STEM ? 8 : 1)] += bv[h][q][vv].y;
@@ -281,6 +292,11 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
 #pragma unroll
           for (int q = 0; q < GB; ++q) {
             float4 b0 = bv[h][q][0], b1 = bv[h][q][NV - 1];
+            if (p.dy_presplit) {
+              *reinterpret_cast<uint4*>(b_hi + q * GRP + off) = make_uint4(__float_as_uint(b0.x), __float_as_uint(b0.y), __float_as_uint(b0.z), __float_as_uint(b0.w));
+              *reinterpret_cast<uint4*>(b_lo + q * GRP + off) = make_uint4(__float_as_uint(b1.x), __float_as_uint(b1.y), __float_as_uint(b1.z), __float_as_uint(b1.w));
+              continue;
+            }
             if (use_scale) {
               b0 = make_float4(b0.x * b_scale, b0.y * b_scale, b0.z * b_scale, b0.w * b_scale);
               b1 = make_float4(b1.x * b_scale, b1.y * b_scale, b1.z * b_scale, b1.w * b_scale);
@@ -436,6 +452,39 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ d
   }
 }
 
+// the same from pre-split gradient planes: value = (hi + lo * 2^-11) / f16_operand_scale(*amax); thread = 8 channels of a pixel
+__global__ void __launch_bounds__(256) colsum_planes_kernel(const unsigned char* __restrict__ planes, size_t plane_bytes, int M, int C,
+                                                            const float* __restrict__ amax, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float sh[256 * 8];
+  const int C8 = C >> 3, c8 = threadIdx.x % C8, ppb = 256 / C8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int m = blockIdx.x * ppb + threadIdx.x / C8; m < M; m += gridDim.x * ppb) {
+    const size_t o = ((size_t)m * C + c8 * 8) * 2;
+    const uint4 h = *reinterpret_cast<const uint4*>(planes + o), l = *reinterpret_cast<const uint4*>(planes + plane_bytes + o);
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[q])), lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[q]));
+      acc[2 * q] += fmaf(lf.x, kF16LoInv, hf.x);
+      acc[2 * q + 1] += fmaf(lf.y, kF16LoInv, hf.y);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 8; ++q) sh[threadIdx.x * 8 + q] = acc[q];
+  __syncthreads();
+  if (threadIdx.x < C8) {
+    const float inv = 1.f / f16_operand_scale(amax[0]);
+    float sres[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int t = threadIdx.x; t < 256; t += C8)
+#pragma unroll
+      for (int q = 0; q < 8; ++q) sres[q] += sh[t * 8 + q];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) out[(size_t)blockIdx.x * C + c8 * 8 + q] = sres[q] * inv;
+  }
+}
+
 static inline int pick_bn(int n) { return n <= 64 ? 64 : 128; }
 
 static int plan(const PcConvGeom* g, int* splits, int* rps) {
@@ -492,7 +541,8 @@ extern "C" size_t pc_conv_wgrad_tc_workspace(const PcConvGeom* g) {
 }
 
 extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeom* g, const PcInXform* xf, float* dw_oihw, float* db,
-                                void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, pc_stream_t stream) {
+                                void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, int dy_presplit,
+                                pc_stream_t stream) {
   PC_REQUIRE(x && dy && g && dw_oihw && workspace, PC_EINVAL, "pc_conv_wgrad_tc: null pointer");
   const bool stem = g->Cin == 1;
   PC_REQUIRE(stem ? (prec == PC_PREC_FP16X2 && pc_conv_wgrad_tc_stem_supported(g)) : pc_conv_wgrad_tc_supported(g), PC_EUNSUPPORTED,
@@ -515,6 +565,12 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
   p.rows_per_split = rps;
   const bool f16 = prec == PC_PREC_FP16X2 && (g->Cin % 64 == 0 || stem);   // 64-channel groups; otherwise the TF32x3 tiles
   p.dy_amax = f16 ? dy_amax : nullptr;
+  if (dy_presplit) {
+    PC_REQUIRE(f16 && !stem && dy_amax != nullptr && g->Cout % 8 == 0 && 256 % (g->Cout / 8) == 0, PC_EINVAL,
+               "pc_conv_wgrad: pre-split dy needs the FP16X2 tiles (Cin %% 64 == 0), dy_amax, and Cout = 8 * 2^k <= 2048");
+    p.dy_presplit = 1;
+    p.dy_plane_bytes = (size_t)p.M * g->Cout * 2;
+  }
   const uint32_t st = stem ? stage_bytes<64, true, true>() : bn == 64 ? (f16 ? stage_bytes<64, true>() : stage_bytes<64, false>())
                                : (f16 ? stage_bytes<128, true>() : stage_bytes<128, false>());
   int stages = (int)(SMEM_BUDGET / st);
@@ -568,7 +624,11 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
   }
   float* cs = p.partial + (size_t)sp * (size_t)(p.K + 1) * g->Cout;
   const int cs_ctas = kNumSMs * 2;
-  launch_pdl(colsum_kernel, dim3(cs_ctas), dim3(256), 0, stream, dy, p.M, g->Cout, cs);
+  if (dy_presplit)
+    launch_pdl(colsum_planes_kernel, dim3(cs_ctas), dim3(256), 0, stream, reinterpret_cast<const unsigned char*>(dy), p.dy_plane_bytes, p.M,
+               g->Cout, dy_amax, cs);
+  else
+    launch_pdl(colsum_kernel, dim3(cs_ctas), dim3(256), 0, stream, dy, p.M, g->Cout, cs);
   PC_LAUNCH_CHECK("colsum_kernel");
   launch_wgrad_reduce(p.partial, sp, g->R, g->S, g->Cin, g->Cout, dw_oihw, nullptr, stream);
   launch_wgrad_reduce(cs, cs_ctas, 0, 0, 0, g->Cout, nullptr, db, stream);

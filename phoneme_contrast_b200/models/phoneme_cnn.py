@@ -159,14 +159,14 @@ class _WgradLane:
             self.side = net._side_stream
             self.main = torch.cuda.current_stream()
 
-    def __call__(self, x, dy, g, xform, dw, db, prec, amax=None):
+    def __call__(self, x, dy, g, xform, dw, db, prec, amax=None, dy_presplit=False):
         if not self.enabled:
-            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax)
+            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax, dy_presplit)
             return
         self.keep.extend((x, dy))
         self.side.wait_stream(self.main)
         with torch.cuda.stream(self.side):
-            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax)
+            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax, dy_presplit)
 
     def join(self):
         if self.enabled:
@@ -340,27 +340,31 @@ def _deep_backward(net, s, demb, grads, training=True):
         r = s.blocks[i]
         g2 = (grads[blk.bn2.weight], grads[blk.bn2.bias])
         m2, m1, ms = amax.take(), amax.take(), amax.take()
+        # gradient tensors in operand form too: when every consumer of dy (data gradient and weight gradient) runs the FP16X2
+        # engine, the BatchNorm backward writes dy only as scaled fp16 hi | lo planes and the convolutions gather bytes
+        gps = (r["a1"] is not None and r["xin_ps"] is not None and prec == L.PREC_FP16X2 and r["cw2"].prec_d == L.PREC_FP16X2
+               and r["cw1"].prec_d == L.PREC_FP16X2 and (not r["proj"] or r["cws"].prec_d == L.PREC_FP16X2))
         if r["proj"]:
             convs, bns = blk.shortcut[0], blk.shortcut[1]
             dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], r["ys"], r["cs"], g2,
-                                                  (grads[bns.weight], grads[bns.bias]), m2, ms)
+                                                  (grads[bns.weight], grads[bns.bias]), m2, ms, planes=gps)
         else:
-            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None)
+            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None, planes=gps)
         if r["a1"] is not None and prec == L.PREC_FP16X2:
-            wgrad(r["a1"], dy2, r["g2"], dict(presplit=True), grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2)
+            wgrad(r["a1"], dy2, r["g2"], dict(presplit=True), grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2, gps)
         else:
             xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
             wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2)
-        dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2)
-        dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1)
+        dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2, dy_presplit=gps)
+        dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1, planes=gps)
         xin_w, xf_w = (r["xin_ps"], dict(presplit=True)) if r["xin_ps"] is not None else (r["xin"], None)
-        wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], grads[blk.conv1.bias], prec, m1)
+        wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], grads[blk.conv1.bias], prec, m1, gps)
         if r["proj"]:
-            wgrad(xin_w, dysc, r["gs"], xf_w, grads[convs.weight], grads[convs.bias], prec, ms)
-            dxin = ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], prec=r["cws"].prec_d, dy_amax=ms)
+            wgrad(xin_w, dysc, r["gs"], xf_w, grads[convs.weight], grads[convs.bias], prec, ms, gps)
+            dxin = ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], prec=r["cws"].prec_d, dy_amax=ms, dy_presplit=gps)
         else:
             dxin = dysc                                        # identity shortcut: d(out)/d(xin) passes g through
-        ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d, dy_amax=m1)
+        ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d, dy_amax=m1, dy_presplit=gps)
         dout = dxin
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
     st = s.stem

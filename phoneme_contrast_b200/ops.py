@@ -174,12 +174,13 @@ def conv_fwd(x, w, bias, g: PcConvGeom, xform=None, stats=None, prec=L.PREC_FP32
     return y
 
 
-def conv_dgrad(dy, wd, g: PcConvGeom, out=None, accumulate=False, prec=L.PREC_FP32, dy_amax=None):
+def conv_dgrad(dy, wd, g: PcConvGeom, out=None, accumulate=False, prec=L.PREC_FP32, dy_amax=None, dy_presplit=False):
     """dy_amax: 1-element device tensor holding max|dy| (FP16X2 operand scale; see include/phoneme_contrast.h)."""
     if out is None:
         out = torch.empty(g.B, g.H, g.W, g.Cin, device=dy.device, dtype=F32)
     L.note_work("pc_conv_dgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
-    call("pc_conv_dgrad", ptr(dy), ptr(wd, None), C.byref(g), ptr(out), 1 if accumulate else 0, prec, ptr(dy_amax), stream())
+    call("pc_conv_dgrad", ptr(dy, None if dy_presplit else F32), ptr(wd, None), C.byref(g), ptr(out), 1 if accumulate else 0, prec,
+         ptr(dy_amax), 1 if dy_presplit else 0, stream())
     return out
 
 
@@ -197,7 +198,7 @@ def _workspace(nbytes: int, device, tag: str = "conv") -> torch.Tensor:
     return buf
 
 
-def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_FP32, dy_amax=None):
+def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_FP32, dy_amax=None, dy_presplit=False):
     if dw is None:
         dw = torch.empty(g.Cout, g.Cin, g.R, g.S, device=x.device, dtype=F32)
     if db is None:
@@ -209,9 +210,9 @@ def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_F
         prec = L.PREC_FP32
     xf = _xf(**xform) if xform else None
     L.note_work("pc_conv_wgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
-    call("pc_conv_wgrad", ptr(x, None if (xform and xform.get("presplit")) else F32), ptr(dy), C.byref(g),
+    call("pc_conv_wgrad", ptr(x, None if (xform and xform.get("presplit")) else F32), ptr(dy, None if dy_presplit else F32), C.byref(g),
          C.byref(xf) if xf is not None else None, ptr(dw), ptr(db),
-         ptr(ws, torch.uint8), ws.numel(), prec, ptr(dy_amax), stream())
+         ptr(ws, torch.uint8), ws.numel(), prec, ptr(dy_amax), 1 if dy_presplit else 0, stream())
     return dw, db
 
 
@@ -255,21 +256,26 @@ def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None, want_planes=False):
     return (out, argmax, planes) if want_planes else (out, argmax)
 
 
-def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None):
+def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None, planes=False):
     """Gradient w.r.t. the pre-BatchNorm tensor y of out = drop * pool(relu(bn(y))) (train-mode statistics).
-    amax: optional zero-initialised 1-element tensor that receives max|dy| (operand scale of the FP16X2 convolutions)."""
+    amax: optional zero-initialised 1-element tensor that receives max|dy| (operand scale of the FP16X2 convolutions).
+    planes=True: dy is returned ONLY as fp16 hi | lo planes (uint8 [2, numel*2]) scaled by the power of two derived from a bound
+    of |dy| that is stored in `amax` (for convolutions called with dy_presplit=True)."""
     B, H, W, C_ = y.shape
     sums = torch.zeros(2, C_, device=y.device, dtype=torch.float64)
+    maxes = torch.zeros(2, device=y.device, dtype=F32) if planes else None
     args = (ptr(dout), ptr(y), B, H, W, C_, ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd), ptr(drop), pool,
             ptr(argmax, torch.uint8))
-    call("pc_bn_act_bwd_reduce", *args, ptr(sums, torch.float64), stream())
-    dy = torch.empty_like(y)
+    call("pc_bn_act_bwd_reduce", *args, ptr(sums, torch.float64), ptr(maxes), stream())
+    dy = None if planes else torch.empty_like(y)
+    dy_ps = torch.empty(2, y.numel() * 2, device=y.device, dtype=torch.uint8) if planes else None
     if dgamma is None:
         dgamma = torch.empty(C_, device=y.device, dtype=F32)
     if dbeta is None:
         dbeta = torch.empty(C_, device=y.device, dtype=F32)
-    call("pc_bn_act_bwd_apply", *args, ptr(sums, torch.float64), ptr(dy), ptr(dgamma), ptr(dbeta), ptr(amax), stream())
-    return dy, dgamma, dbeta
+    call("pc_bn_act_bwd_apply", *args, ptr(sums, torch.float64), ptr(dy), ptr(dgamma), ptr(dbeta), ptr(amax), ptr(maxes),
+         ptr(dy_ps, torch.uint8), stream())
+    return (dy_ps if planes else dy), dgamma, dbeta
 
 
 def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, want_planes=False):
@@ -283,25 +289,32 @@ def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, want_planes=F
 
 
 def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, grads2=None, grads_s=None, amax2=None,
-                    amax_s=None):
-    """Returns dy2, d(shortcut branch input: dysc for a projection shortcut, dx for identity), (dgamma2, dbeta2), (dgamma_s, dbeta_s)."""
+                    amax_s=None, planes=False):
+    """Returns dy2, d(shortcut branch input: dysc for a projection shortcut, dx for identity), (dgamma2, dbeta2), (dgamma_s, dbeta_s).
+    planes=True: dy2 -- and dysc of a projection shortcut -- come back ONLY as scaled fp16 hi | lo planes (see bn_act_bwd); the
+    identity-shortcut dx stays fp32 (it is accumulated into, not convolved)."""
     C_ = y2.shape[-1]
     n_pix = y2.numel() // C_
     dev = y2.device
     sums2 = torch.zeros(2, C_, device=dev, dtype=torch.float64)
     sums_s = torch.zeros(2, C_, device=dev, dtype=torch.float64) if co_s else None
+    maxes = torch.zeros(3, device=dev, dtype=F32) if planes else None
     call("pc_bn_add_relu_bwd_reduce", ptr(dout), ptr(out), ptr(y2), ptr(co2.mean), ptr(co2.invstd), ptr(ysc) if co_s else None,
          ptr(co_s.mean) if co_s else None, ptr(co_s.invstd) if co_s else None, n_pix, C_, ptr(sums2, torch.float64),
-         ptr(sums_s, torch.float64), stream())
-    dy2 = torch.empty_like(y2)
-    dsc = torch.empty_like(y2)
+         ptr(sums_s, torch.float64), ptr(maxes), stream())
+    ps_sc = planes and co_s is not None
+    dy2 = None if planes else torch.empty_like(y2)
+    dsc = None if ps_sc else torch.empty_like(y2)
+    dy2_ps = torch.empty(2, y2.numel() * 2, device=dev, dtype=torch.uint8) if planes else None
+    dsc_ps = torch.empty(2, y2.numel() * 2, device=dev, dtype=torch.uint8) if ps_sc else None
     g2 = grads2 or (torch.empty(C_, device=dev, dtype=F32), torch.empty(C_, device=dev, dtype=F32))
     gs = grads_s or ((torch.empty(C_, device=dev, dtype=F32), torch.empty(C_, device=dev, dtype=F32)) if co_s else (None, None))
     call("pc_bn_add_relu_bwd_apply", ptr(dout), ptr(out), ptr(y2), ptr(co2.scale), ptr(co2.mean), ptr(co2.invstd),
          ptr(sums2, torch.float64), ptr(ysc) if co_s else None, ptr(co_s.scale) if co_s else None,
          ptr(co_s.mean) if co_s else None, ptr(co_s.invstd) if co_s else None, ptr(sums_s, torch.float64), n_pix, C_,
-         ptr(dy2), ptr(dsc), ptr(g2[0]), ptr(g2[1]), ptr(gs[0]), ptr(gs[1]), ptr(amax2), ptr(amax_s), stream())
-    return dy2, dsc, g2, gs
+         ptr(dy2), ptr(dsc), ptr(g2[0]), ptr(g2[1]), ptr(gs[0]), ptr(gs[1]), ptr(amax2), ptr(amax_s if (ps_sc or not planes) else None),
+         ptr(maxes), ptr(dy2_ps, torch.uint8), ptr(dsc_ps, torch.uint8), stream())
+    return (dy2_ps if planes else dy2), (dsc_ps if ps_sc else dsc), g2, gs
 
 
 def attn_pool_fwd(a, w=None, b0=None):

@@ -247,3 +247,34 @@ def test_tc_conv_fwd_presplit_input(case):
     y1 = ops.conv_fwd(planes, cw.wf, bias, g, dict(presplit=True), st, cw.prec_f)
     assert torch.equal(y0, y1)
     np.testing.assert_allclose(st[0].cpu().numpy(), y0.double().sum(dim=(0, 1, 2)).cpu().numpy(), rtol=1e-6, atol=1e-4)
+
+
+@pytest.mark.parametrize("case", [(4, 20, 51, 64, 64, 3, 1, 1), (3, 20, 51, 64, 128, 3, 2, 1), (5, 3, 7, 512, 512, 3, 1, 1)])
+def test_gradient_planes_match_fp32_gradients(case):
+    """BatchNorm backward writing dy only as scaled fp16 hi | lo planes (scale from a bound of |dy|) + dgrad / wgrad gathering
+    those bytes == the fp32-dy path (same FP16X2 engine) to 2e-5 of the result's max."""
+    from phoneme_contrast_b200 import ops
+    B, H, W, Cin, Cout, k, stride, pad = case
+    g = ops.conv_geom(B, H, W, Cin, Cout, k, stride, pad)
+    gen = torch.Generator(device=DEV).manual_seed(Cin + 3 * Cout + k)
+    x = torch.randn(B, H, W, Cin, device=DEV, generator=gen)
+    w = torch.randn(Cout, Cin, k, k, device=DEV, generator=gen) * (2.0 / (Cin * k * k)) ** 0.5
+    yconv = torch.randn(B, g.Ho, g.Wo, Cout, device=DEV, generator=gen)          # pre-BN conv output
+    dout = torch.randn(B, g.Ho, g.Wo, Cout, device=DEV, generator=gen) * 1e-6    # realistic gradient magnitude
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV)
+    st = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    st[0] = yconv.double().sum((0, 1, 2)); st[1] = (yconv.double() ** 2).sum((0, 1, 2))
+    co = ops.bn_finalize(st, B * g.Ho * g.Wo, bn, True)
+    cw = ops.ConvWeights(w, g, 3)
+    a0, a1 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    dy, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a0)
+    dy_ps, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a1, planes=True)
+    assert float(a1) >= float(a0) > 0 and float(a1) <= 64 * float(a0)            # the bound is above, and near, the true max
+    dx0 = ops.conv_dgrad(dy, cw.wd, g, prec=cw.prec_d, dy_amax=a0)
+    dx1 = ops.conv_dgrad(dy_ps, cw.wd, g, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+    assert float((dx0 - dx1).abs().max()) <= 2e-5 * float(dx0.abs().max())
+    planes = ops.bn_act_split(x)
+    dw0, db0 = ops.conv_wgrad(x, dy, g, None, prec=3, dy_amax=a0)
+    dw1, db1 = ops.conv_wgrad(planes, dy_ps, g, dict(presplit=True), prec=3, dy_amax=a1, dy_presplit=True)
+    assert float((dw0 - dw1).abs().max()) <= 2e-5 * float(dw0.abs().max())
+    assert float((db0 - db1).abs().max()) <= 1e-5 * float(dy.abs().sum(dim=(0, 1, 2)).max())
