@@ -338,7 +338,7 @@ conv_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, PcC
 // shared memory, so the result does not depend on scheduling.
 __global__ void __launch_bounds__(256)
 conv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int R, int S, int Cin, int Cout,
-                         float* __restrict__ dw, float* __restrict__ db) {
+                         float* __restrict__ dw, float* __restrict__ db, const float* __restrict__ bias_partial, int n_bias) {
   pdl_trigger();
   pdl_wait();
   __shared__ double sh[8][32][4];
@@ -349,9 +349,14 @@ conv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int R,
   const long long i4 = (long long)blockIdx.x * 32 + tx;
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   if (i4 < total4) {
-    const float4* src = reinterpret_cast<const float4*>(partial) + i4;
-    for (int sp = ty; sp < n_splits; sp += 8) {
-      const float4 a = src[(size_t)sp * total4];
+    // the bias row (k == K) may come from a separate set of partials [n_bias][Cout] (column sums of dy) instead of the splits
+    const bool bias_row = bias_partial != nullptr && (i4 << 2) >= (long long)K * Cout;
+    const float4* src = bias_row ? reinterpret_cast<const float4*>(bias_partial) + (i4 - ((long long)K * Cout >> 2))
+                                 : reinterpret_cast<const float4*>(partial) + i4;
+    const size_t stride4 = bias_row ? (size_t)(Cout >> 2) : (size_t)total4;
+    const int n_part = bias_row ? n_bias : n_splits;
+    for (int sp = ty; sp < n_part; sp += 8) {
+      const float4 a = src[(size_t)sp * stride4];
       s0 += (double)a.x; s1 += (double)a.y; s2 += (double)a.z; s3 += (double)a.w;
     }
   }
@@ -559,9 +564,11 @@ conv_stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy
   }
 }
 
-void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream) {
+void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream,
+                         const float* bias_partial, int n_bias) {
   const long long total4 = ((long long)(R * S * Cin + 1) * Cout) >> 2;
-  launch_pdl(conv_wgrad_reduce_kernel, dim3(ceil_div(total4, 32)), dim3(256), 0, stream, partial, n_splits, R, S, Cin, Cout, dw, db);
+  launch_pdl(conv_wgrad_reduce_kernel, dim3(ceil_div(total4, 32)), dim3(256), 0, stream, partial, n_splits, R, S, Cin, Cout, dw, db,
+             bias_partial, n_bias);
   count_launch();
 }
 
@@ -757,7 +764,8 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
   }
   const long long total4 = ((long long)(g->R * g->S * g->Cin + 1) * g->Cout) >> 2;
   int grid = ceil_div(total4, 32);
-  launch_pdl(conv_wgrad_reduce_kernel, dim3(grid), dim3(256), 0, stream, partial, n_partials, g->R, g->S, g->Cin, g->Cout, dw_oihw, db);
+  launch_pdl(conv_wgrad_reduce_kernel, dim3(grid), dim3(256), 0, stream, partial, n_partials, g->R, g->S, g->Cin, g->Cout, dw_oihw, db,
+             (const float*)nullptr, 0);
   PC_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
   return PC_OK;
 }

@@ -513,7 +513,8 @@ static int plan(const PcConvGeom* g, int* splits, int* rps) {
 using namespace pc;
 using namespace pc::tcwg;
 
-namespace pc { void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream); }
+namespace pc { void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream,
+                                        const float* bias_partial = nullptr, int n_bias = 0); }
 
 // single-channel stem on the FP16X2 tiles: taps as the (padded) M rows
 extern "C" int pc_conv_wgrad_tc_stem_supported(const PcConvGeom* g) {
@@ -630,8 +631,7 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
   else
     launch_pdl(colsum_kernel, dim3(cs_ctas), dim3(256), 0, stream, dy, p.M, g->Cout, cs);
   PC_LAUNCH_CHECK("colsum_kernel");
-  launch_wgrad_reduce(p.partial, sp, g->R, g->S, g->Cin, g->Cout, dw_oihw, nullptr, stream);
-  launch_wgrad_reduce(cs, cs_ctas, 0, 0, 0, g->Cout, nullptr, db, stream);
+  launch_wgrad_reduce(p.partial, sp, g->R, g->S, g->Cin, g->Cout, dw_oihw, db, stream, cs, cs_ctas);   // one launch: dw and db
   PC_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
   return PC_OK;
 }

@@ -134,8 +134,8 @@ class _AmaxSlots:
     """One zeroed float per gradient tensor; the BatchNorm-backward apply kernels atomically max |dy| into a slot and the
     convolutions that consume that dy read it back on the device (no host sync)."""
 
-    def __init__(self, device, n):
-        self.buf = torch.zeros(n, device=device, dtype=torch.float32)
+    def __init__(self, device, n, zp=None):
+        self.buf = zp.take((n,), torch.float32) if zp is not None else torch.zeros(n, device=device, dtype=torch.float32)
         self.k = 0
 
     def take(self):
@@ -334,7 +334,8 @@ def _deep_backward(net, s, demb, grads, training=True):
     keep = []
     wgrad = _WgradLane(net, keep)
     dout = _head_bwd(net, s, demb, grads, training)
-    amax = _AmaxSlots(demb.device, 3 * len(s.blocks))   # max|dy| per gradient tensor a convolution consumes (FP16X2 scale)
+    zp = ops.ZeroPool(demb.device)                      # zeroed reduction targets of all BatchNorm backward passes
+    amax = _AmaxSlots(demb.device, 3 * len(s.blocks), zp)   # max|dy| per gradient tensor a convolution consumes (FP16X2 scale)
     for i in reversed(range(len(s.blocks))):
         blk = net.conv_blocks[i]
         r = s.blocks[i]
@@ -347,16 +348,16 @@ def _deep_backward(net, s, demb, grads, training=True):
         if r["proj"]:
             convs, bns = blk.shortcut[0], blk.shortcut[1]
             dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], r["ys"], r["cs"], g2,
-                                                  (grads[bns.weight], grads[bns.bias]), m2, ms, planes=gps)
+                                                  (grads[bns.weight], grads[bns.bias]), m2, ms, planes=gps, zp=zp)
         else:
-            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None, planes=gps)
+            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None, planes=gps, zp=zp)
         if r["a1"] is not None and prec == L.PREC_FP16X2:
             wgrad(r["a1"], dy2, r["g2"], dict(presplit=True), grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2, gps)
         else:
             xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
             wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2)
         dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2, dy_presplit=gps)
-        dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1, planes=gps)
+        dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1, planes=gps, zp=zp)
         xin_w, xf_w = (r["xin_ps"], dict(presplit=True)) if r["xin_ps"] is not None else (r["xin"], None)
         wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], grads[blk.conv1.bias], prec, m1, gps)
         if r["proj"]:
@@ -368,7 +369,7 @@ def _deep_backward(net, s, demb, grads, training=True):
         dout = dxin
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
     st = s.stem
-    dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias])
+    dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias], zp=zp)
     wgrad(s.x, dy0, st["g"], None, grads[conv0.weight], grads[conv0.bias], prec)
     wgrad.join()
 

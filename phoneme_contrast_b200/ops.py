@@ -216,6 +216,30 @@ def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_F
     return dw, db
 
 
+class ZeroPool:
+    """One zero-filled scratch buffer per backward pass: the per-layer fp64 reduction targets and float max slots are slices of
+    it (one fill kernel instead of one per tensor)."""
+
+    def __init__(self, device, nbytes=1 << 17):
+        self.buf = torch.zeros(nbytes, device=device, dtype=torch.uint8)
+        self.off = 0
+
+    def take(self, shape, dtype):
+        n = 1
+        for d in shape:
+            n *= d
+        nb = n * torch.empty((), dtype=dtype).element_size()
+        start = (self.off + 15) & ~15
+        if start + nb > self.buf.numel():
+            return torch.zeros(shape, device=self.buf.device, dtype=dtype)
+        self.off = start + nb
+        return self.buf[start:start + nb].view(dtype).view(shape)
+
+
+def _zeros(zp, shape, dtype, device):
+    return zp.take(shape, dtype) if zp is not None else torch.zeros(shape, device=device, dtype=dtype)
+
+
 class BnCoeffs:
     """scale/shift/mean/invstd of one BatchNorm for the current batch (or from running stats in eval)."""
     __slots__ = ("scale", "shift", "mean", "invstd", "C")
@@ -256,14 +280,14 @@ def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None, want_planes=False):
     return (out, argmax, planes) if want_planes else (out, argmax)
 
 
-def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None, planes=False):
+def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None, planes=False, zp=None):
     """Gradient w.r.t. the pre-BatchNorm tensor y of out = drop * pool(relu(bn(y))) (train-mode statistics).
     amax: optional zero-initialised 1-element tensor that receives max|dy| (operand scale of the FP16X2 convolutions).
     planes=True: dy is returned ONLY as fp16 hi | lo planes (uint8 [2, numel*2]) scaled by the power of two derived from a bound
     of |dy| that is stored in `amax` (for convolutions called with dy_presplit=True)."""
     B, H, W, C_ = y.shape
-    sums = torch.zeros(2, C_, device=y.device, dtype=torch.float64)
-    maxes = torch.zeros(2, device=y.device, dtype=F32) if planes else None
+    sums = _zeros(zp, (2, C_), torch.float64, y.device)
+    maxes = _zeros(zp, (2,), F32, y.device) if planes else None
     args = (ptr(dout), ptr(y), B, H, W, C_, ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd), ptr(drop), pool,
             ptr(argmax, torch.uint8))
     call("pc_bn_act_bwd_reduce", *args, ptr(sums, torch.float64), ptr(maxes), stream())
@@ -289,16 +313,16 @@ def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, want_planes=F
 
 
 def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, grads2=None, grads_s=None, amax2=None,
-                    amax_s=None, planes=False):
+                    amax_s=None, planes=False, zp=None):
     """Returns dy2, d(shortcut branch input: dysc for a projection shortcut, dx for identity), (dgamma2, dbeta2), (dgamma_s, dbeta_s).
     planes=True: dy2 -- and dysc of a projection shortcut -- come back ONLY as scaled fp16 hi | lo planes (see bn_act_bwd); the
     identity-shortcut dx stays fp32 (it is accumulated into, not convolved)."""
     C_ = y2.shape[-1]
     n_pix = y2.numel() // C_
     dev = y2.device
-    sums2 = torch.zeros(2, C_, device=dev, dtype=torch.float64)
-    sums_s = torch.zeros(2, C_, device=dev, dtype=torch.float64) if co_s else None
-    maxes = torch.zeros(3, device=dev, dtype=F32) if planes else None
+    sums2 = _zeros(zp, (2, C_), torch.float64, dev)
+    sums_s = _zeros(zp, (2, C_), torch.float64, dev) if co_s else None
+    maxes = _zeros(zp, (3,), F32, dev) if planes else None
     call("pc_bn_add_relu_bwd_reduce", ptr(dout), ptr(out), ptr(y2), ptr(co2.mean), ptr(co2.invstd), ptr(ysc) if co_s else None,
          ptr(co_s.mean) if co_s else None, ptr(co_s.invstd) if co_s else None, n_pix, C_, ptr(sums2, torch.float64),
          ptr(sums_s, torch.float64), ptr(maxes), stream())
