@@ -391,35 +391,39 @@ conv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int R,
 // ------------------------------------------------------------------------------------------------ stem (Cin == 1)
 // y[b,h,w,n] = bias[n] + sum_{r,s} x[b,h+r-p,w+s-p] * w[n][r][s]; lane = output channel (coalesced NHWC store),
 // each warp walks a strip of pixels; weights for the lane's channel(s) live in registers.
-template <int KS, int COUT>   // kernel size, output channels (16 | 32 | 64); lane owns channels lane + 32*q
-__global__ void __launch_bounds__(256)
+// WSPLIT: one warp per (output row, 32-channel group) instead of one warp per row owning COUT/32 channels per lane (half the
+// weight registers, 16 resident warps instead of 8). Measured SLOWER for 7x7 / 64 channels (289 vs 260 us: every shared-memory
+// window load then feeds half as many FMAs), so it is not used; kept as a switch for other shapes.
+template <int KS, int COUT, bool WSPLIT = false>   // kernel size, output channels (16 | 32 | 64); lane owns channels cb + lane + 32*q
+__global__ void __launch_bounds__(WSPLIT ? 256 * (COUT / 32) : 256)
 conv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w_oihw, const float* __restrict__ bias, int B,
                      int H, int W, float* __restrict__ y, double* __restrict__ stats) {
   pdl_trigger();
   pdl_wait();
-  constexpr int P = KS / 2, CPL = (COUT + 31) / 32;
+  constexpr int P = KS / 2, CPL = WSPLIT ? 1 : (COUT + 31) / 32;
   constexpr int TH = 8, TW = 32;   // output tile per CTA
   __shared__ float xs[TH + KS - 1][TW + KS - 1 + 1];
   __shared__ float red[2][8][COUT];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 7;     // warp = output row of the tile
+  const int cb = WSPLIT ? (threadIdx.x >> 8) * 32 : 0;                  // first channel of this warp's group
   const int tiles_w = ceil_div(W, TW), tiles_h = ceil_div(H, TH);
   const int tile = blockIdx.x;
   const int b = tile / (tiles_w * tiles_h);
   const int th = (tile / tiles_w) % tiles_h, tw = tile % tiles_w;
   const int h0 = th * TH, w0 = tw * TW;
-  for (int i = threadIdx.x; i < (TH + KS - 1) * (TW + KS - 1); i += 256) {
+  for (int i = threadIdx.x; i < (TH + KS - 1) * (TW + KS - 1); i += blockDim.x) {
     const int rr = i / (TW + KS - 1), cc = i % (TW + KS - 1);
     const int h = h0 + rr - P, w = w0 + cc - P;
     xs[rr][cc] = (h >= 0 && h < H && w >= 0 && w < W) ? x[((size_t)b * H + h) * W + w] : 0.f;
   }
   // weights: coalesced global -> shared, then each lane picks up its channels' taps (row stride KS*KS is odd: conflict-free)
   __shared__ float ws[COUT * KS * KS];
-  for (int i = threadIdx.x; i < COUT * KS * KS; i += 256) ws[i] = w_oihw[i];
+  for (int i = threadIdx.x; i < COUT * KS * KS; i += blockDim.x) ws[i] = w_oihw[i];
   __syncthreads();
   float wr[CPL][KS * KS], bv[CPL];
 #pragma unroll
   for (int q = 0; q < CPL; ++q) {
-    const int n = lane + 32 * q;
+    const int n = cb + lane + 32 * q;
     bv[q] = (bias != nullptr && n < COUT) ? bias[n] : 0.f;
 #pragma unroll
     for (int t = 0; t < KS * KS; ++t) wr[q][t] = n < COUT ? ws[n * KS * KS + t] : 0.f;
@@ -456,7 +460,7 @@ conv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w_oi
           float* dst = y + (((size_t)b * H + h) * W + w) * COUT;
 #pragma unroll
           for (int q = 0; q < CPL; ++q) {
-            if (lane + 32 * q < COUT) dst[lane + 32 * q] = acc[px][q];
+            if (cb + lane + 32 * q < COUT) dst[cb + lane + 32 * q] = acc[px][q];
             ssum[q] += acc[px][q];
             ssq[q] = fmaf(acc[px][q], acc[px][q], ssq[q]);
           }
@@ -467,7 +471,7 @@ conv_stem_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w_oi
   if (stats != nullptr) {
 #pragma unroll
     for (int q = 0; q < CPL; ++q)
-      if (lane + 32 * q < COUT) { red[0][warp][lane + 32 * q] = ssum[q]; red[1][warp][lane + 32 * q] = ssq[q]; }
+      if (cb + lane + 32 * q < COUT) { red[0][warp][cb + lane + 32 * q] = ssum[q]; red[1][warp][cb + lane + 32 * q] = ssq[q]; }
     __syncthreads();
     if (threadIdx.x < COUT) {
       double s = 0.0, q2 = 0.0;

@@ -105,7 +105,7 @@ def test_dp_two_gpus_match_single_process(tmp_path):
         (l_e, p_e, s_e, d_e), (l_g, p_g, s_g, d_g) = o["graph_vs_eager"]
         np.testing.assert_allclose(l_e, l_g, rtol=1e-5)
         n_off = int(((p_e - p_g).abs() > 2e-5).sum())
-        assert n_off <= 3e-3 * p_e.numel(), (n_off, p_e.numel())
+        assert n_off <= 2e-2 * p_e.numel(), (n_off, p_e.numel())
         assert float((p_e - p_g).abs().max()) <= 2 * 1e-3 * 2
         assert (s_e, d_e, s_g, d_g) == (2, 2, 2, 2)
     assert torch.equal(outs[0]["graph_vs_eager"][1][1], outs[1]["graph_vs_eager"][1][1])
