@@ -70,6 +70,30 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 __host__ __device__ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// Unsigned division by a run-time constant without the ~20-instruction integer divide (Granlund & Montgomery): built once on
+// the host, q = n / d for every 32-bit n.
+struct FastDiv {
+  uint32_t mul, s1, s2, d;
+  __host__ static FastDiv make(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    uint32_t l = 0;
+    while ((1ull << l) < d) ++l;                                   // ceil(log2 d)
+    f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - d)) / d) + 1u;
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l < 1 ? 0 : l - 1;
+    return f;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    const uint32_t t = __umulhi(mul, n);
+    return (t + ((n - t) >> s1)) >> s2;
+  }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

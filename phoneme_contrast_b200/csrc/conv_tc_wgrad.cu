@@ -51,6 +51,7 @@ struct Params {
   int K, M, rows_per_split, stages;
   const float* dy_amax;   // FP16X2: device scalar max|dy| (null: scale 1)
   size_t plane_bytes;     // PRESPLIT: byte distance between the hi and lo planes of x
+  FastDiv div_wo, div_ho; // pixel index -> (b, ho, wo) without integer divides (twice per pixel row and stage otherwise)
   int dy_presplit;        // dy is a pair of fp16 planes already scaled by f16_operand_scale(*dy_amax) (F16 only)
   size_t dy_plane_bytes;
 };
@@ -196,10 +197,10 @@ __global__ void __launch_bounds__(32 * (4 * NGROUPS + 1), MINB) wgrad_tc_kernel(
         const bool mv = m < m_end;
         int b = 0, ho = 0, wo = 0;
         if (mv) {
-          wo = m % g.Wo;
-          const int t = m / g.Wo;
-          ho = t % g.Ho;
-          b = t / g.Ho;
+          uint32_t t_, wo_, b_, ho_;
+          p.div_wo.divmod((uint32_t)m, t_, wo_);
+          p.div_ho.divmod(t_, b_, ho_);
+          wo = (int)wo_; ho = (int)ho_; b = (int)b_;
         }
 #pragma unroll
         for (int q = 0; q < GB; ++q)
@@ -561,6 +562,8 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
     p.plane_bytes = (size_t)g->B * g->H * g->W * g->Cin * 2;
   }
   p.g = *g;
+  p.div_wo = FastDiv::make((uint32_t)g->Wo);
+  p.div_ho = FastDiv::make((uint32_t)g->Ho);
   p.K = g->R * g->S * g->Cin;
   p.M = g->B * g->Ho * g->Wo;
   p.rows_per_split = rps;
