@@ -439,7 +439,7 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
             "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -554,10 +554,24 @@ def main():
                                     "sample": f"oracle port (same ATen ops as the reference) of the same {wl['views']}-view step: 1 warm-up + 3 timed steps"}
             pc, bt, _ = cpu_frontend(512)
             line["cpu_baseline"]["frontend_clips_per_sec"] = {"per_clip_calls": pc, "batched": bt, "sample": "512 clips"}
-    print(json.dumps(line))
+    _emit(line)
     if parallel is not None:
         torch.distributed.destroy_process_group()
 
 
+def _emit(line: dict) -> None:
+    """The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version banner with plain printf),
+    so main() runs with file descriptor 1 pointing at stderr and the line goes to the saved real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    while data:
+        data = data[os.write(fd, data):]
+
+
+_REAL_STDOUT = None
+
 if __name__ == "__main__":
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)                 # everything else that prints to stdout (python or C) now lands on stderr
     main()

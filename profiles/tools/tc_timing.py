@@ -3,7 +3,7 @@ sys.path.insert(0,'.')
 from phoneme_contrast_b200 import ops, _lib as L
 lib=L.lib()
 lib.pc_tc_set_debug.argtypes=[ctypes.c_void_p]; lib.pc_tc_set_debug.restype=None
-def run(B,H,W,Cin,Cout,k,stride,pad,prec=1,xf=True):
+def run(B,H,W,Cin,Cout,k,stride,pad,prec=1,xf=True,presplit=False):
     g=ops.conv_geom(B,H,W,Cin,Cout,k,stride,pad)
     x=torch.randn(B,H,W,Cin,device='cuda'); w=torch.randn(Cout,Cin,k,k,device='cuda')*0.05; bias=torch.zeros(Cout,device='cuda')
     sc=torch.ones(Cin,device='cuda'); sh=torch.zeros(Cin,device='cuda')
@@ -12,6 +12,8 @@ def run(B,H,W,Cin,Cout,k,stride,pad,prec=1,xf=True):
     M=B*g.Ho*g.Wo; ntiles=((M+127)//128)*max(1,(Cout+127)//128 if Cout>64 else 1)
     dbg=torch.zeros(ntiles*4,16,device='cuda',dtype=torch.int64)
     xform=dict(scale=sc,shift=sh,relu=True) if xf else None
+    if presplit:
+        x=ops.bn_act_split(x,sc,sh,None,relu=True); xform=dict(presplit=True)
     for it in range(3):
         y=ops.conv_fwd(x,cw.wf,bias,g,xform,stats,cw.prec_f)
     torch.cuda.synchronize()
@@ -29,8 +31,7 @@ def run(B,H,W,Cin,Cout,k,stride,pad,prec=1,xf=True):
     for i,n in enumerate(names): print(f"   {n:18s} median {med[i]:9.0f} cyc")
     span=(d[:,12].max()-d[:,0].min())
     print("   whole-kernel span cycles", span, " CTAs/SM waves ~", len(d)/148)
-for prec in (1,3):
-    print('=== prec',prec)
-    run(256,20,51,64,64,3,1,1,prec=prec)
-    run(256,5,13,256,256,3,1,1,prec=prec)
-    run(256,3,7,512,512,3,1,1,prec=prec)
+print('=== presplit fp16x2')
+run(256,20,51,64,64,3,1,1,prec=3,presplit=True)
+run(256,5,13,256,256,3,1,1,prec=3,presplit=True)
+run(256,3,7,512,512,3,1,1,prec=3,presplit=True)
