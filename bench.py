@@ -40,7 +40,7 @@ FLOP_PER_SAMPLE = {"phoneme_cnn": 3 * 298.07e6, "phoneme_cnn_deep": 3 * 568.59e6
 TRAFFIC_NCU = {}
 try:
     import re as _re
-    _txt = open(os.path.join(ROOT, "profiles", "r1c_tc_conv_full.md")).read()
+    _txt = open(os.path.join(ROOT, "profiles", "r1d_tc_conv_full.md")).read()
     for _entry, _pat in (("pc_conv_fwd", "igemm_tc_kernel"), ("pc_conv_dgrad", "igemm_tc_kernel"), ("pc_conv_wgrad", "wgrad_tc_kernel")):
         _vals = []
         for _sec in _txt.split("## ")[1:]:
@@ -282,7 +282,7 @@ def roofline_from_profile(prof, pk, pk_kind):
     ach = (top["work"] / (top["ms"] * 1e-3)) / 1e12 if top["work"] else None
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     return {"bound": "tensor", "kernel": kernel_of.get(name, name), "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
-            "traffic": TRAFFIC_NCU.get(name), "traffic_note": "mean dram read+write bytes per launch over the launches captured with ncu --set full (profiles/r1c_tc_conv_full.md)",
+            "traffic": TRAFFIC_NCU.get(name), "traffic_note": "mean dram read+write bytes per launch over the launches captured with ncu --set full (profiles/r1d_tc_conv_full.md)",
             "peak_source": f"{pk_kind} cuBLAS bf16 sustained (MEASURED_PEAKS.json); kernel timed inside a long step; achieved counts the convolution's algorithmic fp32 FLOPs once, while the kernels issue 3 fp16 tensor-core products per operand pair (FP16x2 split for fp32-level accuracy), i.e. their own ceiling is peak/3",
             "kernel_share_of_step": top["ms"] / total, "kernel_ms_per_step": top["ms"], "launches_per_step": top["calls"],
             "all_conv": {"ms_per_step": conv_ms, "tflops": conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
