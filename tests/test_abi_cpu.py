@@ -174,3 +174,40 @@ def test_pipeline_factory(golden):
     pipe = build_augmentation_pipeline(cfg)      # reference tests/test_transforms.py:90-103
     assert len(pipe.transforms) == 2
     assert isinstance(pipe.transforms[0], TimeMask) and isinstance(pipe.transforms[1], FrequencyMask)
+
+
+def test_zero_pool_slices_are_zero_aligned_and_disjoint():
+    """ops.ZeroPool hands out dtype views of one zeroed buffer (host logic, runs on CPU tensors too)."""
+    import torch
+    from phoneme_contrast_b200 import ops
+    zp = ops.ZeroPool("cpu", nbytes=4096)
+    a = zp.take((2, 64), torch.float64)
+    b = zp.take((3,), torch.float32)
+    c = zp.take((2, 32), torch.float64)
+    assert a.dtype == torch.float64 and a.shape == (2, 64) and b.shape == (3,) and c.shape == (2, 32)
+    assert float(a.abs().sum()) == 0.0 and float(b.abs().sum()) == 0.0
+    a.fill_(1.0); b.fill_(2.0); c.fill_(3.0)
+    assert float(a.sum()) == 128.0 and float(b.sum()) == 6.0 and float(c.sum()) == 192.0      # no overlap
+    for t in (a, b, c):
+        assert t.data_ptr() % 16 == 0
+    big = zp.take((4096,), torch.float64)            # does not fit any more: falls back to a fresh zero tensor
+    assert big.shape == (4096,) and float(big.abs().sum()) == 0.0
+
+
+def test_fastdiv_formula_matches_integer_division():
+    """Mirror of common.cuh:FastDiv (multiply-shift division used by the weight-gradient producers)."""
+    import random
+
+    def make(d):
+        l = 0
+        while (1 << l) < d:
+            l += 1
+        return (((1 << 32) * ((1 << l) - d)) // d + 1) & 0xFFFFFFFF, min(l, 1), max(l - 1, 0)
+
+    rnd = random.Random(0)
+    for d in [1, 2, 3, 5, 7, 13, 20, 26, 40, 51, 101, 1020, 4040, 65535, 1000003, 2**31 - 1]:
+        mul, s1, s2 = make(d)
+        for n in [0, 1, d - 1, d, d + 1, 2**31 - 1, 2**32 - 1] + [rnd.randrange(2**32) for _ in range(2000)]:
+            t = (mul * n) >> 32
+            q = ((t + ((n - t) >> s1)) & 0xFFFFFFFF) >> s2
+            assert q == n // d, (d, n)
