@@ -68,6 +68,9 @@ typedef struct PcMfccConsts { /* device pointers, built once by the host (featur
   const float* tw;            /* twiddles: cos/sin tables, see mfcc.cu                                 */
   int32_t n_fft, hop, n_mels, n_mfcc;
   int32_t fb_wmax;            /* max over filters of fb_len (0 = unknown: assume PC_FB_MAXW)                  */
+  float preemph;              /* optional pre-emphasis coefficient a: y[n] = x[n] - a x[n-1], y[0] = x[0], applied before
+                               * the reflect padding. 0 = off = the reference's code path (north_star names the stage;
+                               * src/datasets/features.py has none, publication/sections/02_methods.md:32 quotes 0.97) */
 } PcMfccConsts;
 #define PC_FB_MAXW 32
 
@@ -154,6 +157,12 @@ typedef struct PcInXform {
  * redoing this arithmetic for every tap and output-channel tile. hw = pixels per sample (row of `drop` = pixel / hw). */
 int pc_bn_act_split(const float* y, int64_t n_pix, int C, int hw, const float* scale, const float* shift, const float* drop,
                     int relu, void* planes, pc_stream_t stream);
+
+/* FP16X2 activation planes are written unscaled; every plane writer (pc_bn_act_split, the `planes` outputs of pc_bn_act_fwd /
+ * pc_bn_add_relu_fwd) raises a sticky device flag when a value exceeds fp16's range (|a| > 65504, or NaN). This call copies the
+ * flag to *host_flag (synchronising `stream`) and clears it when reset != 0. A set flag means the step's convolutions saw inf:
+ * re-run with PC_PREC_TF32X3, which has no range assumption (ContrastiveTrainer does this at its per-epoch read-back). */
+int pc_f16_overflow_query(int reset, int* host_flag, pc_stream_t stream);
 
 /* OIHW fp32 -> fwd layout Wf [(r,s,c)][o] and dgrad layout Wd [(r,s,o)][c] (either may be NULL). */
 int pc_pack_conv_weight(const float* w_oihw, int O, int I, int R, int S, float* wf, float* wd, pc_stream_t stream);

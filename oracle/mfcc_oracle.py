@@ -77,9 +77,18 @@ def dct_matrix(n_mfcc: int = 40, n_mels: int = 80) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------- pipeline
-def power_spectrogram(wave: np.ndarray, n_fft: int = 400, hop: int = 160) -> np.ndarray:
+def preemphasis(wave: np.ndarray, coeff: float) -> np.ndarray:
+    """torchaudio.functional.preemphasis (functional.py: `waveform[..., 1:] -= coeff * waveform[..., :-1]`): the optional
+    stage north_star names; the reference's MFCCExtractor has none (coeff 0 = identity)."""
+    wave = np.array(wave, dtype=np.float64, copy=True)
+    if coeff:
+        wave[..., 1:] -= coeff * np.asarray(wave[..., :-1]).copy()
+    return wave
+
+
+def power_spectrogram(wave: np.ndarray, n_fft: int = 400, hop: int = 160, preemph: float = 0.0) -> np.ndarray:
     """wave [B,S] -> |STFT|^2 [B, n_fft//2+1, T], center=True, reflect pad, periodic Hann."""
-    wave = np.asarray(wave, dtype=np.float64)
+    wave = preemphasis(wave, preemph)
     pad = n_fft // 2
     padded = np.pad(wave, ((0, 0), (pad, pad)), mode="reflect")
     n_frames = 1 + (padded.shape[1] - n_fft) // hop
@@ -92,7 +101,7 @@ def power_spectrogram(wave: np.ndarray, n_fft: int = 400, hop: int = 160) -> np.
 
 def mel_db(wave: np.ndarray, *, top_db: float | None = 80.0, clamp_scope: str = "clip",
            n_fft: int = 400, hop: int = 160, n_mels: int = 80, sample_rate: int = 16000,
-           f_min: float = 0.0, f_max: float | None = None) -> np.ndarray:
+           f_min: float = 0.0, f_max: float | None = None, preemph: float = 0.0) -> np.ndarray:
     """wave [B,S] -> mel power in dB [B, n_mels, T].
 
     clamp_scope 'clip': the amax of the top_db clamp is taken per clip (what the dataset does:
@@ -100,7 +109,7 @@ def mel_db(wave: np.ndarray, *, top_db: float | None = 80.0, clamp_scope: str = 
     amplitude_to_DB does for a batched [B,80,T] input (functional.py:396-399).
     """
     f_max = f_max or sample_rate / 2
-    power = power_spectrogram(wave, n_fft, hop)
+    power = power_spectrogram(wave, n_fft, hop, preemph)
     fb = mel_filterbank(n_fft // 2 + 1, f_min, f_max, n_mels, sample_rate).astype(np.float64)
     mel = np.einsum("bft,fm->bmt", power, fb)
     db = 10.0 * np.log10(np.maximum(mel, 1e-10))

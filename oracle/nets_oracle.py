@@ -66,14 +66,25 @@ def _resblock(sd, p, x, stride, training, dropm, update_stats):
     return F.relu(out + sc)
 
 
+def _plainblock(sd, p, x, stride, training, dropm, update_stats):
+    """The use_residual=False block (phoneme_cnn.py:231-245): conv(stride) BN ReLU conv BN ReLU Dropout2d."""
+    x = F.conv2d(x, sd[f"{p}.0.weight"], sd[f"{p}.0.bias"], stride=stride, padding=1)
+    x = F.relu(_bn(x, sd, f"{p}.1", training, update=update_stats))
+    x = F.conv2d(x, sd[f"{p}.3.weight"], sd[f"{p}.3.bias"], padding=1)
+    x = F.relu(_bn(x, sd, f"{p}.4", training, update=update_stats))
+    return _drop(x, dropm)
+
+
 def phoneme_net_deep_forward(sd, x, training=True, use_attention=True, drop=None, n_blocks=4, update_stats=True):
-    """PhonemeNetDeep.forward (phoneme_cnn.py:274-304), residual variant. drop: list of n_blocks [B,C] or None."""
+    """PhonemeNetDeep.forward (phoneme_cnn.py:274-304); residual blocks, or the plain blocks of use_residual=False
+    (recognised by their state_dict keys). drop: list of n_blocks [B,C] or None."""
     drop = drop or [None] * n_blocks
+    block = _resblock if "conv_blocks.0.conv1.weight" in sd else _plainblock
     x = F.conv2d(x, sd["init_conv.0.weight"], sd["init_conv.0.bias"], stride=1, padding=3)   # :212
     x = F.relu(_bn(x, sd, "init_conv.1", training, update=update_stats))
     x = F.max_pool2d(x, kernel_size=3, stride=2, padding=1)                                   # :215
     for i in range(n_blocks):
-        x = _resblock(sd, f"conv_blocks.{i}", x, 1 if i == 0 else 2, training, drop[i], update_stats)  # :225-230
+        x = block(sd, f"conv_blocks.{i}", x, 1 if i == 0 else 2, training, drop[i], update_stats)      # :225-245
     if use_attention:
         attn = torch.sigmoid(F.conv2d(x, sd["attention.conv.weight"], sd["attention.conv.bias"]))
         x = x * attn
@@ -123,6 +134,11 @@ def param_shapes(arch: str, cfg: dict | None = None):
         ci = hd[0]
         for i, co in enumerate(hd):
             p = f"conv_blocks.{i}"
+            if not cfg.get("use_residual", True):
+                conv(p + ".0", co, ci, 3); bn(p + ".1", co)
+                conv(p + ".3", co, co, 3); bn(p + ".4", co)
+                ci = co
+                continue
             conv(p + ".conv1", co, ci, 3); bn(p + ".bn1", co)
             conv(p + ".conv2", co, co, 3); bn(p + ".bn2", co)
             if i != 0 or ci != co:

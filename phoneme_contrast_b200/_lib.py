@@ -30,7 +30,8 @@ class PcViewDesc(C.Structure):
 
 class PcMfccConsts(C.Structure):
     _fields_ = [("window", vp), ("fb_start", vp), ("fb_len", vp), ("fb_w", vp), ("dct", vp), ("tw", vp),
-                ("n_fft", C.c_int32), ("hop", C.c_int32), ("n_mels", C.c_int32), ("n_mfcc", C.c_int32), ("fb_wmax", C.c_int32)]
+                ("n_fft", C.c_int32), ("hop", C.c_int32), ("n_mels", C.c_int32), ("n_mfcc", C.c_int32), ("fb_wmax", C.c_int32),
+                ("preemph", C.c_float)]
 
 
 class PcConvGeom(C.Structure):
@@ -78,6 +79,7 @@ SIGNATURES = {
     "pc_bn_act_fwd": (i32, [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp, vp]),
     "pc_bn_act_bwd_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "pc_bn_act_split": (i32, [vp, i64, i32, i32, vp, vp, vp, i32, vp, vp]),
+    "pc_f16_overflow_query": (i32, [i32, C.POINTER(C.c_int), vp]),
     "pc_bn_act_bwd_apply": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pc_bn_add_relu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),
     "pc_bn_add_relu_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp]),
@@ -187,6 +189,13 @@ def ptr(t, dtype=torch.float32):
     if not t.is_contiguous():
         raise ValueError("tensor must be contiguous")
     return C.c_void_p(t.data_ptr())
+
+
+def f16_overflow(reset: bool = True) -> bool:
+    """True when an FP16X2 activation-plane writer met |a| > 65504 (or a NaN) since the last reset. Synchronises the stream."""
+    flag = C.c_int(0)
+    check(lib().pc_f16_overflow_query(1 if reset else 0, C.byref(flag), stream()))
+    return flag.value != 0
 
 
 def launch_count() -> int:

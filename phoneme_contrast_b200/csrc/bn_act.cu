@@ -65,10 +65,20 @@ __device__ __forceinline__ float absmax4(const float (&r)[4], float m) {
   return fmaxf(fmaxf(m, fmaxf(fabsf(r[0]), fabsf(r[1]))), fmaxf(fabsf(r[2]), fabsf(r[3])));
 }
 
+// FP16X2 activation planes are written unscaled (they follow a BatchNorm, so |a| is O(10)); a value beyond fp16's range would
+// become inf in the hi plane and surface later as a NaN loss. Every plane writer therefore raises this sticky device flag when
+// it meets |a| > 65504 (or a NaN); the host reads it with pc_f16_overflow_query (the trainer does so once per epoch, next to
+// its loss read-back, and switches the model to the range-free tf32x3 engine).
+__device__ unsigned int g_f16_overflow = 0u;
+__device__ __forceinline__ void f16_range_check(float m) {
+  if (!(m <= 65504.f)) atomicOr(&g_f16_overflow, 1u);
+}
+
 // optional second output of the forward kernels: the same 4 values in tensor-core operand form (fp16 hi | lo*2^11 planes of
 // `plane_elems` elements each, element index o), so that the next convolution's gather can copy bytes (see pc_bn_act_split)
 __device__ __forceinline__ void emit_planes4(unsigned char* __restrict__ planes, size_t plane_elems, size_t o, float4 r) {
   uint2 h, l;
+  f16_range_check(fmaxf(fmaxf(fabsf(r.x), fabsf(r.y)), fmaxf(fabsf(r.z), fabsf(r.w))));
   tc::split_f16x2(r.x, r.y, h.x, l.x);
   tc::split_f16x2(r.z, r.w, h.y, l.y);
   *reinterpret_cast<uint2*>(planes + o * 2) = h;
@@ -583,6 +593,8 @@ bn_act_split_kernel(const float* __restrict__ y, long long n_pix, int C, int hw,
       b = make_float4(b.x * d1.x, b.y * d1.y, b.z * d1.z, b.w * d1.w);
     }
     uint4 h, l;
+    f16_range_check(fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                          fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
     tc::split_f16x2(a.x, a.y, h.x, l.x);
     tc::split_f16x2(a.z, a.w, h.y, l.y);
     tc::split_f16x2(b.x, b.y, h.z, l.z);
@@ -788,5 +800,19 @@ extern "C" int pc_bn_act_split(const float* y, int64_t n_pix, int C, int hw, con
   launch_pdl(bn_act_split_kernel, dim3(ew_grid(n_pix * (C / 8), 256)), dim3(256), 0, stream, y, (long long)n_pix, C, hw, scale, shift, drop,
              relu, static_cast<unsigned char*>(planes));
   PC_LAUNCH_CHECK("bn_act_split_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_f16_overflow_query(int reset, int* host_flag, pc_stream_t stream) {
+  PC_REQUIRE(host_flag != nullptr, PC_EINVAL, "pc_f16_overflow_query: null pointer");
+  unsigned int v = 0u;
+  PC_CUDA(cudaMemcpyFromSymbolAsync(&v, pc::g_f16_overflow, sizeof(v), 0, cudaMemcpyDeviceToHost, stream));
+  PC_CUDA(cudaStreamSynchronize(stream));
+  if (reset && v != 0u) {
+    const unsigned int zero = 0u;
+    PC_CUDA(cudaMemcpyToSymbolAsync(pc::g_f16_overflow, &zero, sizeof(zero), 0, cudaMemcpyHostToDevice, stream));
+    PC_CUDA(cudaStreamSynchronize(stream));
+  }
+  *host_flag = (int)v;
   return PC_OK;
 }

@@ -26,6 +26,7 @@ struct FeParams {
   const float* wave; int n_clips, S, wave_ld;
   const float* window; const int* fb_start; const int* fb_len; const float* fb_w; const float* dct; const float* tw;
   int hop, n_mels, n_mfcc, T, TLD, Lsz, dct_sz, xs_len, fb_ld, dct_alias;
+  float preemph;    // optional pre-emphasis y[n] = x[n] - a x[n-1], y[0] = x[0] (0 = off: the reference's code path)
   const PcViewDesc* views; int n_views, views_per_clip;
   const float* noise; int kind, clamp_mode; float top_db; const float* clamp_ref; float* clip_max_out; float* out;
   long long* dbg;   // optional [grid][8] per-phase cycle totals (diagnostics: pc_fe_set_debug)
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
 
   // Stage the sample span of the frame chunk starting at frame f into dst: 16-byte cp.async for interior vectors (no
   // register staging, completion tracked per commit group), plain loads with reflect padding at the clip edges.
-  const bool vec_ok = ((p.hop & 3) == 0) && ((p.wave_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const float pre = p.preemph;
+  const bool vec_ok = pre == 0.f && ((p.hop & 3) == 0) && ((p.wave_ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
   auto stage_chunk = [&](int f, float* dst) {
     const int nfc = min(FE_FC, T - f);
     const int base = f * p.hop - FE_NFFT / 2;
@@ -140,6 +142,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
           ii = ii < 0 ? -ii : (ii >= S ? 2 * (S - 1) - ii : ii);
           ii = ii < 0 ? 0 : (ii >= S ? S - 1 : ii);      // only reachable in the unused tail of the last vector
           t[e] = x[ii];
+          if (pre != 0.f && ii > 0) t[e] = fmaf(-pre, x[ii - 1], t[e]);     // the pre-emphasised signal is what gets reflect-padded
         }
         *reinterpret_cast<float4*>(dst + 4 * v) = make_float4(t[0], t[1], t[2], t[3]);
       }
@@ -428,6 +431,7 @@ extern "C" int pc_frontend_fwd(const float* wave, int n_clips, int S, int wave_l
   p.wave = wave; p.n_clips = n_clips; p.S = S; p.wave_ld = wave_ld;
   p.window = c->window; p.fb_start = c->fb_start; p.fb_len = c->fb_len; p.fb_w = c->fb_w; p.dct = c->dct; p.tw = c->tw;
   p.hop = c->hop; p.n_mels = c->n_mels; p.n_mfcc = kind == PC_FE_MFCC ? c->n_mfcc : 0;
+  p.preemph = c->preemph;
   p.T = 1 + S / c->hop;
   p.TLD = p.T | 1;
   p.Lsz = (p.n_mels * p.TLD + 3) & ~3;

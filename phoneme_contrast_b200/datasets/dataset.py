@@ -1,0 +1,173 @@
+"""Drop-in for src/datasets/dataset.py: PhonemeContrastiveDataset with the reference's constructor, attributes,
+`_load_waveform` / `_pad_or_trim` / `_augment_waveform` decisions and `__getitem__` record, plus the device-resident
+input pipeline of SURVEY.md 8f.1 (`device_frontend=True`).
+
+Reference behaviour (dataset.py:65-111): every `__getitem__` clones the cached waveform, draws the gain, runs the
+feature extractor on ONE clip, runs the augmentation pipeline on ONE [1,1,F,T] tensor, and the DataLoader stacks the
+results on the host; the trainer then uploads them (trainer.py:186-199). Per view that is ~0.7 ms of MFCC + ~1.1 ms of
+Python/RNG work on the CPU.
+
+Device-resident path: the fixed-length waveforms (`_pad_or_trim` applied once, exactly as the reference caches them) live
+in ONE [n_items, max_samples] fp32 tensor on the GPU; the (idx, view) -> (gain, masks, noise level) descriptor table is
+drawn once with the reference's RNG calls (it depends only on idx and view, never on the epoch) and cached; a batch is
+then ONE launch of the fused front end (`MFCCExtractor.forward_views`) that reads its clips straight out of the cache
+through the descriptors' clip index -- no gather, no host round trip -- and hands `[B, V, 1, F, T]` views plus labels to
+`ContrastiveTrainer._prepare_batch` unchanged. `DeviceFrontendLoader` is the DataLoader stand-in for that path.
+"""
+from __future__ import annotations
+
+import random
+from pathlib import Path
+from typing import Any, Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch.utils.data import Dataset
+
+from .transforms import build_view_descriptors, pack_view_descs, waveform_gain
+
+
+class PhonemeContrastiveDataset(Dataset):
+    """Dataset for contrastive learning of phonemes; returns multiple augmented views of each audio file
+    (constructor of dataset.py:19-59; `device`, `device_frontend`, `waveforms` are extensions with inert defaults).
+
+    waveforms: optional list of 1-D / [1,n] tensors used instead of reading `file_paths` (synthetic data, tests)."""
+
+    def __init__(self, file_paths: List[Path], labels: List[int], metadata: List[Dict], feature_extractor, augmentation_pipeline,
+                 config: Dict, mode: str = "train", device: Optional[torch.device] = None, device_frontend: bool = False,
+                 waveforms: Optional[Sequence[torch.Tensor]] = None):
+        self.file_paths = file_paths
+        self.labels = labels
+        self.metadata = metadata
+        self.feature_extractor = feature_extractor
+        self.augmentation_pipeline = augmentation_pipeline
+        self.config = config
+        self.mode = mode
+        self.target_sr = config.get("target_sr", 16000)
+        self.max_length_ms = config.get("max_length_ms", 2000)
+        self.max_samples = int(self.max_length_ms * self.target_sr / 1000)
+        self.n_views = config.get("contrastive", {}).get("views_per_sample", 2) if mode == "train" else 1
+        self.use_cache = len(file_paths) < 500
+        self.waveform_cache = {} if self.use_cache else None
+        # ---- extensions
+        self.device = torch.device(device) if device is not None else torch.device("cuda")
+        self.device_frontend = device_frontend
+        self._waveforms = waveforms
+        self._wave_dev = None           # [n_items, max_samples] fp32 on the GPU
+        self._desc = None               # cached PcViewDesc records, item-major [n_items * n_views]
+
+    def __len__(self) -> int:
+        return len(self.file_paths)
+
+    # ------------------------------------------------------------------------------------------- reference-shaped item path
+    def _load_waveform(self, idx: int) -> torch.Tensor:
+        """dataset.py:113-145 -> [1, max_samples] (host)."""
+        if self.use_cache and idx in self.waveform_cache:
+            return self.waveform_cache[idx].clone()
+        if self._waveforms is not None:
+            waveform = torch.as_tensor(self._waveforms[idx], dtype=torch.float32).reshape(1, -1).cpu()
+        else:
+            import torchaudio        # file decoding / resampling stay on the host: off the hot path
+            waveform, sr = torchaudio.load(str(self.file_paths[idx]))
+            if sr != self.target_sr:
+                waveform = torchaudio.transforms.Resample(sr, self.target_sr)(waveform)
+            if waveform.shape[0] > 1:
+                waveform = waveform.mean(dim=0, keepdim=True)
+        waveform = self._pad_or_trim(waveform)
+        if self.use_cache:
+            self.waveform_cache[idx] = waveform.clone()
+        return waveform
+
+    def _pad_or_trim(self, waveform: torch.Tensor) -> torch.Tensor:
+        """dataset.py:174-203: random crop / random left pad in train mode (Python's global RNG, same calls), centred otherwise."""
+        length = waveform.shape[-1]
+        if length > self.max_samples:
+            start = random.randint(0, length - self.max_samples) if self.mode == "train" else (length - self.max_samples) // 2
+            waveform = waveform[..., start:start + self.max_samples]
+        elif length < self.max_samples:
+            pad_total = self.max_samples - length
+            pad_left = random.randint(0, pad_total) if self.mode == "train" else pad_total // 2
+            waveform = torch.nn.functional.pad(waveform, (pad_left, pad_total - pad_left))
+        return waveform
+
+    def _augment_waveform(self, waveform: torch.Tensor, seed: int) -> torch.Tensor:
+        """dataset.py:147-172: reseed random / numpy / torch, then the random gain."""
+        g = waveform_gain(seed)
+        return waveform * g if g != 1.0 else waveform
+
+    def __getitem__(self, idx: int) -> Dict[str, Any]:
+        """dataset.py:65-111. With device_frontend=True the item carries no features (they are produced per batch on the GPU by
+        `batch_views`); otherwise the views are computed one clip at a time like the reference, on the GPU, and returned on the
+        host so that a stock DataLoader can collate them."""
+        if self.device_frontend:
+            return {"label": self.labels[idx], "metadata": self.metadata[idx], "index": idx}
+        waveform = self._load_waveform(idx).to(self.device)
+        views = []
+        for view_idx in range(self.n_views):
+            view_waveform = waveform
+            if self.mode == "train":
+                view_waveform = self._augment_waveform(view_waveform, seed=int(idx * 10000 + view_idx))
+            features = self.feature_extractor(view_waveform)
+            if self.mode == "train" and self.augmentation_pipeline is not None:
+                features = self.augmentation_pipeline(features, seed=int(idx * 20000 + view_idx))
+            views.append(features.squeeze(0))
+        views = torch.stack(views) if len(views) > 1 else views[0]
+        return {"views": views.cpu(), "label": self.labels[idx], "metadata": self.metadata[idx], "index": idx}
+
+    # ------------------------------------------------------------------------------------------- device-resident path (8f.1)
+    def cache_on_device(self) -> torch.Tensor:
+        """Load every item once (`_load_waveform`, i.e. the reference's cached, padded/trimmed clip) into one GPU tensor."""
+        if self._wave_dev is None:
+            host = torch.empty(len(self), self.max_samples, dtype=torch.float32).pin_memory() if torch.cuda.is_available() \
+                else torch.empty(len(self), self.max_samples, dtype=torch.float32)
+            for i in range(len(self)):
+                host[i] = self._load_waveform(i)[0]
+            self._wave_dev = host.to(self.device, non_blocking=True)
+        return self._wave_dev
+
+    def view_descriptors(self) -> np.ndarray:
+        """(idx, view) -> PcViewDesc for the whole dataset, drawn with the reference's RNG calls and cached (the draws depend on
+        idx and view only: seeds idx*10000+view and idx*20000+view, dataset.py:85-94)."""
+        if self._desc is None:
+            n_mfcc = getattr(self.feature_extractor, "n_mfcc", None)
+            if n_mfcc is None:
+                raise NotImplementedError("the device-resident pipeline covers the MFCC extractor (the training configuration)")
+            hop = self.feature_extractor._consts.hop
+            T = 1 + self.max_samples // hop
+            train = self.mode == "train"
+            recs, _ = build_view_descriptors(range(len(self)), self.n_views, n_mfcc, T, self.augmentation_pipeline if train else None,
+                                             with_gain=train)
+            self._desc = recs
+        return self._desc
+
+    def batch_views(self, indices: Iterable[int], noise: Optional[torch.Tensor] = None):
+        """Features of a batch of items, on the GPU, in one fused launch: -> (views [B, V, 1, F, T], labels [B] int64)."""
+        idx = np.asarray(list(indices), dtype=np.int64)
+        wave = self.cache_on_device()
+        V = self.n_views
+        recs = self.view_descriptors()[(idx[:, None] * V + np.arange(V)[None, :]).reshape(-1)].copy()
+        recs["clip"] = np.repeat(idx, V).astype(np.int32)          # row of the device cache each view reads: no gather
+        views = pack_view_descs(recs, self.device)
+        out = self.feature_extractor.forward_views(wave, views, len(idx) * V, noise, n_clips=len(idx))
+        labels = torch.as_tensor([self.labels[i] for i in idx], dtype=torch.int64).to(self.device, non_blocking=True)
+        return out.view(len(idx), V, *out.shape[1:]) if V > 1 else out, labels
+
+
+class DeviceFrontendLoader:
+    """DataLoader stand-in for `PhonemeContrastiveDataset(device_frontend=True)`: iterates a batch sampler (any iterable of
+    index lists, e.g. the reference's ContrastiveBatchSampler) and yields the dict `ContrastiveTrainer._prepare_batch`
+    expects, with device-resident tensors produced by one fused front-end launch per batch."""
+
+    def __init__(self, dataset: PhonemeContrastiveDataset, batch_sampler):
+        if not dataset.device_frontend:
+            raise ValueError("DeviceFrontendLoader needs a dataset built with device_frontend=True")
+        self.dataset = dataset
+        self.batch_sampler = batch_sampler
+
+    def __len__(self):
+        return len(self.batch_sampler)
+
+    def __iter__(self):
+        for indices in self.batch_sampler:
+            views, labels = self.dataset.batch_views(indices)
+            yield {"views": views, "label": labels, "index": torch.as_tensor(list(indices))}

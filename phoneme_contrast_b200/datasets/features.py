@@ -77,8 +77,9 @@ def _band_form(fb: torch.Tensor):
 
 
 class _FrontEndConsts:
-    def __init__(self, sample_rate, n_fft, hop_length, n_mels, f_min, f_max, n_mfcc):
+    def __init__(self, sample_rate, n_fft, hop_length, n_mels, f_min, f_max, n_mfcc, preemphasis=0.0):
         self.n_fft, self.hop, self.n_mels, self.n_mfcc = n_fft, hop_length, n_mels, n_mfcc
+        self.preemphasis = float(preemphasis)
         self.window = torch.hann_window(n_fft)                                     # periodic, fp32 (torchaudio default)
         self.fb = _melscale_fbanks(n_fft // 2 + 1, f_min, f_max, n_mels, sample_rate)
         self.dct = _create_dct(n_mfcc, n_mels) if n_mfcc else None
@@ -92,7 +93,7 @@ class _FrontEndConsts:
             keep = [t.to(device) if t is not None else None for t in (self.window, self.start, self.length, self.w, self.dct, self.tw)]
             st = PcMfccConsts(ptr(keep[0]), ptr(keep[1], torch.int32), ptr(keep[2], torch.int32), ptr(keep[3]),
                               ptr(keep[4]) if keep[4] is not None else None, ptr(keep[5]), self.n_fft, self.hop, self.n_mels,
-                              self.n_mfcc or 0, int(self.length.max()))
+                              self.n_mfcc or 0, int(self.length.max()), self.preemphasis)
             self._dev[key] = (st, keep)
         return self._dev[key]
 
@@ -111,8 +112,10 @@ def _as_batch(waveform: torch.Tensor) -> torch.Tensor:
 
 
 def _run_frontend(consts: _FrontEndConsts, wave, kind, clamp_mode, top_db, views=None, n_views=None, noise=None,
-                  clamp_ref=None, want_max=False):
+                  clamp_ref=None, want_max=False, n_clips=None):
     B, S = wave.shape
+    if n_clips is not None:      # `wave` is a larger resident cache; the views' clip indices select the rows this call reads
+        B = int(n_clips)
     st, _keep = consts.on(wave.device)
     T = 1 + S // consts.hop
     n_out = consts.n_mfcc if kind == L.FE_MFCC else consts.n_mels
@@ -146,7 +149,9 @@ class MFCCExtractor(FeatureExtractor):
 
     def __init__(self, sample_rate: int = 16000, n_mfcc: int = 40, n_fft: int = 400, hop_length: int = 160,
                  n_mels: int = 80, f_min: float = 0.0, f_max: Optional[float] = None, add_delta: bool = False,
-                 add_delta_delta: bool = False):
+                 add_delta_delta: bool = False, preemphasis: float = 0.0):
+        # preemphasis (extension, default off = the reference's arithmetic): y[n] = x[n] - a*x[n-1] before the STFT, the
+        # stage BASELINE.json's north_star names and the manuscript quotes at 0.97; the reference's code has none
         super().__init__()
         if n_mfcc > n_mels:
             raise ValueError("Cannot select more MFCC coefficients than # mel bins")      # torchaudio MFCC.__init__
@@ -154,7 +159,7 @@ class MFCCExtractor(FeatureExtractor):
         self.n_mfcc = n_mfcc
         self.add_delta = add_delta
         self.add_delta_delta = add_delta_delta
-        self._consts = _FrontEndConsts(sample_rate, n_fft, hop_length, n_mels, f_min, f_max or sample_rate / 2, n_mfcc)
+        self._consts = _FrontEndConsts(sample_rate, n_fft, hop_length, n_mels, f_min, f_max or sample_rate / 2, n_mfcc, preemphasis)
 
     def _mfcc(self, wave, clamp_scope):
         if clamp_scope == "clip" or wave.shape[0] == 1:
@@ -183,14 +188,18 @@ class MFCCExtractor(FeatureExtractor):
             feats.append(_deltas(feats[1] if self.add_delta else _deltas(base)))          # features.py:88-95
         return torch.cat(feats, dim=1).unsqueeze(1)
 
-    def forward_views(self, waveform: torch.Tensor, views: torch.Tensor, n_views: int, noise: Optional[torch.Tensor] = None):
+    def forward_views(self, waveform: torch.Tensor, views: torch.Tensor, n_views: int, noise: Optional[torch.Tensor] = None,
+                      n_clips: Optional[int] = None):
         """Batched form of the dataset loop (dataset.py:79-98): for clip i, views[i*V:(i+1)*V] (a uint8 tensor
         holding PcViewDesc records, see datasets.transforms.pack_view_descs) give gain / masks / noise of each
-        view. Per-clip clamp. Returns [B*V, 1, n_mfcc, T]. noise: optional explicit N(0,1) draws [B*V, F*T]."""
+        view. Per-clip clamp. Returns [B*V, 1, n_mfcc, T]. noise: optional explicit N(0,1) draws [B*V, F*T].
+        n_clips: when given, `waveform` is a device-resident cache with more rows than this batch and the descriptors' clip
+        field names the row each group of V views reads (datasets.dataset.PhonemeContrastiveDataset.batch_views)."""
         if self.add_delta or self.add_delta_delta:
             raise NotImplementedError("forward_views covers the plain-MFCC training configuration")
         wave = _as_batch(waveform)
-        out, _ = _run_frontend(self._consts, wave, L.FE_MFCC, L.CLAMP_PER_CLIP, self.top_db, views=views, n_views=n_views, noise=noise)
+        out, _ = _run_frontend(self._consts, wave, L.FE_MFCC, L.CLAMP_PER_CLIP, self.top_db, views=views, n_views=n_views, noise=noise,
+                               n_clips=n_clips)
         return out
 
 
@@ -198,10 +207,10 @@ class MelSpectrogramExtractor(FeatureExtractor):
     """Log-mel spectrogram (features.py:109-153); AmplitudeToDB() there has top_db=None, i.e. no clamp."""
 
     def __init__(self, sample_rate: int = 16000, n_fft: int = 400, hop_length: int = 160, n_mels: int = 80,
-                 f_min: float = 0.0, f_max: Optional[float] = None):
+                 f_min: float = 0.0, f_max: Optional[float] = None, preemphasis: float = 0.0):
         super().__init__()
         self.sample_rate = sample_rate
-        self._consts = _FrontEndConsts(sample_rate, n_fft, hop_length, n_mels, f_min, f_max or sample_rate / 2, 0)
+        self._consts = _FrontEndConsts(sample_rate, n_fft, hop_length, n_mels, f_min, f_max or sample_rate / 2, 0, preemphasis)
 
     def forward(self, waveform: torch.Tensor) -> torch.Tensor:
         wave = _as_batch(waveform)

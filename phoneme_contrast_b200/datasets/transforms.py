@@ -64,6 +64,9 @@ def _blank(n=1) -> np.ndarray:
     return rec
 
 
+blank_view_descs = _blank      # n identity descriptors (gain 1, no masks, no noise): fill in fields, then pack_view_descs
+
+
 class BaseTransform:
     """Base class for augmentations (transforms.py:9-22)."""
 
@@ -120,6 +123,14 @@ class FrequencyMask(BaseTransform):
         return _apply(x, rec, None)
 
 
+_noise_calls = [0]
+
+
+def _unseeded_noise_seed() -> int:
+    _noise_calls[0] += 1
+    return (torch.initial_seed() * 0x9E3779B1 + _noise_calls[0] * 0x85EBCA6B) & 0xFFFFFFFF
+
+
 class GaussianNoise(BaseTransform):
     """x + N(0,1) * level, level ~ U(min_snr, max_snr) (transforms.py:73-97).
 
@@ -139,7 +150,9 @@ class GaussianNoise(BaseTransform):
         if random.random() < self.prob:
             level = random.uniform(self.min_snr, self.max_snr)
             rec["noise_level"] = np.float32(level)
-            rec["noise_seed"] = np.uint32((int(seed) if seed is not None else random.getrandbits(32)) & 0xFFFFFFFF)
+            # seed=None: the device noise seed comes from a private counter mixed with torch's initial seed -- it must not
+            # consume Python's `random` stream, which the reference never touches here
+            rec["noise_seed"] = np.uint32((int(seed) if seed is not None else _unseeded_noise_seed()) & 0xFFFFFFFF)
             if self.noise_source == "torch_cpu":
                 return torch.randn(tuple(shape))
         return None

@@ -275,7 +275,7 @@ def _deep_forward(net, x, training):
     co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
     # On the FP16X2 engine every block input is also kept as fp16 hi | lo planes (written by the kernel that produces it), so
     # that conv1 / the shortcut conv and their weight gradients gather bytes instead of splitting fp32 per tap
-    ps = prec == L.PREC_FP16X2 and all(c % 64 == 0 for c in hd)
+    ps = prec == L.PREC_FP16X2 and all(c % 64 == 0 for c in hd) and net.use_residual
     if ps:
         p0, argmax0, cur_ps = ops.bn_act_fwd(y0, co0, 3, None, want_planes=True)
     else:
@@ -287,6 +287,23 @@ def _deep_forward(net, x, training):
     xps = dict(presplit=True)
     for i, blk in enumerate(net.conv_blocks):
         co = hd[i]
+        if not net.use_residual:
+            # plain block (phoneme_cnn.py:231-245): conv(stride) BN ReLU conv BN ReLU Dropout2d -- the cnn_small block shape
+            stride = blk[0].stride[0]
+            g1 = ops.conv_geom(B, h, w, cin, co, 3, stride, 1)
+            cw1 = ops.ConvWeights(blk[0].weight, g1, prec, packer=packer)
+            st1 = st(co)
+            y1 = ops.conv_fwd(cur, cw1.wf, blk[0].bias, g1, None, st1, cw1.prec_f)
+            c1 = ops.bn_finalize(st1, B * g1.Ho * g1.Wo, blk[1], training)
+            g2 = ops.conv_geom(B, g1.Ho, g1.Wo, co, co, 3, 1, 1)
+            cw2 = ops.ConvWeights(blk[3].weight, g2, prec, packer=packer)
+            st2 = st(co)
+            y2 = ops.conv_fwd(y1, cw2.wf, blk[3].bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True), st2, cw2.prec_f)
+            c2 = ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk[4], training)
+            out, _ = ops.bn_act_fwd(y2, c2, 0, s.drop[i])
+            s.blocks.append(dict(plain=True, xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, cw1=cw1, cw2=cw2, out=out))
+            cur, cin, h, w = out, co, g1.Ho, g1.Wo
+            continue
         stride = blk.stride
         g1 = ops.conv_geom(B, h, w, cin, co, 3, stride, 1)
         cw1 = ops.ConvWeights(blk.conv1.weight, g1, prec, packer=packer)
@@ -335,12 +352,21 @@ def _deep_backward(net, s, demb, grads, training=True):
     wgrad = _WgradLane(net, keep)
     dout = _head_bwd(net, s, demb, grads, training)
     zp = ops.ZeroPool(demb.device)                      # zeroed reduction targets of all BatchNorm backward passes
-    amax = _AmaxSlots(demb.device, 3 * len(s.blocks), zp)   # max|dy| per gradient tensor a convolution consumes (FP16X2 scale)
+    amax = _AmaxSlots(demb.device, 3 * len(s.blocks) + 1, zp)   # max|dy| per gradient tensor a convolution consumes (FP16X2 scale)
     for i in reversed(range(len(s.blocks))):
         blk = net.conv_blocks[i]
         r = s.blocks[i]
-        g2 = (grads[blk.bn2.weight], grads[blk.bn2.bias])
         m2, m1, ms = amax.take(), amax.take(), amax.take()
+        if r.get("plain"):
+            dy2, _, _ = ops.bn_act_bwd(dout, r["y2"], r["c2"], 0, s.drop[i], None, grads[blk[4].weight], grads[blk[4].bias], m2, zp=zp)
+            xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True)
+            wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk[3].weight], grads[blk[3].bias], prec, m2)
+            dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2)
+            dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, None, None, grads[blk[1].weight], grads[blk[1].bias], m1, zp=zp)
+            wgrad(r["xin"], dy1, r["g1"], None, grads[blk[0].weight], grads[blk[0].bias], prec, m1)
+            dout = ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], prec=r["cw1"].prec_d, dy_amax=m1)
+            continue
+        g2 = (grads[blk.bn2.weight], grads[blk.bn2.bias])
         # gradient tensors in operand form too: when every consumer of dy (data gradient and weight gradient) runs the FP16X2
         # engine, the BatchNorm backward writes dy only as scaled fp16 hi | lo planes and the convolutions gather bytes
         gps = (r["a1"] is not None and r["xin_ps"] is not None and prec == L.PREC_FP16X2 and r["cw2"].prec_d == L.PREC_FP16X2
@@ -369,8 +395,10 @@ def _deep_backward(net, s, demb, grads, training=True):
         dout = dxin
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
     st = s.stem
-    dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias], zp=zp)
-    wgrad(s.x, dy0, st["g"], None, grads[conv0.weight], grads[conv0.bias], prec)
+    # the stem's dy is O(1/N) per pixel (the loss is a mean): without the max|dy| operand scale it would sit in fp16 subnormals
+    m0 = amax.take()
+    dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias], m0, zp=zp)
+    wgrad(s.x, dy0, st["g"], None, grads[conv0.weight], grads[conv0.bias], prec, m0)
     wgrad.join()
 
 
@@ -484,15 +512,19 @@ class PhonemeNetDeep(_FusedNet):
         self.dropout_rate = config.get("dropout_rate", 0.2)
         self.hidden_dims = list(config.get("hidden_dims", [64, 128, 256, 512]))
         self.use_residual = config.get("use_residual", True)
-        if not self.use_residual:
-            raise NotImplementedError("use_residual=False is not covered by the fused engine (never run by the reference's configs)")
         hd = self.hidden_dims
         self.init_conv = nn.Sequential(nn.Conv2d(self.in_channels, hd[0], kernel_size=7, stride=1, padding=3),
                                        nn.BatchNorm2d(hd[0]), nn.ReLU(inplace=True),
                                        nn.MaxPool2d(kernel_size=3, stride=2, padding=1))
         layers, cin = [], hd[0]
         for i, co in enumerate(hd):
-            layers.append(ResidualBlock(cin, co, 1 if i == 0 else 2, self.dropout_rate))
+            stride = 1 if i == 0 else 2
+            if self.use_residual:
+                layers.append(ResidualBlock(cin, co, stride, self.dropout_rate))
+            else:           # phoneme_cnn.py:231-245 (same child indices -> same state_dict keys)
+                layers.append(nn.Sequential(nn.Conv2d(cin, co, kernel_size=3, stride=stride, padding=1), nn.BatchNorm2d(co),
+                                            nn.ReLU(inplace=True), nn.Conv2d(co, co, kernel_size=3, padding=1), nn.BatchNorm2d(co),
+                                            nn.ReLU(inplace=True), nn.Dropout2d(self.dropout_rate)))
             cin = co
         self.conv_blocks = nn.Sequential(*layers)
         if self.use_attention:

@@ -94,52 +94,80 @@ class ConvWeights:
             packer.record(w, need_dgrad, self, need_simt_f, need_simt_d)
 
 
+class _PackerState:
+    __slots__ = ("entries", "table", "n_jobs", "total")
+
+    def __init__(self):
+        self.entries, self.table, self.n_jobs, self.total = [], None, 0, 0
+
+
 class WeightPacker:
     """Batches the per-step weight re-packing of a network. The first forward with a given key records, layer by layer,
     which operands are needed (and packs them one launch each, as without a packer); later forwards with the same key
     issue ONE pc_pack_conv_weights_tc_batch launch that refreshes all recorded tensor-core operands in place and hand the
-    same buffers out in recording order. Exact-fp32 SIMT operands (ineligible layers) are still packed per layer."""
+    same buffers out in recording order. Exact-fp32 SIMT operands (ineligible layers) are still packed per layer.
+
+    One recording is kept PER KEY (train / eval, every batch shape) and never freed while the packer lives: a captured CUDA
+    graph bakes the job-table and operand-buffer addresses of the recording it was captured with into its launches, so an
+    interleaved eval forward or odd-shaped batch must not release them (a recording invalidated by re-allocated parameters
+    is retired, not dropped, for the same reason)."""
 
     def __init__(self):
+        self.states = {}
+        self._retired = []
         self.key = None
-        self.entries = []
-        self.table = None
+        self.cur = None
         self.replaying = False
         self.cursor = 0
 
+    # kept for introspection / tests
+    @property
+    def entries(self):
+        return self.cur.entries if self.cur is not None else []
+
+    @property
+    def table(self):
+        return self.cur.table if self.cur is not None else None
+
     def begin(self, key):
-        ok = self.table is not None and key == self.key and all(e["w"].data_ptr() == e["ptr"] for e in self.entries)
+        st = self.states.get(key)
+        ok = st is not None and st.table is not None and all(e["w"].data_ptr() == e["ptr"] for e in st.entries)
         self.cursor = 0
+        self.key = key
         if ok:
+            self.cur = st
             self.replaying = True
-            if self.n_jobs:
-                call("pc_pack_conv_weights_tc_batch", self.table.data_ptr(), self.n_jobs, self.total, stream())
+            if st.n_jobs:
+                call("pc_pack_conv_weights_tc_batch", st.table.data_ptr(), st.n_jobs, st.total, stream())
         else:
+            if st is not None:
+                self._retired.append(st)
             self.replaying = False
-            self.key, self.entries, self.table = key, [], None
+            self.cur = self.states[key] = _PackerState()
 
     def record(self, w, need_dgrad, cw, simt_f, simt_d):
-        self.entries.append(dict(w=w, ptr=w.data_ptr(), need_dgrad=need_dgrad, wf=cw.wf, wd=cw.wd, prec_f=cw.prec_f, prec_d=cw.prec_d,
-                                 simt_f=simt_f, simt_d=simt_d))
+        self.cur.entries.append(dict(w=w, ptr=w.data_ptr(), need_dgrad=need_dgrad, wf=cw.wf, wd=cw.wd, prec_f=cw.prec_f,
+                                     prec_d=cw.prec_d, simt_f=simt_f, simt_d=simt_d))
 
     def end(self):
         if self.replaying:
             return
+        st = self.cur
         jobs, total = [], 0
-        for e in self.entries:
+        for e in st.entries:
             O, I, R, S = e["w"].shape
             for dgrad, buf, prec, simt in ((0, e["wf"], e["prec_f"], e["simt_f"]), (1, e["wd"], e["prec_d"], e["simt_d"])):
                 if buf is None or simt:
                     continue
                 jobs.append(L.PcPackJob(e["ptr"], buf.data_ptr(), O, I, R, S, dgrad, prec, total))
                 total += int(L.lib().pc_pack_conv_weight_tc_items(O, I, R, S, dgrad, prec))
-        self.n_jobs, self.total = len(jobs), total
-        dev = self.entries[0]["w"].device if self.entries else "cpu"
+        st.n_jobs, st.total = len(jobs), total
+        dev = st.entries[0]["w"].device if st.entries else "cpu"
         raw = bytes(b"".join(bytes(j) for j in jobs)) or b"\0"
-        self.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        st.table = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
 
     def next(self, w, need_dgrad):
-        e = self.entries[self.cursor]
+        e = self.cur.entries[self.cursor]
         self.cursor += 1
         if e["ptr"] != w.data_ptr() or e["need_dgrad"] != need_dgrad:
             raise RuntimeError("WeightPacker: layer order changed since recording")

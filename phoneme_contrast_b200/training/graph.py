@@ -31,26 +31,31 @@ class GraphedTrainStep:
         snap_buf = [b.clone() for b in model.buffers()]
         drop_step = getattr(model, "_drop_step", None)
         snap_drop = drop_step.clone() if drop_step is not None else None
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                trainer.train_step(self.views, self.labels)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        opt.sync_lr()
-        with torch.cuda.graph(self.graph):
-            self.loss = trainer.train_step(self.views, self.labels)
-        with torch.no_grad():
-            opt.flat_p.copy_(snap_opt[0]); opt.flat_m.copy_(snap_opt[1]); opt.flat_v.copy_(snap_opt[2])
-            opt._step_dev.copy_(snap_opt[3]); opt._step = snap_opt[4]
-            for b, sb in zip(model.buffers(), snap_buf):
-                b.copy_(sb)
-            if getattr(model, "_drop_step", None) is not None:
-                if snap_drop is not None:
-                    model._drop_step.copy_(snap_drop)
-                else:
-                    model._drop_step.zero_()
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    trainer.train_step(self.views, self.labels)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            opt.sync_lr()
+            with torch.cuda.graph(self.graph):
+                self.loss = trainer.train_step(self.views, self.labels)
+        finally:
+            # whether capture succeeded or raised, the warm-up steps must be invisible to the optimisation trajectory (the trainer
+            # falls back to eager steps from exactly the state it had before)
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                opt.flat_p.copy_(snap_opt[0]); opt.flat_m.copy_(snap_opt[1]); opt.flat_v.copy_(snap_opt[2])
+                opt._step_dev.copy_(snap_opt[3]); opt._step = snap_opt[4]
+                for b, sb in zip(model.buffers(), snap_buf):
+                    b.copy_(sb)
+                if getattr(model, "_drop_step", None) is not None:
+                    if snap_drop is not None:
+                        model._drop_step.copy_(snap_drop)
+                    else:
+                        model._drop_step.zero_()
         self.shape = (tuple(views.shape), tuple(labels.shape))
 
     def matches(self, views: torch.Tensor, labels: torch.Tensor) -> bool:

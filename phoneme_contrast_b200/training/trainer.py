@@ -121,7 +121,7 @@ class ContrastiveTrainer:
         if isinstance(self.optimizer, FusedClipAdam):
             flat = self.optimizer.flat_grad()
             if self.parallel is not None:
-                self.parallel.all_reduce_gradients(flat)          # sum; 1/R folded into grad_prescale
+                self.parallel.all_reduce_gradients(flat)          # SUM: each rank holds disjoint partial sums of the global-loss gradient
             self.optimizer.step(max_grad_norm=clip or 0.0, flat_grad=flat)
         else:
             if self.parallel is not None:
@@ -146,7 +146,23 @@ class ContrastiveTrainer:
             if sync_each and hasattr(pbar, "set_postfix"):
                 pbar.set_postfix({"loss": loss.item()})
         mean_loss = float(total.item()) / max(num_batches, 1)     # the epoch's only host sync
+        self._check_f16_range()
         return {"loss": mean_loss, "lr": self.optimizer.param_groups[0]["lr"]}
+
+    def _check_f16_range(self) -> None:
+        """FP16X2 activation operands are unscaled: if a plane writer saw |a| > 65504 during the epoch (device flag, read here
+        next to the loss), the affected steps computed with inf. Switch the model to the range-free tf32x3 engine and say so
+        loudly; config["f16_overflow"] = "raise" turns it into an error instead."""
+        from .. import _lib as L
+        if not hasattr(self.model, "_prec") or not L.f16_overflow(reset=True):
+            return
+        msg = ("an activation exceeded the fp16 range (65504) on the FP16X2 tensor-core path during this epoch; "
+               "the affected steps saw inf operands")
+        if self.config.get("f16_overflow", "fallback") == "raise":
+            raise FloatingPointError(msg)
+        self.logger.error(msg + " -- switching the model to precision 'tf32x3' (no range assumption) from the next step on")
+        self.model._prec = L.PREC_TF32X3
+        self._graphed = None          # the captured step baked the fp16x2 kernels in
 
     def _validate(self) -> Dict[str, float]:
         self.model.eval()

@@ -211,3 +211,25 @@ def test_fastdiv_formula_matches_integer_division():
             t = (mul * n) >> 32
             q = ((t + ((n - t) >> s1)) & 0xFFFFFFFF) >> s2
             assert q == n // d, (d, n)
+
+
+def test_dataset_pad_or_trim_matches_reference_golden(golden):
+    """Host logic of the dataset mirror (reference dataset.py:174-203): train-mode random crop / left pad drawn from Python's
+    global RNG with the same calls, centred crop / pad in val mode; bit-identical to the reference's outputs."""
+    import random
+
+    import torch
+
+    from phoneme_contrast_b200.datasets.dataset import PhonemeContrastiveDataset
+    g = golden.r2
+    raw = [torch.from_numpy(g[f"ds_raw_{i}"]) for i in range(4)]
+    cfg = {"target_sr": 16000, "max_length_ms": 500, "contrastive": {"views_per_sample": 2}}
+    ds = PhonemeContrastiveDataset(list(range(4)), [3, 1, 4, 1], [{}] * 4, None, None, cfg, mode="train", device="cpu", waveforms=raw)
+    assert ds.max_samples == 8000 and ds.n_views == 2
+    for i, seed in enumerate(g["ds_pad_seeds"]):
+        random.seed(int(seed))
+        assert np.array_equal(ds._load_waveform(i).numpy(), g[f"ds_fixed_{i}"])
+    val = PhonemeContrastiveDataset(list(range(4)), [3, 1, 4, 1], [{}] * 4, None, None, cfg, mode="val", device="cpu", waveforms=raw)
+    assert val.n_views == 1
+    for i in range(4):
+        assert np.array_equal(val._load_waveform(i).numpy(), g[f"ds_val_fixed_{i}"])
