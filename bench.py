@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 T_SUPCON = 0.15
 WORKLOADS = {
     "train_cnn_deep": dict(arch="phoneme_cnn_deep", views=256, desc="cnn_deep PhonemeNetDeep (64->512 ch residual) + SupCon T=0.15, 256 views/GPU, 40x101 MFCC (BASELINE configs[2])"),
+    "train_cnn_deep_4096": dict(arch="phoneme_cnn_deep", views=512, desc="cnn_deep PhonemeNetDeep + SupCon T=0.15 data-parallel, 512 views/GPU = global batch 4096 at 8 GPUs, 40x101 MFCC (BASELINE configs[4])"),
     "train_cnn_small": dict(arch="phoneme_cnn", views=64, desc="cnn_small PhonemeNet + SupCon T=0.15, emb 128, 64 views (8x4x2), 40x101 MFCC (BASELINE configs[0] on GPU)"),
     "frontend": dict(clips=65536, desc="MFCC front end + 2-view augmentation, 65 536 synthetic 1 s 16 kHz clips (BASELINE configs[1])"),
     "supcon_8192": dict(n=8192, d=128, desc="SupCon loss alone, forward+backward, 8192 views x 128-d, 38 classes, rows sharded over the ranks with embedding/label/row-stat all_gather (BASELINE configs[3])"),
@@ -64,6 +65,60 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------------ clocks
+class NvmlClockSampler:
+    """SM clock + throttle reasons through NVML from a sampling thread (~2 ms cadence), so that even a 90 ms timed region holds
+    dozens of samples. Falls back to the nvidia-smi poller (ClockSampler) when NVML is unavailable."""
+
+    def __init__(self, index=0):
+        import threading
+
+        import pynvml
+        self.nv = pynvml
+        pynvml.nvmlInit()
+        self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        self.rows, self.stop_flag = [], False
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        reasons_fn = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), int(reasons_fn(self.h))))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def stop(self):
+        self.stop_flag = True
+        self.t.join(timeout=2)
+        nv = self.nv
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.rows), "source": "nvml thread, 2 ms cadence"}
+        if not self.rows:
+            return out
+        try:
+            out["sm_max_mhz"] = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            pass
+        sm = [r[0] for r in self.rows]
+        hi = [v for v in sm if v >= 0.5 * max(sm)] or sm
+        out["sm_mhz"] = float(np.median(hi))
+        bits = 0
+        for _, b in self.rows:
+            bits |= b
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        out["reasons"] = sorted(n for n, m in names.items() if bits & m)
+        return out
+
+
+def clock_sampler(index=0):
+    try:
+        return NvmlClockSampler(index)
+    except Exception:
+        return ClockSampler(index)
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -146,10 +201,10 @@ def max_over_ranks(ms, parallel, device):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arms
-def bench_train(workload, steps, warmup, parallel, device, want_profile=True, use_graph=True):
+def bench_train(workload, steps, warmup, parallel, device, want_profile=True, use_graph=True, views=None):
     from phoneme_contrast_b200 import _lib
     cfg = WORKLOADS[workload]
-    arch, views = cfg["arch"], cfg["views"]
+    arch, views = cfg["arch"], int(views or cfg["views"])
     rank = 0 if parallel is None else parallel.rank
     world = 1 if parallel is None else parallel.world_size
     tr = build_trainer(arch, device, parallel)
@@ -164,7 +219,7 @@ def bench_train(workload, steps, warmup, parallel, device, want_profile=True, us
     for i in range(warmup):
         tr.step(xs[i % len(xs)], y)
     barrier(parallel)
-    sampler = ClockSampler(torch.cuda.current_device()) if rank == 0 else None
+    sampler = clock_sampler(torch.cuda.current_device()) if rank == 0 else None
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -350,96 +405,299 @@ def bench_frontend(steps, warmup, device, n_clips=65536, desc_clips=2048):
                 h2d=ne * 64000, d2h=2 * ne * 16160, e2e_sample=f"{ne} clips per call, pinned host waveforms in, host features out")
 
 
-# ------------------------------------------------------------------------------------------------ CPU arms (oracle port)
-def cpu_train_steps(arch, views, steps, warmup=1, threads=None):
-    """The reference's CPU training step restated with the oracle (same ATen ops: conv2d/batch_norm/... + SupCon + clip + Adam)."""
+def bench_pipeline(steps, warmup, device, n_items=2048, views_per_item=2, items_per_batch=128):
+    """End-to-end 'clips -> optimiser step' through the device-resident dataset path: per step the host picks the batch's item
+    indices (8 x ... class-balanced recipe scaled to 128 items x 2 views = 256 views), ONE fused front-end launch turns the cached
+    GPU waveforms into augmented MFCC views, and ContrastiveTrainer.step (graph replay) trains cnn_deep on them."""
+    from phoneme_contrast_b200.datasets import DeviceFrontendLoader, MFCCExtractor, PhonemeContrastiveDataset, build_augmentation_pipeline
+    g = torch.Generator().manual_seed(7)
+    waves = 0.1 * torch.randn(n_items, 16000, generator=g)
+    labels = (torch.arange(n_items) % 38).tolist()
+    ds = PhonemeContrastiveDataset(list(range(n_items)), labels, [{}] * n_items, MFCCExtractor(), build_augmentation_pipeline(AUG_CFG),
+                                   {"target_sr": 16000, "max_length_ms": 1000, "contrastive": {"views_per_sample": views_per_item}},
+                                   mode="train", device=device, device_frontend=True, waveforms=waves)
+    ds.use_cache = True
+    ds.waveform_cache = {i: waves[i:i + 1] for i in range(n_items)}
+    t0 = time.perf_counter()
+    ds.cache_on_device()
+    ds.view_descriptors()
+    setup_s = time.perf_counter() - t0
+    tr = build_trainer("phoneme_cnn_deep", device, None)
+    tr.config["cuda_graph"] = True
+    rs = np.random.RandomState(3)
+    by_label = {}
+    for i, l in enumerate(labels):
+        by_label.setdefault(l, []).append(i)
+
+    def sample_batch():      # K classes x 4 items (ContrastiveBatchSampler's recipe, samplers.py:13-21)
+        out = []
+        for c in rs.choice(38, items_per_batch // 4, replace=False if items_per_batch // 4 <= 38 else True):
+            out.extend(rs.choice(by_label[int(c)], 4, replace=False))
+        return out
+    batches = [sample_batch() for _ in range(warmup + steps)]
+    loader = DeviceFrontendLoader(ds, batches)
+    it = iter(loader)
+    for _ in range(warmup):
+        v, y = tr._prepare_batch(next(it))
+        tr.step(v, y)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    loss = None
+    for _ in range(steps):
+        v, y = tr._prepare_batch(next(it))
+        loss = tr.step(v, y)
+    loss = float(loss.item())
+    dt = time.perf_counter() - t0
+    n_views = items_per_batch * views_per_item
+    return {"value": n_views * steps / dt, "unit": "samples/s", "ms_per_step": dt / steps * 1e3, "final_loss": loss,
+            "workload": f"device-resident PhonemeContrastiveDataset ({n_items} cached 1 s clips) -> fused MFCC + 2-view augmentation -> cnn_deep SupCon step, {n_views} views/step; wall clock incl. host batch sampling and descriptor upload",
+            "setup_s": setup_s, "h2d_bytes_per_step": n_views * 32 + items_per_batch * 8}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms (reference / oracle port)
+_REF = None
+
+
+def have_reference():
+    """True when the reference's own modules were vendored into oracle/_ref (oracle/build_ref.py) and import on this box."""
+    global _REF
+    if _REF is None:
+        try:
+            from oracle import build_ref
+            _REF = bool(build_ref.import_reference())
+        except Exception:
+            _REF = False
+    return _REF
+
+
+def ref_kind():
+    return "reference" if have_reference() else "port"
+
+
+def _train_step_fn(arch, views, device="cpu"):
+    """One training step of the reference path as the trainer runs it (trainer.py:126-164: forward, SupCon T=.15, backward,
+    clip_grad_norm_(1.0), Adam(lr 3e-4, L2 wd 1e-4), loss.item()), on `device`: the reference's own nn.Modules when
+    oracle/_ref is present (dropout drawn by nn.Dropout2d), else the oracle's restatement with the same ATen ops."""
+    xs, y = train_inputs(views, 1000, device, n_buffers=2)
+    xs, y = [x.to(device) for x in xs], y.to(device)
+    if have_reference():
+        from src.models import model_registry
+        from src.training.losses import get_loss_fn
+        torch.manual_seed(42)
+        model = model_registry.create(arch, {}).to(device)
+        model.train()
+        loss_fn = get_loss_fn("supervised_contrastive", temperature=T_SUPCON)
+        opt = torch.optim.Adam(model.parameters(), lr=3e-4, weight_decay=1e-4)
+
+        def step(i):
+            opt.zero_grad()
+            loss = loss_fn(model(xs[i % 2]), y)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            return loss.item()
+        return step
     from oracle import nets_oracle, supcon_oracle
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    cfg = {}
-    sd = nets_oracle.synthetic_state_dict(arch, cfg, seed=0)
+    sd = nets_oracle.synthetic_state_dict(arch, {}, seed=0)
+    sd = {k: v.to(device) for k, v in sd.items()}
     params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
     live = dict(sd)
     live.update(params)
     opt = torch.optim.Adam(list(params.values()), lr=3e-4, weight_decay=1e-4)
-    xs, y = train_inputs(views, 1000, "cpu", n_buffers=2)
     p = 0.1 if arch == "phoneme_cnn" else 0.2
     chans = [32, 64, 128] if arch == "phoneme_cnn" else [64, 128, 256, 512]
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        drop = [torch.bernoulli(torch.full((views, c), 1 - p)) / (1 - p) for c in chans]
+
+    def step(i):
+        drop = [torch.bernoulli(torch.full((views, c), 1 - p, device=device)) / (1 - p) for c in chans]
         emb = nets_oracle.forward(arch, live, xs[i % 2], training=True, drop=drop)
         loss = supcon_oracle.loss_torch_cpu(emb, y, temperature=T_SUPCON)
         opt.zero_grad()
         loss.backward()
         torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
         opt.step()
-        float(loss)
+        return loss.item()
+    return step
+
+
+def cpu_train_steps(arch, views, steps, warmup=1, threads=None, budget_s=150.0):
+    """The reference's CPU training step on the host cores: -> (samples/s, threads, steps actually timed). Stops early once
+    `budget_s` of timed work has accumulated, so a large --steps cannot run for an hour."""
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    step = _train_step_fn(arch, views, "cpu")
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        step(i)
         if i >= warmup:
             times.append(time.perf_counter() - t0)
-    return views / (sum(times) / len(times)), threads
+            if sum(times) > budget_s:
+                break
+    return views / (sum(times) / len(times)), threads, len(times)
+
+
+def _ref_mfcc():
+    """(per-clip fn, batched fn) of the front end on the CPU: reference MFCCExtractor when vendored, else the oracle's torch-op port."""
+    if have_reference():
+        from src.datasets.features import MFCCExtractor
+        ext = MFCCExtractor()
+        return (lambda w: [ext(w[i:i + 1]) for i in range(w.shape[0])]), (lambda w: ext(w))
+    from oracle import mfcc_oracle
+    return (lambda w: mfcc_oracle.mfcc_torch_cpu(w, per_clip=True)), (lambda w: mfcc_oracle.mfcc_torch_cpu(w, per_clip=False))
+
+
+def _ref_supcon():
+    if have_reference():
+        from src.training.losses import get_loss_fn
+        fn = get_loss_fn("supervised_contrastive", temperature=T_SUPCON)
+        return lambda f, y: fn(f, y)
+    from oracle import supcon_oracle
+    return lambda f, y: supcon_oracle.loss_torch_cpu(f, y, temperature=T_SUPCON)
 
 
 def cpu_frontend(n_clips=1024, threads=None):
-    """clips/s of the oracle's torch-op port of MFCCExtractor on the host: (a) one clip per call, the reference's real
-    training behaviour (dataset.py:90), timed at 1 thread and at all threads (tiny per-clip ops often run faster
-    single-threaded) and the better one reported; (b) one batched call with all threads (the reference's best case)."""
-    from oracle import mfcc_oracle
+    """clips/s of the reference MFCCExtractor on the host: (a) one clip per call, the reference's real training behaviour
+    (dataset.py:90), timed at 1 thread and at all threads (tiny per-clip ops often run faster single-threaded) and the better
+    one reported; (b) one batched call with all threads (the reference's best case)."""
+    per_clip_fn, batched_fn = _ref_mfcc()
     all_threads = threads or os.cpu_count()
     w = 0.1 * torch.randn(n_clips, 16000, generator=torch.Generator().manual_seed(0))
     best, best_t = 0.0, 1
     for th in sorted({1, all_threads}):
         torch.set_num_threads(th)
-        mfcc_oracle.mfcc_torch_cpu(w[:8], per_clip=True)
+        per_clip_fn(w[:8])
         n = n_clips if th == 1 else max(64, n_clips // 8)
         t0 = time.perf_counter()
-        mfcc_oracle.mfcc_torch_cpu(w[:n], per_clip=True)
+        per_clip_fn(w[:n])
         v = n / (time.perf_counter() - t0)
         if v > best:
             best, best_t = v, th
     torch.set_num_threads(all_threads)
-    mfcc_oracle.mfcc_torch_cpu(w[:64], per_clip=False)
+    batched_fn(w[:64])
     t0 = time.perf_counter()
-    mfcc_oracle.mfcc_torch_cpu(w, per_clip=False)
+    batched_fn(w)
     batched = n_clips / (time.perf_counter() - t0)
     return best, batched, best_t
 
 
+def cpu_supcon(n=8192, d=128, reps=2):
+    fn = _ref_supcon()
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(0)
+    fc = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=1).requires_grad_(True)
+    yc = torch.randint(0, 38, (n,), generator=g)
+    fn(fc, yc).backward()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        fc.grad = None
+        fn(fc, yc).backward()
+    return n / ((time.perf_counter() - t0) / reps)
+
+
+def workload_config(workload, world, views=None):
+    """The `config` object both arms print (identical dicts: the driver compares them)."""
+    wl = WORKLOADS[workload]
+    cfg = {"workload": wl["desc"]}
+    if "arch" in wl:
+        v = int(views or wl["views"])
+        cfg.update(views_per_gpu=v, global_views=v * world)
+    return cfg
+
+
 def run_reference(args):
+    """Reference arm: the reference's own CPU implementation of the path (oracle/_ref when vendored, else the oracle port) on
+    all host cores. Rank 0 alone works; `steps` in the printed line is the number of steps ACTUALLY timed."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
+    kind = ref_kind()
+    timed = args.steps
     if args.workload == "supcon_8192":
-        from oracle import supcon_oracle
-        torch.set_num_threads(os.cpu_count())
-        g = torch.Generator().manual_seed(0)
-        fc = torch.nn.functional.normalize(torch.randn(8192, 128, generator=g), dim=1).requires_grad_(True)
-        yc = torch.randint(0, 38, (8192,), generator=g)
-        supcon_oracle.loss_torch_cpu(fc, yc, temperature=T_SUPCON).backward()
-        t0 = time.perf_counter()
-        fc.grad = None
-        supcon_oracle.loss_torch_cpu(fc, yc, temperature=T_SUPCON).backward()
-        value, unit, metric, threads = 8192 / (time.perf_counter() - t0), "views/s", "supcon_fwd_bwd_views_per_sec", os.cpu_count()
-        sample = "1 timed fwd+bwd of the same 8192 x 128 problem after 1 warm-up"
+        reps = max(1, min(args.steps, 5))
+        value, unit, metric, threads = cpu_supcon(reps=reps), "views/s", "supcon_fwd_bwd_views_per_sec", os.cpu_count()
+        timed = reps
+        sample = f"{reps} timed fwd+bwd of the same 8192 x 128 problem after 1 warm-up"
     elif args.workload == "frontend":
         per_clip, batched, threads = cpu_frontend(1024)
         value, unit = max(per_clip, batched), "clips/s"
-        sample = "1024 clips: one clip per call (dataset.py:90 behaviour, %d thread(s)) %.0f clips/s; one batched call (all %d threads) %.0f clips/s; value = the better" % (threads, per_clip, os.cpu_count(), batched)
+        sample = "1024 of the 65 536 clips: one clip per call (dataset.py:90 behaviour, %d thread(s)) %.0f clips/s; one batched call (all %d threads) %.0f clips/s; value = the better" % (threads, per_clip, os.cpu_count(), batched)
         threads = os.cpu_count() if batched >= per_clip else threads
         metric = "mfcc_frontend_clips_per_sec"
+        timed = 1
     else:
-        steps = max(1, min(args.steps, 3))
-        value, threads = cpu_train_steps(wl["arch"], wl["views"], steps, warmup=min(args.warmup, 1))
+        views = int(args.views_per_gpu or wl["views"])
+        value, threads, timed = cpu_train_steps(wl["arch"], views, max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
         unit, metric = "samples/s", "supcon_train_samples_per_sec"
-        sample = f"{steps} timed step(s) of the same {wl['views']}-view step after {min(args.warmup, 1)} warm-up"
-    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": (wl.get("views", wl.get("n", 1)) / value * 1e3) if args.workload != "frontend" else None, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
-            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port", "sample": sample},
+        sample = (f"{timed} timed step(s) of one {views}-view shard (the per-GPU batch; the global batch is {views * args.gpus} views) after "
+                  f"{max(1, min(args.warmup, 2))} warm-up; a run stops early after 150 s of timed work")
+    per = int(args.views_per_gpu or wl["views"]) if "arch" in wl else wl.get("n", 1)
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": timed, "steps_requested": args.steps,
+            "warmup": args.warmup,
+            "ms_per_step": (per / value * 1e3) if args.workload != "frontend" else None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, args.gpus, args.views_per_gpu),
+            "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     _emit(line)
+
+
+def run_torch_cuda(args):
+    """Yardstick arm (not the reference arm, not the product): the reference's modules -- or the oracle's restatement of them --
+    run by stock PyTorch on cuda:0 (cuDNN / cuBLAS / ATen kernels, TF32 off so the arithmetic class matches), same step, same
+    inputs. Answers "does the hand-written path beat what `device: cuda` in the reference's config would have given?"."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    wl = WORKLOADS[args.workload]
+    dev = "cuda:0"
+    torch.cuda.set_device(0)
+    if args.workload == "supcon_8192":
+        fn = _ref_supcon()
+        g = torch.Generator().manual_seed(0)
+        fc = torch.nn.functional.normalize(torch.randn(8192, 128, generator=g), dim=1).to(dev).requires_grad_(True)
+        yc = torch.randint(0, 38, (8192,), generator=g).to(dev)
+
+        def step(i):
+            fc.grad = None
+            fn(fc, yc).backward()
+        per, unit, metric = 8192, "views/s", "supcon_fwd_bwd_views_per_sec"
+    elif args.workload == "frontend":
+        _, batched_fn = _ref_mfcc()
+        w = frontend_inputs(4096, dev)
+        if have_reference():
+            from src.datasets.features import MFCCExtractor
+            ext = MFCCExtractor().to(dev)
+            batched_fn = lambda t: ext(t)
+        else:
+            raise SystemExit("torch_cuda front end needs the vendored reference (oracle/_ref)")
+
+        def step(i):
+            batched_fn(w)
+        per, unit, metric = 4096, "clips/s", "mfcc_frontend_clips_per_sec"
+    else:
+        views = int(args.views_per_gpu or wl["views"])
+        fn = _train_step_fn(wl["arch"], views, dev)
+
+        def step(i):
+            fn(i)
+        per, unit, metric = views, "samples/s", "supcon_train_samples_per_sec"
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    _emit({"impl": "torch_cuda", "metric": metric, "value": per / (ms * 1e-3), "unit": unit, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+           "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": workload_config(args.workload, 1, args.views_per_gpu),
+           "note": ("stock PyTorch %s on cuda:0, TF32 disabled, cudnn.benchmark on, eager; modules: %s. A yardstick, not the baseline: "
+                    "library kernels (cuDNN/cuBLAS/ATen)" % (torch.__version__, "the reference's own (oracle/_ref)" if have_reference() else "oracle restatement"))})
 
 
 # ------------------------------------------------------------------------------------------------ main
@@ -448,7 +706,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_cuda"])
+    ap.add_argument("--views-per-gpu", type=int, default=None, help="override the workload's per-GPU batch (training workloads), e.g. 512 for BASELINE configs[4]")
     ap.add_argument("--workload", default="train_cnn_deep", choices=list(WORKLOADS))
     ap.add_argument("--no-also", action="store_true", help="skip the secondary workloads")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
@@ -458,6 +717,9 @@ def main():
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.impl == "torch_cuda":
+        run_torch_cuda(args)
         return
 
     if not torch.cuda.is_available():
@@ -490,14 +752,14 @@ def main():
                 "gpu_launches": r["launches"] * args.steps, "config": {"workload": wl["desc"], "l2": "4.19 GB in / 2.1 GB out per step, far larger than the 126 MB L2"}}
         clocks = None
     else:
-        r = bench_train(args.workload, args.steps, args.warmup, parallel, device, use_graph=not args.no_graph)
+        r = bench_train(args.workload, args.steps, args.warmup, parallel, device, use_graph=not args.no_graph, views=args.views_per_gpu)
         roof = roofline_from_profile(r["prof"], pk, pk_kind)
         line = {"metric": "supcon_train_samples_per_sec", "value": r["value"], "unit": "samples/s", "ms_per_step": r["ms_per_step"], "dtype": "f32",
                 "roofline": roof,
                 "e2e": {"value": r["e2e_value"], "unit": "samples/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
                 "gpu_launches": int(round(r["launches"] * args.steps)),
-                "config": {"workload": wl["desc"], "views_per_gpu": r["views"], "global_views": r["views"] * world,
-                           "parallelism": f"dp{world}: all_gather(embeddings, labels, row stats) + flat-bucket gradient all-reduce; per-rank BatchNorm statistics",
+                "config": workload_config(args.workload, world, args.views_per_gpu),
+                "detail": {"parallelism": f"dp{world}: all_gather(embeddings, labels, row stats) + flat-bucket gradient all-reduce; per-rank BatchNorm statistics",
                            "precision": "fp32 storage and accumulate; convolutions on tcgen05 tensor cores with fp32 operands split into fp16 hi + lo (3 products per pair, ~22-bit operands: fp32-level accuracy, parity-tested at 1e-4), exact-fp32 SIMT for the Cin=1 stem",
                            "launch": "eager launches" if args.no_graph else ("whole step captured in one CUDA graph (inputs copied into static buffers each step)" if world == 1 else "four captured graph segments per step with the 5 NCCL exchanges issued eagerly between them"),
                            "l2": "no explicit flush: each step streams ~2 GB of activations (>> 126 MB L2); inputs rotate over 4 device buffers",
@@ -514,46 +776,48 @@ def main():
     if clocks is not None:
         line["clocks"] = clocks
 
+    kind = ref_kind() if (world == 1 and not args.no_cpu) else None
+    ref_note = "the reference's own modules vendored in oracle/_ref" if kind == "reference" else "oracle port (same ATen ops as the reference)"
     if world == 1 and not args.no_also:
         also = {}
         try:
             if args.workload != "frontend":
                 f = bench_frontend(3, 3, device)
-                also["mfcc_frontend_clips_per_sec"] = {"value": f["value"], "unit": "clips/s", "ms_per_step": f["ms_per_step"], "workload": WORKLOADS["frontend"]["desc"],
-                                                       "roofline": {"bound": "hbm", "kernel": "frontend_kernel", "achieved": f["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": f["gbs"] / pk["hbm_gbs"]},
-                                                       "e2e": {"value": f["e2e_value"], "unit": "clips/s", "sample": f["e2e_sample"]}}
+                fe = {"value": f["value"], "unit": "clips/s", "ms_per_step": f["ms_per_step"], "workload": WORKLOADS["frontend"]["desc"],
+                      "roofline": {"bound": "hbm", "kernel": "frontend_kernel", "achieved": f["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": f["gbs"] / pk["hbm_gbs"]},
+                      "e2e": {"value": f["e2e_value"], "unit": "clips/s", "sample": f["e2e_sample"]}}
+                if kind:
+                    pc, bt, th = cpu_frontend(512)
+                    fe["cpu_baseline"] = {"value": max(pc, bt), "unit": "clips/s", "cores": os.cpu_count() if bt >= pc else th, "kind": kind,
+                                          "sample": "512 clips, %s: one clip per call (%d thread(s)) %.0f clips/s; one batched call %.0f clips/s; value = the better" % (ref_note, th, pc, bt)}
+                also["mfcc_frontend_clips_per_sec"] = fe
             other = "train_cnn_small" if args.workload != "train_cnn_small" else "train_cnn_deep"
-            o = bench_train(other, args.steps, args.warmup, None, device, want_profile=False, use_graph=not args.no_graph)
-            also[f"supcon_train_samples_per_sec[{other}]"] = {"value": o["value"], "unit": "samples/s", "ms_per_step": o["ms_per_step"], "e2e": o["e2e_value"],
-                                                              "workload": WORKLOADS[other]["desc"]}
+            o = bench_train(other, args.steps, args.warmup, None, device, want_profile=True, use_graph=not args.no_graph)
+            oe = {"value": o["value"], "unit": "samples/s", "ms_per_step": o["ms_per_step"], "e2e": o["e2e_value"], "workload": WORKLOADS[other]["desc"],
+                  "roofline": roofline_from_profile(o["prof"], pk, pk_kind),
+                  "step_tflops": FLOP_PER_SAMPLE[o["arch"]] * o["views"] / (o["ms_per_step"] * 1e-3) / 1e12}
+            if kind:
+                v, th, n = cpu_train_steps(o["arch"], o["views"], 5, warmup=1, budget_s=30.0)
+                oe["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": th, "kind": kind, "sample": f"{ref_note}: 1 warm-up + {n} timed steps of the same {o['views']}-view step"}
+            also[f"supcon_train_samples_per_sec[{other}]"] = oe
+            # clips -> optimiser step with the device-resident dataset path (SURVEY 8f.1 / 8d's end-to-end row)
+            p = bench_pipeline(max(args.steps, 20), args.warmup, device)
+            also["clips_to_optimizer_step_samples_per_sec"] = p
         except Exception as e:  # secondary numbers must never sink the primary line
             also["error"] = repr(e)
         line["also"] = also
 
-    if world == 1 and not args.no_cpu and args.workload == "supcon_8192":
-        from oracle import supcon_oracle
-        torch.set_num_threads(os.cpu_count())
-        g = torch.Generator().manual_seed(0)
-        fc = torch.nn.functional.normalize(torch.randn(8192, 128, generator=g), dim=1).requires_grad_(True)
-        yc = torch.randint(0, 38, (8192,), generator=g)
-        supcon_oracle.loss_torch_cpu(fc, yc, temperature=T_SUPCON).backward()
-        t0 = time.perf_counter()
-        for _ in range(2):
-            fc.grad = None
-            supcon_oracle.loss_torch_cpu(fc, yc, temperature=T_SUPCON).backward()
-        dt = (time.perf_counter() - t0) / 2
-        line["cpu_baseline"] = {"value": 8192 / dt, "unit": "views/s", "cores": os.cpu_count(), "kind": "port", "sample": "2 timed fwd+bwd of the same 8192 x 128 problem (torch CPU, reference op sequence)"}
-    elif world == 1 and not args.no_cpu:
-        if args.workload == "frontend":
-            per_clip, batched, threads = cpu_frontend(1024)
-            line["cpu_baseline"] = {"value": max(per_clip, batched), "unit": "clips/s", "cores": os.cpu_count() if batched >= per_clip else threads, "kind": "port",
-                                    "sample": "oracle torch-op port of MFCCExtractor on 1024 clips: one clip per call (%d thread(s)) %.0f clips/s; one batched call (all threads) %.0f clips/s; value = the better" % (threads, per_clip, batched)}
-        else:
-            v, threads = cpu_train_steps(wl["arch"], wl["views"], 3, warmup=1)
-            line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
-                                    "sample": f"oracle port (same ATen ops as the reference) of the same {wl['views']}-view step: 1 warm-up + 3 timed steps"}
-            pc, bt, _ = cpu_frontend(512)
-            line["cpu_baseline"]["frontend_clips_per_sec"] = {"per_clip_calls": pc, "batched": bt, "sample": "512 clips"}
+    if kind and args.workload == "supcon_8192":
+        line["cpu_baseline"] = {"value": cpu_supcon(reps=2), "unit": "views/s", "cores": os.cpu_count(), "kind": kind,
+                                "sample": f"2 timed fwd+bwd of the same 8192 x 128 problem, {ref_note}"}
+    elif kind and args.workload == "frontend":
+        per_clip, batched, threads = cpu_frontend(1024)
+        line["cpu_baseline"] = {"value": max(per_clip, batched), "unit": "clips/s", "cores": os.cpu_count() if batched >= per_clip else threads, "kind": kind,
+                                "sample": "1024 of the 65 536 clips, %s: one clip per call (%d thread(s)) %.0f clips/s; one batched call (all threads) %.0f clips/s; value = the better" % (ref_note, threads, per_clip, batched)}
+    elif kind:
+        v, threads, n = cpu_train_steps(wl["arch"], r["views"], 3, warmup=1)
+        line["cpu_baseline"] = {"value": v, "unit": "samples/s", "cores": threads, "kind": kind,
+                                "sample": f"{ref_note}: 1 warm-up + {n} timed steps of the same {r['views']}-view step"}
     _emit(line)
     if parallel is not None:
         torch.distributed.destroy_process_group()

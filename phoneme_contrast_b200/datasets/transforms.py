@@ -196,7 +196,23 @@ class Compose:
     def __init__(self, transforms: list):
         self.transforms = transforms
 
+    def _fusable(self) -> bool:
+        """One pass applies masks, then noise: only an order with every mask ahead of the noise can be fused."""
+        seen_noise = False
+        for t in self.transforms:
+            if isinstance(t, GaussianNoise):
+                seen_noise = True
+            elif seen_noise and isinstance(t, (TimeMask, FrequencyMask)):
+                return False
+            elif not isinstance(t, (TimeMask, FrequencyMask, TimeStretch)):
+                return False
+        return True
+
     def __call__(self, x: torch.Tensor, seed: Optional[int] = None) -> torch.Tensor:
+        if not self._fusable():       # any other composition: the reference's literal loop (transforms.py:139-144)
+            for i, t in enumerate(self.transforms):
+                x = t(x, seed=None if seed is None else seed + i * 1000)
+            return x
         rec, noise = self.describe(seed, x.shape)
         if rec["t1"][0] <= rec["t0"][0] and rec["f1"][0] <= rec["f0"][0] and rec["noise_level"][0] == 0.0:
             return x
