@@ -208,6 +208,17 @@ int pc_conv_fwd(const float* x, const float* wf, const float* bias, const PcConv
  * the BatchNorm-backward apply calls below; PC_PREC_FP16X2 derives its power-of-two operand scale from it (NULL: scale 1). */
 int pc_conv_dgrad(const float* dy, const float* wd, const PcConvGeom* g, float* dx, int accumulate, int prec,
                   const float* dy_amax, int dy_presplit, pc_stream_t stream);
+/* Halo-resident engine for stride-1 3x3 pad-1 layers on the FP16X2 planes (csrc/conv_halo.cu): persistent CTAs, the activation
+ * tile + halo loaded once per 64-channel chunk by tiled TMA boxes (zero padding materialised by out-of-bounds fill) and shared
+ * by all 9 taps through row-shifted UMMA descriptors, weight stages multicast across a cluster (PC_HALO_CLUSTER = 1 | 2 | 4),
+ * double-buffered TMEM accumulators. pc_conv_fwd / pc_conv_dgrad route to it automatically when it covers the layer
+ * (pc_conv_halo_supported; PC_CONV_HALO=0 disables); the weight operand is the one pc_pack_conv_weight_tc writes. Same
+ * arithmetic (three fp16 products per operand pair) and the same outputs as the per-tap-gather kernels. */
+int pc_conv_halo_supported(const PcConvGeom* g, int dgrad);
+int pc_conv_fwd_halo(const void* x_planes, const void* wp, const float* bias, const PcConvGeom* g, float* y, double* stats,
+                     pc_stream_t stream);
+int pc_conv_dgrad_halo(const void* dy_planes, const void* wp, const PcConvGeom* g, float* dx, int accumulate,
+                       const float* dy_amax, pc_stream_t stream);
 /* dy_presplit != 0 (here and in pc_conv_wgrad): `dy` points to the fp16 hi | lo planes written by pc_bn_*_bwd_apply (dy_planes),
  * scaled by the power of two derived from *dy_amax; the gather copies bytes and the epilogue undoes the scale. */
 /* dw (OIHW) and db from x (through xform) and dy. workspace >= pc_conv_wgrad_workspace(g) bytes. */

@@ -803,9 +803,18 @@ extern "C" int pc_pack_conv_weights_tc_batch(const PcPackJob* jobs, int n_jobs, 
   return PC_OK;
 }
 
+extern "C" int pc_conv_halo_supported(const PcConvGeom* g, int dgrad);
+extern "C" int pc_conv_fwd_halo(const void* x_planes, const void* wp, const float* bias, const PcConvGeom* g, float* y, double* stats, pc_stream_t stream);
+extern "C" int pc_conv_dgrad_halo(const void* dy_planes, const void* wp, const PcConvGeom* g, float* dx, int accumulate, const float* dy_amax,
+                                  pc_stream_t stream);
+
 extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias, const PcConvGeom* g, const PcInXform* xf, float* y,
                               double* stats, int prec, pc_stream_t stream) {
   if (!pc_conv_tc_supported(g, 0, prec)) return PC_EUNSUPPORTED;
+  // stride-1 3x3 layers on pre-split planes: the halo-resident persistent engine (conv_halo.cu); same weight operand, same outputs
+  if (prec == PC_PREC_FP16X2 && xf != nullptr && xf->presplit && !xf->scale && !xf->shift && !xf->drop && !xf->relu && g_dbg == nullptr &&
+      pc_conv_halo_supported(g, 0))
+    return pc_conv_fwd_halo(x, wp, bias, g, y, stats, stream);
   Params p{};
   p.A = x; p.Bp = (const unsigned char*)wp; p.bias = bias; p.C = y; p.stats = stats;
   if (xf != nullptr) { p.xf.scale = xf->scale; p.xf.shift = xf->shift; p.xf.drop = xf->drop; p.xf.relu = xf->relu; }
@@ -826,6 +835,8 @@ extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias,
 extern "C" int pc_conv_dgrad_tc(const float* dy, const void* wp, const PcConvGeom* g, float* dx, int accumulate, int prec,
                                 const float* dy_amax, int dy_presplit, pc_stream_t stream) {
   if (!pc_conv_tc_supported(g, 1, prec)) return PC_EUNSUPPORTED;
+  if (prec == PC_PREC_FP16X2 && dy_presplit && dy_amax != nullptr && g_dbg == nullptr && pc_conv_halo_supported(g, 1))
+    return pc_conv_dgrad_halo(dy, wp, g, dx, accumulate, dy_amax, stream);
   Params p{};
   p.A = dy; p.Bp = (const unsigned char*)wp; p.C = dx; p.a_amax = dy_amax;
   if (dy_presplit) {      // dy = fp16 hi | lo planes already scaled by f16_operand_scale(*dy_amax) (pc_bn_*_bwd_apply)

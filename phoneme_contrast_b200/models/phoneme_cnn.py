@@ -20,15 +20,20 @@ from .. import ops
 from .base import BaseModel
 from .registry import model_registry
 
-_PREC = {"fp32": L.PREC_FP32, "tf32x3": L.PREC_TF32X3, "bf16": L.PREC_BF16, "fp16x2": L.PREC_FP16X2}
+_PREC = {"fp32": L.PREC_FP32, "tf32x3": L.PREC_TF32X3, "fp16x2": L.PREC_FP16X2}
 
 
 def _precision(config) -> int:
     # default: fp16x2 -- tcgen05 tensor cores with fp32-level accuracy (operands split into fp16 hi + lo, three products per
     # pair at the kind::f16 rate) for every eligible layer (64-channel granularity; 32-channel layers fall back to the
     # equivalent TF32x3 split), exact-fp32 SIMT kernels elsewhere. "tf32x3" selects the TF32 split everywhere (no fp16 range
-    # assumptions), "fp32" forces the SIMT kernels, "bf16" is the 1e-2 opt-in mode.
+    # assumptions), "fp32" forces the SIMT kernels. A single-product bf16 mode existed in round 1; measured against the oracle it
+    # lands at 1.5e-2 .. 2.9e-2 relative on the embeddings at every batch size tried (profiles/r2_notes.md), i.e. outside
+    # north_star's 1e-2 bar for bf16, so it is no longer selectable for the networks (the GEMM unit test still covers the kernel).
     name = os.environ.get("PC_PRECISION") or config.get("precision", "fp16x2")
+    if name == "bf16":
+        raise ValueError("precision 'bf16' was withdrawn: single-product bf16 convolutions miss the 1e-2 parity bar on these "
+                         "networks (measured 1.5e-2 .. 2.9e-2); use 'fp16x2' (default), 'tf32x3' or 'fp32'")
     if name not in _PREC:
         raise ValueError(f"precision must be one of {list(_PREC)}, got {name!r}")
     return _PREC[name]

@@ -1,0 +1,91 @@
+"""Halo-resident convolution engine (csrc/conv_halo.cu) against an fp64 reference convolution and against the round-1
+per-tap-gather kernel on the same operand bytes: forward (+ bias, BatchNorm sums) and data gradient, every cluster size,
+image shapes of all four cnn_deep stages, batch sizes that leave partial / empty tiles in a cluster."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+CASES = [  # B, H, W, Cin, Cout
+    (3, 20, 51, 64, 64),
+    (5, 10, 26, 128, 128),
+    (7, 5, 13, 256, 256),
+    (9, 3, 7, 512, 512),
+    (2, 5, 13, 64, 192),     # Cout not a multiple of the 128 tile
+    (40, 20, 51, 64, 64),    # several tiles per CTA
+    (1, 3, 7, 128, 64),      # a single, mostly empty tile
+]
+
+
+def _ref_conv(x, w, bias):
+    return torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double() if bias is not None else None, padding=1).permute(0, 2, 3, 1)
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 0])     # 0: streaming kernel even where the weight-resident variant applies
+@pytest.mark.parametrize("case", CASES)
+def test_halo_forward(case, cluster, monkeypatch):
+    from phoneme_contrast_b200 import _lib as L
+    from phoneme_contrast_b200 import ops
+    import ctypes as C
+    B, H, W, Cin, Cout = case
+    g = ops.conv_geom(B, H, W, Cin, Cout, 3, 1, 1)
+    gen = torch.Generator(device=DEV).manual_seed(B * 1000 + Cin + Cout)
+    x = torch.randn(B, H, W, Cin, device=DEV, generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=gen) * (2.0 / (Cin * 9)) ** 0.5
+    bias = torch.randn(Cout, device=DEV, generator=gen)
+    cw = ops.ConvWeights(w, g, L.PREC_FP16X2)
+    planes = ops.bn_act_split(x)
+    monkeypatch.setenv("PC_HALO_CLUSTER", str(max(cluster, 1)))
+    monkeypatch.setenv("PC_HALO_RESIDENT", "0" if cluster == 0 else "1")
+    monkeypatch.setenv("PC_HALO_ALL", "1")       # also the 256-channel layers, which the default routing leaves to the per-tap kernel
+    assert L.lib().pc_conv_halo_supported(C.byref(g), 0) == 1
+    st = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    y = ops.conv_fwd(planes, cw.wf, bias, g, dict(presplit=True), st, cw.prec_f)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, bias)
+    scale = float(ref.abs().max())
+    err = float((y.double() - ref).abs().max())
+    assert err <= 5e-6 * scale, (err, scale)
+    np.testing.assert_allclose(st[0].cpu().numpy(), ref.sum(dim=(0, 1, 2)).cpu().numpy(), rtol=2e-5, atol=2e-4 * scale)
+    np.testing.assert_allclose(st[1].cpu().numpy(), (ref ** 2).sum(dim=(0, 1, 2)).cpu().numpy(), rtol=2e-5)
+    # the round-1 kernel on the same operand bytes
+    monkeypatch.setenv("PC_CONV_HALO", "0")
+    assert L.lib().pc_conv_halo_supported(C.byref(g), 0) == 0
+    y0 = ops.conv_fwd(planes, cw.wf, bias, g, dict(presplit=True), None, cw.prec_f)
+    assert float((y - y0).abs().max()) <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("cluster", [1, 4])
+@pytest.mark.parametrize("case", CASES[:4] + CASES[5:])
+def test_halo_dgrad(case, cluster, monkeypatch):
+    from phoneme_contrast_b200 import _lib as L
+    from phoneme_contrast_b200 import ops
+    import ctypes as C
+    B, H, W, Cin, Cout = case
+    g = ops.conv_geom(B, H, W, Cin, Cout, 3, 1, 1)
+    gen = torch.Generator(device=DEV).manual_seed(B * 77 + Cin + 3 * Cout)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=gen) * (2.0 / (Cin * 9)) ** 0.5
+    yconv = torch.randn(B, H, W, Cout, device=DEV, generator=gen)
+    dout = torch.randn(B, H, W, Cout, device=DEV, generator=gen) * 1e-6
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV)
+    st = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    st[0] = yconv.double().sum((0, 1, 2)); st[1] = (yconv.double() ** 2).sum((0, 1, 2))
+    co = ops.bn_finalize(st, B * H * W, bn, True)
+    cw = ops.ConvWeights(w, g, L.PREC_FP16X2)
+    a0, a1 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    dy, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a0)
+    dy_ps, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a1, planes=True)
+    monkeypatch.setenv("PC_HALO_CLUSTER", str(cluster))
+    monkeypatch.setenv("PC_HALO_ALL", "1")
+    assert L.lib().pc_conv_halo_supported(C.byref(g), 1) == 1
+    dx = ops.conv_dgrad(dy_ps, cw.wd, g, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+    ref = torch.nn.functional.conv_transpose2d(dy.permute(0, 3, 1, 2).double(), w.double(), padding=1).permute(0, 2, 3, 1)
+    scale = float(ref.abs().max())
+    assert float((dx.double() - ref).abs().max()) <= 1e-5 * scale
+    # accumulate into an existing tensor
+    base = torch.randn(B, H, W, Cin, device=DEV, generator=gen) * scale
+    acc = base.clone()
+    ops.conv_dgrad(dy_ps, cw.wd, g, out=acc, accumulate=True, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+    assert float((acc.double() - (base.double() + ref)).abs().max()) <= 1e-5 * scale + 1e-6 * float(base.abs().max())

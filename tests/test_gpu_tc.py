@@ -145,23 +145,15 @@ def test_nets_split_precision_match_oracle(arch, B, precision, monkeypatch):
     _check_grads(grads, grads_ref)
 
 
-@pytest.mark.parametrize("arch,B", [("phoneme_cnn_deep", 8)])
-def test_nets_bf16_within_1e2(arch, B, monkeypatch):
+def test_bf16_network_mode_withdrawn(monkeypatch):
+    """Round 1 offered a single-product bf16 mode; it measures 1.5e-2 .. 2.9e-2 on the embeddings (profiles/tools/bf16_diag.py),
+    outside north_star's 1e-2 bar, so selecting it for a network is an error rather than a silently inaccurate run."""
+    from phoneme_contrast_b200.models import model_registry
+    with pytest.raises(ValueError, match="withdrawn"):
+        model_registry.create("phoneme_cnn_deep", {"precision": "bf16"})
     monkeypatch.setenv("PC_PRECISION", "bf16")
-    from tests.test_gpu_parity import _oracle_net, _run_net
-    from oracle import nets_oracle
-    cfg = {"dropout_rate": 0.0}
-    sd = nets_oracle.synthetic_state_dict(arch, cfg, seed=3)
-    rs = np.random.RandomState(8)
-    x = rs.standard_normal((B, 1, 40, 101)).astype(np.float32)
-    y = (np.arange(B) // 2).astype(np.int64)
-    _, emb, loss, grads = _run_net(arch, cfg, sd, x, y)
-    emb_ref, loss_ref, grads_ref, _ = _oracle_net(arch, cfg, sd, x, y)
-    # bf16 operands through 13 conv layers with small-batch BatchNorm: this synthetic, deliberately ill-conditioned case
-    # (B = 8, random weights) lands at a few percent; the 1e-2 bar of north_star is met by TF32x3, which is the default
-    # tensor-core mode. bf16 stays an opt-in throughput mode.
-    assert np.linalg.norm(emb - emb_ref) / np.linalg.norm(emb_ref) <= 0.1
-    assert abs(loss - loss_ref) <= 2e-2 * abs(loss_ref)
+    with pytest.raises(ValueError, match="withdrawn"):
+        model_registry.create("phoneme_cnn", {})
 
 
 @pytest.mark.parametrize("n,d,row0,nrows", [(1024, 128, 0, 1024), (1100, 128, 0, 1100), (2000, 64, 0, 2000), (2048, 128, 512, 300),
@@ -227,10 +219,12 @@ def test_supcon_tc_backward_matches_simt_and_oracle(n, d, row0, nrows, monkeypat
 
 @pytest.mark.parametrize("case", [(4, 20, 51, 64, 64, 3, 1, 1), (3, 20, 51, 64, 128, 3, 2, 1), (2, 10, 26, 128, 256, 3, 2, 1), (5, 3, 7, 512, 512, 3, 1, 1),
                                   (3, 20, 51, 64, 128, 1, 2, 0)])
-def test_tc_conv_fwd_presplit_input(case):
+def test_tc_conv_fwd_presplit_input(case, monkeypatch):
     """A convolution reading the activation as pre-split fp16 planes (pc_bn_act_split) gives bit-identical outputs to the one
-    that applies BatchNorm + ReLU + dropout + split inside its gather: the operand bytes are the same."""
+    that applies BatchNorm + ReLU + dropout + split inside its gather: the operand bytes are the same. (Per-tap-gather kernel on
+    both sides: the halo engine sums the same products in a different order and is compared separately in test_gpu_halo.py.)"""
     from phoneme_contrast_b200 import ops
+    monkeypatch.setenv("PC_CONV_HALO", "0")
     B, H, W, Cin, Cout, k, stride, pad = case
     g = ops.conv_geom(B, H, W, Cin, Cout, k, stride, pad)
     gen = torch.Generator(device=DEV).manual_seed(Cin + 2 * Cout + k)
