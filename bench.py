@@ -286,9 +286,15 @@ def bench_supcon(steps, warmup, parallel, device, n=8192, d=128):
     y = y_all[rank * nl:(rank + 1) * nl].to(device)
     loss_fn = get_loss_fn("supervised_contrastive", temperature=T_SUPCON)
 
+    graphed = parallel.graphed_loss(loss_fn, f.detach(), y) if parallel is not None else None
+
     def step():
+        if graphed is not None:          # three graph segments + two all_gathers, static buffers (parallel.GraphedShardedLoss)
+            loss, dF = graphed(f.detach(), None)
+            f.grad = dF
+            return loss
         f.grad = None
-        loss = parallel.loss(loss_fn, f, y) if parallel is not None else loss_fn(f, y)
+        loss = loss_fn(f, y)
         loss.backward()
         return loss
 

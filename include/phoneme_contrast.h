@@ -105,6 +105,14 @@ int pc_compute_deltas(const float* x, int rows, int T, float* out, pc_stream_t s
  * = -(T/T_base) * mean_log_prob_pos (losses.py:76-79). The N x N logits never reach HBM. */
 int pc_supcon_fwd(const float* F, const int64_t* labels, const float* mask, int N, int D, int row0, int nrows,
                   float temperature, float base_temperature, float* stats, float* row_loss, pc_stream_t stream);
+/* Data-parallel exchange helpers (csrc/dp.cu). pack: [n][D] embeddings + [n] int64 labels -> [n][D+2] fp32 rows (label bits in the
+ * last two columns) so that ONE all_gather carries both; unpack: gathered [N][D+2] -> contiguous F [N][D] and labels [N].
+ * loss_from_stats: out[0] = scale * sum of the per-row losses implied by the gathered row statistics [N][4] (scale = 1/N for the
+ * reference's mean over all rows, losses.py:81-82) -- every rank derives the identical global loss without a further collective. */
+int pc_dp_pack(const float* emb, const int64_t* labels, int n, int D, float* packed, pc_stream_t stream);
+int pc_dp_unpack(const float* packed, int N, int D, float* F, int64_t* labels, pc_stream_t stream);
+int pc_supcon_loss_from_stats(const float* stats, int N, float temperature, float base_temperature, float scale, float* out,
+                              pc_stream_t stream);
 /* loss[0] = scale * sum(row_loss[0..n)) in a fixed order (scale = 1/N for 'mean', losses.py:81-84). */
 int pc_sum_scaled(const float* x, int n, float scale, float* out, pc_stream_t stream);
 /* dF[row0..row0+nrows) given the stats of ALL N rows (stats_all [N,4]); coef = (T/T_base)*grad_out/N

@@ -57,6 +57,9 @@ SIGNATURES = {
     "pc_compute_deltas": (i32, [vp, i32, i32, vp, vp]),
     "pc_supcon_fwd": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp]),
     "pc_sum_scaled": (i32, [vp, i32, f32, vp, vp]),
+    "pc_dp_pack": (i32, [vp, vp, i32, i32, vp, vp]),
+    "pc_dp_unpack": (i32, [vp, i32, i32, vp, vp, vp]),
+    "pc_supcon_loss_from_stats": (i32, [vp, i32, f32, f32, f32, vp, vp]),
     "pc_supcon_bwd": (i32, [vp, vp, vp, i32, i32, i32, i32, f32, f32, vp, vp, vp, vp]),
     "pc_supcon_tc_supported": (i32, [i32, i32, i32, i32]),
     "pc_supcon_tc_workspace": (sz, [i32, i32, i32]),

@@ -27,7 +27,7 @@ def _precision(config) -> int:
     # default: fp16x2 -- tcgen05 tensor cores with fp32-level accuracy (operands split into fp16 hi + lo, three products per
     # pair at the kind::f16 rate) for every eligible layer (64-channel granularity; 32-channel layers fall back to the
     # equivalent TF32x3 split), exact-fp32 SIMT kernels elsewhere. "tf32x3" selects the TF32 split everywhere (no fp16 range
-    # assumptions), "fp32" forces the SIMT kernels. A single-product bf16 mode existed in round 1; measured against the oracle it
+    # assumptions), "fp32" forces the SIMT kernels. A single-product bf16 mode existed in round 1; measured against the CPU reference it
     # lands at 1.5e-2 .. 2.9e-2 relative on the embeddings at every batch size tried (profiles/r2_notes.md), i.e. outside
     # north_star's 1e-2 bar for bf16, so it is no longer selectable for the networks (the GEMM unit test still covers the kernel).
     name = os.environ.get("PC_PRECISION") or config.get("precision", "fp16x2")
@@ -241,6 +241,8 @@ def _small_forward(net, x, training):
 
 
 def _small_backward(net, s, demb, grads, training=True):
+    """Generator: yields once after the head and the last block (whose gradients form the contiguous tail of the flat bucket,
+    ~73 % of its bytes) so that a data-parallel caller can start reducing that part while the rest of the backward runs."""
     prec = net._prec
     blocks = net.conv_blocks
     keep = []
@@ -259,6 +261,10 @@ def _small_backward(net, s, demb, grads, training=True):
         wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], grads[convA.bias], prec, mA)
         if b > 0:
             dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d, dy_amax=mA)
+        if b == 2:
+            if net._split_backward:
+                wgrad.join()
+            yield
     wgrad.join()
 
 
@@ -352,6 +358,7 @@ def _deep_forward(net, x, training):
 
 
 def _deep_backward(net, s, demb, grads, training=True):
+    """Generator: yields once after the head and the last residual block (see _small_backward; 74 % of the bucket for cnn_deep)."""
     prec = net._prec
     keep = []
     wgrad = _WgradLane(net, keep)
@@ -370,6 +377,10 @@ def _deep_backward(net, s, demb, grads, training=True):
             dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, None, None, grads[blk[1].weight], grads[blk[1].bias], m1, zp=zp)
             wgrad(r["xin"], dy1, r["g1"], None, grads[blk[0].weight], grads[blk[0].bias], prec, m1)
             dout = ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], prec=r["cw1"].prec_d, dy_amax=m1)
+            if i == len(s.blocks) - 1:
+                if net._split_backward:
+                    wgrad.join()
+                yield
             continue
         g2 = (grads[blk.bn2.weight], grads[blk.bn2.bias])
         # gradient tensors in operand form too: when every consumer of dy (data gradient and weight gradient) runs the FP16X2
@@ -398,6 +409,10 @@ def _deep_backward(net, s, demb, grads, training=True):
             dxin = dysc                                        # identity shortcut: d(out)/d(xin) passes g through
         ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d, dy_amax=m1, dy_presplit=gps)
         dout = dxin
+        if i == len(s.blocks) - 1:
+            if net._split_backward:
+                wgrad.join()
+            yield
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
     st = s.stem
     # the stem's dy is O(1/N) per pixel (the loss is a mean): without the max|dy| operand scale it would sit in fp16 subnormals
@@ -447,6 +462,19 @@ class _NetFunction(torch.autograd.Function):
 class _FusedNet(BaseModel):
     _inject_drop = None
     _drop_step = None
+    _split_backward = False      # set by the graphed data-parallel step: join the weight-gradient lane at the backward's split point
+
+    def tail_bucket_offset(self) -> int:
+        """Element offset, inside the flat gradient bucket (parameter order), of the first parameter of the LAST conv block: the
+        bucket's tail [offset, end) = last block + attention + projection is complete when the backward generator first yields."""
+        last = self.conv_blocks[len(self.conv_blocks) - 1]
+        first = next(last.parameters())
+        off = 0
+        for p in self.parameters():
+            if p is first:
+                return off
+            off += p.numel()
+        raise RuntimeError("last block's parameters not found")
 
     def _finish_init(self):
         _init_weights(self)
@@ -501,8 +529,12 @@ class PhonemeNet(_FusedNet):
     def _engine_forward(self, x, training):
         return _small_forward(self, x, training)
 
-    def _engine_backward(self, saved, demb, grads):
+    def _engine_backward_gen(self, saved, demb, grads):
         return _small_backward(self, saved, demb, grads)
+
+    def _engine_backward(self, saved, demb, grads):
+        for _ in _small_backward(self, saved, demb, grads):
+            pass
 
 
 @model_registry.register("phoneme_cnn_deep")
@@ -541,5 +573,9 @@ class PhonemeNetDeep(_FusedNet):
     def _engine_forward(self, x, training):
         return _deep_forward(self, x, training)
 
-    def _engine_backward(self, saved, demb, grads):
+    def _engine_backward_gen(self, saved, demb, grads):
         return _deep_backward(self, saved, demb, grads)
+
+    def _engine_backward(self, saved, demb, grads):
+        for _ in _deep_backward(self, saved, demb, grads):
+            pass

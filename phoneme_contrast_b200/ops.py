@@ -445,6 +445,28 @@ def supcon_fwd(feats, labels, mask, temperature, base_temperature, row0=0, nrows
     return stats, row_loss
 
 
+def dp_pack(emb, labels):
+    """[n,D] embeddings + [n] int64 labels -> [n, D+2] fp32 rows (label bits in the last two columns): one all_gather carries both."""
+    n, D = emb.shape
+    out = torch.empty(n, D + 2, device=emb.device, dtype=F32)
+    call("pc_dp_pack", ptr(emb), ptr(labels, torch.int64), n, D, ptr(out), stream())
+    return out
+
+
+def dp_unpack(packed, D, F=None, y=None):
+    N = packed.shape[0]
+    F = torch.empty(N, D, device=packed.device, dtype=F32) if F is None else F
+    y = torch.empty(N, device=packed.device, dtype=torch.int64) if y is None else y
+    call("pc_dp_unpack", ptr(packed), N, D, ptr(F), ptr(y, torch.int64), stream())
+    return F, y
+
+
+def supcon_loss_from_stats(stats_all, temperature, base_temperature, scale, out=None):
+    out = torch.empty(1, device=stats_all.device, dtype=F32) if out is None else out
+    call("pc_supcon_loss_from_stats", ptr(stats_all), stats_all.shape[0], float(temperature), float(base_temperature), float(scale), ptr(out), stream())
+    return out
+
+
 def sum_scaled(x, scale):
     out = torch.empty((), device=x.device, dtype=F32)
     call("pc_sum_scaled", ptr(x), x.numel(), float(scale), ptr(out), stream())

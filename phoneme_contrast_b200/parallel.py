@@ -1,13 +1,15 @@
 """Sharded data parallelism for the hot path (new work: the reference is single-process).
 
 One process per GPU (torchrun), torch.distributed over NCCL/NVLink for plumbing. Per step there are exactly
-three small exchanges, all latency-bound at these sizes:
+three exchanges, all latency-bound at these sizes (the COUNT of collectives is what costs):
 
-  C1  all_gather of the local embeddings [n,D] and labels [n]  -> every rank sees global negatives;
-      rank r then computes ONLY its rows [r*n,(r+1)*n) x all N columns of the SupCon problem (1/R of the work);
+  C1  ONE all_gather of [n, D+2] rows = the local embeddings with the label bits packed behind them -> every rank sees
+      global negatives; rank r then computes ONLY its rows [r*n,(r+1)*n) x all N columns of the SupCon problem (1/R of the work);
   C1' all_gather of the per-row statistics [n,4] -> the backward needs (max, den, n_pos) of REMOTE rows to form
-      G_ji, which lets each rank produce dL/dF_local exactly with no gradient reduce-scatter;
-  C2  one all-reduce(SUM) of the flat gradient bucket. SUM, not mean: every rank back-propagates the GLOBAL loss
+      G_ji, which lets each rank produce dL/dF_local exactly with no gradient reduce-scatter; the same statistics give every
+      rank the global loss value, so there is no all-reduce of the loss;
+  C2  all-reduce(SUM) of the flat gradient bucket (the graphed step splits it in two so that the large late-layer part
+      overlaps the rest of the backward). SUM, not mean: every rank back-propagates the GLOBAL loss
       through its own samples only, so the per-rank parameter gradients are disjoint partial sums.
 
 BatchNorm uses per-rank batch statistics (the torch-DDP convention); see DESIGN.md "BatchNorm under DP".
@@ -24,7 +26,7 @@ import torch.distributed as dist
 
 
 class _CudaRowsBackend:
-    """Row-block SupCon through libpc_b200.so (pc_supcon_fwd / pc_supcon_bwd)."""
+    """Row-block SupCon and the exchange helpers through libpc_b200.so (csrc/supcon*.cu, csrc/dp.cu)."""
 
     @staticmethod
     def rows_forward(F, y, temperature, base_temperature, row0, nrows):
@@ -36,25 +38,42 @@ class _CudaRowsBackend:
         from . import ops
         return ops.supcon_bwd(F, y, None, temperature, coef, grad_scale, stats_all, row0, nrows)
 
+    @staticmethod
+    def pack(emb, labels):
+        from . import ops
+        return ops.dp_pack(emb, labels)
+
+    @staticmethod
+    def unpack(packed, D):
+        from . import ops
+        return ops.dp_unpack(packed, D)
+
+    @staticmethod
+    def loss_from_stats(stats_all, temperature, base_temperature):
+        from . import ops
+        return ops.supcon_loss_from_stats(stats_all, temperature, base_temperature, 1.0 / stats_all.shape[0])
+
 
 class _ShardedSupCon(torch.autograd.Function):
+    """Global-batch SupCon over row-sharded embeddings with TWO collectives in the forward and none in the backward:
+    all_gather of the packed [n, D+2] (embeddings + label bits) rows, all_gather of the [n, 4] row statistics. The loss value is
+    reduced locally, identically on every rank, from the gathered statistics."""
+
     @staticmethod
     def forward(ctx, emb_local, labels_local, temperature, base_temperature, group, backend):
         world = dist.get_world_size(group)
         rank = dist.get_rank(group)
         n, d = emb_local.shape
         N = n * world
-        emb_local = emb_local.contiguous()
-        F = torch.empty(N, d, device=emb_local.device, dtype=emb_local.dtype)
-        y = torch.empty(N, device=labels_local.device, dtype=torch.int64)
-        dist.all_gather_into_tensor(F, emb_local, group=group)                                   # C1
-        dist.all_gather_into_tensor(y, labels_local.contiguous().to(torch.int64), group=group)
+        packed = backend.pack(emb_local.contiguous(), labels_local.contiguous().to(torch.int64))
+        packed_all = torch.empty(N, d + 2, device=packed.device, dtype=packed.dtype)
+        dist.all_gather_into_tensor(packed_all, packed, group=group)                             # C1: embeddings + labels
+        F, y = backend.unpack(packed_all, d)
         row0 = rank * n
-        stats, row_loss = backend.rows_forward(F, y, temperature, base_temperature, row0, n)
+        stats, _row_loss = backend.rows_forward(F, y, temperature, base_temperature, row0, n)
         stats_all = torch.empty(N, 4, device=F.device, dtype=stats.dtype)
-        dist.all_gather_into_tensor(stats_all, stats.contiguous(), group=group)                  # C1'
-        total = row_loss.sum(dtype=torch.float32).reshape(1) / N                                 # losses.py:81-82: mean over ALL N rows
-        dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
+        dist.all_gather_into_tensor(stats_all, stats.contiguous(), group=group)                  # C1': row statistics
+        total = backend.loss_from_stats(stats_all, temperature, base_temperature)                # losses.py:81-82: mean over ALL N rows
         ctx.save_for_backward(F, y, stats_all)
         ctx.cfg = (temperature, base_temperature, row0, n, N, backend)
         return total.reshape(())
@@ -67,6 +86,77 @@ class _ShardedSupCon(torch.autograd.Function):
         g = grad_out.to(torch.float32).contiguous().view(1)
         dF = backend.rows_backward(F, y, temperature, coef, g, stats_all, row0, n)
         return dF, None, None, None, None, None
+
+
+class GraphedShardedLoss:
+    """Forward + backward of the sharded SupCon loss on static buffers as THREE captured CUDA-graph segments with the two
+    all_gathers issued eagerly between them (no autograd, no per-call allocation): at 8192 x 128 the whole problem is 0.29 ms on
+    one GPU, so at R ranks the Python / launch overhead of the eager path (about 0.15 ms) is what decides whether sharding pays.
+
+        loss_step = ctx.graphed_loss(loss_fn, emb_local, labels_local)
+        loss, dF_local = loss_step(emb_local, labels_local)      # tensors are copied into the static buffers"""
+
+    def __init__(self, ctx: "DataParallelContext", loss_fn, emb_local: torch.Tensor, labels_local: torch.Tensor, warmup: int = 2):
+        if getattr(loss_fn, "reduction", "mean") != "mean":
+            raise NotImplementedError("the sharded loss implements reduction='mean'")
+        self.ctx, self.group = ctx, ctx.group
+        backend = ctx.backend
+        T = float(loss_fn.temperature)
+        Tb = float(getattr(loss_fn, "base_temperature", T))
+        n, d = emb_local.shape
+        R = ctx.world_size
+        N, row0 = n * R, ctx.rank * n
+        dev = emb_local.device
+        self.emb = emb_local.detach().clone().contiguous()
+        self.labels = labels_local.detach().clone().to(torch.int64).contiguous()
+        self.packed_all = torch.empty(N, d + 2, device=dev, dtype=torch.float32)
+        self.stats_all = torch.empty(N, 4, device=dev, dtype=torch.float32)
+        ones = torch.ones(1, device=dev, dtype=torch.float32)
+
+        def seg0():
+            self.packed = backend.pack(self.emb, self.labels)
+
+        def seg1():
+            self.F, self.y = backend.unpack(self.packed_all, d)
+            stats, _ = backend.rows_forward(self.F, self.y, T, Tb, row0, n)
+            self.stats = stats.contiguous()
+
+        def seg2():
+            self.total = backend.loss_from_stats(self.stats_all, T, Tb)
+            self.dF = backend.rows_backward(self.F, self.y, T, (T / Tb) / N, ones, self.stats_all, row0, n)
+
+        self._segs = (seg0, seg1, seg2)
+        for _ in range(warmup):
+            self._run_eager()
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        self.g = [torch.cuda.CUDAGraph() for _ in range(3)]
+        with torch.no_grad():
+            for g, seg in zip(self.g, self._segs):
+                with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
+                    seg()
+
+    def _exchange(self, i):
+        if i == 0:
+            dist.all_gather_into_tensor(self.packed_all, self.packed, group=self.group)
+        elif i == 1:
+            dist.all_gather_into_tensor(self.stats_all, self.stats, group=self.group)
+
+    def _run_eager(self):
+        with torch.no_grad():
+            for i, seg in enumerate(self._segs):
+                seg()
+                self._exchange(i)
+
+    def __call__(self, emb_local: Optional[torch.Tensor] = None, labels_local: Optional[torch.Tensor] = None):
+        if emb_local is not None:
+            self.emb.copy_(emb_local, non_blocking=True)
+        if labels_local is not None:
+            self.labels.copy_(labels_local, non_blocking=True)
+        for i, g in enumerate(self.g):
+            g.replay()
+            self._exchange(i)
+        return self.total.reshape(()), self.dF
 
 
 class DataParallelContext:
@@ -86,6 +176,10 @@ class DataParallelContext:
             raise NotImplementedError("the sharded loss implements reduction='mean' (the trainer's configuration)")
         base_t = getattr(loss_fn, "base_temperature", loss_fn.temperature)
         return _ShardedSupCon.apply(emb_local, labels_local, float(loss_fn.temperature), float(base_t), self.group, self.backend)
+
+    def graphed_loss(self, loss_fn, emb_local: torch.Tensor, labels_local: torch.Tensor) -> GraphedShardedLoss:
+        """Static-shape, graph-replayed forward + backward of the sharded loss (see GraphedShardedLoss)."""
+        return GraphedShardedLoss(self, loss_fn, emb_local, labels_local)
 
     def all_reduce_gradients(self, flat_grad: torch.Tensor) -> None:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=self.group)                       # C2: one flat bucket

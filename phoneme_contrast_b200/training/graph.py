@@ -71,16 +71,21 @@ class GraphedTrainStep:
 
 
 class GraphedDPStep:
-    """Data-parallel step as FOUR captured segments with the NCCL exchanges issued eagerly between them:
+    """Data-parallel step as FIVE captured segments with the three NCCL exchanges issued eagerly between them:
 
-        g1 forward -> local embeddings | all_gather(F), all_gather(y) | g2 SupCon row block -> row stats, loss partial |
-        all_gather(stats), all_reduce(loss) | g3 SupCon backward + network backward -> flat gradient bucket |
-        all_reduce(bucket) | g4 clip + Adam
+        g0 forward -> local embeddings, packed with the label bits        | all_gather(packed rows)                 C1
+        g1 unpack, SupCon row block -> row statistics                     | all_gather(row statistics)              C1'
+        g2 loss from the gathered statistics, SupCon backward, network backward through the head and the LAST block
+                                                                          | all_reduce(bucket tail, async)          C2a
+        g3 rest of the network backward                                   | all_reduce(bucket head, async), wait both C2b
+        g4 clip + Adam
 
-    Capturing the collectives themselves inside one whole-step graph deadlocked under torchrun; this keeps ~150 kernel launches
-    per step inside graphs (the launch gaps of an eager step cost ~0.2 ms) and leaves 5 small NCCL calls + 4 graph launches
-    on the host. The segments talk to the engine directly (no autograd): they do exactly what `_NetFunction` /
-    `_ShardedSupCon` do in the eager `train_step`."""
+    The tail of the flat gradient bucket (last block + attention + projection: 74 % of cnn_deep's bytes) is complete when the
+    backward is a third of the way through, so its all-reduce runs on NCCL's stream under g3. There is no all-reduce of the
+    loss (every rank reduces the gathered row statistics identically) and labels travel inside the embedding gather: 3
+    collectives per step instead of round 1's 5. Capturing the collectives themselves inside one whole-step graph deadlocked
+    under torchrun in round 1; the segments keep ~150 kernel launches per step inside graphs. The segments talk to the engine
+    directly (no autograd): they do exactly what `_NetFunction` / `_ShardedSupCon` do in the eager `train_step`."""
 
     def __init__(self, trainer, views: torch.Tensor, labels: torch.Tensor, warmup: int = 3):
         import torch.distributed as dist
@@ -114,39 +119,45 @@ class GraphedDPStep:
         backend = par.backend
         params = model._param_list
         self.flat = torch.empty(model._n_param_elems, device=dev, dtype=torch.float32)
+        self.split = int(model.tail_bucket_offset())
         grads, off = {}, 0
         for p in params:
             grads[p] = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         ones = torch.ones(1, device=dev, dtype=torch.float32)
-        self.total = torch.zeros(1, device=dev, dtype=torch.float32)
-        self.y = torch.empty(N, device=dev, dtype=torch.int64)
         pool = torch.cuda.graph_pool_handle()
-        self.g = [torch.cuda.CUDAGraph() for _ in range(4)]
+        self.g = [torch.cuda.CUDAGraph() for _ in range(5)]
         kw = dict(pool=pool, capture_error_mode="thread_local")
+        model._split_backward = True
         try:
             with torch.no_grad():
                 with torch.cuda.graph(self.g[0], **kw):
                     emb, saved = model._engine_forward(_prep_input(self.views, model.in_channels), True)
-                    self.emb = emb.contiguous()
-                d = self.emb.shape[1]
-                self.F = torch.empty(N, d, device=dev, dtype=torch.float32)
+                    self.packed = backend.pack(emb.contiguous(), self.labels)
+                d = emb.shape[1]
+                self.packed_all = torch.empty(N, d + 2, device=dev, dtype=torch.float32)
                 self.stats_all = torch.empty(N, 4, device=dev, dtype=torch.float32)
                 with torch.cuda.graph(self.g[1], **kw):
-                    stats, row_loss = backend.rows_forward(self.F, self.y, T, Tb, row0, n)
+                    F, y = backend.unpack(self.packed_all, d)
+                    stats, _ = backend.rows_forward(F, y, T, Tb, row0, n)
                     self.stats = stats.contiguous()
-                    self.total.copy_(row_loss.sum(dtype=torch.float32).reshape(1) / N)
                 with torch.cuda.graph(self.g[2], **kw):
-                    dF = backend.rows_backward(self.F, self.y, T, (T / Tb) / N, ones, self.stats_all, row0, n)
-                    model._engine_backward(saved, dF.contiguous(), grads)
+                    self.total = backend.loss_from_stats(self.stats_all, T, Tb)
+                    dF = backend.rows_backward(F, y, T, (T / Tb) / N, ones, self.stats_all, row0, n)
+                    gen = model._engine_backward_gen(saved, dF.contiguous(), grads)
+                    next(gen)                                    # head + last block: the bucket tail is complete
                 with torch.cuda.graph(self.g[3], **kw):
+                    for _ in gen:
+                        pass
+                with torch.cuda.graph(self.g[4], **kw):
                     opt.step(max_grad_norm=clip, flat_grad=self.flat)
-                self._saved = saved
+                self._saved = (saved, F, y)
                 # the gradients stay visible the usual way: every .grad is a view of the static bucket
                 for p in params:
                     if p.requires_grad:
                         p.grad = grads[p]
         finally:
+            model._split_backward = False
             # warm-up steps and the host-side counters touched during capture must be invisible to the optimisation trajectory
             with torch.no_grad():
                 opt.flat_p.copy_(snap_opt[0]); opt.flat_m.copy_(snap_opt[1]); opt.flat_v.copy_(snap_opt[2])
@@ -169,13 +180,15 @@ class GraphedDPStep:
         self.labels.copy_(labels, non_blocking=True)
         self.trainer.optimizer.sync_lr()
         self.g[0].replay()
-        dist.all_gather_into_tensor(self.F, self.emb, group=grp)                    # C1
-        dist.all_gather_into_tensor(self.y, self.labels, group=grp)
+        dist.all_gather_into_tensor(self.packed_all, self.packed, group=grp)        # C1  embeddings + labels
         self.g[1].replay()
-        dist.all_gather_into_tensor(self.stats_all, self.stats, group=grp)          # C1'
-        dist.all_reduce(self.total, op=dist.ReduceOp.SUM, group=grp)
+        dist.all_gather_into_tensor(self.stats_all, self.stats, group=grp)          # C1' row statistics
         self.g[2].replay()
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=grp)                 # C2
+        w_tail = dist.all_reduce(self.flat[self.split:], op=dist.ReduceOp.SUM, group=grp, async_op=True)    # C2a under g3
         self.g[3].replay()
+        w_head = dist.all_reduce(self.flat[:self.split], op=dist.ReduceOp.SUM, group=grp, async_op=True)    # C2b
+        w_tail.wait()
+        w_head.wait()
+        self.g[4].replay()
         self.trainer.optimizer.note_replayed_steps(1)
         return self.total.reshape(()).clone()

@@ -233,3 +233,25 @@ def test_dataset_pad_or_trim_matches_reference_golden(golden):
     assert val.n_views == 1
     for i in range(4):
         assert np.array_equal(val._load_waveform(i).numpy(), g[f"ds_val_fixed_{i}"])
+
+
+def test_exchange_packing_round_trip_cpu():
+    """Host restatement of csrc/dp.cu's packing (tests/exchange_torch.py, used by the gloo tests): int64 labels survive the
+    trip through two fp32 columns bit for bit, including negative and > 2^31 values; loss_from_stats equals the mean row loss."""
+    import torch
+
+    from oracle import supcon_oracle
+    from tests.exchange_torch import TorchExchangeMixin as X
+    emb = torch.randn(7, 12)
+    lab = torch.tensor([0, 1, -5, 2 ** 31 + 3, 2 ** 40 + 17, -2 ** 62, 37], dtype=torch.int64)
+    F, y = X.unpack(X.pack(emb, lab), 12)
+    assert torch.equal(F, emb) and torch.equal(y, lab)
+    rs = np.random.RandomState(3)
+    f = rs.standard_normal((24, 16))
+    f /= np.linalg.norm(f, axis=1, keepdims=True)
+    yy = rs.randint(0, 4, 24)
+    st = supcon_oracle.row_stats(f, yy, temperature=0.15)
+    stats = torch.from_numpy(np.stack([st["m"], st["den"], st["npos"], st["spos"]], 1))
+    got = float(X.loss_from_stats(stats, 0.15, 0.07))
+    want = supcon_oracle.loss(f, yy, temperature=0.15)
+    assert abs(got - want) <= 1e-9 * abs(want)

@@ -109,3 +109,96 @@ def test_dp_two_gpus_match_single_process(tmp_path):
         assert float((p_e - p_g).abs().max()) <= 2 * 1e-3 * 2
         assert (s_e, d_e, s_g, d_g) == (2, 2, 2, 2)
     assert torch.equal(outs[0]["graph_vs_eager"][1][1], outs[1]["graph_vs_eager"][1][1])
+
+
+# ------------------------------------------------------------------------------------------------ DP step vs R oracle replicas
+def _dp_inputs(world, per_rank=16, hw=(40, 50)):
+    rs = np.random.RandomState(21)
+    xs = [rs.standard_normal((per_rank, 1) + hw).astype(np.float32) for _ in range(world)]
+    ys = [np.repeat(np.arange(per_rank // 2) % 5 + 3 * r, 2).astype(np.int64) for r in range(world)]     # classes overlap across ranks
+    return xs, ys
+
+
+def _replica_worker(rank, world, port, out, arch):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import logging
+        import tempfile
+
+        from oracle import nets_oracle
+        from phoneme_contrast_b200.models import model_registry
+        from phoneme_contrast_b200.parallel import DataParallelContext
+        from phoneme_contrast_b200.training import ContrastiveTrainer, FusedClipAdam, get_loss_fn
+        ctx = DataParallelContext()
+        dev = f"cuda:{rank}"
+        cfg = {"dropout_rate": 0.0} if arch == "phoneme_cnn" else {"dropout_rate": 0.0, "hidden_dims": [64, 64, 128, 128]}
+        xs, ys = _dp_inputs(world)
+        x, y = torch.from_numpy(xs[rank]).to(dev), torch.from_numpy(ys[rank]).to(dev)
+        res = {}
+        for graph in (False, True):
+            m = model_registry.create(arch, cfg).to(dev)
+            m.load_state_dict(nets_oracle.synthetic_state_dict(arch, cfg, seed=6))
+            opt = FusedClipAdam(m.parameters(), lr=3e-4, weight_decay=1e-4)
+            tr = ContrastiveTrainer(m, [], None, get_loss_fn("supervised_contrastive", temperature=0.15), opt, None, torch.device(dev),
+                                    {"gradient_clip_val": 1.0, "progress": False, "cuda_graph": graph}, tempfile.mkdtemp(), logging.getLogger("t"), parallel=ctx)
+            m.train()
+            loss = float(tr.step(x, y))
+            assert (not graph) or tr._graphed, "graphed data-parallel step fell back to eager"
+            names = [n for n, _ in m.named_parameters()]
+            res["graph" if graph else "eager"] = dict(loss=loss, grads={n: p.grad.detach().cpu() for n, p in m.named_parameters()},
+                                                      params={n: p.detach().cpu() for n, p in m.named_parameters()}, names=names,
+                                                      rm=m.state_dict()["projection.1.running_mean"].cpu())
+        torch.save(res, os.path.join(out, f"rep{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("arch", ["phoneme_cnn", "phoneme_cnn_deep"])
+def test_dp_training_step_matches_oracle_replicas(tmp_path, arch):
+    """BASELINE configs[4] semantics at a small size (mode (ii)): R ranks with per-rank BatchNorm statistics ==
+    R oracle replicas sharing one parameter set whose embeddings are concatenated for ONE global SupCon loss; the all-reduced
+    gradient equals the gradient of that loss w.r.t. the shared parameters, and clip + Adam on it gives the ranks' new parameters.
+    Eager exchange path and the graphed five-segment step (3 collectives, split-bucket overlap) are both checked."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import nets_oracle, optim_oracle, supcon_oracle
+    from tests.helpers import analytically_zero_grad
+    world, port = 2, _free_port()
+    mp.spawn(_replica_worker, args=(world, port, str(tmp_path), arch), nprocs=world, join=True)
+    cfg = {"dropout_rate": 0.0} if arch == "phoneme_cnn" else {"dropout_rate": 0.0, "hidden_dims": [64, 64, 128, 128]}
+    sd = nets_oracle.synthetic_state_dict(arch, cfg, seed=6)
+    xs, ys = _dp_inputs(world)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+    embs = []
+    for r in range(world):                                   # replica r: its own BatchNorm batch statistics, shared parameters
+        live = {k: v.clone() for k, v in sd.items()}
+        live.update(params)
+        embs.append(nets_oracle.forward(arch, live, torch.from_numpy(xs[r]), training=True))
+    loss = supcon_oracle.loss_torch_cpu(torch.cat(embs), torch.from_numpy(np.concatenate(ys)), temperature=0.15)
+    loss.backward()
+    outs = [torch.load(os.path.join(tmp_path, f"rep{r}.pt")) for r in range(world)]
+    names = outs[0]["eager"]["names"]
+    gref = [params[n].grad.numpy() for n in names]
+    pn = [sd[n].numpy().copy() for n in names]
+    optim_oracle.adam_step(pn, gref, [np.zeros_like(p) for p in pn], [np.zeros_like(p) for p in pn], 1, lr=3e-4, weight_decay=1e-4, max_norm=1.0)
+    for mode in ("eager", "graph"):
+        for r in range(world):
+            o = outs[r][mode]
+            assert abs(o["loss"] - float(loss)) <= 1e-4 * abs(float(loss)), (mode, r, o["loss"], float(loss))
+            for n, g, pnew in zip(names, gref, pn):
+                if analytically_zero_grad(n):
+                    continue
+                got = o["grads"][n].numpy()
+                l2 = np.linalg.norm((got - g).astype(np.float64)) / max(np.linalg.norm(g.astype(np.float64)), 1e-12)
+                assert l2 <= 3e-3, (mode, r, n, l2)
+                # Adam's first step is lr * sign(g) (|m| / sqrt(v) = 1): elements whose gradient is at round-off level may take
+                # either sign, so the update vectors are compared where the reference gradient is not negligible
+                du, dr = o["params"][n].numpy() - sd[n].numpy(), pnew - sd[n].numpy()
+                sel = np.abs(g) > 0.05 * np.sqrt(np.mean(g.astype(np.float64) ** 2))
+                assert np.linalg.norm((du - dr)[sel]) <= 0.02 * np.linalg.norm(dr[sel]) + 1e-9, (mode, r, n)
+        for n in names:                                      # every rank holds the same parameters after the step
+            assert torch.equal(outs[0][mode]["params"][n], outs[1][mode]["params"][n]), (mode, n)
+        assert not torch.equal(outs[0][mode]["rm"], outs[1][mode]["rm"])     # per-rank BatchNorm statistics, as stated

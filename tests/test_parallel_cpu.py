@@ -11,7 +11,10 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
-class OracleRowsBackend:
+from tests.exchange_torch import TorchExchangeMixin
+
+
+class OracleRowsBackend(TorchExchangeMixin):
     @staticmethod
     def rows_forward(F, y, temperature, base_temperature, row0, nrows):
         from oracle import supcon_oracle
