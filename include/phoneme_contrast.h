@@ -235,6 +235,21 @@ int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* g, const Pc
                   float* db, void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, int dy_presplit,
                   pc_stream_t stream);
 
+/* Stem backward without the full-resolution tensors (csrc/stem_bwd.cu; reference init_conv, src/models/phoneme_cnn.py:211-216):
+ * for Conv2d(1, 64, 7, pad 3) -> BatchNorm2d -> ReLU -> MaxPool2d(3, 2, 1) the gradient from the pool is non-zero only at each
+ * window's argmax pixel, where the BatchNorm output equals the pooled output; the dense BatchNorm-projection terms of the weight
+ * gradient are closed forms in the 49 x 49 Gram matrix G and the tap sums X1 of the input patches (y0 is linear in them). So
+ * dw, db (= 0 exactly), dgamma, dbeta follow from dpool / p0 / argmax at POOLED resolution plus x; the pre-BatchNorm tensor
+ * is never read. pc_stem_gram accumulates G [49*49] and X1 [49] (fp64; zero them first) from x [B][H][W]; pc_stem_bwd needs
+ * zeroed `sums` [2][64] fp64 and `amax_slot` (float) and a workspace of pc_stem_bwd_workspace() bytes. */
+int pc_stem_bwd_supported(int k, int Cout, int H, int W);
+int pc_stem_gram(const float* x, int B, int H, int W, double* G, double* X1, pc_stream_t stream);
+size_t pc_stem_bwd_workspace(void);
+int pc_stem_bwd(const float* dpool, const float* p0, const uint8_t* argmax, const float* x, int B, int H, int W,
+                const float* w_oihw, const float* bias, const float* gamma, const float* scale, const float* shift,
+                const float* mean, const float* invstd, const double* G, const double* X1, double* sums, float* amax_slot,
+                void* workspace, size_t workspace_bytes, float* dw, float* db, float* dgamma, float* dbeta, pc_stream_t stream);
+
 /* BatchNorm statistics -> per-channel coefficients.
  * training: mean/var from stats (count = elements per channel), running stats updated with `momentum`
  * (unbiased variance) exactly like nn.BatchNorm2d; eval: coefficients from the running stats.

@@ -268,7 +268,7 @@ def _small_backward(net, s, demb, grads, training=True):
     wgrad.join()
 
 
-def _deep_forward(net, x, training):
+def _deep_forward(net, x, training, for_backward=True):
     s = _Saved()
     packer = _packer_begin(net, x, training)
     prec = net._prec
@@ -282,6 +282,17 @@ def _deep_forward(net, x, training):
 
     g0 = ops.conv_geom(B, H, W, 1, hd[0], 7, 1, 3)
     st0 = st(hd[0])
+    # stem backward at pooled resolution (csrc/stem_bwd.cu): its data-only part -- the Gram matrix of the input patches -- is
+    # independent of everything else in the step, so it runs on the weight-gradient stream under the forward
+    gram = None
+    if (training and for_backward and os.environ.get("PC_STEM_BWD", "1") == "1" and net.use_residual
+            and L.lib().pc_stem_bwd_supported(7, hd[0], H, W)):
+        if getattr(net, "_side_stream", None) is None:
+            net._side_stream = torch.cuda.Stream()
+        main = torch.cuda.current_stream()
+        net._side_stream.wait_stream(main)
+        with torch.cuda.stream(net._side_stream):
+            gram = ops.stem_gram(x)
     y0 = ops.conv_fwd(x, conv0.weight, conv0.bias, g0, None, st0, prec)
     co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
     # On the FP16X2 engine every block input is also kept as fp16 hi | lo planes (written by the kernel that produces it), so
@@ -291,7 +302,7 @@ def _deep_forward(net, x, training):
         p0, argmax0, cur_ps = ops.bn_act_fwd(y0, co0, 3, None, want_planes=True)
     else:
         (p0, argmax0), cur_ps = ops.bn_act_fwd(y0, co0, 3, None), None
-    s.stem = dict(g=g0, y=y0, co=co0, argmax=argmax0)
+    s.stem = dict(g=g0, y=y0 if gram is None else None, co=co0, argmax=argmax0, gram=gram, p0=p0)
     s.blocks = []
     cur, cin = p0, hd[0]
     h, w = p0.shape[1], p0.shape[2]
@@ -352,6 +363,8 @@ def _deep_forward(net, x, training):
         s.blocks.append(rec)
         cur, cin, h, w = out, co, g1.Ho, g1.Wo
     s.a_last = cur
+    if gram is not None:
+        torch.cuda.current_stream().wait_stream(net._side_stream)     # join (a captured forward segment must end joined)
     emb = _head(net, s, cur, training)
     packer.end()
     return emb, s
@@ -415,6 +428,12 @@ def _deep_backward(net, s, demb, grads, training=True):
             yield
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
     st = s.stem
+    if st.get("gram") is not None:
+        # pooled-resolution stem backward: dW, dgamma, dbeta from dout / p0 / argmax + the Gram matrix; y0 is never read
+        ops.stem_bwd(dout, st["p0"], st["argmax"], s.x, conv0, st["co"], st["gram"], grads[conv0.weight], grads[conv0.bias],
+                     grads[bn0.weight], grads[bn0.bias], zp)
+        wgrad.join()
+        return
     # the stem's dy is O(1/N) per pixel (the loss is a mean): without the max|dy| operand scale it would sit in fp16 subnormals
     m0 = amax.take()
     dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias], m0, zp=zp)
@@ -496,7 +515,7 @@ class _FusedNet(BaseModel):
         if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in params):
             return _NetFunction.apply(self, x, *params)
         with torch.no_grad():
-            emb, _ = self._engine_forward(x, self.training)
+            emb, _ = self._engine_forward(x, self.training, for_backward=False)
         return emb
 
 
@@ -526,7 +545,7 @@ class PhonemeNet(_FusedNet):
         self.projection = nn.Sequential(nn.Linear(128, self.embedding_dim), nn.BatchNorm1d(self.embedding_dim))
         self._finish_init()
 
-    def _engine_forward(self, x, training):
+    def _engine_forward(self, x, training, for_backward=True):
         return _small_forward(self, x, training)
 
     def _engine_backward_gen(self, saved, demb, grads):
@@ -570,8 +589,8 @@ class PhonemeNetDeep(_FusedNet):
         self.projection = nn.Sequential(nn.Linear(hd[-1], self.embedding_dim), nn.BatchNorm1d(self.embedding_dim))
         self._finish_init()
 
-    def _engine_forward(self, x, training):
-        return _deep_forward(self, x, training)
+    def _engine_forward(self, x, training, for_backward=True):
+        return _deep_forward(self, x, training, for_backward)
 
     def _engine_backward_gen(self, saved, demb, grads):
         return _deep_backward(self, saved, demb, grads)

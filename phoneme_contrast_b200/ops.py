@@ -270,7 +270,7 @@ def _zeros(zp, shape, dtype, device):
 
 class BnCoeffs:
     """scale/shift/mean/invstd of one BatchNorm for the current batch (or from running stats in eval)."""
-    __slots__ = ("scale", "shift", "mean", "invstd", "C")
+    __slots__ = ("scale", "shift", "mean", "invstd", "C", "gamma")
 
     def __init__(self, C_, device):
         buf = torch.empty(4, C_, device=device, dtype=F32)
@@ -281,6 +281,7 @@ class BnCoeffs:
 def bn_finalize(stats, count, bn: torch.nn.modules.batchnorm._BatchNorm, training: bool) -> BnCoeffs:
     C_ = bn.num_features
     co = BnCoeffs(C_, bn.weight.device)
+    co.gamma = bn.weight
     momentum = 0.1 if bn.momentum is None else bn.momentum
     call("pc_bn_finalize", ptr(stats, torch.float64), C_, float(count), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
          ptr(bn.running_var), ptr(bn.num_batches_tracked, torch.int64), momentum, bn.eps, 1 if training else 0,
@@ -328,6 +329,26 @@ def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=Non
     call("pc_bn_act_bwd_apply", *args, ptr(sums, torch.float64), ptr(dy), ptr(dgamma), ptr(dbeta), ptr(amax), ptr(maxes),
          ptr(dy_ps, torch.uint8), stream())
     return (dy_ps if planes else dy), dgamma, dbeta
+
+
+def stem_gram(x):
+    """G [49,49] and X1 [49] (fp64) of the 7x7 patches of x [B,1,H,W]: the data-only part of the stem's weight gradient."""
+    B, _, H, W = x.shape
+    buf = torch.zeros(49 * 49 + 49, device=x.device, dtype=torch.float64)
+    call("pc_stem_gram", ptr(x), B, H, W, ptr(buf, torch.float64), buf[49 * 49:].data_ptr(), stream())
+    return buf
+
+
+def stem_bwd(dpool, p0, argmax, x, conv, co: BnCoeffs, gram, dw, db, dgamma, dbeta, zp=None):
+    """Backward of Conv(1,64,7) -> BN -> ReLU -> MaxPool(3,2,1) from the pooled-resolution tensors (csrc/stem_bwd.cu)."""
+    B, _, H, W = x.shape
+    sums = _zeros(zp, (2, 64), torch.float64, x.device)
+    amax = _zeros(zp, (1,), F32, x.device)
+    nbytes = int(L.lib().pc_stem_bwd_workspace())
+    ws = _workspace(nbytes, x.device, "stem")
+    call("pc_stem_bwd", ptr(dpool), ptr(p0), ptr(argmax, torch.uint8), ptr(x), B, H, W, ptr(conv.weight), ptr(conv.bias), ptr(co.gamma),
+         ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd), ptr(gram, torch.float64), gram[49 * 49:].data_ptr(),
+         ptr(sums, torch.float64), ptr(amax), ptr(ws, torch.uint8), ws.numel(), ptr(dw), ptr(db), ptr(dgamma), ptr(dbeta), stream())
 
 
 def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, want_planes=False):

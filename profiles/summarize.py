@@ -16,7 +16,10 @@ FULL_METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_w
                 "launch__block_size", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
                 "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
                 "sm__inst_executed_pipe_tensor.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-                "smsp__cycles_active.avg", "sm__cycles_elapsed.max"]
+                "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+                "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__m_xbar2l1tex_read_bytes.sum",
+                "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+                "sm__inst_executed.avg.per_cycle_elapsed", "smsp__inst_executed.sum"]
 
 
 def launches(path, out, title):

@@ -383,3 +383,42 @@ def test_device_resident_batch_views_vs_reference_golden(golden):
         v, y = tr._prepare_batch(batch)
         assert v.shape == (4, 1, 40, 51) and v.is_cuda and y.shape == (4,)
         assert np.isfinite(float(tr.step(v, y)))
+
+
+# ============================================================================================= pooled-resolution stem backward
+def test_stem_gram_matches_im2col():
+    """G = X^T X and X1 = X^T 1 of the 7x7 'same' patches (csrc/stem_bwd.cu: lag correlations + exact border handling) against
+    an explicit im2col in fp64."""
+    from phoneme_contrast_b200 import ops
+    for (B, H, W) in ((3, 40, 101), (2, 9, 11), (5, 40, 51)):
+        x = torch.randn(B, 1, H, W, device=DEV, generator=torch.Generator(device=DEV).manual_seed(B + H))
+        buf = ops.stem_gram(x).cpu().numpy()
+        G, X1 = buf[:49 * 49].reshape(49, 49), buf[49 * 49:]
+        cols = torch.nn.functional.unfold(x.double().cpu(), kernel_size=7, padding=3)      # [B, 49, H*W]
+        X = cols.permute(0, 2, 1).reshape(-1, 49).numpy()
+        Gref, X1ref = X.T @ X, X.sum(0)
+        assert np.abs(G - Gref).max() <= 2e-6 * np.abs(Gref).max(), np.abs(G - Gref).max() / np.abs(Gref).max()
+        assert np.abs(X1 - X1ref).max() <= 1e-5 * max(np.abs(X1ref).max(), 1.0)
+
+
+@pytest.mark.parametrize("B,shape", [(8, (40, 101)), (6, (40, 64)), (64, (40, 101))])
+def test_stem_backward_pooled_vs_full_resolution_and_oracle(B, shape, monkeypatch):
+    """init_conv gradients (conv weight, BatchNorm weight / bias) from the pooled-resolution closed form == the round-1 path that
+    streams the pre-BatchNorm tensor three times, and both match the oracle."""
+    from tests.test_gpu_parity import _oracle_net, _run_net
+    arch, cfg = "phoneme_cnn_deep", {"dropout_rate": 0.0}
+    sd = nets_oracle.synthetic_state_dict(arch, cfg, seed=13)
+    rs = np.random.RandomState(B)
+    x = rs.standard_normal((B, 1) + shape).astype(np.float32)
+    y = (np.arange(B) // 2).astype(np.int64)
+    monkeypatch.setenv("PC_STEM_BWD", "0")
+    _, emb0, loss0, g0 = _run_net(arch, cfg, sd, x, y)
+    monkeypatch.setenv("PC_STEM_BWD", "1")
+    _, emb1, loss1, g1 = _run_net(arch, cfg, sd, x, y)
+    assert abs(loss0 - loss1) <= 1e-6 * abs(loss0)
+    _, _, gref, _ = _oracle_net(arch, cfg, sd, x, y)
+    for name in ("init_conv.0.weight", "init_conv.1.weight", "init_conv.1.bias"):
+        a, b, r = g1[name].astype(np.float64), g0[name].astype(np.float64), gref[name].astype(np.float64)
+        assert np.linalg.norm(a - b) <= 1e-3 * np.linalg.norm(b), (name, "vs full-resolution path", np.linalg.norm(a - b) / np.linalg.norm(b))
+        assert np.linalg.norm(a - r) <= GRAD_RTOL * np.linalg.norm(r), (name, "vs oracle", np.linalg.norm(a - r) / np.linalg.norm(r))
+    assert np.abs(g1["init_conv.0.bias"]).max() == 0.0          # analytically zero, written as such
