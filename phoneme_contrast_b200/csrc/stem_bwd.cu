@@ -36,24 +36,17 @@ constexpr int CO = 64;                                     // output channels (t
 // where xz is x zero-extended and I(r') = [max(0, r'-3), min(H-1, H-4+r')] (the rows some output pixel reads through tap row
 // r'), J likewise. With f(i, j; d) = x[i][j] xz[i + dr][j + ds] summed over the WHOLE image (C0), over the first / last three
 // rows (R), columns (C) and their 6 x 6 corner blocks (X), inclusion-exclusion gives every G[t'][t] from 49 numbers per lag.
-struct GramAcc {
-  float c0, rows[6], cols[6], corner[36];
-};
-
-__global__ void __launch_bounds__(192) stem_gram_kernel(const float* __restrict__ x, int B, int H, int W, double* __restrict__ G,
+// Thread roles: 13 row lags x 4 groups of 4 column lags x 4 row partitions (208 of 256 threads) for C0 / R -- each thread slides a
+// 4-wide register window along the lagged row, i.e. 2 shared-memory loads per 4 multiply-adds; then one thread per (lag, boundary
+// column) for C / X. The per-lag table [49] lives in shared memory and accumulates over the CTA's samples.
+__global__ void __launch_bounds__(256) stem_gram_kernel(const float* __restrict__ x, int B, int H, int W, double* __restrict__ G,
                                                         double* __restrict__ X1) {
   extern __shared__ float sm[];
-  const int Wz = W + 12, Hz = H + 12;
-  float* xz = sm;                                  // [(H+12)][(W+12)] zero-extended image
-  float* tab = xz + Hz * Wz;                       // [NLAG][49] per-lag accumulators of this CTA (summed over its samples)
+  const int Wz = W + 16, Hz = H + 12;              // 6 zero rows above / below, 6 zero columns left, 10 right (the 4-wide window over-reads)
+  float* xz = sm;                                  // [(H+12)][(W+16)] zero-extended image
+  float* tab = xz + Hz * Wz;                       // [NLAG][49]: c0 | rows[6] | cols[6] | corner[6][6]
   const int tid = threadIdx.x;
-  const int lag = tid;                             // threads 0..168 own one lag (dr, ds) in [-6, 6]^2
-  const int dr = lag / LAG - 6, ds = lag % LAG - 6;
-  GramAcc acc;
-  acc.c0 = 0.f;
-  for (int k = 0; k < 6; ++k) acc.rows[k] = acc.cols[k] = 0.f;
-  for (int k = 0; k < 36; ++k) acc.corner[k] = 0.f;
-  // per-thread partial sums for X1: thread t < 49 accumulates sum over I(r) x J(s) of x
+  for (int i = tid; i < NLAG * 49; i += blockDim.x) tab[i] = 0.f;
   float x1 = 0.f;
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     __syncthreads();
@@ -62,41 +55,49 @@ __global__ void __launch_bounds__(192) stem_gram_kernel(const float* __restrict_
       xz[i] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? x[((size_t)b * H + hh) * W + ww] : 0.f;
     }
     __syncthreads();
-    if (lag < NLAG) {
-      // whole image: C0 and the six boundary columns (static register indices: the loops below are fully unrolled in k)
-      for (int i = 0; i < H; ++i) {
+    if (tid < 208) {
+      const int part = tid & 3, g = (tid >> 2) & 3, dri = tid >> 4;       // row partition, column-lag group, row lag index
+      const int dr = dri - 6, ds0 = 4 * g - 6;
+      float c0[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = part; i < H; i += 4) {
         const float* a = xz + (i + 6) * Wz + 6;
-        const float* bb = xz + (i + 6 + dr) * Wz + 6 + ds;
-        float rs = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < W; ++j) rs = fmaf(a[j], bb[j], rs);
-        acc.c0 += rs;
+        const float* bb = xz + (i + 6 + dr) * Wz + 6 + ds0;
+        float w0 = bb[0], w1 = bb[1], w2 = bb[2];
+        float rs[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < W; ++j) {
+          const float av = a[j], w3 = bb[j + 3];
+          rs[0] = fmaf(av, w0, rs[0]); rs[1] = fmaf(av, w1, rs[1]); rs[2] = fmaf(av, w2, rs[2]); rs[3] = fmaf(av, w3, rs[3]);
+          w0 = w1; w1 = w2; w2 = w3;
+        }
+        const int slot = i < 3 ? i : (i >= H - 3 ? i - (H - 6) : -1);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          acc.cols[k] = fmaf(a[k], bb[k], acc.cols[k]);
-          acc.cols[3 + k] = fmaf(a[W - 3 + k], bb[W - 3 + k], acc.cols[3 + k]);
+        for (int k = 0; k < 4; ++k) {
+          c0[k] += rs[k];
+          if (slot >= 0 && ds0 + k <= 6) atomicAdd(&tab[(dri * LAG + ds0 + k + 6) * 49 + 1 + slot], rs[k]);
         }
       }
-      // the six boundary rows once more: their row sums and the 6 x 6 corner products
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ds0 + k <= 6) atomicAdd(&tab[(dri * LAG + ds0 + k + 6) * 49], c0[k]);
+    }
+    // boundary columns and corners: one thread per (lag, boundary-column slot)
+    for (int task = tid; task < NLAG * 6; task += blockDim.x) {
+      const int lag = task / 6, cs = task - lag * 6;
+      const int dr = lag / LAG - 6, ds = lag % LAG - 6;
+      const int jc = cs < 3 ? cs : W - 6 + cs;
+      float col = 0.f;
+      for (int i = 0; i < H; ++i) col = fmaf(xz[(i + 6) * Wz + 6 + jc], xz[(i + 6 + dr) * Wz + 6 + jc + ds], col);
+      float* t = tab + lag * 49;
+      t[7 + cs] += col;
 #pragma unroll
       for (int rsl = 0; rsl < 6; ++rsl) {
         const int i = rsl < 3 ? rsl : H - 6 + rsl;
-        const float* a = xz + (i + 6) * Wz + 6;
-        const float* bb = xz + (i + 6 + dr) * Wz + 6 + ds;
-        float rs = 0.f;
-#pragma unroll 4
-        for (int j = 0; j < W; ++j) rs = fmaf(a[j], bb[j], rs);
-        acc.rows[rsl] += rs;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          acc.corner[rsl * 6 + k] = fmaf(a[k], bb[k], acc.corner[rsl * 6 + k]);
-          acc.corner[rsl * 6 + 3 + k] = fmaf(a[W - 3 + k], bb[W - 3 + k], acc.corner[rsl * 6 + 3 + k]);
-        }
+        t[13 + rsl * 6 + cs] += xz[(i + 6) * Wz + 6 + jc] * xz[(i + 6 + dr) * Wz + 6 + jc + ds];
       }
     }
     if (tid < NT) {
-      const int r = tid / KS, s = tid % KS;
-      const int i0 = max(0, r - 3), i1 = min(H - 1, H - 4 + r), j0 = max(0, s - 3), j1 = min(W - 1, W - 4 + s);
+      const int r = tid / KS, s2 = tid % KS;
+      const int i0 = max(0, r - 3), i1 = min(H - 1, H - 4 + r), j0 = max(0, s2 - 3), j1 = min(W - 1, W - 4 + s2);
       float t = 0.f;
       for (int i = i0; i <= i1; ++i)
         for (int j = j0; j <= j1; ++j) t += xz[(i + 6) * Wz + 6 + j];
@@ -104,18 +105,11 @@ __global__ void __launch_bounds__(192) stem_gram_kernel(const float* __restrict_
     }
   }
   __syncthreads();
-  if (lag < NLAG) {
-    float* t = tab + lag * 49;
-    t[0] = acc.c0;
-    for (int k = 0; k < 6; ++k) { t[1 + k] = acc.rows[k]; t[7 + k] = acc.cols[k]; }
-    for (int k = 0; k < 36; ++k) t[13 + k] = acc.corner[k];
-  }
-  __syncthreads();
   // assemble G[t'][t] for this CTA's samples and add it to the global fp64 matrix
   for (int pair = tid; pair < NT * NT; pair += blockDim.x) {
     const int tp = pair / NT, t = pair % NT;
-    const int rp = tp / KS, sp = tp % KS, r = t / KS, s = t % KS;
-    const float* e = tab + ((r - rp + 6) * LAG + (s - sp + 6)) * 49;
+    const int rp = tp / KS, sp = tp % KS, r = t / KS, s2 = t % KS;
+    const float* e = tab + ((r - rp + 6) * LAG + (s2 - sp + 6)) * 49;
     // excluded rows: r' < 3 -> the last 3 - r' rows (slots 3 + r' .. 5); r' > 3 -> the first r' - 3 rows (slots 0 .. r' - 4)
     const int ra = rp < 3 ? 3 + rp : 0, rb = rp < 3 ? 6 : (rp > 3 ? rp - 3 : 0);
     const int ca = sp < 3 ? 3 + sp : 0, cb = sp < 3 ? 6 : (sp > 3 ? sp - 3 : 0);
@@ -141,7 +135,10 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
 }
 
 // ------------------------------------------------------------------------------------------------ T1 on tensor cores
-constexpr int QPB = 14;                    // pooled pixels per 128-row K block: row = ql * 9 + window position a (126 rows + 2 zero)
+constexpr int QPB = 14;                    // pooled pixels per 128-row K block: row = ql * 9 + window position a (126 rows + 2 zero);
+                                           // a block's pixels lie in ONE pooled row (pw = 14 seg + ql), so all its input patches fall
+                                           // inside a 9 x 36 window of the image that is staged in shared memory once per block
+constexpr int RG_H = 9, RG_W = 36, RG_LD = 37;
 constexpr int ROWS = 128;
 constexpr uint32_t PART = ROWS * 128;      // one 64-wide group of one operand part: [128 rows][128 B], SWIZZLE_128B (MN-major)
 constexpr uint32_t STAGE = 4 * PART;       // A_hi | A_lo | B_hi | B_lo
@@ -160,8 +157,9 @@ struct PoolParams {
   double* sums;              // [2][64]: sum dz, sum dz * xhat
   int B, H, W, Hp, Wp;
   long long n_pooled;        // B * Hp * Wp
-  int n_blocks;              // ceil(n_pooled / QPB)
-  FastDiv d_wp, d_hp;
+  int n_seg;                 // K blocks per pooled row: ceil(Wp / QPB)
+  int n_blocks;              // B * Hp * n_seg
+  FastDiv d_seg, d_hp;
 };
 
 __device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo_bytes) {
@@ -185,6 +183,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
   uint64_t* acc_full = empty + NSTAGE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   float* s_red = reinterpret_cast<float*>(tmem_slot + 2);                // [2][64]
+  float* s_reg = s_red + 128;                                            // [NGROUPS][RG_H * RG_LD] staged image windows
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < (int)(PART / 16); i += THREADS) reinterpret_cast<uint4*>(zeros)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -230,76 +229,89 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
     const float muv[8] = {mu0.x, mu0.y, mu0.z, mu0.w, mu1.x, mu1.y, mu1.z, mu1.w};
     const float isv[8] = {is0.x, is0.y, is0.z, is0.w, is1.x, is1.y, is1.z, is1.w};
     float rs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int tap_dh[8], tap_dw[8];
+    int tap_off[8];                    // offset of tap 8 j + q inside the staged window, -1 for the padding taps 49..63
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const int t = 8 * j + q;
-      tap_dh[q] = t < NT ? t / KS - 3 : -100000;
-      tap_dw[q] = t % KS - 3;
+      tap_off[q] = t < NT ? (t / KS) * RG_LD + (t % KS) : -1;
+    }
+    float* reg = s_reg + group * (RG_H * RG_LD);
+    int row_base[8];                   // window offset of the conv pixel of my 8 rows (row = pr + 16 i = ql' * 9 + a')
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = pr + 16 * i;
+      const int rq_ = row / 9, ra = row - rq_ * 9;
+      row_base[i] = (ra / 3) * RG_LD + 2 * min(rq_, QPB - 1) + ra % 3;
     }
     for (int it = group; it < n_my; it += NGROUPS) {
       const int s = it % NSTAGE;
       const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
-      const long long q_first = (long long)(blk0 + it) * QPB;
+      uint32_t bph, seg, b, php;
+      p.d_seg.divmod((uint32_t)(blk0 + it), bph, seg);
+      p.d_hp.divmod(bph, b, php);
+      const int pw0 = (int)seg * QPB;
+      const int n_valid = min(QPB, p.Wp - pw0);
+      // ---------------- stage the image window rows 2 ph - 4 .. 2 ph + 4, columns 2 pw0 - 4 .. 2 pw0 + 31 (zero outside the image)
+      {
+        const float* img = p.x + (size_t)b * p.H * p.W;
+        const int h0 = 2 * (int)php - 4, w0 = 2 * pw0 - 4;
+        float rv[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int e = gt + 128 * k;
+          const int rr = e / RG_W, cc = e - rr * RG_W;
+          const int hi = h0 + rr, wi = w0 + cc;
+          rv[k] = (e < RG_H * RG_W && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W) ? img[hi * p.W + wi] : 0.f;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");      // the previous block's patch reads are done
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int e = gt + 128 * k;
+          const int rr = e / RG_W, cc = e - rr * RG_W;
+          if (e < RG_H * RG_W) reg[rr * RG_LD + cc] = rv[k];
+        }
+      }
       // ---------------- S unit: loads first (latency), stores after the slot is free
       uint4 hh = make_uint4(0u, 0u, 0u, 0u), ll = hh;
       uint2 am = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-      if (gt < 112) {
-        const long long qg = q_first + ql;
-        if (qg < p.n_pooled) {
-          const size_t o = (size_t)qg * CO + 8 * cj;
-          const float4 d0 = *reinterpret_cast<const float4*>(p.dpool + o), d1 = *reinterpret_cast<const float4*>(p.dpool + o + 4);
-          const float4 a0 = *reinterpret_cast<const float4*>(p.p0 + o), a1 = *reinterpret_cast<const float4*>(p.p0 + o + 4);
-          am = *reinterpret_cast<const uint2*>(p.argmax + o);
-          const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-          const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          float dz[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            dz[q] = a[q] > 0.f ? d[q] : 0.f;                                   // ReLU gate: pooled output > 0
-            // xhat at the argmax pixel from the pooled value: bn(y) = p0  =>  xhat = ((p0 - shift) / scale - mean) * invstd
-            const float xh = scv[q] != 0.f ? (__fdividef(a[q] - shv[q], scv[q]) - muv[q]) * isv[q] : 0.f;
-            rs[q] += dz[q];
-            rq[q] = fmaf(dz[q], xh, rq[q]);
-            dz[q] *= g_scale;
-          }
-          split_f16x2(dz[0], dz[1], hh.x, ll.x); split_f16x2(dz[2], dz[3], hh.y, ll.y);
-          split_f16x2(dz[4], dz[5], hh.z, ll.z); split_f16x2(dz[6], dz[7], hh.w, ll.w);
-        }
-      }
-      // ---------------- patch chunks: values of the input under taps 8 j .. 8 j + 7 of the conv pixel of row (ql', a')
-      float tv[8][8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = pr + 16 * i;
-        const int rq_ = row / 9, ra = row - rq_ * 9;
-        const long long qg = q_first + rq_;
-        const bool okq = rq_ < QPB && qg < p.n_pooled;
-        uint32_t b = 0, php = 0, pwp = 0, t_ = 0;
-        if (okq) {
-          p.d_wp.divmod((uint32_t)qg, t_, pwp);
-          p.d_hp.divmod(t_, b, php);
-        }
-        const int hc = 2 * (int)php - 1 + ra / 3, wc = 2 * (int)pwp - 1 + ra % 3;
-        const float* img = p.x + (size_t)b * p.H * p.W;
+      if (gt < 112 && ql < n_valid) {
+        const size_t o = (((size_t)b * p.Hp + php) * p.Wp + pw0 + ql) * CO + 8 * cj;
+        const float4 d0 = *reinterpret_cast<const float4*>(p.dpool + o), d1 = *reinterpret_cast<const float4*>(p.dpool + o + 4);
+        const float4 a0 = *reinterpret_cast<const float4*>(p.p0 + o), a1 = *reinterpret_cast<const float4*>(p.p0 + o + 4);
+        am = *reinterpret_cast<const uint2*>(p.argmax + o);
+        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        float dz[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const int hi = hc + tap_dh[q], wi = wc + tap_dw[q];
-          const bool ok = okq && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W;
-          tv[i][q] = ok ? img[hi * p.W + wi] : 0.f;
+          dz[q] = a[q] > 0.f ? d[q] : 0.f;                                   // ReLU gate: pooled output > 0
+          // xhat at the argmax pixel from the pooled value: bn(y) = p0  =>  xhat = ((p0 - shift) / scale - mean) * invstd
+          const float xh = scv[q] != 0.f ? (__fdividef(a[q] - shv[q], scv[q]) - muv[q]) * isv[q] : 0.f;
+          rs[q] += dz[q];
+          rq[q] = fmaf(dz[q], xh, rq[q]);
+          dz[q] *= g_scale;
         }
+        split_f16x2(dz[0], dz[1], hh.x, ll.x); split_f16x2(dz[2], dz[3], hh.y, ll.y);
+        split_f16x2(dz[4], dz[5], hh.z, ll.z); split_f16x2(dz[6], dz[7], hh.w, ll.w);
       }
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");        // staged window visible to the group
       mbar_wait(&empty[s], ph ^ 1u);
       unsigned char* a_hi = tiles + (size_t)s * STAGE;
       unsigned char* a_lo = a_hi + PART;
       unsigned char* b_hi = a_hi + 2 * PART;
       unsigned char* b_lo = a_hi + 3 * PART;
+      // ---------------- patch chunks: row (ql', a') = taps 8 j .. 8 j + 7 of the conv pixel (2 ph - 1 + a'/3, 2 (pw0 + ql') - 1 + a'%3),
+      // i.e. window element [a'/3 + tr][2 ql' + a'%3 + ts]
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = pr + 16 * i;
+        const float* base = reg + row_base[i];
+        float tv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) tv[q] = tap_off[q] >= 0 ? base[tap_off[q]] : 0.f;
         uint4 h, l;
-        split_f16x2(tv[i][0], tv[i][1], h.x, l.x); split_f16x2(tv[i][2], tv[i][3], h.y, l.y);
-        split_f16x2(tv[i][4], tv[i][5], h.z, l.z); split_f16x2(tv[i][6], tv[i][7], h.w, l.w);
+        split_f16x2(tv[0], tv[1], h.x, l.x); split_f16x2(tv[2], tv[3], h.y, l.y);
+        split_f16x2(tv[4], tv[5], h.z, l.z); split_f16x2(tv[6], tv[7], h.w, l.w);
         const uint32_t off = mn_off(row, j);
         *reinterpret_cast<uint4*>(a_hi + off) = h;
         *reinterpret_cast<uint4*>(a_lo + off) = l;
@@ -439,21 +451,21 @@ using namespace pc;
 using namespace pc::stemb;
 
 extern "C" int pc_stem_bwd_supported(int k, int Cout, int H, int W) {
-  return (k == 7 && Cout == 64 && H >= 7 && W >= 7 && (size_t)(H + 12) * (W + 12) * 4 + NLAG * 49 * 4 <= 200 * 1024) ? 1 : 0;
+  return (k == 7 && Cout == 64 && H >= 7 && W >= 7 && (size_t)(H + 12) * (W + 16) * 4 + NLAG * 49 * 4 <= 200 * 1024) ? 1 : 0;
 }
 
 // G [49*49] and X1 [49] (fp64, ACCUMULATED into: the caller zeroes them) of the stem's input patches, x [B][H][W].
 extern "C" int pc_stem_gram(const float* x, int B, int H, int W, double* G, double* X1, pc_stream_t stream) {
   PC_REQUIRE(x && G && X1 && B > 0, PC_EINVAL, "pc_stem_gram: bad arguments");
   PC_REQUIRE(pc_stem_bwd_supported(7, 64, H, W), PC_EUNSUPPORTED, "pc_stem_gram: image %dx%d not covered", H, W);
-  const size_t smem = ((size_t)(H + 12) * (W + 12) + NLAG * 49) * sizeof(float);
+  const size_t smem = ((size_t)(H + 12) * (W + 16) + NLAG * 49) * sizeof(float);
   static size_t conf = 0;
   if (smem > conf) {
     PC_CUDA(cudaFuncSetAttribute(stem_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     conf = smem;
   }
   const int grid = B < 2 * kNumSMs ? B : 2 * kNumSMs;
-  stem_gram_kernel<<<grid, 192, smem, stream>>>(x, B, H, W, G, X1);
+  stem_gram_kernel<<<grid, 256, smem, stream>>>(x, B, H, W, G, X1);
   PC_LAUNCH_CHECK("stem_gram_kernel");
   return PC_OK;
 }
@@ -484,9 +496,10 @@ extern "C" int pc_stem_bwd(const float* dpool, const float* p0, const uint8_t* a
   p.dpool = dpool; p.p0 = p0; p.argmax = argmax; p.x = x; p.scale = scale; p.shift = shift; p.mean = mean; p.invstd = invstd;
   p.amax = amax_slot; p.t1_partial = static_cast<float*>(workspace); p.sums = sums;
   p.B = B; p.H = H; p.W = W; p.Hp = Hp; p.Wp = Wp; p.n_pooled = n_pooled;
-  p.n_blocks = ceil_div(n_pooled, QPB);
-  p.d_wp = FastDiv::make((uint32_t)Wp); p.d_hp = FastDiv::make((uint32_t)Hp);
-  const size_t smem = (size_t)NSTAGE * STAGE + PART + sizeof(uint64_t) * (2 * NSTAGE + 1) + 16 + 128 * sizeof(float) + 1024;
+  p.n_seg = ceil_div(Wp, QPB);
+  p.n_blocks = B * Hp * p.n_seg;
+  p.d_seg = FastDiv::make((uint32_t)p.n_seg); p.d_hp = FastDiv::make((uint32_t)Hp);
+  const size_t smem = (size_t)NSTAGE * STAGE + PART + sizeof(uint64_t) * (2 * NSTAGE + 1) + 16 + (128 + NGROUPS * RG_H * RG_LD) * sizeof(float) + 1024;
   static bool conf = false;
   if (!conf) {
     PC_CUDA(cudaFuncSetAttribute(stem_bwd_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

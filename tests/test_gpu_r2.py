@@ -415,10 +415,10 @@ def test_stem_backward_pooled_vs_full_resolution_and_oracle(B, shape, monkeypatc
     _, emb0, loss0, g0 = _run_net(arch, cfg, sd, x, y)
     monkeypatch.setenv("PC_STEM_BWD", "1")
     _, emb1, loss1, g1 = _run_net(arch, cfg, sd, x, y)
-    assert abs(loss0 - loss1) <= 1e-6 * abs(loss0)
+    assert abs(loss0 - loss1) <= 1e-5 * abs(loss0)      # two runs differ in the last bits of the atomically accumulated BatchNorm statistics
     _, _, gref, _ = _oracle_net(arch, cfg, sd, x, y)
     for name in ("init_conv.0.weight", "init_conv.1.weight", "init_conv.1.bias"):
         a, b, r = g1[name].astype(np.float64), g0[name].astype(np.float64), gref[name].astype(np.float64)
-        assert np.linalg.norm(a - b) <= 1e-3 * np.linalg.norm(b), (name, "vs full-resolution path", np.linalg.norm(a - b) / np.linalg.norm(b))
+        assert np.linalg.norm(a - b) <= GRAD_RTOL * np.linalg.norm(b), (name, "vs full-resolution path", np.linalg.norm(a - b) / np.linalg.norm(b))
         assert np.linalg.norm(a - r) <= GRAD_RTOL * np.linalg.norm(r), (name, "vs oracle", np.linalg.norm(a - r) / np.linalg.norm(r))
     assert np.abs(g1["init_conv.0.bias"]).max() == 0.0          # analytically zero, written as such
