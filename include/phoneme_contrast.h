@@ -250,6 +250,17 @@ int pc_stem_bwd(const float* dpool, const float* p0, const uint8_t* argmax, cons
                 const float* mean, const float* invstd, const double* G, const double* X1, double* sums, float* amax_slot,
                 void* workspace, size_t workspace_bytes, float* dw, float* db, float* dgamma, float* dbeta, pc_stream_t stream);
 
+/* Stem forward in ONE pass (csrc/stem_fwd.cu): the batch statistics of y0 = conv7x7(x) + b are closed forms in the Gram matrix /
+ * tap sums of the input patches (pc_stem_gram), so BatchNorm's coefficients are known before the convolution runs and the kernel
+ * -- tcgen05 implicit GEMM over 128-pixel row tiles, operand tiles built in shared memory from a staged input window -- applies
+ * BatchNorm + ReLU + MaxPool2d(3, 2, 1) in its epilogue and stores only the pooled tensor (+ argmax, + optional fp16 hi | lo
+ * planes). pc_stem_stats_from_gram: stats [2][64] fp64 = (sum y0, sum y0^2), the input of pc_bn_finalize. */
+int pc_stem_fwd_supported(int k, int Cout, int H, int W);
+int pc_stem_stats_from_gram(const double* G, const double* X1, const float* w_oihw, const float* bias, int B, int H, int W,
+                            double* stats, pc_stream_t stream);
+int pc_stem_fwd(const float* x, const float* w_oihw, const float* bias, const float* scale, const float* shift, int B, int H, int W,
+                float* p0, uint8_t* argmax, void* planes, pc_stream_t stream);
+
 /* BatchNorm statistics -> per-channel coefficients.
  * training: mean/var from stats (count = elements per channel), running stats updated with `momentum`
  * (unbiased variance) exactly like nn.BatchNorm2d; eval: coefficients from the running stats.

@@ -81,6 +81,9 @@ SIGNATURES = {
     "pc_conv_dgrad_halo": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, i32, vp, vp]),
     "pc_conv_wgrad_workspace": (sz, [C.POINTER(PcConvGeom)]),
     "pc_conv_wgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, vp, sz, i32, vp, i32, vp]),
+    "pc_stem_fwd_supported": (i32, [i32, i32, i32, i32]),
+    "pc_stem_stats_from_gram": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
+    "pc_stem_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "pc_stem_bwd_supported": (i32, [i32, i32, i32, i32]),
     "pc_stem_gram": (i32, [vp, i32, i32, i32, vp, vp, vp]),
     "pc_stem_bwd_workspace": (sz, []),

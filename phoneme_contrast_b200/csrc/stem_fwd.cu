@@ -1,0 +1,339 @@
+// Forward of the cnn_deep stem as ONE pass: Conv2d(1, 64, 7, pad 3) -> BatchNorm2d -> ReLU -> MaxPool2d(3, 2, 1)
+// (reference src/models/phoneme_cnn.py:211-216) on tcgen05, writing only the pooled output.
+//
+// Round 1 wrote the 265 MB pre-BatchNorm tensor y0 with a SIMT convolution (0.26 ms), then read it again to normalise and pool
+// (0.14 ms) -- a two-pass structure forced by BatchNorm needing the batch statistics of y0 before it can be applied. For THIS
+// layer the statistics do not need y0: y0 = W x_patch + b is linear in the 49-tap input patches, so
+//     sum_p y0[p,o]   = sum_t W[o,t] X1[t] + M b_o
+//     sum_p y0[p,o]^2 = sum_{t,t'} W[o,t] W[o,t'] G[t,t'] + 2 b_o sum_t W[o,t] X1[t] + M b_o^2
+// with G / X1 the Gram matrix / tap sums of the patches (csrc/stem_bwd.cu computes them from lag correlations of the input; the
+// backward needs them anyway). pc_stem_stats_from_gram evaluates these closed forms in fp64; BatchNorm's scale / shift are then
+// known BEFORE the convolution runs and the whole stem becomes a single kernel whose epilogue normalises, rectifies and pools:
+//   work item  = one pooled row (b, ph): conv rows 2ph-1, 2ph, 2ph+1 (those inside the image), one 128-pixel MMA tile each;
+//   producers  = 2 groups x 4 warps: stage the 9 x (W+6) input window of the item in shared memory, build the K-major
+//                [128 pixels][64 taps] fp16 hi / lo operand tiles of its rows (taps 49..63 zero);
+//   MMA        = a_hi x [w_hi ; w_lo] (N = 128: main | corr) + a_lo x w_hi per 16-tap k-step, weights resident in smem,
+//                accumulators in a ring of four 128-column TMEM slots;
+//   epilogue   = 4 warps: TMEM -> + bias -> scale / shift -> ReLU -> shared act[row][channel][w]; then every pooled pixel takes
+//                the first maximum of its 3x3 window in scan order (PyTorch's tie rule) and the pooled value, its window
+//                position (argmax, for the backward) and, optionally, the fp16 hi | lo planes for block 0 are stored.
+// y0 is never materialised: 265 MB less to write, read twice and keep.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace pc {
+namespace stemf {
+
+using namespace pc::tc;
+
+constexpr int KS = 7, NT = 49, CO = 64;
+constexpr int NSTAGE = 3, NSLOT = 4;
+constexpr int NGROUPS = 2, NPROD = 128, PROD_WARPS = 4 * NGROUPS, EPI_WARPS = 4;
+constexpr int THREADS = 32 * (PROD_WARPS + 1 + EPI_WARPS);
+constexpr uint32_t A_PART = 128 * 128;          // [128 pixels][128 B]
+constexpr uint32_t STAGE = 2 * A_PART;          // hi | lo
+constexpr uint32_t B_BYTES = 2 * CO * 128;      // [w_hi rows ; w_lo rows]
+
+struct Params {
+  const float* x; const float* w; const float* bias; const float* scale; const float* shift;
+  float* p0; uint8_t* argmax; unsigned char* planes;
+  int B, H, W, Hp, Wp, WLD, RG_LD;
+  int n_items;                 // B * Hp
+  FastDiv d_hp;
+  size_t plane_elems;
+};
+
+__device__ __forceinline__ int tiles_of(int ph, int H) {        // conv rows 2ph-1 .. 2ph+1 inside [0, H)
+  int n = 0;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) n += (unsigned)(2 * ph - 1 + kh) < (unsigned)H ? 1 : 0;
+  return n;
+}
+
+__global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  unsigned char* stages = smem;                                              // [NSTAGE][STAGE]
+  unsigned char* b_tile = smem + (size_t)NSTAGE * STAGE;                     // [2 * 64 rows][128 B]
+  float* act = reinterpret_cast<float*>(b_tile + B_BYTES);                   // [3][64][WLD]
+  float* win = act + 3 * CO * p.WLD;                                         // [NGROUPS][9 * RG_LD]
+  uint64_t* full = reinterpret_cast<uint64_t*>(win + NGROUPS * 9 * p.RG_LD + 4);
+  uint64_t* empty = full + NSTAGE;
+  uint64_t* acc_full = empty + NSTAGE;        // [NSLOT]
+  uint64_t* acc_empty = acc_full + NSLOT;     // [NSLOT]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NSLOT);
+  float* s_co = reinterpret_cast<float*>(tmem_slot + 2);                     // [3][64] bias | scale | shift
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // weights -> K-major SWIZZLE_128B fp16 hi / lo rows (row o, 16-byte chunk j = taps 8j .. 8j+7; taps >= 49 are zero)
+  for (int i = tid; i < CO * 8; i += THREADS) {
+    const int o = i >> 3, j = i & 7;
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = 8 * j + q;
+      v[q] = t < NT ? p.w[o * NT + t] : 0.f;
+    }
+    uint4 h, l;
+    split_f16x2(v[0], v[1], h.x, l.x); split_f16x2(v[2], v[3], h.y, l.y);
+    split_f16x2(v[4], v[5], h.z, l.z); split_f16x2(v[6], v[7], h.w, l.w);
+    *reinterpret_cast<uint4*>(b_tile + sw128_offset((uint32_t)o, (uint32_t)j)) = h;
+    *reinterpret_cast<uint4*>(b_tile + CO * 128 + sw128_offset((uint32_t)o, (uint32_t)j)) = l;
+  }
+  for (int i = tid; i < CO; i += THREADS) {
+    s_co[i] = p.bias != nullptr ? p.bias[i] : 0.f;
+    s_co[CO + i] = p.scale[i];
+    s_co[2 * CO + i] = p.shift[i];
+  }
+  if (warp == PROD_WARPS) {
+    if (lane == 0) {
+      for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], 1); }
+      for (int s = 0; s < NSLOT; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], EPI_WARPS); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int per = (p.n_items + gridDim.x - 1) / gridDim.x;
+  const int it0 = blockIdx.x * per, it1 = min(p.n_items, it0 + per);
+
+  if (warp < PROD_WARPS) {
+    // ================================================================================= producers
+    const int group = warp >> 2, gt = tid & (NPROD - 1);
+    const int j = gt & 7, pr = gt >> 3;
+    float* wbuf = win + group * 9 * p.RG_LD;
+    int tap_off[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int t = 8 * j + q;
+      tap_off[q] = t < NT ? (t / KS) * p.RG_LD + (t % KS) : -1;
+    }
+    int tile_idx = 0;       // global tile counter of this CTA at the start of the current item
+    for (int it = it0; it < it1; ++it) {
+      uint32_t b, ph;
+      p.d_hp.divmod((uint32_t)it, b, ph);
+      const int nt = tiles_of((int)ph, p.H);
+      if (((it - it0) & (NGROUPS - 1)) == group) {
+        // ---- window: input rows 2ph-4 .. 2ph+4, columns -3 .. W+2 (zero outside)
+        const float* img = p.x + (size_t)b * p.H * p.W;
+        const int h0 = 2 * (int)ph - 4;
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");
+        for (int e = gt; e < 9 * (p.W + 6); e += NPROD) {
+          const int rr = e / (p.W + 6), cc = e - rr * (p.W + 6);
+          const int hi = h0 + rr, wi = cc - 3;
+          wbuf[rr * p.RG_LD + cc] = ((unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W) ? img[hi * p.W + wi] : 0.f;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");
+        int k = 0;
+#pragma unroll 1
+        for (int kh = 0; kh < 3; ++kh) {
+          const int h = 2 * (int)ph - 1 + kh;
+          if ((unsigned)h >= (unsigned)p.H) continue;
+          const int t_glob = tile_idx + k;
+          ++k;
+          const int s = t_glob % NSTAGE;
+          const uint32_t phs = (uint32_t)(t_glob / NSTAGE) & 1u;
+          // conv pixel (h, w): tap (tr, ts) reads input (h + tr - 3, w + ts - 3) = window[(kh + tr)][w + ts]
+          uint4 hh[8], ll[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int w = pr + 16 * i;
+            const float* base = wbuf + kh * p.RG_LD + min(w, p.W - 1);
+            float tv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tv[q] = (tap_off[q] >= 0 && w < p.W) ? base[tap_off[q]] : 0.f;
+            split_f16x2(tv[0], tv[1], hh[i].x, ll[i].x); split_f16x2(tv[2], tv[3], hh[i].y, ll[i].y);
+            split_f16x2(tv[4], tv[5], hh[i].z, ll[i].z); split_f16x2(tv[6], tv[7], hh[i].w, ll[i].w);
+          }
+          // Two producer groups share one stage ring, so a group may reach use n of a stage while use n-1 (the other group's) has
+          // not even been filled; a parity wait on `empty` alone would then alias to an older phase. Waiting first for use n-1 to
+          // be FILLED pins the phase: by then `empty` has completed exactly the phases 0 .. n-2.
+          if (t_glob >= NSTAGE) mbar_wait(&full[s], (uint32_t)(t_glob / NSTAGE - 1) & 1u);
+          mbar_wait(&empty[s], phs ^ 1u);
+          unsigned char* a_hi = stages + (size_t)s * STAGE;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t off = sw128_offset((uint32_t)(pr + 16 * i), (uint32_t)j);
+            *reinterpret_cast<uint4*>(a_hi + off) = hh[i];
+            *reinterpret_cast<uint4*>(a_hi + A_PART + off) = ll[i];
+          }
+          fence_proxy_async();
+          mbar_arrive(&full[s]);
+        }
+      }
+      tile_idx += nt;
+    }
+  } else if (warp == PROD_WARPS) {
+    // ================================================================================= MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(0u, 128, CO), idesc2 = instr_desc(0u, 128, 2 * CO);
+      const uint64_t b_hi = smem_desc_sw128(smem_u32(b_tile));
+      int t_glob = 0;
+      for (int it = it0; it < it1; ++it) {
+        uint32_t b, ph;
+        p.d_hp.divmod((uint32_t)it, b, ph);
+        const int nt = tiles_of((int)ph, p.H);
+        for (int k = 0; k < nt; ++k, ++t_glob) {
+          const int s = t_glob % NSTAGE, slot = t_glob % NSLOT;
+          mbar_wait(&acc_empty[slot], ((uint32_t)(t_glob / NSLOT) & 1u) ^ 1u);
+          mbar_wait(&full[s], (uint32_t)(t_glob / NSTAGE) & 1u);
+          tc_fence_after();
+          const uint32_t base = smem_u32(stages + (size_t)s * STAGE);
+          const uint64_t a_hi = smem_desc_sw128(base), a_lo = smem_desc_sw128(base + A_PART);
+          const uint32_t d = tmem_base + (uint32_t)slot * 128u;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            mma_bf16(d, a_hi + (uint64_t)(kk * 2), b_hi + (uint64_t)(kk * 2), idesc2, kk > 0 ? 1u : 0u);
+            mma_bf16(d + CO, a_lo + (uint64_t)(kk * 2), b_hi + (uint64_t)(kk * 2), idesc, 1u);
+          }
+          mma_commit(&empty[s]);
+          mma_commit(&acc_full[slot]);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================================= epilogue: normalise, rectify, pool
+    const int ew = warp - PROD_WARPS - 1;                 // 0..3 = TMEM lane quarter (warp % 4 must equal the quarter)
+    const int quarter = warp & 3;
+    const int et = (warp - PROD_WARPS - 1) * 32 + lane;   // 0..127
+    (void)ew;
+    const int wpix = quarter * 32 + lane;                 // conv pixel (column) of my TMEM lane
+    int t_glob = 0;
+    for (int it = it0; it < it1; ++it) {
+      uint32_t b, ph;
+      p.d_hp.divmod((uint32_t)it, b, ph);
+      // ---- part 1: the item's conv rows from TMEM into act[kh][c][w] (BatchNorm + ReLU applied)
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");      // previous item's pooling no longer reads act
+#pragma unroll 1
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h = 2 * (int)ph - 1 + kh;
+        if ((unsigned)h >= (unsigned)p.H) continue;
+        const int slot = t_glob % NSLOT;
+        mbar_wait(&acc_full[slot], (uint32_t)(t_glob / NSLOT) & 1u);
+        tc_fence_after();
+        ++t_glob;
+        const uint32_t t_row = tmem_base + (uint32_t)slot * 128u + ((uint32_t)(quarter * 32) << 16);
+        float* arow = act + (size_t)kh * CO * p.WLD + wpix;
+#pragma unroll 1
+        for (int c0 = 0; c0 < CO; c0 += 32) {
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(t_row + (uint32_t)c0, r0);
+          tmem_ld_32x32(t_row + (uint32_t)(c0 + CO), r1);
+          tmem_ld_wait();
+          if (wpix < p.W) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) {
+              const float y = fmaf(__uint_as_float(r1[k]), kF16LoInv, __uint_as_float(r0[k])) + s_co[c0 + k];
+              arow[(size_t)(c0 + k) * p.WLD] = fmaxf(fmaf(y, s_co[CO + c0 + k], s_co[2 * CO + c0 + k]), 0.f);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[slot]);
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");      // act complete
+      // ---- part 2: pooled row ph. thread = channel pair; 2 threads groups of 64 channels alternate over pw
+      const int c = et & 63, pw_par = et >> 6;
+      for (int pw = pw_par; pw < p.Wp; pw += 2) {
+        float best = -INFINITY;
+        int arg = 0;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int h = 2 * (int)ph - 1 + kh;
+          if ((unsigned)h >= (unsigned)p.H) continue;
+          const float* ar = act + ((size_t)kh * CO + c) * p.WLD;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int w = 2 * pw - 1 + kw;
+            if ((unsigned)w >= (unsigned)p.W) continue;
+            const float a = ar[w];
+            if (a > best) { best = a; arg = kh * 3 + kw; }
+          }
+        }
+        const size_t o = (((size_t)b * p.Hp + ph) * p.Wp + pw) * CO + c;
+        p.p0[o] = best;
+        if (p.argmax != nullptr) p.argmax[o] = (uint8_t)arg;
+        if (p.planes != nullptr) {
+          const __half hi = __float2half_rn(best);
+          const __half lo = __float2half_rn((best - __half2float(hi)) * kF16LoScale);
+          reinterpret_cast<__half*>(p.planes)[o] = hi;
+          reinterpret_cast<__half*>(p.planes)[p.plane_elems + o] = lo;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == PROD_WARPS) tmem_dealloc(tmem_base, 512);
+}
+
+// stats[0][o] = sum_p y0, stats[1][o] = sum_p y0^2 from the Gram matrix / tap sums of the input patches (fp64)
+__global__ void __launch_bounds__(64) stem_stats_kernel(const double* __restrict__ G, const double* __restrict__ X1, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, double M, double* __restrict__ stats) {
+  const int o = threadIdx.x;
+  if (o >= CO) return;
+  const double b = bias != nullptr ? (double)bias[o] : 0.0;
+  double wx = 0.0, wgw = 0.0;
+  for (int t = 0; t < NT; ++t) {
+    const double wt = (double)w[o * NT + t];
+    wx += wt * X1[t];
+    double r = 0.0;
+    for (int u = 0; u < NT; ++u) r += G[t * NT + u] * (double)w[o * NT + u];
+    wgw += wt * r;
+  }
+  stats[o] = wx + M * b;
+  stats[CO + o] = wgw + 2.0 * b * wx + M * b * b;
+}
+
+}  // namespace stemf
+}  // namespace pc
+
+using namespace pc;
+using namespace pc::stemf;
+
+extern "C" int pc_stem_fwd_supported(int k, int Cout, int H, int W) { return (k == 7 && Cout == 64 && H >= 3 && W >= 7 && W <= 128) ? 1 : 0; }
+
+extern "C" int pc_stem_stats_from_gram(const double* G, const double* X1, const float* w_oihw, const float* bias, int B, int H, int W,
+                                       double* stats, pc_stream_t stream) {
+  PC_REQUIRE(G && X1 && w_oihw && stats, PC_EINVAL, "pc_stem_stats_from_gram: null pointer");
+  stem_stats_kernel<<<1, 64, 0, stream>>>(G, X1, w_oihw, bias, (double)B * H * W, stats);
+  PC_LAUNCH_CHECK("stem_stats_kernel");
+  return PC_OK;
+}
+
+// x [B][H][W] -> p0 [B][Hp][Wp][64] = maxpool3x3s2p1(relu(scale * (conv7x7(x) + bias) + shift)); argmax (may be NULL) receives the
+// window position kh*3+kw of each maximum; planes (may be NULL) the fp16 hi | lo planes of p0 (pc_bn_act_split layout).
+extern "C" int pc_stem_fwd(const float* x, const float* w_oihw, const float* bias, const float* scale, const float* shift, int B, int H,
+                           int W, float* p0, uint8_t* argmax, void* planes, pc_stream_t stream) {
+  PC_REQUIRE(x && w_oihw && scale && shift && p0 && B > 0, PC_EINVAL, "pc_stem_fwd: bad arguments");
+  PC_REQUIRE(pc_stem_fwd_supported(7, 64, H, W), PC_EUNSUPPORTED, "pc_stem_fwd: image %dx%d not covered (one 128-pixel tile per row)", H, W);
+  Params p{};
+  p.x = x; p.w = w_oihw; p.bias = bias; p.scale = scale; p.shift = shift; p.p0 = p0; p.argmax = argmax;
+  p.planes = static_cast<unsigned char*>(planes);
+  p.B = B; p.H = H; p.W = W; p.Hp = (H + 2 - 3) / 2 + 1; p.Wp = (W + 2 - 3) / 2 + 1;
+  p.WLD = (W + 4) | 1;
+  p.RG_LD = (W + 6) | 1;
+  p.n_items = B * p.Hp;
+  p.d_hp = FastDiv::make((uint32_t)p.Hp);
+  p.plane_elems = (size_t)B * p.Hp * p.Wp * CO;
+  const size_t smem = (size_t)NSTAGE * STAGE + B_BYTES + sizeof(float) * (3 * (size_t)CO * p.WLD + NGROUPS * 9 * (size_t)p.RG_LD + 4) +
+                      sizeof(uint64_t) * (2 * NSTAGE + 2 * NSLOT + 1) + 16 + sizeof(float) * 3 * CO + 1024;
+  PC_REQUIRE(smem <= 227 * 1024, PC_EUNSUPPORTED, "pc_stem_fwd: row width %d needs %zu B of shared memory", W, smem);
+  static size_t conf = 0;
+  if (smem > conf) {
+    PC_CUDA(cudaFuncSetAttribute(stem_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conf = smem;
+  }
+  const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
+  stem_fwd_kernel<<<grid, THREADS, smem, stream>>>(p);
+  PC_LAUNCH_CHECK("stem_fwd_kernel");
+  return PC_OK;
+}

@@ -282,27 +282,43 @@ def _deep_forward(net, x, training, for_backward=True):
 
     g0 = ops.conv_geom(B, H, W, 1, hd[0], 7, 1, 3)
     st0 = st(hd[0])
-    # stem backward at pooled resolution (csrc/stem_bwd.cu): its data-only part -- the Gram matrix of the input patches -- is
-    # independent of everything else in the step, so it runs on the weight-gradient stream under the forward
-    gram = None
-    if (training and for_backward and os.environ.get("PC_STEM_BWD", "1") == "1" and net.use_residual
-            and L.lib().pc_stem_bwd_supported(7, hd[0], H, W)):
-        if getattr(net, "_side_stream", None) is None:
-            net._side_stream = torch.cuda.Stream()
-        main = torch.cuda.current_stream()
-        net._side_stream.wait_stream(main)
-        with torch.cuda.stream(net._side_stream):
-            gram = ops.stem_gram(x)
-    y0 = ops.conv_fwd(x, conv0.weight, conv0.bias, g0, None, st0, prec)
-    co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
     # On the FP16X2 engine every block input is also kept as fp16 hi | lo planes (written by the kernel that produces it), so
     # that conv1 / the shortcut conv and their weight gradients gather bytes instead of splitting fp32 per tap
     ps = prec == L.PREC_FP16X2 and all(c % 64 == 0 for c in hd) and net.use_residual
-    if ps:
-        p0, argmax0, cur_ps = ops.bn_act_fwd(y0, co0, 3, None, want_planes=True)
+    lib = L.lib()
+    pooled_bwd = os.environ.get("PC_STEM_BWD", "1") == "1" and bool(lib.pc_stem_bwd_supported(7, hd[0], H, W))
+    fused_fwd = (prec != L.PREC_FP32 and os.environ.get("PC_STEM_FWD", "1") == "1" and lib.pc_stem_fwd_supported(7, hd[0], H, W)
+                 and (not training or pooled_bwd))          # without y0 the backward must be the pooled-resolution one
+    want_gram = training and (fused_fwd or (for_backward and pooled_bwd))
+    gram = None
+    y0 = None
+    if fused_fwd:
+        # One-pass stem (csrc/stem_fwd.cu): the batch statistics of y0 are closed forms in the Gram matrix of the input patches,
+        # so BatchNorm is known before the convolution runs and the kernel pools in its epilogue; y0 is never materialised
+        if training:
+            gram = ops.stem_gram(x)
+            ops.stem_stats_from_gram(gram, conv0, B, H, W, st0)
+        co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
+        p0, argmax0, cur_ps = ops.stem_fwd(x, conv0, co0, want_planes=ps)
     else:
-        (p0, argmax0), cur_ps = ops.bn_act_fwd(y0, co0, 3, None), None
-    s.stem = dict(g=g0, y=y0 if gram is None else None, co=co0, argmax=argmax0, gram=gram, p0=p0)
+        if want_gram:
+            # stem backward at pooled resolution (csrc/stem_bwd.cu): its data-only part -- the Gram matrix of the input patches --
+            # is independent of everything else in the step, so it runs on the weight-gradient stream under the forward
+            if getattr(net, "_side_stream", None) is None:
+                net._side_stream = torch.cuda.Stream()
+            main = torch.cuda.current_stream()
+            net._side_stream.wait_stream(main)
+            with torch.cuda.stream(net._side_stream):
+                gram = ops.stem_gram(x)
+        y0 = ops.conv_fwd(x, conv0.weight, conv0.bias, g0, None, st0, prec)
+        co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
+        if ps:
+            p0, argmax0, cur_ps = ops.bn_act_fwd(y0, co0, 3, None, want_planes=True)
+        else:
+            (p0, argmax0), cur_ps = ops.bn_act_fwd(y0, co0, 3, None), None
+    gram_bwd = gram if (for_backward and pooled_bwd) else None
+    side_gram = gram is not None and not fused_fwd
+    s.stem = dict(g=g0, y=y0 if gram_bwd is None else None, co=co0, argmax=argmax0, gram=gram_bwd, p0=p0)
     s.blocks = []
     cur, cin = p0, hd[0]
     h, w = p0.shape[1], p0.shape[2]
@@ -363,7 +379,7 @@ def _deep_forward(net, x, training, for_backward=True):
         s.blocks.append(rec)
         cur, cin, h, w = out, co, g1.Ho, g1.Wo
     s.a_last = cur
-    if gram is not None:
+    if side_gram:
         torch.cuda.current_stream().wait_stream(net._side_stream)     # join (a captured forward segment must end joined)
     emb = _head(net, s, cur, training)
     packer.end()

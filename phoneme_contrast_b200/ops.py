@@ -339,6 +339,25 @@ def stem_gram(x):
     return buf
 
 
+def stem_stats_from_gram(gram, conv, B, H, W, stats):
+    """stats [2,64] fp64 = (sum y0, sum y0^2) of y0 = conv(x) + b from the Gram matrix / tap sums of x's patches (closed form)."""
+    call("pc_stem_stats_from_gram", ptr(gram, torch.float64), gram[49 * 49:].data_ptr(), ptr(conv.weight), ptr(conv.bias), B, H, W,
+         ptr(stats, torch.float64), stream())
+
+
+def stem_fwd(x, conv, co: BnCoeffs, want_planes=False):
+    """maxpool3x3s2p1(relu(bn(conv7x7(x)))) in one kernel -> (p0 [B,Hp,Wp,64], argmax uint8, planes or None)."""
+    B, _, H, W = x.shape
+    Hp, Wp = pool_dims(H, W, 3)
+    p0 = torch.empty(B, Hp, Wp, 64, device=x.device, dtype=F32)
+    argmax = torch.empty(B, Hp, Wp, 64, device=x.device, dtype=torch.uint8)
+    planes = torch.empty(2, p0.numel() * 2, device=x.device, dtype=torch.uint8) if want_planes else None
+    L.note_work("pc_stem_fwd", 2.0 * B * H * W * 64 * 49)
+    call("pc_stem_fwd", ptr(x), ptr(conv.weight), ptr(conv.bias), ptr(co.scale), ptr(co.shift), B, H, W, ptr(p0), ptr(argmax, torch.uint8),
+         ptr(planes, torch.uint8), stream())
+    return p0, argmax, planes
+
+
 def stem_bwd(dpool, p0, argmax, x, conv, co: BnCoeffs, gram, dw, db, dgamma, dbeta, zp=None):
     """Backward of Conv(1,64,7) -> BN -> ReLU -> MaxPool(3,2,1) from the pooled-resolution tensors (csrc/stem_bwd.cu)."""
     B, _, H, W = x.shape

@@ -422,3 +422,52 @@ def test_stem_backward_pooled_vs_full_resolution_and_oracle(B, shape, monkeypatc
         assert np.linalg.norm(a - b) <= GRAD_RTOL * np.linalg.norm(b), (name, "vs full-resolution path", np.linalg.norm(a - b) / np.linalg.norm(b))
         assert np.linalg.norm(a - r) <= GRAD_RTOL * np.linalg.norm(r), (name, "vs oracle", np.linalg.norm(a - r) / np.linalg.norm(r))
     assert np.abs(g1["init_conv.0.bias"]).max() == 0.0          # analytically zero, written as such
+
+
+@pytest.mark.parametrize("B,shape,training", [(4, (40, 101), True), (3, (40, 64), True), (2, (9, 17), True), (5, (40, 101), False), (40, (40, 101), True)])
+def test_stem_forward_one_pass_vs_two_pass(B, shape, training, monkeypatch):
+    """Fused stem (statistics from the Gram matrix, conv + BatchNorm + ReLU + max-pool in one tcgen05 kernel, no y0) == the
+    two-pass path (SIMT conv + statistics, then normalise + pool): pooled output to 1e-5 of its max, argmax positions identical
+    except at ties within rounding, planes consistent, running statistics equal."""
+    from phoneme_contrast_b200 import _lib as L
+    from phoneme_contrast_b200 import ops
+    H, W = shape
+    gen = torch.Generator(device=DEV).manual_seed(B + W)
+    x = torch.randn(B, 1, H, W, device=DEV, generator=gen)
+    outs = []
+    for fused in (False, True):
+        torch.manual_seed(3)
+        conv = torch.nn.Conv2d(1, 64, 7, padding=3).to(DEV)
+        bn = torch.nn.BatchNorm2d(64).to(DEV)
+        with torch.no_grad():
+            bn.weight.copy_(1.0 + 0.1 * torch.randn(64, device=DEV, generator=gen)); bn.bias.copy_(0.1 * torch.randn(64, device=DEV, generator=gen))
+            bn.running_mean.copy_(0.05 * torch.randn(64, device=DEV, generator=gen)); bn.running_var.copy_(1.0 + 0.1 * torch.rand(64, device=DEV, generator=gen))
+        gen = torch.Generator(device=DEV).manual_seed(B + W)           # same draws for both variants
+        x = torch.randn(B, 1, H, W, device=DEV, generator=gen)
+        st = torch.zeros(2, 64, device=DEV, dtype=torch.float64)
+        if fused:
+            if training:
+                gram = ops.stem_gram(x)
+                ops.stem_stats_from_gram(gram, conv, B, H, W, st)
+            co = ops.bn_finalize(st if training else None, B * H * W, bn, training)
+            p0, am, planes = ops.stem_fwd(x, conv, co, want_planes=True)
+        else:
+            g = ops.conv_geom(B, H, W, 1, 64, 7, 1, 3)
+            y0 = ops.conv_fwd(x, conv.weight, conv.bias, g, None, st if training else None, L.PREC_FP32)
+            co = ops.bn_finalize(st if training else None, B * H * W, bn, training)
+            p0, am, planes = ops.bn_act_fwd(y0, co, 3, None, want_planes=True)
+        outs.append((p0, am, planes, st.clone(), bn.running_mean.clone(), bn.running_var.clone()))
+    (p_a, am_a, pl_a, st_a, rm_a, rv_a), (p_b, am_b, pl_b, st_b, rm_b, rv_b) = outs
+    scale = float(p_a.abs().max())
+    assert float((p_a - p_b).abs().max()) <= 1e-5 * scale, float((p_a - p_b).abs().max()) / scale
+    if training:
+        np.testing.assert_allclose(st_b.cpu().numpy(), st_a.cpu().numpy(), rtol=2e-6, atol=1e-3)
+    np.testing.assert_allclose(rm_b.cpu().numpy(), rm_a.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(rv_b.cpu().numpy(), rv_a.cpu().numpy(), rtol=1e-5, atol=1e-7)
+    differ = (am_a != am_b)
+    assert float(differ.float().mean()) <= 1e-4                      # ties / near-ties inside a window only
+    assert float((p_a - p_b).abs()[differ].max()) <= 1e-5 * scale if differ.any() else True
+    halves = pl_b.view(torch.float16).reshape(-1)
+    hi = halves[: p_b.numel()].float().view_as(p_b)
+    lo = halves[p_b.numel():].float().view_as(p_b)
+    assert float((hi + lo / 2048.0 - p_b).abs().max()) <= 1e-6 * scale
