@@ -171,6 +171,8 @@ def train_inputs(views, seed, device, n_buffers=4):
 
 def build_trainer(arch, device, parallel):
     import logging
+    if not logging.getLogger("bench").handlers:          # warnings (e.g. a failed graph capture) must be visible on stderr
+        logging.getLogger("bench").addHandler(logging.StreamHandler(sys.stderr))
 
     from phoneme_contrast_b200.models import model_registry
     from phoneme_contrast_b200.training import ContrastiveTrainer, FusedClipAdam, get_loss_fn

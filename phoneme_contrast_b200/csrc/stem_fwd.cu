@@ -37,7 +37,7 @@ constexpr uint32_t B_BYTES = 2 * CO * 128;      // [w_hi rows ; w_lo rows]
 struct Params {
   const float* x; const float* w; const float* bias; const float* scale; const float* shift;
   float* p0; uint8_t* argmax; unsigned char* planes;
-  int B, H, W, Hp, Wp, WLD, RG_LD;
+  int B, H, W, Hp, Wp, WLD, LDH;     // LDH: halves per row of the pre-split window arrays (even)
   int n_items;                 // B * Hp
   FastDiv d_hp;
   size_t plane_elems;
@@ -56,35 +56,35 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
   unsigned char* stages = smem;                                              // [NSTAGE][STAGE]
   unsigned char* b_tile = smem + (size_t)NSTAGE * STAGE;                     // [2 * 64 rows][128 B]
   float* act = reinterpret_cast<float*>(b_tile + B_BYTES);                   // [3][64][WLD]
-  float* win = act + 3 * CO * p.WLD;                                         // [NGROUPS][9 * RG_LD]
-  uint64_t* full = reinterpret_cast<uint64_t*>(win + NGROUPS * 9 * p.RG_LD + 4);
+  __half* win = reinterpret_cast<__half*>(act + 3 * CO * p.WLD);             // [NGROUPS][4 arrays: hi0 | hi1 | lo0 | lo1][9][LDH] fp16
+  uint64_t* full = reinterpret_cast<uint64_t*>(win + (size_t)NGROUPS * 4 * 9 * p.LDH + 8);
   uint64_t* empty = full + NSTAGE;
   uint64_t* acc_full = empty + NSTAGE;        // [NSLOT]
   uint64_t* acc_empty = acc_full + NSLOT;     // [NSLOT]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + NSLOT);
-  float* s_co = reinterpret_cast<float*>(tmem_slot + 2);                     // [3][64] bias | scale | shift
+  float* s_co = reinterpret_cast<float*>(tmem_slot + 4);                     // [3][64] bias | scale | shift (16-byte aligned: read as float4)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  // weights -> K-major SWIZZLE_128B fp16 hi / lo rows (row o, 16-byte chunk j = taps 8j .. 8j+7; taps >= 49 are zero)
+  // weights -> K-major SWIZZLE_128B fp16 hi / lo rows. The reduction index is k = 8 * tr + ts (tap row tr = 16-byte chunk, tap
+  // column ts < 7 inside it; k = 8 tr + 7 and chunk 7 are zero): a chunk of the A operand is then 8 CONSECUTIVE input samples
   for (int i = tid; i < CO * 8; i += THREADS) {
     const int o = i >> 3, j = i & 7;
     float v[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int t = 8 * j + q;
-      v[q] = t < NT ? p.w[o * NT + t] : 0.f;
-    }
+    for (int q = 0; q < 8; ++q) v[q] = (j < KS && q < KS) ? p.w[o * NT + j * KS + q] : 0.f;
     uint4 h, l;
     split_f16x2(v[0], v[1], h.x, l.x); split_f16x2(v[2], v[3], h.y, l.y);
     split_f16x2(v[4], v[5], h.z, l.z); split_f16x2(v[6], v[7], h.w, l.w);
     *reinterpret_cast<uint4*>(b_tile + sw128_offset((uint32_t)o, (uint32_t)j)) = h;
     *reinterpret_cast<uint4*>(b_tile + CO * 128 + sw128_offset((uint32_t)o, (uint32_t)j)) = l;
   }
-  for (int i = tid; i < CO; i += THREADS) {
-    s_co[i] = p.bias != nullptr ? p.bias[i] : 0.f;
+  for (int i = tid; i < CO; i += THREADS) {       // bn(y + b) = scale * y + (scale * b + shift)
+    const float bsv = p.bias != nullptr ? p.bias[i] : 0.f;
+    s_co[i] = bsv;
     s_co[CO + i] = p.scale[i];
-    s_co[2 * CO + i] = p.shift[i];
+    s_co[2 * CO + i] = fmaf(p.scale[i], bsv, p.shift[i]);
   }
+  for (int i = tid; i < NGROUPS * 4 * 9 * p.LDH / 2; i += THREADS) reinterpret_cast<uint32_t*>(win)[i] = 0u;
   if (warp == PROD_WARPS) {
     if (lane == 0) {
       for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], 1); }
@@ -106,27 +106,34 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
     // ================================================================================= producers
     const int group = warp >> 2, gt = tid & (NPROD - 1);
     const int j = gt & 7, pr = gt >> 3;
-    float* wbuf = win + group * 9 * p.RG_LD;
-    int tap_off[8];
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int t = 8 * j + q;
-      tap_off[q] = t < NT ? (t / KS) * p.RG_LD + (t % KS) : -1;
-    }
+    // pre-split window of the current item: fp16 hi and lo*2^11 planes, each stored twice -- copy 0 with sample cc at half index
+    // cc, copy 1 at cc + 1 -- so that the 8 consecutive samples of ANY operand chunk start on a 4-byte boundary in one of them
+    const int asz = 9 * p.LDH;
+    __half* whi0 = win + (size_t)group * 4 * asz;
+    __half* whi1 = whi0 + asz;
+    __half* wlo0 = whi1 + asz;
+    __half* wlo1 = wlo0 + asz;
+    const int odd = pr & 1;                                   // parity of my rows w = pr + 16 i
+    const __half* my_hi = odd ? whi1 : whi0;
+    const __half* my_lo = odd ? wlo1 : wlo0;
     int tile_idx = 0;       // global tile counter of this CTA at the start of the current item
     for (int it = it0; it < it1; ++it) {
       uint32_t b, ph;
       p.d_hp.divmod((uint32_t)it, b, ph);
       const int nt = tiles_of((int)ph, p.H);
       if (((it - it0) & (NGROUPS - 1)) == group) {
-        // ---- window: input rows 2ph-4 .. 2ph+4, columns -3 .. W+2 (zero outside)
+        // ---- window: input rows 2ph-4 .. 2ph+4, columns -3 .. W+2 (zero outside), split once per sample
         const float* img = p.x + (size_t)b * p.H * p.W;
         const int h0 = 2 * (int)ph - 4;
         asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");
         for (int e = gt; e < 9 * (p.W + 6); e += NPROD) {
           const int rr = e / (p.W + 6), cc = e - rr * (p.W + 6);
           const int hi = h0 + rr, wi = cc - 3;
-          wbuf[rr * p.RG_LD + cc] = ((unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W) ? img[hi * p.W + wi] : 0.f;
+          const float v = ((unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W) ? img[hi * p.W + wi] : 0.f;
+          const __half vh = __float2half_rn(v);
+          const __half vl = __float2half_rn((v - __half2float(vh)) * kF16LoScale);
+          const int o0 = rr * p.LDH + cc;
+          whi0[o0] = vh; whi1[o0 + 1] = vh; wlo0[o0] = vl; wlo1[o0 + 1] = vl;
         }
         asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");
         int k = 0;
@@ -138,17 +145,20 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
           ++k;
           const int s = t_glob % NSTAGE;
           const uint32_t phs = (uint32_t)(t_glob / NSTAGE) & 1u;
-          // conv pixel (h, w): tap (tr, ts) reads input (h + tr - 3, w + ts - 3) = window[(kh + tr)][w + ts]
+          // conv pixel (h, w), chunk j = tap row tr: input samples (h + tr - 3, w - 3 .. w + 4) = window row kh + tr, columns w .. w + 7
           uint4 hh[8], ll[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int w = pr + 16 * i;
-            const float* base = wbuf + kh * p.RG_LD + min(w, p.W - 1);
-            float tv[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) tv[q] = (tap_off[q] >= 0 && w < p.W) ? base[tap_off[q]] : 0.f;
-            split_f16x2(tv[0], tv[1], hh[i].x, ll[i].x); split_f16x2(tv[2], tv[3], hh[i].y, ll[i].y);
-            split_f16x2(tv[4], tv[5], hh[i].z, ll[i].z); split_f16x2(tv[6], tv[7], hh[i].w, ll[i].w);
+            hh[i] = make_uint4(0u, 0u, 0u, 0u);
+            ll[i] = hh[i];
+            if (j < KS && w < p.W) {
+              const int o0 = (kh + j) * p.LDH + w + odd;          // even half index
+              const uint32_t* ph_ = reinterpret_cast<const uint32_t*>(my_hi + o0);
+              const uint32_t* pl_ = reinterpret_cast<const uint32_t*>(my_lo + o0);
+              hh[i] = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
+              ll[i] = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
+            }
           }
           // Two producer groups share one stage ring, so a group may reach use n of a stage while use n-1 (the other group's) has
           // not even been filled; a parity wait on `empty` alone would then alias to an older phase. Waiting first for use n-1 to
@@ -228,9 +238,14 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
           tmem_ld_wait();
           if (wpix < p.W) {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) {
-              const float y = fmaf(__uint_as_float(r1[k]), kF16LoInv, __uint_as_float(r0[k])) + s_co[c0 + k];
-              arow[(size_t)(c0 + k) * p.WLD] = fmaxf(fmaf(y, s_co[CO + c0 + k], s_co[2 * CO + c0 + k]), 0.f);
+            for (int k = 0; k < 32; k += 4) {
+              const float4 sc = *reinterpret_cast<const float4*>(s_co + CO + c0 + k), tt = *reinterpret_cast<const float4*>(s_co + 2 * CO + c0 + k);
+              const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, ttv[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float y = fmaf(__uint_as_float(r1[k + q]), kF16LoInv, __uint_as_float(r0[k + q]));
+                arow[(size_t)(c0 + k + q) * p.WLD] = fmaxf(fmaf(y, scv[q], ttv[q]), 0.f);
+              }
             }
           }
         }
@@ -275,22 +290,29 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
   if (warp == PROD_WARPS) tmem_dealloc(tmem_base, 512);
 }
 
-// stats[0][o] = sum_p y0, stats[1][o] = sum_p y0^2 from the Gram matrix / tap sums of the input patches (fp64)
+// stats[0][o] = sum_p y0, stats[1][o] = sum_p y0^2 from the Gram matrix / tap sums of the input patches (fp64); block = channel
 __global__ void __launch_bounds__(64) stem_stats_kernel(const double* __restrict__ G, const double* __restrict__ X1, const float* __restrict__ w,
                                                         const float* __restrict__ bias, double M, double* __restrict__ stats) {
-  const int o = threadIdx.x;
-  if (o >= CO) return;
-  const double b = bias != nullptr ? (double)bias[o] : 0.0;
-  double wx = 0.0, wgw = 0.0;
-  for (int t = 0; t < NT; ++t) {
-    const double wt = (double)w[o * NT + t];
-    wx += wt * X1[t];
+  __shared__ double s_w[NT], s_a[64], s_b[64];
+  const int o = blockIdx.x, t = threadIdx.x;
+  if (t < NT) s_w[t] = (double)w[o * NT + t];
+  __syncthreads();
+  double a = 0.0, q = 0.0;
+  if (t < NT) {
     double r = 0.0;
-    for (int u = 0; u < NT; ++u) r += G[t * NT + u] * (double)w[o * NT + u];
-    wgw += wt * r;
+    for (int u = 0; u < NT; ++u) r = fma(G[t * NT + u], s_w[u], r);
+    q = s_w[t] * r;
+    a = s_w[t] * X1[t];
   }
-  stats[o] = wx + M * b;
-  stats[CO + o] = wgw + 2.0 * b * wx + M * b * b;
+  s_a[t] = a; s_b[t] = q;
+  __syncthreads();
+  if (t == 0) {
+    double wx = 0.0, wgw = 0.0;
+    for (int u = 0; u < NT; ++u) { wx += s_a[u]; wgw += s_b[u]; }
+    const double b = bias != nullptr ? (double)bias[o] : 0.0;
+    stats[o] = wx + M * b;
+    stats[CO + o] = wgw + 2.0 * b * wx + M * b * b;
+  }
 }
 
 }  // namespace stemf
@@ -304,7 +326,7 @@ extern "C" int pc_stem_fwd_supported(int k, int Cout, int H, int W) { return (k 
 extern "C" int pc_stem_stats_from_gram(const double* G, const double* X1, const float* w_oihw, const float* bias, int B, int H, int W,
                                        double* stats, pc_stream_t stream) {
   PC_REQUIRE(G && X1 && w_oihw && stats, PC_EINVAL, "pc_stem_stats_from_gram: null pointer");
-  stem_stats_kernel<<<1, 64, 0, stream>>>(G, X1, w_oihw, bias, (double)B * H * W, stats);
+  stem_stats_kernel<<<CO, 64, 0, stream>>>(G, X1, w_oihw, bias, (double)B * H * W, stats);
   PC_LAUNCH_CHECK("stem_stats_kernel");
   return PC_OK;
 }
@@ -320,11 +342,11 @@ extern "C" int pc_stem_fwd(const float* x, const float* w_oihw, const float* bia
   p.planes = static_cast<unsigned char*>(planes);
   p.B = B; p.H = H; p.W = W; p.Hp = (H + 2 - 3) / 2 + 1; p.Wp = (W + 2 - 3) / 2 + 1;
   p.WLD = (W + 4) | 1;
-  p.RG_LD = (W + 6) | 1;
+  p.LDH = (W + 6 + 8 + 2 + 1) & ~1;
   p.n_items = B * p.Hp;
   p.d_hp = FastDiv::make((uint32_t)p.Hp);
   p.plane_elems = (size_t)B * p.Hp * p.Wp * CO;
-  const size_t smem = (size_t)NSTAGE * STAGE + B_BYTES + sizeof(float) * (3 * (size_t)CO * p.WLD + NGROUPS * 9 * (size_t)p.RG_LD + 4) +
+  const size_t smem = (size_t)NSTAGE * STAGE + B_BYTES + sizeof(float) * (3 * (size_t)CO * p.WLD) + sizeof(__half) * ((size_t)NGROUPS * 4 * 9 * p.LDH + 8) +
                       sizeof(uint64_t) * (2 * NSTAGE + 2 * NSLOT + 1) + 16 + sizeof(float) * 3 * CO + 1024;
   PC_REQUIRE(smem <= 227 * 1024, PC_EUNSUPPORTED, "pc_stem_fwd: row width %d needs %zu B of shared memory", W, smem);
   static size_t conf = 0;
