@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) stem_gram_kernel(const float* __restrict_
   const int Wz = W + 16, Hz = H + 12;              // 6 zero rows above / below, 6 zero columns left, 10 right (the 4-wide window over-reads)
   float* xz = sm;                                  // [(H+12)][(W+16)] zero-extended image
   float* tab = xz + Hz * Wz;                       // [NLAG][49]: c0 | rows[6] | cols[6] | corner[6][6]
+  float* rowval = tab + NLAG * 49;                 // [H][7]: sum of row i over the columns tap column s reaches
   const int tid = threadIdx.x;
   for (int i = tid; i < NLAG * 49; i += blockDim.x) tab[i] = 0.f;
   float x1 = 0.f;
@@ -64,6 +65,7 @@ __global__ void __launch_bounds__(256) stem_gram_kernel(const float* __restrict_
         const float* bb = xz + (i + 6 + dr) * Wz + 6 + ds0;
         float w0 = bb[0], w1 = bb[1], w2 = bb[2];
         float rs[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
         for (int j = 0; j < W; ++j) {
           const float av = a[j], w3 = bb[j + 3];
           rs[0] = fmaf(av, w0, rs[0]); rs[1] = fmaf(av, w1, rs[1]); rs[2] = fmaf(av, w2, rs[2]); rs[3] = fmaf(av, w3, rs[3]);
@@ -95,12 +97,26 @@ __global__ void __launch_bounds__(256) stem_gram_kernel(const float* __restrict_
         t[13 + rsl * 6 + cs] += xz[(i + 6) * Wz + 6 + jc] * xz[(i + 6 + dr) * Wz + 6 + jc + ds];
       }
     }
+    // X1[(r, s)] = sum of x over rows [max(0, r-3), min(H-1, H-4+r)] x columns [max(0, s-3), min(W-1, W-4+s)]: one warp per row
+    // forms the row total and removes the (at most three) border columns tap column s does not reach, then 49 threads add rows
+    for (int i = tid >> 5; i < H; i += (int)(blockDim.x >> 5)) {
+      const float* a = xz + (i + 6) * Wz + 6;
+      float t = 0.f;
+      for (int j = tid & 31; j < W; j += 32) t += a[j];
+      t = warp_sum(t);
+      if ((tid & 31) == 0) {
+        float* rv = rowval + i * 7;
+        rv[3] = t;
+        rv[2] = t - a[W - 1]; rv[1] = rv[2] - a[W - 2]; rv[0] = rv[1] - a[W - 3];
+        rv[4] = t - a[0]; rv[5] = rv[4] - a[1]; rv[6] = rv[5] - a[2];
+      }
+    }
+    __syncthreads();
     if (tid < NT) {
       const int r = tid / KS, s2 = tid % KS;
-      const int i0 = max(0, r - 3), i1 = min(H - 1, H - 4 + r), j0 = max(0, s2 - 3), j1 = min(W - 1, W - 4 + s2);
+      const int i0 = max(0, r - 3), i1 = min(H - 1, H - 4 + r);
       float t = 0.f;
-      for (int i = i0; i <= i1; ++i)
-        for (int j = j0; j <= j1; ++j) t += xz[(i + 6) * Wz + 6 + j];
+      for (int i = i0; i <= i1; ++i) t += rowval[i * 7 + s2];
       x1 += t;
     }
   }
@@ -451,14 +467,14 @@ using namespace pc;
 using namespace pc::stemb;
 
 extern "C" int pc_stem_bwd_supported(int k, int Cout, int H, int W) {
-  return (k == 7 && Cout == 64 && H >= 7 && W >= 7 && (size_t)(H + 12) * (W + 16) * 4 + NLAG * 49 * 4 <= 200 * 1024) ? 1 : 0;
+  return (k == 7 && Cout == 64 && H >= 7 && W >= 7 && (size_t)(H + 12) * (W + 16) * 4 + NLAG * 49 * 4 + (size_t)H * 7 * 4 <= 200 * 1024) ? 1 : 0;
 }
 
 // G [49*49] and X1 [49] (fp64, ACCUMULATED into: the caller zeroes them) of the stem's input patches, x [B][H][W].
 extern "C" int pc_stem_gram(const float* x, int B, int H, int W, double* G, double* X1, pc_stream_t stream) {
   PC_REQUIRE(x && G && X1 && B > 0, PC_EINVAL, "pc_stem_gram: bad arguments");
   PC_REQUIRE(pc_stem_bwd_supported(7, 64, H, W), PC_EUNSUPPORTED, "pc_stem_gram: image %dx%d not covered", H, W);
-  const size_t smem = ((size_t)(H + 12) * (W + 16) + NLAG * 49) * sizeof(float);
+  const size_t smem = ((size_t)(H + 12) * (W + 16) + NLAG * 49 + (size_t)H * 7) * sizeof(float);
   static size_t conf = 0;
   if (smem > conf) {
     PC_CUDA(cudaFuncSetAttribute(stem_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

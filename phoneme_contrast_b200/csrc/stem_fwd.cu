@@ -28,7 +28,7 @@ using namespace pc::tc;
 
 constexpr int KS = 7, NT = 49, CO = 64;
 constexpr int NSTAGE = 3, NSLOT = 4;
-constexpr int NGROUPS = 2, NPROD = 128, PROD_WARPS = 4 * NGROUPS, EPI_WARPS = 4;
+constexpr int NGROUPS = 2, NPROD = 128, PROD_WARPS = 4 * NGROUPS, EPI_WARPS = 8;
 constexpr int THREADS = 32 * (PROD_WARPS + 1 + EPI_WARPS);
 constexpr uint32_t A_PART = 128 * 128;          // [128 pixels][128 B]
 constexpr uint32_t STAGE = 2 * A_PART;          // hi | lo
@@ -43,12 +43,17 @@ struct Params {
   size_t plane_elems;
 };
 
-__device__ __forceinline__ int tiles_of(int ph, int H) {        // conv rows 2ph-1 .. 2ph+1 inside [0, H)
+// Conv rows 2ph-1 .. 2ph+1 inside [0, H) feed pooled row ph. Row 2ph-1 is also row 2(ph-1)+1 of the previous pooled row: a CTA walks
+// consecutive items, so unless the item is the CTA's first or starts an image (`fresh`) that row is still in the activation ring
+// (slot (h + 1) % 3) and only two new rows are convolved.
+__device__ __forceinline__ int first_kh(bool fresh) { return fresh ? 0 : 1; }
+__device__ __forceinline__ int tiles_of(int ph, int H, bool fresh) {
   int n = 0;
 #pragma unroll
-  for (int kh = 0; kh < 3; ++kh) n += (unsigned)(2 * ph - 1 + kh) < (unsigned)H ? 1 : 0;
+  for (int kh = 0; kh < 3; ++kh) n += (kh >= first_kh(fresh) && (unsigned)(2 * ph - 1 + kh) < (unsigned)H) ? 1 : 0;
   return n;
 }
+__device__ __forceinline__ int act_slot(int h) { return (h + 1) % 3; }
 
 __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -85,6 +90,9 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
     s_co[2 * CO + i] = fmaf(p.scale[i], bsv, p.shift[i]);
   }
   for (int i = tid; i < NGROUPS * 4 * 9 * p.LDH / 2; i += THREADS) reinterpret_cast<uint32_t*>(win)[i] = 0u;
+  // activation rows: column 0 is w = -1, columns 1 .. W the pixels, the rest padding; padding holds -1 (< any ReLU output), so the
+  // pooling windows need no bounds checks
+  for (int i = tid; i < 3 * CO * p.WLD; i += THREADS) act[i] = -1.f;
   if (warp == PROD_WARPS) {
     if (lane == 0) {
       for (int s = 0; s < NSTAGE; ++s) { mbar_init(&full[s], NPROD); mbar_init(&empty[s], 1); }
@@ -120,13 +128,15 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
     for (int it = it0; it < it1; ++it) {
       uint32_t b, ph;
       p.d_hp.divmod((uint32_t)it, b, ph);
-      const int nt = tiles_of((int)ph, p.H);
+      const bool fresh = it == it0 || ph == 0u;
+      const int nt = tiles_of((int)ph, p.H, fresh);
       if (((it - it0) & (NGROUPS - 1)) == group) {
         // ---- window: input rows 2ph-4 .. 2ph+4, columns -3 .. W+2 (zero outside), split once per sample
         const float* img = p.x + (size_t)b * p.H * p.W;
         const int h0 = 2 * (int)ph - 4;
         asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");
-        for (int e = gt; e < 9 * (p.W + 6); e += NPROD) {
+        const int rr0 = first_kh(fresh);                      // window row 0 only feeds conv row 2ph-1
+        for (int e = gt + rr0 * (p.W + 6); e < 9 * (p.W + 6); e += NPROD) {
           const int rr = e / (p.W + 6), cc = e - rr * (p.W + 6);
           const int hi = h0 + rr, wi = cc - 3;
           const float v = ((unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W) ? img[hi * p.W + wi] : 0.f;
@@ -138,7 +148,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
         asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");
         int k = 0;
 #pragma unroll 1
-        for (int kh = 0; kh < 3; ++kh) {
+        for (int kh = rr0; kh < 3; ++kh) {
           const int h = 2 * (int)ph - 1 + kh;
           if ((unsigned)h >= (unsigned)p.H) continue;
           const int t_glob = tile_idx + k;
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
       for (int it = it0; it < it1; ++it) {
         uint32_t b, ph;
         p.d_hp.divmod((uint32_t)it, b, ph);
-        const int nt = tiles_of((int)ph, p.H);
+        const int nt = tiles_of((int)ph, p.H, it == it0 || ph == 0u);
         for (int k = 0; k < nt; ++k, ++t_glob) {
           const int s = t_glob % NSTAGE, slot = t_glob % NSLOT;
           mbar_wait(&acc_empty[slot], ((uint32_t)(t_glob / NSLOT) & 1u) ^ 1u);
@@ -209,19 +219,24 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
     __syncwarp();
   } else {
     // ================================================================================= epilogue: normalise, rectify, pool
-    const int ew = warp - PROD_WARPS - 1;                 // 0..3 = TMEM lane quarter (warp % 4 must equal the quarter)
+    // 8 warps: TMEM lane quarter = warp % 4 (hardware rule), two warps per quarter split the 64 channels
     const int quarter = warp & 3;
-    const int et = (warp - PROD_WARPS - 1) * 32 + lane;   // 0..127
-    (void)ew;
+    const int chalf = (warp - PROD_WARPS - 1) >> 2;
+    const int et = (warp - PROD_WARPS - 1) * 32 + lane;   // 0..255
     const int wpix = quarter * 32 + lane;                 // conv pixel (column) of my TMEM lane
+    const int c0 = 32 * chalf;
+    // pooling role: channel c, quarter rq of the pooled row
+    const int c = et & 63, rq = et >> 6;
+    const int per = (p.Wp + 3) >> 2;
+    const int pw0 = rq * per, pw1 = min(p.Wp, pw0 + per);
     int t_glob = 0;
     for (int it = it0; it < it1; ++it) {
       uint32_t b, ph;
       p.d_hp.divmod((uint32_t)it, b, ph);
-      // ---- part 1: the item's conv rows from TMEM into act[kh][c][w] (BatchNorm + ReLU applied)
+      // ---- part 1: the item's new conv rows from TMEM into act[slot][c][1 + w] (BatchNorm + ReLU applied)
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");      // previous item's pooling no longer reads act
 #pragma unroll 1
-      for (int kh = 0; kh < 3; ++kh) {
+      for (int kh = first_kh(it == it0 || ph == 0u); kh < 3; ++kh) {
         const int h = 2 * (int)ph - 1 + kh;
         if ((unsigned)h >= (unsigned)p.H) continue;
         const int slot = t_glob % NSLOT;
@@ -229,23 +244,20 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
         tc_fence_after();
         ++t_glob;
         const uint32_t t_row = tmem_base + (uint32_t)slot * 128u + ((uint32_t)(quarter * 32) << 16);
-        float* arow = act + (size_t)kh * CO * p.WLD + wpix;
-#pragma unroll 1
-        for (int c0 = 0; c0 < CO; c0 += 32) {
-          uint32_t r0[32], r1[32];
-          tmem_ld_32x32(t_row + (uint32_t)c0, r0);
-          tmem_ld_32x32(t_row + (uint32_t)(c0 + CO), r1);
-          tmem_ld_wait();
-          if (wpix < p.W) {
+        float* arow = act + (size_t)act_slot(h) * CO * p.WLD + wpix + 1;
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(t_row + (uint32_t)c0, r0);
+        tmem_ld_32x32(t_row + (uint32_t)(c0 + CO), r1);
+        tmem_ld_wait();
+        if (wpix < p.W) {
 #pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-              const float4 sc = *reinterpret_cast<const float4*>(s_co + CO + c0 + k), tt = *reinterpret_cast<const float4*>(s_co + 2 * CO + c0 + k);
-              const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, ttv[4] = {tt.x, tt.y, tt.z, tt.w};
+          for (int k = 0; k < 32; k += 4) {
+            const float4 sc = *reinterpret_cast<const float4*>(s_co + CO + c0 + k), tt = *reinterpret_cast<const float4*>(s_co + 2 * CO + c0 + k);
+            const float scv[4] = {sc.x, sc.y, sc.z, sc.w}, ttv[4] = {tt.x, tt.y, tt.z, tt.w};
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float y = fmaf(__uint_as_float(r1[k + q]), kF16LoInv, __uint_as_float(r0[k + q]));
-                arow[(size_t)(c0 + k + q) * p.WLD] = fmaxf(fmaf(y, scv[q], ttv[q]), 0.f);
-              }
+            for (int q = 0; q < 4; ++q) {
+              const float y = fmaf(__uint_as_float(r1[k + q]), kF16LoInv, __uint_as_float(r0[k + q]));
+              arow[(size_t)(c0 + k + q) * p.WLD] = fmaxf(fmaf(y, scv[q], ttv[q]), 0.f);
             }
           }
         }
@@ -254,25 +266,32 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
         if (lane == 0) mbar_arrive(&acc_empty[slot]);
       }
       asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");      // act complete
-      // ---- part 2: pooled row ph. thread = channel pair; 2 threads groups of 64 channels alternate over pw
-      const int c = et & 63, pw_par = et >> 6;
-      for (int pw = pw_par; pw < p.Wp; pw += 2) {
+      // ---- part 2: pooled row ph. Window of pooled pixel pw = act columns 2pw, 2pw+1, 2pw+2 (column 0 is w = -1): one 8-byte
+      // load per row and pixel, the third column is the first of the next pair. Rows scanned in order with a strict compare =
+      // first maximum in (kh, kw) scan order (PyTorch's tie rule).
+      const float* rowp[3];
+      bool rv[3];
+      float2 cur[3];
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h = 2 * (int)ph - 1 + kh;
+        rv[kh] = (unsigned)h < (unsigned)p.H;
+        rowp[kh] = act + ((size_t)act_slot(rv[kh] ? h : 0) * CO + c) * p.WLD;
+        cur[kh] = (rv[kh] && pw0 < pw1) ? *reinterpret_cast<const float2*>(rowp[kh] + 2 * pw0) : make_float2(-1.f, -1.f);
+      }
+      size_t o = (((size_t)b * p.Hp + ph) * p.Wp + pw0) * CO + c;
+      for (int pw = pw0; pw < pw1; ++pw, o += CO) {
         float best = -INFINITY;
         int arg = 0;
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh) {
-          const int h = 2 * (int)ph - 1 + kh;
-          if ((unsigned)h >= (unsigned)p.H) continue;
-          const float* ar = act + ((size_t)kh * CO + c) * p.WLD;
-#pragma unroll
-          for (int kw = 0; kw < 3; ++kw) {
-            const int w = 2 * pw - 1 + kw;
-            if ((unsigned)w >= (unsigned)p.W) continue;
-            const float a = ar[w];
-            if (a > best) { best = a; arg = kh * 3 + kw; }
-          }
+          if (!rv[kh]) continue;
+          const float2 nx = *reinterpret_cast<const float2*>(rowp[kh] + 2 * pw + 2);
+          if (cur[kh].x > best) { best = cur[kh].x; arg = kh * 3; }
+          if (cur[kh].y > best) { best = cur[kh].y; arg = kh * 3 + 1; }
+          if (nx.x > best) { best = nx.x; arg = kh * 3 + 2; }
+          cur[kh] = nx;
         }
-        const size_t o = (((size_t)b * p.Hp + ph) * p.Wp + pw) * CO + c;
         p.p0[o] = best;
         if (p.argmax != nullptr) p.argmax[o] = (uint8_t)arg;
         if (p.planes != nullptr) {
@@ -341,7 +360,7 @@ extern "C" int pc_stem_fwd(const float* x, const float* w_oihw, const float* bia
   p.x = x; p.w = w_oihw; p.bias = bias; p.scale = scale; p.shift = shift; p.p0 = p0; p.argmax = argmax;
   p.planes = static_cast<unsigned char*>(planes);
   p.B = B; p.H = H; p.W = W; p.Hp = (H + 2 - 3) / 2 + 1; p.Wp = (W + 2 - 3) / 2 + 1;
-  p.WLD = (W + 4) | 1;
+  p.WLD = 2 * ((p.Wp + 1) | 1);          // 2 * odd (conflict-free 8-byte loads across channels), >= 2 Wp + 2 columns
   p.LDH = (W + 6 + 8 + 2 + 1) & ~1;
   p.n_items = B * p.Hp;
   p.d_hp = FastDiv::make((uint32_t)p.Hp);

@@ -1,0 +1,7 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+export PYTHONUNBUFFERED=1
+CMD="python profiles/tools/stem_bench.py"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"stem_fwd_kernel" -s 3 -c 1 -o gpurun_out/r2o_stem_fwd_full $CMD > gpurun_out/r2o_ncu1.log 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"stem_bwd_pool_kernel" -s 3 -c 1 -o gpurun_out/r2o_stem_bwd_full $CMD > gpurun_out/r2o_ncu2.log 2>&1; echo "ncu rc=$?"
