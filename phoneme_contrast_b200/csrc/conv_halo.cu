@@ -52,6 +52,10 @@ struct Params {
   long long Q;
   int n_mtiles, n_ntiles, n_items, cpt, accumulate, cluster;
   int tap_shift[9];          // row shift of weight tap r * 3 + s
+  int ntaps;                 // 9 (3x3) or 1 (1x1 shortcut convolutions)
+  int halo;                  // positions staged on either side of a tile: W + 2 (3x3) or 0 (1x1)
+  int a_stride;              // 1x1 forward with stride 2: the activation boxes sample every a_stride-th pixel (TMA elementStrides)
+  int Hout, Wout, o_stride;  // output image and pixel stride: position (hp, wp) -> pixel (o_stride (hp-1), o_stride (wp-1)) (1x1 stride-2 dgrad: 2)
   int b_stages;
   uint32_t region_bytes;     // one part (hi or lo) of an A region: nbox * box_pos * 128, rounded up to 1024
   uint32_t a_tx_bytes;       // bytes the TMA boxes of one region deliver (both parts, unrounded)
@@ -138,7 +142,7 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
       p.d_pimg.divmod((uint32_t)q, b, rem);
       p.d_wp.divmod(rem, hp, wp);
       valid = hp >= 1u && wp >= 1u;
-      pix = ((long long)b * p.H + (hp - 1u)) * p.W + (wp - 1u);
+      pix = ((long long)b * p.Hout + (long long)p.o_stride * (hp - 1u)) * p.Wout + (long long)p.o_stride * (wp - 1u);
     }
     float* dst_row = p.C + (size_t)(valid ? pix : 0) * p.Nn + n0;
     const uint32_t tb = ti % NBUF;
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const __grid_cons
         p.d_nt.divmod(item, mg, nt);
         const int m_tile = (int)(mg * (uint32_t)CL + rank);
         const int n0 = (int)nt * BN;
-        const int q_lo = m_tile * BM - p.Wp - 1;
+        const int q_lo = m_tile * BM - p.halo;
         const int bx0 = floor_div(q_lo, p.box_pos);
         for (int cc = 0; cc < p.cpt; ++cc) {
           // ---- A region of this chunk: nbox boxes of RB padded rows, hi and lo planes
@@ -314,12 +318,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const __grid_cons
             const int rg = (bx0 + j) * p.RB;                    // global padded-row index of the box's first row
             const int b = floor_div(rg, p.H + 1);
             const int hp0 = rg - b * (p.H + 1);
-            tma_load_5d(dst + (size_t)j * p.box_pos * 128, &amap, &a_full[ab], cc * 64, -1, hp0 - 1, b, 0);
-            tma_load_5d(dst + p.region_bytes + (size_t)j * p.box_pos * 128, &amap, &a_full[ab], cc * 64, -1, hp0 - 1, b, 1);
+            tma_load_5d(dst + (size_t)j * p.box_pos * 128, &amap, &a_full[ab], cc * 64, -p.a_stride, p.a_stride * (hp0 - 1), b, 0);
+            tma_load_5d(dst + p.region_bytes + (size_t)j * p.box_pos * 128, &amap, &a_full[ab], cc * 64, -p.a_stride, p.a_stride * (hp0 - 1), b, 1);
           }
           ++ai;
           // ---- weight stages of this chunk, one per tap
-          for (int t = 0; t < 9; ++t) {
+          for (int t = 0; t < p.ntaps; ++t) {
             const uint32_t s = bi % (uint32_t)p.b_stages;
             mbar_wait(&b_empty[s], ((bi / (uint32_t)p.b_stages) & 1u) ^ 1u);
             mbar_arrive_expect_tx(&b_full[s], B_STAGE);
@@ -348,7 +352,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const __grid_cons
         uint32_t mg, nt;
         p.d_nt.divmod(item, mg, nt);
         const int m_tile = (int)(mg * (uint32_t)CL + rank);
-        const int q_lo = m_tile * BM - p.Wp - 1;
+        const int q_lo = m_tile * BM - p.halo;
         const int bx0 = floor_div(q_lo, p.box_pos);
         const int delta = m_tile * BM - bx0 * p.box_pos;          // row of the tile's first position inside the region
         const uint32_t tb = ti % NBUF;
@@ -361,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const __grid_cons
           mbar_wait(&a_full[ab], (ai >> 1) & 1u);
           tc_fence_after();
           const uint32_t a_base = smem_u32(a_buf + (size_t)ab * a_buf_bytes);
-          for (int t = 0; t < 9; ++t) {
+          for (int t = 0; t < p.ntaps; ++t) {
             const uint32_t s = bi % (uint32_t)p.b_stages;
             mbar_wait(&b_full[s], (bi / (uint32_t)p.b_stages) & 1u);
             tc_fence_after();
@@ -566,8 +570,9 @@ struct Plan {
   uint32_t region_bytes;
   size_t smem;
 };
-static bool make_plan(int H, int W, int BN, int Npad, Plan& pl) {
+static bool make_plan(int H, int W, int BN, int Npad, Plan& pl, int halo = -1) {
   const int Wp = W + 1;
+  if (halo < 0) halo = Wp + 1;
   // RB: rows per TMA box; must divide H + 1 so that a box never straddles two images. Largest divisor with <= 64 positions.
   int RB = 1;
   for (int d = 1; d <= H + 1; ++d)
@@ -576,7 +581,7 @@ static bool make_plan(int H, int W, int BN, int Npad, Plan& pl) {
   pl.RB = RB;
   pl.box_pos = RB * Wp;
   // worst case: the region starts up to box_pos - 1 positions before q_lo
-  pl.nbox = (Wp + 1 + pl.box_pos - 1 + BM + Wp + 1 + pl.box_pos - 1) / pl.box_pos;
+  pl.nbox = (halo + pl.box_pos - 1 + BM + halo + pl.box_pos - 1) / pl.box_pos;
   if (pl.nbox > MAX_BOX) return false;
   pl.region_bytes = (uint32_t)pl.nbox * pl.box_pos * 128u;
   pl.region_bytes = (pl.region_bytes + 1023u) & ~1023u;
@@ -592,12 +597,21 @@ static bool make_plan(int H, int W, int BN, int Npad, Plan& pl) {
 
 static inline int pick_bn(int Nn) { return Nn <= 64 ? 64 : 128; }
 
+// H, W: the image the POSITION space is built on (the output image of a forward pass, the dy image of a data gradient).
+// ntaps = 9: 3x3 stride-1 "same" convolution. ntaps = 1: 1x1 convolution (the residual shortcuts); a_stride = 2 samples every second
+// pixel of the (Ha x Wa) activation tensor (stride-2 forward), o_stride = 2 scatters the rows to every second pixel of the
+// (Hout x Wout) output (stride-2 data gradient, accumulate only: the other pixels receive nothing from this convolution).
 static int run(const void* planes, const void* wp, const float* bias, const float* a_amax, float* out, double* stats, int B, int H, int W, int Ca,
-               int Nn, int dgrad, int accumulate, pc_stream_t stream) {
+               int Nn, int dgrad, int accumulate, pc_stream_t stream, int ntaps = 9, int a_stride = 1, int Ha = 0, int Wa = 0, int Hout = 0,
+               int Wout = 0, int o_stride = 1) {
   const int BN = pick_bn(Nn);
   const int Npad = ceil_div(Nn, BN) * BN;
+  if (Ha == 0) { Ha = H; Wa = W; }
+  if (Hout == 0) { Hout = H; Wout = W; }
+  const int halo = ntaps == 1 ? 0 : W + 2;
   Plan pl;
-  PC_REQUIRE(make_plan(H, W, BN, Npad, pl), PC_EUNSUPPORTED, "conv_halo: image %dx%d does not fit the halo plan", H, W);
+  PC_REQUIRE(make_plan(H, W, BN, Npad, pl, halo), PC_EUNSUPPORTED, "conv_halo: image %dx%d does not fit the halo plan", H, W);
+  PC_REQUIRE(a_stride * (W + 1) <= 256 && a_stride * pl.RB <= 256, PC_EUNSUPPORTED, "conv_halo: strided box exceeds the TMA box limit");
   EncodeTiledFn enc = encode_tiled();
   PC_REQUIRE(enc != nullptr, PC_ECUDA, "conv_halo: cuTensorMapEncodeTiled is not available from this driver");
   Params p{};
@@ -615,7 +629,8 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
   p.n_items = ceil_div(p.n_mtiles, CL) * p.n_ntiles;
   // forward: tap (r, s) reads position q + (r-1) (W+1) + (s-1); data gradient: dx[q] = sum dy[q - (r-1)(W+1) - (s-1)] w[r][s]
   for (int r = 0; r < 3; ++r)
-    for (int s = 0; s < 3; ++s) p.tap_shift[r * 3 + s] = (dgrad ? -1 : 1) * ((r - 1) * p.Wp + (s - 1));
+    for (int s = 0; s < 3; ++s) p.tap_shift[r * 3 + s] = ntaps == 1 ? 0 : (dgrad ? -1 : 1) * ((r - 1) * p.Wp + (s - 1));
+  p.ntaps = ntaps; p.halo = halo; p.a_stride = a_stride; p.Hout = Hout; p.Wout = Wout; p.o_stride = o_stride;
   p.b_stages = pl.b_stages;
   p.region_bytes = pl.region_bytes;
   p.a_tx_bytes = 2u * (uint32_t)pl.nbox * (uint32_t)pl.box_pos * 128u;
@@ -623,10 +638,11 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
   p.d_box = FastDiv::make((uint32_t)p.box_pos); p.d_hp1 = FastDiv::make((uint32_t)(H + 1));
 
   CUtensorMap amap;
-  const cuuint64_t dims[5] = {(cuuint64_t)Ca, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B, 2};
-  const cuuint64_t strides[4] = {(cuuint64_t)Ca * 2, (cuuint64_t)W * Ca * 2, (cuuint64_t)H * W * Ca * 2, (cuuint64_t)B * H * W * Ca * 2};
-  const cuuint32_t box[5] = {64, (cuuint32_t)p.Wp, (cuuint32_t)p.RB, 1, 1};
-  const cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  const cuuint64_t dims[5] = {(cuuint64_t)Ca, (cuuint64_t)Wa, (cuuint64_t)Ha, (cuuint64_t)B, 2};
+  const cuuint64_t strides[4] = {(cuuint64_t)Ca * 2, (cuuint64_t)Wa * Ca * 2, (cuuint64_t)Ha * Wa * Ca * 2, (cuuint64_t)B * Ha * Wa * Ca * 2};
+  // with an element stride s the box spans s * n tensor elements and delivers n of them (every s-th)
+  const cuuint32_t box[5] = {64, (cuuint32_t)(a_stride * p.Wp), (cuuint32_t)(a_stride * p.RB), 1, 1};
+  const cuuint32_t es[5] = {1, (cuuint32_t)a_stride, (cuuint32_t)a_stride, 1, 1};
   const CUresult cr = enc(&amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<void*>(planes), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PC_REQUIRE(cr == CUDA_SUCCESS, PC_ECUDA, "conv_halo: cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
@@ -634,7 +650,7 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
   // weight-resident variant: one 64-channel chunk, one 64-channel output tile, and all nine taps' weights + one activation
   // region fit the 227 KB of shared memory
   const size_t res_smem = 2 * (size_t)pl.region_bytes + 9 * (size_t)2 * BN * 128 + sizeof(uint64_t) * 10 + 16 + sizeof(float) * 3 * (size_t)Npad + 1024;
-  const bool resident = env_int("PC_HALO_RESIDENT", 1) != 0 && BN == 64 && p.cpt == 1 && p.n_ntiles == 1 && res_smem <= 227 * 1024;
+  const bool resident = env_int("PC_HALO_RESIDENT", 1) != 0 && ntaps == 9 && BN == 64 && p.cpt == 1 && p.n_ntiles == 1 && res_smem <= 227 * 1024;
   if (resident) {
     p.cluster = CL = 1;
     p.n_items = p.n_mtiles;
@@ -690,9 +706,18 @@ using namespace pc;
 extern "C" int pc_conv_halo_supported(const PcConvGeom* g, int dgrad) {
   if (g == nullptr) return 0;
   if (!pc::halo::env_int("PC_CONV_HALO", 1)) return 0;
-  if (g->R != 3 || g->S != 3 || g->stride != 1 || g->pad != 1 || g->Ho != g->H || g->Wo != g->W) return 0;
   const int ca = dgrad ? g->Cout : g->Cin, nn = dgrad ? g->Cin : g->Cout;
   if (ca % 64 != 0 || nn % 64 != 0 || nn < 64) return 0;
+  if (g->R == 1 && g->S == 1 && g->pad == 0 && (g->stride == 1 || g->stride == 2)) {
+    // 1x1 (shortcut) convolutions: position space = the (Ho x Wo) image; PC_HALO_1X1=0 keeps them on the per-tap-gather kernel
+    if (!pc::halo::env_int("PC_HALO_1X1", 1)) return 0;
+    if ((long long)g->B * (g->Ho + 1) * (g->Wo + 1) + 4096 >= (1LL << 31) || (long long)g->B * g->H * g->W * (ca > nn ? ca : nn) >= (1LL << 31)) return 0;
+    pc::halo::Plan pl1;
+    const int bn1 = pc::halo::pick_bn(nn);
+    if (g->stride * (g->Wo + 1) > 256) return 0;
+    return pc::halo::make_plan(g->Ho, g->Wo, bn1, ceil_div(nn, bn1) * bn1, pl1, 0) && g->stride * pl1.RB <= 256 ? 1 : 0;
+  }
+  if (g->R != 3 || g->S != 3 || g->stride != 1 || g->pad != 1 || g->Ho != g->H || g->Wo != g->W) return 0;
   // Measured per layer at 256 views (profiles/r2_halo_bench.md): 64ch 131 -> 58 us, 128ch 98 -> 77, 512ch 119 -> 107, but 256ch
   // (5x13 images) 76 -> 88: with 4 chunks x 288 KB of streamed weights per tile and only 168 position tiles the per-tap-gather
   // kernel's two resident... one-tile-per-CTA grid balances better. PC_HALO_ALL=1 forces the halo engine everywhere.
@@ -708,6 +733,9 @@ extern "C" int pc_conv_fwd_halo(const void* x_planes, const void* wp, const floa
                                 pc_stream_t stream) {
   PC_REQUIRE(x_planes && wp && g && y, PC_EINVAL, "pc_conv_fwd_halo: null pointer");
   if (!pc_conv_halo_supported(g, 0)) return PC_EUNSUPPORTED;
+  if (g->R == 1)
+    return pc::halo::run(x_planes, wp, bias, nullptr, y, stats, g->B, g->Ho, g->Wo, g->Cin, g->Cout, 0, 0, stream, 1, g->stride, g->H, g->W, g->Ho,
+                         g->Wo, 1);
   return pc::halo::run(x_planes, wp, bias, nullptr, y, stats, g->B, g->H, g->W, g->Cin, g->Cout, 0, 0, stream);
 }
 
@@ -715,5 +743,11 @@ extern "C" int pc_conv_dgrad_halo(const void* dy_planes, const void* wp, const P
                                   pc_stream_t stream) {
   PC_REQUIRE(dy_planes && wp && g && dx && dy_amax, PC_EINVAL, "pc_conv_dgrad_halo: null pointer");
   if (!pc_conv_halo_supported(g, 1)) return PC_EUNSUPPORTED;
+  if (g->R == 1) {
+    // dx[b, s ho, s wo, :] (+)= dy[b, ho, wo, :] W^T; with stride 2 the remaining pixels get no contribution, so only accumulation is defined here
+    if (g->stride != 1 && !accumulate) return PC_EUNSUPPORTED;
+    return pc::halo::run(dy_planes, wp, nullptr, dy_amax, dx, nullptr, g->B, g->Ho, g->Wo, g->Cout, g->Cin, 1, accumulate, stream, 1, 1, g->Ho, g->Wo,
+                         g->H, g->W, g->stride);
+  }
   return pc::halo::run(dy_planes, wp, nullptr, dy_amax, dx, nullptr, g->B, g->H, g->W, g->Cout, g->Cin, 1, accumulate, stream);
 }

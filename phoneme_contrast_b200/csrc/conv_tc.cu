@@ -835,7 +835,8 @@ extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias,
 extern "C" int pc_conv_dgrad_tc(const float* dy, const void* wp, const PcConvGeom* g, float* dx, int accumulate, int prec,
                                 const float* dy_amax, int dy_presplit, pc_stream_t stream) {
   if (!pc_conv_tc_supported(g, 1, prec)) return PC_EUNSUPPORTED;
-  if (prec == PC_PREC_FP16X2 && dy_presplit && dy_amax != nullptr && g_dbg == nullptr && pc_conv_halo_supported(g, 1))
+  if (prec == PC_PREC_FP16X2 && dy_presplit && dy_amax != nullptr && g_dbg == nullptr && pc_conv_halo_supported(g, 1) &&
+      (g->R != 1 || g->stride == 1 || accumulate))      // a strided 1x1 data gradient only touches every second pixel: accumulate-only
     return pc_conv_dgrad_halo(dy, wp, g, dx, accumulate, dy_amax, stream);
   Params p{};
   p.A = dy; p.Bp = (const unsigned char*)wp; p.C = dx; p.a_amax = dy_amax;

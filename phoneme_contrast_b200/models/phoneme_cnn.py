@@ -433,10 +433,13 @@ def _deep_backward(net, s, demb, grads, training=True):
         wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], grads[blk.conv1.bias], prec, m1, gps)
         if r["proj"]:
             wgrad(xin_w, dysc, r["gs"], xf_w, grads[convs.weight], grads[convs.bias], prec, ms, gps)
-            dxin = ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], prec=r["cws"].prec_d, dy_amax=ms, dy_presplit=gps)
+            # conv1's data gradient writes every pixel of dxin; the strided 1x1 shortcut then adds into the pixels it reads
+            # (csrc/conv_halo.cu runs it as an accumulate-only scatter to every second pixel)
+            dxin = ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], prec=r["cw1"].prec_d, dy_amax=m1, dy_presplit=gps)
+            ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], out=dxin, accumulate=True, prec=r["cws"].prec_d, dy_amax=ms, dy_presplit=gps)
         else:
             dxin = dysc                                        # identity shortcut: d(out)/d(xin) passes g through
-        ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d, dy_amax=m1, dy_presplit=gps)
+            ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d, dy_amax=m1, dy_presplit=gps)
         dout = dxin
         if i == len(s.blocks) - 1:
             if net._split_backward:

@@ -89,3 +89,67 @@ def test_halo_dgrad(case, cluster, monkeypatch):
     acc = base.clone()
     ops.conv_dgrad(dy_ps, cw.wd, g, out=acc, accumulate=True, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
     assert float((acc.double() - (base.double() + ref)).abs().max()) <= 1e-5 * scale + 1e-6 * float(base.abs().max())
+
+
+CASES_1X1 = [  # B, H, W, Cin, Cout, stride  (the three cnn_deep projection shortcuts + a stride-1 case + ragged sizes)
+    (4, 20, 51, 64, 128, 2),
+    (6, 10, 26, 128, 256, 2),
+    (9, 5, 13, 256, 512, 2),
+    (3, 10, 26, 64, 64, 1),
+    (2, 7, 9, 64, 128, 2),
+    (33, 20, 51, 64, 128, 2),
+]
+
+
+@pytest.mark.parametrize("case", CASES_1X1)
+def test_halo_1x1_forward_and_dgrad(case, monkeypatch):
+    """1x1 (shortcut) convolutions on the halo engine: strided TMA boxes sample every second pixel in the forward pass, the data
+    gradient scatters its rows to every second pixel of an existing tensor. Against fp64 and against the per-tap-gather kernel."""
+    from phoneme_contrast_b200 import _lib as L
+    from phoneme_contrast_b200 import ops
+    import ctypes as C
+    B, H, W, Cin, Cout, stride = case
+    g = ops.conv_geom(B, H, W, Cin, Cout, 1, stride, 0)
+    gen = torch.Generator(device=DEV).manual_seed(B * 31 + Cin + Cout + stride)
+    x = torch.randn(B, H, W, Cin, device=DEV, generator=gen)
+    w = torch.randn(Cout, Cin, 1, 1, device=DEV, generator=gen) * (2.0 / Cin) ** 0.5
+    bias = torch.randn(Cout, device=DEV, generator=gen)
+    cw = ops.ConvWeights(w, g, L.PREC_FP16X2)
+    planes = ops.bn_act_split(x)
+    assert L.lib().pc_conv_halo_supported(C.byref(g), 0) == 1
+    st = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    y = ops.conv_fwd(planes, cw.wf, bias, g, dict(presplit=True), st, cw.prec_f)
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.conv2d(x.permute(0, 3, 1, 2).double(), w.double(), bias.double(), stride=stride).permute(0, 2, 3, 1)
+    assert tuple(y.shape) == tuple(ref.shape)
+    scale = float(ref.abs().max())
+    assert float((y.double() - ref).abs().max()) <= 5e-6 * scale
+    np.testing.assert_allclose(st[0].cpu().numpy(), ref.sum(dim=(0, 1, 2)).cpu().numpy(), rtol=2e-5, atol=2e-4 * scale)
+    np.testing.assert_allclose(st[1].cpu().numpy(), (ref ** 2).sum(dim=(0, 1, 2)).cpu().numpy(), rtol=2e-5)
+    monkeypatch.setenv("PC_HALO_1X1", "0")
+    assert L.lib().pc_conv_halo_supported(C.byref(g), 0) == 0
+    y0 = ops.conv_fwd(planes, cw.wf, bias, g, dict(presplit=True), None, cw.prec_f)
+    assert float((y - y0).abs().max()) <= 2e-6 * scale
+    monkeypatch.setenv("PC_HALO_1X1", "1")
+
+    # data gradient: accumulate into an existing dx
+    Ho, Wo = g.Ho, g.Wo
+    yconv = torch.randn(B, Ho, Wo, Cout, device=DEV, generator=gen)
+    dout = torch.randn(B, Ho, Wo, Cout, device=DEV, generator=gen) * 1e-6
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV)
+    st2 = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    st2[0] = yconv.double().sum((0, 1, 2)); st2[1] = (yconv.double() ** 2).sum((0, 1, 2))
+    co = ops.bn_finalize(st2, B * Ho * Wo, bn, True)
+    a0, a1 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    dy, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a0)
+    dy_ps, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a1, planes=True)
+    refd = torch.nn.functional.conv_transpose2d(dy.permute(0, 3, 1, 2).double(), w.double(), stride=stride,
+                                                output_padding=(H - ((Ho - 1) * stride + 1), W - ((Wo - 1) * stride + 1))).permute(0, 2, 3, 1)
+    dscale = float(refd.abs().max())
+    base = torch.randn(B, H, W, Cin, device=DEV, generator=gen) * dscale
+    acc = base.clone()
+    ops.conv_dgrad(dy_ps, cw.wd, g, out=acc, accumulate=True, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+    assert float((acc.double() - (base.double() + refd)).abs().max()) <= 1e-5 * dscale + 1e-6 * float(base.abs().max())
+    # without accumulation a strided 1x1 gradient must still define every pixel (the per-tap-gather kernel handles it)
+    dx = ops.conv_dgrad(dy_ps, cw.wd, g, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+    assert float((dx.double() - refd).abs().max()) <= 1e-5 * dscale
