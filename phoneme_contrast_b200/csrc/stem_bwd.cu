@@ -240,10 +240,20 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
       mu0 = *reinterpret_cast<const float4*>(p.mean + 8 * cj); mu1 = *reinterpret_cast<const float4*>(p.mean + 8 * cj + 4);
       is0 = *reinterpret_cast<const float4*>(p.invstd + 8 * cj); is1 = *reinterpret_cast<const float4*>(p.invstd + 8 * cj + 4);
     }
-    const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
-    const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
-    const float muv[8] = {mu0.x, mu0.y, mu0.z, mu0.w, mu1.x, mu1.y, mu1.z, mu1.w};
-    const float isv[8] = {is0.x, is0.y, is0.z, is0.w, is1.x, is1.y, is1.z, is1.w};
+    // xhat at the argmax pixel from the pooled value: bn(y) = p0  =>  xhat = ((p0 - shift) / scale - mean) * invstd = xk1 * p0 + xk0
+    float xk1[8], xk0[8];
+    {
+      const float scv[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+      const float shv[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+      const float muv[8] = {mu0.x, mu0.y, mu0.z, mu0.w, mu1.x, mu1.y, mu1.z, mu1.w};
+      const float isv[8] = {is0.x, is0.y, is0.z, is0.w, is1.x, is1.y, is1.z, is1.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float inv = scv[q] != 0.f ? 1.f / scv[q] : 0.f;
+        xk1[q] = inv * isv[q];
+        xk0[q] = scv[q] != 0.f ? (-shv[q] * inv - muv[q]) * isv[q] : 0.f;
+      }
+    }
     float rs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int tap_off[8];                    // offset of tap 8 j + q inside the staged window, -1 for the padding taps 49..63
 #pragma unroll
@@ -259,50 +269,66 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
       const int rq_ = row / 9, ra = row - rq_ * 9;
       row_base[i] = (ra / 3) * RG_LD + 2 * min(rq_, QPB - 1) + ra % 3;
     }
-    for (int it = group; it < n_my; it += NGROUPS) {
-      const int s = it % NSTAGE;
-      const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+    // Global loads of a K block -- its image window and its S unit (dpool, p0, argmax) -- are issued ONE block ahead into registers:
+    // measured, a group otherwise sits out two full DRAM latencies per block (window -> barrier -> patch build; dpool / p0 -> S).
+    struct Pre {
+      float rv[3];
+      float4 d0, d1, a0, a1;
+      uint2 am;
+      int n_valid;
+    };
+    auto issue = [&](int it, Pre& r) {
       uint32_t bph, seg, b, php;
       p.d_seg.divmod((uint32_t)(blk0 + it), bph, seg);
       p.d_hp.divmod(bph, b, php);
       const int pw0 = (int)seg * QPB;
-      const int n_valid = min(QPB, p.Wp - pw0);
-      // ---------------- stage the image window rows 2 ph - 4 .. 2 ph + 4, columns 2 pw0 - 4 .. 2 pw0 + 31 (zero outside the image)
-      {
-        const float* img = p.x + (size_t)b * p.H * p.W;
-        const int h0 = 2 * (int)php - 4, w0 = 2 * pw0 - 4;
-        float rv[3];
+      r.n_valid = min(QPB, p.Wp - pw0);
+      // image window rows 2 ph - 4 .. 2 ph + 4, columns 2 pw0 - 4 .. 2 pw0 + 31 (zero outside the image)
+      const float* img = p.x + (size_t)b * p.H * p.W;
+      const int h0 = 2 * (int)php - 4, w0 = 2 * pw0 - 4;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int e = gt + 128 * k;
-          const int rr = e / RG_W, cc = e - rr * RG_W;
-          const int hi = h0 + rr, wi = w0 + cc;
-          rv[k] = (e < RG_H * RG_W && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W) ? img[hi * p.W + wi] : 0.f;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");      // the previous block's patch reads are done
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int e = gt + 128 * k;
-          const int rr = e / RG_W, cc = e - rr * RG_W;
-          if (e < RG_H * RG_W) reg[rr * RG_LD + cc] = rv[k];
-        }
+      for (int k = 0; k < 3; ++k) {
+        const int e = gt + 128 * k;
+        const int rr = e / RG_W, cc = e - rr * RG_W;
+        const int hi = h0 + rr, wi = w0 + cc;
+        r.rv[k] = (e < RG_H * RG_W && (unsigned)hi < (unsigned)p.H && (unsigned)wi < (unsigned)p.W) ? img[hi * p.W + wi] : 0.f;
       }
-      // ---------------- S unit: loads first (latency), stores after the slot is free
-      uint4 hh = make_uint4(0u, 0u, 0u, 0u), ll = hh;
-      uint2 am = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-      if (gt < 112 && ql < n_valid) {
+      r.d0 = r.d1 = r.a0 = r.a1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      r.am = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+      if (gt < 112 && ql < r.n_valid) {
         const size_t o = (((size_t)b * p.Hp + php) * p.Wp + pw0 + ql) * CO + 8 * cj;
-        const float4 d0 = *reinterpret_cast<const float4*>(p.dpool + o), d1 = *reinterpret_cast<const float4*>(p.dpool + o + 4);
-        const float4 a0 = *reinterpret_cast<const float4*>(p.p0 + o), a1 = *reinterpret_cast<const float4*>(p.p0 + o + 4);
-        am = *reinterpret_cast<const uint2*>(p.argmax + o);
-        const float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        r.d0 = *reinterpret_cast<const float4*>(p.dpool + o); r.d1 = *reinterpret_cast<const float4*>(p.dpool + o + 4);
+        r.a0 = *reinterpret_cast<const float4*>(p.p0 + o); r.a1 = *reinterpret_cast<const float4*>(p.p0 + o + 4);
+        r.am = *reinterpret_cast<const uint2*>(p.argmax + o);
+      }
+    };
+    Pre cur;
+    if (group < n_my) issue(group, cur);
+    for (int it = group; it < n_my; it += NGROUPS) {
+      const int s = it % NSTAGE;
+      const uint32_t ph = (uint32_t)(it / NSTAGE) & 1u;
+      Pre nxt = cur;
+      if (it + NGROUPS < n_my) issue(it + NGROUPS, nxt);
+      const int n_valid = cur.n_valid;
+      // ---------------- stage the image window
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");      // the previous block's patch reads are done
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int e = gt + 128 * k;
+        const int rr = e / RG_W, cc = e - rr * RG_W;
+        if (e < RG_H * RG_W) reg[rr * RG_LD + cc] = cur.rv[k];
+      }
+      // ---------------- S unit
+      uint4 hh = make_uint4(0u, 0u, 0u, 0u), ll = hh;
+      const uint2 am = cur.am;
+      if (gt < 112 && ql < n_valid) {
+        const float d[8] = {cur.d0.x, cur.d0.y, cur.d0.z, cur.d0.w, cur.d1.x, cur.d1.y, cur.d1.z, cur.d1.w};
+        const float a[8] = {cur.a0.x, cur.a0.y, cur.a0.z, cur.a0.w, cur.a1.x, cur.a1.y, cur.a1.z, cur.a1.w};
         float dz[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           dz[q] = a[q] > 0.f ? d[q] : 0.f;                                   // ReLU gate: pooled output > 0
-          // xhat at the argmax pixel from the pooled value: bn(y) = p0  =>  xhat = ((p0 - shift) / scale - mean) * invstd
-          const float xh = scv[q] != 0.f ? (__fdividef(a[q] - shv[q], scv[q]) - muv[q]) * isv[q] : 0.f;
+          const float xh = fmaf(a[q], xk1[q], xk0[q]);
           rs[q] += dz[q];
           rq[q] = fmaf(dz[q], xh, rq[q]);
           dz[q] *= g_scale;
@@ -310,6 +336,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
         split_f16x2(dz[0], dz[1], hh.x, ll.x); split_f16x2(dz[2], dz[3], hh.y, ll.y);
         split_f16x2(dz[4], dz[5], hh.z, ll.z); split_f16x2(dz[6], dz[7], hh.w, ll.w);
       }
+      cur = nxt;
       asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");        // staged window visible to the group
       mbar_wait(&empty[s], ph ^ 1u);
       unsigned char* a_hi = tiles + (size_t)s * STAGE;
