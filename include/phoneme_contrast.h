@@ -285,7 +285,12 @@ int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, int H, int W,
 int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
                         const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
                         const uint8_t* argmax, const double* sums, float* dy, float* dgamma, float* dbeta,
-                        float* dy_amax, const float* maxes, void* dy_planes, pc_stream_t stream);
+                        float* dy_amax, const float* maxes, void* dy_planes, const double* y_stats, float* db_conv,
+                        pc_stream_t stream);
+/* db_conv (may be NULL; with y_stats = the [2][C] fp64 sums of y the forward pass accumulated): gradient of the bias of the
+ * convolution that produced y, i.e. sum_p dy, in closed form from the per-channel constants -- no pass over dy. The bias is
+ * absorbed by the batch mean, so this is the fp32 round-off residual the reference reports there (csrc/bn_act.cu:
+ * bias_grad_closed_form); pc_conv_wgrad can then be called with db = NULL and skips its column-sum kernel. */
 /* dy_planes (may be NULL): write dy (also) in tensor-core operand form -- fp16 hi | lo planes (pc_bn_act_split layout) of
  * dy * 2^k, with 2^k derived from a bound of |dy| computed from `maxes` and `sums`; the bound is stored in dy_amax (which
  * pc_conv_dgrad / pc_conv_wgrad with dy_presplit != 0 read to undo the scale). `dy` itself may then be NULL. */
@@ -304,8 +309,10 @@ int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, const float* y
                              const float* sc_scale, const float* mean_s, const float* invstd_s, const double* sums_s,
                              int64_t n_pix, int C, float* dy2, float* dysc_or_dx, float* dgamma2, float* dbeta2,
                              float* dgamma_s, float* dbeta_s, float* dy2_amax, float* dysc_amax, const float* maxes,
-                             void* dy2_planes, void* dysc_planes, pc_stream_t stream);
-/* maxes: float[3] (max|g|, max|xhat2|, max|xhat_s|) from the reduce pass; *_planes as dy_planes of pc_bn_act_bwd_apply. */
+                             void* dy2_planes, void* dysc_planes, const double* y2_stats, float* db2, const double* ysc_stats,
+                             float* db_s, pc_stream_t stream);
+/* maxes: float[3] (max|g|, max|xhat2|, max|xhat_s|) from the reduce pass; *_planes as dy_planes of pc_bn_act_bwd_apply;
+ * db2 / db_s (may be NULL) with y2_stats / ysc_stats: bias gradients of conv2 / the shortcut convolution as db_conv there. */
 
 /* SpatialAttention + AdaptiveAvgPool2d(1): pooled[b,c] = mean_p a[b,p,c] * sigmoid(w.a[b,p,:] + b0)
  * (phoneme_cnn.py:134-143,117-118). w == NULL: plain mean (use_attention False). gate [B,HW] saved for backward. */

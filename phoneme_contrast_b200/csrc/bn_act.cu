@@ -317,6 +317,18 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict
   block_channel_reduce<2>(acc, C4, c4_off, dst, sh);
 }
 
+// Gradient of the bias of the convolution that produced y (= sum over pixels of dy) WITHOUT a pass over dy. With the per-channel
+// constants the apply kernels use -- a = fl(sum_dz / M), b = fl(sum_dz_xhat / M), mean and invstd in fp32 --
+//     sum_p dy = scale * ( (sum_dz - M a) - b * sum_p xhat ),     sum_p xhat = invstd * (sum_p y - M mean),
+// i.e. the two residuals left by rounding the batch mean and sum_dz / M to fp32: the bias is absorbed by the batch mean, its
+// gradient is analytically zero and the reference reports fp32 round-off of this size there. sum_p y is the fp64 statistic the
+// forward pass accumulated (`y_stats`). Replaces a column-sum kernel over every gradient tensor (125 us per cnn_deep step).
+__device__ __forceinline__ float bias_grad_closed_form(float scale, float mean, float invstd, double sum_dz, float a, float b, double sum_y,
+                                                       double M) {
+  const double sum_xhat = (double)invstd * (sum_y - M * (double)mean);
+  return (float)((double)scale * ((sum_dz - M * (double)a) - (double)b * sum_xhat));
+}
+
 template <int POOL>
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y, int B, int H, int W, int C, int Ho,
@@ -324,7 +336,8 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
                         const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ drop,
                         const uint8_t* __restrict__ argmax, const double* __restrict__ sums, float* __restrict__ dy,
                         float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dy_amax,
-                        const float* __restrict__ maxes, unsigned char* __restrict__ dy_planes) {
+                        const float* __restrict__ maxes, unsigned char* __restrict__ dy_planes,
+                        const double* __restrict__ y_stats, float* __restrict__ db_conv) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh_max[9];
@@ -348,6 +361,11 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
     }
   }
   const float sv[4] = PC_F4_ARR(s), muv[4] = PC_F4_ARR(mu), isv[4] = PC_F4_ARR(is);
+  if (blockIdx.x == 0 && threadIdx.x < C4 && db_conv != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      db_conv[c + q] = bias_grad_closed_form(sv[q], muv[q], isv[q], sums[c + q], sdz[q] * invM, sdzx[q] * invM, y_stats[c + q], (double)npix);
+  }
   // Pre-split output: dy is (also) written as fp16 hi | lo planes scaled by a power of two. The scale must be known before
   // the first element is written, so it comes from a BOUND of |dy| built from the reduce pass (max |dz|, max |xhat|, the
   // per-channel sums): |dy| <= |scale_c| (max|dz| + |sum dz_c| / M + max|xhat| |sum dz xhat_c| / M). Every block derives
@@ -477,7 +495,9 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
                              float* __restrict__ dysc, float* __restrict__ dgamma2, float* __restrict__ dbeta2,
                              float* __restrict__ dgamma_s, float* __restrict__ dbeta_s, float* __restrict__ dy2_amax,
                              float* __restrict__ dysc_amax, const float* __restrict__ maxes,
-                             unsigned char* __restrict__ dy2_planes, unsigned char* __restrict__ dysc_planes) {
+                             unsigned char* __restrict__ dy2_planes, unsigned char* __restrict__ dysc_planes,
+                             const double* __restrict__ y2_stats, float* __restrict__ db2, const double* __restrict__ ysc_stats,
+                             float* __restrict__ db_s) {
   pdl_trigger();
   pdl_wait();
   __shared__ float sh_max[9];
@@ -507,6 +527,15 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
   }
   const float s2v[4] = PC_F4_ARR(s2), mu2v[4] = PC_F4_ARR(mu2), is2v[4] = PC_F4_ARR(is2);
   const float ssv[4] = PC_F4_ARR(ss), musv[4] = PC_F4_ARR(mus), issv[4] = PC_F4_ARR(iss);
+  if (blockIdx.x == 0 && threadIdx.x < C4) {        // conv bias gradients in closed form (see bias_grad_closed_form)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (db2 != nullptr)
+        db2[c + q] = bias_grad_closed_form(s2v[q], mu2v[q], is2v[q], sums2[c + q], sg[q] * invM, sgx2[q] * invM, y2_stats[c + q], (double)n_pix);
+      if (proj && db_s != nullptr)
+        db_s[c + q] = bias_grad_closed_form(ssv[q], musv[q], issv[q], sums2[c + q], sg[q] * invM, sgxs[q] * invM, ysc_stats[c + q], (double)n_pix);
+    }
+  }
   // pre-split outputs: same scheme as bn_act_bwd_apply_kernel (power-of-two scale from a bound of |dy|, published in *_amax)
   float pscale2 = 1.f, pscales = 1.f;
   if (dy2_planes != nullptr || dysc_planes != nullptr) {
@@ -720,8 +749,10 @@ extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, in
 extern "C" int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,
                                    const float* shift, const float* mean, const float* invstd, const float* drop, int pool,
                                    const uint8_t* argmax, const double* sums, float* dy, float* dgamma, float* dbeta,
-                                   float* dy_amax, const float* maxes, void* dy_planes, pc_stream_t stream) {
+                                   float* dy_amax, const float* maxes, void* dy_planes, const double* y_stats, float* db_conv,
+                                   pc_stream_t stream) {
   PC_REQUIRE(dout && y && scale && shift && mean && invstd && sums && (dy || dy_planes), PC_EINVAL, "pc_bn_act_bwd_apply: null pointer");
+  PC_REQUIRE(db_conv == nullptr || y_stats != nullptr, PC_EINVAL, "pc_bn_act_bwd_apply: db_conv needs the forward statistics y_stats");
   PC_REQUIRE(dy_planes == nullptr || (maxes != nullptr && dy_amax != nullptr), PC_EINVAL,
              "pc_bn_act_bwd_apply: dy_planes needs the maxes of the reduce pass and a dy_amax slot");
   PC_CHECK_C4("pc_bn_act_bwd_apply", C);
@@ -730,9 +761,9 @@ extern "C" int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int
   pool_out_dims(H, W, pool, &Ho, &Wo);
   const long long items = (long long)B * H * W * (C / 4);
   const int grid = ew_grid(items, 256 * 2);
-  if (pool == 0) launch_pdl((bn_act_bwd_apply_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes));
-  else if (pool == 2) launch_pdl((bn_act_bwd_apply_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes));
-  else launch_pdl((bn_act_bwd_apply_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes));
+  if (pool == 0) launch_pdl((bn_act_bwd_apply_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes), y_stats, db_conv);
+  else if (pool == 2) launch_pdl((bn_act_bwd_apply_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes), y_stats, db_conv);
+  else launch_pdl((bn_act_bwd_apply_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes), y_stats, db_conv);
   PC_LAUNCH_CHECK("bn_act_bwd_apply_kernel");
   return PC_OK;
 }
@@ -766,16 +797,18 @@ extern "C" int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, con
                                         const double* sums_s, int64_t n_pix, int C, float* dy2, float* dysc_or_dx,
                                         float* dgamma2, float* dbeta2, float* dgamma_s, float* dbeta_s, float* dy2_amax,
                                         float* dysc_amax, const float* maxes, void* dy2_planes, void* dysc_planes,
-                                        pc_stream_t stream) {
+                                        const double* y2_stats, float* db2, const double* ysc_stats, float* db_s, pc_stream_t stream) {
   PC_REQUIRE(dout && out && y2 && scale2 && mean2 && invstd2 && sums2 && (dy2 || dy2_planes) && (dysc_or_dx || dysc_planes) && n_pix > 0,
              PC_EINVAL, "pc_bn_add_relu_bwd_apply: bad arguments");
+  PC_REQUIRE((db2 == nullptr || y2_stats != nullptr) && (db_s == nullptr || ysc_stats != nullptr), PC_EINVAL,
+             "pc_bn_add_relu_bwd_apply: db2 / db_s need the forward statistics of y2 / ysc");
   PC_REQUIRE((dy2_planes == nullptr || (maxes && dy2_amax)) && (dysc_planes == nullptr || (maxes && dysc_amax)), PC_EINVAL,
              "pc_bn_add_relu_bwd_apply: *_planes need the maxes of the reduce pass and the matching *_amax slot");
   PC_REQUIRE(sc_scale == nullptr || (ysc && mean_s && invstd_s && sums_s), PC_EINVAL, "pc_bn_add_relu_bwd_apply: shortcut pointers");
   PC_CHECK_C4("pc_bn_add_relu_bwd_apply", C);
   launch_pdl(bn_add_relu_bwd_apply_kernel, dim3(ew_grid(n_pix * (C / 4), 256 * 2)), dim3(256), 0, stream, dout, out, y2, scale2, mean2, invstd2, sums2, ysc, sc_scale, mean_s, invstd_s, sums_s, n_pix, C, dy2, dysc_or_dx,
       dgamma2, dbeta2, dgamma_s, dbeta_s, dy2_amax, dysc_amax, maxes, static_cast<unsigned char*>(dy2_planes),
-      static_cast<unsigned char*>(dysc_planes));
+      static_cast<unsigned char*>(dysc_planes), y2_stats, db2, ysc_stats, db_s);
   PC_LAUNCH_CHECK("bn_add_relu_bwd_apply_kernel");
   return PC_OK;
 }

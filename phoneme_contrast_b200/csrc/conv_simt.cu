@@ -388,6 +388,39 @@ conv_wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int R,
   }
 }
 
+
+// The same reduction for the layers with FEW splits and MANY outputs (256- / 512-channel layers: 2 .. 8 splits, up to 2.4 M weights),
+// where the kernel above is bound by its scattered 4-byte OIHW stores (one 32-byte sector each). Block = 32 output channels x 8
+// input channels x all taps: partial rows are read as 128-byte segments, the tile is transposed in shared memory and every output
+// channel's run of 8 * taps consecutive OIHW floats leaves as one segment. No bias row (db comes from the BatchNorm backward).
+__global__ void __launch_bounds__(256)
+conv_wgrad_reduce_t_kernel(const float* __restrict__ partial, int n_splits, int taps, int Cin, int Cout, float* __restrict__ dw) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float tile[32][8 * 9 + 1];
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 8;
+  const int K = taps * Cin, rows = taps * 8;
+  const size_t stride = (size_t)(K + 1) * Cout;
+  for (int item = threadIdx.x; item < rows * 8; item += 256) {
+    const int row = item >> 3, f4 = item & 7;
+    const int tap = row >> 3, c = row & 7;
+    const float* src = partial + (size_t)(tap * Cin + c0 + c) * Cout + n0 + 4 * f4;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 4
+    for (int sp = 0; sp < n_splits; ++sp) {
+      const float4 a = *reinterpret_cast<const float4*>(src + (size_t)sp * stride);
+      s0 += (double)a.x; s1 += (double)a.y; s2 += (double)a.z; s3 += (double)a.w;
+    }
+    const int j = c * taps + tap;
+    tile[4 * f4 + 0][j] = (float)s0; tile[4 * f4 + 1][j] = (float)s1; tile[4 * f4 + 2][j] = (float)s2; tile[4 * f4 + 3][j] = (float)s3;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * rows; i += 256) {
+    const int n = i / rows, j = i - n * rows;
+    dw[((size_t)(n0 + n) * Cin + c0) * taps + j] = tile[n][j];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ stem (Cin == 1)
 // y[b,h,w,n] = bias[n] + sum_{r,s} x[b,h+r-p,w+s-p] * w[n][r][s]; lane = output channel (coalesced NHWC store),
 // each warp walks a strip of pixels; weights for the lane's channel(s) live in registers.
@@ -570,6 +603,12 @@ conv_stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy
 
 void launch_wgrad_reduce(const float* partial, int n_splits, int R, int S, int Cin, int Cout, float* dw, float* db, pc_stream_t stream,
                          const float* bias_partial, int n_bias) {
+  if (db == nullptr && bias_partial == nullptr && dw != nullptr && n_splits <= 8 && R * S <= 9 && Cin % 8 == 0 && Cout % 32 == 0 &&
+      (long long)R * S * Cin * Cout >= 200000) {
+    launch_pdl(conv_wgrad_reduce_t_kernel, dim3(Cout / 32, Cin / 8), dim3(256), 0, stream, partial, n_splits, R * S, Cin, Cout, dw);
+    count_launch();
+    return;
+  }
   const long long total4 = ((long long)(R * S * Cin + 1) * Cout) >> 2;
   launch_pdl(conv_wgrad_reduce_kernel, dim3(ceil_div(total4, 32)), dim3(256), 0, stream, partial, n_splits, R, S, Cin, Cout, dw, db,
              bias_partial, n_bias);

@@ -626,6 +626,11 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
     PC_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
     return PC_OK;
   }
+  if (db == nullptr) {   // the caller gets the bias gradient elsewhere (closed form of the BatchNorm backward, csrc/bn_act.cu): no column sums
+    launch_wgrad_reduce(p.partial, sp, g->R, g->S, g->Cin, g->Cout, dw_oihw, nullptr, stream);
+    PC_LAUNCH_CHECK("conv_wgrad_reduce_kernel");
+    return PC_OK;
+  }
   float* cs = p.partial + (size_t)sp * (size_t)(p.K + 1) * g->Cout;
   const int cs_ctas = kNumSMs * 2;
   if (dy_presplit)

@@ -336,7 +336,6 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
         split_f16x2(dz[0], dz[1], hh.x, ll.x); split_f16x2(dz[2], dz[3], hh.y, ll.y);
         split_f16x2(dz[4], dz[5], hh.z, ll.z); split_f16x2(dz[6], dz[7], hh.w, ll.w);
       }
-      cur = nxt;
       asm volatile("bar.sync %0, 128;" ::"r"(2 + group) : "memory");        // staged window visible to the group
       mbar_wait(&empty[s], ph ^ 1u);
       unsigned char* a_hi = tiles + (size_t)s * STAGE;
@@ -382,6 +381,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
+      cur = nxt;        // (the register moves wait for the prefetched loads: keep them behind this block's tile build)
     }
     // ---------------- per-channel sums of this CTA
     if (gt < 112) {

@@ -165,17 +165,29 @@ class _WgradLane:
             self.main = torch.cuda.current_stream()
 
     def __call__(self, x, dy, g, xform, dw, db, prec, amax=None, dy_presplit=False):
+        # db is None: the bias gradient was already produced by the BatchNorm backward that wrote dy (closed form, _bias_from_bn)
         if not self.enabled:
-            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax, dy_presplit)
+            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax, dy_presplit, want_db=db is not None)
             return
         self.keep.extend((x, dy))
         self.side.wait_stream(self.main)
         with torch.cuda.stream(self.side):
-            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax, dy_presplit)
+            ops.conv_wgrad(x, dy, g, xform, dw, db, prec, amax, dy_presplit, want_db=db is not None)
 
     def join(self):
         if self.enabled:
             self.main.wait_stream(self.side)
+
+
+def _bias_from_bn(co, grads, bias):
+    """(db_conv for the BatchNorm backward, db for the weight-gradient call): a convolution followed by a train-mode BatchNorm gets
+    its bias gradient -- analytically zero, fp32 round-off in the reference -- in closed form from the BatchNorm backward
+    (csrc/bn_act.cu: bias_grad_closed_form) and its weight-gradient call skips the column sums of dy."""
+    if bias is None:
+        return None, None
+    if getattr(co, "stats", None) is not None:
+        return grads[bias], None
+    return None, grads[bias]
 
 
 def _head(net, s, a, training):
@@ -253,12 +265,14 @@ def _small_backward(net, s, demb, grads, training=True):
         convA, bnA, convB, bnB = blocks[b][0], blocks[b][1], blocks[b][3], blocks[b][4]
         ly = s.layers[b]
         mB, mA = amax.take(), amax.take()
-        dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias], mB)
+        dbB_bn, dbB_w = _bias_from_bn(ly["coB"], grads, convB.bias)
+        dbA_bn, dbA_w = _bias_from_bn(ly["coA"], grads, convA.bias)
+        dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias], mB, db_conv=dbB_bn)
         xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
-        wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], grads[convB.bias], prec, mB)
+        wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], dbB_w, prec, mB)
         dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d, dy_amax=mB)
-        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA)
-        wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], grads[convA.bias], prec, mA)
+        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA, db_conv=dbA_bn)
+        wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], dbA_w, prec, mA)
         if b > 0:
             dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d, dy_amax=mA)
         if b == 2:
@@ -399,12 +413,14 @@ def _deep_backward(net, s, demb, grads, training=True):
         r = s.blocks[i]
         m2, m1, ms = amax.take(), amax.take(), amax.take()
         if r.get("plain"):
-            dy2, _, _ = ops.bn_act_bwd(dout, r["y2"], r["c2"], 0, s.drop[i], None, grads[blk[4].weight], grads[blk[4].bias], m2, zp=zp)
+            db2_bn, db2_w = _bias_from_bn(r["c2"], grads, blk[3].bias)
+            db1_bn, db1_w = _bias_from_bn(r["c1"], grads, blk[0].bias)
+            dy2, _, _ = ops.bn_act_bwd(dout, r["y2"], r["c2"], 0, s.drop[i], None, grads[blk[4].weight], grads[blk[4].bias], m2, zp=zp, db_conv=db2_bn)
             xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True)
-            wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk[3].weight], grads[blk[3].bias], prec, m2)
+            wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk[3].weight], db2_w, prec, m2)
             dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2)
-            dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, None, None, grads[blk[1].weight], grads[blk[1].bias], m1, zp=zp)
-            wgrad(r["xin"], dy1, r["g1"], None, grads[blk[0].weight], grads[blk[0].bias], prec, m1)
+            dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, None, None, grads[blk[1].weight], grads[blk[1].bias], m1, zp=zp, db_conv=db1_bn)
+            wgrad(r["xin"], dy1, r["g1"], None, grads[blk[0].weight], db1_w, prec, m1)
             dout = ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], prec=r["cw1"].prec_d, dy_amax=m1)
             if i == len(s.blocks) - 1:
                 if net._split_backward:
@@ -416,23 +432,27 @@ def _deep_backward(net, s, demb, grads, training=True):
         # engine, the BatchNorm backward writes dy only as scaled fp16 hi | lo planes and the convolutions gather bytes
         gps = (r["a1"] is not None and r["xin_ps"] is not None and prec == L.PREC_FP16X2 and r["cw2"].prec_d == L.PREC_FP16X2
                and r["cw1"].prec_d == L.PREC_FP16X2 and (not r["proj"] or r["cws"].prec_d == L.PREC_FP16X2))
+        db2_bn, db2_w = _bias_from_bn(r["c2"], grads, blk.conv2.bias)
+        db1_bn, db1_w = _bias_from_bn(r["c1"], grads, blk.conv1.bias)
         if r["proj"]:
             convs, bns = blk.shortcut[0], blk.shortcut[1]
+            dbs_bn, dbs_w = _bias_from_bn(r["cs"], grads, convs.bias)
             dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], r["ys"], r["cs"], g2,
-                                                  (grads[bns.weight], grads[bns.bias]), m2, ms, planes=gps, zp=zp)
+                                                  (grads[bns.weight], grads[bns.bias]), m2, ms, planes=gps, zp=zp, db2=db2_bn, db_s=dbs_bn)
         else:
-            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None, planes=gps, zp=zp)
+            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None, planes=gps, zp=zp, db2=db2_bn)
         if r["a1"] is not None and prec == L.PREC_FP16X2:
-            wgrad(r["a1"], dy2, r["g2"], dict(presplit=True), grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2, gps)
+            wgrad(r["a1"], dy2, r["g2"], dict(presplit=True), grads[blk.conv2.weight], db2_w, prec, m2, gps)
         else:
             xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
-            wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], grads[blk.conv2.bias], prec, m2)
+            wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], db2_w, prec, m2)
         dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2, dy_presplit=gps)
-        dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1, planes=gps, zp=zp)
+        dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1, planes=gps, zp=zp,
+                                   db_conv=db1_bn)
         xin_w, xf_w = (r["xin_ps"], dict(presplit=True)) if r["xin_ps"] is not None else (r["xin"], None)
-        wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], grads[blk.conv1.bias], prec, m1, gps)
+        wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], db1_w, prec, m1, gps)
         if r["proj"]:
-            wgrad(xin_w, dysc, r["gs"], xf_w, grads[convs.weight], grads[convs.bias], prec, ms, gps)
+            wgrad(xin_w, dysc, r["gs"], xf_w, grads[convs.weight], dbs_w, prec, ms, gps)
             # conv1's data gradient writes every pixel of dxin; the strided 1x1 shortcut then adds into the pixels it reads
             # (csrc/conv_halo.cu runs it as an accumulate-only scatter to every second pixel)
             dxin = ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], prec=r["cw1"].prec_d, dy_amax=m1, dy_presplit=gps)
@@ -455,8 +475,9 @@ def _deep_backward(net, s, demb, grads, training=True):
         return
     # the stem's dy is O(1/N) per pixel (the loss is a mean): without the max|dy| operand scale it would sit in fp16 subnormals
     m0 = amax.take()
-    dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias], m0, zp=zp)
-    wgrad(s.x, dy0, st["g"], None, grads[conv0.weight], grads[conv0.bias], prec, m0)
+    db0_bn, db0_w = _bias_from_bn(st["co"], grads, conv0.bias)
+    dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias], m0, zp=zp, db_conv=db0_bn)
+    wgrad(s.x, dy0, st["g"], None, grads[conv0.weight], db0_w, prec, m0)
     wgrad.join()
 
 

@@ -226,11 +226,15 @@ def _workspace(nbytes: int, device, tag: str = "conv") -> torch.Tensor:
     return buf
 
 
-def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_FP32, dy_amax=None, dy_presplit=False):
+def conv_wgrad(x, dy, g: PcConvGeom, xform=None, dw=None, db=None, prec=L.PREC_FP32, dy_amax=None, dy_presplit=False, want_db=True):
+    """want_db=False: the bias gradient comes from elsewhere (the BatchNorm backward's closed form, bn_act_bwd(db_conv=...)); the
+    column-sum pass over dy is skipped."""
     if dw is None:
         dw = torch.empty(g.Cout, g.Cin, g.R, g.S, device=x.device, dtype=F32)
-    if db is None:
+    if db is None and want_db:
         db = torch.empty(g.Cout, device=x.device, dtype=F32)
+    if not want_db:
+        db = None
     nbytes = int(L.lib().pc_conv_wgrad_workspace(C.byref(g)))
     ws = _workspace(nbytes, x.device)
     import os
@@ -270,18 +274,20 @@ def _zeros(zp, shape, dtype, device):
 
 class BnCoeffs:
     """scale/shift/mean/invstd of one BatchNorm for the current batch (or from running stats in eval)."""
-    __slots__ = ("scale", "shift", "mean", "invstd", "C", "gamma")
+    __slots__ = ("scale", "shift", "mean", "invstd", "C", "gamma", "stats")
 
     def __init__(self, C_, device):
         buf = torch.empty(4, C_, device=device, dtype=F32)
         self.scale, self.shift, self.mean, self.invstd = buf[0], buf[1], buf[2], buf[3]
         self.C = C_
+        self.stats = None
 
 
 def bn_finalize(stats, count, bn: torch.nn.modules.batchnorm._BatchNorm, training: bool) -> BnCoeffs:
     C_ = bn.num_features
     co = BnCoeffs(C_, bn.weight.device)
     co.gamma = bn.weight
+    co.stats = stats if training else None      # fp64 [2, C] sums of y: the closed-form conv bias gradient of the backward reads them
     momentum = 0.1 if bn.momentum is None else bn.momentum
     call("pc_bn_finalize", ptr(stats, torch.float64), C_, float(count), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
          ptr(bn.running_var), ptr(bn.num_batches_tracked, torch.int64), momentum, bn.eps, 1 if training else 0,
@@ -309,7 +315,8 @@ def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None, want_planes=False):
     return (out, argmax, planes) if want_planes else (out, argmax)
 
 
-def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None, planes=False, zp=None):
+def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None, planes=False, zp=None,
+               db_conv=None):
     """Gradient w.r.t. the pre-BatchNorm tensor y of out = drop * pool(relu(bn(y))) (train-mode statistics).
     amax: optional zero-initialised 1-element tensor that receives max|dy| (operand scale of the FP16X2 convolutions).
     planes=True: dy is returned ONLY as fp16 hi | lo planes (uint8 [2, numel*2]) scaled by the power of two derived from a bound
@@ -326,8 +333,12 @@ def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=Non
         dgamma = torch.empty(C_, device=y.device, dtype=F32)
     if dbeta is None:
         dbeta = torch.empty(C_, device=y.device, dtype=F32)
+    # db_conv: gradient of the bias of the convolution that produced y, in closed form (no pass over dy; csrc/bn_act.cu)
+    st = getattr(co, "stats", None) if db_conv is not None else None
+    if db_conv is not None and st is None:
+        raise ValueError("bn_act_bwd: db_conv needs coefficients finalised from train-mode statistics")
     call("pc_bn_act_bwd_apply", *args, ptr(sums, torch.float64), ptr(dy), ptr(dgamma), ptr(dbeta), ptr(amax), ptr(maxes),
-         ptr(dy_ps, torch.uint8), stream())
+         ptr(dy_ps, torch.uint8), ptr(st, torch.float64), ptr(db_conv), stream())
     return (dy_ps if planes else dy), dgamma, dbeta
 
 
@@ -381,7 +392,7 @@ def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, want_planes=F
 
 
 def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, grads2=None, grads_s=None, amax2=None,
-                    amax_s=None, planes=False, zp=None):
+                    amax_s=None, planes=False, zp=None, db2=None, db_s=None):
     """Returns dy2, d(shortcut branch input: dysc for a projection shortcut, dx for identity), (dgamma2, dbeta2), (dgamma_s, dbeta_s).
     planes=True: dy2 -- and dysc of a projection shortcut -- come back ONLY as scaled fp16 hi | lo planes (see bn_act_bwd); the
     identity-shortcut dx stays fp32 (it is accumulated into, not convolved)."""
@@ -405,7 +416,9 @@ def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, gr
          ptr(sums2, torch.float64), ptr(ysc) if co_s else None, ptr(co_s.scale) if co_s else None,
          ptr(co_s.mean) if co_s else None, ptr(co_s.invstd) if co_s else None, ptr(sums_s, torch.float64), n_pix, C_,
          ptr(dy2), ptr(dsc), ptr(g2[0]), ptr(g2[1]), ptr(gs[0]), ptr(gs[1]), ptr(amax2), ptr(amax_s if (ps_sc or not planes) else None),
-         ptr(maxes), ptr(dy2_ps, torch.uint8), ptr(dsc_ps, torch.uint8), stream())
+         ptr(maxes), ptr(dy2_ps, torch.uint8), ptr(dsc_ps, torch.uint8),
+         ptr(getattr(co2, "stats", None) if db2 is not None else None, torch.float64), ptr(db2),
+         ptr(getattr(co_s, "stats", None) if (db_s is not None and co_s) else None, torch.float64), ptr(db_s if co_s else None), stream())
     return (dy2_ps if planes else dy2), (dsc_ps if ps_sc else dsc), g2, gs
 
 
