@@ -26,6 +26,7 @@ struct FeParams {
   const float* wave; int n_clips, S, wave_ld;
   const float* window; const int* fb_start; const int* fb_len; const float* fb_w; const float* dct; const float* tw;
   int hop, n_mels, n_mfcc, T, TLD, Lsz, dct_sz, xs_len, fb_ld, dct_alias;
+  int dct_mma;      // DCT on mma.sync (n_mels, n_mfcc multiples of 8, n_mfcc <= 64, T <= 128): dct staged as tf32 hi | lo arrays
   float preemph;    // optional pre-emphasis y[n] = x[n] - a x[n-1], y[0] = x[0] (0 = off: the reference's code path)
   const PcViewDesc* views; int n_views, views_per_clip;
   const float* noise; int kind, clamp_mode; float top_db; const float* clamp_ref; float* clip_max_out; float* out;
@@ -77,6 +78,36 @@ __device__ __forceinline__ void dft5(float2 x[5]) {
   x[3] = make_float2(m2.x - n2.y, m2.y + n2.x);
 }
 
+// ---- DCT on the tensor cores: out[t][c] = sum_m val[m][t] dct[m][c] is a [T x n_mels] x [n_mels x n_mfcc] product per clip. It ran
+// as scalar FMAs (28 % of the kernel's instructions for two views); mma.sync m16n8k8 with the 3xTF32 split (hi * hi + hi * lo +
+// lo * hi, fp32 accumulate: ~2^-21 relative) does a 16 x 8 x 8 block per instruction. tcgen05 is not the tool for a 101 x 40 x 80
+// product inside an FFT kernel: no TMEM / descriptor set-up, operands straight from the log-mel tile in shared memory.
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// Device noise: element (f, t) of a view takes one of the two Box-Muller normals of the Philox block of its row PAIR (f >> 1, t), so
+// a thread that owns two adjacent rows pays one Philox call for both (it used to take one of four normals per call). Fast-math
+// log / sincos: these are noise samples, checked statistically.
+__device__ __forceinline__ float2 fe_noise_pair(uint32_t view, int f_pair, int t, int T, uint32_t seed) {
+  const uint4 rr = Philox::round10(make_uint4((uint32_t)(f_pair * T + t), view, 0x4e4f4953u, 0u), make_uint2(seed, 0x70635f66u));
+  const float u1 = Philox::u01(rr.x), u2 = Philox::u01(rr.y);
+  const float r = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  return make_float2(r * cs, r * sn);
+}
+__device__ __forceinline__ float fe_noise(uint32_t view, int f, int t, int T, uint32_t seed) {
+  const float2 n2 = fe_noise_pair(view, f >> 1, t, T, seed);
+  return (f & 1) ? n2.y : n2.x;
+}
+
 // position of natural-order bin k (0..199) after the in-place 8 x 5 x 5 passes
 __device__ __forceinline__ int fft_pos(int k) {
   const int k1 = k & 7, k2 = k >> 3;
@@ -95,10 +126,12 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
   float2* W400 = W200 + 200;
   // the DCT matrix is only needed after the last frame chunk: when it fits it aliases the FFT work buffers (Z, P), which
   // keeps the CTA at ~104 KB so that two CTAs stay resident per SM
-  float* dcts = p.dct_alias ? reinterpret_cast<float*>(Z) : reinterpret_cast<float*>(W400 + 202);
-  float* xs = reinterpret_cast<float*>(W400 + 202) + (p.dct_alias ? 0 : p.dct_sz);   // 2 x [(FC-1)*hop + n_fft] samples of the current / next frame chunk (reflect-padded)
+  float* dcts = p.dct_alias ? reinterpret_cast<float*>(Z) : reinterpret_cast<float*>(W400 + 202);     // [dct_sz] (+ [dct_sz] tf32 lo parts with dct_mma)
+  float* xs = reinterpret_cast<float*>(W400 + 202) + (p.dct_alias ? 0 : 2 * p.dct_sz);   // 2 x [(FC-1)*hop + n_fft] samples of the current / next frame chunk (reflect-padded)
   float* fbw = xs + 2 * p.xs_len;                                  // [n_mels][fb_ld] filter weights
   int* fbs = reinterpret_cast<int*>(fbw + p.n_mels * p.fb_ld);     // [n_mels] first bin, [n_mels] length
+  int* posk = fbs + 2 * p.n_mels;                                  // [101 + 101]: position of bin k, then of bin 200 - k, after the FFT passes
+  float* csum = reinterpret_cast<float*>(posk + 202);              // [64] column sums of the DCT matrix
   __shared__ float red[FE_THREADS / 32];
   __shared__ float lmax_s;
 
@@ -113,13 +146,25 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
   for (int i = tid; i < FE_NFFT; i += FE_THREADS) win[i] = p.window[i];
   for (int i = tid; i < 200; i += FE_THREADS) W200[i] = make_float2(p.tw[2 * i], p.tw[2 * i + 1]);
   for (int i = tid; i < 201; i += FE_THREADS) W400[i] = make_float2(p.tw[400 + 2 * i], p.tw[400 + 2 * i + 1]);
-  if (p.kind == PC_FE_MFCC && !p.dct_alias)
-    for (int i = tid; i < p.n_mels * p.n_mfcc; i += FE_THREADS) dcts[i] = p.dct[i];
+  auto load_dct = [&]() {     // plain fp32, or tf32 hi | lo parts for the tensor-core DCT
+    for (int i = tid; i < p.n_mels * p.n_mfcc; i += FE_THREADS) {
+      const float v = p.dct[i];
+      if (p.dct_mma) {
+        const float hi = __uint_as_float(f2tf32(v));
+        dcts[i] = hi;
+        dcts[p.dct_sz + i] = __uint_as_float(f2tf32(v - hi));
+      } else {
+        dcts[i] = v;
+      }
+    }
+  };
+  if (p.kind == PC_FE_MFCC && !p.dct_alias) load_dct();
   for (int i = tid; i < p.n_mels * p.fb_ld; i += FE_THREADS) {
     const int m = i / p.fb_ld, q = i - m * p.fb_ld;
     fbw[i] = p.fb_w[m * PC_FB_MAXW + q];
   }
   for (int i = tid; i < p.n_mels; i += FE_THREADS) { fbs[i] = p.fb_start[i]; fbs[p.n_mels + i] = p.fb_len[i]; }
+  for (int k = tid; k < 101; k += FE_THREADS) { posk[k] = fft_pos(k % 200); posk[101 + k] = fft_pos((200 - k) % 200); }
   __syncthreads();
 
   // Stage the sample span of the frame chunk starting at frame f into dst: 16-byte cp.async for interior vectors (no
@@ -150,6 +195,8 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
   };
   stage_chunk(0, xs);
   asm volatile("cp.async.commit_group;" ::: "memory");
+  float lm = -INFINITY;
+  static_assert(FE_FC == 16, "the mel loop's index split assumes 16-frame chunks");
 
   for (int f0 = 0; f0 < T; f0 += FE_FC) {
     const int nf = min(FE_FC, T - f0);
@@ -161,23 +208,19 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
     const float* xc = xs + buf * p.xs_len;
-    // ---- P1: window, pack even/odd samples into complex points
-#pragma unroll 4
-    for (int i = tid; i < nf * FE_NC; i += FE_THREADS) {
-      const int fl = i / FE_NC, n = i - fl * FE_NC;
-      const float* sp = xc + fl * p.hop + 2 * n;                 // (hop may be odd: no vector access here)
-      const float2 wv = *reinterpret_cast<const float2*>(win + 2 * n);
-      Z[fl * FE_ZLD + n] = make_float2(sp[0] * wv.x, sp[1] * wv.y);
-    }
-    __syncthreads();
     FE_T(0);
-    // ---- A: 25 radix-8 butterflies per frame over stride-25 points, twiddle W200^(n2*k1)
+    // ---- A: 25 radix-8 butterflies per frame over stride-25 points, twiddle W200^(n2*k1). The points come straight from the
+    // staged samples: complex point n = (x[2n] w[2n], x[2n+1] w[2n+1]) of the Hann-windowed frame (hop may be odd: scalar loads)
     for (int i = tid; i < nf * 25; i += FE_THREADS) {
       const int fl = i / 25, n2 = i - fl * 25;
       float2* z = Z + fl * FE_ZLD;
+      const float* sp = xc + fl * p.hop + 2 * n2;
       float2 v[8];
 #pragma unroll
-      for (int n1 = 0; n1 < 8; ++n1) v[n1] = z[25 * n1 + n2];
+      for (int n1 = 0; n1 < 8; ++n1) {
+        const float2 wv = *reinterpret_cast<const float2*>(win + 50 * n1 + 2 * n2);
+        v[n1] = make_float2(sp[50 * n1] * wv.x, sp[50 * n1 + 1] * wv.y);
+      }
       dft8(v);
 #pragma unroll
       for (int k1 = 0; k1 < 8; ++k1) z[25 * k1 + n2] = k1 == 0 ? v[0] : cmul(v[k1], W200[n2 * k1]);
@@ -217,8 +260,8 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
     for (int i = tid; i < nf * 101; i += FE_THREADS) {
       const int fl = i / 101, k = i - fl * 101;
       const float2* z = Z + fl * FE_ZLD;
-      const float2 zk = z[fft_pos(k % 200)];
-      const float2 zn = z[fft_pos((200 - k) % 200)];
+      const float2 zk = z[posk[k]];
+      const float2 zn = z[posk[101 + k]];
       // Xe = (zk + conj(zn))/2 ; Xo = -i (zk - conj(zn))/2 ; X[k] = Xe + W400^k Xo ; X[200-k] = conj(Xe - W400^k Xo)
       const float2 xe = make_float2(0.5f * (zk.x + zn.x), 0.5f * (zk.y - zn.y));
       const float2 dd = make_float2(0.5f * (zk.x - zn.x), 0.5f * (zk.y + zn.y));
@@ -233,27 +276,23 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
     // ---- mel: banded filterbank, stored as 10 log10(mel)
 #pragma unroll 2
     for (int i = tid; i < nf * p.n_mels; i += FE_THREADS) {
-      const int m = i / nf, fl = i - m * nf;   // fl fastest -> conflict-free L writes
+      const int m = nf == FE_FC ? (i >> 4) : i / nf, fl = i - m * nf;   // fl fastest -> conflict-free L writes
       const int s = fbs[m], len = fbs[p.n_mels + m];
       const float* wq = fbw + m * p.fb_ld;
       const float* pq = P + fl * FE_PLD + s;
       float acc = 0.f;
 #pragma unroll 4
       for (int q = 0; q < len; ++q) acc = fmaf(pq[q], wq[q], acc);
-      L[m * p.TLD + f0 + fl] = 3.0102999566398120f * __log2f(fmaxf(acc, FE_LOG_FLOOR));   // 10 log10(x) = 10 log10(2) log2(x)
+      const float lv = 3.0102999566398120f * __log2f(fmaxf(acc, FE_LOG_FLOOR));   // 10 log10(x) = 10 log10(2) log2(x)
+      L[m * p.TLD + f0 + fl] = lv;
+      lm = fmaxf(lm, lv);                                                           // clip-wide maximum, tracked as the tile is written
     }
     __syncthreads();
     FE_T(4);
   }
 
-  if (p.kind == PC_FE_MFCC && p.dct_alias)      // FFT buffers are free now (the frame loop ended with a barrier)
-    for (int i = tid; i < p.n_mels * p.n_mfcc; i += FE_THREADS) dcts[i] = p.dct[i];
+  if (p.kind == PC_FE_MFCC && p.dct_alias) load_dct();     // FFT buffers are free now (the frame loop ended with a barrier)
   // ---- clip-wide maximum of the log-mel tile (the barriers below also publish the DCT matrix)
-  float lm = -INFINITY;
-  for (int i = tid; i < p.n_mels * T; i += FE_THREADS) {
-    const int m = i / T, t = i - m * T;
-    lm = fmaxf(lm, L[m * p.TLD + t]);
-  }
   lm = warp_max(lm);
   if ((tid & 31) == 0) red[tid >> 5] = lm;
   __syncthreads();
@@ -262,12 +301,19 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
     for (int w = 1; w < FE_THREADS / 32; ++w) v = fmaxf(v, red[w]);
     lmax_s = v;
   }
+  if (p.kind == PC_FE_MFCC && p.dct_mma && tid < p.n_mfcc) {       // column sums of the DCT matrix (the gain enters as G * csum[c])
+    float a = 0.f;
+    for (int m = 0; m < p.n_mels; ++m) a += dcts[m * p.n_mfcc + tid] + dcts[p.dct_sz + m * p.n_mfcc + tid];
+    csum[tid] = a;
+  }
   __syncthreads();
   const float lmax = lmax_s;
   const float amin_db = -100.0f;   // 10 log10(1e-10)
 
   FE_T(5);
   const int n_out = p.kind == PC_FE_MFCC ? p.n_mfcc : p.n_mels;
+  float dacc[8][4];          // tensor-core DCT accumulators of this warp's 16 frames (up to 8 coefficient tiles)
+  float dct_clamp = 0.f;     // clamp level they were computed with
   for (int v = 0; v < V; ++v) {
     const int view = view0 + v;
     if (view >= p.n_views) break;
@@ -285,7 +331,70 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
     float* o = p.out + (size_t)view * n_out * T;
     const float* nz = p.noise != nullptr ? p.noise + (size_t)view * n_out * T : nullptr;
 
-    if (p.kind == PC_FE_MFCC) {
+    if (p.kind == PC_FE_MFCC && p.dct_mma) {
+      // val_v[m][t] = max(L + G_v, lo_v) = G_v + max(L, lo_v - G_v): the DCT of the clamped tile is shared by every view of the clip
+      // with the same clamp level (all of them unless a gain pushes the floor below -100 dB), the gain enters as G_v * csum[c].
+      // Warp w owns frames 16 w .. 16 w + 15 and all coefficient tiles; accumulators stay in registers across the views.
+      const int warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tig = lane & 3;
+      const int t0 = 16 * warp;
+      const int n_nt = p.n_mfcc >> 3;
+      const float lclamp = lo - G;
+      if (t0 < T) {
+        if (v == 0 || lclamp != dct_clamp) {
+          dct_clamp = lclamp;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) dacc[nt][0] = dacc[nt][1] = dacc[nt][2] = dacc[nt][3] = 0.f;
+          const int ta = min(t0 + gq, T - 1), tb = min(t0 + gq + 8, T - 1);
+          for (int ks = 0; ks < (p.n_mels >> 3); ++ks) {
+            const float* Lk = L + (8 * ks + tig) * p.TLD;
+            const float av[4] = {fmaxf(Lk[ta], lclamp), fmaxf(Lk[tb], lclamp), fmaxf(Lk[4 * p.TLD + ta], lclamp), fmaxf(Lk[4 * p.TLD + tb], lclamp)};
+            uint32_t ah[4], al[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              ah[e] = f2tf32(av[e]);
+              al[e] = f2tf32(av[e] - __uint_as_float(ah[e]));
+            }
+            const float* dk = dcts + (8 * ks + tig) * p.n_mfcc + gq;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+              if (nt < n_nt) {
+                const uint32_t bh0 = __float_as_uint(dk[8 * nt]), bh1 = __float_as_uint(dk[4 * p.n_mfcc + 8 * nt]);
+                const uint32_t bl0 = __float_as_uint(dk[p.dct_sz + 8 * nt]), bl1 = __float_as_uint(dk[p.dct_sz + 4 * p.n_mfcc + 8 * nt]);
+                mma_tf32_16x8x8(dacc[nt], al, bh0, bh1);      // small terms first
+                mma_tf32_16x8x8(dacc[nt], ah, bl0, bl1);
+                mma_tf32_16x8x8(dacc[nt], ah, bh0, bh1);
+              }
+            }
+          }
+        }
+        // accumulator element e of tile nt: frame t0 + gq + 8 (e >> 1), coefficient 8 nt + 2 tig + (e & 1)
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          if (nt < n_nt) {
+            const int c0 = 8 * nt + 2 * tig;
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+              const int t = t0 + gq + 8 * hrow;
+              if (t < T) {
+                float r0 = fmaf(G, csum[c0], dacc[nt][2 * hrow]), r1 = fmaf(G, csum[c0 + 1], dacc[nt][2 * hrow + 1]);
+                const bool tm = t >= d.t0 && t < d.t1;
+                if (tm || (c0 >= d.f0 && c0 < d.f1)) r0 = 0.f;
+                if (tm || (c0 + 1 >= d.f0 && c0 + 1 < d.f1)) r1 = 0.f;
+                if (d.noise_level != 0.f) {
+                  float2 nv;
+                  if (nz != nullptr) nv = make_float2(nz[c0 * T + t], nz[(c0 + 1) * T + t]);
+                  else nv = fe_noise_pair((uint32_t)view, c0 >> 1, t, T, d.noise_seed);
+                  r0 = fmaf(nv.x, d.noise_level, r0);
+                  r1 = fmaf(nv.y, d.noise_level, r1);
+                }
+                o[c0 * T + t] = r0;
+                o[(c0 + 1) * T + t] = r1;
+              }
+            }
+          }
+        }
+      }
+    } else if (p.kind == PC_FE_MFCC) {
       const int n_cg = (p.n_mfcc + 7) >> 3;
       for (int i = tid; i < n_cg * T; i += FE_THREADS) {
         const int cg = i / T, t = i - cg * T;
@@ -317,10 +426,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
           if (d.noise_level != 0.f) {
             float nv;
             if (nz != nullptr) nv = nz[c * T + t];
-            else {
-              const uint4 rr = Philox::round10(make_uint4((uint32_t)(c * T + t), (uint32_t)view, 0x4e4f4953u, 0u), make_uint2(d.noise_seed, 0x70635f66u));
-              nv = Philox::normal2(rr.x, rr.y).x;
-            }
+            else nv = fe_noise((uint32_t)view, c, t, T, d.noise_seed);
             r = fmaf(nv, d.noise_level, r);
           }
           o[c * T + t] = r;
@@ -334,10 +440,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
         if (d.noise_level != 0.f) {
           float nv;
           if (nz != nullptr) nv = nz[i];
-          else {
-            const uint4 rr = Philox::round10(make_uint4((uint32_t)i, (uint32_t)view, 0x4e4f4953u, 0u), make_uint2(d.noise_seed, 0x70635f66u));
-            nv = Philox::normal2(rr.x, rr.y).x;
-          }
+          else nv = fe_noise((uint32_t)view, m, t, T, d.noise_seed);
           r = fmaf(nv, d.noise_level, r);
         }
         o[i] = r;
@@ -373,10 +476,7 @@ __global__ void augment_apply_kernel(const float* __restrict__ x, const PcViewDe
     if (d.noise_level != 0.f) {
       float nv;
       if (noise != nullptr) nv = noise[idx];
-      else {
-        const uint4 rr = Philox::round10(make_uint4((uint32_t)(f * T + t), (uint32_t)v, 0x4e4f4953u, 0u), make_uint2(d.noise_seed, 0x70635f66u));
-        nv = Philox::normal2(rr.x, rr.y).x;
-      }
+      else nv = fe_noise((uint32_t)v, f, t, T, d.noise_seed);
       r = fmaf(nv, d.noise_level, r);
     }
     out[idx] = r;
@@ -433,18 +533,19 @@ extern "C" int pc_frontend_fwd(const float* wave, int n_clips, int S, int wave_l
   p.hop = c->hop; p.n_mels = c->n_mels; p.n_mfcc = kind == PC_FE_MFCC ? c->n_mfcc : 0;
   p.preemph = c->preemph;
   p.T = 1 + S / c->hop;
-  p.TLD = p.T | 1;
+  p.TLD = p.T + ((8 - p.T % 32) + 32) % 32;      // TLD % 32 == 8: the tensor-core DCT's fragment loads (4 mel rows x 8 frames) hit 32 distinct banks
   p.Lsz = (p.n_mels * p.TLD + 3) & ~3;
   p.dct_sz = (p.n_mels * p.n_mfcc + 3) & ~3;
   p.xs_len = ((FE_FC - 1) * c->hop + FE_NFFT + 7) & ~3;
   p.fb_ld = c->fb_wmax > 0 ? ((c->fb_wmax + 3) & ~3) : PC_FB_MAXW;
-  p.dct_alias = (sizeof(float) * (size_t)p.dct_sz <= sizeof(float2) * FE_FC * FE_ZLD + sizeof(float) * FE_FC * FE_PLD) ? 1 : 0;
+  p.dct_mma = (kind == PC_FE_MFCC && p.n_mels % 8 == 0 && p.n_mfcc % 8 == 0 && p.n_mfcc <= 64 && p.T <= 16 * (FE_THREADS / 32)) ? 1 : 0;
+  p.dct_alias = (sizeof(float) * 2 * (size_t)p.dct_sz <= sizeof(float2) * FE_FC * FE_ZLD + sizeof(float) * FE_FC * FE_PLD) ? 1 : 0;
   p.views = views; p.n_views = n_views; p.views_per_clip = V;
   p.noise = noise; p.kind = kind; p.clamp_mode = clamp_mode; p.top_db = top_db; p.clamp_ref = clamp_ref;
   p.clip_max_out = clip_max_out; p.out = out;
   p.dbg = g_fe_dbg;
   size_t smem = sizeof(float2) * FE_FC * FE_ZLD + sizeof(float) * (FE_FC * FE_PLD + (size_t)p.Lsz + FE_NFFT) +
-                sizeof(float2) * (200 + 202) + sizeof(float) * ((p.dct_alias ? 0 : (size_t)p.dct_sz) + 2 * (size_t)p.xs_len + (size_t)p.n_mels * p.fb_ld + 2 * (size_t)p.n_mels + 4);
+                sizeof(float2) * (200 + 202) + sizeof(float) * ((p.dct_alias ? 0 : 2 * (size_t)p.dct_sz) + 2 * (size_t)p.xs_len + (size_t)p.n_mels * p.fb_ld + 2 * (size_t)p.n_mels + 202 + 64 + 4);
   PC_REQUIRE(smem <= 227 * 1024, PC_EUNSUPPORTED, "pc_frontend_fwd: clip of %d samples (%d frames) needs %zu B shared memory (> 227 KB)", S, p.T, smem);
   static size_t smem_set = 0;
   if (smem > smem_set) {
