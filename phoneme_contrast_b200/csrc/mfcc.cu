@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
   int* fbs = reinterpret_cast<int*>(fbw + p.n_mels * p.fb_ld);     // [n_mels] first bin, [n_mels] length
   int* posk = fbs + 2 * p.n_mels;                                  // [101 + 101]: position of bin k, then of bin 200 - k, after the FFT passes
   float* csum = reinterpret_cast<float*>(posk + 202);              // [64] column sums of the DCT matrix
+  float2* twa = reinterpret_cast<float2*>(csum + 64);              // [7][25] twiddles of the radix-8 pass in access order: W200^(n2 * k1), k1 = 1..7
   __shared__ float red[FE_THREADS / 32];
   __shared__ float lmax_s;
 
@@ -165,6 +166,10 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
   }
   for (int i = tid; i < p.n_mels; i += FE_THREADS) { fbs[i] = p.fb_start[i]; fbs[p.n_mels + i] = p.fb_len[i]; }
   for (int k = tid; k < 101; k += FE_THREADS) { posk[k] = fft_pos(k % 200); posk[101 + k] = fft_pos((200 - k) % 200); }
+  for (int i = tid; i < 7 * 25; i += FE_THREADS) {
+    const int k1 = i / 25 + 1, n2 = i % 25;
+    twa[i] = make_float2(p.tw[2 * (n2 * k1)], p.tw[2 * (n2 * k1) + 1]);
+  }
   __syncthreads();
 
   // Stage the sample span of the frame chunk starting at frame f into dst: 16-byte cp.async for interior vectors (no
@@ -196,6 +201,7 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
   stage_chunk(0, xs);
   asm volatile("cp.async.commit_group;" ::: "memory");
   float lm = -INFINITY;
+  const bool hop_even = (p.hop & 1) == 0;
   static_assert(FE_FC == 16, "the mel loop's index split assumes 16-frame chunks");
 
   for (int f0 = 0; f0 < T; f0 += FE_FC) {
@@ -219,11 +225,14 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
 #pragma unroll
       for (int n1 = 0; n1 < 8; ++n1) {
         const float2 wv = *reinterpret_cast<const float2*>(win + 50 * n1 + 2 * n2);
-        v[n1] = make_float2(sp[50 * n1] * wv.x, sp[50 * n1 + 1] * wv.y);
+        float2 xv;
+        if (hop_even) xv = *reinterpret_cast<const float2*>(sp + 50 * n1);      // 8-byte aligned: xs, fl * hop and 2 n are even
+        else xv = make_float2(sp[50 * n1], sp[50 * n1 + 1]);
+        v[n1] = make_float2(xv.x * wv.x, xv.y * wv.y);
       }
       dft8(v);
 #pragma unroll
-      for (int k1 = 0; k1 < 8; ++k1) z[25 * k1 + n2] = k1 == 0 ? v[0] : cmul(v[k1], W200[n2 * k1]);
+      for (int k1 = 0; k1 < 8; ++k1) z[25 * k1 + n2] = k1 == 0 ? v[0] : cmul(v[k1], twa[(k1 - 1) * 25 + n2]);
     }
     __syncthreads();
     FE_T(1);
@@ -255,10 +264,13 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
     }
     __syncthreads();
     FE_T(2);
-    // ---- post: real-FFT split, power spectrum bins k and 200-k together
+    // ---- post: real-FFT split, power spectrum bins k and 200-k together. All 16 frame slots are processed (thread = (bin, frame),
+    // frame fastest; slots beyond nf hold stale finite data and are never stored) and the power spectrum is written TRANSPOSED,
+    // PT[bin][16 frames], so that the filterbank below reads four frames per 16-byte load.
+    float* PT = P;
 #pragma unroll 2
-    for (int i = tid; i < nf * 101; i += FE_THREADS) {
-      const int fl = i / 101, k = i - fl * 101;
+    for (int i = tid; i < 101 * FE_FC; i += FE_THREADS) {
+      const int k = i >> 4, fl = i & 15;
       const float2* z = Z + fl * FE_ZLD;
       const float2 zk = z[posk[k]];
       const float2 zn = z[posk[101 + k]];
@@ -268,24 +280,35 @@ __global__ void __launch_bounds__(FE_THREADS, 2) frontend_kernel(FeParams p) {
       const float2 xo = cmul_mi(dd);
       const float2 wx = cmul(W400[k], xo);
       const float2 a = cadd(xe, wx), b = csub(xe, wx);
-      P[fl * FE_PLD + k] = a.x * a.x + a.y * a.y;
-      P[fl * FE_PLD + 200 - k] = b.x * b.x + b.y * b.y;
+      PT[k * FE_FC + fl] = a.x * a.x + a.y * a.y;
+      PT[(200 - k) * FE_FC + fl] = b.x * b.x + b.y * b.y;
     }
     __syncthreads();
     FE_T(3);
-    // ---- mel: banded filterbank, stored as 10 log10(mel)
-#pragma unroll 2
-    for (int i = tid; i < nf * p.n_mels; i += FE_THREADS) {
-      const int m = nf == FE_FC ? (i >> 4) : i / nf, fl = i - m * nf;   // fl fastest -> conflict-free L writes
+    // ---- mel: banded filterbank, stored as 10 log10(mel); thread = (mel bin, group of four frames)
+    for (int i = tid; i < 4 * p.n_mels; i += FE_THREADS) {
+      const int m = i >> 2, fq = i & 3;
       const int s = fbs[m], len = fbs[p.n_mels + m];
       const float* wq = fbw + m * p.fb_ld;
-      const float* pq = P + fl * FE_PLD + s;
-      float acc = 0.f;
+      const float* pq = PT + s * FE_FC + 4 * fq;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
-      for (int q = 0; q < len; ++q) acc = fmaf(pq[q], wq[q], acc);
-      const float lv = 3.0102999566398120f * __log2f(fmaxf(acc, FE_LOG_FLOOR));   // 10 log10(x) = 10 log10(2) log2(x)
-      L[m * p.TLD + f0 + fl] = lv;
-      lm = fmaxf(lm, lv);                                                           // clip-wide maximum, tracked as the tile is written
+      for (int q = 0; q < len; ++q) {
+        const float w = wq[q];
+        const float4 pv = *reinterpret_cast<const float4*>(pq + q * FE_FC);
+        acc.x = fmaf(pv.x, w, acc.x); acc.y = fmaf(pv.y, w, acc.y); acc.z = fmaf(pv.z, w, acc.z); acc.w = fmaf(pv.w, w, acc.w);
+      }
+      // 10 log10(x) = 10 log10(2) log2(x)
+      const float lv[4] = {3.0102999566398120f * __log2f(fmaxf(acc.x, FE_LOG_FLOOR)), 3.0102999566398120f * __log2f(fmaxf(acc.y, FE_LOG_FLOOR)),
+                           3.0102999566398120f * __log2f(fmaxf(acc.z, FE_LOG_FLOOR)), 3.0102999566398120f * __log2f(fmaxf(acc.w, FE_LOG_FLOOR))};
+      float* lp = L + m * p.TLD + f0 + 4 * fq;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (4 * fq + e < nf) {
+          lp[e] = lv[e];
+          lm = fmaxf(lm, lv[e]);            // clip-wide maximum, tracked as the tile is written
+        }
+      }
     }
     __syncthreads();
     FE_T(4);
@@ -545,7 +568,7 @@ extern "C" int pc_frontend_fwd(const float* wave, int n_clips, int S, int wave_l
   p.clip_max_out = clip_max_out; p.out = out;
   p.dbg = g_fe_dbg;
   size_t smem = sizeof(float2) * FE_FC * FE_ZLD + sizeof(float) * (FE_FC * FE_PLD + (size_t)p.Lsz + FE_NFFT) +
-                sizeof(float2) * (200 + 202) + sizeof(float) * ((p.dct_alias ? 0 : 2 * (size_t)p.dct_sz) + 2 * (size_t)p.xs_len + (size_t)p.n_mels * p.fb_ld + 2 * (size_t)p.n_mels + 202 + 64 + 4);
+                sizeof(float2) * (200 + 202) + sizeof(float) * ((p.dct_alias ? 0 : 2 * (size_t)p.dct_sz) + 2 * (size_t)p.xs_len + (size_t)p.n_mels * p.fb_ld + 2 * (size_t)p.n_mels + 202 + 64 + 2 * 7 * 25 + 4);
   PC_REQUIRE(smem <= 227 * 1024, PC_EUNSUPPORTED, "pc_frontend_fwd: clip of %d samples (%d frames) needs %zu B shared memory (> 227 KB)", S, p.T, smem);
   static size_t smem_set = 0;
   if (smem > smem_set) {
