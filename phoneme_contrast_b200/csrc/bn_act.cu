@@ -238,6 +238,27 @@ __device__ __forceinline__ void max_commit(float* slot, float local_max) {   // 
   if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(local_max));
 }
 
+// The same with ONE atomic per block and slot (up to three slots): per-warp atomics put 8 x 592 same-address operations per slot on
+// the L2 atomic unit at the end of a reduce pass. sh: [3][8] floats. All threads of the block must call it.
+template <int N>
+__device__ __forceinline__ void max_commit_block(float* slots, const float (&local)[N], float* sh) {
+  if (slots == nullptr) return;      // uniform across the block
+  float w[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) w[i] = warp_max(local[i]);
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) sh[i * 8 + (threadIdx.x >> 5)] = w[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float m = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m = fmaxf(m, sh[threadIdx.x * 8 + k]);
+    atomicMax(reinterpret_cast<unsigned int*>(slots + threadIdx.x), __float_as_uint(m));
+  }
+  __syncthreads();                   // sh is reused by the channel reduction that follows
+}
+
 // Visits the pixels of this block: f(p, b, h, w) with p the linear NHWC pixel index. Without pooling only p is needed (b
 // only for the per-sample dropout multiplier), so the loop is flat and division-free; with pooling a block walks whole
 // image rows, which keeps the (b, h) decomposition out of the inner loop.
@@ -309,9 +330,9 @@ bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict
     gmax = absmax4(dz, gmax);
     xmax = absmax4(xh, xmax);
   });
-  if (maxes != nullptr) {
-    max_commit(maxes, gmax);
-    max_commit(maxes + 1, xmax);
+  {
+    const float mx[2] = {gmax, xmax};
+    max_commit_block<2>(maxes, mx, sh);
   }
   double* dst[2] = {sums, sums + C};
   block_channel_reduce<2>(acc, C4, c4_off, dst, sh);
@@ -467,10 +488,9 @@ bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __res
       xsmax = absmax4(xs, xsmax);
     }
   }
-  if (maxes != nullptr) {
-    max_commit(maxes, gmax);
-    max_commit(maxes + 1, x2max);
-    max_commit(maxes + 2, xsmax);
+  {
+    const float mx[3] = {gmax, x2max, xsmax};
+    max_commit_block<3>(maxes, mx, sh);
   }
   // sums2 = [sum g, sum g*xhat2]; sums_s = [sum g, sum g*xhat_s]
   if (proj) {

@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ x
 constexpr int QPB = 14;                    // pooled pixels per 128-row K block: row = ql * 9 + window position a (126 rows + 2 zero);
                                            // a block's pixels lie in ONE pooled row (pw = 14 seg + ql), so all its input patches fall
                                            // inside a 9 x 36 window of the image that is staged in shared memory once per block
-constexpr int RG_H = 9, RG_W = 36, RG_LD = 37;
+constexpr int RG_H = 9, RG_W = 36, RG_LDH = 38;        // staged window: 9 x 36 samples; fp16 rows of 38 halves (even: 4-byte aligned chunks)
+constexpr int RG_ASZ = RG_H * RG_LDH;                  // one of the four window arrays (hi / lo, two column parities)
 constexpr int ROWS = 128;
 constexpr uint32_t PART = ROWS * 128;      // one 64-wide group of one operand part: [128 rows][128 B], SWIZZLE_128B (MN-major)
 constexpr uint32_t STAGE = 4 * PART;       // A_hi | A_lo | B_hi | B_lo
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
   uint64_t* acc_full = empty + NSTAGE;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
   float* s_red = reinterpret_cast<float*>(tmem_slot + 2);                // [2][64]
-  float* s_reg = s_red + 128;                                            // [NGROUPS][RG_H * RG_LD] staged image windows
+  __half* s_reg = reinterpret_cast<__half*>(s_red + 128);                // [NGROUPS][hi0 | hi1 | lo0 | lo1][RG_H][RG_LDH] staged image windows, pre-split
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < (int)(PART / 16); i += THREADS) reinterpret_cast<uint4*>(zeros)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -255,19 +256,18 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
       }
     }
     float rs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, rq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    int tap_off[8];                    // offset of tap 8 j + q inside the staged window, -1 for the padding taps 49..63
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const int t = 8 * j + q;
-      tap_off[q] = t < NT ? (t / KS) * RG_LD + (t % KS) : -1;
-    }
-    float* reg = s_reg + group * (RG_H * RG_LD);
-    int row_base[8];                   // window offset of the conv pixel of my 8 rows (row = pr + 16 i = ql' * 9 + a')
+    // The reduction index of T1's M side is m = 8 * tr + ts (tap row tr = 16-byte chunk j of an operand row, tap column ts < 7 inside
+    // it; m = 8 tr + 7 and chunk 7 carry junk that the finish kernel never reads): a chunk is then 8 CONSECUTIVE window samples,
+    // copied as four 4-byte words from a window that was split into fp16 hi / lo ONCE per sample when it was staged. Each plane is
+    // kept twice, sample cc at half index cc (copy 0) and cc + 1 (copy 1), so that chunks starting at an odd column are aligned too.
+    __half* reg = s_reg + (size_t)group * 4 * RG_ASZ;
+    int row_base[8];                   // half offset (inside the hi arrays) of the window sample under tap (0, 0) of my 8 rows (row = ql' * 9 + a')
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int row = pr + 16 * i;
       const int rq_ = row / 9, ra = row - rq_ * 9;
-      row_base[i] = (ra / 3) * RG_LD + 2 * min(rq_, QPB - 1) + ra % 3;
+      const int cbase = 2 * min(rq_, QPB - 1) + ra % 3, sel = cbase & 1;
+      row_base[i] = sel * RG_ASZ + (ra / 3) * RG_LDH + cbase + sel;
     }
     // Global loads of a K block -- its image window and its S unit (dpool, p0, argmax) -- are issued ONE block ahead into registers:
     // measured, a group otherwise sits out two full DRAM latencies per block (window -> barrier -> patch build; dpool / p0 -> S).
@@ -316,7 +316,13 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
       for (int k = 0; k < 3; ++k) {
         const int e = gt + 128 * k;
         const int rr = e / RG_W, cc = e - rr * RG_W;
-        if (e < RG_H * RG_W) reg[rr * RG_LD + cc] = cur.rv[k];
+        if (e < RG_H * RG_W) {
+          const float v = cur.rv[k];
+          const __half vh = __float2half_rn(v);
+          const __half vl = __float2half_rn((v - __half2float(vh)) * kF16LoScale);
+          __half* w0 = reg + rr * RG_LDH + cc;
+          w0[0] = vh; w0[RG_ASZ + 1] = vh; w0[2 * RG_ASZ] = vl; w0[3 * RG_ASZ + 1] = vl;
+        }
       }
       // ---------------- S unit
       uint4 hh = make_uint4(0u, 0u, 0u, 0u), ll = hh;
@@ -342,36 +348,40 @@ __global__ void __launch_bounds__(THREADS, 1) stem_bwd_pool_kernel(const PoolPar
       unsigned char* a_lo = a_hi + PART;
       unsigned char* b_hi = a_hi + 2 * PART;
       unsigned char* b_lo = a_hi + 3 * PART;
-      // ---------------- patch chunks: row (ql', a') = taps 8 j .. 8 j + 7 of the conv pixel (2 ph - 1 + a'/3, 2 (pw0 + ql') - 1 + a'%3),
-      // i.e. window element [a'/3 + tr][2 ql' + a'%3 + ts]
+      // ---------------- patch chunks: row (ql', a'), chunk j = tap row j of the conv pixel (2 ph - 1 + a'/3, 2 (pw0 + ql') - 1 + a'%3),
+      // i.e. window samples [a'/3 + j][2 ql' + a'%3 .. + 7]
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int row = pr + 16 * i;
-        const float* base = reg + row_base[i];
-        float tv[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) tv[q] = tap_off[q] >= 0 ? base[tap_off[q]] : 0.f;
-        uint4 h, l;
-        split_f16x2(tv[0], tv[1], h.x, l.x); split_f16x2(tv[2], tv[3], h.y, l.y);
-        split_f16x2(tv[4], tv[5], h.z, l.z); split_f16x2(tv[6], tv[7], h.w, l.w);
+        uint4 h = make_uint4(0u, 0u, 0u, 0u), l = h;
+        if (j < KS) {
+          const uint32_t* ph_ = reinterpret_cast<const uint32_t*>(reg + row_base[i] + j * RG_LDH);
+          const uint32_t* pl_ = reinterpret_cast<const uint32_t*>(reg + row_base[i] + j * RG_LDH + 2 * RG_ASZ);
+          h = make_uint4(ph_[0], ph_[1], ph_[2], ph_[3]);
+          l = make_uint4(pl_[0], pl_[1], pl_[2], pl_[3]);
+        }
         const uint32_t off = mn_off(row, j);
         *reinterpret_cast<uint4*>(a_hi + off) = h;
         *reinterpret_cast<uint4*>(a_lo + off) = l;
       }
       if (gt < 112) {
-        // row ql * 9 + a holds this pixel's (scaled) gradient in the channels whose argmax is window position a, zero elsewhere
-        const uint32_t amv[2] = {am.x, am.y};
+        // row ql * 9 + a holds this pixel's (scaled) gradient in the channels whose argmax is window position a, zero elsewhere:
+        // clear my nine 16-byte chunks of both planes, then drop each channel's two halves into the row its argmax names
 #pragma unroll
         for (int a = 0; a < 9; ++a) {
-          uint32_t m16[4];
-#pragma unroll
-          for (int w2 = 0; w2 < 4; ++w2) {           // 32-bit word w2 holds channels 2 w2, 2 w2 + 1
-            const uint32_t c_lo = (amv[w2 >> 1] >> (16 * (w2 & 1))) & 0xFFu, c_hi = (amv[w2 >> 1] >> (16 * (w2 & 1) + 8)) & 0xFFu;
-            m16[w2] = (c_lo == (uint32_t)a ? 0x0000FFFFu : 0u) | (c_hi == (uint32_t)a ? 0xFFFF0000u : 0u);
-          }
           const uint32_t off = mn_off(ql * 9 + a, cj);
-          *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(hh.x & m16[0], hh.y & m16[1], hh.z & m16[2], hh.w & m16[3]);
-          *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(ll.x & m16[0], ll.y & m16[1], ll.z & m16[2], ll.w & m16[3]);
+          *reinterpret_cast<uint4*>(b_hi + off) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(b_lo + off) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        const uint32_t amv[2] = {am.x, am.y}, hw[4] = {hh.x, hh.y, hh.z, hh.w}, lw[4] = {ll.x, ll.y, ll.z, ll.w};
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const uint32_t a = (amv[q >> 2] >> (8 * (q & 3))) & 0xFFu;
+          if (a < 9u) {
+            const uint32_t off = mn_off(ql * 9 + (int)a, cj) + 2u * (uint32_t)q;
+            *reinterpret_cast<unsigned short*>(b_hi + off) = (unsigned short)(hw[q >> 1] >> (16 * (q & 1)));
+            *reinterpret_cast<unsigned short*>(b_lo + off) = (unsigned short)(lw[q >> 1] >> (16 * (q & 1)));
+          }
         }
       } else {
         const int u = gt - 112;                       // rows 126, 127 of S: zero
@@ -469,7 +479,8 @@ __global__ void __launch_bounds__(256) stem_bwd_finish_kernel(const float* __res
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < CO * NT; idx += gridDim.x * blockDim.x) {
     const int o = idx / NT, t = idx % NT;
     double t1 = 0.0;
-    for (int k = 0; k < n_partial; ++k) t1 += (double)t1_partial[((size_t)k * 64 + t) * CO + o];
+    const int trow = 8 * (t / KS) + t % KS;             // T1's M index of tap t (see stem_bwd_pool_kernel)
+    for (int k = 0; k < n_partial; ++k) t1 += (double)t1_partial[((size_t)k * 64 + trow) * CO + o];
     t1 *= unscale;
     double yx = 0.0;
     for (int tp = 0; tp < NT; ++tp) yx += (double)w[o * NT + tp] * G[tp * NT + t];
@@ -542,7 +553,7 @@ extern "C" int pc_stem_bwd(const float* dpool, const float* p0, const uint8_t* a
   p.n_seg = ceil_div(Wp, QPB);
   p.n_blocks = B * Hp * p.n_seg;
   p.d_seg = FastDiv::make((uint32_t)p.n_seg); p.d_hp = FastDiv::make((uint32_t)Hp);
-  const size_t smem = (size_t)NSTAGE * STAGE + PART + sizeof(uint64_t) * (2 * NSTAGE + 1) + 16 + (128 + NGROUPS * RG_H * RG_LD) * sizeof(float) + 1024;
+  const size_t smem = (size_t)NSTAGE * STAGE + PART + sizeof(uint64_t) * (2 * NSTAGE + 1) + 16 + 128 * sizeof(float) + (size_t)NGROUPS * 4 * RG_ASZ * sizeof(__half) + 1024;
   static bool conf = false;
   if (!conf) {
     PC_CUDA(cudaFuncSetAttribute(stem_bwd_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
