@@ -235,6 +235,16 @@ int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* g, const Pc
                   float* db, void* workspace, size_t workspace_bytes, int prec, const float* dy_amax, int dy_presplit,
                   pc_stream_t stream);
 
+/* Halo weight-gradient engine (csrc/conv_halo_wgrad.cu) for stride-1 3x3 pad-1 layers with both operands as FP16X2 planes
+ * (Cin % 64 == 0, Cout == 64 or Cout % 128 == 0): x and dy are loaded once per position tile by tiled TMA boxes (zero padding by
+ * out-of-bounds fill) and the nine taps come from UMMA descriptors -- the three column taps as N groups one position apart, the
+ * row taps as separate work units (or, for 64 output channels, as M groups one padded row apart). pc_conv_wgrad routes here when
+ * prec == PC_PREC_FP16X2, xf->presplit, dy_presplit and db == NULL (PC_WGRAD_HALO=0 disables); dw only, no bias gradient. */
+int pc_conv_wgrad_halo_supported(const PcConvGeom* g);
+size_t pc_conv_wgrad_halo_workspace(const PcConvGeom* g);
+int pc_conv_wgrad_halo(const void* x_planes, const void* dy_planes, const PcConvGeom* g, float* dw_oihw, void* workspace,
+                       size_t workspace_bytes, const float* dy_amax, pc_stream_t stream);
+
 /* Stem backward without the full-resolution tensors (csrc/stem_bwd.cu; reference init_conv, src/models/phoneme_cnn.py:211-216):
  * for Conv2d(1, 64, 7, pad 3) -> BatchNorm2d -> ReLU -> MaxPool2d(3, 2, 1) the gradient from the pool is non-zero only at each
  * window's argmax pixel, where the BatchNorm output equals the pooled output; the dense BatchNorm-projection terms of the weight

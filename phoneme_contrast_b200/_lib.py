@@ -76,6 +76,9 @@ SIGNATURES = {
     "pc_tc_gemm": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, vp, sz, vp]),
     "pc_conv_fwd": (i32, [vp, vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, i32, vp]),
     "pc_conv_dgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, i32, i32, vp, i32, vp]),
+    "pc_conv_wgrad_halo_supported": (i32, [C.POINTER(PcConvGeom)]),
+    "pc_conv_wgrad_halo_workspace": (sz, [C.POINTER(PcConvGeom)]),
+    "pc_conv_wgrad_halo": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, vp, sz, vp, vp]),
     "pc_conv_halo_supported": (i32, [C.POINTER(PcConvGeom), i32]),
     "pc_conv_fwd_halo": (i32, [vp, vp, vp, C.POINTER(PcConvGeom), vp, vp, vp]),
     "pc_conv_dgrad_halo": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, i32, vp, vp]),

@@ -750,9 +750,18 @@ extern "C" int pc_conv_wgrad_tc(const float* x, const float* dy, const PcConvGeo
 
 static size_t wgrad_workspace_simt(const PcConvGeom* g);
 
+extern "C" int pc_conv_wgrad_halo_supported(const PcConvGeom* g);
+extern "C" size_t pc_conv_wgrad_halo_workspace(const PcConvGeom* g);
+extern "C" int pc_conv_wgrad_halo(const void* x_planes, const void* dy_planes, const PcConvGeom* g, float* dw_oihw, void* workspace,
+                                  size_t workspace_bytes, const float* dy_amax, pc_stream_t stream);
+
 extern "C" size_t pc_conv_wgrad_workspace(const PcConvGeom* g) {
   if (g == nullptr) return 0;
   size_t a = wgrad_workspace_simt(g);
+  if (pc_conv_wgrad_halo_supported(g)) {
+    const size_t h = pc_conv_wgrad_halo_workspace(g);
+    if (h > a) a = h;
+  }
   if ((g->Cin != 1 && pc_conv_wgrad_tc_supported(g)) || pc_conv_wgrad_tc_stem_supported(g)) {
     const size_t b = pc_conv_wgrad_tc_workspace(g);
     if (b > a) a = b;
@@ -775,6 +784,10 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
   PC_REQUIRE(x && dy && dw_oihw && workspace, PC_EINVAL, "pc_conv_wgrad: null pointer");
   PC_REQUIRE(workspace_bytes >= pc_conv_wgrad_workspace(g), PC_EINVAL, "pc_conv_wgrad: workspace too small (%zu < %zu)", workspace_bytes,
              pc_conv_wgrad_workspace(g));
+  // stride-1 3x3 layers with both operands in plane form and the bias gradient coming from the BatchNorm backward: the halo engine
+  // (csrc/conv_halo_wgrad.cu: operands loaded once per position tile by TMA, taps from descriptors)
+  if (prec == PC_PREC_FP16X2 && dy_presplit && xf != nullptr && xf->presplit && db == nullptr && dy_amax != nullptr && pc_conv_wgrad_halo_supported(g))
+    return pc_conv_wgrad_halo(x, dy, g, dw_oihw, workspace, workspace_bytes, dy_amax, stream);
   // tensor-core path (TF32x3) for eligible layers whenever a tensor-core precision is requested
   if (prec != PC_PREC_FP32 && g->Cin != 1 && pc_conv_wgrad_tc_supported(g))
     return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, dy_presplit, stream);

@@ -153,3 +153,54 @@ def test_halo_1x1_forward_and_dgrad(case, monkeypatch):
     # without accumulation a strided 1x1 gradient must still define every pixel (the per-tap-gather kernel handles it)
     dx = ops.conv_dgrad(dy_ps, cw.wd, g, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
     assert float((dx.double() - refd).abs().max()) <= 1e-5 * dscale
+
+
+WG_CASES = [  # B, H, W, Cin, Cout  (the stride-1 3x3 layers of cnn_deep + ragged batches / channel mixes)
+    (6, 20, 51, 64, 64),
+    (37, 20, 51, 64, 64),
+    (8, 10, 26, 128, 128),
+    (8, 5, 13, 256, 256),
+    (8, 3, 7, 512, 512),
+    (5, 5, 13, 64, 128),
+    (3, 20, 51, 128, 64),
+    (16, 3, 7, 128, 256),
+]
+
+
+@pytest.mark.parametrize("case", WG_CASES)
+def test_halo_wgrad(case, monkeypatch):
+    """Halo weight-gradient engine (csrc/conv_halo_wgrad.cu) against fp64 and against the per-tap-gather kernel on the same planes."""
+    from phoneme_contrast_b200 import _lib as L
+    from phoneme_contrast_b200 import ops
+    import ctypes as C
+    B, H, W, Cin, Cout = case
+    g = ops.conv_geom(B, H, W, Cin, Cout, 3, 1, 1)
+    gen = torch.Generator(device=DEV).manual_seed(B * 13 + Cin + 7 * Cout + H)
+    x = torch.relu(torch.randn(B, H, W, Cin, device=DEV, generator=gen))
+    yconv = torch.randn(B, H, W, Cout, device=DEV, generator=gen)
+    dout = torch.randn(B, H, W, Cout, device=DEV, generator=gen) * 1e-6
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV)
+    st = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    st[0] = yconv.double().sum((0, 1, 2)); st[1] = (yconv.double() ** 2).sum((0, 1, 2))
+    co = ops.bn_finalize(st, B * H * W, bn, True)
+    a0, a1 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    dy, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a0)
+    dy_ps, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a1, planes=True)
+    x_ps = ops.bn_act_split(x)
+    assert L.lib().pc_conv_wgrad_halo_supported(C.byref(g)) == 1
+    dw, _ = ops.conv_wgrad(x_ps, dy_ps, g, dict(presplit=True), prec=L.PREC_FP16X2, dy_amax=a1, dy_presplit=True, want_db=False)
+    torch.cuda.synchronize()
+    # fp64 reference: dW[o][c][r][s] = sum dy[b,h,w,o] x[b,h+r-1,w+s-1,c]
+    xp = torch.nn.functional.pad(x.double().permute(0, 3, 1, 2), (1, 1, 1, 1))
+    dyd = dy.double().permute(0, 3, 1, 2)
+    ref = torch.empty(Cout, Cin, 3, 3, device=DEV, dtype=torch.float64)
+    for r in range(3):
+        for s in range(3):
+            ref[:, :, r, s] = torch.einsum("bohw,bchw->oc", dyd, xp[:, :, r:r + H, s:s + W])
+    scale = float(ref.abs().max())
+    err = float((dw.double() - ref).abs().max())
+    assert err <= 2e-5 * scale, (err, scale)
+    monkeypatch.setenv("PC_WGRAD_HALO", "0")
+    assert L.lib().pc_conv_wgrad_halo_supported(C.byref(g)) == 0
+    dw0, _ = ops.conv_wgrad(x_ps, dy_ps, g, dict(presplit=True), prec=L.PREC_FP16X2, dy_amax=a1, dy_presplit=True, want_db=False)
+    assert float((dw - dw0).abs().max()) <= 1e-5 * scale
