@@ -223,10 +223,11 @@ __global__ void __launch_bounds__(THREADS, 1) wgrad_halo_kernel(const __grid_con
 // sums are combined in a fixed order, so the result does not depend on scheduling.
 __global__ void __launch_bounds__(192 * 4) wgrad_halo_reduce_kernel(const float* __restrict__ partial, int splits, int n_cc, int Cin, int pair,
                                                                     float* __restrict__ dw) {
-  __shared__ double sh[4][192];
-  const int o = blockIdx.x, cc = blockIdx.y, ty = threadIdx.y;
-  for (int j = threadIdx.x; j < 576; j += 192) {
-    const int c = j / 9, tap = j - 9 * c, r = tap / 3, s = tap - 3 * r;
+  __shared__ double sh[4][3][NN];
+  const int o = blockIdx.x, cc = blockIdx.y, n = threadIdx.x, ty = threadIdx.y;
+  // reads follow the partials' own layout (192 consecutive floats per row tap), the (c, r, s) order of OIHW is restored through shared memory
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
     int unit, m;
     if (pair) {              // pass 0: M group 0 = row tap dr = 0 (r = 1), group 1 = dr = -1 (r = 0); pass 1: group 0 = dr = +1 (r = 2)
       unit = cc * 2 + (r == 2 ? 1 : 0);
@@ -235,14 +236,18 @@ __global__ void __launch_bounds__(192 * 4) wgrad_halo_reduce_kernel(const float*
       unit = ((o >> 7) * n_cc + cc) * 3 + r;
       m = o & 127;
     }
-    const float* src = partial + (((size_t)unit * splits) * 128 + m) * NN + s * 64 + c;
+    const float* src = partial + (((size_t)unit * splits) * 128 + m) * NN + n;
     double acc = 0.0;
 #pragma unroll 4
     for (int sp = ty; sp < splits; sp += 4) acc += (double)src[(size_t)sp * 128 * NN];
-    sh[ty][threadIdx.x] = acc;
-    __syncthreads();
-    if (ty == 0) dw[((size_t)o * Cin + cc * 64) * 9 + j] = (float)(((sh[0][threadIdx.x] + sh[1][threadIdx.x]) + sh[2][threadIdx.x]) + sh[3][threadIdx.x]);
-    __syncthreads();
+    sh[ty][r][n] = acc;
+  }
+  __syncthreads();
+  const int j = ty * 192 + n;
+  if (j < 576) {
+    const int c = j / 9, tap = j - 9 * c, r = tap / 3, sc = tap - 3 * r;
+    const int nn = sc * 64 + c;
+    dw[((size_t)o * Cin + cc * 64) * 9 + j] = (float)(((sh[0][r][nn] + sh[1][r][nn]) + sh[2][r][nn]) + sh[3][r][nn]);
   }
 }
 

@@ -223,6 +223,8 @@ def _small_forward(net, x, training):
     slots = _StatSlots([c for c in chans for _ in range(2)], x.device, training)
     s.layers = []
     cur, cin, h, w = x, 1, H, W
+    cur_ps = None            # `cur` once more as fp16 hi | lo planes, when the next convolution runs the FP16X2 plane engine
+    use_planes = prec == L.PREC_FP16X2 and os.environ.get("PC_SMALL_PLANES", "1") == "1"
     for b in range(3):
         convA, bnA, convB, bnB = blocks[b][0], blocks[b][1], blocks[b][3], blocks[b][4]
         co = chans[b]
@@ -234,17 +236,31 @@ def _small_forward(net, x, training):
             cwA = ops.ConvWeights(convA.weight, gA, prec, packer=packer)
             wfA, precA = cwA.wf, cwA.prec_f
         stA = slots.take(co)
-        yA = ops.conv_fwd(cur, wfA, convA.bias, gA, None, stA, precA)
+        # 64- / 128-channel layers run the plane engine of cnn_deep (halo-resident forward / data gradient / weight gradient): their
+        # inputs are written once as fp16 hi | lo planes instead of being transformed and split per tap inside the gather
+        psA = cur_ps is not None and cwA is not None and cwA.prec_f == L.PREC_FP16X2 and cwA.prec_d == L.PREC_FP16X2
+        yA = ops.conv_fwd(cur_ps if psA else cur, wfA, convA.bias, gA, dict(presplit=True) if psA else None, stA, precA)
         coA = ops.bn_finalize(stA, B * gA.Ho * gA.Wo, bnA, training)
         gB = ops.conv_geom(B, h, w, co, co, 3, 1, 1)
         cwB = ops.ConvWeights(convB.weight, gB, prec, packer=packer)
         stB = slots.take(co)
-        yB = ops.conv_fwd(yA, cwB.wf, convB.bias, gB, dict(scale=coA.scale, shift=coA.shift, relu=True), stB, cwB.prec_f)
+        psB = use_planes and co % 64 == 0 and cwB.prec_f == L.PREC_FP16X2 and cwB.prec_d == L.PREC_FP16X2
+        aA = None
+        if psB:
+            aA = ops.bn_act_split(yA, coA.scale, coA.shift, None, relu=True)
+            yB = ops.conv_fwd(aA, cwB.wf, convB.bias, gB, dict(presplit=True), stB, cwB.prec_f)
+        else:
+            yB = ops.conv_fwd(yA, cwB.wf, convB.bias, gB, dict(scale=coA.scale, shift=coA.shift, relu=True), stB, cwB.prec_f)
         coB = ops.bn_finalize(stB, B * h * w, bnB, training)
         pool = 2 if b < 2 else 0
-        out, _ = ops.bn_act_fwd(yB, coB, pool, s.drop[b])
-        s.layers.append(dict(xin=cur, gA=gA, gB=gB, yA=yA, yB=yB, coA=coA, coB=coB, cwA=cwA, cwB=cwB, pool=pool))
-        cur, cin = out, co
+        next_ps = use_planes and b < 2 and co % 64 == 0      # the next block's first convolution gathers co channels
+        if next_ps:
+            out, _, out_ps = ops.bn_act_fwd(yB, coB, pool, s.drop[b], want_planes=True)
+        else:
+            (out, _), out_ps = ops.bn_act_fwd(yB, coB, pool, s.drop[b]), None
+        s.layers.append(dict(xin=cur, xin_ps=cur_ps if psA else None, aA=aA, gA=gA, gB=gB, yA=yA, yB=yB, coA=coA, coB=coB, cwA=cwA, cwB=cwB,
+                             pool=pool))
+        cur, cin, cur_ps = out, co, out_ps
         h, w = ops.pool_dims(h, w, pool)
     s.a_last = cur
     emb = _head(net, s, cur, training)
@@ -267,14 +283,22 @@ def _small_backward(net, s, demb, grads, training=True):
         mB, mA = amax.take(), amax.take()
         dbB_bn, dbB_w = _bias_from_bn(ly["coB"], grads, convB.bias)
         dbA_bn, dbA_w = _bias_from_bn(ly["coA"], grads, convA.bias)
-        dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias], mB, db_conv=dbB_bn)
-        xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
-        wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], dbB_w, prec, mB)
-        dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d, dy_amax=mB)
-        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA, db_conv=dbA_bn)
-        wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], dbA_w, prec, mA)
+        psB, psA = ly["aA"] is not None, ly["xin_ps"] is not None       # gradient tensors in plane form wherever the consumers gather planes
+        dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias], mB, db_conv=dbB_bn,
+                                   planes=psB)
+        if psB:
+            wgrad(ly["aA"], dyB, ly["gB"], dict(presplit=True), grads[convB.weight], dbB_w, prec, mB, True)
+        else:
+            xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
+            wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], dbB_w, prec, mB)
+        dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d, dy_amax=mB, dy_presplit=psB)
+        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA, db_conv=dbA_bn, planes=psA)
+        if psA:
+            wgrad(ly["xin_ps"], dyA, ly["gA"], dict(presplit=True), grads[convA.weight], dbA_w, prec, mA, True)
+        else:
+            wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], dbA_w, prec, mA)
         if b > 0:
-            dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d, dy_amax=mA)
+            dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d, dy_amax=mA, dy_presplit=psA)
         if b == 2:
             if net._split_backward:
                 wgrad.join()
