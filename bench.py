@@ -243,12 +243,16 @@ def bench_train(workload, steps, warmup, parallel, device, want_profile=True, us
     # end to end through the public API with HOST buffers: pinned H2D of this step's views + labels, loss read back every step
     xs_p = [x.pin_memory() for x in xs_h]
     y_p = y_h.pin_memory()
-    for i in range(2):
-        tr.step(xs_p[i % len(xs_p)].to(device, non_blocking=True), y_p.to(device, non_blocking=True)).item()
+    # (the trainer's own loop: ContrastiveTrainer.prefetch copies batch i + 1 on a side stream while step i computes)
+    def host_batches(n):
+        for i in range(n):
+            yield {"views": xs_p[i % len(xs_p)], "label": y_p}
+    for v_d, y_d in tr.prefetch(host_batches(2)):
+        tr.step(v_d, y_d).item()
     barrier(parallel)
     t0 = time.perf_counter()
-    for i in range(steps):
-        float(tr.step(xs_p[i % len(xs_p)].to(device, non_blocking=True), y_p.to(device, non_blocking=True)).item())
+    for v_d, y_d in tr.prefetch(host_batches(steps)):
+        float(tr.step(v_d, y_d).item())
     barrier(parallel)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, parallel, device)
 

@@ -137,8 +137,7 @@ class ContrastiveTrainer:
         num_batches = 0
         sync_each = bool(self.config.get("sync_loss_every_step", False))
         pbar = tqdm(self.train_loader, desc=f"Epoch {self.current_epoch + 1}", disable=not self.config.get("progress", True))
-        for batch in pbar:
-            views, labels = self._prepare_batch(batch)
+        for views, labels in self.prefetch(pbar):
             loss = self.step(views, labels)
             total += loss
             num_batches += 1
@@ -175,6 +174,41 @@ class ContrastiveTrainer:
                 total += self.loss_fn(embeddings, labels)
                 num_batches += 1
         return {"loss": float(total.item()) / max(num_batches, 1)}
+
+    def prefetch(self, batches):
+        """Yields (views, labels) on the device ONE batch ahead: batch i + 1 is copied host -> device on a side stream while step i
+        computes (the reference's loop, trainer.py:138-146, copies and computes back to back). Pinned host batches overlap fully."""
+        if self.device.type != "cuda":
+            for batch in batches:
+                yield self._prepare_batch(batch)
+            return
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+
+        def fetch(batch):
+            self._copy_stream.wait_stream(main)        # (buffers freed by the main stream may be reused by the allocator)
+            with torch.cuda.stream(self._copy_stream):
+                views, labels = self._prepare_batch(batch)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return views, labels, ev
+
+        it = iter(batches)
+        try:
+            nxt = fetch(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            views, labels, ev = nxt
+            try:
+                nxt = fetch(next(it))
+            except StopIteration:
+                nxt = None
+            main.wait_event(ev)
+            views.record_stream(main)
+            labels.record_stream(main)
+            yield views, labels
 
     def _prepare_batch(self, batch: Dict) -> Tuple[torch.Tensor, torch.Tensor]:
         """trainer.py:186-199: H2D, [B,V,C,H,W] -> [B*V,C,H,W], labels repeat_interleave(V)."""

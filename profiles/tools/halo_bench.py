@@ -43,7 +43,9 @@ for (H, W, Cin, Cout) in LAYERS:
     flops = 2.0 * B * H * W * Cin * Cout * 9
     row = [f"{H}x{W} {Cin}->{Cout}"]
     for name, env in (("old", {"PC_CONV_HALO": "0"}), ("stream", {"PC_CONV_HALO": "1", "PC_HALO_CLUSTER": "1", "PC_HALO_RESIDENT": "0"}),
-                      ("default", {"PC_CONV_HALO": "1", "PC_HALO_CLUSTER": "1", "PC_HALO_RESIDENT": "1"})):
+                      ("default", {"PC_CONV_HALO": "1", "PC_HALO_CLUSTER": "1", "PC_HALO_RESIDENT": "1", "PC_HALO_ALL": "1"}),
+                      ("cl2", {"PC_CONV_HALO": "1", "PC_HALO_CLUSTER": "2", "PC_HALO_RESIDENT": "1", "PC_HALO_ALL": "1"}),
+                      ("cl4", {"PC_CONV_HALO": "1", "PC_HALO_CLUSTER": "4", "PC_HALO_RESIDENT": "1", "PC_HALO_ALL": "1"})):
         os.environ.update(env)
         tf = timeit(lambda: ops.conv_fwd(planes, cw.wf, bias, g, dict(presplit=True), st, cw.prec_f))
         td = timeit(lambda: ops.conv_dgrad(dyp, cw.wd, g, prec=cw.prec_d, dy_amax=amax, dy_presplit=True))
