@@ -449,14 +449,13 @@ def bench_pipeline(steps, warmup, device, n_items=2048, views_per_item=2, items_
     batches = [sample_batch() for _ in range(warmup + steps)]
     loader = DeviceFrontendLoader(ds, batches)
     it = iter(loader)
-    for _ in range(warmup):
-        v, y = tr._prepare_batch(next(it))
+    import itertools
+    for v, y in tr.prefetch(itertools.islice(it, warmup)):
         tr.step(v, y)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     loss = None
-    for _ in range(steps):
-        v, y = tr._prepare_batch(next(it))
+    for v, y in tr.prefetch(itertools.islice(it, steps)):      # the trainer's own loop: batch i + 1 is produced on a side stream during step i
         loss = tr.step(v, y)
     loss = float(loss.item())
     dt = time.perf_counter() - t0

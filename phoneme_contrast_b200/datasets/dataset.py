@@ -149,7 +149,10 @@ class PhonemeContrastiveDataset(Dataset):
         recs["clip"] = np.repeat(idx, V).astype(np.int32)          # row of the device cache each view reads: no gather
         views = pack_view_descs(recs, self.device)
         out = self.feature_extractor.forward_views(wave, views, len(idx) * V, noise, n_clips=len(idx))
-        labels = torch.as_tensor([self.labels[i] for i in idx], dtype=torch.int64).to(self.device, non_blocking=True)
+        labels = torch.as_tensor([self.labels[i] for i in idx], dtype=torch.int64)
+        if torch.device(self.device).type == "cuda":
+            labels = labels.pin_memory()
+        labels = labels.to(self.device, non_blocking=True)
         return out.view(len(idx), V, *out.shape[1:]) if V > 1 else out, labels
 
 

@@ -294,4 +294,10 @@ def build_view_descriptors(indices: Sequence[int], n_views: int, n_freq: int, n_
 
 def pack_view_descs(recs: np.ndarray, device) -> torch.Tensor:
     """numpy records -> uint8 CUDA tensor laid out as PcViewDesc[]."""
-    return torch.from_numpy(np.ascontiguousarray(recs).view(np.uint8).copy()).to(device)
+    host = torch.from_numpy(np.ascontiguousarray(recs).view(np.uint8).copy())
+    if torch.device(device).type == "cuda":
+        # pinned staging + asynchronous copy: a pageable copy would block the host until everything queued on the stream before
+        # it (the previous training step) has finished
+        host = host.pin_memory()
+        return host.to(device, non_blocking=True)
+    return host.to(device)

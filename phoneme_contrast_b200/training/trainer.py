@@ -186,25 +186,26 @@ class ContrastiveTrainer:
             self._copy_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
 
-        def fetch(batch):
+        it = iter(batches)
+
+        def fetch():
+            # the loader itself runs under the side stream: a device-resident loader (datasets.DeviceFrontendLoader) launches its
+            # descriptor upload and front-end kernel there, so they overlap the training step as well
             self._copy_stream.wait_stream(main)        # (buffers freed by the main stream may be reused by the allocator)
             with torch.cuda.stream(self._copy_stream):
+                try:
+                    batch = next(it)
+                except StopIteration:
+                    return None
                 views, labels = self._prepare_batch(batch)
                 ev = torch.cuda.Event()
                 ev.record(self._copy_stream)
             return views, labels, ev
 
-        it = iter(batches)
-        try:
-            nxt = fetch(next(it))
-        except StopIteration:
-            return
+        nxt = fetch()
         while nxt is not None:
             views, labels, ev = nxt
-            try:
-                nxt = fetch(next(it))
-            except StopIteration:
-                nxt = None
+            nxt = fetch()
             main.wait_event(ev)
             views.record_stream(main)
             labels.record_stream(main)
