@@ -160,6 +160,27 @@ typedef struct PcInXform {
                          applied; scale/shift/drop must be NULL, relu 0). PC_PREC_FP16X2 tensor-core paths only. */
 } PcInXform;
 
+/* Train-mode BatchNorm finalisation folded into the kernel that first consumes the coefficients (pc_bn_act_split_fin,
+ * pc_bn_add_relu_fwd_fin): stats = the [2][C] fp64 sums (sum y, sum y^2) a convolution accumulated over `count` elements per
+ * channel. Every block derives scale / shift itself; block 0 writes scale, shift (required), mean, invstd (may be NULL), updates
+ * running_mean / running_var (may be NULL, both or neither) with `momentum` and increments num_batches_tracked (may be NULL).
+ * Same arithmetic as pc_bn_finalize(training = 1); saves one dependent launch per BatchNorm layer. */
+typedef struct PcBnFinalize {
+  const double* stats;
+  double count;
+  const float* gamma;
+  const float* beta;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches_tracked;
+  float momentum;
+  float eps;
+  float* scale;
+  float* shift;
+  float* mean;
+  float* invstd;
+} PcBnFinalize;
+
 /* a = drop * relu(scale*y + shift) written ONCE in the tensor-core operand form: planes[0][n_pix*C] = fp16 hi, planes[1] = fp16
  * lo * 2^11 (see PC_PREC_FP16X2). A convolution that reads its input through `presplit` then only copies bytes instead of
  * redoing this arithmetic for every tap and output-channel tile. hw = pixels per sample (row of `drop` = pixel / hw). */
@@ -267,7 +288,8 @@ int pc_stem_bwd(const float* dpool, const float* p0, const uint8_t* argmax, cons
  * planes). pc_stem_stats_from_gram: stats [2][64] fp64 = (sum y0, sum y0^2), the input of pc_bn_finalize. */
 int pc_stem_fwd_supported(int k, int Cout, int H, int W);
 int pc_stem_stats_from_gram(const double* G, const double* X1, const float* w_oihw, const float* bias, int B, int H, int W,
-                            double* stats, pc_stream_t stream);
+                            double* stats, const PcBnFinalize* fin /* may be NULL: also finalise the BatchNorm (train mode) */,
+                            pc_stream_t stream);
 int pc_stem_fwd(const float* x, const float* w_oihw, const float* bias, const float* scale, const float* shift, int B, int H, int W,
                 float* p0, uint8_t* argmax, void* planes, pc_stream_t stream);
 
@@ -304,6 +326,13 @@ int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int H, int W, 
 /* dy_planes (may be NULL): write dy (also) in tensor-core operand form -- fp16 hi | lo planes (pc_bn_act_split layout) of
  * dy * 2^k, with 2^k derived from a bound of |dy| computed from `maxes` and `sums`; the bound is stored in dy_amax (which
  * pc_conv_dgrad / pc_conv_wgrad with dy_presplit != 0 read to undo the scale). `dy` itself may then be NULL. */
+
+/* pc_bn_act_split / pc_bn_add_relu_fwd with the BatchNorm coefficients finalised inside the kernel (PcBnFinalize above).
+ * fin_s == NULL: identity shortcut (ysc is added as it is). */
+int pc_bn_act_split_fin(const float* y, int64_t n_pix, int C, int hw, const PcBnFinalize* fin, const float* drop, int relu,
+                        void* planes, pc_stream_t stream);
+int pc_bn_add_relu_fwd_fin(const float* y2, const PcBnFinalize* fin2, const float* ysc, const PcBnFinalize* fin_s, int64_t n_pix,
+                           int C, float* out, void* planes, pc_stream_t stream);
 
 /* Residual tail: out = relu(bn2(y2) + (sc_scale ? bn_s(ysc) : ysc))   (phoneme_cnn.py:177-182). */
 int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const float* shift2, const float* ysc,

@@ -42,6 +42,12 @@ class PcInXform(C.Structure):
     _fields_ = [("scale", vp), ("shift", vp), ("drop", vp), ("relu", C.c_int32), ("presplit", C.c_int32)]
 
 
+class PcBnFinalize(C.Structure):
+    _fields_ = [("stats", vp), ("count", C.c_double), ("gamma", vp), ("beta", vp), ("running_mean", vp), ("running_var", vp),
+                ("num_batches_tracked", vp), ("momentum", C.c_float), ("eps", C.c_float), ("scale", vp), ("shift", vp), ("mean", vp),
+                ("invstd", vp)]
+
+
 class PcPackJob(C.Structure):
     _fields_ = [("w_oihw", vp), ("out", vp)] + [(n, C.c_int32) for n in ("O", "I", "R", "S", "dgrad", "prec")] + [("item_begin", C.c_int64)]
 
@@ -85,7 +91,7 @@ SIGNATURES = {
     "pc_conv_wgrad_workspace": (sz, [C.POINTER(PcConvGeom)]),
     "pc_conv_wgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, vp, sz, i32, vp, i32, vp]),
     "pc_stem_fwd_supported": (i32, [i32, i32, i32, i32]),
-    "pc_stem_stats_from_gram": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp]),
+    "pc_stem_stats_from_gram": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, C.POINTER(PcBnFinalize), vp]),
     "pc_stem_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp]),
     "pc_stem_bwd_supported": (i32, [i32, i32, i32, i32]),
     "pc_stem_gram": (i32, [vp, i32, i32, i32, vp, vp, vp]),
@@ -96,6 +102,8 @@ SIGNATURES = {
     "pc_bn_act_bwd_reduce": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
     "pc_bn_act_split": (i32, [vp, i64, i32, i32, vp, vp, vp, i32, vp, vp]),
     "pc_f16_overflow_query": (i32, [i32, C.POINTER(C.c_int), vp]),
+    "pc_bn_act_split_fin": (i32, [vp, i64, i32, i32, C.POINTER(PcBnFinalize), vp, i32, vp, vp]),
+    "pc_bn_add_relu_fwd_fin": (i32, [vp, C.POINTER(PcBnFinalize), vp, C.POINTER(PcBnFinalize), i64, i32, vp, vp, vp]),
     "pc_bn_act_bwd_apply": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pc_bn_add_relu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),
     "pc_bn_add_relu_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp]),

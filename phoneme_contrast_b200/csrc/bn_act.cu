@@ -23,13 +23,9 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, doub
   if (c >= C) return;
   float mean, invstd;
   if (training) {
-    const double mu = stats[c] / count;
-    double var = stats[C + c] / count - mu * mu;
-    var = var < 0.0 ? 0.0 : var;
-    mean = (float)mu;
-    invstd = (float)(1.0 / sqrt(var + (double)eps));
+    double unbiased;
+    bn_train_coeffs(stats, C, c, count, eps, mean, invstd, unbiased);
     if (rmean != nullptr) {
-      const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
       rmean[c] = (1.f - momentum) * rmean[c] + momentum * mean;
       rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
     }
@@ -43,6 +39,33 @@ __global__ void bn_finalize_kernel(const double* __restrict__ stats, int C, doub
   shift[c] = b - mean * s;
   if (mean_o != nullptr) mean_o[c] = mean;
   if (invstd_o != nullptr) invstd_o[c] = invstd;
+}
+
+// The same finalisation INSIDE the kernel that first consumes the coefficients (pc_bn_act_split_fin, pc_bn_add_relu_fwd_fin): every
+// block derives scale / shift of all C channels into shared memory (a few hundred fp64 operations), block 0 also publishes them
+// (the backward reads them) and updates the running statistics. Saves one dependent launch per BatchNorm on the critical path.
+__device__ __forceinline__ void bn_finalize_in_block(const PcBnFinalize& f, int C, float* __restrict__ s_scale, float* __restrict__ s_shift) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float mean, invstd;
+    double unbiased;
+    bn_train_coeffs(f.stats, C, c, f.count, f.eps, mean, invstd, unbiased);
+    const float g = f.gamma != nullptr ? f.gamma[c] : 1.f, b = f.beta != nullptr ? f.beta[c] : 0.f;
+    const float sc = g * invstd, sh = b - mean * sc;
+    s_scale[c] = sc;
+    s_shift[c] = sh;
+    if (blockIdx.x == 0) {
+      if (f.running_mean != nullptr) {
+        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+      }
+      f.scale[c] = sc;
+      f.shift[c] = sh;
+      if (f.mean != nullptr) f.mean[c] = mean;
+      if (f.invstd != nullptr) f.invstd[c] = invstd;
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && f.num_batches_tracked != nullptr) f.num_batches_tracked[0] += 1;
+  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------------ helpers
@@ -426,9 +449,19 @@ bn_act_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict_
 __global__ void __launch_bounds__(256)
 bn_add_relu_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ scale2, const float* __restrict__ shift2,
                        const float* __restrict__ ysc, const float* __restrict__ sc_scale, const float* __restrict__ sc_shift,
-                       long long n_pix, int C, float* __restrict__ out, unsigned char* __restrict__ planes) {
+                       long long n_pix, int C, float* __restrict__ out, unsigned char* __restrict__ planes, const PcBnFinalize fin2,
+                       const PcBnFinalize fin_s) {
   pdl_trigger();
   pdl_wait();
+  extern __shared__ __align__(16) float s_fin[];       // [4][C] when the coefficients are finalised here
+  if (fin2.stats != nullptr) {
+    bn_finalize_in_block(fin2, C, s_fin, s_fin + C);
+    scale2 = s_fin; shift2 = s_fin + C;
+    if (fin_s.stats != nullptr) {
+      bn_finalize_in_block(fin_s, C, s_fin + 2 * C, s_fin + 3 * C);
+      sc_scale = s_fin + 2 * C; sc_shift = s_fin + 3 * C;
+    }
+  }
   const int C4 = C >> 2;
   const long long total = n_pix * C4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -615,9 +648,15 @@ bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __rest
 // thread = 8 consecutive channels of one pixel: two float4 loads, two 16-byte stores.
 __global__ void __launch_bounds__(256)
 bn_act_split_kernel(const float* __restrict__ y, long long n_pix, int C, int hw, const float* __restrict__ scale,
-                    const float* __restrict__ shift, const float* __restrict__ drop, int relu, unsigned char* __restrict__ planes) {
+                    const float* __restrict__ shift, const float* __restrict__ drop, int relu, unsigned char* __restrict__ planes,
+                    const PcBnFinalize fin) {
   pdl_trigger();
   pdl_wait();
+  extern __shared__ __align__(16) float s_fin[];       // [2][C] when the coefficients are finalised here
+  if (fin.stats != nullptr) {
+    bn_finalize_in_block(fin, C, s_fin, s_fin + C);
+    scale = s_fin; shift = s_fin + C;
+  }
   const int C8 = C >> 3;
   const long long total = n_pix * C8;
   const size_t plane_bytes = (size_t)n_pix * C * 2;
@@ -711,6 +750,12 @@ static inline void pool_out_dims(int H, int W, int pool, int* Ho, int* Wo) {
 
 using namespace pc;
 
+static int check_fin(const char* fn, const PcBnFinalize* f) {
+  PC_REQUIRE(f->stats && f->count > 0.0 && f->scale && f->shift, PC_EINVAL, "%s: PcBnFinalize needs stats, a positive count and scale / shift outputs", fn);
+  PC_REQUIRE((f->running_mean == nullptr) == (f->running_var == nullptr), PC_EINVAL, "%s: running_mean / running_var mismatch", fn);
+  return PC_OK;
+}
+
 extern "C" int pc_bn_finalize(const double* stats, int C, double count, const float* gamma, const float* beta,
                               float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum,
                               float eps, int training, float* scale, float* shift, float* mean, float* invstd,
@@ -794,8 +839,26 @@ extern "C" int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const fl
   PC_REQUIRE(y2 && scale2 && shift2 && ysc && out && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_fwd: bad arguments");
   PC_REQUIRE((sc_scale == nullptr) == (sc_shift == nullptr), PC_EINVAL, "pc_bn_add_relu_fwd: shortcut scale/shift mismatch");
   PC_CHECK_C4("pc_bn_add_relu_fwd", C);
-  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid(n_pix * (C / 4), 256)), dim3(256), 0, stream, y2, scale2, shift2, ysc, sc_scale, sc_shift, n_pix, C, out, static_cast<unsigned char*>(planes));
+  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid(n_pix * (C / 4), 256)), dim3(256), 0, stream, y2, scale2, shift2, ysc, sc_scale, sc_shift, n_pix, C, out, static_cast<unsigned char*>(planes),
+             PcBnFinalize{}, PcBnFinalize{});
   PC_LAUNCH_CHECK("bn_add_relu_fwd_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_bn_add_relu_fwd_fin(const float* y2, const PcBnFinalize* fin2, const float* ysc, const PcBnFinalize* fin_s, int64_t n_pix, int C,
+                                      float* out, void* planes, pc_stream_t stream) {
+  PC_REQUIRE(y2 && fin2 && ysc && out && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_fwd_fin: bad arguments");
+  PC_CHECK_C4("pc_bn_add_relu_fwd_fin", C);
+  int rc = check_fin("pc_bn_add_relu_fwd_fin", fin2);
+  if (rc != PC_OK) return rc;
+  if (fin_s != nullptr) {
+    rc = check_fin("pc_bn_add_relu_fwd_fin", fin_s);
+    if (rc != PC_OK) return rc;
+  }
+  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid(n_pix * (C / 4), 256)), dim3(256), sizeof(float) * 4 * (size_t)C, stream, y2, (const float*)nullptr,
+             (const float*)nullptr, ysc, (const float*)nullptr, (const float*)nullptr, (long long)n_pix, C, out, static_cast<unsigned char*>(planes), *fin2,
+             fin_s != nullptr ? *fin_s : PcBnFinalize{});
+  PC_LAUNCH_CHECK("bn_add_relu_fwd_kernel<fin>");
   return PC_OK;
 }
 
@@ -851,8 +914,20 @@ extern "C" int pc_bn_act_split(const float* y, int64_t n_pix, int C, int hw, con
   PC_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0, PC_EINVAL,
              "pc_bn_act_split: buffers must be 16-byte aligned");
   launch_pdl(bn_act_split_kernel, dim3(ew_grid(n_pix * (C / 8), 256)), dim3(256), 0, stream, y, (long long)n_pix, C, hw, scale, shift, drop,
-             relu, static_cast<unsigned char*>(planes));
+             relu, static_cast<unsigned char*>(planes), PcBnFinalize{});
   PC_LAUNCH_CHECK("bn_act_split_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_bn_act_split_fin(const float* y, int64_t n_pix, int C, int hw, const PcBnFinalize* fin, const float* drop, int relu,
+                                   void* planes, pc_stream_t stream) {
+  PC_REQUIRE(y && planes && fin && n_pix > 0 && hw > 0, PC_EINVAL, "pc_bn_act_split_fin: bad arguments");
+  PC_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, PC_EUNSUPPORTED, "pc_bn_act_split_fin: channels=%d must be a multiple of 8, at most 1024", C);
+  const int rc = check_fin("pc_bn_act_split_fin", fin);
+  if (rc != PC_OK) return rc;
+  launch_pdl(bn_act_split_kernel, dim3(ew_grid(n_pix * (C / 8), 256)), dim3(256), sizeof(float) * 2 * (size_t)C, stream, y, (long long)n_pix, C, hw,
+             (const float*)nullptr, (const float*)nullptr, drop, relu, static_cast<unsigned char*>(planes), *fin);
+  PC_LAUNCH_CHECK("bn_act_split_kernel<fin>");
   return PC_OK;
 }
 

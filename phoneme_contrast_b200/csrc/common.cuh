@@ -94,6 +94,35 @@ struct FastDiv {
   }
 };
 
+// Train-mode BatchNorm coefficients of one channel from the fp64 sums (sum y, sum y^2): identical arithmetic wherever it is evaluated
+// (pc_bn_finalize, the in-kernel finalisation of csrc/bn_act.cu, the stem statistics kernel). sum_y / sum_y2 are passed by value so that a
+// caller may hand in numbers it has just computed.
+__device__ __forceinline__ void bn_train_coeffs_v(double sum_y, double sum_y2, double count, float eps, float& mean, float& invstd, double& unbiased) {
+  const double mu = sum_y / count;
+  double var = sum_y2 / count - mu * mu;
+  var = var < 0.0 ? 0.0 : var;
+  mean = (float)mu;
+  invstd = (float)(1.0 / sqrt(var + (double)eps));
+  unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+}
+__device__ __forceinline__ void bn_train_coeffs(const double* __restrict__ stats, int C, int c, double count, float eps, float& mean, float& invstd,
+                                                double& unbiased) {
+  bn_train_coeffs_v(stats[c], stats[C + c], count, eps, mean, invstd, unbiased);
+}
+// one channel of a PcBnFinalize: running statistics, published coefficients
+__device__ __forceinline__ void bn_publish_channel(const PcBnFinalize& f, int c, float mean, float invstd, double unbiased) {
+  const float g = f.gamma != nullptr ? f.gamma[c] : 1.f, b = f.beta != nullptr ? f.beta[c] : 0.f;
+  const float sc = g * invstd;
+  if (f.running_mean != nullptr) {
+    f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+    f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)unbiased;
+  }
+  f.scale[c] = sc;
+  f.shift[c] = b - mean * sc;
+  if (f.mean != nullptr) f.mean[c] = mean;
+  if (f.invstd != nullptr) f.invstd[c] = invstd;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

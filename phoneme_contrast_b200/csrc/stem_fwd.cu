@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(THREADS, 1) stem_fwd_kernel(const Params p) {
 
 // stats[0][o] = sum_p y0, stats[1][o] = sum_p y0^2 from the Gram matrix / tap sums of the input patches (fp64); block = channel
 __global__ void __launch_bounds__(64) stem_stats_kernel(const double* __restrict__ G, const double* __restrict__ X1, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, double M, double* __restrict__ stats) {
+                                                        const float* __restrict__ bias, double M, double* __restrict__ stats, const PcBnFinalize fin) {
   __shared__ double s_w[NT], s_a[64], s_b[64];
   const int o = blockIdx.x, t = threadIdx.x;
   if (t < NT) s_w[t] = (double)w[o * NT + t];
@@ -329,8 +329,16 @@ __global__ void __launch_bounds__(64) stem_stats_kernel(const double* __restrict
     double wx = 0.0, wgw = 0.0;
     for (int u = 0; u < NT; ++u) { wx += s_a[u]; wgw += s_b[u]; }
     const double b = bias != nullptr ? (double)bias[o] : 0.0;
-    stats[o] = wx + M * b;
-    stats[CO + o] = wgw + 2.0 * b * wx + M * b * b;
+    const double sy = wx + M * b, sy2 = wgw + 2.0 * b * wx + M * b * b;
+    stats[o] = sy;
+    stats[CO + o] = sy2;
+    if (fin.scale != nullptr) {        // BatchNorm finalisation of this channel right here (one launch less before the stem forward)
+      float mean, invstd;
+      double unbiased;
+      bn_train_coeffs_v(sy, sy2, M, fin.eps, mean, invstd, unbiased);
+      bn_publish_channel(fin, o, mean, invstd, unbiased);
+      if (o == 0 && fin.num_batches_tracked != nullptr) fin.num_batches_tracked[0] += 1;
+    }
   }
 }
 
@@ -343,9 +351,10 @@ using namespace pc::stemf;
 extern "C" int pc_stem_fwd_supported(int k, int Cout, int H, int W) { return (k == 7 && Cout == 64 && H >= 3 && W >= 7 && W <= 128) ? 1 : 0; }
 
 extern "C" int pc_stem_stats_from_gram(const double* G, const double* X1, const float* w_oihw, const float* bias, int B, int H, int W,
-                                       double* stats, pc_stream_t stream) {
+                                       double* stats, const PcBnFinalize* fin, pc_stream_t stream) {
   PC_REQUIRE(G && X1 && w_oihw && stats, PC_EINVAL, "pc_stem_stats_from_gram: null pointer");
-  stem_stats_kernel<<<CO, 64, 0, stream>>>(G, X1, w_oihw, bias, (double)B * H * W, stats);
+  PC_REQUIRE(fin == nullptr || (fin->scale && fin->shift), PC_EINVAL, "pc_stem_stats_from_gram: PcBnFinalize needs scale / shift outputs");
+  stem_stats_kernel<<<CO, 64, 0, stream>>>(G, X1, w_oihw, bias, (double)B * H * W, stats, fin != nullptr ? *fin : PcBnFinalize{});
   PC_LAUNCH_CHECK("stem_stats_kernel");
   return PC_OK;
 }

@@ -240,14 +240,18 @@ def _small_forward(net, x, training):
         # inputs are written once as fp16 hi | lo planes instead of being transformed and split per tap inside the gather
         psA = cur_ps is not None and cwA is not None and cwA.prec_f == L.PREC_FP16X2 and cwA.prec_d == L.PREC_FP16X2
         yA = ops.conv_fwd(cur_ps if psA else cur, wfA, convA.bias, gA, dict(presplit=True) if psA else None, stA, precA)
-        coA = ops.bn_finalize(stA, B * gA.Ho * gA.Wo, bnA, training)
         gB = ops.conv_geom(B, h, w, co, co, 3, 1, 1)
         cwB = ops.ConvWeights(convB.weight, gB, prec, packer=packer)
         stB = slots.take(co)
         psB = use_planes and co % 64 == 0 and cwB.prec_f == L.PREC_FP16X2 and cwB.prec_d == L.PREC_FP16X2
+        fuse_fin = psB and training and os.environ.get("PC_BN_FIN_FUSE", "1") == "1"      # finalise bnA inside the split kernel
+        coA = None if fuse_fin else ops.bn_finalize(stA, B * gA.Ho * gA.Wo, bnA, training)
         aA = None
         if psB:
-            aA = ops.bn_act_split(yA, coA.scale, coA.shift, None, relu=True)
+            if fuse_fin:
+                aA, coA = ops.bn_act_split_fin(yA, stA, B * gA.Ho * gA.Wo, bnA, None, relu=True)
+            else:
+                aA = ops.bn_act_split(yA, coA.scale, coA.shift, None, relu=True)
             yB = ops.conv_fwd(aA, cwB.wf, convB.bias, gB, dict(presplit=True), stB, cwB.prec_f)
         else:
             yB = ops.conv_fwd(yA, cwB.wf, convB.bias, gB, dict(scale=coA.scale, shift=coA.shift, relu=True), stB, cwB.prec_f)
@@ -308,7 +312,20 @@ def _small_backward(net, s, demb, grads, training=True):
 
 def _deep_forward(net, x, training, for_backward=True):
     s = _Saved()
-    packer = _packer_begin(net, x, training)
+    # The batched refresh of the tensor-core weight operands (0.05 ms) is needed by block 0 at the earliest: it runs on the side
+    # stream under the stem (Gram matrix, statistics, one-pass stem forward), which reads the OIHW weights directly
+    pack_side = x.is_cuda and os.environ.get("PC_PACK_STREAM", "1") == "1"
+    if pack_side:
+        if getattr(net, "_side_stream", None) is None:
+            net._side_stream = torch.cuda.Stream()
+        net._side_stream.wait_stream(torch.cuda.current_stream())      # the optimiser's parameter update ran on the main stream
+        with torch.cuda.stream(net._side_stream):
+            packer = _packer_begin(net, x, training)
+        pack_side = packer.replaying          # a recording forward packs layer by layer on the main stream
+        if not pack_side:
+            torch.cuda.current_stream().wait_stream(net._side_stream)
+    else:
+        packer = _packer_begin(net, x, training)
     prec = net._prec
     B, _, H, W = x.shape
     s.x = x
@@ -333,10 +350,12 @@ def _deep_forward(net, x, training, for_backward=True):
     if fused_fwd:
         # One-pass stem (csrc/stem_fwd.cu): the batch statistics of y0 are closed forms in the Gram matrix of the input patches,
         # so BatchNorm is known before the convolution runs and the kernel pools in its epilogue; y0 is never materialised
+        co0 = None
         if training:
             gram = ops.stem_gram(x)
-            ops.stem_stats_from_gram(gram, conv0, B, H, W, st0)
-        co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
+            co0 = ops.stem_stats_from_gram(gram, conv0, B, H, W, st0, bn0 if os.environ.get("PC_BN_FIN_FUSE", "1") == "1" else None)
+        if co0 is None:
+            co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
         p0, argmax0, cur_ps = ops.stem_fwd(x, conv0, co0, want_planes=ps)
     else:
         if want_gram:
@@ -361,6 +380,8 @@ def _deep_forward(net, x, training, for_backward=True):
     cur, cin = p0, hd[0]
     h, w = p0.shape[1], p0.shape[2]
     xps = dict(presplit=True)
+    if pack_side:
+        torch.cuda.current_stream().wait_stream(net._side_stream)     # packed operands ready (joins the side-stream Gram too)
     for i, blk in enumerate(net.conv_blocks):
         co = hd[i]
         if not net.use_residual:
@@ -386,21 +407,29 @@ def _deep_forward(net, x, training, for_backward=True):
         st1 = st(co)
         in_ps = cur_ps if (cur_ps is not None and cw1.prec_f == L.PREC_FP16X2) else None
         y1 = ops.conv_fwd(in_ps if in_ps is not None else cur, cw1.wf, blk.conv1.bias, g1, xps if in_ps is not None else None, st1, cw1.prec_f)
-        c1 = ops.bn_finalize(st1, B * g1.Ho * g1.Wo, blk.bn1, training)
         g2 = ops.conv_geom(B, g1.Ho, g1.Wo, co, co, 3, 1, 1)
         cw2 = ops.ConvWeights(blk.conv2.weight, g2, prec, packer=packer)
+        # train mode on the plane engine: the BatchNorm coefficients are finalised INSIDE the kernel that first applies them
+        # (pc_bn_act_split_fin / pc_bn_add_relu_fwd_fin): one dependent launch less per BatchNorm layer
+        fuse_fin = training and cw2.prec_f == L.PREC_FP16X2 and os.environ.get("PC_BN_FIN_FUSE", "1") == "1"
+        c1 = None if fuse_fin else ops.bn_finalize(st1, B * g1.Ho * g1.Wo, blk.bn1, training)
         st2 = st(co)
         # conv2 reads a1 = drop * relu(bn1(y1)). On the FP16X2 engine a1 is written once as fp16 hi | lo planes (one elementwise
         # pass) and conv2's gather -- and later its weight gradient's -- only copies bytes, instead of redoing BatchNorm + ReLU +
         # dropout + split for every tap and output-channel tile
         a1 = None
         if cw2.prec_f == L.PREC_FP16X2:
-            a1 = ops.bn_act_split(y1, c1.scale, c1.shift, s.drop[i], relu=True)
+            if fuse_fin:
+                a1, c1 = ops.bn_act_split_fin(y1, st1, B * g1.Ho * g1.Wo, blk.bn1, s.drop[i], relu=True)
+            else:
+                a1 = ops.bn_act_split(y1, c1.scale, c1.shift, s.drop[i], relu=True)
             y2 = ops.conv_fwd(a1, cw2.wf, blk.conv2.bias, g2, dict(presplit=True), st2, cw2.prec_f)
         else:
             y2 = ops.conv_fwd(y1, cw2.wf, blk.conv2.bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True, drop=s.drop[i]), st2, cw2.prec_f)
-        c2 = ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk.bn2, training)
+        fuse_tail = training and os.environ.get("PC_BN_FIN_FUSE", "1") == "1"
+        c2 = None if fuse_tail else ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk.bn2, training)
         rec = dict(xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, cw1=cw1, cw2=cw2, proj=len(blk.shortcut) > 0, a1=a1, xin_ps=in_ps)
+        sts = bns = None
         if rec["proj"]:
             convs, bns = blk.shortcut[0], blk.shortcut[1]
             gs = ops.conv_geom(B, h, w, cin, co, 1, stride, 0)
@@ -408,10 +437,17 @@ def _deep_forward(net, x, training, for_backward=True):
             sts = st(co)
             sc_ps = in_ps if cws.prec_f == L.PREC_FP16X2 else None
             ys = ops.conv_fwd(sc_ps if sc_ps is not None else cur, cws.wf, convs.bias, gs, xps if sc_ps is not None else None, sts, cws.prec_f)
-            cs = ops.bn_finalize(sts, B * gs.Ho * gs.Wo, bns, training)
+            cs = None if fuse_tail else ops.bn_finalize(sts, B * gs.Ho * gs.Wo, bns, training)
             rec.update(gs=gs, ys=ys, cs=cs, cws=cws)
         last = i == len(net.conv_blocks) - 1          # the last block's output feeds the attention pool, not a convolution
-        res = ops.bn_add_relu_fwd(y2, c2, rec["ys"] if rec["proj"] else cur, rec["cs"] if rec["proj"] else None, want_planes=ps and not last)
+        if fuse_tail:
+            res, c2, cs = ops.bn_add_relu_fwd_fin(y2, st2, B * g2.Ho * g2.Wo, blk.bn2, rec["ys"] if rec["proj"] else cur, sts, bns,
+                                                  want_planes=ps and not last)
+            rec["c2"] = c2
+            if rec["proj"]:
+                rec["cs"] = cs
+        else:
+            res = ops.bn_add_relu_fwd(y2, c2, rec["ys"] if rec["proj"] else cur, rec["cs"] if rec["proj"] else None, want_planes=ps and not last)
         out, cur_ps = res if (ps and not last) else (res, None)
         rec["out"] = out
         s.blocks.append(rec)

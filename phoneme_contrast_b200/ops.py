@@ -295,6 +295,46 @@ def bn_finalize(stats, count, bn: torch.nn.modules.batchnorm._BatchNorm, trainin
     return co
 
 
+def _bn_fin(stats, count, bn, co: BnCoeffs) -> "L.PcBnFinalize":
+    momentum = 0.1 if bn.momentum is None else bn.momentum
+    return L.PcBnFinalize(ptr(stats, torch.float64), float(count), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
+                          ptr(bn.num_batches_tracked, torch.int64), momentum, bn.eps, ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd))
+
+
+def _new_coeffs(stats, bn) -> BnCoeffs:
+    co = BnCoeffs(bn.num_features, bn.weight.device)
+    co.gamma = bn.weight
+    co.stats = stats
+    return co
+
+
+def bn_act_split_fin(y, stats, count, bn, drop=None, relu=True):
+    """bn_finalize (train mode) + bn_act_split in ONE launch -> (planes, coefficients)."""
+    B, H, W, C_ = y.shape
+    co = _new_coeffs(stats, bn)
+    fin = _bn_fin(stats, count, bn, co)
+    planes = torch.empty(2, y.numel() * 2, device=y.device, dtype=torch.uint8)
+    call("pc_bn_act_split_fin", ptr(y), B * H * W, C_, H * W, C.byref(fin), ptr(drop), 1 if relu else 0, ptr(planes, torch.uint8), stream())
+    return planes, co
+
+
+def bn_add_relu_fwd_fin(y2, stats2, count, bn2, ysc, stats_s=None, bn_s=None, want_planes=False):
+    """bn_finalize of bn2 (and of the projection shortcut's norm) + bn_add_relu_fwd in ONE launch -> (out[, planes], co2, co_s)."""
+    C_ = y2.shape[-1]
+    n_pix = y2.numel() // C_
+    co2 = _new_coeffs(stats2, bn2)
+    fin2 = _bn_fin(stats2, count, bn2, co2)
+    co_s = fin_s = None
+    if bn_s is not None:
+        co_s = _new_coeffs(stats_s, bn_s)
+        fin_s = _bn_fin(stats_s, count, bn_s, co_s)
+    out = torch.empty_like(y2)
+    planes = torch.empty(2, out.numel() * 2, device=y2.device, dtype=torch.uint8) if want_planes else None
+    call("pc_bn_add_relu_fwd_fin", ptr(y2), C.byref(fin2), ptr(ysc), C.byref(fin_s) if fin_s is not None else None, n_pix, C_, ptr(out),
+         ptr(planes, torch.uint8), stream())
+    return ((out, planes) if want_planes else out), co2, co_s
+
+
 def pool_dims(H, W, pool):
     if pool == 0:
         return H, W
@@ -350,10 +390,16 @@ def stem_gram(x):
     return buf
 
 
-def stem_stats_from_gram(gram, conv, B, H, W, stats):
-    """stats [2,64] fp64 = (sum y0, sum y0^2) of y0 = conv(x) + b from the Gram matrix / tap sums of x's patches (closed form)."""
+def stem_stats_from_gram(gram, conv, B, H, W, stats, bn=None):
+    """stats [2,64] fp64 = (sum y0, sum y0^2) of y0 = conv(x) + b from the Gram matrix / tap sums of x's patches (closed form).
+    bn: also finalise that BatchNorm (train mode) in the same launch and return its coefficients."""
+    co = fin = None
+    if bn is not None:
+        co = _new_coeffs(stats, bn)
+        fin = _bn_fin(stats, B * H * W, bn, co)
     call("pc_stem_stats_from_gram", ptr(gram, torch.float64), gram[49 * 49:].data_ptr(), ptr(conv.weight), ptr(conv.bias), B, H, W,
-         ptr(stats, torch.float64), stream())
+         ptr(stats, torch.float64), C.byref(fin) if fin is not None else None, stream())
+    return co
 
 
 def stem_fwd(x, conv, co: BnCoeffs, want_planes=False):
