@@ -37,22 +37,33 @@ WORKLOADS = {
 FLOP_PER_SAMPLE = {"phoneme_cnn": 3 * 298.07e6, "phoneme_cnn_deep": 3 * 568.59e6}   # fwd MAC*2, x3 for training
 
 
-# mean dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels, from profiles/r1_tc_conv_full.md
+# mean dram__bytes_read.sum + dram__bytes_write.sum per launch of the kernels behind each convolution entry point, from the round-2
+# `ncu --set full` capture of one eager cnn_deep step (profiles/r2f_conv_full.md; round 1: profiles/r1d_tc_conv_full.md)
 TRAFFIC_NCU = {}
+TRAFFIC_SRC = None
 try:
     import re as _re
-    _txt = open(os.path.join(ROOT, "profiles", "r1d_tc_conv_full.md")).read()
-    for _entry, _pat in (("pc_conv_fwd", "igemm_tc_kernel"), ("pc_conv_dgrad", "igemm_tc_kernel"), ("pc_conv_wgrad", "wgrad_tc_kernel")):
-        _vals = []
-        for _sec in _txt.split("## ")[1:]:
-            if _pat in _sec.splitlines()[0]:
-                _r = _re.search(r"dram__bytes_read.sum \| ([0-9.]+) \| (\w+)", _sec)
-                _w = _re.search(r"dram__bytes_write.sum \| ([0-9.]+) \| (\w+)", _sec)
-                if _r and _w:
-                    _u = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
-                    _vals.append(float(_r.group(1)) * _u.get(_r.group(2), 1.0) + float(_w.group(1)) * _u.get(_w.group(2), 1.0))
-        if _vals:
-            TRAFFIC_NCU[_entry] = sum(_vals) / len(_vals)
+    for _src in ("r2f_conv_full.md", "r1d_tc_conv_full.md"):
+        _path = os.path.join(ROOT, "profiles", _src)
+        if not os.path.exists(_path):
+            continue
+        _txt = open(_path).read()
+        # forward and data gradient share kernels (conv_halo*, igemm_tc): one figure for both entry points
+        for _entry, _pats in (("pc_conv_fwd", ("conv_halo", "igemm_tc_kernel")), ("pc_conv_dgrad", ("conv_halo", "igemm_tc_kernel")),
+                              ("pc_conv_wgrad", ("wgrad_halo_kernel", "wgrad_tc_kernel"))):
+            _vals = []
+            for _sec in _txt.split("## ")[1:]:
+                if any(_p in _sec.splitlines()[0] for _p in _pats):
+                    _r = _re.search(r"dram__bytes_read.sum \| ([0-9.]+) \| (\w+)", _sec)
+                    _w = _re.search(r"dram__bytes_write.sum \| ([0-9.]+) \| (\w+)", _sec)
+                    _u = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                    if _r and _w:
+                        _vals.append(float(_r.group(1)) * _u.get(_r.group(2), 1.0) + float(_w.group(1)) * _u.get(_w.group(2), 1.0))
+            if _vals:
+                TRAFFIC_NCU[_entry] = sum(_vals) / len(_vals)
+        if TRAFFIC_NCU:
+            TRAFFIC_SRC = "profiles/" + _src
+            break
 except Exception:
     pass
 
@@ -343,13 +354,13 @@ def roofline_from_profile(prof, pk, pk_kind):
     conv_ms = sum(v["ms"] for v in conv.values())
     conv_flop = sum(v["work"] for v in conv.values())
     top = prof[name]
-    kernel_of = {"pc_conv_fwd": "tcconv::igemm_tc_kernel<fwd> (entry pc_conv_fwd; includes the Cin=1 stem kernel)",
-                 "pc_conv_dgrad": "tcconv::igemm_tc_kernel<dgrad> (entry pc_conv_dgrad)",
-                 "pc_conv_wgrad": "tcwg::wgrad_tc_kernel (entry pc_conv_wgrad; includes the split reduce and the stem wgrad kernel)"}
+    kernel_of = {"pc_conv_fwd": "halo::conv_halo_kernel / conv_halo_res_kernel + tcconv::igemm_tc_kernel for the strided layers (entry pc_conv_fwd)",
+                 "pc_conv_dgrad": "halo::conv_halo_kernel / conv_halo_res_kernel + tcconv::igemm_tc_kernel for the strided layers (entry pc_conv_dgrad)",
+                 "pc_conv_wgrad": "halowg::wgrad_halo_kernel (stride-1 3x3 layers) + tcwg::wgrad_tc_kernel (strided / 1x1 layers), incl. their split reduces (entry pc_conv_wgrad)"}
     ach = (top["work"] / (top["ms"] * 1e-3)) / 1e12 if top["work"] else None
     peak = pk.get("bf16_tflops_sustained", pk["bf16_tflops"])
     return {"bound": "tensor", "kernel": kernel_of.get(name, name), "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": (ach / peak) if ach else None,
-            "traffic": TRAFFIC_NCU.get(name), "traffic_note": "mean dram read+write bytes per launch over the launches captured with ncu --set full (profiles/r1d_tc_conv_full.md)",
+            "traffic": TRAFFIC_NCU.get(name), "traffic_note": f"mean dram read+write bytes per launch over this entry point's kernel launches captured with ncu --set full ({TRAFFIC_SRC})",
             "peak_source": f"{pk_kind} cuBLAS bf16 sustained (MEASURED_PEAKS.json); kernel timed inside a long step; achieved counts the convolution's algorithmic fp32 FLOPs once, while the kernels issue 3 fp16 tensor-core products per operand pair (FP16x2 split for fp32-level accuracy), i.e. their own ceiling is peak/3",
             "kernel_share_of_step": top["ms"] / total, "kernel_ms_per_step": top["ms"], "launches_per_step": top["calls"],
             "all_conv": {"ms_per_step": conv_ms, "tflops": conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms else None,
