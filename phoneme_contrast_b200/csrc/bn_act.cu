@@ -482,7 +482,7 @@ bn_add_relu_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ s
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)      // 4 blocks per SM = the grid's cap (reduce_grid2): at 66 registers only 3 fitted and the grid ran 1.33 waves
 bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y2,
                               const float* __restrict__ mean2, const float* __restrict__ invstd2,
                               const float* __restrict__ ysc, const float* __restrict__ mean_s,
@@ -538,7 +538,7 @@ bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __res
   }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)      // 4 resident blocks per SM: the 16-per-SM grid cap (ew_grid) is then exactly 4 waves
 bn_add_relu_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y2,
                              const float* __restrict__ scale2, const float* __restrict__ mean2,
                              const float* __restrict__ invstd2, const double* __restrict__ sums2,
@@ -740,6 +740,30 @@ static inline int ew_grid(long long work_items, int per_block) {
   return (int)g;
 }
 
+// Grid of a grid-stride elementwise kernel in WHOLE waves of its resident blocks (occupancy queried once per kernel and shared-memory
+// size): ew_grid's fixed 16-blocks-per-SM cap left the last wave a third full for kernels that fit 3, 5 or 6 blocks per SM.
+template <typename K>
+static int ew_grid_waves(K kernel, size_t smem, long long work_items, int per_block) {
+  struct Entry { const void* fn; size_t smem; int occ; };
+  static Entry cache[32];
+  static int n_cache = 0;
+  int occ = 0;
+  for (int i = 0; i < n_cache; ++i)
+    if (cache[i].fn == (const void*)kernel && cache[i].smem == smem) occ = cache[i].occ;
+  if (occ == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, smem) != cudaSuccess || occ < 1) occ = 4;
+    if (n_cache < 32) cache[n_cache++] = Entry{(const void*)kernel, smem, occ};
+  }
+  const long long wave = (long long)kNumSMs * occ;
+  long long g = (work_items + per_block - 1) / per_block;
+  if (g > wave) {
+    long long waves = g / wave;
+    if (waves > 4) waves = 4;
+    g = waves * wave;
+  }
+  return (int)(g < 1 ? 1 : g);
+}
+
 static inline void pool_out_dims(int H, int W, int pool, int* Ho, int* Wo) {
   if (pool == 0) { *Ho = H; *Wo = W; }
   else if (pool == 2) { *Ho = H / 2; *Wo = W / 2; }
@@ -784,7 +808,8 @@ extern "C" int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const f
   pool_out_dims(H, W, pool, &Ho, &Wo);
   PC_REQUIRE(Ho > 0 && Wo > 0, PC_EINVAL, "pc_bn_act_fwd: input %dx%d too small for pooling", H, W);
   const long long total = (long long)B * Ho * Wo * (C / 4);
-  const int grid = ew_grid(total, 256);
+  const int grid = pool == 0 ? ew_grid_waves(bn_act_fwd_kernel<0>, 0, total, 256)
+                             : (pool == 2 ? ew_grid_waves(bn_act_fwd_kernel<2>, 0, total, 256) : ew_grid_waves(bn_act_fwd_kernel<3>, 0, total, 256));
   if (pool == 0) launch_pdl((bn_act_fwd_kernel<0>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes));
   else if (pool == 2) launch_pdl((bn_act_fwd_kernel<2>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes));
   else launch_pdl((bn_act_fwd_kernel<3>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes));
@@ -825,7 +850,8 @@ extern "C" int pc_bn_act_bwd_apply(const float* dout, const float* y, int B, int
   int Ho, Wo;
   pool_out_dims(H, W, pool, &Ho, &Wo);
   const long long items = (long long)B * H * W * (C / 4);
-  const int grid = ew_grid(items, 256 * 2);
+  const int grid = pool == 0 ? ew_grid_waves(bn_act_bwd_apply_kernel<0>, 0, items, 256 * 2)
+                             : (pool == 2 ? ew_grid_waves(bn_act_bwd_apply_kernel<2>, 0, items, 256 * 2) : ew_grid_waves(bn_act_bwd_apply_kernel<3>, 0, items, 256 * 2));
   if (pool == 0) launch_pdl((bn_act_bwd_apply_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes), y_stats, db_conv);
   else if (pool == 2) launch_pdl((bn_act_bwd_apply_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes), y_stats, db_conv);
   else launch_pdl((bn_act_bwd_apply_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, dy, dgamma, dbeta, dy_amax, maxes, static_cast<unsigned char*>(dy_planes), y_stats, db_conv);
@@ -839,7 +865,7 @@ extern "C" int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const fl
   PC_REQUIRE(y2 && scale2 && shift2 && ysc && out && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_fwd: bad arguments");
   PC_REQUIRE((sc_scale == nullptr) == (sc_shift == nullptr), PC_EINVAL, "pc_bn_add_relu_fwd: shortcut scale/shift mismatch");
   PC_CHECK_C4("pc_bn_add_relu_fwd", C);
-  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid(n_pix * (C / 4), 256)), dim3(256), 0, stream, y2, scale2, shift2, ysc, sc_scale, sc_shift, n_pix, C, out, static_cast<unsigned char*>(planes),
+  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid_waves(bn_add_relu_fwd_kernel, 0, n_pix * (C / 4), 256)), dim3(256), 0, stream, y2, scale2, shift2, ysc, sc_scale, sc_shift, n_pix, C, out, static_cast<unsigned char*>(planes),
              PcBnFinalize{}, PcBnFinalize{});
   PC_LAUNCH_CHECK("bn_add_relu_fwd_kernel");
   return PC_OK;
@@ -855,7 +881,7 @@ extern "C" int pc_bn_add_relu_fwd_fin(const float* y2, const PcBnFinalize* fin2,
     rc = check_fin("pc_bn_add_relu_fwd_fin", fin_s);
     if (rc != PC_OK) return rc;
   }
-  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid(n_pix * (C / 4), 256)), dim3(256), sizeof(float) * 4 * (size_t)C, stream, y2, (const float*)nullptr,
+  launch_pdl(bn_add_relu_fwd_kernel, dim3(ew_grid_waves(bn_add_relu_fwd_kernel, sizeof(float) * 4 * (size_t)C, n_pix * (C / 4), 256)), dim3(256), sizeof(float) * 4 * (size_t)C, stream, y2, (const float*)nullptr,
              (const float*)nullptr, ysc, (const float*)nullptr, (const float*)nullptr, (long long)n_pix, C, out, static_cast<unsigned char*>(planes), *fin2,
              fin_s != nullptr ? *fin_s : PcBnFinalize{});
   PC_LAUNCH_CHECK("bn_add_relu_fwd_kernel<fin>");
@@ -889,7 +915,7 @@ extern "C" int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, con
              "pc_bn_add_relu_bwd_apply: *_planes need the maxes of the reduce pass and the matching *_amax slot");
   PC_REQUIRE(sc_scale == nullptr || (ysc && mean_s && invstd_s && sums_s), PC_EINVAL, "pc_bn_add_relu_bwd_apply: shortcut pointers");
   PC_CHECK_C4("pc_bn_add_relu_bwd_apply", C);
-  launch_pdl(bn_add_relu_bwd_apply_kernel, dim3(ew_grid(n_pix * (C / 4), 256 * 2)), dim3(256), 0, stream, dout, out, y2, scale2, mean2, invstd2, sums2, ysc, sc_scale, mean_s, invstd_s, sums_s, n_pix, C, dy2, dysc_or_dx,
+  launch_pdl(bn_add_relu_bwd_apply_kernel, dim3(ew_grid_waves(bn_add_relu_bwd_apply_kernel, 0, n_pix * (C / 4), 256 * 2)), dim3(256), 0, stream, dout, out, y2, scale2, mean2, invstd2, sums2, ysc, sc_scale, mean_s, invstd_s, sums_s, n_pix, C, dy2, dysc_or_dx,
       dgamma2, dbeta2, dgamma_s, dbeta_s, dy2_amax, dysc_amax, maxes, static_cast<unsigned char*>(dy2_planes),
       static_cast<unsigned char*>(dysc_planes), y2_stats, db2, ysc_stats, db_s);
   PC_LAUNCH_CHECK("bn_add_relu_bwd_apply_kernel");
@@ -913,7 +939,7 @@ extern "C" int pc_bn_act_split(const float* y, int64_t n_pix, int C, int hw, con
   PC_REQUIRE((scale == nullptr) == (shift == nullptr), PC_EINVAL, "pc_bn_act_split: scale/shift mismatch");
   PC_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(planes) & 15) == 0, PC_EINVAL,
              "pc_bn_act_split: buffers must be 16-byte aligned");
-  launch_pdl(bn_act_split_kernel, dim3(ew_grid(n_pix * (C / 8), 256)), dim3(256), 0, stream, y, (long long)n_pix, C, hw, scale, shift, drop,
+  launch_pdl(bn_act_split_kernel, dim3(ew_grid_waves(bn_act_split_kernel, 0, n_pix * (C / 8), 256)), dim3(256), 0, stream, y, (long long)n_pix, C, hw, scale, shift, drop,
              relu, static_cast<unsigned char*>(planes), PcBnFinalize{});
   PC_LAUNCH_CHECK("bn_act_split_kernel");
   return PC_OK;
@@ -925,7 +951,7 @@ extern "C" int pc_bn_act_split_fin(const float* y, int64_t n_pix, int C, int hw,
   PC_REQUIRE(C > 0 && C % 8 == 0 && C <= 1024, PC_EUNSUPPORTED, "pc_bn_act_split_fin: channels=%d must be a multiple of 8, at most 1024", C);
   const int rc = check_fin("pc_bn_act_split_fin", fin);
   if (rc != PC_OK) return rc;
-  launch_pdl(bn_act_split_kernel, dim3(ew_grid(n_pix * (C / 8), 256)), dim3(256), sizeof(float) * 2 * (size_t)C, stream, y, (long long)n_pix, C, hw,
+  launch_pdl(bn_act_split_kernel, dim3(ew_grid_waves(bn_act_split_kernel, sizeof(float) * 2 * (size_t)C, n_pix * (C / 8), 256)), dim3(256), sizeof(float) * 2 * (size_t)C, stream, y, (long long)n_pix, C, hw,
              (const float*)nullptr, (const float*)nullptr, drop, relu, static_cast<unsigned char*>(planes), *fin);
   PC_LAUNCH_CHECK("bn_act_split_kernel<fin>");
   return PC_OK;
