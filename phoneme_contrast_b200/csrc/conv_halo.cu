@@ -55,7 +55,9 @@ struct Params {
   int ntaps;                 // 9 (3x3) or 1 (1x1 shortcut convolutions)
   int halo;                  // positions staged on either side of a tile: W + 2 (3x3) or 0 (1x1)
   int a_stride;              // 1x1 forward with stride 2: the activation boxes sample every a_stride-th pixel (TMA elementStrides)
-  int Hout, Wout, o_stride;  // output image and pixel stride: position (hp, wp) -> pixel (o_stride (hp-1), o_stride (wp-1)) (1x1 stride-2 dgrad: 2)
+  int Hout, Wout, o_stride;  // output image and pixel stride: position (hp, wp) -> pixel (o_stride (hp-1) + o_off_h, o_stride (wp-1) + o_off_w)
+  int o_off_h, o_off_w;      // (stride-2 data gradients: o_stride = 2, offsets = the output parity class; pixels past the image are dropped)
+  int tap_id[9];             // weight tap (r * 3 + s) behind issued tap t (a stride-2 data gradient issues 1 / 2 / 2 / 4 of the nine per class)
   int b_stages;
   uint32_t region_bytes;     // one part (hi or lo) of an A region: nbox * box_pos * 128, rounded up to 1024
   uint32_t a_tx_bytes;       // bytes the TMA boxes of one region deliver (both parts, unrounded)
@@ -141,8 +143,9 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
       uint32_t b, rem, hp, wp;
       p.d_pimg.divmod((uint32_t)q, b, rem);
       p.d_wp.divmod(rem, hp, wp);
-      valid = hp >= 1u && wp >= 1u;
-      pix = ((long long)b * p.Hout + (long long)p.o_stride * (hp - 1u)) * p.Wout + (long long)p.o_stride * (wp - 1u);
+      const int oh = p.o_stride * ((int)hp - 1) + p.o_off_h, ow = p.o_stride * ((int)wp - 1) + p.o_off_w;
+      valid = hp >= 1u && wp >= 1u && oh < p.Hout && ow < p.Wout;
+      pix = ((long long)b * p.Hout + oh) * p.Wout + ow;
     }
     float* dst_row = p.C + (size_t)(valid ? pix : 0) * p.Nn + n0;
     const uint32_t tb = ti % NBUF;
@@ -339,7 +342,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const __grid_cons
             const uint32_t s = bi % (uint32_t)p.b_stages;
             mbar_wait(&b_empty[s], ((bi / (uint32_t)p.b_stages) & 1u) ^ 1u);
             mbar_arrive_expect_tx(&b_full[s], B_STAGE);
-            const unsigned char* src = p.Bp + (size_t)(t * p.cpt + cc) * kc_stride + (size_t)n0 * 128;
+            const unsigned char* src = p.Bp + (size_t)(p.tap_id[t] * p.cpt + cc) * kc_stride + (size_t)n0 * 128;
             unsigned char* bd = b_buf + (size_t)s * B_STAGE;
             for (int k = 0; k < n_copy; ++k) {
               const uint32_t row0 = (CL == 1 ? (uint32_t)k * BN : rank * copy_rows);      // row inside the [hi ; lo] stage
@@ -613,14 +616,19 @@ static inline int pick_bn(int Nn) { return Nn <= 64 ? 64 : 128; }
 // ntaps = 9: 3x3 stride-1 "same" convolution. ntaps = 1: 1x1 convolution (the residual shortcuts); a_stride = 2 samples every second
 // pixel of the (Ha x Wa) activation tensor (stride-2 forward), o_stride = 2 scatters the rows to every second pixel of the
 // (Hout x Wout) output (stride-2 data gradient, accumulate only: the other pixels receive nothing from this convolution).
+// taps (optional): an explicit tap list -- position shift and weight tap id per issued tap -- with the output parity offsets of a
+// stride-2 3x3 data gradient: dx[2i + p, 2j + q] = sum over the taps (r, s) with r = p + 1 (mod 2), s = q + 1 (mod 2) of
+// dy[i + a, j + b] w[r][s]^T, a = 1 for r = 0 (else 0), b = 1 for s = 0 (else 0): a stride-1 "convolution" of dy per output class.
+struct TapSpec { int n; int shift[9]; int id[9]; int off_h, off_w; };
 static int run(const void* planes, const void* wp, const float* bias, const float* a_amax, float* out, double* stats, int B, int H, int W, int Ca,
                int Nn, int dgrad, int accumulate, pc_stream_t stream, int ntaps = 9, int a_stride = 1, int Ha = 0, int Wa = 0, int Hout = 0,
-               int Wout = 0, int o_stride = 1) {
+               int Wout = 0, int o_stride = 1, const TapSpec* taps = nullptr) {
+  if (taps != nullptr) ntaps = taps->n;
   const int BN = pick_bn(Nn);
   const int Npad = ceil_div(Nn, BN) * BN;
   if (Ha == 0) { Ha = H; Wa = W; }
   if (Hout == 0) { Hout = H; Wout = W; }
-  const int halo = ntaps == 1 ? 0 : W + 2;
+  const int halo = (ntaps == 1 && taps == nullptr) ? 0 : W + 2;
   Plan pl;
   PC_REQUIRE(make_plan(H, W, BN, Npad, pl, halo), PC_EUNSUPPORTED, "conv_halo: image %dx%d does not fit the halo plan", H, W);
   PC_REQUIRE(a_stride * (W + 1) <= 256 && a_stride * pl.RB <= 256, PC_EUNSUPPORTED, "conv_halo: strided box exceeds the TMA box limit");
@@ -642,6 +650,12 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
   // forward: tap (r, s) reads position q + (r-1) (W+1) + (s-1); data gradient: dx[q] = sum dy[q - (r-1)(W+1) - (s-1)] w[r][s]
   for (int r = 0; r < 3; ++r)
     for (int s = 0; s < 3; ++s) p.tap_shift[r * 3 + s] = ntaps == 1 ? 0 : (dgrad ? -1 : 1) * ((r - 1) * p.Wp + (s - 1));
+  for (int t = 0; t < 9; ++t) p.tap_id[t] = ntaps == 1 ? 0 : t;
+  p.o_off_h = p.o_off_w = 0;
+  if (taps != nullptr) {
+    for (int t = 0; t < taps->n; ++t) { p.tap_shift[t] = taps->shift[t]; p.tap_id[t] = taps->id[t]; }
+    p.o_off_h = taps->off_h; p.o_off_w = taps->off_w;
+  }
   p.ntaps = ntaps; p.halo = halo; p.a_stride = a_stride; p.Hout = Hout; p.Wout = Wout; p.o_stride = o_stride;
   p.b_stages = pl.b_stages;
   p.region_bytes = pl.region_bytes;
@@ -662,7 +676,7 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
   // weight-resident variant: one 64-channel chunk, one 64-channel output tile, and all nine taps' weights + one activation
   // region fit the 227 KB of shared memory
   const size_t res_smem = 2 * (size_t)pl.region_bytes + 9 * (size_t)2 * BN * 128 + sizeof(uint64_t) * 10 + 16 + sizeof(float) * 3 * (size_t)Npad + 1024;
-  const bool resident = env_int("PC_HALO_RESIDENT", 1) != 0 && ntaps == 9 && BN == 64 && p.cpt == 1 && p.n_ntiles == 1 && res_smem <= 227 * 1024;
+  const bool resident = env_int("PC_HALO_RESIDENT", 1) != 0 && ntaps == 9 && taps == nullptr && BN == 64 && p.cpt == 1 && p.n_ntiles == 1 && res_smem <= 227 * 1024;
   if (resident) {
     p.cluster = CL = 1;
     p.n_items = p.n_mtiles;
@@ -729,6 +743,19 @@ extern "C" int pc_conv_halo_supported(const PcConvGeom* g, int dgrad) {
     if (g->stride * (g->Wo + 1) > 256) return 0;
     return pc::halo::make_plan(g->Ho, g->Wo, bn1, ceil_div(nn, bn1) * bn1, pl1, 0) && g->stride * pl1.RB <= 256 ? 1 : 0;
   }
+  if (dgrad && g->R == 3 && g->S == 3 && g->stride == 2 && g->pad == 1) {
+    // stride-2 3x3 data gradient as four stride-1 problems over dy, one per output parity class (see TapSpec). Correct
+    // (tests/test_gpu_halo.py::test_halo_stride2_dgrad) but measured SLOWER than the per-tap-gather kernel with its parity-class tap
+    // skipping at 256 views -- pc_conv_dgrad 0.716 ms -> 0.800 (128- and 256-channel dy) -> 0.882 (all three layers): every class
+    // re-loads the dy tile + halo and runs 1 - 4 taps per tile. OFF by default (PC_HALO_S2=1 enables, PC_HALO_ALL=1 adds the 512-channel
+    // layer); the version worth building keeps the four classes' accumulators in TMEM and loads dy once.
+    if (!pc::halo::env_int("PC_HALO_S2", 0)) return 0;
+    if (ca > 256 && !pc::halo::env_int("PC_HALO_ALL", 0)) return 0;
+    if ((long long)g->B * (g->Ho + 1) * (g->Wo + 1) + 4096 >= (1LL << 31) || (long long)g->B * g->H * g->W * (ca > nn ? ca : nn) >= (1LL << 31)) return 0;
+    pc::halo::Plan pl2;
+    const int bn2 = pc::halo::pick_bn(nn);
+    return pc::halo::make_plan(g->Ho, g->Wo, bn2, ceil_div(nn, bn2) * bn2, pl2) ? 1 : 0;
+  }
   if (g->R != 3 || g->S != 3 || g->stride != 1 || g->pad != 1 || g->Ho != g->H || g->Wo != g->W) return 0;
   // Measured per layer at 256 views (profiles/r2_halo_bench.md): 64ch 131 -> 58 us, 128ch 98 -> 77, 512ch 119 -> 107, but 256ch
   // (5x13 images) 76 -> 88: with 4 chunks x 288 KB of streamed weights per tile and only 168 position tiles the per-tap-gather
@@ -755,6 +782,29 @@ extern "C" int pc_conv_dgrad_halo(const void* dy_planes, const void* wp, const P
                                   pc_stream_t stream) {
   PC_REQUIRE(dy_planes && wp && g && dx && dy_amax, PC_EINVAL, "pc_conv_dgrad_halo: null pointer");
   if (!pc_conv_halo_supported(g, 1)) return PC_EUNSUPPORTED;
+  if (g->R == 3 && g->stride == 2) {
+    const int Wp = g->Wo + 1;
+    for (int pc_ = 0; pc_ < 2; ++pc_)
+      for (int qc = 0; qc < 2; ++qc) {
+        pc::halo::TapSpec ts{};
+        ts.off_h = pc_; ts.off_w = qc;
+        for (int r = 0; r < 3; ++r) {
+          if (((r + 1) & 1) != pc_) continue;             // h = 2 ho + r - 1: the parity of h is that of r + 1
+          for (int sx = 0; sx < 3; ++sx) {
+            if (((sx + 1) & 1) != qc) continue;
+            // ho = (h + 1 - r) / 2 = i + (p + 1 - r) / 2 with h = 2 i + p: r = 0 -> i + 1 (p = 1), r = 1 -> i (p = 0), r = 2 -> i (p = 1)
+            const int a = r == 0 ? 1 : 0, b = sx == 0 ? 1 : 0;
+            ts.shift[ts.n] = a * Wp + b;
+            ts.id[ts.n] = r * 3 + sx;
+            ++ts.n;
+          }
+        }
+        const int rc = pc::halo::run(dy_planes, wp, nullptr, dy_amax, dx, nullptr, g->B, g->Ho, g->Wo, g->Cout, g->Cin, 1, accumulate, stream, ts.n, 1,
+                                     g->Ho, g->Wo, g->H, g->W, 2, &ts);
+        if (rc != PC_OK) return rc;
+      }
+    return PC_OK;
+  }
   if (g->R == 1) {
     // dx[b, s ho, s wo, :] (+)= dy[b, ho, wo, :] W^T; with stride 2 the remaining pixels get no contribution, so only accumulation is defined here
     if (g->stride != 1 && !accumulate) return PC_EUNSUPPORTED;

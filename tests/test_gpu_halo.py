@@ -204,3 +204,52 @@ def test_halo_wgrad(case, monkeypatch):
     assert L.lib().pc_conv_wgrad_halo_supported(C.byref(g)) == 0
     dw0, _ = ops.conv_wgrad(x_ps, dy_ps, g, dict(presplit=True), prec=L.PREC_FP16X2, dy_amax=a1, dy_presplit=True, want_db=False)
     assert float((dw - dw0).abs().max()) <= 1e-5 * scale
+
+
+S2_CASES = [  # B, H, W, Cin, Cout  (cnn_deep's stride-2 3x3 layers: data gradient as four parity-class problems over dy)
+    (4, 20, 51, 64, 128),
+    (7, 10, 26, 128, 256),
+    (33, 20, 51, 64, 128),
+    (3, 9, 12, 64, 64),
+]
+
+
+@pytest.mark.parametrize("accumulate", [False, True])
+@pytest.mark.parametrize("case", S2_CASES)
+def test_halo_stride2_dgrad(case, accumulate, monkeypatch):
+    from phoneme_contrast_b200 import _lib as L
+    from phoneme_contrast_b200 import ops
+    import ctypes as C
+    B, H, W, Cin, Cout = case
+    monkeypatch.setenv("PC_HALO_S2", "1")       # off by default: measured slower than the per-tap-gather kernel (csrc/conv_halo.cu)
+    g = ops.conv_geom(B, H, W, Cin, Cout, 3, 2, 1)
+    Ho, Wo = g.Ho, g.Wo
+    gen = torch.Generator(device=DEV).manual_seed(B * 5 + Cin + 11 * Cout + W)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=gen) * (2.0 / (Cin * 9)) ** 0.5
+    yconv = torch.randn(B, Ho, Wo, Cout, device=DEV, generator=gen)
+    dout = torch.randn(B, Ho, Wo, Cout, device=DEV, generator=gen) * 1e-6
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV)
+    st = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    st[0] = yconv.double().sum((0, 1, 2)); st[1] = (yconv.double() ** 2).sum((0, 1, 2))
+    co = ops.bn_finalize(st, B * Ho * Wo, bn, True)
+    cw = ops.ConvWeights(w, g, L.PREC_FP16X2)
+    a0, a1 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    dy, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a0)
+    dy_ps, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a1, planes=True)
+    assert L.lib().pc_conv_halo_supported(C.byref(g), 1) == 1
+    ref = torch.nn.functional.conv_transpose2d(dy.permute(0, 3, 1, 2).double(), w.double(), stride=2, padding=1,
+                                               output_padding=(H - ((Ho - 1) * 2 - 2 + 3), W - ((Wo - 1) * 2 - 2 + 3))).permute(0, 2, 3, 1)
+    assert tuple(ref.shape) == (B, H, W, Cin)
+    scale = float(ref.abs().max())
+    if accumulate:
+        base = torch.randn(B, H, W, Cin, device=DEV, generator=gen) * scale
+        dx = base.clone()
+        ops.conv_dgrad(dy_ps, cw.wd, g, out=dx, accumulate=True, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+        assert float((dx.double() - (base.double() + ref)).abs().max()) <= 1e-5 * scale + 1e-6 * float(base.abs().max())
+    else:
+        dx = ops.conv_dgrad(dy_ps, cw.wd, g, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+        assert float((dx.double() - ref).abs().max()) <= 1e-5 * scale
+        monkeypatch.setenv("PC_HALO_S2", "0")
+        assert L.lib().pc_conv_halo_supported(C.byref(g), 1) == 0
+        dx0 = ops.conv_dgrad(dy_ps, cw.wd, g, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+        assert float((dx - dx0).abs().max()) <= 2e-6 * scale
