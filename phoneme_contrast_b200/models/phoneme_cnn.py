@@ -290,19 +290,20 @@ def _small_backward(net, s, demb, grads, training=True):
         psB, psA = ly["aA"] is not None, ly["xin_ps"] is not None       # gradient tensors in plane form wherever the consumers gather planes
         dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias], mB, db_conv=dbB_bn,
                                    planes=psB)
+        # data gradient (critical path) first, then the weight gradient of the same dy on the side stream (see _deep_backward)
+        dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d, dy_amax=mB, dy_presplit=psB)
         if psB:
             wgrad(ly["aA"], dyB, ly["gB"], dict(presplit=True), grads[convB.weight], dbB_w, prec, mB, True)
         else:
             xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
             wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], dbB_w, prec, mB)
-        dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d, dy_amax=mB, dy_presplit=psB)
         dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA, db_conv=dbA_bn, planes=psA)
+        if b > 0:
+            dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d, dy_amax=mA, dy_presplit=psA)
         if psA:
             wgrad(ly["xin_ps"], dyA, ly["gA"], dict(presplit=True), grads[convA.weight], dbA_w, prec, mA, True)
         else:
             wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], dbA_w, prec, mA)
-        if b > 0:
-            dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d, dy_amax=mA, dy_presplit=psA)
         if b == 2:
             if net._split_backward:
                 wgrad.join()
@@ -501,25 +502,30 @@ def _deep_backward(net, s, demb, grads, training=True):
                                                   (grads[bns.weight], grads[bns.bias]), m2, ms, planes=gps, zp=zp, db2=db2_bn, db_s=dbs_bn)
         else:
             dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None, planes=gps, zp=zp, db2=db2_bn)
+        # Order: the data gradient (main stream, critical path) is issued BEFORE the weight gradient of the same dy (side stream). Both
+        # are persistent one-CTA-per-SM tensor kernels that cannot share an SM; issued the other way round the weight gradient took
+        # the SMs first and the critical path waited (measured: only 0.18 of its 0.76 ms was hidden). Behind the data gradient it
+        # runs under the next layer's BatchNorm-backward passes, which are HBM-bound and co-reside with it.
+        dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2, dy_presplit=gps)
         if r["a1"] is not None and prec == L.PREC_FP16X2:
             wgrad(r["a1"], dy2, r["g2"], dict(presplit=True), grads[blk.conv2.weight], db2_w, prec, m2, gps)
         else:
             xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
             wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], db2_w, prec, m2)
-        dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2, dy_presplit=gps)
         dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1, planes=gps, zp=zp,
                                    db_conv=db1_bn)
         xin_w, xf_w = (r["xin_ps"], dict(presplit=True)) if r["xin_ps"] is not None else (r["xin"], None)
-        wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], db1_w, prec, m1, gps)
         if r["proj"]:
-            wgrad(xin_w, dysc, r["gs"], xf_w, grads[convs.weight], dbs_w, prec, ms, gps)
             # conv1's data gradient writes every pixel of dxin; the strided 1x1 shortcut then adds into the pixels it reads
             # (csrc/conv_halo.cu runs it as an accumulate-only scatter to every second pixel)
             dxin = ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], prec=r["cw1"].prec_d, dy_amax=m1, dy_presplit=gps)
             ops.conv_dgrad(dysc, r["cws"].wd, r["gs"], out=dxin, accumulate=True, prec=r["cws"].prec_d, dy_amax=ms, dy_presplit=gps)
+            wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], db1_w, prec, m1, gps)
+            wgrad(xin_w, dysc, r["gs"], xf_w, grads[convs.weight], dbs_w, prec, ms, gps)
         else:
             dxin = dysc                                        # identity shortcut: d(out)/d(xin) passes g through
             ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d, dy_amax=m1, dy_presplit=gps)
+            wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], db1_w, prec, m1, gps)
         dout = dxin
         if i == len(s.blocks) - 1:
             if net._split_backward:

@@ -40,7 +40,11 @@ class GraphedTrainStep:
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             opt.sync_lr()
-            with torch.cuda.graph(self.graph):
+            # capture on a HIGH-priority stream: the kernel nodes of the main chain inherit it, the weight-gradient lane's side
+            # stream (default = lowest priority) yields the SMs to them whenever both have blocks ready
+            import os
+            prio = int(os.environ.get("PC_GRAPH_PRIORITY", "-1"))
+            with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(priority=prio)):
                 self.loss = trainer.train_step(self.views, self.labels)
         finally:
             # whether capture succeeded or raised, the warm-up steps must be invisible to the optimisation trajectory (the trainer
