@@ -43,7 +43,7 @@ class GraphedTrainStep:
             # capture on a HIGH-priority stream: the kernel nodes of the main chain inherit it, the weight-gradient lane's side
             # stream (default = lowest priority) yields the SMs to them whenever both have blocks ready
             import os
-            prio = int(os.environ.get("PC_GRAPH_PRIORITY", "-1"))
+            prio = int(os.environ.get("PC_GRAPH_PRIORITY", "0"))      # measured: -1 vs 0 within noise (3.04 - 3.07 ms)
             with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(priority=prio)):
                 self.loss = trainer.train_step(self.views, self.labels)
         finally:
