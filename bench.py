@@ -221,8 +221,8 @@ def bench_train(workload, steps, warmup, parallel, device, want_profile=True, us
     rank = 0 if parallel is None else parallel.rank
     world = 1 if parallel is None else parallel.world_size
     tr = build_trainer(arch, device, parallel)
-    # multi-rank steps replay four captured segments with the NCCL exchanges issued eagerly between them (training/graph.py:
-    # GraphedDPStep); capturing the collectives themselves in one whole-step graph deadlocked under torchrun
+    # multi-rank steps replay ONE captured graph whose exchanges are this library's peer-memory kernels over NVLink (training/graph.py:
+    # GraphedDPStepPeer; PC_DP_EXCHANGE=nccl selects the five captured segments with NCCL calls between them, GraphedDPStep)
     use_graph = bool(use_graph)
     tr.config["cuda_graph"] = use_graph
     xs_h, y_h = train_inputs(views, 1000 + rank, device)
@@ -250,6 +250,9 @@ def bench_train(workload, steps, warmup, parallel, device, want_profile=True, us
         launches = (_lib.launch_count() - c0) * steps
     clocks = sampler.stop() if sampler else None
     assert torch.isfinite(loss).item(), "training diverged"
+    if tr._graphed and hasattr(tr._graphed, "check"):
+        tr._graphed.check()            # a peer barrier that timed out would have invalidated the timed steps
+    exchange = type(tr._graphed).__name__ if tr._graphed else "eager"
 
     # end to end through the public API with HOST buffers: pinned H2D of this step's views + labels, loss read back every step
     xs_p = [x.pin_memory() for x in xs_h]
@@ -286,7 +289,7 @@ def bench_train(workload, steps, warmup, parallel, device, want_profile=True, us
     barrier(parallel)
     return dict(arch=arch, views=views, ms_per_step=ms / steps, value=views * world * steps / (ms * 1e-3),
                 e2e_value=views * world * steps / (e2e_ms * 1e-3), launches=launches / steps, clocks=clocks, prof=prof,
-                h2d=views * 4040 * 4 + views * 8, d2h=4, loss=float(loss))
+                h2d=views * 4040 * 4 + views * 8, d2h=4, loss=float(loss), exchange=exchange)
 
 
 def bench_supcon(steps, warmup, parallel, device, n=8192, d=128):
@@ -339,9 +342,12 @@ def bench_supcon(steps, warmup, parallel, device, n=8192, d=128):
         torch.cuda.synchronize()
     barrier(parallel)
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3, parallel, device) / steps
+    if graphed is not None and getattr(graphed, "region", None) is not None:
+        assert graphed.region.error() == 0, "a peer barrier timed out during the timed steps"
     flops = 8.0 * n * n * d / world          # 2N^2D forward + 2N^2D recompute + 4N^2D backward products, per rank 1/R
     return dict(ms_per_step=ms, value=n / (ms * 1e-3), e2e_value=n / (e2e_ms * 1e-3), launches=launches, tflops=flops / (ms * 1e-3) / 1e12,
-                loss=float(loss), h2d=nl * d * 4, d2h=nl * d * 4)
+                loss=float(loss), h2d=nl * d * 4, d2h=nl * d * 4,
+                exchange=("single process" if graphed is None else ("peer memory, one graph" if getattr(graphed, "region", None) is not None else "NCCL all_gathers between three graph segments")))
 
 
 def roofline_from_profile(prof, pk, pk_kind):
@@ -763,7 +769,7 @@ def main():
                              "note": "per-rank algorithmic FLOPs 8*N^2*D/R (forward S, backward S recompute, dF = W F counted twice as in SURVEY 8d's 6N^2D + recompute) / step time; tcgen05 kernels with the FP16x2 operand split (3 fp16 products per pair: own ceiling = peak/3)"},
                 "e2e": {"value": r["e2e_value"], "unit": "views/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
                 "gpu_launches": int(round(r["launches"] * args.steps)),
-                "config": {"workload": wl["desc"], "final_loss": r["loss"], "l2": "F is 4 MB (L2-resident by design: every rank re-reads all N rows); no flush"}}
+                "config": {"workload": wl["desc"], "final_loss": r["loss"], "exchange": r["exchange"], "l2": "F is 4 MB (L2-resident by design: every rank re-reads all N rows); no flush"}}
         clocks = None
     elif args.workload == "frontend":
         r = bench_frontend(args.steps, args.warmup, device)
@@ -783,7 +789,9 @@ def main():
                 "config": workload_config(args.workload, world, args.views_per_gpu),
                 "detail": {"parallelism": f"dp{world}: all_gather(embeddings, labels, row stats) + flat-bucket gradient all-reduce; per-rank BatchNorm statistics",
                            "precision": "fp32 storage and accumulate; convolutions on tcgen05 tensor cores with fp32 operands split into fp16 hi + lo (3 products per pair, ~22-bit operands: fp32-level accuracy, parity-tested at 1e-4), exact-fp32 SIMT for the Cin=1 stem",
-                           "launch": "eager launches" if args.no_graph else ("whole step captured in one CUDA graph (inputs copied into static buffers each step)" if world == 1 else "four captured graph segments per step with the 5 NCCL exchanges issued eagerly between them"),
+                           "launch": "eager launches" if args.no_graph else ("whole step captured in one CUDA graph (inputs copied into static buffers each step)" if world == 1 else
+                                                                            {"GraphedDPStepPeer": "whole data-parallel step captured in ONE CUDA graph; all_gathers and the split gradient all-reduce are this library's kernels over NVLink peer memory (csrc/peer.cu), no NCCL call on the step",
+                                                                             "GraphedDPStep": "five captured graph segments per step with 4 NCCL calls issued eagerly between them"}.get(r["exchange"], r["exchange"])),
                            "l2": "no explicit flush: each step streams ~2 GB of activations (>> 126 MB L2); inputs rotate over 4 device buffers",
                            "step_tflops": FLOP_PER_SAMPLE[r["arch"]] * r["views"] / (r["ms_per_step"] * 1e-3) / 1e12,
                            "final_loss": r["loss"]}}

@@ -396,6 +396,38 @@ int pc_clip_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, co
 /* counter[0] += inc on the stream (device-side step counters for captured steps). */
 int pc_counter_add(int64_t* counter, int64_t inc, pc_stream_t stream);
 
+/* ----------------------------------------------------------------------------------------------
+ * 8. Data-parallel exchanges over NVLink peer memory (csrc/peer.cu; SURVEY.md 8e C1 / C1' / C2 -- absent in the
+ *    single-process reference: the hot loop they serve is src/training/trainer.py:126-164)
+ *    Every rank owns one "peer region" of identical layout, exported with pc_peer_export and mapped by the other
+ *    ranks of the node with pc_peer_open; `bases` is a HOST array of the R region addresses as seen from the calling
+ *    process (own region at index `rank`). The exchanges are ordinary stream-ordered kernels (graph-capturable, no host
+ *    participation, no NCCL).
+ * ---------------------------------------------------------------------------------------------- */
+/* Bytes of the flag block a region reserves at `flag_off` (zero it before the first barrier); most ranks supported. */
+int pc_peer_flag_bytes(void);
+int pc_peer_max_ranks(void);
+/* IPC handle (64 bytes) of the cudaMalloc block containing ptr, and ptr's byte offset inside it. */
+int pc_peer_export(const void* ptr, unsigned char* handle64, size_t* offset);
+/* Map a peer's block into this process (peer access enabled lazily); *base = address of the block's first byte. */
+int pc_peer_open(const unsigned char* handle64, void** base);
+int pc_peer_close(void* base);
+/* Flag barrier between the R ranks on `channel` (0 or 1; each has its own epoch). Writes of earlier kernels of the stream, local or
+ * to peer regions, are visible to every rank's kernels that follow its own barrier. After timeout_ms without a peer's arrival the
+ * region's sticky error word is set (1 + the missing rank) and this and all later barriers return without waiting. */
+int pc_peer_barrier(const unsigned long long* bases, int R, int rank, size_t flag_off, int channel, int timeout_ms, pc_stream_t stream);
+/* *out = the sticky error word (0 = none); synchronises the stream. */
+int pc_peer_error(const unsigned long long* bases, int R, int rank, size_t flag_off, int reset, int* out, pc_stream_t stream);
+/* pc_dp_pack fused with the all_gather: packed rows [n][D+2] are stored at rows [row0, row0+n) of the gathered buffer at byte
+ * offset dst_off of EVERY region. */
+int pc_dp_pack_peer(const float* emb, const int64_t* labels, int n, int D, const unsigned long long* bases, int R, size_t dst_off, int row0,
+                    pc_stream_t stream);
+/* bytes (multiple of 16) from src to byte offset dst_off of every region. */
+int pc_peer_bcast(const void* src, size_t bytes, const unsigned long long* bases, int R, size_t dst_off, pc_stream_t stream);
+/* In-place sum over the ranks of `count` floats (multiple of 4) at byte offset off of every region: rank r reduces slice r in
+ * rank order and stores it to all regions (results bit-identical on every rank). The caller brackets it with barriers. */
+int pc_peer_allreduce(const unsigned long long* bases, int R, int rank, size_t off, long long count, int blocks, pc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

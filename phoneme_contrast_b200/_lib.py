@@ -118,6 +118,16 @@ SIGNATURES = {
     "pc_counter_add": (i32, [vp, i64, vp]),
     "pc_grad_sumsq": (i32, [vp, i64, vp, vp]),
     "pc_clip_adam": (i32, [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, f32, vp, f32, i64, vp]),
+    "pc_peer_flag_bytes": (i32, []),
+    "pc_peer_max_ranks": (i32, []),
+    "pc_peer_export": (i32, [vp, vp, C.POINTER(sz)]),
+    "pc_peer_open": (i32, [vp, C.POINTER(vp)]),
+    "pc_peer_close": (i32, [vp]),
+    "pc_peer_barrier": (i32, [vp, i32, i32, sz, i32, i32, vp]),
+    "pc_peer_error": (i32, [vp, i32, i32, sz, i32, C.POINTER(C.c_int), vp]),
+    "pc_dp_pack_peer": (i32, [vp, vp, i32, i32, vp, i32, sz, i32, vp]),
+    "pc_peer_bcast": (i32, [vp, sz, vp, i32, sz, vp]),
+    "pc_peer_allreduce": (i32, [vp, i32, i32, sz, C.c_longlong, i32, vp]),
 }
 
 _lib = None

@@ -305,7 +305,7 @@ def _small_backward(net, s, demb, grads, training=True):
         else:
             wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], dbA_w, prec, mA)
         if b == 2:
-            if net._split_backward:
+            if net._split_backward is True:
                 wgrad.join()
             yield
     wgrad.join()
@@ -484,7 +484,7 @@ def _deep_backward(net, s, demb, grads, training=True):
             wgrad(r["xin"], dy1, r["g1"], None, grads[blk[0].weight], db1_w, prec, m1)
             dout = ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], prec=r["cw1"].prec_d, dy_amax=m1)
             if i == len(s.blocks) - 1:
-                if net._split_backward:
+                if net._split_backward is True:
                     wgrad.join()
                 yield
             continue
@@ -528,7 +528,7 @@ def _deep_backward(net, s, demb, grads, training=True):
             wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], db1_w, prec, m1, gps)
         dout = dxin
         if i == len(s.blocks) - 1:
-            if net._split_backward:
+            if net._split_backward is True:
                 wgrad.join()
             yield
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
@@ -587,7 +587,10 @@ class _NetFunction(torch.autograd.Function):
 class _FusedNet(BaseModel):
     _inject_drop = None
     _drop_step = None
-    _split_backward = False      # set by the graphed data-parallel step: join the weight-gradient lane at the backward's split point
+    # set by the graphed data-parallel steps. True: join the weight-gradient lane at the backward's split point (a captured segment must
+    # end joined). "fork": do not join -- the caller makes its exchange stream wait for the lane (net._side_stream) itself, so that the
+    # main stream keeps running the backward while the last block's weight gradients finish
+    _split_backward = False
 
     def tail_bucket_offset(self) -> int:
         """Element offset, inside the flat gradient bucket (parameter order), of the first parameter of the LAST conv block: the

@@ -129,12 +129,53 @@ class GraphedShardedLoss:
         for _ in range(warmup):
             self._run_eager()
         torch.cuda.synchronize()
+        # Exchange over NVLink peer memory (peer.PeerRegion, csrc/peer.cu): the packed rows and the row statistics are stored straight
+        # into every rank's gathered buffers by this library's kernels and the whole forward + backward is ONE graph. Falls back
+        # (all ranks together) to the three segments with NCCL all_gathers between them when the regions cannot be mapped.
+        self.region = None
+        if (os.environ.get("PC_DP_EXCHANGE") or "peer") == "peer" and emb_local.is_cuda:
+            try:
+                self._capture_peer(backend, T, Tb, n, d, N, row0, ones)
+            except Exception as exc:      # noqa: BLE001
+                import warnings
+                warnings.warn(f"sharded loss: peer-memory exchange unavailable ({exc}); using NCCL all_gathers")
+                self.region = None
+        if self.region is not None:
+            return
         pool = torch.cuda.graph_pool_handle()
         self.g = [torch.cuda.CUDAGraph() for _ in range(3)]
         with torch.no_grad():
             for g, seg in zip(self.g, self._segs):
                 with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
                     seg()
+
+    def _capture_peer(self, backend, T, Tb, n, d, N, row0, ones):
+        from .peer import PeerRegion
+        region = PeerRegion([("packed", (N, d + 2), torch.float32), ("stats", (N, 4), torch.float32)], self.emb.device, group=self.group)
+        packed_all, stats_all = region.local("packed"), region.local("stats")
+        graph = torch.cuda.CUDAGraph()
+        failure = None
+        try:
+            with torch.no_grad(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                region.pack_rows(self.emb, self.labels, "packed", row0)
+                region.barrier(0)
+                self.F, self.y = backend.unpack(packed_all, d)
+                stats, _ = backend.rows_forward(self.F, self.y, T, Tb, row0, n)
+                self.stats = stats.contiguous()
+                region.bcast(self.stats, "stats", row0 * 16)
+                region.barrier(0)
+                self.total = backend.loss_from_stats(stats_all, T, Tb)
+                self.dF = backend.rows_backward(self.F, self.y, T, (T / Tb) / N, ones, stats_all, row0, n)
+        except Exception as exc:      # noqa: BLE001
+            failure = f"rank {self.ctx.rank}: {exc}"
+        torch.cuda.synchronize()
+        outcomes = [None] * self.ctx.world_size
+        dist.all_gather_object(outcomes, failure, group=self.group)       # succeed or fall back together; host barrier before the first replay
+        outcomes = [o for o in outcomes if o]
+        if outcomes:
+            region.close()
+            raise RuntimeError("; ".join(outcomes))
+        self.region, self.graph = region, graph
 
     def _exchange(self, i):
         if i == 0:
@@ -153,6 +194,9 @@ class GraphedShardedLoss:
             self.emb.copy_(emb_local, non_blocking=True)
         if labels_local is not None:
             self.labels.copy_(labels_local, non_blocking=True)
+        if self.region is not None:
+            self.graph.replay()
+            return self.total.reshape(()), self.dF
         for i, g in enumerate(self.g):
             g.replay()
             self._exchange(i)

@@ -196,3 +196,148 @@ class GraphedDPStep:
         self.g[4].replay()
         self.trainer.optimizer.note_replayed_steps(1)
         return self.total.reshape(()).clone()
+
+
+class GraphedDPStepPeer:
+    """Data-parallel step as ONE captured CUDA graph: the three exchanges run over NVLink peer memory in this library's own kernels
+    (csrc/peer.cu, phoneme_contrast_b200.peer.PeerRegion) instead of NCCL calls between graph segments.
+
+        forward -> pc_dp_pack_peer stores the packed local rows into EVERY rank's gathered buffer        | barrier       C1
+        unpack, SupCon row block -> row statistics -> pc_peer_bcast into every rank's statistics buffer   | barrier       C1'
+        loss from the gathered statistics, SupCon backward, network backward through the head and the LAST block
+          side stream: barrier(ch 1), two-shot pc_peer_allreduce of the bucket tail (74 % of cnn_deep's bytes)            C2a
+          main stream: rest of the network backward; join; barrier; pc_peer_allreduce of the bucket head; barrier        C2b
+        clip + Adam
+
+    The flat gradient bucket itself lives in the peer region, so the all-reduce needs no staging copy. One graph launch per step and
+    no host work between the exchanges: what is exposed per step is five flag barriers (NVLink round trips) and the head of the
+    bucket. The all-reduce adds in rank order and each slice is reduced by exactly one rank, so all ranks hold bit-identical sums."""
+
+    def __init__(self, trainer, views: torch.Tensor, labels: torch.Tensor, warmup: int = 3):
+        import os
+        import torch.distributed as dist
+        from ..models.phoneme_cnn import _prep_input
+        from ..peer import PeerRegion
+        if not isinstance(trainer.optimizer, FusedClipAdam):
+            raise TypeError("CUDA-graph capture needs the FusedClipAdam optimiser (device-resident step count / lr)")
+        par = trainer.parallel
+        lf = trainer.loss_fn
+        if getattr(lf, "reduction", "mean") != "mean" or not hasattr(lf, "temperature"):
+            raise NotImplementedError("the graphed data-parallel step implements the SupCon loss with reduction='mean'")
+        self.trainer = trainer
+        opt, model = trainer.optimizer, trainer.model
+        model.train()
+        dev = views.device
+        n, R = views.shape[0], par.world_size
+        N, row0 = n * R, par.rank * n
+        d = int(model.embedding_dim)
+        n_par = int(model._n_param_elems)
+        n_flat = (n_par + 3) // 4 * 4                     # the all-reduce moves 16-byte words; the pad stays zero
+        self.region = PeerRegion([("packed", (N, d + 2), torch.float32), ("stats", (N, 4), torch.float32), ("flat", (n_flat,), torch.float32)],
+                                 dev, group=par.group)
+        region = self.region
+        self.views = views.clone()
+        self.labels = labels.clone().to(torch.int64)
+        snap_opt = (opt.flat_p.clone(), opt.flat_m.clone(), opt.flat_v.clone(), opt._step_dev.clone(), opt._step)
+        snap_buf = [b.clone() for b in model.buffers()]
+        drop_step = getattr(model, "_drop_step", None)
+        snap_drop = drop_step.clone() if drop_step is not None else None
+        for _ in range(warmup):                               # eager steps (NCCL exchanges): allocator pools, weight-packer recording
+            trainer.train_step(self.views, self.labels)
+        torch.cuda.synchronize()
+        opt.sync_lr()
+
+        T = float(lf.temperature)
+        Tb = float(getattr(lf, "base_temperature", T))
+        clip = float(trainer.config.get("gradient_clip_val") or 0.0)
+        backend = par.backend
+        params = model._param_list
+        self.flat = region.local("flat")[:n_par]
+        packed_all, stats_all = region.local("packed"), region.local("stats")
+        split = (int(model.tail_bucket_offset()) + 3) // 4 * 4          # tail = [split, n_flat) is complete at the backward's split point
+        ar_blocks = int(os.environ.get("PC_PEER_AR_BLOCKS", "0"))
+        grads, off = {}, 0
+        for p in params:
+            grads[p] = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        ones = torch.ones(1, device=dev, dtype=torch.float32)
+        self.graph = torch.cuda.CUDAGraph()
+        self._ar_stream = torch.cuda.Stream()
+        model._split_backward = "fork"
+        failure = None
+        try:
+            with torch.no_grad():
+                with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                    main = torch.cuda.current_stream()
+                    emb, saved = model._engine_forward(_prep_input(self.views, model.in_channels), True)
+                    region.pack_rows(emb.contiguous(), self.labels, "packed", row0)                      # C1: the gather is the store loop
+                    region.barrier(0)
+                    F, y = backend.unpack(packed_all, d)
+                    stats, _ = backend.rows_forward(F, y, T, Tb, row0, n)
+                    region.bcast(stats.contiguous(), "stats", row0 * 16)                                  # C1': row statistics
+                    region.barrier(0)
+                    self.total = backend.loss_from_stats(stats_all, T, Tb)
+                    dF = backend.rows_backward(F, y, T, (T / Tb) / N, ones, stats_all, row0, n)
+                    gen = model._engine_backward_gen(saved, dF.contiguous(), grads)
+                    next(gen)                                    # head + last block: the bucket tail is complete
+                    if split < n_flat:
+                        self._ar_stream.wait_stream(main)
+                        if getattr(model, "_side_stream", None) is not None:
+                            self._ar_stream.wait_stream(model._side_stream)      # the last block's weight gradients (not joined into main)
+                        with torch.cuda.stream(self._ar_stream):
+                            region.barrier(1)
+                            region.allreduce("flat", split, n_flat - split, ar_blocks)                   # C2a under the rest of the backward
+                    for _ in gen:
+                        pass
+                    if split < n_flat:
+                        main.wait_stream(self._ar_stream)
+                    region.barrier(0)                            # every rank: backward finished, its share of the tail reduced and stored
+                    if split > 0:
+                        region.allreduce("flat", 0, split, ar_blocks)                                     # C2b
+                        region.barrier(0)
+                    opt.step(max_grad_norm=clip, flat_grad=self.flat)
+                self._saved = (saved, F, y, emb, dF, stats)
+                for p in params:
+                    if p.requires_grad:
+                        p.grad = grads[p]
+        except Exception as exc:      # noqa: BLE001 -- reported to every rank below
+            failure = f"rank {par.rank}: {exc}"
+        finally:
+            model._split_backward = False
+            with torch.no_grad():
+                opt.flat_p.copy_(snap_opt[0]); opt.flat_m.copy_(snap_opt[1]); opt.flat_v.copy_(snap_opt[2])
+                opt._step_dev.copy_(snap_opt[3]); opt._step = snap_opt[4]
+                for b, sb in zip(model.buffers(), snap_buf):
+                    b.copy_(sb)
+                if getattr(model, "_drop_step", None) is not None:
+                    if snap_drop is not None:
+                        model._drop_step.copy_(snap_drop)
+                    else:
+                        model._drop_step.zero_()
+        torch.cuda.synchronize()
+        # all ranks succeed or fail together (a rank that fell back to NCCL alone would leave the others spinning in a device barrier);
+        # the exchange doubles as the host barrier that keeps anyone from replaying while a peer is still capturing
+        outcomes = [None] * R
+        dist.all_gather_object(outcomes, failure, group=par.group)
+        outcomes = [o for o in outcomes if o]
+        if outcomes:
+            region.close()
+            raise RuntimeError("peer-memory capture failed (" + "; ".join(outcomes) + ")")
+        self.shape = (tuple(views.shape), tuple(labels.shape))
+
+    def matches(self, views: torch.Tensor, labels: torch.Tensor) -> bool:
+        return (tuple(views.shape), tuple(labels.shape)) == self.shape
+
+    def check(self) -> None:
+        """Raises when a device barrier of an earlier step timed out (a peer stopped). Synchronises the stream."""
+        e = self.region.error(reset=True)
+        if e:
+            raise RuntimeError(f"data-parallel peer barrier timed out waiting for rank {e - 1}: the steps since the last check are invalid")
+
+    def __call__(self, views: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        self.views.copy_(views, non_blocking=True)
+        self.labels.copy_(labels, non_blocking=True)
+        self.trainer.optimizer.sync_lr()
+        self.graph.replay()
+        self.trainer.optimizer.note_replayed_steps(1)
+        return self.total.reshape(()).clone()

@@ -97,13 +97,23 @@ class ContrastiveTrainer:
         if not self.config.get("cuda_graph") or not isinstance(self.optimizer, FusedClipAdam):
             return self.train_step(views, labels)
         if self._graphed is None:
-            from .graph import GraphedDPStep, GraphedTrainStep
-            # data parallel: four captured segments with the NCCL exchanges issued eagerly between them
-            try:
-                self._graphed = (GraphedDPStep if self.parallel is not None else GraphedTrainStep)(self, views, labels)
-            except Exception as exc:      # capture is an optimisation: keep training eagerly (training state was restored)
-                self.logger.warning("CUDA-graph capture of the training step failed (%s); continuing with eager launches", exc)
-                self._graphed = False
+            from .graph import GraphedDPStep, GraphedDPStepPeer, GraphedTrainStep
+            kinds = [GraphedTrainStep]
+            if self.parallel is not None:
+                # data parallel: ONE graph with the exchanges over NVLink peer memory (config["dp_exchange"] = "peer", the default on a
+                # CUDA node), or five captured segments with NCCL calls between them ("nccl"; also the fallback when the peer regions
+                # cannot be mapped -- every rank falls back together, see peer.PeerRegion)
+                import os
+                mode = os.environ.get("PC_DP_EXCHANGE") or self.config.get("dp_exchange", "peer")
+                kinds = [GraphedDPStepPeer, GraphedDPStep] if mode == "peer" else [GraphedDPStep]
+            self._graphed = False
+            for kind in kinds:
+                try:
+                    self._graphed = kind(self, views, labels)
+                    break
+                except Exception as exc:      # capture is an optimisation: keep training eagerly (training state was restored)
+                    self.logger.warning("%s: capture of the training step failed (%s)%s", kind.__name__, exc,
+                                        "" if kind is not kinds[-1] else "; continuing with eager launches")
         if self._graphed and self._graphed.matches(views, labels):
             return self._graphed(views, labels)
         return self.train_step(views, labels)
@@ -146,6 +156,8 @@ class ContrastiveTrainer:
                 pbar.set_postfix({"loss": loss.item()})
         mean_loss = float(total.item()) / max(num_batches, 1)     # the epoch's only host sync
         self._check_f16_range()
+        if self._graphed and hasattr(self._graphed, "check"):
+            self._graphed.check()          # peer-memory exchange: a device barrier that timed out (a rank stopped) invalidates the epoch
         return {"loss": mean_loss, "lr": self.optimizer.param_groups[0]["lr"]}
 
     def _check_f16_range(self) -> None:

@@ -62,15 +62,19 @@ def _worker(rank, world, port, out):
         # exact-fp32 kernels so both trajectories are deterministic
         cfg32 = {"dropout_rate": 0.0, "precision": "fp32"}
         finals = []
-        for graph in (False, True):
+        for graph, exch in ((False, "nccl"), (True, "nccl"), (True, "peer")):
             m2 = model_registry.create("phoneme_cnn", cfg32).to(dev)
             m2.load_state_dict(nets_oracle.synthetic_state_dict("phoneme_cnn", cfg32, seed=2))
             o2 = FusedClipAdam(m2.parameters(), lr=1e-3)
             t2 = ContrastiveTrainer(m2, [], None, get_loss_fn("supervised_contrastive", temperature=0.15), o2, None, torch.device(dev),
-                                    {"gradient_clip_val": 1.0, "progress": False, "cuda_graph": graph}, tempfile.mkdtemp(),
+                                    {"gradient_clip_val": 1.0, "progress": False, "cuda_graph": graph, "dp_exchange": exch}, tempfile.mkdtemp(),
                                     logging.getLogger("t"), parallel=ctx)
             m2.train()
             losses = [float(t2.step(x, yl)), float(t2.step(x * 0.5, yl))]
+            if graph:
+                assert type(t2._graphed).__name__ == ("GraphedDPStepPeer" if exch == "peer" else "GraphedDPStep"), type(t2._graphed)
+                if exch == "peer":
+                    t2._graphed.check()
             finals.append((losses, o2.flat_p.cpu(), o2._step, int(o2._step_dev.item())))
         res["graph_vs_eager"] = finals
         torch.save(res, os.path.join(out, f"r{rank}.pt"))
@@ -102,13 +106,15 @@ def test_dp_two_gpus_match_single_process(tmp_path):
     # graphed data-parallel step == eager data-parallel step (same losses; parameters identical up to the order-dependent last
     # bit of the fp64 BatchNorm statistics, cf. test_cuda_graph_step_matches_eager), on every rank, step counters advanced
     for o in outs:
-        (l_e, p_e, s_e, d_e), (l_g, p_g, s_g, d_g) = o["graph_vs_eager"]
-        np.testing.assert_allclose(l_e, l_g, rtol=1e-5)
-        n_off = int(((p_e - p_g).abs() > 2e-5).sum())
-        assert n_off <= 2e-2 * p_e.numel(), (n_off, p_e.numel())
-        assert float((p_e - p_g).abs().max()) <= 2 * 1e-3 * 2
-        assert (s_e, d_e, s_g, d_g) == (2, 2, 2, 2)
-    assert torch.equal(outs[0]["graph_vs_eager"][1][1], outs[1]["graph_vs_eager"][1][1])
+        (l_e, p_e, s_e, d_e) = o["graph_vs_eager"][0]
+        for (l_g, p_g, s_g, d_g) in o["graph_vs_eager"][1:]:          # NCCL segments, then the one-graph peer-memory step
+            np.testing.assert_allclose(l_e, l_g, rtol=1e-5)
+            n_off = int(((p_e - p_g).abs() > 2e-5).sum())
+            assert n_off <= 2e-2 * p_e.numel(), (n_off, p_e.numel())
+            assert float((p_e - p_g).abs().max()) <= 2 * 1e-3 * 2
+            assert (s_e, d_e, s_g, d_g) == (2, 2, 2, 2)
+    for k in (1, 2):
+        assert torch.equal(outs[0]["graph_vs_eager"][k][1], outs[1]["graph_vs_eager"][k][1])
 
 
 # ------------------------------------------------------------------------------------------------ DP step vs R oracle replicas
@@ -137,17 +143,21 @@ def _replica_worker(rank, world, port, out, arch):
         xs, ys = _dp_inputs(world)
         x, y = torch.from_numpy(xs[rank]).to(dev), torch.from_numpy(ys[rank]).to(dev)
         res = {}
-        for graph in (False, True):
+        for mode in ("eager", "graph", "peer"):
+            graph = mode != "eager"
             m = model_registry.create(arch, cfg).to(dev)
             m.load_state_dict(nets_oracle.synthetic_state_dict(arch, cfg, seed=6))
             opt = FusedClipAdam(m.parameters(), lr=3e-4, weight_decay=1e-4)
             tr = ContrastiveTrainer(m, [], None, get_loss_fn("supervised_contrastive", temperature=0.15), opt, None, torch.device(dev),
-                                    {"gradient_clip_val": 1.0, "progress": False, "cuda_graph": graph}, tempfile.mkdtemp(), logging.getLogger("t"), parallel=ctx)
+                                    {"gradient_clip_val": 1.0, "progress": False, "cuda_graph": graph, "dp_exchange": "peer" if mode == "peer" else "nccl"},
+                                    tempfile.mkdtemp(), logging.getLogger("t"), parallel=ctx)
             m.train()
             loss = float(tr.step(x, y))
-            assert (not graph) or tr._graphed, "graphed data-parallel step fell back to eager"
+            assert (not graph) or type(tr._graphed).__name__ == ("GraphedDPStepPeer" if mode == "peer" else "GraphedDPStep"), tr._graphed
+            if mode == "peer":
+                tr._graphed.check()
             names = [n for n, _ in m.named_parameters()]
-            res["graph" if graph else "eager"] = dict(loss=loss, grads={n: p.grad.detach().cpu() for n, p in m.named_parameters()},
+            res[mode] = dict(loss=loss, grads={n: p.grad.detach().cpu() for n, p in m.named_parameters()},
                                                       params={n: p.detach().cpu() for n, p in m.named_parameters()}, names=names,
                                                       rm=m.state_dict()["projection.1.running_mean"].cpu())
         torch.save(res, os.path.join(out, f"rep{rank}.pt"))
@@ -161,7 +171,8 @@ def test_dp_training_step_matches_oracle_replicas(tmp_path, arch):
     """BASELINE configs[4] semantics at a small size (mode (ii)): R ranks with per-rank BatchNorm statistics ==
     R oracle replicas sharing one parameter set whose embeddings are concatenated for ONE global SupCon loss; the all-reduced
     gradient equals the gradient of that loss w.r.t. the shared parameters, and clip + Adam on it gives the ranks' new parameters.
-    Eager exchange path and the graphed five-segment step (3 collectives, split-bucket overlap) are both checked."""
+    Eager exchange path, the graphed five-segment step (3 NCCL collectives, split-bucket overlap) and the ONE-graph step with the
+    exchanges over NVLink peer memory (csrc/peer.cu) are all checked."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from oracle import nets_oracle, optim_oracle, supcon_oracle
@@ -184,7 +195,7 @@ def test_dp_training_step_matches_oracle_replicas(tmp_path, arch):
     gref = [params[n].grad.numpy() for n in names]
     pn = [sd[n].numpy().copy() for n in names]
     optim_oracle.adam_step(pn, gref, [np.zeros_like(p) for p in pn], [np.zeros_like(p) for p in pn], 1, lr=3e-4, weight_decay=1e-4, max_norm=1.0)
-    for mode in ("eager", "graph"):
+    for mode in ("eager", "graph", "peer"):
         for r in range(world):
             o = outs[r][mode]
             assert abs(o["loss"] - float(loss)) <= 1e-4 * abs(float(loss)), (mode, r, o["loss"], float(loss))
