@@ -418,10 +418,10 @@ int pc_peer_close(void* base);
 int pc_peer_barrier(const unsigned long long* bases, int R, int rank, size_t flag_off, int channel, int timeout_ms, pc_stream_t stream);
 /* *out = the sticky error word (0 = none); synchronises the stream. */
 int pc_peer_error(const unsigned long long* bases, int R, int rank, size_t flag_off, int reset, int* out, pc_stream_t stream);
-/* pc_dp_pack fused with the all_gather: packed rows [n][D+2] are stored at rows [row0, row0+n) of the gathered buffer at byte
- * offset dst_off of EVERY region. */
-int pc_dp_pack_peer(const float* emb, const int64_t* labels, int n, int D, const unsigned long long* bases, int R, size_t dst_off, int row0,
-                    pc_stream_t stream);
+/* The embedding / label all_gather as a store loop: emb [n][D] (D % 4 == 0) -> rows [row0, row0+n) of the [N][D] fp32 field at byte
+ * offset f_off, labels [n] -> elements [row0, row0+n) of the [N] int64 field at y_off, of EVERY region. */
+int pc_dp_gather_peer(const float* emb, const int64_t* labels, int n, int D, const unsigned long long* bases, int R, size_t f_off, size_t y_off,
+                      int row0, pc_stream_t stream);
 /* bytes (multiple of 16) from src to byte offset dst_off of every region. */
 int pc_peer_bcast(const void* src, size_t bytes, const unsigned long long* bases, int R, size_t dst_off, pc_stream_t stream);
 /* In-place sum over the ranks of `count` floats (multiple of 4) at byte offset off of every region: rank r reduces slice r in

@@ -125,7 +125,7 @@ SIGNATURES = {
     "pc_peer_close": (i32, [vp]),
     "pc_peer_barrier": (i32, [vp, i32, i32, sz, i32, i32, vp]),
     "pc_peer_error": (i32, [vp, i32, i32, sz, i32, C.POINTER(C.c_int), vp]),
-    "pc_dp_pack_peer": (i32, [vp, vp, i32, i32, vp, i32, sz, i32, vp]),
+    "pc_dp_gather_peer": (i32, [vp, vp, i32, i32, vp, i32, sz, sz, i32, vp]),
     "pc_peer_bcast": (i32, [vp, sz, vp, i32, sz, vp]),
     "pc_peer_allreduce": (i32, [vp, i32, i32, sz, C.c_longlong, i32, vp]),
 }

@@ -1,12 +1,12 @@
 // Data-parallel exchanges over NVLink / NVSwitch PEER MEMORY (new work, the reference is single-process).
 //
 // Every rank owns one "peer region" (a cudaMalloc'ed block exported with cudaIpcGetMemHandle and mapped by all other ranks of the
-// node), laid out identically on all ranks: [flags | gathered embedding rows | gathered row statistics | flat gradient bucket].
+// node), laid out identically on all ranks: [flags | gathered embeddings F | gathered labels | gathered row statistics | flat gradient bucket].
 // The three exchanges of a training step are then plain kernels that load / store through the mapped pointers -- no NCCL call, no
 // host involvement -- so that the WHOLE data-parallel step (forward, loss, backward, exchanges, clip + Adam) is ONE captured CUDA graph:
 //
-//   pc_dp_pack_peer      pack the local [n][D] embeddings + label bits and store the rows straight into EVERY rank's gathered
-//                        buffer (the all_gather is the producer's store loop)
+//   pc_dp_gather_peer    store the local [n][D] embeddings and [n] labels straight into rows [row0, row0 + n) of EVERY rank's gathered
+//                        F / label buffers (the all_gather is the producer's store loop; nothing to pack or unpack)
 //   pc_peer_bcast        same for the [n][4] SupCon row statistics (or any small block)
 //   pc_peer_allreduce    two-shot sum of the flat gradient bucket: rank r loads slice r from every rank (fixed rank order, so the
 //                        result is bit-identical everywhere and independent of timing), adds, and stores the sum back into
@@ -75,20 +75,20 @@ __global__ void __launch_bounds__(32) barrier_kernel(const Bases b, size_t flag_
   if (t == 0) *epoch = e;
 }
 
-// packed row i = D floats of emb[i] followed by the two 32-bit halves of labels[i]; stored at row (row0 + i) of every rank's buffer
-__global__ void __launch_bounds__(256) pack_peer_kernel(const float* __restrict__ emb, const int64_t* __restrict__ labels, int n, int D, const Bases b,
-                                                        size_t dst_off, int row0, int R) {
-  const int ld = D + 2;
-  const long long total = (long long)n * ld;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int r = (int)(i / ld), c = (int)(i - (long long)r * ld);
-    float v;
-    if (c < D) v = emb[(size_t)r * D + c];
-    else {
-      const unsigned long long bits = (unsigned long long)labels[r];
-      v = __uint_as_float(c == D ? (uint32_t)(bits & 0xFFFFFFFFull) : (uint32_t)(bits >> 32));
+// the all_gather of embeddings and labels as the producer's store loop: emb[i][:] -> row (row0 + i) of the [N][D] field at f_off and
+// labels[i] -> element (row0 + i) of the [N] int64 field at y_off of EVERY rank's region (D % 4 == 0; no packing / unpacking pass)
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restrict__ emb, const int64_t* __restrict__ labels, int n, int D4, const Bases b,
+                                                          size_t f_off, size_t y_off, int row0, int R) {
+  const long long total = (long long)n * D4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total + n; i += (long long)gridDim.x * blockDim.x) {
+    if (i < total) {
+      const float4 v = emb[i];
+      for (int k = 0; k < R; ++k) reinterpret_cast<float4*>(b.p[k] + f_off)[(size_t)row0 * D4 + i] = v;
+    } else {
+      const int r = (int)(i - total);
+      const int64_t v = labels[r];
+      for (int k = 0; k < R; ++k) reinterpret_cast<int64_t*>(b.p[k] + y_off)[row0 + r] = v;
     }
-    for (int k = 0; k < R; ++k) reinterpret_cast<float*>(b.p[k] + dst_off)[(size_t)row0 * ld + i] = v;
   }
 }
 
@@ -203,15 +203,16 @@ extern "C" int pc_peer_error(const unsigned long long* bases, int R, int rank, s
   return PC_OK;
 }
 
-extern "C" int pc_dp_pack_peer(const float* emb, const int64_t* labels, int n, int D, const unsigned long long* bases, int R, size_t dst_off, int row0,
-                               pc_stream_t stream) {
-  PC_REQUIRE(emb && labels && n > 0 && D > 0 && row0 >= 0 && dst_off % 16 == 0, PC_EINVAL, "pc_dp_pack_peer: bad arguments");
+extern "C" int pc_dp_gather_peer(const float* emb, const int64_t* labels, int n, int D, const unsigned long long* bases, int R, size_t f_off, size_t y_off,
+                                 int row0, pc_stream_t stream) {
+  PC_REQUIRE(emb && labels && n > 0 && D > 0 && D % 4 == 0 && row0 >= 0 && f_off % 16 == 0 && y_off % 8 == 0 && (reinterpret_cast<uintptr_t>(emb) & 15u) == 0,
+             PC_EINVAL, "pc_dp_gather_peer: bad arguments (D must be a multiple of 4, emb and the field offsets 16-byte aligned)");
   Bases b;
   if (int rc = pc::peer::load_bases(bases, R, b)) return rc;
-  int grid = ceil_div((long long)n * (D + 2), 256);
+  int grid = ceil_div((long long)n * (D / 4) + n, 256);
   if (grid > kNumSMs) grid = kNumSMs;
-  pc::peer::pack_peer_kernel<<<grid, 256, 0, stream>>>(emb, labels, n, D, b, dst_off, row0, R);
-  PC_LAUNCH_CHECK("peer::pack_peer_kernel");
+  pc::peer::gather_rows_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(emb), labels, n, D / 4, b, f_off, y_off, row0, R);
+  PC_LAUNCH_CHECK("peer::gather_rows_kernel");
   return PC_OK;
 }
 

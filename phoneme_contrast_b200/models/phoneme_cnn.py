@@ -304,7 +304,7 @@ def _small_backward(net, s, demb, grads, training=True):
             wgrad(ly["xin_ps"], dyA, ly["gA"], dict(presplit=True), grads[convA.weight], dbA_w, prec, mA, True)
         else:
             wgrad(ly["xin"], dyA, ly["gA"], None, grads[convA.weight], dbA_w, prec, mA)
-        if b == 2:
+        if b == 2 or (b == 1 and net._split_backward == "fork"):
             if net._split_backward is True:
                 wgrad.join()
             yield
@@ -483,7 +483,7 @@ def _deep_backward(net, s, demb, grads, training=True):
             dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, None, None, grads[blk[1].weight], grads[blk[1].bias], m1, zp=zp, db_conv=db1_bn)
             wgrad(r["xin"], dy1, r["g1"], None, grads[blk[0].weight], db1_w, prec, m1)
             dout = ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], prec=r["cw1"].prec_d, dy_amax=m1)
-            if i == len(s.blocks) - 1:
+            if i == len(s.blocks) - 1 or (i == len(s.blocks) - 2 and i >= 1 and net._split_backward == "fork"):
                 if net._split_backward is True:
                     wgrad.join()
                 yield
@@ -527,7 +527,7 @@ def _deep_backward(net, s, demb, grads, training=True):
             ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], out=dxin, accumulate=True, prec=r["cw1"].prec_d, dy_amax=m1, dy_presplit=gps)
             wgrad(xin_w, dy1, r["g1"], xf_w, grads[blk.conv1.weight], db1_w, prec, m1, gps)
         dout = dxin
-        if i == len(s.blocks) - 1:
+        if i == len(s.blocks) - 1 or (i == len(s.blocks) - 2 and i >= 1 and net._split_backward == "fork"):
             if net._split_backward is True:
                 wgrad.join()
             yield
@@ -603,6 +603,23 @@ class _FusedNet(BaseModel):
                 return off
             off += p.numel()
         raise RuntimeError("last block's parameters not found")
+
+    def tail_bucket_offsets(self):
+        """Element offsets of the first parameter of the LAST and of the SECOND-TO-LAST conv block (descending): the bucket is complete
+        from offsets[k] on when the backward generator yields for the (k+1)-th time."""
+        offs = []
+        nb = len(self.conv_blocks)
+        for bi in (nb - 1, nb - 2):
+            if bi < 1:
+                break
+            first = next(self.conv_blocks[bi].parameters())
+            off = 0
+            for p in self.parameters():
+                if p is first:
+                    offs.append(off)
+                    break
+                off += p.numel()
+        return offs
 
     def _finish_init(self):
         _init_weights(self)

@@ -151,15 +151,16 @@ class GraphedShardedLoss:
 
     def _capture_peer(self, backend, T, Tb, n, d, N, row0, ones):
         from .peer import PeerRegion
-        region = PeerRegion([("packed", (N, d + 2), torch.float32), ("stats", (N, 4), torch.float32)], self.emb.device, group=self.group)
-        packed_all, stats_all = region.local("packed"), region.local("stats")
+        region = PeerRegion([("F", (N, d), torch.float32), ("y", (N,), torch.int64), ("stats", (N, 4), torch.float32)], self.emb.device,
+                            group=self.group)
+        stats_all = region.local("stats")
         graph = torch.cuda.CUDAGraph()
         failure = None
         try:
             with torch.no_grad(), torch.cuda.graph(graph, capture_error_mode="thread_local"):
-                region.pack_rows(self.emb, self.labels, "packed", row0)
+                region.gather_rows(self.emb, self.labels, "F", "y", row0)
                 region.barrier(0)
-                self.F, self.y = backend.unpack(packed_all, d)
+                self.F, self.y = region.local("F"), region.local("y")
                 stats, _ = backend.rows_forward(self.F, self.y, T, Tb, row0, n)
                 self.stats = stats.contiguous()
                 region.bcast(self.stats, "stats", row0 * 16)

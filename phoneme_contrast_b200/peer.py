@@ -102,10 +102,12 @@ class PeerRegion:
     def barrier(self, channel: int = 0) -> None:
         L.call("pc_peer_barrier", self.bases, self.world_size, self.rank, self.flag_off, int(channel), self.timeout_ms, L.stream())
 
-    def pack_rows(self, emb: torch.Tensor, labels: torch.Tensor, name: str, row0: int) -> None:
-        """emb [n, D] + labels [n] int64 -> rows [row0, row0 + n) of the [N, D + 2] field `name` of EVERY rank."""
+    def gather_rows(self, emb: torch.Tensor, labels: torch.Tensor, f_name: str, y_name: str, row0: int) -> None:
+        """emb [n, D] -> rows [row0, row0 + n) of the [N, D] field f_name, labels [n] int64 -> the same rows of the [N] field y_name,
+        of EVERY rank."""
         n, D = emb.shape
-        L.call("pc_dp_pack_peer", L.ptr(emb), L.ptr(labels, torch.int64), n, D, self.bases, self.world_size, self.offset(name) , int(row0), L.stream())
+        L.call("pc_dp_gather_peer", L.ptr(emb), L.ptr(labels, torch.int64), n, D, self.bases, self.world_size, self.offset(f_name),
+               self.offset(y_name), int(row0), L.stream())
 
     def bcast(self, src: torch.Tensor, name: str, byte_off: int = 0) -> None:
         """The bytes of `src` -> byte offset byte_off of the field `name` of EVERY rank."""

@@ -202,11 +202,12 @@ class GraphedDPStepPeer:
     """Data-parallel step as ONE captured CUDA graph: the three exchanges run over NVLink peer memory in this library's own kernels
     (csrc/peer.cu, phoneme_contrast_b200.peer.PeerRegion) instead of NCCL calls between graph segments.
 
-        forward -> pc_dp_pack_peer stores the packed local rows into EVERY rank's gathered buffer        | barrier       C1
-        unpack, SupCon row block -> row statistics -> pc_peer_bcast into every rank's statistics buffer   | barrier       C1'
-        loss from the gathered statistics, SupCon backward, network backward through the head and the LAST block
-          side stream: barrier(ch 1), two-shot pc_peer_allreduce of the bucket tail (74 % of cnn_deep's bytes)            C2a
-          main stream: rest of the network backward; join; barrier; pc_peer_allreduce of the bucket head; barrier        C2b
+        forward -> pc_dp_gather_peer stores the local embeddings / labels into EVERY rank's gathered F / y     | barrier       C1
+        SupCon row block -> row statistics -> pc_peer_bcast into every rank's statistics buffer             | barrier       C1'
+        SupCon backward, network backward; whenever a part of the bucket is complete (head + last block = 74 % of cnn_deep's
+        bytes, then the block before it = 18 %):
+          side stream: barrier(ch 1), two-shot pc_peer_allreduce of that part (+ the loss value from the gathered statistics)  C2a
+          main stream: rest of the network backward; join; barrier; pc_peer_allreduce of the remainder (7 %); barrier        C2b
         clip + Adam
 
     The flat gradient bucket itself lives in the peer region, so the all-reduce needs no staging copy. One graph launch per step and
@@ -233,8 +234,8 @@ class GraphedDPStepPeer:
         d = int(model.embedding_dim)
         n_par = int(model._n_param_elems)
         n_flat = (n_par + 3) // 4 * 4                     # the all-reduce moves 16-byte words; the pad stays zero
-        self.region = PeerRegion([("packed", (N, d + 2), torch.float32), ("stats", (N, 4), torch.float32), ("flat", (n_flat,), torch.float32)],
-                                 dev, group=par.group)
+        self.region = PeerRegion([("F", (N, d), torch.float32), ("y", (N,), torch.int64), ("stats", (N, 4), torch.float32),
+                                  ("flat", (n_flat,), torch.float32)], dev, group=par.group)
         region = self.region
         self.views = views.clone()
         self.labels = labels.clone().to(torch.int64)
@@ -253,8 +254,10 @@ class GraphedDPStepPeer:
         backend = par.backend
         params = model._param_list
         self.flat = region.local("flat")[:n_par]
-        packed_all, stats_all = region.local("packed"), region.local("stats")
-        split = (int(model.tail_bucket_offset()) + 3) // 4 * 4          # tail = [split, n_flat) is complete at the backward's split point
+        F, y, stats_all = region.local("F"), region.local("y"), region.local("stats")
+        # the bucket is exchanged in up to three parts, each as soon as the backward has completed it (tail_bucket_offsets: last block +
+        # head, then the block before it); only the small remainder is reduced after the backward
+        cuts = sorted({(int(o) + 3) // 4 * 4 for o in model.tail_bucket_offsets()}, reverse=True)
         ar_blocks = int(os.environ.get("PC_PEER_AR_BLOCKS", "0"))
         grads, off = {}, 0
         for p in params:
@@ -270,30 +273,40 @@ class GraphedDPStepPeer:
                 with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                     main = torch.cuda.current_stream()
                     emb, saved = model._engine_forward(_prep_input(self.views, model.in_channels), True)
-                    region.pack_rows(emb.contiguous(), self.labels, "packed", row0)                      # C1: the gather is the store loop
+                    region.gather_rows(emb.contiguous(), self.labels, "F", "y", row0)                     # C1: the gather is the store loop
                     region.barrier(0)
-                    F, y = backend.unpack(packed_all, d)
                     stats, _ = backend.rows_forward(F, y, T, Tb, row0, n)
                     region.bcast(stats.contiguous(), "stats", row0 * 16)                                  # C1': row statistics
                     region.barrier(0)
-                    self.total = backend.loss_from_stats(stats_all, T, Tb)
                     dF = backend.rows_backward(F, y, T, (T / Tb) / N, ones, stats_all, row0, n)
                     gen = model._engine_backward_gen(saved, dF.contiguous(), grads)
-                    next(gen)                                    # head + last block: the bucket tail is complete
-                    if split < n_flat:
+                    hi, first = n_flat, True
+                    for cut in cuts:
+                        try:
+                            next(gen)                            # the bucket is complete from `cut` on
+                        except StopIteration:
+                            break
+                        if cut >= hi:
+                            continue
                         self._ar_stream.wait_stream(main)
                         if getattr(model, "_side_stream", None) is not None:
-                            self._ar_stream.wait_stream(model._side_stream)      # the last block's weight gradients (not joined into main)
+                            self._ar_stream.wait_stream(model._side_stream)      # this part's weight gradients (not joined into main)
                         with torch.cuda.stream(self._ar_stream):
+                            if first:                            # the loss value is off the critical path
+                                self.total = backend.loss_from_stats(stats_all, T, Tb)
+                                first = False
                             region.barrier(1)
-                            region.allreduce("flat", split, n_flat - split, ar_blocks)                   # C2a under the rest of the backward
+                            region.allreduce("flat", cut, hi - cut, ar_blocks)                            # C2a under the rest of the backward
+                        hi = cut
                     for _ in gen:
                         pass
-                    if split < n_flat:
+                    if first:
+                        self.total = backend.loss_from_stats(stats_all, T, Tb)
+                    else:
                         main.wait_stream(self._ar_stream)
-                    region.barrier(0)                            # every rank: backward finished, its share of the tail reduced and stored
-                    if split > 0:
-                        region.allreduce("flat", 0, split, ar_blocks)                                     # C2b
+                    region.barrier(0)                            # every rank: backward finished, its shares of the earlier parts reduced and stored
+                    if hi > 0:
+                        region.allreduce("flat", 0, hi, ar_blocks)                                        # C2b: the remainder
                         region.barrier(0)
                     opt.step(max_grad_norm=clip, flat_grad=self.flat)
                 self._saved = (saved, F, y, emb, dF, stats)

@@ -20,7 +20,7 @@ def _regions(R, fields, timeout_ms=5000):
 def test_peer_exchanges_single_device(R):
     n, D, P = 24, 128, 4 * 12345
     N = n * R
-    regs = _regions(R, [("packed", (N, D + 2), torch.float32), ("stats", (N, 4), torch.float32), ("flat", (P,), torch.float32)])
+    regs = _regions(R, [("F", (N, D), torch.float32), ("y", (N,), torch.int64), ("stats", (N, 4), torch.float32), ("flat", (P,), torch.float32)])
     rs = np.random.RandomState(R)
     emb = [torch.from_numpy(rs.standard_normal((n, D)).astype(np.float32)).cuda() for _ in range(R)]
     lab = [torch.from_numpy(rs.randint(-2 ** 40, 2 ** 40, n)).cuda() for _ in range(R)]
@@ -34,7 +34,7 @@ def test_peer_exchanges_single_device(R):
     solo = _regions(1, [("x", (4,), torch.float32)])[0]
     solo.barrier(0)
     solo.barrier(1)
-    regs[0].pack_rows(emb[0], lab[0], "packed", 0)
+    regs[0].gather_rows(emb[0], lab[0], "F", "y", 0)
     regs[0].bcast(st[0], "stats", 0)
     regs[0].allreduce("flat", split, P - split)
     torch.cuda.synchronize()
@@ -44,7 +44,7 @@ def test_peer_exchanges_single_device(R):
         torch.cuda.synchronize()
         for r in range(R):
             with torch.cuda.stream(streams[r]):
-                regs[r].pack_rows(emb[r], lab[r], "packed", r * n)
+                regs[r].gather_rows(emb[r], lab[r], "F", "y", r * n)
                 regs[r].bcast(st[r], "stats", r * n * 16)
                 regs[r].barrier(0)
                 regs[r].barrier(1)
@@ -53,12 +53,10 @@ def test_peer_exchanges_single_device(R):
                 regs[r].allreduce("flat", 0, split, blocks=3)
                 regs[r].barrier(0)
         torch.cuda.synchronize()
-        from phoneme_contrast_b200 import ops
         want = torch.stack(g).double().sum(0) * (rep + 1)
         for r in range(R):
             assert regs[r].error() == 0
-            F, y = ops.dp_unpack(regs[r].local("packed"), D)
-            assert torch.equal(F, torch.cat(emb)) and torch.equal(y, torch.cat(lab))
+            assert torch.equal(regs[r].local("F"), torch.cat(emb)) and torch.equal(regs[r].local("y"), torch.cat(lab))
             assert torch.equal(regs[r].local("stats"), torch.cat(st))
             got = regs[r].local("flat")
             assert torch.equal(got, regs[0].local("flat"))                # bit-identical on every rank
