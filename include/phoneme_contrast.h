@@ -396,6 +396,17 @@ int pc_clip_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, co
 /* counter[0] += inc on the stream (device-side step counters for captured steps). */
 int pc_counter_add(int64_t* counter, int64_t inc, pc_stream_t stream);
 
+/* Two-phase forms of pc_head_fwd / pc_head_bwd for BatchNorm1d statistics synchronised across data-parallel ranks (train mode): the caller
+ * exchanges bn_sums [2][N] fp64 between the phases. forward phase 1: Linear + (sum z, sum z^2) -> bn_sums; phase 2: mean / invstd /
+ * running statistics from bn_sums over `count` rows (the GLOBAL batch) + normalise. backward phase 1: dL/d(bn output) + (sum d, sum d xhat)
+ * -> bn_sums; phase 2: BatchNorm backward with bn_sums taken as the per-rank AVERAGE of the global sums (so that B stays the local row
+ * count and dgamma / dbeta / dbias come out as this rank's share of the all-reduced gradient) + dW + dx. */
+int pc_head_fwd_sync(const float* x, int B, int K, int N, const float* W, const float* bias, const float* gamma, const float* beta,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* emb, void* ws,
+                     double* bn_sums, double count, int phase, pc_stream_t stream);
+int pc_head_bwd_sync(const float* demb, const float* x, int B, int K, int N, const float* W, const float* gamma, const float* beta, void* ws,
+                     float* dx, float* dW, float* dbias, float* dgamma, float* dbeta, double* bn_sums, int phase, pc_stream_t stream);
+
 /* ----------------------------------------------------------------------------------------------
  * 8. Data-parallel exchanges over NVLink peer memory (csrc/peer.cu; SURVEY.md 8e C1 / C1' / C2 -- absent in the
  *    single-process reference: the hot loop they serve is src/training/trainer.py:126-164)
@@ -427,6 +438,9 @@ int pc_peer_bcast(const void* src, size_t bytes, const unsigned long long* bases
 /* In-place sum over the ranks of `count` floats (multiple of 4) at byte offset off of every region: rank r reduces slice r in
  * rank order and stores it to all regions (results bit-identical on every rank). The caller brackets it with barriers. */
 int pc_peer_allreduce(const unsigned long long* bases, int R, int rank, size_t off, long long count, int blocks, pc_stream_t stream);
+/* One-shot all-reduce of a small fp64 block (synchronised BatchNorm statistics): after every rank has stored its [n]
+ * block into slot `rank` of the [R][n] LOCAL slot array of every region (pc_peer_bcast) and a barrier, dst[i] = scale * sum_r slots[r][i]. */
+int pc_peer_sum_slots(const double* slots, int R, int n, double scale, double* dst, pc_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -128,6 +128,9 @@ SIGNATURES = {
     "pc_dp_gather_peer": (i32, [vp, vp, i32, i32, vp, i32, sz, sz, i32, vp]),
     "pc_peer_bcast": (i32, [vp, sz, vp, i32, sz, vp]),
     "pc_peer_allreduce": (i32, [vp, i32, i32, sz, C.c_longlong, i32, vp]),
+    "pc_peer_sum_slots": (i32, [vp, i32, i32, f64, vp, vp]),
+    "pc_head_fwd_sync": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, vp, vp, vp, f64, i32, vp]),
+    "pc_head_bwd_sync": (i32, [vp, vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, vp]),
 }
 
 _lib = None

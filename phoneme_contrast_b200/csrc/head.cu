@@ -249,6 +249,80 @@ head_bn_bwd_kernel(float* __restrict__ dzn, const float* __restrict__ z, int B, 
   if (tid == 0 && dbias != nullptr) dbias[n] = (float)(sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]);
 }
 
+// ---- BatchNorm1d with statistics synchronised across data-parallel ranks: reduce and apply as separate kernels, the caller exchanges
+// the fp64 sums in between (pc_head_fwd_sync / pc_head_bwd_sync)
+__global__ void __launch_bounds__(128) head_bn_sums_kernel(const float* __restrict__ z, int B, int N, double* __restrict__ sums) {
+  __shared__ double sh[2][4];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int b = tid; b < B; b += 128) { const double v = (double)z[(size_t)b * N + n]; s += v; q += v * v; }
+  s = warp_sum(s); q = warp_sum(q);
+  if ((tid & 31) == 0) { sh[0][tid >> 5] = s; sh[1][tid >> 5] = q; }
+  __syncthreads();
+  if (tid == 0) { sums[n] = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]; sums[N + n] = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3]; }
+}
+
+__global__ void __launch_bounds__(128) head_bn_from_sums_kernel(const double* __restrict__ sums, double count, int N, float* __restrict__ rmean,
+                                                                float* __restrict__ rvar, int64_t* __restrict__ nbt, float momentum, float eps,
+                                                                float* __restrict__ mean_o, float* __restrict__ invstd_o) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float mean, invstd;
+  double unbiased;
+  bn_train_coeffs_v(sums[n], sums[N + n], count, eps, mean, invstd, unbiased);
+  mean_o[n] = mean;
+  invstd_o[n] = invstd;
+  if (rmean != nullptr) {
+    rmean[n] = (1.f - momentum) * rmean[n] + momentum * mean;
+    rvar[n] = (1.f - momentum) * rvar[n] + momentum * (float)unbiased;
+  }
+  if (n == 0 && nbt != nullptr) nbt[0] += 1;
+}
+
+__global__ void __launch_bounds__(128) head_bn_bwd_sums_kernel(const float* __restrict__ dzn, const float* __restrict__ z, int B, int N,
+                                                               const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ sums) {
+  __shared__ double sh[2][4];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const float mu = mean[n], is = invstd[n];
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = tid; b < B; b += 128) {
+    const float d = dzn[(size_t)b * N + n];
+    s1 += (double)d;
+    s2 += (double)d * (double)((z[(size_t)b * N + n] - mu) * is);
+  }
+  s1 = warp_sum(s1); s2 = warp_sum(s2);
+  if ((tid & 31) == 0) { sh[0][tid >> 5] = s1; sh[1][tid >> 5] = s2; }
+  __syncthreads();
+  if (tid == 0) { sums[n] = sh[0][0] + sh[0][1] + sh[0][2] + sh[0][3]; sums[N + n] = sh[1][0] + sh[1][1] + sh[1][2] + sh[1][3]; }
+}
+
+// sums = the per-rank average of the global (sum d, sum d xhat): with the LOCAL row count B the projection terms are those of the global batch
+__global__ void __launch_bounds__(128) head_bn_bwd_apply_kernel(float* __restrict__ dzn, const float* __restrict__ z, int B, int N,
+                                                                const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                                const float* __restrict__ gamma, const double* __restrict__ sums,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dbias) {
+  __shared__ double sh[4];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  const float mu = mean[n], is = invstd[n], g = gamma[n];
+  const float sdz = (float)sums[n], sdzx = (float)sums[N + n], invB = 1.0f / (float)B;
+  if (tid == 0) {
+    if (dbeta != nullptr) dbeta[n] = sdz;
+    if (dgamma != nullptr) dgamma[n] = sdzx;
+  }
+  double sb = 0.0;
+  for (int b = tid; b < B; b += 128) {
+    const float d = dzn[(size_t)b * N + n];
+    const float xhat = (z[(size_t)b * N + n] - mu) * is;
+    const float r = g * is * (d - sdz * invB - xhat * sdzx * invB);
+    dzn[(size_t)b * N + n] = r;
+    sb += (double)r;
+  }
+  sb = warp_sum(sb);
+  if ((tid & 31) == 0) sh[tid >> 5] = sb;
+  __syncthreads();
+  if (tid == 0 && dbias != nullptr) dbias[n] = (float)(sh[0] + sh[1] + sh[2] + sh[3]);
+}
+
 // dW[n,k] = sum_b dz[b,n] x[b,k]
 // dW[n][k] = sum_b dz[b][n] x[b][k]: block = 128 consecutive k of one n x 4 batch quarters (fixed-order smem reduce: deterministic)
 __global__ void __launch_bounds__(512)
@@ -343,6 +417,53 @@ extern "C" int pc_head_bwd(const float* demb, const float* x, int B, int K, int 
   PC_LAUNCH_CHECK("head_normalize_bwd_kernel");
   head_bn_bwd_kernel<<<N, 128, 0, stream>>>(dz, z, B, N, mean, invstd, gamma, training, dgamma, dbeta, dbias);
   PC_LAUNCH_CHECK("head_bn_bwd_kernel");
+  head_dw_kernel<<<N * ceil_div(K, 128), 512, 0, stream>>>(dz, x, B, K, N, dW);
+  PC_LAUNCH_CHECK("head_dw_kernel");
+  head_dx_kernel<<<ceil_div((long long)B * K, 128), 128, 0, stream>>>(dz, W, B, K, N, dx);
+  PC_LAUNCH_CHECK("head_dx_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_head_fwd_sync(const float* x, int B, int K, int N, const float* W, const float* bias, const float* gamma, const float* beta,
+                                float* running_mean, float* running_var, int64_t* num_batches_tracked, float momentum, float eps, float* emb, void* ws,
+                                double* bn_sums, double count, int phase, pc_stream_t stream) {
+  PC_REQUIRE(x && W && gamma && beta && emb && ws && bn_sums && B > 0 && K > 0 && N > 0 && (phase == 1 || phase == 2), PC_EINVAL, "pc_head_fwd_sync: bad arguments");
+  float* z = static_cast<float*>(ws);
+  float* mean = z + (size_t)B * N;
+  float* invstd = mean + N;
+  if (phase == 1) {
+    const int vec4 = ((K & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W)) & 15) == 0) ? 1 : 0;
+    head_linear_kernel<<<ceil_div((long long)B * ((N + 3) / 4), 8), 256, 0, stream>>>(x, B, K, N, W, bias, z, vec4);
+    PC_LAUNCH_CHECK("head_linear_kernel");
+    head_bn_sums_kernel<<<N, 128, 0, stream>>>(z, B, N, bn_sums);
+    PC_LAUNCH_CHECK("head_bn_sums_kernel");
+    return PC_OK;
+  }
+  PC_REQUIRE(count > 1.0, PC_EINVAL, "Expected more than 1 value per channel when training");
+  head_bn_from_sums_kernel<<<ceil_div(N, 128), 128, 0, stream>>>(bn_sums, count, N, running_mean, running_var, num_batches_tracked, momentum, eps, mean, invstd);
+  PC_LAUNCH_CHECK("head_bn_from_sums_kernel");
+  head_normalize_kernel<<<ceil_div(B, 8), 256, 0, stream>>>(z, B, N, mean, invstd, gamma, beta, emb);
+  PC_LAUNCH_CHECK("head_normalize_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_head_bwd_sync(const float* demb, const float* x, int B, int K, int N, const float* W, const float* gamma, const float* beta, void* ws,
+                                float* dx, float* dW, float* dbias, float* dgamma, float* dbeta, double* bn_sums, int phase, pc_stream_t stream) {
+  PC_REQUIRE(demb && x && W && gamma && beta && ws && dx && dW && bn_sums && B > 0 && K > 0 && N > 0 && (phase == 1 || phase == 2), PC_EINVAL,
+             "pc_head_bwd_sync: bad arguments");
+  float* z = static_cast<float*>(ws);
+  float* mean = z + (size_t)B * N;
+  float* invstd = mean + N;
+  float* dz = invstd + N;
+  if (phase == 1) {
+    head_normalize_bwd_kernel<<<ceil_div(B, 8), 256, 0, stream>>>(demb, z, B, N, mean, invstd, gamma, beta, dz);
+    PC_LAUNCH_CHECK("head_normalize_bwd_kernel");
+    head_bn_bwd_sums_kernel<<<N, 128, 0, stream>>>(dz, z, B, N, mean, invstd, bn_sums);
+    PC_LAUNCH_CHECK("head_bn_bwd_sums_kernel");
+    return PC_OK;
+  }
+  head_bn_bwd_apply_kernel<<<N, 128, 0, stream>>>(dz, z, B, N, mean, invstd, gamma, bn_sums, dgamma, dbeta, dbias);
+  PC_LAUNCH_CHECK("head_bn_bwd_apply_kernel");
   head_dw_kernel<<<N * ceil_div(K, 128), 512, 0, stream>>>(dz, x, B, K, N, dW);
   PC_LAUNCH_CHECK("head_dw_kernel");
   head_dx_kernel<<<ceil_div((long long)B * K, 128), 128, 0, stream>>>(dz, W, B, K, N, dx);

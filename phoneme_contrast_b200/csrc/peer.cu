@@ -122,6 +122,16 @@ __global__ void __launch_bounds__(512) allreduce_kernel(const Bases b, size_t of
   }
 }
 
+// dst[i] = scale * sum over r (rank order) of slots[r][i]: the local half of a one-shot all-reduce of a few hundred fp64 values (every
+// rank stored its [n] block into slot `rank` of every region before the barrier). Same order everywhere -> bit-identical results.
+__global__ void __launch_bounds__(256) sum_slots_kernel(const double* __restrict__ slots, int R, int n, double scale, double* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 0.0;
+  for (int r = 0; r < R; ++r) s += __ldcg(slots + (size_t)r * n + i);
+  dst[i] = s * scale;
+}
+
 static int load_bases(const unsigned long long* bases, int R, Bases& b) {
   PC_REQUIRE(bases != nullptr && R >= 1 && R <= MAX_RANKS, PC_EINVAL, "peer: need 1..%d region base addresses", MAX_RANKS);
   for (int k = 0; k < MAX_RANKS; ++k) b.p[k] = k < R ? bases[k] : 0ull;
@@ -246,5 +256,12 @@ extern "C" int pc_peer_allreduce(const unsigned long long* bases, int R, int ran
     default: pc::peer::allreduce_kernel<0><<<blocks, 512, 0, stream>>>(b, off, n4, per, rank, R); break;
   }
   PC_LAUNCH_CHECK("peer::allreduce_kernel");
+  return PC_OK;
+}
+
+extern "C" int pc_peer_sum_slots(const double* slots, int R, int n, double scale, double* dst, pc_stream_t stream) {
+  PC_REQUIRE(slots && dst && R >= 1 && n > 0, PC_EINVAL, "pc_peer_sum_slots: bad arguments");
+  pc::peer::sum_slots_kernel<<<ceil_div(n, 256), 256, 0, stream>>>(slots, R, n, scale, dst);
+  PC_LAUNCH_CHECK("peer::sum_slots_kernel");
   return PC_OK;
 }

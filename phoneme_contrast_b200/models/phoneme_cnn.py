@@ -190,18 +190,39 @@ def _bias_from_bn(co, grads, bias):
     return None, grads[bias]
 
 
+def _sync_of(net, training):
+    """The SyncStats exchange of a net whose BatchNorm statistics span all data-parallel ranks (enable_sync_batchnorm), else None."""
+    return net._sync_bn if (training and net._sync_bn is not None) else None
+
+
+def _sync_stats(sb, *stats):
+    """Synchronised BatchNorm, forward: the fp64 (sum y, sum y^2) blocks the convolution epilogues filled become the sums over ALL
+    ranks (finalised with the global count by the caller)."""
+    if sb is not None:
+        sb.sync([t for t in stats if t is not None], 1.0)
+
+
+def _local_only(sb, *coeffs):
+    """Under synchronised statistics the closed-form conv-bias gradient (which pairs the forward sums with the LOCAL pixel count) does
+    not apply: drop the sums from the coefficient records, the weight-gradient calls then produce the bias gradients (column sums)."""
+    if sb is not None:
+        for co in coeffs:
+            if co is not None:
+                co.stats = None
+
+
 def _head(net, s, a, training):
     att = net.attention.conv if net.use_attention else None
     w_att = att.weight.view(-1) if att is not None else None
     s.pooled, s.gate = ops.attn_pool_fwd(a, w_att, att.bias if att is not None else None)
-    emb, s.head_ws = ops.head_fwd(s.pooled, net.projection[0], net.projection[1], training)
+    emb, s.head_ws = ops.head_fwd(s.pooled, net.projection[0], net.projection[1], training, sync=_sync_of(net, training))
     return emb
 
 
 def _head_bwd(net, s, demb, grads, training):
     lin, bn = net.projection[0], net.projection[1]
     dpooled, *_ = ops.head_bwd(demb, s.pooled, lin.weight, bn.weight, bn.bias, training, s.head_ws, dW=grads[lin.weight],
-                               dbias=grads[lin.bias], dgamma=grads[bn.weight], dbeta=grads[bn.bias])
+                               dbias=grads[lin.bias], dgamma=grads[bn.weight], dbeta=grads[bn.bias], sync=_sync_of(net, training))
     if net.use_attention:
         att = net.attention.conv
         da, _, _ = ops.attn_pool_bwd(s.a_last, s.gate, dpooled, att.weight.view(-1), dw=grads[att.weight].view(-1),
@@ -217,6 +238,10 @@ def _small_forward(net, x, training):
     prec = net._prec
     B, _, H, W = x.shape
     s.x = x
+    sb = _sync_of(net, training)
+    cm = sb.R if sb is not None else 1          # BatchNorm counts span all ranks under synchronised statistics
+    if sb is not None:
+        sb.begin_step()
     blocks = net.conv_blocks
     chans = [blocks[b][0].out_channels for b in range(3)]
     s.drop = _drop_masks(net, B, chans, training)
@@ -245,17 +270,20 @@ def _small_forward(net, x, training):
         stB = slots.take(co)
         psB = use_planes and co % 64 == 0 and cwB.prec_f == L.PREC_FP16X2 and cwB.prec_d == L.PREC_FP16X2
         fuse_fin = psB and training and os.environ.get("PC_BN_FIN_FUSE", "1") == "1"      # finalise bnA inside the split kernel
-        coA = None if fuse_fin else ops.bn_finalize(stA, B * gA.Ho * gA.Wo, bnA, training)
+        _sync_stats(sb, stA)
+        coA = None if fuse_fin else ops.bn_finalize(stA, cm * B * gA.Ho * gA.Wo, bnA, training)
         aA = None
         if psB:
             if fuse_fin:
-                aA, coA = ops.bn_act_split_fin(yA, stA, B * gA.Ho * gA.Wo, bnA, None, relu=True)
+                aA, coA = ops.bn_act_split_fin(yA, stA, cm * B * gA.Ho * gA.Wo, bnA, None, relu=True)
             else:
                 aA = ops.bn_act_split(yA, coA.scale, coA.shift, None, relu=True)
             yB = ops.conv_fwd(aA, cwB.wf, convB.bias, gB, dict(presplit=True), stB, cwB.prec_f)
         else:
             yB = ops.conv_fwd(yA, cwB.wf, convB.bias, gB, dict(scale=coA.scale, shift=coA.shift, relu=True), stB, cwB.prec_f)
-        coB = ops.bn_finalize(stB, B * h * w, bnB, training)
+        _sync_stats(sb, stB)
+        coB = ops.bn_finalize(stB, cm * B * h * w, bnB, training)
+        _local_only(sb, coA, coB)
         pool = 2 if b < 2 else 0
         next_ps = use_planes and b < 2 and co % 64 == 0      # the next block's first convolution gathers co channels
         if next_ps:
@@ -279,6 +307,7 @@ def _small_backward(net, s, demb, grads, training=True):
     blocks = net.conv_blocks
     keep = []
     wgrad = _WgradLane(net, keep)
+    sb = _sync_of(net, training)
     dout = _head_bwd(net, s, demb, grads, training)
     amax = _AmaxSlots(demb.device, 6)   # max|dy| of every gradient tensor a convolution consumes (FP16X2 operand scale)
     for b in (2, 1, 0):
@@ -289,7 +318,7 @@ def _small_backward(net, s, demb, grads, training=True):
         dbA_bn, dbA_w = _bias_from_bn(ly["coA"], grads, convA.bias)
         psB, psA = ly["aA"] is not None, ly["xin_ps"] is not None       # gradient tensors in plane form wherever the consumers gather planes
         dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias], mB, db_conv=dbB_bn,
-                                   planes=psB)
+                                   planes=psB, sync=sb)
         # data gradient (critical path) first, then the weight gradient of the same dy on the side stream (see _deep_backward)
         dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d, dy_amax=mB, dy_presplit=psB)
         if psB:
@@ -297,7 +326,7 @@ def _small_backward(net, s, demb, grads, training=True):
         else:
             xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
             wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], dbB_w, prec, mB)
-        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA, db_conv=dbA_bn, planes=psA)
+        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA, db_conv=dbA_bn, planes=psA, sync=sb)
         if b > 0:
             dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d, dy_amax=mA, dy_presplit=psA)
         if psA:
@@ -330,6 +359,10 @@ def _deep_forward(net, x, training, for_backward=True):
     prec = net._prec
     B, _, H, W = x.shape
     s.x = x
+    sb = _sync_of(net, training)
+    cm = sb.R if sb is not None else 1          # BatchNorm counts span all ranks under synchronised statistics
+    if sb is not None:
+        sb.begin_step()
     hd = net.hidden_dims
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
     s.drop = _drop_masks(net, B, list(hd), training)
@@ -342,8 +375,9 @@ def _deep_forward(net, x, training, for_backward=True):
     # that conv1 / the shortcut conv and their weight gradients gather bytes instead of splitting fp32 per tap
     ps = prec == L.PREC_FP16X2 and all(c % 64 == 0 for c in hd) and net.use_residual
     lib = L.lib()
-    pooled_bwd = os.environ.get("PC_STEM_BWD", "1") == "1" and bool(lib.pc_stem_bwd_supported(7, hd[0], H, W))
-    fused_fwd = (prec != L.PREC_FP32 and os.environ.get("PC_STEM_FWD", "1") == "1" and lib.pc_stem_fwd_supported(7, hd[0], H, W)
+    # (synchronised statistics take the unfused stem: conv -> exchange of the sums -> BatchNorm + ReLU + pool, three-pass backward)
+    pooled_bwd = sb is None and os.environ.get("PC_STEM_BWD", "1") == "1" and bool(lib.pc_stem_bwd_supported(7, hd[0], H, W))
+    fused_fwd = (sb is None and prec != L.PREC_FP32 and os.environ.get("PC_STEM_FWD", "1") == "1" and lib.pc_stem_fwd_supported(7, hd[0], H, W)
                  and (not training or pooled_bwd))          # without y0 the backward must be the pooled-resolution one
     want_gram = training and (fused_fwd or (for_backward and pooled_bwd))
     gram = None
@@ -369,7 +403,9 @@ def _deep_forward(net, x, training, for_backward=True):
             with torch.cuda.stream(net._side_stream):
                 gram = ops.stem_gram(x)
         y0 = ops.conv_fwd(x, conv0.weight, conv0.bias, g0, None, st0, prec)
-        co0 = ops.bn_finalize(st0, B * H * W, bn0, training)
+        _sync_stats(sb, st0)
+        co0 = ops.bn_finalize(st0, cm * B * H * W, bn0, training)
+        _local_only(sb, co0)
         if ps:
             p0, argmax0, cur_ps = ops.bn_act_fwd(y0, co0, 3, None, want_planes=True)
         else:
@@ -392,12 +428,15 @@ def _deep_forward(net, x, training, for_backward=True):
             cw1 = ops.ConvWeights(blk[0].weight, g1, prec, packer=packer)
             st1 = st(co)
             y1 = ops.conv_fwd(cur, cw1.wf, blk[0].bias, g1, None, st1, cw1.prec_f)
-            c1 = ops.bn_finalize(st1, B * g1.Ho * g1.Wo, blk[1], training)
+            _sync_stats(sb, st1)
+            c1 = ops.bn_finalize(st1, cm * B * g1.Ho * g1.Wo, blk[1], training)
             g2 = ops.conv_geom(B, g1.Ho, g1.Wo, co, co, 3, 1, 1)
             cw2 = ops.ConvWeights(blk[3].weight, g2, prec, packer=packer)
             st2 = st(co)
             y2 = ops.conv_fwd(y1, cw2.wf, blk[3].bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True), st2, cw2.prec_f)
-            c2 = ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk[4], training)
+            _sync_stats(sb, st2)
+            c2 = ops.bn_finalize(st2, cm * B * g2.Ho * g2.Wo, blk[4], training)
+            _local_only(sb, c1, c2)
             out, _ = ops.bn_act_fwd(y2, c2, 0, s.drop[i])
             s.blocks.append(dict(plain=True, xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, cw1=cw1, cw2=cw2, out=out))
             cur, cin, h, w = out, co, g1.Ho, g1.Wo
@@ -413,7 +452,8 @@ def _deep_forward(net, x, training, for_backward=True):
         # train mode on the plane engine: the BatchNorm coefficients are finalised INSIDE the kernel that first applies them
         # (pc_bn_act_split_fin / pc_bn_add_relu_fwd_fin): one dependent launch less per BatchNorm layer
         fuse_fin = training and cw2.prec_f == L.PREC_FP16X2 and os.environ.get("PC_BN_FIN_FUSE", "1") == "1"
-        c1 = None if fuse_fin else ops.bn_finalize(st1, B * g1.Ho * g1.Wo, blk.bn1, training)
+        _sync_stats(sb, st1)
+        c1 = None if fuse_fin else ops.bn_finalize(st1, cm * B * g1.Ho * g1.Wo, blk.bn1, training)
         st2 = st(co)
         # conv2 reads a1 = drop * relu(bn1(y1)). On the FP16X2 engine a1 is written once as fp16 hi | lo planes (one elementwise
         # pass) and conv2's gather -- and later its weight gradient's -- only copies bytes, instead of redoing BatchNorm + ReLU +
@@ -421,14 +461,14 @@ def _deep_forward(net, x, training, for_backward=True):
         a1 = None
         if cw2.prec_f == L.PREC_FP16X2:
             if fuse_fin:
-                a1, c1 = ops.bn_act_split_fin(y1, st1, B * g1.Ho * g1.Wo, blk.bn1, s.drop[i], relu=True)
+                a1, c1 = ops.bn_act_split_fin(y1, st1, cm * B * g1.Ho * g1.Wo, blk.bn1, s.drop[i], relu=True)
             else:
                 a1 = ops.bn_act_split(y1, c1.scale, c1.shift, s.drop[i], relu=True)
             y2 = ops.conv_fwd(a1, cw2.wf, blk.conv2.bias, g2, dict(presplit=True), st2, cw2.prec_f)
         else:
             y2 = ops.conv_fwd(y1, cw2.wf, blk.conv2.bias, g2, dict(scale=c1.scale, shift=c1.shift, relu=True, drop=s.drop[i]), st2, cw2.prec_f)
         fuse_tail = training and os.environ.get("PC_BN_FIN_FUSE", "1") == "1"
-        c2 = None if fuse_tail else ops.bn_finalize(st2, B * g2.Ho * g2.Wo, blk.bn2, training)
+        c2 = None        # (finalised below, after the shortcut's statistics exist: one exchange for both under synchronised statistics)
         rec = dict(xin=cur, g1=g1, g2=g2, y1=y1, y2=y2, c1=c1, c2=c2, cw1=cw1, cw2=cw2, proj=len(blk.shortcut) > 0, a1=a1, xin_ps=in_ps)
         sts = bns = None
         if rec["proj"]:
@@ -438,18 +478,23 @@ def _deep_forward(net, x, training, for_backward=True):
             sts = st(co)
             sc_ps = in_ps if cws.prec_f == L.PREC_FP16X2 else None
             ys = ops.conv_fwd(sc_ps if sc_ps is not None else cur, cws.wf, convs.bias, gs, xps if sc_ps is not None else None, sts, cws.prec_f)
-            cs = None if fuse_tail else ops.bn_finalize(sts, B * gs.Ho * gs.Wo, bns, training)
-            rec.update(gs=gs, ys=ys, cs=cs, cws=cws)
+            rec.update(gs=gs, ys=ys, cs=None, cws=cws)
         last = i == len(net.conv_blocks) - 1          # the last block's output feeds the attention pool, not a convolution
+        _sync_stats(sb, st2, sts)
         if fuse_tail:
-            res, c2, cs = ops.bn_add_relu_fwd_fin(y2, st2, B * g2.Ho * g2.Wo, blk.bn2, rec["ys"] if rec["proj"] else cur, sts, bns,
+            res, c2, cs = ops.bn_add_relu_fwd_fin(y2, st2, cm * B * g2.Ho * g2.Wo, blk.bn2, rec["ys"] if rec["proj"] else cur, sts, bns,
                                                   want_planes=ps and not last)
             rec["c2"] = c2
             if rec["proj"]:
                 rec["cs"] = cs
         else:
+            rec["c2"] = c2 = ops.bn_finalize(st2, cm * B * g2.Ho * g2.Wo, blk.bn2, training)
+            if rec["proj"]:
+                rec["cs"] = ops.bn_finalize(sts, cm * B * rec["gs"].Ho * rec["gs"].Wo, bns, training)
             res = ops.bn_add_relu_fwd(y2, c2, rec["ys"] if rec["proj"] else cur, rec["cs"] if rec["proj"] else None, want_planes=ps and not last)
         out, cur_ps = res if (ps and not last) else (res, None)
+        rec["c1"] = c1
+        _local_only(sb, rec["c1"], rec["c2"], rec.get("cs"))
         rec["out"] = out
         s.blocks.append(rec)
         cur, cin, h, w = out, co, g1.Ho, g1.Wo
@@ -466,6 +511,7 @@ def _deep_backward(net, s, demb, grads, training=True):
     prec = net._prec
     keep = []
     wgrad = _WgradLane(net, keep)
+    sb = _sync_of(net, training)
     dout = _head_bwd(net, s, demb, grads, training)
     zp = ops.ZeroPool(demb.device)                      # zeroed reduction targets of all BatchNorm backward passes
     amax = _AmaxSlots(demb.device, 3 * len(s.blocks) + 1, zp)   # max|dy| per gradient tensor a convolution consumes (FP16X2 scale)
@@ -476,11 +522,11 @@ def _deep_backward(net, s, demb, grads, training=True):
         if r.get("plain"):
             db2_bn, db2_w = _bias_from_bn(r["c2"], grads, blk[3].bias)
             db1_bn, db1_w = _bias_from_bn(r["c1"], grads, blk[0].bias)
-            dy2, _, _ = ops.bn_act_bwd(dout, r["y2"], r["c2"], 0, s.drop[i], None, grads[blk[4].weight], grads[blk[4].bias], m2, zp=zp, db_conv=db2_bn)
+            dy2, _, _ = ops.bn_act_bwd(dout, r["y2"], r["c2"], 0, s.drop[i], None, grads[blk[4].weight], grads[blk[4].bias], m2, zp=zp, db_conv=db2_bn, sync=sb)
             xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True)
             wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk[3].weight], db2_w, prec, m2)
             dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2)
-            dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, None, None, grads[blk[1].weight], grads[blk[1].bias], m1, zp=zp, db_conv=db1_bn)
+            dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, None, None, grads[blk[1].weight], grads[blk[1].bias], m1, zp=zp, db_conv=db1_bn, sync=sb)
             wgrad(r["xin"], dy1, r["g1"], None, grads[blk[0].weight], db1_w, prec, m1)
             dout = ops.conv_dgrad(dy1, r["cw1"].wd, r["g1"], prec=r["cw1"].prec_d, dy_amax=m1)
             if i == len(s.blocks) - 1 or (i == len(s.blocks) - 2 and i >= 1 and net._split_backward == "fork"):
@@ -499,9 +545,9 @@ def _deep_backward(net, s, demb, grads, training=True):
             convs, bns = blk.shortcut[0], blk.shortcut[1]
             dbs_bn, dbs_w = _bias_from_bn(r["cs"], grads, convs.bias)
             dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], r["ys"], r["cs"], g2,
-                                                  (grads[bns.weight], grads[bns.bias]), m2, ms, planes=gps, zp=zp, db2=db2_bn, db_s=dbs_bn)
+                                                  (grads[bns.weight], grads[bns.bias]), m2, ms, planes=gps, zp=zp, db2=db2_bn, db_s=dbs_bn, sync=sb)
         else:
-            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None, planes=gps, zp=zp, db2=db2_bn)
+            dy2, dysc, _, _ = ops.bn_add_relu_bwd(dout, r["out"], r["y2"], r["c2"], None, None, g2, None, m2, None, planes=gps, zp=zp, db2=db2_bn, sync=sb)
         # Order: the data gradient (main stream, critical path) is issued BEFORE the weight gradient of the same dy (side stream). Both
         # are persistent one-CTA-per-SM tensor kernels that cannot share an SM; issued the other way round the weight gradient took
         # the SMs first and the critical path waited (measured: only 0.18 of its 0.76 ms was hidden). Behind the data gradient it
@@ -513,7 +559,7 @@ def _deep_backward(net, s, demb, grads, training=True):
             xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
             wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], db2_w, prec, m2)
         dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1, planes=gps, zp=zp,
-                                   db_conv=db1_bn)
+                                   db_conv=db1_bn, sync=sb)
         xin_w, xf_w = (r["xin_ps"], dict(presplit=True)) if r["xin_ps"] is not None else (r["xin"], None)
         if r["proj"]:
             # conv1's data gradient writes every pixel of dxin; the strided 1x1 shortcut then adds into the pixels it reads
@@ -542,7 +588,7 @@ def _deep_backward(net, s, demb, grads, training=True):
     # the stem's dy is O(1/N) per pixel (the loss is a mean): without the max|dy| operand scale it would sit in fp16 subnormals
     m0 = amax.take()
     db0_bn, db0_w = _bias_from_bn(st["co"], grads, conv0.bias)
-    dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias], m0, zp=zp, db_conv=db0_bn)
+    dy0, _, _ = ops.bn_act_bwd(dout, st["y"], st["co"], 3, None, st["argmax"], grads[bn0.weight], grads[bn0.bias], m0, zp=zp, db_conv=db0_bn, sync=sb)
     wgrad(s.x, dy0, st["g"], None, grads[conv0.weight], db0_w, prec, m0)
     wgrad.join()
 
@@ -585,12 +631,25 @@ class _NetFunction(torch.autograd.Function):
 
 
 class _FusedNet(BaseModel):
+    _sync_bn = None              # peer.SyncStats when the BatchNorm statistics span all data-parallel ranks (enable_sync_batchnorm)
     _inject_drop = None
     _drop_step = None
     # set by the graphed data-parallel steps. True: join the weight-gradient lane at the backward's split point (a captured segment must
     # end joined). "fork": do not join -- the caller makes its exchange stream wait for the lane (net._side_stream) itself, so that the
     # main stream keeps running the backward while the last block's weight gradients finish
     _split_backward = False
+
+    def enable_sync_batchnorm(self, parallel=None, sync=None):
+        """Train-mode BatchNorm statistics (every BatchNorm2d and the head's BatchNorm1d) over the GLOBAL data-parallel batch, SURVEY.md 8e
+        mode (i): R ranks then compute exactly what the single-process reference computes on the concatenated batch. The sums are
+        exchanged over NVLink peer memory (peer.SyncStats: one store loop + one flag barrier per BatchNorm, forward and backward).
+        Costs 2 x (number of BatchNorm layers) small exchanges per step and takes the unfused stem; the default (per-rank statistics,
+        the torch-DDP convention) needs none."""
+        if sync is None:
+            from ..peer import SyncStats
+            sync = SyncStats(next(self.parameters()).device, group=getattr(parallel, "group", None))
+        self._sync_bn = sync
+        return self
 
     def tail_bucket_offset(self) -> int:
         """Element offset, inside the flat gradient bucket (parameter order), of the first parameter of the LAST conv block: the

@@ -356,7 +356,7 @@ def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None, want_planes=False):
 
 
 def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None, planes=False, zp=None,
-               db_conv=None):
+               db_conv=None, sync=None):
     """Gradient w.r.t. the pre-BatchNorm tensor y of out = drop * pool(relu(bn(y))) (train-mode statistics).
     amax: optional zero-initialised 1-element tensor that receives max|dy| (operand scale of the FP16X2 convolutions).
     planes=True: dy is returned ONLY as fp16 hi | lo planes (uint8 [2, numel*2]) scaled by the power of two derived from a bound
@@ -367,6 +367,10 @@ def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=Non
     args = (ptr(dout), ptr(y), B, H, W, C_, ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd), ptr(drop), pool,
             ptr(argmax, torch.uint8))
     call("pc_bn_act_bwd_reduce", *args, ptr(sums, torch.float64), ptr(maxes), stream())
+    if sync is not None:
+        # synchronised BatchNorm: the apply pass takes the per-rank AVERAGE of the global (sum dz, sum dz xhat); with its local pixel
+        # count the projection terms are then those of the global batch, and dgamma / dbeta are this rank's share of the all-reduced sum
+        sync.sync([sums], 1.0 / sync.R)
     dy = None if planes else torch.empty_like(y)
     dy_ps = torch.empty(2, y.numel() * 2, device=y.device, dtype=torch.uint8) if planes else None
     if dgamma is None:
@@ -438,7 +442,7 @@ def bn_add_relu_fwd(y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, want_planes=F
 
 
 def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, grads2=None, grads_s=None, amax2=None,
-                    amax_s=None, planes=False, zp=None, db2=None, db_s=None):
+                    amax_s=None, planes=False, zp=None, db2=None, db_s=None, sync=None):
     """Returns dy2, d(shortcut branch input: dysc for a projection shortcut, dx for identity), (dgamma2, dbeta2), (dgamma_s, dbeta_s).
     planes=True: dy2 -- and dysc of a projection shortcut -- come back ONLY as scaled fp16 hi | lo planes (see bn_act_bwd); the
     identity-shortcut dx stays fp32 (it is accumulated into, not convolved)."""
@@ -451,6 +455,8 @@ def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, gr
     call("pc_bn_add_relu_bwd_reduce", ptr(dout), ptr(out), ptr(y2), ptr(co2.mean), ptr(co2.invstd), ptr(ysc) if co_s else None,
          ptr(co_s.mean) if co_s else None, ptr(co_s.invstd) if co_s else None, n_pix, C_, ptr(sums2, torch.float64),
          ptr(sums_s, torch.float64), ptr(maxes), stream())
+    if sync is not None:      # see bn_act_bwd
+        sync.sync([sums2] + ([sums_s] if co_s else []), 1.0 / sync.R)
     ps_sc = planes and co_s is not None
     dy2 = None if planes else torch.empty_like(y2)
     dsc = None if ps_sc else torch.empty_like(y2)
@@ -486,20 +492,29 @@ def attn_pool_bwd(a, gate, dpooled, w=None, dw=None, db0=None):
     return da, dw, db0
 
 
-def head_fwd(x, lin: torch.nn.Linear, bn: torch.nn.BatchNorm1d, training: bool):
+def head_fwd(x, lin: torch.nn.Linear, bn: torch.nn.BatchNorm1d, training: bool, sync=None):
     B, K = x.shape
     N = lin.out_features
     nbytes = int(L.lib().pc_head_workspace(B, K, N))
     ws = torch.empty(nbytes // 4, device=x.device, dtype=F32)
     emb = torch.empty(B, N, device=x.device, dtype=F32)
     momentum = 0.1 if bn.momentum is None else bn.momentum
+    if sync is not None and training:
+        # BatchNorm1d statistics over the GLOBAL batch: Linear + local sums | exchange | coefficients from the global sums + normalise
+        sums = torch.empty(2, N, device=x.device, dtype=torch.float64)
+        args = (ptr(x), B, K, N, ptr(lin.weight), ptr(lin.bias), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean), ptr(bn.running_var),
+                ptr(bn.num_batches_tracked, torch.int64), momentum, bn.eps, ptr(emb), ptr(ws), ptr(sums, torch.float64), float(B * sync.R))
+        call("pc_head_fwd_sync", *args, 1, stream())
+        sync.sync([sums], 1.0)
+        call("pc_head_fwd_sync", *args, 2, stream())
+        return emb, ws
     call("pc_head_fwd", ptr(x), B, K, N, ptr(lin.weight), ptr(lin.bias), ptr(bn.weight), ptr(bn.bias), ptr(bn.running_mean),
          ptr(bn.running_var), ptr(bn.num_batches_tracked, torch.int64), momentum, bn.eps, 1 if training else 0, ptr(emb),
          ptr(ws), stream())
     return emb, ws
 
 
-def head_bwd(demb, x, lin_w, bn_w, bn_b, training, ws, dW=None, dbias=None, dgamma=None, dbeta=None):
+def head_bwd(demb, x, lin_w, bn_w, bn_b, training, ws, dW=None, dbias=None, dgamma=None, dbeta=None, sync=None):
     B, K = x.shape
     N = lin_w.shape[0]
     dev = x.device
@@ -508,6 +523,14 @@ def head_bwd(demb, x, lin_w, bn_w, bn_b, training, ws, dW=None, dbias=None, dgam
     dbias = torch.empty(N, device=dev, dtype=F32) if dbias is None else dbias
     dgamma = torch.empty(N, device=dev, dtype=F32) if dgamma is None else dgamma
     dbeta = torch.empty(N, device=dev, dtype=F32) if dbeta is None else dbeta
+    if sync is not None and training:
+        sums = torch.empty(2, N, device=dev, dtype=torch.float64)
+        args = (ptr(demb), ptr(x), B, K, N, ptr(lin_w), ptr(bn_w), ptr(bn_b), ptr(ws), ptr(dx), ptr(dW), ptr(dbias), ptr(dgamma), ptr(dbeta),
+                ptr(sums, torch.float64))
+        call("pc_head_bwd_sync", *args, 1, stream())
+        sync.sync([sums], 1.0 / sync.R)
+        call("pc_head_bwd_sync", *args, 2, stream())
+        return dx, dW, dbias, dgamma, dbeta
     call("pc_head_bwd", ptr(demb), ptr(x), B, K, N, ptr(lin_w), ptr(bn_w), ptr(bn_b), 1 if training else 0, ptr(ws), ptr(dx),
          ptr(dW), ptr(dbias), ptr(dgamma), ptr(dbeta), stream())
     return dx, dW, dbias, dgamma, dbeta

@@ -16,6 +16,11 @@ import torch
 from . import _lib as L
 
 
+# IPC handles name whole cudaMalloc blocks, and the caching allocator places several tensors in one block: two regions of a peer can
+# arrive with the SAME handle. A handle is mapped once per process and the mapping is kept until exit (torch's own IPC cache does the same).
+_MAPPED: dict = {}
+
+
 def _align(x: int, a: int = 256) -> int:
     return (x + a - 1) // a * a
 
@@ -38,7 +43,6 @@ class PeerRegion:
             off = _align(off + nbytes)
         self.nbytes = off
         self.timeout_ms = int(timeout_ms)
-        self._opened = []
         if bases is not None:
             # single-process form (tests: several "ranks" on one device): the caller supplies the regions' buffers / addresses
             self.buf, self.rank, self.world_size = buf, int(rank), len(bases)
@@ -70,14 +74,15 @@ class PeerRegion:
                 if r == self.rank:
                     self._bases_py.append(self.buf.data_ptr())
                     continue
-                base = C.c_void_p()
-                hb = (C.c_ubyte * 64).from_buffer_copy(h)
-                rc = lib.pc_peer_open(hb, C.byref(base))
-                if rc != 0:
-                    fail = f"rank {self.rank} could not map rank {r}: {L.last_error()}"
-                    break
-                self._opened.append(base.value)
-                self._bases_py.append(base.value + o)
+                if h not in _MAPPED:
+                    base = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(h)
+                    rc = lib.pc_peer_open(hb, C.byref(base))
+                    if rc != 0:
+                        fail = f"rank {self.rank} could not map rank {r}: {L.last_error()}"
+                        break
+                    _MAPPED[h] = base.value
+                self._bases_py.append(_MAPPED[h] + o)
             fails = [None] * self.world_size
             dist.all_gather_object(fails, fail, group=group)     # doubles as the barrier: everyone zeroed its flags and mapped everybody
             fails = [f for f in fails if f]
@@ -131,6 +136,42 @@ class PeerRegion:
         return int(out.value)
 
     def close(self) -> None:
-        for base in self._opened:
-            L.lib().pc_peer_close(C.c_void_p(base))
-        self._opened = []
+        """Drops this region's references; the peer mappings themselves stay cached for the life of the process (_MAPPED)."""
+        self._bases_py = []
+
+
+class SyncStats:
+    """Synchronised BatchNorm statistics (SURVEY.md 8e mode (i), C3): a one-shot all-reduce of small fp64 blocks over peer memory.
+    Every call site of a step takes the next slice of the region's slot array (same order on every rank; begin_step() rewinds), stores
+    its block into slot `rank` of EVERY region, and after ONE flag barrier each rank sums its local slots in rank order -- the results
+    are bit-identical on all ranks. Stream-ordered kernels only, so the exchanges work in eager steps and inside captured graphs."""
+
+    def __init__(self, device, group=None, capacity: int = 1 << 15, region: PeerRegion = None, world_size: int = None):
+        if region is None:
+            import torch.distributed as dist
+            world_size = dist.get_world_size(group)
+            region = PeerRegion([("bn", (world_size * capacity,), torch.float64)], device, group=group)
+        self.region = region
+        self.R, self.rank, self.cap = region.world_size, region.rank, int(capacity)
+        self.off = 0
+
+    def begin_step(self) -> None:
+        self.off = 0
+
+    def sync(self, tensors, scale: float = 1.0) -> None:
+        """In place, for each contiguous fp64 tensor t (even element count): t <- scale * sum over ranks of t. ONE barrier for the lot."""
+        R, taken = self.R, []
+        for t in tensors:
+            n = t.numel()
+            if t.dtype != torch.float64 or not t.is_contiguous() or n % 2:
+                raise ValueError("SyncStats.sync takes contiguous float64 tensors with an even element count")
+            if self.off + n > self.cap:
+                raise RuntimeError("SyncStats: slot capacity exhausted (was begin_step() called at the start of the step?)")
+            base = self.off * R
+            self.region.bcast(t, "bn", (base + self.rank * n) * 8)
+            taken.append((base, n))
+            self.off += n
+        self.region.barrier(0)
+        slots = self.region.local("bn")
+        for t, (base, n) in zip(tensors, taken):
+            L.call("pc_peer_sum_slots", L.ptr(slots[base:base + R * n], torch.float64), R, n, float(scale), L.ptr(t, torch.float64), L.stream())

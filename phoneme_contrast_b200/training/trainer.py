@@ -58,6 +58,9 @@ class ContrastiveTrainer:
         self.best_val_loss = float("inf")
         self.metrics_history = defaultdict(list)
         self._graphed = None            # GraphedTrainStep, built lazily when config["cuda_graph"] is set
+        if parallel is not None and config.get("sync_batchnorm") and hasattr(model, "enable_sync_batchnorm") and model._sync_bn is None:
+            # BatchNorm statistics over the global batch (SURVEY.md 8e mode (i)); the default is per-rank statistics (mode (ii))
+            model.enable_sync_batchnorm(parallel)
 
     # ------------------------------------------------------------------------------------------- loop
     def train(self, num_epochs: int) -> None:

@@ -125,7 +125,7 @@ def _dp_inputs(world, per_rank=16, hw=(40, 50)):
     return xs, ys
 
 
-def _replica_worker(rank, world, port, out, arch):
+def _replica_worker(rank, world, port, out, arch, syncbn=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -149,17 +149,22 @@ def _replica_worker(rank, world, port, out, arch):
             m.load_state_dict(nets_oracle.synthetic_state_dict(arch, cfg, seed=6))
             opt = FusedClipAdam(m.parameters(), lr=3e-4, weight_decay=1e-4)
             tr = ContrastiveTrainer(m, [], None, get_loss_fn("supervised_contrastive", temperature=0.15), opt, None, torch.device(dev),
-                                    {"gradient_clip_val": 1.0, "progress": False, "cuda_graph": graph, "dp_exchange": "peer" if mode == "peer" else "nccl"},
+                                    {"gradient_clip_val": 1.0, "progress": False, "cuda_graph": graph, "dp_exchange": "peer" if mode == "peer" else "nccl",
+                                     "sync_batchnorm": syncbn},
                                     tempfile.mkdtemp(), logging.getLogger("t"), parallel=ctx)
             m.train()
+            assert (m._sync_bn is not None) == bool(syncbn)
             loss = float(tr.step(x, y))
+            if syncbn:
+                assert m._sync_bn.region.error() == 0
             assert (not graph) or type(tr._graphed).__name__ == ("GraphedDPStepPeer" if mode == "peer" else "GraphedDPStep"), tr._graphed
             if mode == "peer":
                 tr._graphed.check()
             names = [n for n, _ in m.named_parameters()]
             res[mode] = dict(loss=loss, grads={n: p.grad.detach().cpu() for n, p in m.named_parameters()},
                                                       params={n: p.detach().cpu() for n, p in m.named_parameters()}, names=names,
-                                                      rm=m.state_dict()["projection.1.running_mean"].cpu())
+                                                      rm=m.state_dict()["projection.1.running_mean"].cpu(),
+                                                      buffers={k: v.detach().cpu() for k, v in m.state_dict().items() if "running" in k})
         torch.save(res, os.path.join(out, f"rep{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -213,3 +218,52 @@ def test_dp_training_step_matches_oracle_replicas(tmp_path, arch):
         for n in names:                                      # every rank holds the same parameters after the step
             assert torch.equal(outs[0][mode]["params"][n], outs[1][mode]["params"][n]), (mode, n)
         assert not torch.equal(outs[0][mode]["rm"], outs[1][mode]["rm"])     # per-rank BatchNorm statistics, as stated
+
+
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("arch", ["phoneme_cnn", "phoneme_cnn_deep"])
+def test_dp_sync_batchnorm_matches_single_process_oracle(tmp_path, arch):
+    """SURVEY.md 8e mode (i): with synchronised BatchNorm statistics (peer.SyncStats) R ranks compute what the SINGLE-PROCESS reference
+    computes on the concatenated batch -- loss, all-reduced gradients, updated parameters and BatchNorm running statistics -- through
+    the eager step, the NCCL-segment graph and the one-graph peer-memory step."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from oracle import nets_oracle, optim_oracle, supcon_oracle
+    from tests.helpers import analytically_zero_grad
+    world, port = 2, _free_port()
+    mp.spawn(_replica_worker, args=(world, port, str(tmp_path), arch, True), nprocs=world, join=True)
+    cfg = {"dropout_rate": 0.0} if arch == "phoneme_cnn" else {"dropout_rate": 0.0, "hidden_dims": [64, 64, 128, 128]}
+    sd = nets_oracle.synthetic_state_dict(arch, cfg, seed=6)
+    xs, ys = _dp_inputs(world)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point and "running" not in k}
+    live = {k: v.clone() for k, v in sd.items()}
+    live.update(params)
+    emb = nets_oracle.forward(arch, live, torch.from_numpy(np.concatenate(xs)), training=True)       # ONE process, the global batch
+    loss = supcon_oracle.loss_torch_cpu(emb, torch.from_numpy(np.concatenate(ys)), temperature=0.15)
+    loss.backward()
+    outs = [torch.load(os.path.join(tmp_path, f"rep{r}.pt")) for r in range(world)]
+    names = outs[0]["eager"]["names"]
+    gref = [params[n].grad.numpy() for n in names]
+    pn = [sd[n].numpy().copy() for n in names]
+    optim_oracle.adam_step(pn, gref, [np.zeros_like(p) for p in pn], [np.zeros_like(p) for p in pn], 1, lr=3e-4, weight_decay=1e-4, max_norm=1.0)
+    for mode in ("eager", "graph", "peer"):
+        for r in range(world):
+            o = outs[r][mode]
+            assert abs(o["loss"] - float(loss.detach())) <= 1e-4 * abs(float(loss.detach())), (mode, r, o["loss"], float(loss.detach()))
+            for n, g, pnew in zip(names, gref, pn):
+                if analytically_zero_grad(n):
+                    continue
+                got = o["grads"][n].numpy()
+                l2 = np.linalg.norm((got - g).astype(np.float64)) / max(np.linalg.norm(g.astype(np.float64)), 1e-12)
+                assert l2 <= 3e-3, (mode, r, n, l2)
+                du, dr = o["params"][n].numpy() - sd[n].numpy(), pnew - sd[n].numpy()
+                sel = np.abs(g) > 0.05 * np.sqrt(np.mean(g.astype(np.float64) ** 2))
+                assert np.linalg.norm((du - dr)[sel]) <= 0.02 * np.linalg.norm(dr[sel]) + 1e-9, (mode, r, n)
+            # running statistics are those of the GLOBAL batch (the oracle's forward updated `live` in place)
+            for k, v in o["buffers"].items():
+                want = live[k].detach().numpy()
+                assert np.abs(v.numpy() - want).max() <= 1e-4 * max(np.abs(want).max(), 1e-3), (mode, r, k)
+        for n in names:
+            assert torch.equal(outs[0][mode]["params"][n], outs[1][mode]["params"][n]), (mode, n)
+        for k in outs[0][mode]["buffers"]:                       # bit-identical on every rank: same sums, same order
+            assert torch.equal(outs[0][mode]["buffers"][k], outs[1][mode]["buffers"][k]), (mode, k)
