@@ -2,6 +2,8 @@
 // forward and backward. Reference: src/models/phoneme_cnn.py:129-143 (SpatialAttention), :117-124 / :295-302
 // (pool, projection, F.normalize). Tensors are tiny here ([B,HW,C] with HW*C <= 32 K floats per sample,
 // [B,128] embeddings); the kernels are latency-bound, so they are kept few and simple.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pc {
@@ -78,6 +80,122 @@ attn_pool_bwd_kernel(const float* __restrict__ a, const float* __restrict__ gate
     } else {
       for (int p = 0; p < HW; ++p) dab[(size_t)p * C + c] = g;
     }
+  }
+}
+
+// Single-pass forms for C = 128 * NV (NV float4 per lane): a warp owns pixels p = warp, warp + 8, ...; it reads row p ONCE (coalesced
+// 512-byte segments), forms the gate from the row's dot product with w and accumulates gate * row into per-lane partial sums; the eight
+// warps' partials are added through shared memory in a fixed order. The per-channel loops of the kernels above walk all HW pixels
+// serially with C of 256 threads active (35 / 45 us at 64 x 250 x 128, the cnn_small head); these take one pass with all warps busy.
+template <int NV>
+__global__ void __launch_bounds__(256)
+attn_pool_fwd1_kernel(const float* __restrict__ a, int HW, const float* __restrict__ w, const float* __restrict__ b0, float* __restrict__ gate,
+                      float* __restrict__ pooled) {
+  constexpr int C = 128 * NV;
+  __shared__ float4 part[8][32 * NV];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4* ab = reinterpret_cast<const float4*>(a + (size_t)b * HW * C);
+  float* gb = gate + (size_t)b * HW;
+  float4 wv[NV], acc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    wv[j] = w != nullptr ? reinterpret_cast<const float4*>(w)[lane + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float bias = (w != nullptr && b0 != nullptr) ? b0[0] : 0.f;
+  for (int p = warp; p < HW; p += 8) {
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = ab[(size_t)p * (C / 4) + lane + 32 * j];
+    float g = 1.0f;
+    if (w != nullptr) {
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) s = fmaf(v[j].x, wv[j].x, fmaf(v[j].y, wv[j].y, fmaf(v[j].z, wv[j].z, fmaf(v[j].w, wv[j].w, s))));
+      s = warp_sum(s);
+      g = 1.0f / (1.0f + expf(-(s + bias)));
+    }
+    if (lane == 0) gb[p] = g;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      acc[j].x = fmaf(v[j].x, g, acc[j].x); acc[j].y = fmaf(v[j].y, g, acc[j].y);
+      acc[j].z = fmaf(v[j].z, g, acc[j].z); acc[j].w = fmaf(v[j].w, g, acc[j].w);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) part[warp][lane + 32 * j] = acc[j];
+  __syncthreads();
+  const float inv = 1.0f / (float)HW;
+  for (int i = tid; i < 32 * NV; i += 256) {
+    float4 s = part[0][i];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { const float4 q = part[k][i]; s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w; }
+    reinterpret_cast<float4*>(pooled + (size_t)b * C)[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256)
+attn_pool_bwd1_kernel(const float* __restrict__ a, const float* __restrict__ gate, const float* __restrict__ dpooled, int HW, const float* __restrict__ w,
+                      float* __restrict__ da, float* __restrict__ dw, float* __restrict__ db0) {
+  constexpr int C = 128 * NV;
+  __shared__ float4 part[8][32 * NV];
+  __shared__ float dbs[8];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float4* ab = reinterpret_cast<const float4*>(a + (size_t)b * HW * C);
+  float4* dab = reinterpret_cast<float4*>(da + (size_t)b * HW * C);
+  const float* gb = gate + (size_t)b * HW;
+  const float inv = 1.0f / (float)HW;
+  float4 gp[NV], wv[NV], dwacc[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    gp[j] = reinterpret_cast<const float4*>(dpooled + (size_t)b * C)[lane + 32 * j];
+    gp[j].x *= inv; gp[j].y *= inv; gp[j].z *= inv; gp[j].w *= inv;
+    wv[j] = w != nullptr ? reinterpret_cast<const float4*>(w)[lane + 32 * j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    dwacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float dbacc = 0.f;
+  for (int p = warp; p < HW; p += 8) {
+    if (w == nullptr) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j) dab[(size_t)p * (C / 4) + lane + 32 * j] = gp[j];
+      continue;
+    }
+    float4 v[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) v[j] = ab[(size_t)p * (C / 4) + lane + 32 * j];
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) t = fmaf(v[j].x, gp[j].x, fmaf(v[j].y, gp[j].y, fmaf(v[j].z, gp[j].z, fmaf(v[j].w, gp[j].w, t))));
+    t = warp_sum(t);                                  // = (row . dpooled) / HW
+    const float sg = gb[p];
+    const float d = sg * (1.0f - sg) * t;
+    dbacc += d;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float4 o;
+      o.x = fmaf(gp[j].x, sg, d * wv[j].x); o.y = fmaf(gp[j].y, sg, d * wv[j].y);
+      o.z = fmaf(gp[j].z, sg, d * wv[j].z); o.w = fmaf(gp[j].w, sg, d * wv[j].w);
+      dab[(size_t)p * (C / 4) + lane + 32 * j] = o;
+      dwacc[j].x = fmaf(d, v[j].x, dwacc[j].x); dwacc[j].y = fmaf(d, v[j].y, dwacc[j].y);
+      dwacc[j].z = fmaf(d, v[j].z, dwacc[j].z); dwacc[j].w = fmaf(d, v[j].w, dwacc[j].w);
+    }
+  }
+  if (w == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) part[warp][lane + 32 * j] = dwacc[j];
+  if (lane == 0) dbs[warp] = dbacc;
+  __syncthreads();
+  for (int i = tid; i < 32 * NV; i += 256) {
+    float4 s = part[0][i];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { const float4 q = part[k][i]; s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w; }
+    atomicAdd(dw + 4 * i + 0, s.x); atomicAdd(dw + 4 * i + 1, s.y); atomicAdd(dw + 4 * i + 2, s.z); atomicAdd(dw + 4 * i + 3, s.w);
+  }
+  if (tid == 0 && db0 != nullptr) {
+    float s = 0.f;
+    for (int k = 0; k < 8; ++k) s += dbs[k];
+    atomicAdd(db0, s);
   }
 }
 
@@ -359,9 +477,22 @@ __global__ void head_dx_kernel(const float* __restrict__ dz, const float* __rest
 
 using namespace pc;
 
+static bool attn_single_pass() {
+  static const bool on = [] { const char* e = getenv("PC_ATTN_POOL1"); return e == nullptr || e[0] != '0'; }();
+  return on;
+}
+
 extern "C" int pc_attn_pool_fwd(const float* a, int B, int HW, int C, const float* w, const float* b0, float* gate,
                                 float* pooled, pc_stream_t stream) {
   PC_REQUIRE(a && gate && pooled && B > 0 && HW > 0 && C > 0, PC_EINVAL, "pc_attn_pool_fwd: bad arguments");
+  const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(pooled)) & 15) == 0;
+  if (al && attn_single_pass() && (C == 128 || C == 256 || C == 512)) {
+    if (C == 128) attn_pool_fwd1_kernel<1><<<B, 256, 0, stream>>>(a, HW, w, b0, gate, pooled);
+    else if (C == 256) attn_pool_fwd1_kernel<2><<<B, 256, 0, stream>>>(a, HW, w, b0, gate, pooled);
+    else attn_pool_fwd1_kernel<4><<<B, 256, 0, stream>>>(a, HW, w, b0, gate, pooled);
+    PC_LAUNCH_CHECK("attn_pool_fwd1_kernel");
+    return PC_OK;
+  }
   attn_pool_fwd_kernel<<<B, 256, 0, stream>>>(a, HW, C, w, b0, gate, pooled);
   PC_LAUNCH_CHECK("attn_pool_fwd_kernel");
   return PC_OK;
@@ -375,6 +506,14 @@ extern "C" int pc_attn_pool_bwd(const float* a, const float* gate, const float* 
   if (w != nullptr) {
     PC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * C, stream));
     PC_CUDA(cudaMemsetAsync(db0, 0, sizeof(float), stream));
+  }
+  const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dpooled) | reinterpret_cast<uintptr_t>(da)) & 15) == 0;
+  if (al && attn_single_pass() && (C == 128 || C == 256 || C == 512)) {
+    if (C == 128) attn_pool_bwd1_kernel<1><<<B, 256, 0, stream>>>(a, gate, dpooled, HW, w, da, dw, db0);
+    else if (C == 256) attn_pool_bwd1_kernel<2><<<B, 256, 0, stream>>>(a, gate, dpooled, HW, w, da, dw, db0);
+    else attn_pool_bwd1_kernel<4><<<B, 256, 0, stream>>>(a, gate, dpooled, HW, w, da, dw, db0);
+    PC_LAUNCH_CHECK("attn_pool_bwd1_kernel");
+    return PC_OK;
   }
   attn_pool_bwd_kernel<<<B, 256, sizeof(float) * HW, stream>>>(a, gate, dpooled, HW, C, w, da, dw, db0);
   PC_LAUNCH_CHECK("attn_pool_bwd_kernel");

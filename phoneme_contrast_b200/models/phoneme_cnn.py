@@ -309,7 +309,8 @@ def _small_backward(net, s, demb, grads, training=True):
     wgrad = _WgradLane(net, keep)
     sb = _sync_of(net, training)
     dout = _head_bwd(net, s, demb, grads, training)
-    amax = _AmaxSlots(demb.device, 6)   # max|dy| of every gradient tensor a convolution consumes (FP16X2 operand scale)
+    zp = ops.ZeroPool(demb.device, 1 << 15)     # zeroed reduction targets of all BatchNorm backward passes: one fill instead of one per tensor
+    amax = _AmaxSlots(demb.device, 6, zp)   # max|dy| of every gradient tensor a convolution consumes (FP16X2 operand scale)
     for b in (2, 1, 0):
         convA, bnA, convB, bnB = blocks[b][0], blocks[b][1], blocks[b][3], blocks[b][4]
         ly = s.layers[b]
@@ -318,7 +319,7 @@ def _small_backward(net, s, demb, grads, training=True):
         dbA_bn, dbA_w = _bias_from_bn(ly["coA"], grads, convA.bias)
         psB, psA = ly["aA"] is not None, ly["xin_ps"] is not None       # gradient tensors in plane form wherever the consumers gather planes
         dyB, _, _ = ops.bn_act_bwd(dout, ly["yB"], ly["coB"], ly["pool"], s.drop[b], None, grads[bnB.weight], grads[bnB.bias], mB, db_conv=dbB_bn,
-                                   planes=psB, sync=sb)
+                                   planes=psB, zp=zp, sync=sb)
         # data gradient (critical path) first, then the weight gradient of the same dy on the side stream (see _deep_backward)
         dA = ops.conv_dgrad(dyB, ly["cwB"].wd, ly["gB"], prec=ly["cwB"].prec_d, dy_amax=mB, dy_presplit=psB)
         if psB:
@@ -326,7 +327,7 @@ def _small_backward(net, s, demb, grads, training=True):
         else:
             xfA = dict(scale=ly["coA"].scale, shift=ly["coA"].shift, relu=True)
             wgrad(ly["yA"], dyB, ly["gB"], xfA, grads[convB.weight], dbB_w, prec, mB)
-        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA, db_conv=dbA_bn, planes=psA, sync=sb)
+        dyA, _, _ = ops.bn_act_bwd(dA, ly["yA"], ly["coA"], 0, None, None, grads[bnA.weight], grads[bnA.bias], mA, db_conv=dbA_bn, planes=psA, zp=zp, sync=sb)
         if b > 0:
             dout = ops.conv_dgrad(dyA, ly["cwA"].wd, ly["gA"], prec=ly["cwA"].prec_d, dy_amax=mA, dy_presplit=psA)
         if psA:

@@ -471,3 +471,34 @@ def test_stem_forward_one_pass_vs_two_pass(B, shape, training, monkeypatch):
     hi = halves[: p_b.numel()].float().view_as(p_b)
     lo = halves[p_b.numel():].float().view_as(p_b)
     assert float((hi + lo / 2048.0 - p_b).abs().max()) <= 1e-6 * scale
+
+
+@pytest.mark.parametrize("shape", [(64, 10, 25, 128), (16, 3, 7, 512), (8, 5, 13, 256), (4, 3, 5, 96)])
+@pytest.mark.parametrize("attention", [True, False])
+def test_attn_pool_single_pass_vs_torch(shape, attention):
+    """SpatialAttention gate + global average pool (reference phoneme_cnn.py:129-143, :117-119): the single-pass warp-per-pixel kernels
+    (C = 128 / 256 / 512) and the general kernels (C = 96) against torch autograd on the GPU."""
+    from phoneme_contrast_b200 import ops
+    B, H, W, C_ = shape
+    g = torch.Generator().manual_seed(B + C_)
+    a = torch.randn(B, H, W, C_, generator=g).cuda()
+    w = (torch.randn(C_, generator=g) * 0.2).cuda() if attention else None
+    b0 = torch.randn(1, generator=g).cuda() if attention else None
+    dp = torch.randn(B, C_, generator=g).cuda()
+    pooled, gate = ops.attn_pool_fwd(a, w, b0)
+    da, dw, db0 = ops.attn_pool_bwd(a, gate, dp, w)
+    ar = a.clone().requires_grad_(True)
+    if attention:
+        wr, br = w.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+        gr = torch.sigmoid((ar * wr).sum(-1) + br)
+        want = (ar * gr.unsqueeze(-1)).mean((1, 2))
+    else:
+        want = ar.mean((1, 2))
+    want.backward(dp)
+    tol = dict(rtol=2e-5, atol=2e-5)
+    torch.testing.assert_close(pooled, want.detach(), **tol)
+    torch.testing.assert_close(da, ar.grad, **tol)
+    if attention:
+        torch.testing.assert_close(gate, gr.detach().reshape(B, H * W), **tol)
+        torch.testing.assert_close(dw, wr.grad, rtol=1e-4, atol=1e-4)
+        torch.testing.assert_close(db0, br.grad, rtol=1e-4, atol=1e-4)
