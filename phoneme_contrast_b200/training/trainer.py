@@ -144,20 +144,43 @@ class ContrastiveTrainer:
             self.optimizer.step()
         return loss.detach()
 
-    def _train_epoch(self) -> Dict[str, float]:
-        self.model.train()
+    def run_batches(self, batches, on_loss=None) -> Tuple[torch.Tensor, int]:
+        """The hot loop of reference trainer.py:138-160 over an iterable of host (or device-resident) batches: one-batch-ahead copy on a
+        side stream (`prefetch`), `step`, loss accumulated on the device. Returns (device sum of the losses, number of batches).
+        on_loss(i, value): every step's loss is ALSO read on the host, without stalling the pipeline -- step i's scalar is copied to
+        pinned memory behind the step and handed to the callback while step i + 1 is already running (the reference reads
+        `loss.item()` right after each step, trainer.py:155,160, which drains the GPU every iteration); the last one is delivered
+        before this method returns."""
         total = torch.zeros((), device=self.device, dtype=torch.float32)
-        num_batches = 0
-        sync_each = bool(self.config.get("sync_loss_every_step", False))
-        pbar = tqdm(self.train_loader, desc=f"Epoch {self.current_epoch + 1}", disable=not self.config.get("progress", True))
-        for views, labels in self.prefetch(pbar):
+        n = 0
+        pending = None            # (index, pinned scalar, event) of the previous step
+        ring = torch.empty(2, dtype=torch.float32).pin_memory() if on_loss is not None else None
+        for views, labels in self.prefetch(batches):
             loss = self.step(views, labels)
             total += loss
-            num_batches += 1
+            if on_loss is not None:
+                slot = ring[n & 1:(n & 1) + 1]
+                slot.copy_(loss.reshape(1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[2].synchronize()
+                    on_loss(pending[0], float(pending[1]))
+                pending = (n, slot, ev)
+            n += 1
             self.global_step += 1
-            if sync_each and hasattr(pbar, "set_postfix"):
-                pbar.set_postfix({"loss": loss.item()})
-        mean_loss = float(total.item()) / max(num_batches, 1)     # the epoch's only host sync
+        if pending is not None:
+            pending[2].synchronize()
+            on_loss(pending[0], float(pending[1]))
+        return total, n
+
+    def _train_epoch(self) -> Dict[str, float]:
+        self.model.train()
+        sync_each = bool(self.config.get("sync_loss_every_step", False))
+        pbar = tqdm(self.train_loader, desc=f"Epoch {self.current_epoch + 1}", disable=not self.config.get("progress", True))
+        show = (lambda i, v: pbar.set_postfix({"loss": v})) if (sync_each and hasattr(pbar, "set_postfix")) else None
+        total, num_batches = self.run_batches(pbar, on_loss=show)
+        mean_loss = float(total.item()) / max(num_batches, 1)     # the epoch's only blocking host sync
         self._check_f16_range()
         if self._graphed and hasattr(self._graphed, "check"):
             self._graphed.check()          # peer-memory exchange: a device barrier that timed out (a rank stopped) invalidates the epoch
