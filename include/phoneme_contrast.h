@@ -396,6 +396,24 @@ int pc_clip_adam_dev(float* p, const float* g, float* m, float* v, int64_t n, co
 /* counter[0] += inc on the stream (device-side step counters for captured steps). */
 int pc_counter_add(int64_t* counter, int64_t inc, pc_stream_t stream);
 
+/* Fused BatchNorm-backward reduce (csrc/conv_halo.cu): the stride-1 3x3 data gradient that produces dx = dL/d(drop * relu(bn(y)))
+ * also accumulates, for the pixels it writes, sums [2][C] fp64 = (sum dz, sum dz xhat) and maxes [2] = (max |dz|, max |xhat|) with
+ * dz = [bn(y) > 0] * dx * drop, xhat = (y - mean) * invstd -- the outputs of pc_bn_act_bwd_reduce(dx, y, ..., pool = 0), which is then
+ * skipped (one read of dx and y less per layer). sums / maxes must be zeroed by the caller. PC_EUNSUPPORTED when the layer is not on
+ * the halo engine (pc_conv_halo_supported). Reference: the autograd backward of ResidualBlock.forward, src/models/phoneme_cnn.py:173-184. */
+typedef struct PcBnBwdReduce {
+  const float* y;        /* [B,H,W,C] pre-BatchNorm tensor of the layer below                      */
+  const float* scale;    /* [C] train-mode BatchNorm coefficients of that layer                    */
+  const float* shift;
+  const float* mean;
+  const float* invstd;
+  const float* drop;     /* [B,C] Dropout2d multipliers or NULL                                    */
+  double* sums;          /* [2][C] out                                                             */
+  float* maxes;          /* [2] out or NULL                                                        */
+} PcBnBwdReduce;
+int pc_conv_dgrad_halo_bnred(const void* dy_planes, const void* wp, const PcConvGeom* g, float* dx, const float* dy_amax,
+                             const PcBnBwdReduce* red, pc_stream_t stream);
+
 /* Two-phase forms of pc_head_fwd / pc_head_bwd for BatchNorm1d statistics synchronised across data-parallel ranks (train mode): the caller
  * exchanges bn_sums [2][N] fp64 between the phases. forward phase 1: Linear + (sum z, sum z^2) -> bn_sums; phase 2: mean / invstd /
  * running statistics from bn_sums over `count` rows (the GLOBAL batch) + normalise. backward phase 1: dL/d(bn output) + (sum d, sum d xhat)

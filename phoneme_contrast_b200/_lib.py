@@ -48,6 +48,10 @@ class PcBnFinalize(C.Structure):
                 ("invstd", vp)]
 
 
+class PcBnBwdReduce(C.Structure):
+    _fields_ = [("y", vp), ("scale", vp), ("shift", vp), ("mean", vp), ("invstd", vp), ("drop", vp), ("sums", vp), ("maxes", vp)]
+
+
 class PcPackJob(C.Structure):
     _fields_ = [("w_oihw", vp), ("out", vp)] + [(n, C.c_int32) for n in ("O", "I", "R", "S", "dgrad", "prec")] + [("item_begin", C.c_int64)]
 
@@ -88,6 +92,7 @@ SIGNATURES = {
     "pc_conv_halo_supported": (i32, [C.POINTER(PcConvGeom), i32]),
     "pc_conv_fwd_halo": (i32, [vp, vp, vp, C.POINTER(PcConvGeom), vp, vp, vp]),
     "pc_conv_dgrad_halo": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, i32, vp, vp]),
+    "pc_conv_dgrad_halo_bnred": (i32, [vp, vp, C.POINTER(PcConvGeom), vp, vp, C.POINTER(PcBnBwdReduce), vp]),
     "pc_conv_wgrad_workspace": (sz, [C.POINTER(PcConvGeom)]),
     "pc_conv_wgrad": (i32, [vp, vp, C.POINTER(PcConvGeom), C.POINTER(PcInXform), vp, vp, vp, sz, i32, vp, i32, vp]),
     "pc_stem_fwd_supported": (i32, [i32, i32, i32, i32]),

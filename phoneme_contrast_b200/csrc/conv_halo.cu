@@ -62,6 +62,10 @@ struct Params {
   uint32_t region_bytes;     // one part (hi or lo) of an A region: nbox * box_pos * 128, rounded up to 1024
   uint32_t a_tx_bytes;       // bytes the TMA boxes of one region deliver (both parts, unrounded)
   FastDiv d_pimg, d_wp, d_box, d_hp1, d_nt;
+  // Fused BatchNorm-backward REDUCE pass (data gradient of conv2 -> backward of bn1, pool-free): with red.y set the epilogue also forms
+  // dz = [bn(y) > 0] * dA * drop and xhat = (y - mean) * invstd for every pixel it has just produced and accumulates sum dz, sum dz xhat
+  // per channel plus max |dz|, max |xhat| -- what pc_bn_act_bwd_reduce would re-read dA and y from HBM for.
+  PcBnBwdReduce red;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -115,7 +119,7 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
 // BatchNorm sums: BN = 64 layers have one output-channel tile and up to 15 tiles per CTA with a 3.5 k-cycle main loop, so a
 // 62-shuffle cross-row reduction per chunk and tile would make the epilogue the bottleneck; each thread instead keeps its row's
 // running sum / sum of squares of its 32 columns in registers over ALL its tiles and the cross-row reduction happens once per CTA.
-template <int BN, int NACC, int NBUF>
+template <int BN, int NACC, int NBUF, bool RED>
 __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_base, float a_scale, uint64_t* acc_full, uint64_t* acc_empty,
                                                float* s_sum, float* s_sq, const float* s_bias, uint32_t cl_id, uint32_t n_cl, int CL, uint32_t rank) {
   constexpr uint32_t TM_BUF = NACC * BN;
@@ -126,7 +130,13 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
   const int half = (warp - 2) >> 2;
   const int row = quarter * 32 + lane;
   const float out_scale = 1.f / a_scale;
-  const bool want_stats = p.stats != nullptr;
+  const bool want_red = RED;                                // fused BatchNorm-backward reduce (see Params::red); never accumulates into C
+  const bool want_stats = p.stats != nullptr || want_red;   // the same accumulators serve (sum v, sum v^2) or (sum dz, sum dz xhat)
+  const float* s_rscale = s_bias + p.Npad;                  // [Npad] each, filled by the kernel prologue when want_red
+  const float* s_rshift = s_rscale + p.Npad;
+  const float* s_rmean = s_rshift + p.Npad;
+  const float* s_rinv = s_rmean + p.Npad;
+  float mx_dz = 0.f, mx_xh = 0.f;
   float rs[REGSTATS ? 32 : 1], rq[REGSTATS ? 32 : 1];
 #pragma unroll
   for (int k = 0; k < (REGSTATS ? 32 : 1); ++k) rs[k] = rq[k] = 0.f;
@@ -139,8 +149,9 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
     const long long q = (long long)m_tile * BM + row;
     bool valid = q < p.Q;
     long long pix = 0;
+    uint32_t b = 0;
     if (valid) {
-      uint32_t b, rem, hp, wp;
+      uint32_t rem, hp, wp;
       p.d_pimg.divmod((uint32_t)q, b, rem);
       p.d_wp.divmod(rem, hp, wp);
       const int oh = p.o_stride * ((int)hp - 1) + p.o_off_h, ow = p.o_stride * ((int)wp - 1) + p.o_off_w;
@@ -156,17 +167,29 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         oldv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.accumulate && valid && n0 + c0 + 4 * k < p.Nn) oldv[k] = *reinterpret_cast<const float4*>(dst_row + c0 + 4 * k);
+        if (!RED && p.accumulate && valid && n0 + c0 + 4 * k < p.Nn) oldv[k] = *reinterpret_cast<const float4*>(dst_row + c0 + 4 * k);
       }
     };
     load_old(32 * half);
+    // fused reduce: this row's y chunk (and dropout multipliers) are fetched before waiting for the accumulator as well
+    const float* y_row = want_red ? p.red.y + (size_t)(valid ? pix : 0) * p.Nn + n0 : nullptr;
+    const float* d_row = (want_red && p.red.drop != nullptr) ? p.red.drop + (size_t)b * p.Nn + n0 : nullptr;
+    float4 yv[8];
+    auto load_y = [&](int c0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        yv[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (RED && valid && n0 + c0 + 4 * k < p.Nn) yv[k] = *reinterpret_cast<const float4*>(y_row + c0 + 4 * k);
+      }
+    };
+    load_y(32 * half);
     mbar_wait(&acc_full[tb], (ti / NBUF) & 1u);
     tc_fence_after();
     const uint32_t t_row = tmem_base + tb * TM_BUF + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
     for (int ci = 0; ci < NCH; ++ci) {
       const int c0 = 32 * (half + 2 * ci);
-      if (ci > 0) load_old(c0);
+      if (ci > 0) { load_old(c0); load_y(c0); }
       float v[32], u[32];
       {
         uint32_t r0[32], r1[32];
@@ -195,7 +218,7 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
           if (n0 + c0 + k < p.Nn) {
             float4 o = make_float4(v[k], v[k + 1], v[k + 2], v[k + 3]);
             float* d = dst_row + c0 + k;
-            if (p.accumulate) {
+            if (!RED && p.accumulate) {
               const float4 old = oldv[k >> 2];
               o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
             }
@@ -203,14 +226,34 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
           }
         }
       }
+      if (want_red) {
+        // v[k] = dA of a real pixel (0 otherwise) -> v[k] = dz, u[k] = dz * xhat
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int c = n0 + c0 + k;
+          const float4 y4 = yv[k >> 2];
+          const float yy = (k & 3) == 0 ? y4.x : ((k & 3) == 1 ? y4.y : ((k & 3) == 2 ? y4.z : y4.w));
+          const bool on = valid && c < p.Nn && fmaf(yy, s_rscale[c], s_rshift[c]) > 0.f;
+          const float dr = d_row != nullptr && valid && c < p.Nn ? __ldg(d_row + c0 + k) : 1.f;
+          const float dzv = on ? v[k] * dr : 0.f;
+          const float xh = (valid && c < p.Nn) ? (yy - s_rmean[c]) * s_rinv[c] : 0.f;
+          v[k] = dzv;
+          u[k] = dzv * xh;
+          mx_dz = fmaxf(mx_dz, fabsf(dzv));
+          mx_xh = fmaxf(mx_xh, fabsf(xh));
+        }
+      }
       if (want_stats) {
         if (REGSTATS) {
 #pragma unroll
-          for (int k = 0; k < 32; ++k) { rs[k & (REGSTATS ? 31 : 0)] += v[k]; rq[k & (REGSTATS ? 31 : 0)] = fmaf(v[k], v[k], rq[k & (REGSTATS ? 31 : 0)]); }
+          for (int k = 0; k < 32; ++k) {
+            rs[k & (REGSTATS ? 31 : 0)] += v[k];
+            rq[k & (REGSTATS ? 31 : 0)] = want_red ? rq[k & (REGSTATS ? 31 : 0)] + u[k] : fmaf(v[k], v[k], rq[k & (REGSTATS ? 31 : 0)]);
+          }
         } else {
           float sq[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) sq[k] = v[k] * v[k];
+          for (int k = 0; k < 32; ++k) sq[k] = want_red ? u[k] : v[k] * v[k];
           const float cs = warp_reduce_scatter32(v, lane);
           const float cq = warp_reduce_scatter32(sq, lane);
           atomicAdd(&s_sum[n0 + c0 + lane], cs);
@@ -234,11 +277,20 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
       atomicAdd(&s_sq[32 * half + lane], cq);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+    double* dst = want_red ? p.red.sums : p.stats;
     for (int i = tid - 64; i < p.Nn; i += 32 * EPI_WARPS) {
       const float a = s_sum[i], b = s_sq[i];
       if (a != 0.f || b != 0.f) {
-        atomicAdd(p.stats + i, (double)a);
-        atomicAdd(p.stats + p.Nn + i, (double)b);
+        atomicAdd(dst + i, (double)a);
+        atomicAdd(dst + p.Nn + i, (double)b);
+      }
+    }
+    if (want_red && p.red.maxes != nullptr) {        // non-negative floats order like their bit patterns
+      mx_dz = warp_max(mx_dz);
+      mx_xh = warp_max(mx_xh);
+      if (lane == 0) {
+        atomicMax(reinterpret_cast<unsigned int*>(p.red.maxes), __float_as_uint(mx_dz));
+        atomicMax(reinterpret_cast<unsigned int*>(p.red.maxes + 1), __float_as_uint(mx_xh));
       }
     }
   }
@@ -249,7 +301,7 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
 // 5.6e-6 of max|y| against fp64 where the alternating sets give ~2e-6, so the deep-K layers (>= 256 gathered channels) use NACC = 4
 // with ONE TMEM buffer (their tiles run 36-72 k-chunks, the un-overlapped epilogue is < 5 % of a tile) and the shallow ones two
 // buffers (the epilogue of tile i hides under the main loop of tile i + 1).
-template <int BN, int NACC, int NBUF>
+template <int BN, int NACC, int NBUF, bool RED>
 __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
   constexpr uint32_t B_STAGE = 2u * BN * 128u;          // hi rows then lo rows
   constexpr uint32_t TM_BUF = NACC * BN;                 // TMEM columns per accumulator buffer
@@ -283,6 +335,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const __grid_cons
     s_sum[i] = 0.f;
     s_sq[i] = 0.f;
     s_bias[i] = (p.bias != nullptr && i < p.Nn) ? p.bias[i] : 0.f;
+    if (RED) {
+      const bool in = i < p.Nn;
+      s_bias[p.Npad + i] = in ? p.red.scale[i] : 0.f;
+      s_bias[2 * p.Npad + i] = in ? p.red.shift[i] : 0.f;
+      s_bias[3 * p.Npad + i] = in ? p.red.mean[i] : 0.f;
+      s_bias[4 * p.Npad + i] = in ? p.red.invstd[i] : 0.f;
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -411,7 +470,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const __grid_cons
     __syncwarp();
   } else {
     // ================================================================================= epilogue (warps 2..5)
-    epilogue_warps<BN, NACC, NBUF>(p, tmem_base, a_scale, acc_full, acc_empty, s_sum, s_sq, s_bias, cl_id, n_cl, CL, rank);
+    epilogue_warps<BN, NACC, NBUF, RED>(p, tmem_base, a_scale, acc_full, acc_empty, s_sum, s_sq, s_bias, cl_id, n_cl, CL, rank);
   }
 
   tc_fence_before();
@@ -430,7 +489,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_kernel(const __grid_cons
 // give comes from phasing the two operand planes instead: the MMAs that read the hi plane (36 per tile, a_hi x [b_hi ; b_lo])
 // are issued first, then the 36 that read the lo plane (a_lo x b_hi), and each plane has its own full / empty barrier pair, so
 // the lo plane of tile i + 1 streams in under the hi MMAs of tile i + 1 and the hi plane of tile i + 1 under the lo MMAs of tile i.
-template <int BN, int NACC, int NBUF>
+template <int BN, int NACC, int NBUF, bool RED>
 __global__ void __launch_bounds__(THREADS, 1) conv_halo_res_kernel(const __grid_constant__ CUtensorMap amap, const Params p) {
   constexpr uint32_t B_STAGE = 2u * BN * 128u;
   constexpr uint32_t TM_BUF = NACC * BN;
@@ -455,6 +514,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_res_kernel(const __grid_
     s_sum[i] = 0.f;
     s_sq[i] = 0.f;
     s_bias[i] = (p.bias != nullptr && i < p.Nn) ? p.bias[i] : 0.f;
+    if (RED) {
+      const bool in = i < p.Nn;
+      s_bias[p.Npad + i] = in ? p.red.scale[i] : 0.f;
+      s_bias[2 * p.Npad + i] = in ? p.red.shift[i] : 0.f;
+      s_bias[3 * p.Npad + i] = in ? p.red.mean[i] : 0.f;
+      s_bias[4 * p.Npad + i] = in ? p.red.invstd[i] : 0.f;
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -554,7 +620,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_halo_res_kernel(const __grid_
     }
     __syncwarp();
   } else {
-    epilogue_warps<BN, NACC, NBUF>(p, tmem_base, a_scale, acc_full, acc_empty, s_sum, s_sq, s_bias, blockIdx.x, gridDim.x, 1, 0u);
+    epilogue_warps<BN, NACC, NBUF, RED>(p, tmem_base, a_scale, acc_full, acc_empty, s_sum, s_sq, s_bias, blockIdx.x, gridDim.x, 1, 0u);
   }
   tc_fence_before();
   __syncthreads();
@@ -600,7 +666,7 @@ static bool make_plan(int H, int W, int BN, int Npad, Plan& pl, int halo = -1) {
   if (pl.nbox > MAX_BOX) return false;
   pl.region_bytes = (uint32_t)pl.nbox * pl.box_pos * 128u;
   pl.region_bytes = (pl.region_bytes + 1023u) & ~1023u;
-  const size_t fixed = 2 * (size_t)2 * pl.region_bytes + sizeof(uint64_t) * (8 + 2 * MAX_BST) + 16 + sizeof(float) * 3 * (size_t)Npad + 1024;
+  const size_t fixed = 2 * (size_t)2 * pl.region_bytes + sizeof(uint64_t) * (8 + 2 * MAX_BST) + 16 + sizeof(float) * 7 * (size_t)Npad + 1024;
   const size_t budget = 227 * 1024;
   if (fixed + 2 * (size_t)2 * BN * 128 > budget) return false;
   int st = (int)((budget - fixed) / ((size_t)2 * BN * 128));
@@ -622,7 +688,7 @@ static inline int pick_bn(int Nn) { return Nn <= 64 ? 64 : 128; }
 struct TapSpec { int n; int shift[9]; int id[9]; int off_h, off_w; };
 static int run(const void* planes, const void* wp, const float* bias, const float* a_amax, float* out, double* stats, int B, int H, int W, int Ca,
                int Nn, int dgrad, int accumulate, pc_stream_t stream, int ntaps = 9, int a_stride = 1, int Ha = 0, int Wa = 0, int Hout = 0,
-               int Wout = 0, int o_stride = 1, const TapSpec* taps = nullptr) {
+               int Wout = 0, int o_stride = 1, const TapSpec* taps = nullptr, const PcBnBwdReduce* red = nullptr) {
   if (taps != nullptr) ntaps = taps->n;
   const int BN = pick_bn(Nn);
   const int Npad = ceil_div(Nn, BN) * BN;
@@ -636,6 +702,7 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
   PC_REQUIRE(enc != nullptr, PC_ECUDA, "conv_halo: cuTensorMapEncodeTiled is not available from this driver");
   Params p{};
   p.Bp = static_cast<const unsigned char*>(wp); p.bias = bias; p.a_amax = a_amax; p.C = out; p.stats = stats;
+  if (red != nullptr) p.red = *red;
   p.B = B; p.H = H; p.W = W; p.Ca = Ca; p.Nn = Nn; p.Npad = Npad;
   p.Wp = W + 1; p.Pimg = (H + 1) * (W + 1); p.RB = pl.RB; p.box_pos = pl.box_pos; p.nbox = pl.nbox;
   p.Q = (long long)B * p.Pimg;
@@ -675,19 +742,28 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
 
   // weight-resident variant: one 64-channel chunk, one 64-channel output tile, and all nine taps' weights + one activation
   // region fit the 227 KB of shared memory
-  const size_t res_smem = 2 * (size_t)pl.region_bytes + 9 * (size_t)2 * BN * 128 + sizeof(uint64_t) * 10 + 16 + sizeof(float) * 3 * (size_t)Npad + 1024;
+  const size_t res_smem = 2 * (size_t)pl.region_bytes + 9 * (size_t)2 * BN * 128 + sizeof(uint64_t) * 10 + 16 + sizeof(float) * 7 * (size_t)Npad + 1024;
   const bool resident = env_int("PC_HALO_RESIDENT", 1) != 0 && ntaps == 9 && taps == nullptr && BN == 64 && p.cpt == 1 && p.n_ntiles == 1 && res_smem <= 227 * 1024;
   if (resident) {
     p.cluster = CL = 1;
     p.n_items = p.n_mtiles;
     p.d_nt = FastDiv::make(1u);
-    static size_t conf = 0;
-    if (res_smem > conf) {
-      PC_CUDA(cudaFuncSetAttribute((conv_halo_res_kernel<64, 2, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
-      conf = res_smem;
-    }
     const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-    conv_halo_res_kernel<64, 2, 2><<<grid, THREADS, res_smem, stream>>>(amap, p);
+    if (red != nullptr) {
+      static size_t conf_r = 0;
+      if (res_smem > conf_r) {
+        PC_CUDA(cudaFuncSetAttribute((conv_halo_res_kernel<64, 2, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
+        conf_r = res_smem;
+      }
+      conv_halo_res_kernel<64, 2, 2, true><<<grid, THREADS, res_smem, stream>>>(amap, p);
+    } else {
+      static size_t conf = 0;
+      if (res_smem > conf) {
+        PC_CUDA(cudaFuncSetAttribute((conv_halo_res_kernel<64, 2, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
+        conf = res_smem;
+      }
+      conv_halo_res_kernel<64, 2, 2, false><<<grid, THREADS, res_smem, stream>>>(amap, p);
+    }
     PC_LAUNCH_CHECK("conv_halo_res_kernel");
     return PC_OK;
   }
@@ -705,20 +781,26 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = CL > 1 ? 1 : 0;
-#define PC_HALO_LAUNCH(BN_, NACC_, NBUF_)                                                                                              \
+#define PC_HALO_LAUNCH1(BN_, NACC_, NBUF_, RED_)                                                                                       \
   do {                                                                                                                          \
     static size_t conf = 0;                                                                                                     \
     if (pl.smem > conf) {                                                                                                       \
-      PC_CUDA(cudaFuncSetAttribute((conv_halo_kernel<BN_, NACC_, NBUF_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
+      PC_CUDA(cudaFuncSetAttribute((conv_halo_kernel<BN_, NACC_, NBUF_, RED_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem)); \
       conf = pl.smem;                                                                                                           \
     }                                                                                                                           \
-    PC_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN_, NACC_, NBUF_>, amap, p));                                                   \
+    PC_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN_, NACC_, NBUF_, RED_>, amap, p));                                             \
+  } while (0)
+#define PC_HALO_LAUNCH(BN_, NACC_, NBUF_)                       \
+  do {                                                          \
+    if (red != nullptr) PC_HALO_LAUNCH1(BN_, NACC_, NBUF_, true); \
+    else PC_HALO_LAUNCH1(BN_, NACC_, NBUF_, false);               \
   } while (0)
   if (BN == 64 && p.cpt <= 2) PC_HALO_LAUNCH(64, 2, 2);
   else if (BN == 64) PC_HALO_LAUNCH(64, 4, 2);
   else if (p.cpt >= 4) PC_HALO_LAUNCH(128, 4, 1);
   else PC_HALO_LAUNCH(128, 2, 2);
 #undef PC_HALO_LAUNCH
+#undef PC_HALO_LAUNCH1
   PC_LAUNCH_CHECK("conv_halo_kernel");
   return PC_OK;
 }
@@ -812,4 +894,15 @@ extern "C" int pc_conv_dgrad_halo(const void* dy_planes, const void* wp, const P
                          g->H, g->W, g->stride);
   }
   return pc::halo::run(dy_planes, wp, nullptr, dy_amax, dx, nullptr, g->B, g->H, g->W, g->Cout, g->Cin, 1, accumulate, stream);
+}
+
+// Stride-1 3x3 data gradient with the REDUCE pass of the BatchNorm backward that consumes dx fused into the epilogue (Params::red):
+// dx = dgrad(dy) is written as usual; red->sums / red->maxes (zeroed by the caller) receive what pc_bn_act_bwd_reduce(dx, red->y, ...,
+// pool = 0) would have produced, without re-reading dx and y from HBM.
+extern "C" int pc_conv_dgrad_halo_bnred(const void* dy_planes, const void* wp, const PcConvGeom* g, float* dx, const float* dy_amax,
+                                        const PcBnBwdReduce* red, pc_stream_t stream) {
+  PC_REQUIRE(dy_planes && wp && g && dx && dy_amax && red, PC_EINVAL, "pc_conv_dgrad_halo_bnred: null pointer");
+  PC_REQUIRE(red->y && red->scale && red->shift && red->mean && red->invstd && red->sums, PC_EINVAL, "pc_conv_dgrad_halo_bnred: incomplete reduce record");
+  if (!pc_conv_halo_supported(g, 1) || g->R != 3 || g->stride != 1) return PC_EUNSUPPORTED;
+  return pc::halo::run(dy_planes, wp, nullptr, dy_amax, dx, nullptr, g->B, g->H, g->W, g->Cout, g->Cin, 1, 0, stream, 9, 1, 0, 0, 0, 0, 1, nullptr, red);
 }

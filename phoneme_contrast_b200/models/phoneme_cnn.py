@@ -553,14 +553,24 @@ def _deep_backward(net, s, demb, grads, training=True):
         # are persistent one-CTA-per-SM tensor kernels that cannot share an SM; issued the other way round the weight gradient took
         # the SMs first and the critical path waited (measured: only 0.18 of its 0.76 ms was hidden). Behind the data gradient it
         # runs under the next layer's BatchNorm-backward passes, which are HBM-bound and co-reside with it.
-        dA1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2, dy_presplit=gps)
+        # PC_DGRAD_BNRED=1: on the halo engine the data gradient's epilogue also runs the REDUCE pass of bn1's backward over the dA1 it
+        # has just produced (sum dz, sum dz xhat, maxima; csrc/conv_halo.cu Params::red), one read of dA1 and y1 less per block.
+        # Correct (tests/test_gpu_halo.py::test_halo_dgrad_fused_bn_reduce) and 33 us less kernel time per step in isolation, but
+        # measured SLOWER in the captured step (3.022 vs 2.994 ms): the stand-alone reduce pass is HBM-bound and ran under the
+        # weight-gradient lane, the heavier epilogue sits on the critical path. OFF by default.
+        fused = ops.conv_dgrad_bn_reduce(dy2, r["cw2"].wd, r["g2"], m2, r["y1"], r["c1"], s.drop[i], planes=gps, zp=zp) \
+            if (gps and r["cw2"].prec_d == L.PREC_FP16X2 and os.environ.get("PC_DGRAD_BNRED", "0") == "1") else None
+        if fused is not None:
+            dA1, red1 = fused
+        else:
+            dA1, red1 = ops.conv_dgrad(dy2, r["cw2"].wd, r["g2"], prec=r["cw2"].prec_d, dy_amax=m2, dy_presplit=gps), None
         if r["a1"] is not None and prec == L.PREC_FP16X2:
             wgrad(r["a1"], dy2, r["g2"], dict(presplit=True), grads[blk.conv2.weight], db2_w, prec, m2, gps)
         else:
             xf1 = dict(scale=r["c1"].scale, shift=r["c1"].shift, relu=True, drop=s.drop[i])
             wgrad(r["y1"], dy2, r["g2"], xf1, grads[blk.conv2.weight], db2_w, prec, m2)
         dy1, _, _ = ops.bn_act_bwd(dA1, r["y1"], r["c1"], 0, s.drop[i], None, grads[blk.bn1.weight], grads[blk.bn1.bias], m1, planes=gps, zp=zp,
-                                   db_conv=db1_bn, sync=sb)
+                                   db_conv=db1_bn, sync=sb, reduced=red1)
         xin_w, xf_w = (r["xin_ps"], dict(presplit=True)) if r["xin_ps"] is not None else (r["xin"], None)
         if r["proj"]:
             # conv1's data gradient writes every pixel of dxin; the strided 1x1 shortcut then adds into the pixels it reads

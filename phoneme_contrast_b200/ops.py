@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib as L
@@ -212,6 +214,22 @@ def conv_dgrad(dy, wd, g: PcConvGeom, out=None, accumulate=False, prec=L.PREC_FP
     return out
 
 
+def conv_dgrad_bn_reduce(dy_ps, wd, g: PcConvGeom, dy_amax, y, co: "BnCoeffs", drop=None, planes=False, zp=None):
+    """conv_dgrad on the halo engine (pre-split dy planes) with the REDUCE pass of the BatchNorm backward that consumes its output
+    fused into the epilogue -> (dx, (sums, maxes)) to hand to bn_act_bwd(..., reduced=...), or None when the layer is not covered
+    (the caller then runs conv_dgrad + the stand-alone reduce)."""
+    if not (g.R == 3 and g.stride == 1) or not L.lib().pc_conv_halo_supported(C.byref(g), 1):
+        return None
+    C_ = g.Cin
+    out = torch.empty(g.B, g.H, g.W, C_, device=y.device, dtype=F32)
+    sums = _zeros(zp, (2, C_), torch.float64, y.device)
+    maxes = _zeros(zp, (2,), F32, y.device) if planes else None
+    red = L.PcBnBwdReduce(ptr(y), ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd), ptr(drop), ptr(sums, torch.float64), ptr(maxes))
+    L.note_work("pc_conv_dgrad", 2.0 * g.B * g.Ho * g.Wo * g.Cout * g.R * g.S * g.Cin)
+    call("pc_conv_dgrad_halo_bnred", ptr(dy_ps, None), ptr(wd, None), C.byref(g), ptr(out), ptr(dy_amax), C.byref(red), stream())
+    return out, (sums, maxes)
+
+
 _ws_cache: dict = {}
 
 
@@ -356,17 +374,20 @@ def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None, want_planes=False):
 
 
 def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None, planes=False, zp=None,
-               db_conv=None, sync=None):
+               db_conv=None, sync=None, reduced=None):
     """Gradient w.r.t. the pre-BatchNorm tensor y of out = drop * pool(relu(bn(y))) (train-mode statistics).
     amax: optional zero-initialised 1-element tensor that receives max|dy| (operand scale of the FP16X2 convolutions).
     planes=True: dy is returned ONLY as fp16 hi | lo planes (uint8 [2, numel*2]) scaled by the power of two derived from a bound
     of |dy| that is stored in `amax` (for convolutions called with dy_presplit=True)."""
     B, H, W, C_ = y.shape
-    sums = _zeros(zp, (2, C_), torch.float64, y.device)
-    maxes = _zeros(zp, (2,), F32, y.device) if planes else None
     args = (ptr(dout), ptr(y), B, H, W, C_, ptr(co.scale), ptr(co.shift), ptr(co.mean), ptr(co.invstd), ptr(drop), pool,
             ptr(argmax, torch.uint8))
-    call("pc_bn_act_bwd_reduce", *args, ptr(sums, torch.float64), ptr(maxes), stream())
+    if reduced is not None:
+        sums, maxes = reduced          # produced by the data gradient that wrote dout (conv_dgrad_bn_reduce): no reduce pass here
+    else:
+        sums = _zeros(zp, (2, C_), torch.float64, y.device)
+        maxes = _zeros(zp, (2,), F32, y.device) if planes else None
+        call("pc_bn_act_bwd_reduce", *args, ptr(sums, torch.float64), ptr(maxes), stream())
     if sync is not None:
         # synchronised BatchNorm: the apply pass takes the per-rank AVERAGE of the global (sum dz, sum dz xhat); with its local pixel
         # count the projection terms are then those of the global batch, and dgamma / dbeta are this rank's share of the all-reduced sum

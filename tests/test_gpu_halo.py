@@ -253,3 +253,59 @@ def test_halo_stride2_dgrad(case, accumulate, monkeypatch):
         assert L.lib().pc_conv_halo_supported(C.byref(g), 1) == 0
         dx0 = ops.conv_dgrad(dy_ps, cw.wd, g, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
         assert float((dx - dx0).abs().max()) <= 2e-6 * scale
+
+
+@pytest.mark.parametrize("drop_on", [False, True])
+@pytest.mark.parametrize("case", CASES[:4] + CASES[5:])
+def test_halo_dgrad_fused_bn_reduce(case, drop_on, monkeypatch):
+    """The data gradient whose epilogue also runs the REDUCE pass of the BatchNorm backward below it (Params::red): dx bit-identical
+    to the plain data gradient, (sum dz, sum dz xhat) and (max |dz|, max |xhat|) equal to pc_bn_act_bwd_reduce on that dx."""
+    from phoneme_contrast_b200 import _lib as L
+    from phoneme_contrast_b200 import ops
+    from phoneme_contrast_b200._lib import call, ptr, stream
+    B, H, W, Cin, Cout = case
+    g = ops.conv_geom(B, H, W, Cin, Cout, 3, 1, 1)
+    gen = torch.Generator(device=DEV).manual_seed(B * 31 + Cin + 5 * Cout)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=gen) * (2.0 / (Cin * 9)) ** 0.5
+    yconv = torch.randn(B, H, W, Cout, device=DEV, generator=gen)
+    dout = torch.randn(B, H, W, Cout, device=DEV, generator=gen) * 1e-6
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV)
+    st = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    st[0] = yconv.double().sum((0, 1, 2)); st[1] = (yconv.double() ** 2).sum((0, 1, 2))
+    co = ops.bn_finalize(st, B * H * W, bn, True)
+    cw = ops.ConvWeights(w, g, L.PREC_FP16X2)
+    a1 = torch.zeros(1, device=DEV)
+    dy_ps, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a1, planes=True)
+    monkeypatch.setenv("PC_HALO_ALL", "1")
+    # the layer BELOW (whose BatchNorm backward consumes dx): Cin channels, its own pre-BN tensor, coefficients and dropout multipliers
+    ylow = torch.randn(B, H, W, Cin, device=DEV, generator=gen) * 1.5 + 0.2
+    bnl = torch.nn.BatchNorm2d(Cin).to(DEV)
+    with torch.no_grad():
+        bnl.weight.copy_(torch.rand(Cin, device=DEV, generator=gen) + 0.5); bnl.bias.copy_(torch.randn(Cin, device=DEV, generator=gen) * 0.3)
+    stl = torch.zeros(2, Cin, device=DEV, dtype=torch.float64)
+    stl[0] = ylow.double().sum((0, 1, 2)); stl[1] = (ylow.double() ** 2).sum((0, 1, 2))
+    col = ops.bn_finalize(stl, B * H * W, bnl, True)
+    drop = ((torch.rand(B, Cin, device=DEV, generator=gen) > 0.2).float() / 0.8) if drop_on else None
+    fused = ops.conv_dgrad_bn_reduce(dy_ps, cw.wd, g, a1, ylow, col, drop, planes=True)
+    assert fused is not None
+    dx_f, (sums_f, maxes_f) = fused
+    dx = ops.conv_dgrad(dy_ps, cw.wd, g, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+    assert torch.equal(dx, dx_f)
+    sums = torch.zeros(2, Cin, device=DEV, dtype=torch.float64)
+    maxes = torch.zeros(2, device=DEV)
+    call("pc_bn_act_bwd_reduce", ptr(dx), ptr(ylow), B, H, W, Cin, ptr(col.scale), ptr(col.shift), ptr(col.mean), ptr(col.invstd), ptr(drop), 0,
+         None, ptr(sums, torch.float64), ptr(maxes), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(maxes, maxes_f), (maxes, maxes_f)
+    ref_scale = float(sums.abs().max())
+    assert float((sums - sums_f).abs().max()) <= 2e-5 * ref_scale, (float((sums - sums_f).abs().max()), ref_scale)
+    # and the whole BatchNorm backward from the fused reduce equals the two-pass one
+    m1, m2 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    dg1, db1 = torch.empty(Cin, device=DEV), torch.empty(Cin, device=DEV)
+    dg2, db2 = torch.empty(Cin, device=DEV), torch.empty(Cin, device=DEV)
+    dy_a, _, _ = ops.bn_act_bwd(dx, ylow, col, 0, drop, None, dg1, db1, m1)
+    dy_b, _, _ = ops.bn_act_bwd(dx, ylow, col, 0, drop, None, dg2, db2, m2, reduced=(sums_f, None))
+    sc = float(dy_a.abs().max())
+    assert float((dy_a - dy_b).abs().max()) <= 2e-5 * sc
+    torch.testing.assert_close(dg1, dg2, rtol=1e-4, atol=1e-5 * float(dg1.abs().max()))
+    torch.testing.assert_close(db1, db2, rtol=1e-4, atol=1e-5 * float(db1.abs().max()))
