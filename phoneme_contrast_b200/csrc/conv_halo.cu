@@ -123,8 +123,8 @@ template <int BN, int NACC, int NBUF, bool RED>
 __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_base, float a_scale, uint64_t* acc_full, uint64_t* acc_empty,
                                                float* s_sum, float* s_sq, const float* s_bias, uint32_t cl_id, uint32_t n_cl, int CL, uint32_t rank) {
   constexpr uint32_t TM_BUF = NACC * BN;
-  constexpr bool REGSTATS = (BN == 64);
-  constexpr int NCH = BN / 64;                       // 32-column chunks per warp and tile
+  constexpr bool REGSTATS = (BN <= 64);
+  constexpr int NCH = BN >= 64 ? BN / 64 : 1;        // 32-column chunks per warp and tile (BN = 32: one chunk, read by the `half` 0 warps only)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int quarter = warp & 3;
   const int half = (warp - 2) >> 2;
@@ -170,7 +170,8 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
         if (!RED && p.accumulate && valid && n0 + c0 + 4 * k < p.Nn) oldv[k] = *reinterpret_cast<const float4*>(dst_row + c0 + 4 * k);
       }
     };
-    load_old(32 * half);
+    const bool idle = BN == 32 && half == 1;                 // BN = 32: the second warp of each lane quarter has no columns
+    if (!idle) load_old(32 * half);
     // fused reduce: this row's y chunk (and dropout multipliers) are fetched before waiting for the accumulator as well
     const float* y_row = want_red ? p.red.y + (size_t)(valid ? pix : 0) * p.Nn + n0 : nullptr;
     const float* d_row = (want_red && p.red.drop != nullptr) ? p.red.drop + (size_t)b * p.Nn + n0 : nullptr;
@@ -182,12 +183,12 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
         if (RED && valid && n0 + c0 + 4 * k < p.Nn) yv[k] = *reinterpret_cast<const float4*>(y_row + c0 + 4 * k);
       }
     };
-    load_y(32 * half);
+    if (!idle) load_y(32 * half);
     mbar_wait(&acc_full[tb], (ti / NBUF) & 1u);
     tc_fence_after();
     const uint32_t t_row = tmem_base + tb * TM_BUF + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
-    for (int ci = 0; ci < NCH; ++ci) {
+    for (int ci = 0; ci < (idle ? 0 : NCH); ++ci) {
       const int c0 = 32 * (half + 2 * ci);
       if (ci > 0) { load_old(c0); load_y(c0); }
       float v[32], u[32];
@@ -267,7 +268,7 @@ __device__ __forceinline__ void epilogue_warps(const Params& p, uint32_t tmem_ba
     if (lane == 0) mbar_arrive(&acc_empty[tb]);
   }
   if (want_stats) {
-    if (REGSTATS) {        // one cross-row reduction per CTA (n_ntiles == 1: channel = 32 * half + lane)
+    if (REGSTATS && !(BN == 32 && half == 1)) {        // one cross-row reduction per CTA (n_ntiles == 1: channel = 32 * half + lane)
       float a[32], b[32];
 #pragma unroll
       for (int k = 0; k < 32; ++k) { a[k] = rs[k & (REGSTATS ? 31 : 0)]; b[k] = rq[k & (REGSTATS ? 31 : 0)]; }
@@ -641,6 +642,7 @@ static EncodeTiledFn encode_tiled() {
   return fn;
 }
 
+
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e == nullptr ? dflt : atoi(e);
@@ -649,9 +651,12 @@ static int env_int(const char* name, int dflt) {
 struct Plan {
   int RB, box_pos, nbox, b_stages;
   uint32_t region_bytes;
-  size_t smem;
+  size_t smem;            // streaming kernel (0: it does not fit)
+  size_t res_smem;        // weight-resident kernel (0: not applicable / does not fit)
 };
-static bool make_plan(int H, int W, int BN, int Npad, Plan& pl, int halo = -1) {
+// Geometry of the activation regions plus the shared-memory footprints of the two kernels. cpt / n_ntiles / ntaps decide whether the
+// weight-resident variant applies (one 64-channel chunk, one output tile, nine taps). False when neither kernel fits.
+static bool make_plan(int H, int W, int BN, int Npad, Plan& pl, int halo = -1, int cpt = 0, int n_ntiles = 0, int ntaps = 9, bool explicit_taps = false) {
   const int Wp = W + 1;
   if (halo < 0) halo = Wp + 1;
   // RB: rows per TMA box; must divide H + 1 so that a box never straddles two images. Largest divisor with <= 64 positions.
@@ -666,17 +671,28 @@ static bool make_plan(int H, int W, int BN, int Npad, Plan& pl, int halo = -1) {
   if (pl.nbox > MAX_BOX) return false;
   pl.region_bytes = (uint32_t)pl.nbox * pl.box_pos * 128u;
   pl.region_bytes = (pl.region_bytes + 1023u) & ~1023u;
-  const size_t fixed = 2 * (size_t)2 * pl.region_bytes + sizeof(uint64_t) * (8 + 2 * MAX_BST) + 16 + sizeof(float) * 7 * (size_t)Npad + 1024;
   const size_t budget = 227 * 1024;
-  if (fixed + 2 * (size_t)2 * BN * 128 > budget) return false;
-  int st = (int)((budget - fixed) / ((size_t)2 * BN * 128));
-  if (st > MAX_BST) st = MAX_BST;
-  pl.b_stages = st;
-  pl.smem = fixed + (size_t)st * 2 * BN * 128;
-  return true;
+  const size_t tail = sizeof(float) * 7 * (size_t)Npad + 1024;
+  // streaming kernel: two activation buffers (hi | lo each) + >= 2 weight stages; needs 64-column output tiles
+  pl.smem = 0; pl.b_stages = 0;
+  const size_t fixed = 2 * (size_t)2 * pl.region_bytes + sizeof(uint64_t) * (8 + 2 * MAX_BST) + 16 + tail;
+  if (BN >= 64 && fixed + 2 * (size_t)2 * BN * 128 <= budget) {
+    int st = (int)((budget - fixed) / ((size_t)2 * BN * 128));
+    if (st > MAX_BST) st = MAX_BST;
+    pl.b_stages = st;
+    pl.smem = fixed + (size_t)st * 2 * BN * 128;
+  }
+  // weight-resident kernel: one activation region + all nine taps' weights
+  pl.res_smem = 0;
+  if (env_int("PC_HALO_RESIDENT", 1) != 0 && ntaps == 9 && !explicit_taps && BN <= 64 && cpt == 1 && n_ntiles == 1) {
+    const size_t rs = 2 * (size_t)pl.region_bytes + 9 * (size_t)2 * BN * 128 + sizeof(uint64_t) * 10 + 16 + tail;
+    if (rs <= budget) pl.res_smem = rs;
+  }
+  return pl.smem != 0 || pl.res_smem != 0;
 }
 
-static inline int pick_bn(int Nn) { return Nn <= 64 ? 64 : 128; }
+// (32: layers with 32 produced channels, weight-resident kernel only -- their operand is packed with 32 rows per part, csrc/conv_tc.cu npad_of)
+static inline int pick_bn(int Nn) { return Nn <= 32 ? 32 : (Nn <= 64 ? 64 : 128); }
 
 // H, W: the image the POSITION space is built on (the output image of a forward pass, the dy image of a data gradient).
 // ntaps = 9: 3x3 stride-1 "same" convolution. ntaps = 1: 1x1 convolution (the residual shortcuts); a_stride = 2 samples every second
@@ -695,8 +711,9 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
   if (Ha == 0) { Ha = H; Wa = W; }
   if (Hout == 0) { Hout = H; Wout = W; }
   const int halo = (ntaps == 1 && taps == nullptr) ? 0 : W + 2;
+  const int cpt_ = ceil_div(Ca, 64);          // a 32-channel tensor is one chunk whose channels 32..63 the TMA unit zero-fills (box > tensor)
   Plan pl;
-  PC_REQUIRE(make_plan(H, W, BN, Npad, pl, halo), PC_EUNSUPPORTED, "conv_halo: image %dx%d does not fit the halo plan", H, W);
+  PC_REQUIRE(make_plan(H, W, BN, Npad, pl, halo, cpt_, Npad / BN, ntaps, taps != nullptr), PC_EUNSUPPORTED, "conv_halo: image %dx%d does not fit the halo plan", H, W);
   PC_REQUIRE(a_stride * (W + 1) <= 256 && a_stride * pl.RB <= 256, PC_EUNSUPPORTED, "conv_halo: strided box exceeds the TMA box limit");
   EncodeTiledFn enc = encode_tiled();
   PC_REQUIRE(enc != nullptr, PC_ECUDA, "conv_halo: cuTensorMapEncodeTiled is not available from this driver");
@@ -708,7 +725,7 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
   p.Q = (long long)B * p.Pimg;
   p.n_mtiles = ceil_div(p.Q, BM);
   p.n_ntiles = Npad / BN;
-  p.cpt = Ca / 64;
+  p.cpt = cpt_;
   p.accumulate = accumulate;
   int CL = env_int("PC_HALO_CLUSTER", 1);
   if (CL != 1 && CL != 2 && CL != 4) CL = 1;
@@ -740,30 +757,30 @@ static int run(const void* planes, const void* wp, const float* bias, const floa
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   PC_REQUIRE(cr == CUDA_SUCCESS, PC_ECUDA, "conv_halo: cuTensorMapEncodeTiled failed (CUresult %d)", (int)cr);
 
-  // weight-resident variant: one 64-channel chunk, one 64-channel output tile, and all nine taps' weights + one activation
+  // weight-resident variant: one 64-channel chunk, one output tile of <= 64 channels, and all nine taps' weights + one activation
   // region fit the 227 KB of shared memory
-  const size_t res_smem = 2 * (size_t)pl.region_bytes + 9 * (size_t)2 * BN * 128 + sizeof(uint64_t) * 10 + 16 + sizeof(float) * 7 * (size_t)Npad + 1024;
-  const bool resident = env_int("PC_HALO_RESIDENT", 1) != 0 && ntaps == 9 && taps == nullptr && BN == 64 && p.cpt == 1 && p.n_ntiles == 1 && res_smem <= 227 * 1024;
+  const size_t res_smem = pl.res_smem;
+  const bool resident = res_smem != 0;
+  PC_REQUIRE(resident || pl.smem != 0, PC_EUNSUPPORTED, "conv_halo: no kernel variant fits this layer");
+  PC_REQUIRE(BN != 32 || (resident && red == nullptr), PC_EUNSUPPORTED, "conv_halo: 32 produced channels run the weight-resident kernel only");
   if (resident) {
     p.cluster = CL = 1;
     p.n_items = p.n_mtiles;
     p.d_nt = FastDiv::make(1u);
     const int grid = p.n_items < kNumSMs ? p.n_items : kNumSMs;
-    if (red != nullptr) {
-      static size_t conf_r = 0;
-      if (res_smem > conf_r) {
-        PC_CUDA(cudaFuncSetAttribute((conv_halo_res_kernel<64, 2, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
-        conf_r = res_smem;
-      }
-      conv_halo_res_kernel<64, 2, 2, true><<<grid, THREADS, res_smem, stream>>>(amap, p);
-    } else {
-      static size_t conf = 0;
-      if (res_smem > conf) {
-        PC_CUDA(cudaFuncSetAttribute((conv_halo_res_kernel<64, 2, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem));
-        conf = res_smem;
-      }
-      conv_halo_res_kernel<64, 2, 2, false><<<grid, THREADS, res_smem, stream>>>(amap, p);
-    }
+#define PC_HALO_RES(BN_, RED_)                                                                                                        \
+  do {                                                                                                                                \
+    static size_t conf = 0;                                                                                                           \
+    if (res_smem > conf) {                                                                                                            \
+      PC_CUDA(cudaFuncSetAttribute((conv_halo_res_kernel<BN_, 2, 2, RED_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)res_smem)); \
+      conf = res_smem;                                                                                                                \
+    }                                                                                                                                 \
+    conv_halo_res_kernel<BN_, 2, 2, RED_><<<grid, THREADS, res_smem, stream>>>(amap, p);                                              \
+  } while (0)
+    if (BN == 32) PC_HALO_RES(32, false);
+    else if (red != nullptr) PC_HALO_RES(64, true);
+    else PC_HALO_RES(64, false);
+#undef PC_HALO_RES
     PC_LAUNCH_CHECK("conv_halo_res_kernel");
     return PC_OK;
   }
@@ -815,7 +832,13 @@ extern "C" int pc_conv_halo_supported(const PcConvGeom* g, int dgrad) {
   if (g == nullptr) return 0;
   if (!pc::halo::env_int("PC_CONV_HALO", 1)) return 0;
   const int ca = dgrad ? g->Cout : g->Cin, nn = dgrad ? g->Cin : g->Cout;
-  if (ca % 64 != 0 || nn % 64 != 0 || nn < 64) return 0;
+  // channel counts: multiples of 64 -- or exactly 32 for the stride-1 3x3 layers (cnn_small): 32 gathered channels are one 64-channel
+  // chunk whose upper half the TMA boxes zero-fill (box wider than the tensor), 32 produced channels run the weight-resident kernel with
+  // a 32-column tile
+  const bool strict = ca % 64 == 0 && nn % 64 == 0 && nn >= 64;
+  const bool relaxed = (ca % 64 == 0 || ca == 32) && (nn % 64 == 0 || nn == 32);
+  if (!relaxed) return 0;
+  if (!strict && !(g->R == 3 && g->S == 3 && g->stride == 1 && g->pad == 1 && pc::halo::env_int("PC_HALO_C32", 1))) return 0;
   if (g->R == 1 && g->S == 1 && g->pad == 0 && (g->stride == 1 || g->stride == 2)) {
     // 1x1 (shortcut) convolutions: position space = the (Ho x Wo) image; PC_HALO_1X1=0 keeps them on the per-tap-gather kernel
     if (!pc::halo::env_int("PC_HALO_1X1", 1)) return 0;
@@ -847,7 +870,9 @@ extern "C" int pc_conv_halo_supported(const PcConvGeom* g, int dgrad) {
   if (Q + 4096 >= (1LL << 31) || (long long)g->B * g->H * g->W * (ca > nn ? ca : nn) >= (1LL << 31)) return 0;
   pc::halo::Plan pl;
   const int bn = pc::halo::pick_bn(nn);
-  return pc::halo::make_plan(g->H, g->W, bn, ceil_div(nn, bn) * bn, pl) ? 1 : 0;
+  const int npad = ceil_div(nn, bn) * bn;
+  if (!pc::halo::make_plan(g->H, g->W, bn, npad, pl, -1, ceil_div(ca, 64), npad / bn)) return 0;
+  return (bn != 32 || pl.res_smem != 0) ? 1 : 0;
 }
 
 extern "C" int pc_conv_fwd_halo(const void* x_planes, const void* wp, const float* bias, const PcConvGeom* g, float* y, double* stats,

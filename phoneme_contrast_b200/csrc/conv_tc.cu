@@ -599,7 +599,7 @@ __device__ __forceinline__ void pack_b_item(const float* __restrict__ src, int O
   constexpr int BKC = P::BKC, PARTS = P::PARTS;
   constexpr int EPC = (PREC == PC_PREC_TF32X3) ? 4 : 8;
   (void)O;
-  const int cpt = Ca / BKC;
+  const int cpt = (Ca + BKC - 1) / BKC;      // the last chunk of a 32-channel layer on the FP16X2 halo engine is zero-padded to 64
   const int j = (int)(idx & 7);
   const int n = (int)((idx >> 3) % Npad);
   const int kc = (int)((idx >> 3) / Npad);
@@ -608,8 +608,8 @@ __device__ __forceinline__ void pack_b_item(const float* __restrict__ src, int O
 #pragma unroll
   for (int q = 0; q < EPC; ++q) {
     float x = 0.f;
-    if (n < Nn) {
-      const int c = c0 + q;
+    const int c = c0 + q;
+    if (n < Nn && c < Ca) {
       if (src_mode == 0) x = src[(((size_t)n * I + c) * R + tap / S) * S + tap % S];
       else if (src_mode == 1) x = src[(((size_t)c * I + n) * R + tap / S) * S + tap % S];
       else x = src[(size_t)n * ld + c];
@@ -645,7 +645,7 @@ __global__ void pack_b_kernel(const float* __restrict__ src, int O, int I, int R
   pdl_trigger();
   pdl_wait();
   const int taps = src_mode == 2 ? 1 : R * S;
-  const long long total = (long long)taps * (Ca / Prec<PREC>::BKC) * Npad * 8;
+  const long long total = (long long)taps * ((Ca + Prec<PREC>::BKC - 1) / Prec<PREC>::BKC) * Npad * 8;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
     pack_b_item<PREC>(src, O, I, R, S, src_mode, ld, Nn, Npad, Ca, out, idx);
 }
@@ -758,6 +758,8 @@ using namespace pc::tcconv;
 // Diagnostics: when set, every tensor-core tile writes 16 clock64() stamps (see PC_STAMP) to buf[tile][16].
 extern "C" void pc_tc_set_debug(long long* buf) { pc::tcconv::g_dbg = buf; }
 
+extern "C" int pc_conv_halo_supported(const PcConvGeom* g, int dgrad);
+
 extern "C" int pc_conv_tc_supported(const PcConvGeom* g, int dgrad, int prec) {
   if (g == nullptr || !tc_prec(prec)) return 0;
   const int ca = dgrad ? g->Cout : g->Cin, nn = dgrad ? g->Cin : g->Cout;
@@ -765,12 +767,16 @@ extern "C" int pc_conv_tc_supported(const PcConvGeom* g, int dgrad, int prec) {
   // the tap bitmask holds at most 32 taps
   const long long in_elems = (long long)g->B * g->H * g->W * g->Cin, out_elems = (long long)g->B * g->Ho * g->Wo * g->Cout;
   if (in_elems >= (1LL << 31) || out_elems >= (1LL << 31) || g->R * g->S > 32) return 0;
-  return (ca % bkc_of(prec) == 0 && nn % 4 == 0 && nn >= 16) ? 1 : 0;
+  if (nn % 4 != 0 || nn < 16) return 0;
+  if (ca % bkc_of(prec) == 0) return 1;
+  // 32 gathered channels on the FP16X2 engine: only through the halo engine, whose TMA boxes zero-fill channels 32..63 (the weight
+  // operand is packed with a zero-padded 64-channel chunk); the per-tap-gather kernel needs whole 64-channel chunks
+  return (prec == PC_PREC_FP16X2 && ca == 32 && pc_conv_halo_supported(g, dgrad)) ? 1 : 0;
 }
 
 extern "C" size_t pc_conv_tc_packed_bytes(int O, int I, int R, int S, int dgrad, int prec) {
   const int ca = dgrad ? O : I, nn = dgrad ? I : O;
-  return (size_t)R * S * (ca / bkc_of(prec)) * parts_of(prec) * npad_of(nn) * 128;
+  return (size_t)R * S * ceil_div(ca, bkc_of(prec)) * parts_of(prec) * npad_of(nn) * 128;
 }
 
 extern "C" int pc_pack_conv_weight_tc(const float* w_oihw, int O, int I, int R, int S, int dgrad, int prec, void* out,
@@ -778,9 +784,10 @@ extern "C" int pc_pack_conv_weight_tc(const float* w_oihw, int O, int I, int R, 
   PC_REQUIRE(w_oihw && out && O > 0 && I > 0 && R > 0 && S > 0, PC_EINVAL, "pc_pack_conv_weight_tc: bad arguments");
   PC_REQUIRE(tc_prec(prec), PC_EINVAL, "pc_pack_conv_weight_tc: precision must be TF32X3, FP16X2 or BF16");
   const int ca = dgrad ? O : I, nn = dgrad ? I : O;
-  PC_REQUIRE(ca % bkc_of(prec) == 0, PC_EUNSUPPORTED, "pc_pack_conv_weight_tc: %d channels not a multiple of %d", ca, bkc_of(prec));
+  PC_REQUIRE(ca % bkc_of(prec) == 0 || (prec == PC_PREC_FP16X2 && ca == 32), PC_EUNSUPPORTED, "pc_pack_conv_weight_tc: %d channels not a multiple of %d", ca,
+             bkc_of(prec));
   const int npad = npad_of(nn);
-  const long long total = (long long)R * S * (ca / bkc_of(prec)) * npad * 8;
+  const long long total = (long long)R * S * ceil_div(ca, bkc_of(prec)) * npad * 8;
   int grid = ceil_div(total, 256);
   if (grid > kNumSMs * 8) grid = kNumSMs * 8;
   launch_pack(prec, grid, stream, w_oihw, O, I, R, S, dgrad ? 1 : 0, 0, nn, npad, ca, out);
@@ -791,7 +798,7 @@ extern "C" int pc_pack_conv_weight_tc(const float* w_oihw, int O, int I, int R, 
 extern "C" int64_t pc_pack_conv_weight_tc_items(int O, int I, int R, int S, int dgrad, int prec) {
   if (!tc_prec(prec)) return 0;
   const int ca = dgrad ? O : I, nn = dgrad ? I : O;
-  return (int64_t)R * S * (ca / bkc_of(prec)) * npad_of(nn) * 8;
+  return (int64_t)R * S * ceil_div(ca, bkc_of(prec)) * npad_of(nn) * 8;
 }
 
 extern "C" int pc_pack_conv_weights_tc_batch(const PcPackJob* jobs, int n_jobs, int64_t total_items, pc_stream_t stream) {
@@ -815,6 +822,7 @@ extern "C" int pc_conv_fwd_tc(const float* x, const void* wp, const float* bias,
   if (prec == PC_PREC_FP16X2 && xf != nullptr && xf->presplit && !xf->scale && !xf->shift && !xf->drop && !xf->relu && g_dbg == nullptr &&
       pc_conv_halo_supported(g, 0))
     return pc_conv_fwd_halo(x, wp, bias, g, y, stats, stream);
+  PC_REQUIRE(g->Cin % bkc_of(prec) == 0, PC_EUNSUPPORTED, "pc_conv_fwd: %d input channels reach the FP16X2 engine only as pre-split planes on the halo path", g->Cin);
   Params p{};
   p.A = x; p.Bp = (const unsigned char*)wp; p.bias = bias; p.C = y; p.stats = stats;
   if (xf != nullptr) { p.xf.scale = xf->scale; p.xf.shift = xf->shift; p.xf.drop = xf->drop; p.xf.relu = xf->relu; }
@@ -838,6 +846,7 @@ extern "C" int pc_conv_dgrad_tc(const float* dy, const void* wp, const PcConvGeo
   if (prec == PC_PREC_FP16X2 && dy_presplit && dy_amax != nullptr && g_dbg == nullptr && pc_conv_halo_supported(g, 1) &&
       (g->R != 1 || g->stride == 1 || accumulate))      // a strided 1x1 data gradient only touches every second pixel: accumulate-only
     return pc_conv_dgrad_halo(dy, wp, g, dx, accumulate, dy_amax, stream);
+  PC_REQUIRE(g->Cout % bkc_of(prec) == 0, PC_EUNSUPPORTED, "pc_conv_dgrad: %d gradient channels reach the FP16X2 engine only as pre-split planes on the halo path", g->Cout);
   Params p{};
   p.A = dy; p.Bp = (const unsigned char*)wp; p.C = dx; p.a_amax = dy_amax;
   if (dy_presplit) {      // dy = fp16 hi | lo planes already scaled by f16_operand_scale(*dy_amax) (pc_bn_*_bwd_apply)

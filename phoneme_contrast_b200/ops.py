@@ -47,8 +47,13 @@ def pack_conv_weight(w: torch.Tensor, want_fwd=True, want_dgrad=True):
     return wf, wd
 
 
-def tc_supported(g: PcConvGeom, dgrad: bool, prec: int) -> bool:
-    return prec != L.PREC_FP32 and bool(L.lib().pc_conv_tc_supported(C.byref(g), 1 if dgrad else 0, prec))
+def tc_supported(g: PcConvGeom, dgrad: bool, prec: int, planes_ok: bool = False) -> bool:
+    """planes_ok: the gathered operand will be supplied as pre-split fp16 planes. Layers with 32 gathered channels reach the FP16X2
+    engine only that way (halo path: the TMA boxes zero-fill the missing half of the 64-channel chunk)."""
+    if prec == L.PREC_FP32 or not L.lib().pc_conv_tc_supported(C.byref(g), 1 if dgrad else 0, prec):
+        return False
+    ca = g.Cout if dgrad else g.Cin
+    return planes_ok or prec != L.PREC_FP16X2 or ca % 64 == 0
 
 
 def pack_conv_weight_tc(w: torch.Tensor, dgrad: bool, prec: int) -> torch.Tensor:
@@ -66,7 +71,9 @@ class ConvWeights:
     all layers are written by one batched launch at the start of the step instead of one launch per operand."""
     __slots__ = ("wf", "wd", "prec_f", "prec_d")
 
-    def __init__(self, w: torch.Tensor, g: PcConvGeom, prec: int, need_dgrad: bool = True, packer=None):
+    def __init__(self, w: torch.Tensor, g: PcConvGeom, prec: int, need_dgrad: bool = True, packer=None, planes_ok: bool = False):
+        """planes_ok: the caller supplies this layer's gathered operands as pre-split fp16 planes -- required for the layers that reach the
+        FP16X2 engine only through the halo path (32 gathered channels: the TMA boxes zero-fill the missing half of the 64-channel chunk)."""
         import os
         if packer is not None and packer.replaying:
             self.wf, self.wd, self.prec_f, self.prec_d = packer.next(w, need_dgrad)
@@ -77,7 +84,7 @@ class ConvWeights:
         def pick(dgrad):
             # FP16X2 needs 64-channel k-chunks; a layer with only 32-channel granularity runs the TF32x3 engine instead
             for cand in ((prec, L.PREC_TF32X3) if prec == L.PREC_FP16X2 else (prec,)):
-                if tc_supported(g, dgrad, cand):
+                if tc_supported(g, dgrad, cand, planes_ok):
                     return cand
             return L.PREC_FP32
         self.prec_f = pick(False) if (os.environ.get("PC_TC_FWD", "1") == "1" and tag not in skip.split(",")) else L.PREC_FP32

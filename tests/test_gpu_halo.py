@@ -309,3 +309,56 @@ def test_halo_dgrad_fused_bn_reduce(case, drop_on, monkeypatch):
     assert float((dy_a - dy_b).abs().max()) <= 2e-5 * sc
     torch.testing.assert_close(dg1, dg2, rtol=1e-4, atol=1e-5 * float(dg1.abs().max()))
     torch.testing.assert_close(db1, db2, rtol=1e-4, atol=1e-5 * float(db1.abs().max()))
+
+
+CASES_C32 = [  # B, H, W, Cin, Cout: the 32-channel layers of cnn_small (reference src/models/phoneme_cnn.py:36-60) and ragged variants
+    (2, 40, 101, 32, 32),
+    (3, 20, 50, 32, 64),
+    (5, 10, 25, 32, 32),
+    (1, 7, 9, 32, 64),
+]
+
+
+@pytest.mark.parametrize("case", CASES_C32)
+def test_halo_32_channel_layers(case, monkeypatch):
+    """32 gathered channels = one 64-channel chunk whose upper half the TMA boxes zero-fill (box wider than the tensor), 32 produced
+    channels = the weight-resident kernel with a 32-column tile: forward (+ bias, BatchNorm sums) and data gradient against fp64."""
+    from phoneme_contrast_b200 import _lib as L
+    from phoneme_contrast_b200 import ops
+    import ctypes as C
+    B, H, W, Cin, Cout = case
+    g = ops.conv_geom(B, H, W, Cin, Cout, 3, 1, 1)
+    gen = torch.Generator(device=DEV).manual_seed(B * 13 + Cin + 7 * Cout)
+    x = torch.randn(B, H, W, Cin, device=DEV, generator=gen)
+    w = torch.randn(Cout, Cin, 3, 3, device=DEV, generator=gen) * (2.0 / (Cin * 9)) ** 0.5
+    bias = torch.randn(Cout, device=DEV, generator=gen)
+    assert L.lib().pc_conv_halo_supported(C.byref(g), 0) == 1 and L.lib().pc_conv_halo_supported(C.byref(g), 1) == 1
+    cw = ops.ConvWeights(w, g, L.PREC_FP16X2, planes_ok=True)
+    assert cw.prec_f == L.PREC_FP16X2 and cw.prec_d == L.PREC_FP16X2
+    assert ops.ConvWeights(w, g, L.PREC_FP16X2).prec_f == L.PREC_TF32X3        # without planes the layer stays on the TF32x3 engine
+    planes = ops.bn_act_split(x)
+    st = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    y = ops.conv_fwd(planes, cw.wf, bias, g, dict(presplit=True), st, cw.prec_f)
+    ref = _ref_conv(x, w, bias)
+    scale = float(ref.abs().max())
+    assert float((y.double() - ref).abs().max()) <= 5e-6 * scale
+    np.testing.assert_allclose(st[0].cpu().numpy(), ref.sum(dim=(0, 1, 2)).cpu().numpy(), rtol=2e-5, atol=2e-4 * scale)
+    np.testing.assert_allclose(st[1].cpu().numpy(), (ref ** 2).sum(dim=(0, 1, 2)).cpu().numpy(), rtol=2e-5)
+    # data gradient
+    yconv = torch.randn(B, H, W, Cout, device=DEV, generator=gen)
+    dout = torch.randn(B, H, W, Cout, device=DEV, generator=gen) * 1e-6
+    bn = torch.nn.BatchNorm2d(Cout).to(DEV)
+    s2 = torch.zeros(2, Cout, device=DEV, dtype=torch.float64)
+    s2[0] = yconv.double().sum((0, 1, 2)); s2[1] = (yconv.double() ** 2).sum((0, 1, 2))
+    co = ops.bn_finalize(s2, B * H * W, bn, True)
+    a0, a1 = torch.zeros(1, device=DEV), torch.zeros(1, device=DEV)
+    dy, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a0)
+    dy_ps, _, _ = ops.bn_act_bwd(dout, yconv, co, 0, None, None, amax=a1, planes=True)
+    dx = ops.conv_dgrad(dy_ps, cw.wd, g, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+    refd = torch.nn.functional.conv_transpose2d(dy.permute(0, 3, 1, 2).double(), w.double(), padding=1).permute(0, 2, 3, 1)
+    sd = float(refd.abs().max())
+    assert float((dx.double() - refd).abs().max()) <= 1e-5 * sd
+    base = torch.randn(B, H, W, Cin, device=DEV, generator=gen) * sd
+    acc = base.clone()
+    ops.conv_dgrad(dy_ps, cw.wd, g, out=acc, accumulate=True, prec=cw.prec_d, dy_amax=a1, dy_presplit=True)
+    assert float((acc.double() - (base.double() + refd)).abs().max()) <= 1e-5 * sd + 1e-6 * float(base.abs().max())
