@@ -244,7 +244,8 @@ __global__ void __launch_bounds__(192 * 4) wgrad_halo_reduce_kernel(const float*
   }
   __syncthreads();
   const int j = ty * 192 + n;
-  if (j < 576) {
+  const int c_here = min(64, Cin - cc * 64);       // channels of this chunk that exist (32 for the 32-channel layers)
+  if (j < 9 * c_here) {
     const int c = j / 9, tap = j - 9 * c, r = tap / 3, sc = tap - 3 * r;
     const int nn = sc * 64 + c;
     dw[((size_t)o * Cin + cc * 64) * 9 + j] = (float)(((sh[0][r][nn] + sh[1][r][nn]) + sh[2][r][nn]) + sh[3][r][nn]);
@@ -296,7 +297,7 @@ static void size_plan(const PcConvGeom* g, Plan& pl) {
 static bool make_plan(const PcConvGeom* g, Plan& pl) {
   const int H = g->H, Wp = g->W + 1;
   if (Wp > 256) return false;
-  pl.pair = g->Cout == 64 ? 1 : 0;
+  pl.pair = g->Cout <= 64 ? 1 : 0;          // (32 output channels: the dy boxes zero-fill channels 32..63, the reduce only reads rows o < Cout)
   // A tile = n_box TMA boxes of NB images x RB padded rows; RB divides H + 1 (a box never straddles two images), several images per
   // box only for whole-image boxes (and not in pair mode, whose extra row per box assumes one image). Among the shapes that fit the
   // shared memory pick the one that wastes the fewest k-step rows (tile positions are rounded up to 16), then the largest tile.
@@ -323,7 +324,7 @@ static bool make_plan(const PcConvGeom* g, Plan& pl) {
   if (!found) return false;
   const long long boxes_total = pl.NB > 1 ? (long long)(g->B / pl.NB) : (long long)g->B * ((H + 1) / pl.RB);
   pl.n_tiles = (int)((boxes_total + pl.n_box - 1) / pl.n_box);
-  pl.n_cc = g->Cin / 64;
+  pl.n_cc = (g->Cin + 63) / 64;            // (32 input channels: one chunk whose upper half the x boxes zero-fill)
   pl.n_ot = pl.pair ? 1 : g->Cout / 128;
   pl.n_units = pl.pair ? 2 * pl.n_cc : pl.n_ot * pl.n_cc * 3;
   // splits: fill the 148 SMs in (nearly) whole waves with at least ~4 tiles per CTA
@@ -348,11 +349,11 @@ static bool make_plan(const PcConvGeom* g, Plan& pl) {
 using namespace pc;
 
 // 1 when the halo weight-gradient engine covers this convolution: stride-1 3x3 pad-1, FP16X2 planes on both operands, input channels
-// a multiple of 64, output channels 64 or a multiple of 128. PC_WGRAD_HALO=0 disables it.
+// a multiple of 64 (or 32), output channels 64 (or 32) or a multiple of 128. PC_WGRAD_HALO=0 disables it.
 extern "C" int pc_conv_wgrad_halo_supported(const PcConvGeom* g) {
   if (g == nullptr || !pc::halowg::env_int("PC_WGRAD_HALO", 1)) return 0;
   if (g->R != 3 || g->S != 3 || g->stride != 1 || g->pad != 1 || g->Ho != g->H || g->Wo != g->W) return 0;
-  if (g->Cin % 64 != 0 || !(g->Cout == 64 || g->Cout % 128 == 0)) return 0;
+  if (!(g->Cin % 64 == 0 || g->Cin == 32) || !(g->Cout == 64 || g->Cout == 32 || g->Cout % 128 == 0)) return 0;
   const long long Q = (long long)g->B * (g->H + 1) * (g->W + 1);
   const int cmax = g->Cin > g->Cout ? g->Cin : g->Cout;
   if (Q + 4096 >= (1LL << 31) || (long long)g->B * g->H * g->W * cmax >= (1LL << 31)) return 0;

@@ -232,6 +232,15 @@ def _head_bwd(net, s, demb, grads, training):
     return da
 
 
+def _halo_everything(g) -> bool:
+    """Forward, data gradient AND weight gradient of this layer are on the halo engine. The 32-channel layers have no other FP16X2 kernel
+    (the per-tap-gather kernels need whole 64-channel chunks), so they take the plane route only when all three passes are covered."""
+    import ctypes
+    lib = L.lib()
+    return bool(lib.pc_conv_halo_supported(ctypes.byref(g), 0)) and bool(lib.pc_conv_halo_supported(ctypes.byref(g), 1)) and \
+        bool(lib.pc_conv_wgrad_halo_supported(ctypes.byref(g)))
+
+
 def _small_forward(net, x, training):
     s = _Saved()
     packer = _packer_begin(net, x, training)
@@ -250,6 +259,11 @@ def _small_forward(net, x, training):
     cur, cin, h, w = x, 1, H, W
     cur_ps = None            # `cur` once more as fp16 hi | lo planes, when the next convolution runs the FP16X2 plane engine
     use_planes = prec == L.PREC_FP16X2 and os.environ.get("PC_SMALL_PLANES", "1") == "1"
+    # the 32-channel layers too (PC_SMALL_C32=0: TF32x3 per-tap kernel as before): their planes are [pixels][32] and the halo engine's TMA
+    # boxes zero-fill the other half of the 64-channel chunk
+    # (not under synchronised BatchNorm statistics: their weight-gradient calls also produce the bias gradients, which the halo
+    # weight-gradient kernel does not)
+    cmin = 32 if (os.environ.get("PC_SMALL_C32", "1") == "1" and sb is None) else 64
     for b in range(3):
         convA, bnA, convB, bnB = blocks[b][0], blocks[b][1], blocks[b][3], blocks[b][4]
         co = chans[b]
@@ -258,7 +272,7 @@ def _small_forward(net, x, training):
             cwA = None                             # stem kernel reads OIHW directly; no dgrad into the input
             wfA, precA = convA.weight, L.PREC_FP32
         else:
-            cwA = ops.ConvWeights(convA.weight, gA, prec, packer=packer)
+            cwA = ops.ConvWeights(convA.weight, gA, prec, packer=packer, planes_ok=cur_ps is not None)
             wfA, precA = cwA.wf, cwA.prec_f
         stA = slots.take(co)
         # 64- / 128-channel layers run the plane engine of cnn_deep (halo-resident forward / data gradient / weight gradient): their
@@ -266,9 +280,10 @@ def _small_forward(net, x, training):
         psA = cur_ps is not None and cwA is not None and cwA.prec_f == L.PREC_FP16X2 and cwA.prec_d == L.PREC_FP16X2
         yA = ops.conv_fwd(cur_ps if psA else cur, wfA, convA.bias, gA, dict(presplit=True) if psA else None, stA, precA)
         gB = ops.conv_geom(B, h, w, co, co, 3, 1, 1)
-        cwB = ops.ConvWeights(convB.weight, gB, prec, packer=packer)
+        planesB = use_planes and co % cmin == 0 and (co % 64 == 0 or _halo_everything(gB))
+        cwB = ops.ConvWeights(convB.weight, gB, prec, packer=packer, planes_ok=planesB)
         stB = slots.take(co)
-        psB = use_planes and co % 64 == 0 and cwB.prec_f == L.PREC_FP16X2 and cwB.prec_d == L.PREC_FP16X2
+        psB = planesB and cwB.prec_f == L.PREC_FP16X2 and cwB.prec_d == L.PREC_FP16X2
         fuse_fin = psB and training and os.environ.get("PC_BN_FIN_FUSE", "1") == "1"      # finalise bnA inside the split kernel
         _sync_stats(sb, stA)
         coA = None if fuse_fin else ops.bn_finalize(stA, cm * B * gA.Ho * gA.Wo, bnA, training)
@@ -285,7 +300,10 @@ def _small_forward(net, x, training):
         coB = ops.bn_finalize(stB, cm * B * h * w, bnB, training)
         _local_only(sb, coA, coB)
         pool = 2 if b < 2 else 0
-        next_ps = use_planes and b < 2 and co % 64 == 0      # the next block's first convolution gathers co channels
+        next_ps = use_planes and b < 2 and co % cmin == 0    # the next block's first convolution gathers co channels
+        if next_ps and co % 64 != 0:
+            hn, wn = ops.pool_dims(h, w, pool)
+            next_ps = _halo_everything(ops.conv_geom(B, hn, wn, co, chans[b + 1], 3, 1, 1))
         if next_ps:
             out, _, out_ps = ops.bn_act_fwd(yB, coB, pool, s.drop[b], want_planes=True)
         else:
