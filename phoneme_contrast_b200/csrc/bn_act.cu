@@ -5,6 +5,8 @@
 //
 // Reference modules: nn.BatchNorm2d / ReLU / MaxPool2d / Dropout2d as composed in
 // src/models/phoneme_cnn.py:36-63 (PhonemeNet blocks), :211-216 (init_conv), :173-184 (ResidualBlock).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -726,7 +728,8 @@ static inline dim3 reduce_grid2(long long n_pix, int C) {
   const int c4t = c4 / tiles;
   const int ppb = 256 / c4t;
   long long gx = (n_pix + (long long)ppb * 4 - 1) / ((long long)ppb * 4);
-  const long long cap = (long long)kNumSMs * 4 / tiles;
+  static const int bps = [] { const char* e = getenv("PC_BN_REDUCE_BPS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
+  const long long cap = (long long)kNumSMs * bps / tiles;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)tiles);
