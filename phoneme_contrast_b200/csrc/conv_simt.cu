@@ -8,6 +8,8 @@
 // Fusions: (1) the previous BatchNorm-apply + ReLU + Dropout2d multiplier is applied while the input
 // tile is gathered (PcInXform), so that activation never round-trips HBM; (2) the epilogue adds the
 // bias and accumulates the per-channel sum / sum-of-squares the next train-mode BatchNorm needs.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace pc {
@@ -791,7 +793,11 @@ extern "C" int pc_conv_wgrad(const float* x, const float* dy, const PcConvGeom* 
   // tensor-core path (TF32x3) for eligible layers whenever a tensor-core precision is requested
   if (prec != PC_PREC_FP32 && g->Cin != 1 && pc_conv_wgrad_tc_supported(g))
     return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, dy_presplit, stream);
-  if (prec == PC_PREC_FP16X2 && xf == nullptr && pc_conv_wgrad_tc_stem_supported(g))   // single-channel stem on the tensor cores
+  // single-channel stem on the tensor cores (taps as M rows: built for the 49 taps of cnn_deep's 7x7 stem; with the 9 taps of cnn_small's
+  // 3x3 stem most of the 128-row tile is padding -- 59 us against the direct kernel below, so 3x3 stems stay on that one unless
+  // PC_WGRAD_TC_STEM3=1)
+  static const bool stem3_tc = [] { const char* e = getenv("PC_WGRAD_TC_STEM3"); return e != nullptr && e[0] == '1'; }();
+  if (prec == PC_PREC_FP16X2 && xf == nullptr && pc_conv_wgrad_tc_stem_supported(g) && (g->R > 3 || stem3_tc))
     return pc_conv_wgrad_tc(x, dy, g, xf, dw_oihw, db, workspace, workspace_bytes, prec, dy_amax, 0, stream);
   PC_REQUIRE(!dy_presplit, PC_EUNSUPPORTED, "pc_conv_wgrad: pre-split dy needs the FP16X2 tensor-core path");
   PC_REQUIRE(xf == nullptr || !xf->presplit, PC_EUNSUPPORTED, "pc_conv_wgrad: pre-split input planes need the FP16X2 tensor-core path");
