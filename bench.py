@@ -68,6 +68,31 @@ except Exception:
     pass
 
 
+def ncu_traffic(md_name, kernel_substrings, per="launch"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the kernels whose section title contains one of the substrings, from an
+    `ncu --set full` summary under profiles/: the mean over the launches of each kernel, summed over the kernels (per step of one launch
+    each), or None when the file is absent."""
+    try:
+        import re
+        txt = open(os.path.join(ROOT, "profiles", md_name)).read()
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = 0.0
+        for sub in kernel_substrings:
+            vals = []
+            for sec in txt.split("## ")[1:]:
+                if sub in sec.splitlines()[0]:
+                    r = re.search(r"dram__bytes_read.sum \| ([0-9.]+) \| (\w+)", sec)
+                    w = re.search(r"dram__bytes_write.sum \| ([0-9.]+) \| (\w+)", sec)
+                    if r and w:
+                        vals.append(float(r.group(1)) * unit.get(r.group(2), 1.0) + float(w.group(1)) * unit.get(w.group(2), 1.0))
+            if not vals:
+                return None
+            total += sum(vals) / len(vals)
+        return total
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -770,7 +795,9 @@ def main():
         r = bench_supcon(args.steps, args.warmup, parallel, device)
         line = {"metric": "supcon_fwd_bwd_views_per_sec", "value": r["value"], "unit": "views/s", "ms_per_step": r["ms_per_step"], "dtype": "f32",
                 "roofline": {"bound": "tensor", "kernel": "sctc::supcon_bwd_tc_kernel (+ supcon_fwd_tc_kernel)", "achieved": r["tflops"], "peak": pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
-                             "unit": "TFLOP/s", "frac": r["tflops"] / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]), "traffic": None,
+                             "unit": "TFLOP/s", "frac": r["tflops"] / pk.get("bf16_tflops_sustained", pk["bf16_tflops"]),
+                             "traffic": ncu_traffic("r3_supcon_full.md", ("supcon_fwd_tc_kernel", "supcon_bwd_tc_kernel")),
+                             "traffic_note": "dram read+write bytes of one forward + one backward launch at N = 8192 on one GPU (profiles/r3_supcon_full.md): F is read once per kernel (4.2 MB), the N x N logits never reach HBM",
                              "note": "per-rank algorithmic FLOPs 8*N^2*D/R (forward S, backward S recompute, dF = W F counted twice as in SURVEY 8d's 6N^2D + recompute) / step time; tcgen05 kernels with the FP16x2 operand split (3 fp16 products per pair: own ceiling = peak/3)"},
                 "e2e": {"value": r["e2e_value"], "unit": "views/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
                 "gpu_launches": int(round(r["launches"] * args.steps)),
@@ -780,7 +807,9 @@ def main():
         r = bench_frontend(args.steps, args.warmup, device)
         line = {"metric": "mfcc_frontend_clips_per_sec", "value": r["value"], "unit": "clips/s", "ms_per_step": r["ms_per_step"], "dtype": "f32",
                 "roofline": {"bound": "hbm", "kernel": "frontend_kernel", "achieved": r["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s",
-                             "frac": r["gbs"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk_kind},
+                             "frac": r["gbs"] / pk["hbm_gbs"], "traffic": ncu_traffic("r2f_frontend_full.md", ("frontend_kernel",)),
+                             "traffic_note": "dram read+write bytes of one launch over 65 536 clips x 2 views (profiles/r2f_frontend_full.md): 6.29 GB against 6.31 GB algorithmic",
+                             "peak_source": pk_kind},
                 "e2e": {"value": r["e2e_value"], "unit": "clips/s", "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"], "sample": r["e2e_sample"]},
                 "gpu_launches": r["launches"] * args.steps, "config": {"workload": wl["desc"], "l2": "4.19 GB in / 2.1 GB out per step, far larger than the 126 MB L2"}}
         clocks = None
@@ -820,7 +849,8 @@ def main():
             if args.workload != "frontend":
                 f = bench_frontend(3, 3, device)
                 fe = {"value": f["value"], "unit": "clips/s", "ms_per_step": f["ms_per_step"], "workload": WORKLOADS["frontend"]["desc"],
-                      "roofline": {"bound": "hbm", "kernel": "frontend_kernel", "achieved": f["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": f["gbs"] / pk["hbm_gbs"]},
+                      "roofline": {"bound": "hbm", "kernel": "frontend_kernel", "achieved": f["gbs"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": f["gbs"] / pk["hbm_gbs"],
+                                   "traffic": ncu_traffic("r2f_frontend_full.md", ("frontend_kernel",))},
                       "e2e": {"value": f["e2e_value"], "unit": "clips/s", "sample": f["e2e_sample"]}}
                 if kind:
                     pc, bt, th = cpu_frontend(512)
