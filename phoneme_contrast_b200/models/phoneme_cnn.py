@@ -370,11 +370,14 @@ def _deep_forward(net, x, training, for_backward=True):
         net._side_stream.wait_stream(torch.cuda.current_stream())      # the optimiser's parameter update ran on the main stream
         with torch.cuda.stream(net._side_stream):
             packer = _packer_begin(net, x, training)
+            # the Dropout2d masks (counter + one small launch per block) are first needed by block 0, like the packed operands
+            drop_early = _drop_masks(net, x.shape[0], list(net.hidden_dims), training)
         pack_side = packer.replaying          # a recording forward packs layer by layer on the main stream
         if not pack_side:
             torch.cuda.current_stream().wait_stream(net._side_stream)
     else:
         packer = _packer_begin(net, x, training)
+        drop_early = None
     prec = net._prec
     B, _, H, W = x.shape
     s.x = x
@@ -384,7 +387,7 @@ def _deep_forward(net, x, training, for_backward=True):
         sb.begin_step()
     hd = net.hidden_dims
     conv0, bn0 = net.init_conv[0], net.init_conv[1]
-    s.drop = _drop_masks(net, B, list(hd), training)
+    s.drop = drop_early if drop_early is not None else _drop_masks(net, B, list(hd), training)
     slots = _StatSlots([hd[0]] + [c for c in hd for _ in range(3)], x.device, training)
     st = slots.take
 
