@@ -383,8 +383,8 @@ __device__ __forceinline__ void block_channel_reduce(float (&acc)[NV][4], int C4
   }
 }
 
-template <int POOL>
-__global__ void __launch_bounds__(256, 4)
+template <int POOL, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 bn_act_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ y, int B, int H, int W, int C, int Ho,
                          int Wo, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, const float* __restrict__ drop,
@@ -554,7 +554,8 @@ bn_add_relu_fwd_kernel(const float* __restrict__ y2, const float* __restrict__ s
   }
 }
 
-__global__ void __launch_bounds__(256, 4)      // 4 blocks per SM = the grid's cap (reduce_grid2): at 66 registers only 3 fitted and the grid ran 1.33 waves
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB)   // MINB blocks per SM = the grid's cap (reduce_grid2): the grid must be whole waves of what fits
 bn_add_relu_bwd_reduce_kernel(const float* __restrict__ dout, const float* __restrict__ out, const float* __restrict__ y2,
                               const float* __restrict__ mean2, const float* __restrict__ invstd2,
                               const float* __restrict__ ysc, const float* __restrict__ mean_s,
@@ -792,14 +793,17 @@ static inline int reduce_grid(long long work_items, int per_block) {
 }
 // 2-D grid of a reduction pass: y = channel tiles of 64 channels (each block then ends with 64 atomics per sum instead of C),
 // x * y capped at 4 blocks per SM
+static inline int reduce_bps() {
+  static const int bps = [] { const char* e = getenv("PC_BN_REDUCE_BPS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
+  return bps;
+}
 static inline dim3 reduce_grid2(long long n_pix, int C) {
   const int c4 = C / 4;
   const int tiles = (c4 % 16 == 0) ? c4 / 16 : 1;
   const int c4t = c4 / tiles;
   const int ppb = 256 / c4t;
   long long gx = (n_pix + (long long)ppb * 4 - 1) / ((long long)ppb * 4);
-  static const int bps = [] { const char* e = getenv("PC_BN_REDUCE_BPS"); const int v = e ? atoi(e) : 4; return v >= 1 && v <= 4 ? v : 4; }();
-  const long long cap = (long long)kNumSMs * bps / tiles;
+  const long long cap = (long long)kNumSMs * reduce_bps() / tiles;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
   return dim3((unsigned)gx, (unsigned)tiles);
@@ -902,9 +906,9 @@ extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, in
   PC_REQUIRE((long long)B * H * W < (1LL << 31), PC_EUNSUPPORTED, "pc_bn_act_bwd_reduce: too many pixels");
   (void)items;
   const dim3 grid = reduce_grid2((long long)B * H * W, C);
-  if (pool == 0) launch_pdl((bn_act_bwd_reduce_kernel<0>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes);
-  else if (pool == 2) launch_pdl((bn_act_bwd_reduce_kernel<2>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes);
-  else launch_pdl((bn_act_bwd_reduce_kernel<3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes);
+  if (pool == 0) { if (reduce_bps() == 3) launch_pdl((bn_act_bwd_reduce_kernel<0, 3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes); else launch_pdl((bn_act_bwd_reduce_kernel<0, 4>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes); }
+  else if (pool == 2) { if (reduce_bps() == 3) launch_pdl((bn_act_bwd_reduce_kernel<2, 3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes); else launch_pdl((bn_act_bwd_reduce_kernel<2, 4>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes); }
+  else { if (reduce_bps() == 3) launch_pdl((bn_act_bwd_reduce_kernel<3, 3>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes); else launch_pdl((bn_act_bwd_reduce_kernel<3, 4>), dim3(grid), dim3(256), 0, stream, dout, y, B, H, W, C, Ho, Wo, scale, shift, mean, invstd, drop, argmax, sums, maxes); }
   PC_LAUNCH_CHECK("bn_act_bwd_reduce_kernel");
   return PC_OK;
 }
@@ -968,7 +972,8 @@ extern "C" int pc_bn_add_relu_bwd_reduce(const float* dout, const float* out, co
   PC_REQUIRE(dout && out && y2 && mean2 && invstd2 && sums2 && n_pix > 0, PC_EINVAL, "pc_bn_add_relu_bwd_reduce: bad arguments");
   PC_REQUIRE(sums_s == nullptr || (ysc && mean_s && invstd_s), PC_EINVAL, "pc_bn_add_relu_bwd_reduce: shortcut pointers");
   PC_CHECK_C4("pc_bn_add_relu_bwd_reduce", C);
-  launch_pdl(bn_add_relu_bwd_reduce_kernel, reduce_grid2(n_pix, C), dim3(256), 0, stream, dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s, maxes);
+  if (reduce_bps() == 3) launch_pdl(bn_add_relu_bwd_reduce_kernel<3>, reduce_grid2(n_pix, C), dim3(256), 0, stream, dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s, maxes);
+  else launch_pdl(bn_add_relu_bwd_reduce_kernel<4>, reduce_grid2(n_pix, C), dim3(256), 0, stream, dout, out, y2, mean2, invstd2, ysc, mean_s, invstd_s, n_pix, C, sums2, sums_s, maxes);
   PC_LAUNCH_CHECK("bn_add_relu_bwd_reduce_kernel");
   return PC_OK;
 }
