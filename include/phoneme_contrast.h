@@ -357,6 +357,12 @@ int pc_bn_add_relu_bwd_apply(const float* dout, const float* out, const float* y
  * (phoneme_cnn.py:134-143,117-118). w == NULL: plain mean (use_attention False). gate [B,HW] saved for backward. */
 int pc_attn_pool_fwd(const float* a, int B, int HW, int C, const float* w, const float* b0, float* gate,
                      float* pooled, pc_stream_t stream);
+/* The same with a workspace that lets S = pc_attn_pool_splits(B) blocks share one sample's pixels (small batches leave SMs idle with
+ * one block per sample): scratch >= B * S * C floats; counters >= B unsigned ints, ZERO before the first call (the kernel leaves them
+ * zero). The S partial sums are combined in a fixed order by the block that finishes last, so the result is deterministic. */
+int pc_attn_pool_splits(int B);
+int pc_attn_pool_fwd_ws(const float* a, int B, int HW, int C, const float* w, const float* b0, float* gate, float* pooled,
+                        float* scratch, unsigned int* counters, pc_stream_t stream);
 int pc_attn_pool_bwd(const float* a, const float* gate, const float* dpooled, int B, int HW, int C, const float* w,
                      float* da, float* dw, float* db0, pc_stream_t stream);
 

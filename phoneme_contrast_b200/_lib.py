@@ -114,6 +114,8 @@ SIGNATURES = {
     "pc_bn_add_relu_bwd_reduce": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp]),
     "pc_bn_add_relu_bwd_apply": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pc_attn_pool_fwd": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp]),
+    "pc_attn_pool_splits": (i32, [i32]),
+    "pc_attn_pool_fwd_ws": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
     "pc_attn_pool_bwd": (i32, [vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "pc_head_workspace": (sz, [i32, i32, i32]),
     "pc_head_fwd": (i32, [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, i32, vp, vp, vp]),

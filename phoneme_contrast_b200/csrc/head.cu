@@ -90,10 +90,12 @@ attn_pool_bwd_kernel(const float* __restrict__ a, const float* __restrict__ gate
 template <int NV>
 __global__ void __launch_bounds__(256)
 attn_pool_fwd1_kernel(const float* __restrict__ a, int HW, const float* __restrict__ w, const float* __restrict__ b0, float* __restrict__ gate,
-                      float* __restrict__ pooled) {
+                      float* __restrict__ pooled, float* __restrict__ scratch, unsigned int* __restrict__ counters) {
   constexpr int C = 128 * NV;
   __shared__ float4 part[8][32 * NV];
+  __shared__ unsigned int s_ticket;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int S = gridDim.y, sy = blockIdx.y;          // S blocks share a sample's pixels (few samples: cnn_small's 64 would leave 84 SMs idle)
   const float4* ab = reinterpret_cast<const float4*>(a + (size_t)b * HW * C);
   float* gb = gate + (size_t)b * HW;
   float4 wv[NV], acc[NV];
@@ -103,7 +105,7 @@ attn_pool_fwd1_kernel(const float* __restrict__ a, int HW, const float* __restri
     acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float bias = (w != nullptr && b0 != nullptr) ? b0[0] : 0.f;
-  for (int p = warp; p < HW; p += 8) {
+  for (int p = warp + 8 * sy; p < HW; p += 8 * S) {
     float4 v[NV];
 #pragma unroll
     for (int j = 0; j < NV; ++j) v[j] = ab[(size_t)p * (C / 4) + lane + 32 * j];
@@ -126,12 +128,29 @@ attn_pool_fwd1_kernel(const float* __restrict__ a, int HW, const float* __restri
   for (int j = 0; j < NV; ++j) part[warp][lane + 32 * j] = acc[j];
   __syncthreads();
   const float inv = 1.0f / (float)HW;
+  float4* mine = reinterpret_cast<float4*>(scratch) + ((size_t)b * S + sy) * (C / 4);
   for (int i = tid; i < 32 * NV; i += 256) {
     float4 s = part[0][i];
 #pragma unroll
     for (int k = 1; k < 8; ++k) { const float4 q = part[k][i]; s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w; }
+    if (S == 1) reinterpret_cast<float4*>(pooled + (size_t)b * C)[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
+    else mine[i] = s;
+  }
+  if (S == 1) return;
+  // the block that arrives last for this sample adds the S partial sums in a FIXED order (the result does not depend on scheduling)
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_ticket = atomicAdd(&counters[b], 1u);
+  __syncthreads();
+  if (s_ticket != (unsigned)(S - 1)) return;
+  __threadfence();
+  const float4* all = reinterpret_cast<const float4*>(scratch) + (size_t)b * S * (C / 4);
+  for (int i = tid; i < 32 * NV; i += 256) {
+    float4 s = __ldcg(all + i);
+    for (int k = 1; k < S; ++k) { const float4 q = __ldcg(all + (size_t)k * (C / 4) + i); s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w; }
     reinterpret_cast<float4*>(pooled + (size_t)b * C)[i] = make_float4(s.x * inv, s.y * inv, s.z * inv, s.w * inv);
   }
+  if (tid == 0) counters[b] = 0u;                    // ready for the next launch (the counters start zeroed and stay so between launches)
 }
 
 template <int NV>
@@ -155,7 +174,7 @@ attn_pool_bwd1_kernel(const float* __restrict__ a, const float* __restrict__ gat
     dwacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   float dbacc = 0.f;
-  for (int p = warp; p < HW; p += 8) {
+  for (int p = warp + 8 * (int)blockIdx.y; p < HW; p += 8 * (int)gridDim.y) {
     if (w == nullptr) {
 #pragma unroll
       for (int j = 0; j < NV; ++j) dab[(size_t)p * (C / 4) + lane + 32 * j] = gp[j];
@@ -482,20 +501,40 @@ static bool attn_single_pass() {
   return on;
 }
 
-extern "C" int pc_attn_pool_fwd(const float* a, int B, int HW, int C, const float* w, const float* b0, float* gate,
-                                float* pooled, pc_stream_t stream) {
+// scratch: >= B * S * C floats, counters: >= B zeroed unsigned ints (reset by the kernel), S = pc_attn_pool_splits(B): how many blocks share
+// one sample's pixels. Both may be NULL (one block per sample).
+extern "C" int pc_attn_pool_splits(int B) {
+  if (!attn_single_pass()) return 1;
+  int s = (2 * kNumSMs) / (B > 0 ? B : 1);
+  return s < 1 ? 1 : (s > 4 ? 4 : s);
+}
+
+static int attn_pool_fwd_impl(const float* a, int B, int HW, int C, const float* w, const float* b0, float* gate, float* pooled, float* scratch,
+                              unsigned int* counters, pc_stream_t stream) {
   PC_REQUIRE(a && gate && pooled && B > 0 && HW > 0 && C > 0, PC_EINVAL, "pc_attn_pool_fwd: bad arguments");
-  const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(pooled)) & 15) == 0;
+  const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(pooled) | reinterpret_cast<uintptr_t>(scratch)) & 15) == 0;
   if (al && attn_single_pass() && (C == 128 || C == 256 || C == 512)) {
-    if (C == 128) attn_pool_fwd1_kernel<1><<<B, 256, 0, stream>>>(a, HW, w, b0, gate, pooled);
-    else if (C == 256) attn_pool_fwd1_kernel<2><<<B, 256, 0, stream>>>(a, HW, w, b0, gate, pooled);
-    else attn_pool_fwd1_kernel<4><<<B, 256, 0, stream>>>(a, HW, w, b0, gate, pooled);
+    const int S = (scratch != nullptr && counters != nullptr) ? pc_attn_pool_splits(B) : 1;
+    const dim3 grid((unsigned)B, (unsigned)S);
+    if (C == 128) attn_pool_fwd1_kernel<1><<<grid, 256, 0, stream>>>(a, HW, w, b0, gate, pooled, scratch, counters);
+    else if (C == 256) attn_pool_fwd1_kernel<2><<<grid, 256, 0, stream>>>(a, HW, w, b0, gate, pooled, scratch, counters);
+    else attn_pool_fwd1_kernel<4><<<grid, 256, 0, stream>>>(a, HW, w, b0, gate, pooled, scratch, counters);
     PC_LAUNCH_CHECK("attn_pool_fwd1_kernel");
     return PC_OK;
   }
   attn_pool_fwd_kernel<<<B, 256, 0, stream>>>(a, HW, C, w, b0, gate, pooled);
   PC_LAUNCH_CHECK("attn_pool_fwd_kernel");
   return PC_OK;
+}
+
+extern "C" int pc_attn_pool_fwd(const float* a, int B, int HW, int C, const float* w, const float* b0, float* gate,
+                                float* pooled, pc_stream_t stream) {
+  return attn_pool_fwd_impl(a, B, HW, C, w, b0, gate, pooled, nullptr, nullptr, stream);
+}
+
+extern "C" int pc_attn_pool_fwd_ws(const float* a, int B, int HW, int C, const float* w, const float* b0, float* gate, float* pooled,
+                                   float* scratch, unsigned int* counters, pc_stream_t stream) {
+  return attn_pool_fwd_impl(a, B, HW, C, w, b0, gate, pooled, scratch, counters, stream);
 }
 
 extern "C" int pc_attn_pool_bwd(const float* a, const float* gate, const float* dpooled, int B, int HW, int C, const float* w,
@@ -509,9 +548,10 @@ extern "C" int pc_attn_pool_bwd(const float* a, const float* gate, const float* 
   }
   const bool al = ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(dpooled) | reinterpret_cast<uintptr_t>(da)) & 15) == 0;
   if (al && attn_single_pass() && (C == 128 || C == 256 || C == 512)) {
-    if (C == 128) attn_pool_bwd1_kernel<1><<<B, 256, 0, stream>>>(a, gate, dpooled, HW, w, da, dw, db0);
-    else if (C == 256) attn_pool_bwd1_kernel<2><<<B, 256, 0, stream>>>(a, gate, dpooled, HW, w, da, dw, db0);
-    else attn_pool_bwd1_kernel<4><<<B, 256, 0, stream>>>(a, gate, dpooled, HW, w, da, dw, db0);
+    const dim3 grid((unsigned)B, (unsigned)pc_attn_pool_splits(B));      // blocks of one sample take disjoint pixels; dw / db0 are atomics already
+    if (C == 128) attn_pool_bwd1_kernel<1><<<grid, 256, 0, stream>>>(a, gate, dpooled, HW, w, da, dw, db0);
+    else if (C == 256) attn_pool_bwd1_kernel<2><<<grid, 256, 0, stream>>>(a, gate, dpooled, HW, w, da, dw, db0);
+    else attn_pool_bwd1_kernel<4><<<grid, 256, 0, stream>>>(a, gate, dpooled, HW, w, da, dw, db0);
     PC_LAUNCH_CHECK("attn_pool_bwd1_kernel");
     return PC_OK;
   }

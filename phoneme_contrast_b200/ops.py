@@ -502,11 +502,23 @@ def bn_add_relu_bwd(dout, out, y2, co2: BnCoeffs, ysc, co_s: BnCoeffs | None, gr
     return (dy2_ps if planes else dy2), (dsc_ps if ps_sc else dsc), g2, gs
 
 
+_attn_ws: dict = {}
+
+
 def attn_pool_fwd(a, w=None, b0=None):
     B, H, W, C_ = a.shape
     gate = torch.empty(B, H * W, device=a.device, dtype=F32)
     pooled = torch.empty(B, C_, device=a.device, dtype=F32)
-    call("pc_attn_pool_fwd", ptr(a), B, H * W, C_, ptr(w), ptr(b0), ptr(gate), ptr(pooled), stream())
+    S = int(L.lib().pc_attn_pool_splits(B))
+    if S > 1:
+        # few samples: S blocks share a sample's pixels; persistent scratch + zeroed arrival counters (the kernel leaves them zero)
+        key = (a.device, B, S, C_)
+        ws = _attn_ws.get(key)
+        if ws is None:
+            ws = _attn_ws[key] = (torch.empty(B * S * C_, device=a.device, dtype=F32), torch.zeros(B, device=a.device, dtype=torch.int32))
+        call("pc_attn_pool_fwd_ws", ptr(a), B, H * W, C_, ptr(w), ptr(b0), ptr(gate), ptr(pooled), ptr(ws[0]), ptr(ws[1], torch.int32), stream())
+    else:
+        call("pc_attn_pool_fwd", ptr(a), B, H * W, C_, ptr(w), ptr(b0), ptr(gate), ptr(pooled), stream())
     return pooled, gate
 
 
