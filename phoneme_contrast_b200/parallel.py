@@ -1,16 +1,21 @@
 """Sharded data parallelism for the hot path (new work: the reference is single-process).
 
-One process per GPU (torchrun), torch.distributed over NCCL/NVLink for plumbing. Per step there are exactly
-three exchanges, all latency-bound at these sizes (the COUNT of collectives is what costs):
+One process per GPU (torchrun), torch.distributed for plumbing. Per step there are exactly three exchanges, all latency-bound at
+these sizes (the COUNT of exchanges is what costs):
 
-  C1  ONE all_gather of [n, D+2] rows = the local embeddings with the label bits packed behind them -> every rank sees
-      global negatives; rank r then computes ONLY its rows [r*n,(r+1)*n) x all N columns of the SupCon problem (1/R of the work);
-  C1' all_gather of the per-row statistics [n,4] -> the backward needs (max, den, n_pos) of REMOTE rows to form
-      G_ji, which lets each rank produce dL/dF_local exactly with no gradient reduce-scatter; the same statistics give every
-      rank the global loss value, so there is no all-reduce of the loss;
-  C2  all-reduce(SUM) of the flat gradient bucket (the graphed step splits it in two so that the large late-layer part
-      overlaps the rest of the backward). SUM, not mean: every rank back-propagates the GLOBAL loss
-      through its own samples only, so the per-rank parameter gradients are disjoint partial sums.
+  C1  ONE gather of the local embeddings with their labels -> every rank sees global negatives; rank r then computes ONLY its rows
+      [r*n,(r+1)*n) x all N columns of the SupCon problem (1/R of the work);
+  C1' gather of the per-row statistics [n,4] -> the backward needs (max, den, n_pos) of REMOTE rows to form G_ji, which lets each
+      rank produce dL/dF_local exactly with no gradient reduce-scatter; the same statistics give every rank the global loss value,
+      so there is no all-reduce of the loss;
+  C2  all-reduce(SUM) of the flat gradient bucket (the graphed steps split it so that the large late-layer parts overlap the rest
+      of the backward). SUM, not mean: every rank back-propagates the GLOBAL loss through its own samples only, so the per-rank
+      parameter gradients are disjoint partial sums.
+
+Two transports. The graphed steps (training/graph.py:GraphedDPStepPeer, GraphedShardedLoss) run the exchanges as this library's own
+kernels over NVLink peer memory (peer.py, csrc/peer.cu: IPC-mapped regions, flag barriers), so that a whole step is ONE CUDA graph with
+no NCCL call on it. The eager path below -- and the fallback when the regions cannot be mapped -- uses NCCL: one all_gather of packed
+[n, D+2] rows (label bits in the last two columns), one of the statistics, one all-reduce.
 
 BatchNorm uses per-rank batch statistics (the torch-DDP convention); see DESIGN.md "BatchNorm under DP".
 The local row-block compute is pluggable (`backend`) so that the exchange logic is testable on CPU with gloo;
