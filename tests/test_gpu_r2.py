@@ -502,3 +502,34 @@ def test_attn_pool_single_pass_vs_torch(shape, attention):
         torch.testing.assert_close(gate, gr.detach().reshape(B, H * W), **tol)
         torch.testing.assert_close(dw, wr.grad, rtol=1e-4, atol=1e-4)
         torch.testing.assert_close(db0, br.grad, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_run_batches_delivers_every_loss_in_order(graph):
+    """ContrastiveTrainer.run_batches (the epoch loop of reference trainer.py:138-160): host batches are prefetched one ahead, the loss is
+    accumulated on the device, and the on_loss callback receives EVERY step's loss, in order, one step behind -- the same values a loop
+    that reads loss.item() after each step (as the reference does) sees."""
+    from phoneme_contrast_b200.models import model_registry
+    from phoneme_contrast_b200.training import ContrastiveTrainer, FusedClipAdam, get_loss_fn
+    cfg = {"dropout_rate": 0.0, "precision": "fp32"}
+    sd = nets_oracle.synthetic_state_dict("phoneme_cnn", cfg, seed=9)
+    rs = np.random.RandomState(12)
+    batches = [{"views": torch.from_numpy(rs.standard_normal((16, 2, 1, 40, 64)).astype(np.float32)).pin_memory(),
+                "label": torch.from_numpy((np.arange(16) // 2).astype(np.int64)).pin_memory()} for _ in range(5)]
+    got = {}
+    for mode in ("item", "pipelined"):
+        m = model_registry.create("phoneme_cnn", cfg).to(DEV)
+        m.load_state_dict(sd)
+        opt = FusedClipAdam(m.parameters(), lr=1e-3, weight_decay=1e-4)
+        tr = ContrastiveTrainer(m, [], None, get_loss_fn("supervised_contrastive", temperature=0.15), opt, None, torch.device(DEV),
+                                {"gradient_clip_val": 1.0, "cuda_graph": graph, "progress": False}, tempfile.mkdtemp(), logging.getLogger("t"))
+        m.train()
+        if mode == "item":
+            got[mode] = [float(tr.step(*tr._prepare_batch(b)).item()) for b in batches]
+        else:
+            seen = []
+            total, n = tr.run_batches(iter(batches), on_loss=lambda i, v: seen.append((i, v)))
+            assert n == len(batches) and [i for i, _ in seen] == list(range(len(batches))) and tr.global_step == len(batches)
+            got[mode] = [v for _, v in seen]
+            assert abs(float(total) - sum(got[mode])) <= 1e-4 * abs(sum(got[mode]))
+    np.testing.assert_allclose(got["pipelined"], got["item"], rtol=2e-5)
