@@ -333,6 +333,9 @@ int pc_bn_act_split_fin(const float* y, int64_t n_pix, int C, int hw, const PcBn
                         void* planes, pc_stream_t stream);
 int pc_bn_add_relu_fwd_fin(const float* y2, const PcBnFinalize* fin2, const float* ysc, const PcBnFinalize* fin_s, int64_t n_pix,
                            int C, float* out, void* planes, pc_stream_t stream);
+/* pc_bn_act_fwd (BatchNorm + ReLU + pool + dropout, optional planes) with the coefficients finalised inside the kernel. */
+int pc_bn_act_fwd_fin(const float* y, int B, int H, int W, int C, const PcBnFinalize* fin, const float* drop, int pool, float* out,
+                      uint8_t* argmax, void* planes, pc_stream_t stream);
 
 /* Residual tail: out = relu(bn2(y2) + (sc_scale ? bn_s(ysc) : ysc))   (phoneme_cnn.py:177-182). */
 int pc_bn_add_relu_fwd(const float* y2, const float* scale2, const float* shift2, const float* ysc,

@@ -108,6 +108,7 @@ SIGNATURES = {
     "pc_bn_act_split": (i32, [vp, i64, i32, i32, vp, vp, vp, i32, vp, vp]),
     "pc_f16_overflow_query": (i32, [i32, C.POINTER(C.c_int), vp]),
     "pc_bn_act_split_fin": (i32, [vp, i64, i32, i32, C.POINTER(PcBnFinalize), vp, i32, vp, vp]),
+    "pc_bn_act_fwd_fin": (i32, [vp, i32, i32, i32, i32, C.POINTER(PcBnFinalize), vp, i32, vp, vp, vp, vp]),
     "pc_bn_add_relu_fwd_fin": (i32, [vp, C.POINTER(PcBnFinalize), vp, C.POINTER(PcBnFinalize), i64, i32, vp, vp, vp]),
     "pc_bn_act_bwd_apply": (i32, [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pc_bn_add_relu_fwd": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, vp, vp, vp]),

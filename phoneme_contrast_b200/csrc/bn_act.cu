@@ -115,9 +115,14 @@ template <int POOL>
 __global__ void __launch_bounds__(256)
 bn_act_fwd_kernel(const float* __restrict__ y, int B, int H, int W, int C, int Ho, int Wo, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ drop, float* __restrict__ out,
-                  uint8_t* __restrict__ argmax, unsigned char* __restrict__ planes) {
+                  uint8_t* __restrict__ argmax, unsigned char* __restrict__ planes, const PcBnFinalize fin) {
   pdl_trigger();
   pdl_wait();
+  extern __shared__ __align__(16) float s_fin_fwd[];    // [2][C] when the coefficients are finalised here (pc_bn_act_fwd_fin)
+  if (fin.stats != nullptr) {
+    bn_finalize_in_block(fin, C, s_fin_fwd, s_fin_fwd + C);
+    scale = s_fin_fwd; shift = s_fin_fwd + C;
+  }
   const int C4 = C >> 2;
   const long long total = (long long)B * Ho * Wo * C4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
@@ -876,22 +881,38 @@ extern "C" int pc_bn_finalize(const double* stats, int C, double count, const fl
 #define PC_CHECK_C4(fn, C) \
   PC_REQUIRE((C) > 0 && (C) % 4 == 0 && (C) <= 1024 && 256 % ((C) / 4) == 0, PC_EUNSUPPORTED, fn ": channels=%d must be 4*2^k <= 1024", (C))
 
-extern "C" int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const float* scale, const float* shift,
-                             const float* drop, int pool, float* out, uint8_t* argmax, void* planes, pc_stream_t stream) {
-  PC_REQUIRE(y && scale && shift && out && B > 0 && H > 0 && W > 0, PC_EINVAL, "pc_bn_act_fwd: bad arguments");
+static int bn_act_fwd_impl(const float* y, int B, int H, int W, int C, const float* scale, const float* shift, const PcBnFinalize* fin,
+                           const float* drop, int pool, float* out, uint8_t* argmax, void* planes, pc_stream_t stream) {
   PC_CHECK_C4("pc_bn_act_fwd", C);
   PC_REQUIRE(pool == 0 || pool == 2 || pool == 3, PC_EINVAL, "pc_bn_act_fwd: pool must be 0, 2 or 3");
   int Ho, Wo;
   pool_out_dims(H, W, pool, &Ho, &Wo);
   PC_REQUIRE(Ho > 0 && Wo > 0, PC_EINVAL, "pc_bn_act_fwd: input %dx%d too small for pooling", H, W);
   const long long total = (long long)B * Ho * Wo * (C / 4);
-  const int grid = pool == 0 ? ew_grid_waves(bn_act_fwd_kernel<0>, 0, total, 256)
-                             : (pool == 2 ? ew_grid_waves(bn_act_fwd_kernel<2>, 0, total, 256) : ew_grid_waves(bn_act_fwd_kernel<3>, 0, total, 256));
-  if (pool == 0) launch_pdl((bn_act_fwd_kernel<0>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes));
-  else if (pool == 2) launch_pdl((bn_act_fwd_kernel<2>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes));
-  else launch_pdl((bn_act_fwd_kernel<3>), dim3(grid), dim3(256), 0, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes));
+  PcBnFinalize f{};
+  size_t smem = 0;
+  if (fin != nullptr) { f = *fin; smem = sizeof(float) * 2 * (size_t)C; }
+  const int grid = pool == 0 ? ew_grid_waves(bn_act_fwd_kernel<0>, smem, total, 256)
+                             : (pool == 2 ? ew_grid_waves(bn_act_fwd_kernel<2>, smem, total, 256) : ew_grid_waves(bn_act_fwd_kernel<3>, smem, total, 256));
+  if (pool == 0) launch_pdl((bn_act_fwd_kernel<0>), dim3(grid), dim3(256), smem, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes), f);
+  else if (pool == 2) launch_pdl((bn_act_fwd_kernel<2>), dim3(grid), dim3(256), smem, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes), f);
+  else launch_pdl((bn_act_fwd_kernel<3>), dim3(grid), dim3(256), smem, stream, y, B, H, W, C, Ho, Wo, scale, shift, drop, out, argmax, static_cast<unsigned char*>(planes), f);
   PC_LAUNCH_CHECK("bn_act_fwd_kernel");
   return PC_OK;
+}
+
+extern "C" int pc_bn_act_fwd(const float* y, int B, int H, int W, int C, const float* scale, const float* shift,
+                             const float* drop, int pool, float* out, uint8_t* argmax, void* planes, pc_stream_t stream) {
+  PC_REQUIRE(y && scale && shift && out && B > 0 && H > 0 && W > 0, PC_EINVAL, "pc_bn_act_fwd: bad arguments");
+  return bn_act_fwd_impl(y, B, H, W, C, scale, shift, nullptr, drop, pool, out, argmax, planes, stream);
+}
+
+// pc_bn_act_fwd with the train-mode BatchNorm coefficients finalised inside the kernel (PcBnFinalize): one dependent launch less
+extern "C" int pc_bn_act_fwd_fin(const float* y, int B, int H, int W, int C, const PcBnFinalize* fin, const float* drop, int pool, float* out,
+                                 uint8_t* argmax, void* planes, pc_stream_t stream) {
+  PC_REQUIRE(y && fin && fin->stats && fin->scale && fin->shift && out && B > 0 && H > 0 && W > 0 && fin->count > 0, PC_EINVAL, "pc_bn_act_fwd_fin: bad arguments");
+  PC_REQUIRE(C <= 4096, PC_EUNSUPPORTED, "pc_bn_act_fwd_fin: too many channels for the in-block finalisation");
+  return bn_act_fwd_impl(y, B, H, W, C, nullptr, nullptr, fin, drop, pool, out, argmax, planes, stream);
 }
 
 extern "C" int pc_bn_act_bwd_reduce(const float* dout, const float* y, int B, int H, int W, int C, const float* scale,

@@ -297,17 +297,21 @@ def _small_forward(net, x, training):
         else:
             yB = ops.conv_fwd(yA, cwB.wf, convB.bias, gB, dict(scale=coA.scale, shift=coA.shift, relu=True), stB, cwB.prec_f)
         _sync_stats(sb, stB)
-        coB = ops.bn_finalize(stB, cm * B * h * w, bnB, training)
-        _local_only(sb, coA, coB)
         pool = 2 if b < 2 else 0
         next_ps = use_planes and b < 2 and co % cmin == 0    # the next block's first convolution gathers co channels
         if next_ps and co % 64 != 0:
             hn, wn = ops.pool_dims(h, w, pool)
             next_ps = _halo_everything(ops.conv_geom(B, hn, wn, co, chans[b + 1], 3, 1, 1))
-        if next_ps:
-            out, _, out_ps = ops.bn_act_fwd(yB, coB, pool, s.drop[b], want_planes=True)
+        if training and os.environ.get("PC_BN_FIN_FUSE", "1") == "1":      # bnB finalised inside the kernel that applies it
+            res, coB = ops.bn_act_fwd_fin(yB, stB, cm * B * h * w, bnB, pool, s.drop[b], want_planes=next_ps)
         else:
-            (out, _), out_ps = ops.bn_act_fwd(yB, coB, pool, s.drop[b]), None
+            coB = ops.bn_finalize(stB, cm * B * h * w, bnB, training)
+            res = ops.bn_act_fwd(yB, coB, pool, s.drop[b], want_planes=next_ps)
+        _local_only(sb, coA, coB)
+        if next_ps:
+            out, _, out_ps = res
+        else:
+            (out, _), out_ps = res, None
         s.layers.append(dict(xin=cur, xin_ps=cur_ps if psA else None, aA=aA, gA=gA, gB=gB, yA=yA, yB=yB, coA=coA, coB=coB, cwA=cwA, cwB=cwB,
                              pool=pool))
         cur, cin, cur_ps = out, co, out_ps

@@ -380,6 +380,20 @@ def bn_act_fwd(y, co: BnCoeffs, pool=0, drop=None, want_planes=False):
     return (out, argmax, planes) if want_planes else (out, argmax)
 
 
+def bn_act_fwd_fin(y, stats, count, bn, pool=0, drop=None, want_planes=False):
+    """bn_finalize (train mode) + bn_act_fwd in ONE launch -> ((out, argmax[, planes]), coefficients)."""
+    B, H, W, C_ = y.shape
+    Ho, Wo = pool_dims(H, W, pool)
+    co = _new_coeffs(stats, bn)
+    fin = _bn_fin(stats, count, bn, co)
+    out = torch.empty(B, Ho, Wo, C_, device=y.device, dtype=F32)
+    argmax = torch.empty(B, Ho, Wo, C_, device=y.device, dtype=torch.uint8) if pool == 3 else None
+    planes = torch.empty(2, out.numel() * 2, device=y.device, dtype=torch.uint8) if want_planes else None
+    call("pc_bn_act_fwd_fin", ptr(y), B, H, W, C_, C.byref(fin), ptr(drop), pool, ptr(out), ptr(argmax, torch.uint8), ptr(planes, torch.uint8),
+         stream())
+    return ((out, argmax, planes) if want_planes else (out, argmax)), co
+
+
 def bn_act_bwd(dout, y, co: BnCoeffs, pool=0, drop=None, argmax=None, dgamma=None, dbeta=None, amax=None, planes=False, zp=None,
                db_conv=None, sync=None, reduced=None):
     """Gradient w.r.t. the pre-BatchNorm tensor y of out = drop * pool(relu(bn(y))) (train-mode statistics).
