@@ -170,6 +170,7 @@ extern "C" int pc_peer_export(const void* ptr, unsigned char* handle64, size_t* 
   PC_REQUIRE(cr == CUDA_SUCCESS, PC_ECUDA, "pc_peer_export: cuMemGetAddressRange failed (CUresult %d)", (int)cr);
   cudaIpcMemHandle_t h;
   const cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));
+  if (e != cudaSuccess) (void)cudaGetLastError();      // do not leave the error for the next launch check: the caller falls back to NCCL
   PC_REQUIRE(e == cudaSuccess, PC_ECUDA,
              "pc_peer_export: cudaIpcGetMemHandle failed (%s); the region must come from cudaMalloc (PyTorch's default caching allocator, not "
              "expandable_segments)", cudaGetErrorString(e));
@@ -183,6 +184,7 @@ extern "C" int pc_peer_open(const unsigned char* handle64, void** base) {
   cudaIpcMemHandle_t h;
   memcpy(&h, handle64, 64);
   const cudaError_t e = cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) (void)cudaGetLastError();
   PC_REQUIRE(e == cudaSuccess, PC_ECUDA, "pc_peer_open: cudaIpcOpenMemHandle failed (%s)", cudaGetErrorString(e));
   return PC_OK;
 }
