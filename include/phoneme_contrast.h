@@ -447,6 +447,9 @@ int pc_peer_flag_bytes(void);
 int pc_peer_max_ranks(void);
 /* IPC handle (64 bytes) of the cudaMalloc block containing ptr, and ptr's byte offset inside it. */
 int pc_peer_export(const void* ptr, unsigned char* handle64, size_t* offset);
+/* A zero-filled cudaMalloc block of the library's own, for callers whose allocator's memory cannot be exported (virtual-memory backed). */
+int pc_peer_alloc(size_t bytes, void** ptr);
+int pc_peer_free(void* ptr);
 /* Map a peer's block into this process (peer access enabled lazily); *base = address of the block's first byte. */
 int pc_peer_open(const unsigned char* handle64, void** base);
 int pc_peer_close(void* base);

@@ -130,6 +130,8 @@ SIGNATURES = {
     "pc_peer_max_ranks": (i32, []),
     "pc_peer_export": (i32, [vp, vp, C.POINTER(sz)]),
     "pc_peer_open": (i32, [vp, C.POINTER(vp)]),
+    "pc_peer_alloc": (i32, [sz, C.POINTER(vp)]),
+    "pc_peer_free": (i32, [vp]),
     "pc_peer_close": (i32, [vp]),
     "pc_peer_barrier": (i32, [vp, i32, i32, sz, i32, i32, vp]),
     "pc_peer_error": (i32, [vp, i32, i32, sz, i32, C.POINTER(C.c_int), vp]),

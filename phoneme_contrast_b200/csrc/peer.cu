@@ -267,3 +267,19 @@ extern "C" int pc_peer_sum_slots(const double* slots, int R, int n, double scale
   PC_LAUNCH_CHECK("peer::sum_slots_kernel");
   return PC_OK;
 }
+
+// A region of the library's own (cudaMalloc, zero-filled): used when the caller's allocator hands out memory that cannot be exported
+// over CUDA IPC (PyTorch's expandable segments are virtual-memory mappings, not cudaMalloc blocks).
+extern "C" int pc_peer_alloc(size_t bytes, void** ptr) {
+  PC_REQUIRE(ptr && bytes > 0, PC_EINVAL, "pc_peer_alloc: bad arguments");
+  PC_CUDA(cudaMalloc(ptr, bytes));
+  PC_CUDA(cudaMemset(*ptr, 0, bytes));
+  PC_CUDA(cudaDeviceSynchronize());
+  return PC_OK;
+}
+
+extern "C" int pc_peer_free(void* ptr) {
+  PC_REQUIRE(ptr, PC_EINVAL, "pc_peer_free: null pointer");
+  PC_CUDA(cudaFree(ptr));
+  return PC_OK;
+}

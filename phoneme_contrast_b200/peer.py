@@ -21,6 +21,22 @@ from . import _lib as L
 _MAPPED: dict = {}
 
 
+class _OwnBlock:
+    """A cudaMalloc block of the library's own, visible to torch through __cuda_array_interface__ (zero-copy uint8 view)."""
+
+    def __init__(self, nbytes: int):
+        base = C.c_void_p()
+        L.check(L.lib().pc_peer_alloc(nbytes, C.byref(base)))
+        self.ptr, self.nbytes = int(base.value), int(nbytes)
+        self.__cuda_array_interface__ = {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2, "strides": None}
+
+    def __del__(self):
+        try:
+            L.lib().pc_peer_free(C.c_void_p(self.ptr))
+        except Exception:      # noqa: BLE001 -- interpreter shutdown
+            pass
+
+
 def _align(x: int, a: int = 256) -> int:
     return (x + a - 1) // a * a
 
@@ -57,13 +73,21 @@ class PeerRegion:
             # export; a rank that cannot (allocator without cudaMalloc blocks, IPC forbidden in the container) says so to everyone, so
             # that all ranks raise together and the caller falls back to the NCCL exchanges on every rank alike
             mine = None
+            handle = (C.c_ubyte * 64)()
+            offset = C.c_size_t(0)
             try:
-                handle = (C.c_ubyte * 64)()
-                offset = C.c_size_t(0)
                 L.check(lib.pc_peer_export(C.c_void_p(self.buf.data_ptr()), handle, C.byref(offset)))
                 mine = (bytes(handle), int(offset.value))
             except Exception as exc:      # noqa: BLE001
-                mine = ("error", str(exc))
+                # torch's allocator handed out memory that CUDA IPC cannot export (expandable segments): take a cudaMalloc block of the
+                # library's own instead and view it as a tensor
+                try:
+                    self._own = _OwnBlock(self.nbytes)
+                    self.buf = torch.as_tensor(self._own, device=device)
+                    L.check(lib.pc_peer_export(C.c_void_p(self.buf.data_ptr()), handle, C.byref(offset)))
+                    mine = (bytes(handle), int(offset.value))
+                except Exception as exc2:      # noqa: BLE001
+                    mine = ("error", f"{exc}; own block: {exc2}")
             everyone = [None] * self.world_size
             dist.all_gather_object(everyone, mine, group=group)
             bad = [f"rank {r}: {e[1]}" for r, e in enumerate(everyone) if e[0] == "error"]
